@@ -1,0 +1,340 @@
+"""ctypes binding of the C ABI (include/dmk.h).  This is harness code: tests and bench.py drive the library
+through exactly the entry points a darmok maintainer would bind.
+
+There is no fallback of any kind here: if libdarmok_b200.so is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdarmok_b200.so")
+
+OK, ERR_INVALID, ERR_FORMAT, ERR_CUDA, ERR_UNSUPPORTED, ERR_JOB = range(6)
+STEP_ADVANCE, STEP_POSE, STEP_CULL, STEP_SKIN, STEP_SKIN_VISIBLE_ONLY = 1, 2, 4, 8, 16
+STEP_ALL = 15
+OUT_MODELS, OUT_LOCALS, OUT_KEY_INDICES = 1, 2, 4
+
+# every symbol include/dmk.h declares: (name, restype, argtypes)
+_vp, _i, _i64, _f, _u32, _sz, _cp = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32, C.c_size_t, C.c_char_p
+SIGNATURES = [
+    ("dmk_context_create", _i, [_i, _vp, C.POINTER(_vp)]),
+    ("dmk_context_destroy", None, [_vp]),
+    ("dmk_last_error", _cp, [_vp]),
+    ("dmk_sync", _i, [_vp]),
+    ("dmk_context_stream", _vp, [_vp]),
+    ("dmk_version", _cp, []),
+    ("dmk_context_launch_count", C.c_uint64, [_vp]),
+    ("dmk_skeleton_load_ozz", _i, [_vp, _vp, _sz, C.POINTER(_vp)]),
+    ("dmk_skeleton_destroy", None, [_vp]),
+    ("dmk_skeleton_num_joints", _i, [_vp]),
+    ("dmk_skeleton_joint_name", _cp, [_vp, _i]),
+    ("dmk_skeleton_joint_parent", _i, [_vp, _i]),
+    ("dmk_skeleton_find_joint", _i, [_vp, _cp]),
+    ("dmk_clip_load_ozz", _i, [_vp, _vp, _sz, C.POINTER(_vp)]),
+    ("dmk_clip_destroy", None, [_vp]),
+    ("dmk_clip_duration", _f, [_vp]),
+    ("dmk_clip_name", _cp, [_vp]),
+    ("dmk_clip_num_tracks", _i, [_vp]),
+    ("dmk_clipset_create", _i, [_vp, _vp, C.POINTER(_vp), _i, C.POINTER(_vp)]),
+    ("dmk_clipset_destroy", None, [_vp]),
+    ("dmk_armature_create", _i, [_vp, _vp, C.POINTER(_cp), _vp, _i, C.POINTER(_vp)]),
+    ("dmk_armature_destroy", None, [_vp]),
+    ("dmk_armature_palette_size", _i, [_vp]),
+    ("dmk_mesh_create", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
+    ("dmk_mesh_destroy", None, [_vp]),
+    ("dmk_mesh_num_vertices", _i, [_vp]),
+    ("dmk_mesh_vertex_pitch", _i, [_vp]),
+    ("dmk_crowd_create", _i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, C.POINTER(_vp)]),
+    ("dmk_crowd_destroy", None, [_vp]),
+    ("dmk_crowd_size", _i64, [_vp]),
+    ("dmk_crowd_enable_outputs", _i, [_vp, _u32]),
+    ("dmk_crowd_set_layers", _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f]),
+    ("dmk_crowd_update_layers", _i, [_vp, _i, _vp, _vp, _vp]),
+    ("dmk_crowd_set_instances", _i, [_vp, _vp, _vp]),
+    ("dmk_crowd_set_camera", _i, [_vp, _vp, _f]),
+    ("dmk_crowd_set_frustum_corners", _i, [_vp, _vp]),
+    ("dmk_crowd_step", _i, [_vp, _f, _u32]),
+    ("dmk_crowd_palette_dev", _vp, [_vp]),
+    ("dmk_crowd_skinned_dev", _vp, [_vp]),
+    ("dmk_crowd_visibility_dev", _vp, [_vp]),
+    ("dmk_crowd_visible_ids_dev", _vp, [_vp]),
+    ("dmk_crowd_visible_count_dev", _vp, [_vp]),
+    ("dmk_crowd_get_palette", _i, [_vp, _i64, _i64, _vp]),
+    ("dmk_crowd_get_models", _i, [_vp, _i64, _i64, _vp]),
+    ("dmk_crowd_get_locals", _i, [_vp, _i64, _i64, _vp]),
+    ("dmk_crowd_get_key_indices", _i, [_vp, _i64, _i64, _vp]),
+    ("dmk_crowd_get_skinned", _i, [_vp, _i64, _i64, _vp]),
+    ("dmk_crowd_get_visibility", _i, [_vp, _vp, C.POINTER(_i64)]),
+    ("dmk_crowd_get_ratios", _i, [_vp, _vp, _vp]),
+    ("dmk_crowd_pack_visible_palettes", _i, [_vp, _vp, _i64]),
+    ("dmk_cull_dev", _i, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    ("dmk_cull_host", _i, [_vp, _vp, _f, _vp, _vp, _i64, _vp]),
+    ("dmk_frustum_corners", _i, [_vp, _f, _vp]),
+]
+
+_LIB = None
+
+
+class DmkError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"dmk status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+def lib():
+    """Loads the in-tree shared library.  Raises loudly if it has not been built (python -m darmok_b200.build)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -m darmok_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SIGNATURES:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _LIB = L
+    return _LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        st = lib().dmk_context_create(device, stream, C.byref(h))
+        if st:
+            raise DmkError(st, lib().dmk_last_error(None).decode())
+        self.h = h
+
+    def check(self, st):
+        if st:
+            raise DmkError(st, lib().dmk_last_error(self.h).decode())
+
+    def sync(self):
+        self.check(lib().dmk_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return lib().dmk_context_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().dmk_context_destroy(self.h)
+            self.h = None
+
+    def frustum_corners(self, view_proj, near_depth=0.0):
+        vp = _f32(view_proj)
+        out = np.zeros((8, 3), np.float32)
+        self.check(lib().dmk_frustum_corners(_ptr(vp), near_depth, _ptr(out)))
+        return out
+
+    def cull_host(self, view_proj, near_depth, world_inverse, bbox):
+        vp, wi, bb = _f32(view_proj), _f32(world_inverse), _f32(bbox)
+        n = wi.shape[0]
+        bits = np.zeros((n + 31) // 32, np.uint32)
+        self.check(lib().dmk_cull_host(self.h, _ptr(vp), near_depth, _ptr(wi), _ptr(bb), n, _ptr(bits)))
+        return bits
+
+    def cull_dev(self, corners, world_inverse_ptr, bbox_ptr, n, vis_bits_ptr):
+        c = _f32(corners)
+        self.check(lib().dmk_cull_dev(self.h, _ptr(c), world_inverse_ptr, bbox_ptr, n, vis_bits_ptr))
+
+
+class Skeleton:
+    def __init__(self, ctx: Context, data: bytes):
+        self.ctx = ctx
+        h = C.c_void_p()
+        buf = (C.c_char * len(data)).from_buffer_copy(data) if data else None
+        ctx.check(lib().dmk_skeleton_load_ozz(ctx.h, buf, len(data), C.byref(h)))
+        self.h = h
+        self.num_joints = lib().dmk_skeleton_num_joints(h)
+        self.num_soa = (self.num_joints + 3) // 4
+
+    def joint_name(self, i):
+        return lib().dmk_skeleton_joint_name(self.h, i).decode()
+
+    def joint_parent(self, i):
+        return lib().dmk_skeleton_joint_parent(self.h, i)
+
+    def find_joint(self, name: str):
+        return lib().dmk_skeleton_find_joint(self.h, name.encode())
+
+    def close(self):
+        if self.h:
+            lib().dmk_skeleton_destroy(self.h)
+            self.h = None
+
+
+class Clip:
+    def __init__(self, ctx: Context, data: bytes):
+        self.ctx = ctx
+        h = C.c_void_p()
+        buf = (C.c_char * len(data)).from_buffer_copy(data) if data else None
+        ctx.check(lib().dmk_clip_load_ozz(ctx.h, buf, len(data), C.byref(h)))
+        self.h = h
+        self.duration = lib().dmk_clip_duration(h)
+        self.name = lib().dmk_clip_name(h).decode()
+        self.num_tracks = lib().dmk_clip_num_tracks(h)
+
+    def close(self):
+        if self.h:
+            lib().dmk_clip_destroy(self.h)
+            self.h = None
+
+
+class ClipSet:
+    def __init__(self, ctx: Context, skel: Skeleton, clips):
+        self.ctx, self.clips = ctx, list(clips)
+        arr = (C.c_void_p * len(self.clips))(*[c.h for c in self.clips])
+        h = C.c_void_p()
+        ctx.check(lib().dmk_clipset_create(ctx.h, skel.h, arr, len(self.clips), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().dmk_clipset_destroy(self.h)
+            self.h = None
+
+
+class Armature:
+    def __init__(self, ctx: Context, skel: Skeleton, names, inv_bind):
+        self.ctx = ctx
+        ib = _f32(inv_bind)
+        k = len(names)
+        arr = (C.c_char_p * max(k, 1))(*[n.encode() for n in names])
+        h = C.c_void_p()
+        ctx.check(lib().dmk_armature_create(ctx.h, skel.h, arr, _ptr(ib), k, C.byref(h)))
+        self.h = h
+        self.palette_size = lib().dmk_armature_palette_size(h)
+
+    def close(self):
+        if self.h:
+            lib().dmk_armature_destroy(self.h)
+            self.h = None
+
+
+class Mesh:
+    def __init__(self, ctx: Context, pos, nrm, tan, indices, weights, palette_size):
+        self.ctx = ctx
+        pos, nrm, tan, indices, weights = (_f32(a) for a in (pos, nrm, tan, indices, weights))
+        h = C.c_void_p()
+        ctx.check(lib().dmk_mesh_create(ctx.h, _ptr(pos), _ptr(nrm), _ptr(tan), _ptr(indices), _ptr(weights), pos.shape[0],
+                                        palette_size, C.byref(h)))
+        self.h = h
+        self.num_vertices = lib().dmk_mesh_num_vertices(h)
+        self.vertex_pitch = lib().dmk_mesh_vertex_pitch(h)
+
+    def close(self):
+        if self.h:
+            lib().dmk_mesh_destroy(self.h)
+            self.h = None
+
+
+class Crowd:
+    def __init__(self, ctx: Context, skel: Skeleton, clips: ClipSet, arm: Armature | None, mesh: Mesh | None, n, max_layers):
+        self.ctx, self.skel, self.clips, self.arm, self.mesh = ctx, skel, clips, arm, mesh
+        self.n, self.max_layers, self.num_layers = n, max_layers, 0
+        h = C.c_void_p()
+        ctx.check(lib().dmk_crowd_create(ctx.h, skel.h, clips.h, arm.h if arm else None, mesh.h if mesh else None, n, max_layers,
+                                         C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().dmk_crowd_destroy(self.h)
+            self.h = None
+
+    def enable_outputs(self, flags):
+        self.ctx.check(lib().dmk_crowd_enable_outputs(self.h, flags))
+
+    def set_layers(self, clip, ratio, weight, speed=None, loop=None, threshold=1.17549435e-38):
+        clip = np.ascontiguousarray(clip, np.int32)
+        ratio, weight, speed = _f32(ratio), _f32(weight), _f32(speed)
+        loop = None if loop is None else np.ascontiguousarray(loop, np.uint8)
+        self.num_layers = clip.shape[0]
+        self.ctx.check(lib().dmk_crowd_set_layers(self.h, self.num_layers, _ptr(clip), _ptr(ratio), _ptr(weight), _ptr(speed),
+                                                  _ptr(loop), threshold))
+
+    def update_layers(self, clip, ratio, weight):
+        self.ctx.check(lib().dmk_crowd_update_layers(self.h, self.num_layers, _ptr(clip), _ptr(ratio), _ptr(weight)))
+
+    def set_instances(self, world_inverse, bbox):
+        wi, bb = _f32(world_inverse), _f32(bbox)
+        self.ctx.check(lib().dmk_crowd_set_instances(self.h, _ptr(wi), _ptr(bb)))
+
+    def set_camera(self, view_proj, near_depth=0.0):
+        vp = _f32(view_proj)
+        self.ctx.check(lib().dmk_crowd_set_camera(self.h, _ptr(vp), near_depth))
+
+    def step(self, dt, flags):
+        self.ctx.check(lib().dmk_crowd_step(self.h, dt, flags))
+
+    def _get(self, fn, shape, dtype, first, count):
+        out = np.zeros((count,) + shape, dtype)
+        self.ctx.check(fn(self.h, first, count, _ptr(out)))
+        return out
+
+    def get_palette(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        return self._get(lib().dmk_crowd_get_palette, (self.arm.palette_size, 16), np.float32, first, count)
+
+    def get_models(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        return self._get(lib().dmk_crowd_get_models, (self.skel.num_joints, 16), np.float32, first, count)
+
+    def get_locals(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        return self._get(lib().dmk_crowd_get_locals, (self.skel.num_soa, 40), np.float32, first, count)
+
+    def get_key_indices(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        return self._get(lib().dmk_crowd_get_key_indices, (self.num_layers, 3, self.skel.num_soa * 4, 2), np.int32, first, count)
+
+    def get_skinned(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        return self._get(lib().dmk_crowd_get_skinned, (self.mesh.num_vertices, 9), np.float32, first, count)
+
+    def get_visibility(self):
+        bits = np.zeros((self.n + 31) // 32, np.uint32)
+        cnt = C.c_int64()
+        self.ctx.check(lib().dmk_crowd_get_visibility(self.h, _ptr(bits), C.byref(cnt)))
+        return bits, cnt.value
+
+    def get_ratios(self):
+        r = np.zeros((self.num_layers, self.n), np.float32)
+        l = np.zeros((self.num_layers, self.n), np.uint8)
+        self.ctx.check(lib().dmk_crowd_get_ratios(self.h, _ptr(r), _ptr(l)))
+        return r, l
+
+    def pack_visible_palettes(self, out_dev_ptr, capacity):
+        self.ctx.check(lib().dmk_crowd_pack_visible_palettes(self.h, out_dev_ptr, capacity))
+
+    # raw device pointers (ints)
+    def palette_dev(self):
+        return lib().dmk_crowd_palette_dev(self.h)
+
+    def skinned_dev(self):
+        return lib().dmk_crowd_skinned_dev(self.h)
+
+    def visibility_dev(self):
+        return lib().dmk_crowd_visibility_dev(self.h)
+
+    def visible_ids_dev(self):
+        return lib().dmk_crowd_visible_ids_dev(self.h)
+
+    def visible_count_dev(self):
+        return lib().dmk_crowd_visible_count_dev(self.h)
+
+
+def bits_to_bool(bits: np.ndarray, n: int) -> np.ndarray:
+    return np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)

@@ -1,0 +1,892 @@
+// api.cu -- implementation of the C ABI declared in include/dmk.h (host side; the kernels are in *_kernel.cu).
+//
+// No CPU fallback lives here: every compute entry point launches the sm_100a kernels or fails with DMK_ERR_CUDA.
+#include "../../include/dmk.h"
+
+#include "device_types.cuh"
+#include "host_math.hpp"
+#include "kernels.cuh"
+#include "ozz_io.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace dmk;
+
+// ------------------------------------------------------------------------------------------------------------
+// objects behind the opaque handles
+// ------------------------------------------------------------------------------------------------------------
+struct dmk_context_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int num_sms = 0;
+    std::string err;
+    uint64_t launches = 0;
+    // grow-only scratch of the host-buffer cull entry point
+    void* cull_scratch = nullptr;
+    size_t cull_scratch_bytes = 0;
+};
+
+struct dmk_skeleton_s {
+    dmk_context_t ctx;
+    SkeletonData data;
+    int16_t* d_parents = nullptr;
+    uint16_t* d_schedule = nullptr;
+    int rounds = 0;
+};
+
+struct dmk_clip_s {
+    dmk_context_t ctx;
+    AnimationData data;
+};
+
+struct dmk_clipset_s {
+    dmk_context_t ctx;
+    int num_clips = 0;
+    int padded_tracks = 0;
+    std::vector<float> durations;
+    uint2* d_dir = nullptr;
+    float* d_ratio[3] = {nullptr, nullptr, nullptr};
+    uint2* d_value[3] = {nullptr, nullptr, nullptr};
+    int32_t* d_stream[3] = {nullptr, nullptr, nullptr};
+    float* d_duration = nullptr;
+};
+
+struct dmk_armature_s {
+    dmk_context_t ctx;
+    int num_joints = 0;
+    std::vector<int32_t> remap;
+    int32_t* d_remap = nullptr;
+    float* d_inv_bind = nullptr;  // [K][12]
+};
+
+struct dmk_mesh_s {
+    dmk_context_t ctx;
+    int num_vertices = 0;
+    int vpad = 0;
+    int palette_size = 0;
+    float *d_pos = nullptr, *d_nrm = nullptr, *d_tan = nullptr, *d_weights = nullptr;
+    uint32_t* d_slots = nullptr;
+};
+
+struct dmk_crowd_s {
+    dmk_context_t ctx;
+    dmk_skeleton_t skel;
+    dmk_clipset_t clips;
+    dmk_armature_t arm;
+    dmk_mesh_t mesh;
+    int64_t n = 0;
+    int max_layers = 0;
+    int num_layers = 0;
+    float threshold = 0.f;
+    bool layers_set = false, has_loop = false, instances_set = false, camera_set = false;
+    // layer state [max_layers][n]
+    int32_t* d_clip = nullptr;
+    float *d_ratio = nullptr, *d_weight = nullptr, *d_speed = nullptr;
+    uint8_t *d_loop = nullptr, *d_looped = nullptr;
+    // pinned staging for the per-frame host state machine
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    // results
+    float *d_palette = nullptr, *d_palette34 = nullptr, *d_skinned = nullptr;
+    float *d_models = nullptr, *d_locals = nullptr;
+    int32_t* d_key_indices = nullptr;
+    int32_t* d_error = nullptr;
+    int32_t* h_error = nullptr;  // pinned
+    // cull
+    float *d_world_inverse = nullptr, *d_bbox = nullptr;
+    uint32_t* d_vis_bits = nullptr;
+    int32_t *d_visible_ids = nullptr, *d_visible_count = nullptr, *d_scratch = nullptr;
+    float corners[24] = {0};
+    bool culled_once = false;
+    SkinPlan plan{};
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+static dmk_status fail(dmk_context_t ctx, dmk_status code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+static dmk_status cuda_fail(dmk_context_t ctx, cudaError_t e, const char* what) {
+    return fail(ctx, DMK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define DMK_CUDA(ctx, expr)                                        \
+    do {                                                           \
+        cudaError_t e__ = (expr);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #expr); \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+template <typename T>
+static cudaError_t upload(dmk_context_t ctx, T** p, const std::vector<T>& v) {
+    cudaError_t e = dev_alloc(p, v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    e = cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ctx->stream);  // v may be a temporary
+}
+static void dev_free(void* p) {
+    if (p) cudaFree(p);
+}
+static dmk_status bind(dmk_context_t ctx) {
+    DMK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return DMK_OK;
+}
+
+namespace {
+struct PackedComponent {
+    std::vector<float> ratio;
+    std::vector<uint2> value;
+    std::vector<int32_t> stream;
+};
+uint2 pack_key(const Float3Key& k) {
+    return make_uint2(static_cast<uint32_t>(k.value[0]) | (static_cast<uint32_t>(k.value[1]) << 16), static_cast<uint32_t>(k.value[2]));
+}
+uint2 pack_key(const QuaternionKey& k) {
+    return make_uint2(static_cast<uint32_t>(static_cast<uint16_t>(k.value[0])) | (static_cast<uint32_t>(static_cast<uint16_t>(k.value[1])) << 16),
+                      static_cast<uint32_t>(static_cast<uint16_t>(k.value[2])) | (static_cast<uint32_t>(k.largest) << 16) |
+                          (static_cast<uint32_t>(k.sign) << 18));
+}
+// keys of the ozz stream regrouped per track (stream order within a track = time order)
+template <typename Key>
+bool regroup(const std::vector<Key>& keys, int padded, PackedComponent& pc, uint2* dir, std::string& err) {
+    std::vector<uint32_t> count(padded, 0);
+    for (const auto& k : keys) ++count[k.track];
+    uint32_t first = static_cast<uint32_t>(pc.ratio.size());
+    std::vector<uint32_t> cursor(padded);
+    for (int t = 0; t < padded; ++t) {
+        if (count[t] < 2) {
+            err = "corrupt ozz animation archive (a track has fewer than 2 keys)";
+            return false;
+        }
+        dir[t] = make_uint2(first, count[t]);
+        cursor[t] = first;
+        first += count[t];
+    }
+    pc.ratio.resize(first);
+    pc.value.resize(first);
+    pc.stream.resize(first);
+    for (size_t i = 0; i < keys.size(); ++i) {
+        const uint32_t at = cursor[keys[i].track]++;
+        pc.ratio[at] = keys[i].ratio;
+        pc.value[at] = pack_key(keys[i]);
+        pc.stream[at] = static_cast<int32_t>(i);
+    }
+    for (int t = 0; t < padded; ++t)
+        for (uint32_t i = dir[t].x + 1; i < dir[t].x + dir[t].y; ++i)
+            if (pc.ratio[i] < pc.ratio[i - 1]) {
+                err = "corrupt ozz animation archive (track keys are not sorted by ratio)";
+                return false;
+            }
+    return true;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* dmk_version(void) { return "darmok_b200 0.1 (sm_100a)"; }
+
+dmk_status dmk_context_create(int device, void* cuda_stream, dmk_context_t* out) {
+    if (!out) return fail(nullptr, DMK_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, DMK_ERR_CUDA, std::string("no CUDA device (this library has no CPU fallback): ") +
+                                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count) return fail(nullptr, DMK_ERR_INVALID, "device index out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    auto ctx = std::make_unique<dmk_context_s>();
+    ctx->device = device;
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        return fail(nullptr, DMK_ERR_CUDA, std::string("device is not sm_100a class (found sm_") + std::to_string(prop.major) +
+                                               std::to_string(prop.minor) + "); kernels are built for B200 only");
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cuda_stream) {
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(nullptr, e, "cudaStreamCreate");
+        ctx->owns_stream = true;
+    }
+    *out = ctx.release();
+    return DMK_OK;
+}
+
+void dmk_context_destroy(dmk_context_t ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx->cull_scratch);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* dmk_last_error(dmk_context_t ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void* dmk_context_stream(dmk_context_t ctx) { return ctx ? ctx->stream : nullptr; }
+uint64_t dmk_context_launch_count(dmk_context_t ctx) { return ctx ? ctx->launches : 0; }
+
+dmk_status dmk_sync(dmk_context_t ctx) {
+    if (!ctx) return DMK_ERR_INVALID;
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// skeleton
+// ------------------------------------------------------------------------------------------------------------
+dmk_status dmk_skeleton_load_ozz(dmk_context_t ctx, const void* bytes, size_t size, dmk_skeleton_t* out) {
+    if (!ctx || !out) return fail(ctx, DMK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    auto skel = std::make_unique<dmk_skeleton_s>();
+    skel->ctx = ctx;
+    std::string err;
+    if (!parse_skeleton(bytes, size, skel->data, err)) return fail(ctx, DMK_ERR_FORMAT, err);
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const int J = skel->data.num_joints;
+    // level-order schedule of LocalToModelJob: a joint's model matrix needs its parent's, so joints are processed by
+    // depth; within a depth every (joint, column) pair is an independent task, 32 tasks per round (one per lane)
+    std::vector<int> depth(J, 0);
+    int max_depth = 0;
+    for (int j = 0; j < J; ++j) {
+        depth[j] = skel->data.parents[j] < 0 ? 0 : depth[skel->data.parents[j]] + 1;
+        max_depth = std::max(max_depth, depth[j]);
+    }
+    std::vector<uint16_t> sched;
+    for (int d = 0; d <= max_depth && J > 0; ++d) {
+        size_t in_round = 0;
+        for (int j = 0; j < J; ++j) {
+            if (depth[j] != d) continue;
+            for (int c = 0; c < 4; ++c) {
+                sched.push_back(static_cast<uint16_t>(j | (c << 12)));
+                ++in_round;
+            }
+        }
+        while (in_round % 32) {
+            sched.push_back(kIdleTask);
+            ++in_round;
+        }
+    }
+    skel->rounds = static_cast<int>(sched.size() / 32);
+    DMK_CUDA(ctx, upload(ctx, &skel->d_parents, skel->data.parents));
+    DMK_CUDA(ctx, upload(ctx, &skel->d_schedule, sched));
+    *out = skel.release();
+    return DMK_OK;
+}
+
+void dmk_skeleton_destroy(dmk_skeleton_t skel) {
+    if (!skel) return;
+    cudaSetDevice(skel->ctx->device);
+    dev_free(skel->d_parents);
+    dev_free(skel->d_schedule);
+    delete skel;
+}
+int dmk_skeleton_num_joints(dmk_skeleton_t skel) { return skel ? skel->data.num_joints : 0; }
+const char* dmk_skeleton_joint_name(dmk_skeleton_t skel, int i) {
+    return (skel && i >= 0 && i < skel->data.num_joints) ? skel->data.names[i].c_str() : nullptr;
+}
+int dmk_skeleton_joint_parent(dmk_skeleton_t skel, int i) {
+    return (skel && i >= 0 && i < skel->data.num_joints) ? skel->data.parents[i] : -1;
+}
+int dmk_skeleton_find_joint(dmk_skeleton_t skel, const char* name) {
+    if (!skel || !name) return -1;
+    for (int i = 0; i < skel->data.num_joints; ++i)
+        if (skel->data.names[i] == name) return i;
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// clips
+// ------------------------------------------------------------------------------------------------------------
+dmk_status dmk_clip_load_ozz(dmk_context_t ctx, const void* bytes, size_t size, dmk_clip_t* out) {
+    if (!ctx || !out) return fail(ctx, DMK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    auto clip = std::make_unique<dmk_clip_s>();
+    clip->ctx = ctx;
+    std::string err;
+    if (!parse_animation(bytes, size, clip->data, err)) return fail(ctx, DMK_ERR_FORMAT, err);
+    *out = clip.release();
+    return DMK_OK;
+}
+void dmk_clip_destroy(dmk_clip_t clip) { delete clip; }
+float dmk_clip_duration(dmk_clip_t clip) { return clip ? clip->data.duration : 0.f; }
+const char* dmk_clip_name(dmk_clip_t clip) { return clip ? clip->data.name.c_str() : nullptr; }
+int dmk_clip_num_tracks(dmk_clip_t clip) { return clip ? clip->data.num_tracks : 0; }
+
+
+dmk_status dmk_clipset_create(dmk_context_t ctx, dmk_skeleton_t skel, const dmk_clip_t* clips, int num_clips, dmk_clipset_t* out) {
+    if (!ctx || !skel || !clips || !out || num_clips <= 0) return fail(ctx, DMK_ERR_INVALID, "null argument or empty clip list");
+    *out = nullptr;
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const int padded = skel->data.num_soa() * 4;
+    auto set = std::make_unique<dmk_clipset_s>();
+    set->ctx = ctx;
+    set->num_clips = num_clips;
+    set->padded_tracks = padded;
+    std::vector<uint2> dir(static_cast<size_t>(num_clips) * 3 * padded);
+    PackedComponent pc[3];
+    for (int c = 0; c < num_clips; ++c) {
+        if (!clips[c]) return fail(ctx, DMK_ERR_INVALID, "null clip");
+        const AnimationData& a = clips[c]->data;
+        if (a.num_soa() != skel->data.num_soa())
+            return fail(ctx, DMK_ERR_UNSUPPORTED,
+                        "animation '" + a.name + "' has " + std::to_string(a.num_tracks) + " tracks, skeleton has " +
+                            std::to_string(skel->data.num_joints) + " joints (SoA track counts must match)");
+        std::string err;
+        uint2* d = dir.data() + static_cast<size_t>(c) * 3 * padded;
+        if (!regroup(a.translations, padded, pc[0], d, err) || !regroup(a.rotations, padded, pc[1], d + padded, err) ||
+            !regroup(a.scales, padded, pc[2], d + 2 * padded, err))
+            return fail(ctx, DMK_ERR_FORMAT, err);
+        set->durations.push_back(a.duration);
+    }
+    DMK_CUDA(ctx, upload(ctx, &set->d_dir, dir));
+    for (int k = 0; k < 3; ++k) {
+        DMK_CUDA(ctx, upload(ctx, &set->d_ratio[k], pc[k].ratio));
+        DMK_CUDA(ctx, upload(ctx, &set->d_value[k], pc[k].value));
+        DMK_CUDA(ctx, upload(ctx, &set->d_stream[k], pc[k].stream));
+    }
+    DMK_CUDA(ctx, upload(ctx, &set->d_duration, set->durations));
+    *out = set.release();
+    return DMK_OK;
+}
+
+void dmk_clipset_destroy(dmk_clipset_t set) {
+    if (!set) return;
+    cudaSetDevice(set->ctx->device);
+    dev_free(set->d_dir);
+    for (int k = 0; k < 3; ++k) {
+        dev_free(set->d_ratio[k]);
+        dev_free(set->d_value[k]);
+        dev_free(set->d_stream[k]);
+    }
+    dev_free(set->d_duration);
+    delete set;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// armature + mesh
+// ------------------------------------------------------------------------------------------------------------
+dmk_status dmk_armature_create(dmk_context_t ctx, dmk_skeleton_t skel, const char* const* joint_names, const float* inv_bind,
+                               int num_joints, dmk_armature_t* out) {
+    if (!ctx || !skel || !out || num_joints < 0 || (num_joints > 0 && (!joint_names || !inv_bind)))
+        return fail(ctx, DMK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (num_joints + 1 > kMaxPalette)
+        return fail(ctx, DMK_ERR_UNSUPPORTED, "armature has more than 255 joints (palette slots are bytes; the reference caps at 64)");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    auto arm = std::make_unique<dmk_armature_s>();
+    arm->ctx = ctx;
+    arm->num_joints = num_joints;
+    std::vector<float> ib(static_cast<size_t>(num_joints) * 12);
+    for (int k = 0; k < num_joints; ++k) {
+        const float* m = inv_bind + static_cast<size_t>(k) * 16;
+        if (m[3] != 0.f || m[7] != 0.f || m[11] != 0.f || m[15] != 1.f)
+            return fail(ctx, DMK_ERR_UNSUPPORTED, "inverse bind pose of joint " + std::to_string(k) + " is not affine (bottom row must be 0,0,0,1)");
+        for (int c = 0; c < 4; ++c)
+            for (int r = 0; r < 3; ++r) ib[static_cast<size_t>(k) * 12 + c * 3 + r] = m[c * 4 + r];
+        arm->remap.push_back(joint_names[k] ? dmk_skeleton_find_joint(skel, joint_names[k]) : -1);
+    }
+    DMK_CUDA(ctx, upload(ctx, &arm->d_remap, arm->remap));
+    DMK_CUDA(ctx, upload(ctx, &arm->d_inv_bind, ib));
+    *out = arm.release();
+    return DMK_OK;
+}
+void dmk_armature_destroy(dmk_armature_t arm) {
+    if (!arm) return;
+    cudaSetDevice(arm->ctx->device);
+    dev_free(arm->d_remap);
+    dev_free(arm->d_inv_bind);
+    delete arm;
+}
+int dmk_armature_palette_size(dmk_armature_t arm) { return arm ? arm->num_joints + 1 : 0; }
+
+dmk_status dmk_mesh_create(dmk_context_t ctx, const float* position, const float* normal, const float* tangent, const float* indices,
+                           const float* weights, int num_vertices, int palette_size, dmk_mesh_t* out) {
+    if (!ctx || !out || num_vertices < 0 || (num_vertices > 0 && (!position || !normal || !tangent || !indices || !weights)))
+        return fail(ctx, DMK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (palette_size < 1 || palette_size > kMaxPalette) return fail(ctx, DMK_ERR_INVALID, "palette_size must be in [1, 256]");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    auto mesh = std::make_unique<dmk_mesh_s>();
+    mesh->ctx = ctx;
+    mesh->num_vertices = num_vertices;
+    mesh->palette_size = palette_size;
+    const int vpad = (num_vertices + 7) / 8 * 8;
+    mesh->vpad = vpad;
+    std::vector<float> pos(static_cast<size_t>(vpad) * 3, 0.f), nrm(pos.size(), 0.f), tan(pos.size(), 0.f);
+    std::vector<float> w(static_cast<size_t>(vpad) * 4, 0.f);
+    std::vector<uint32_t> slots(vpad, 0u);
+    std::copy(position, position + static_cast<size_t>(num_vertices) * 3, pos.begin());
+    std::copy(normal, normal + static_cast<size_t>(num_vertices) * 3, nrm.begin());
+    std::copy(tangent, tangent + static_cast<size_t>(num_vertices) * 3, tan.begin());
+    for (int v = 0; v < vpad; ++v) {
+        float* wv = &w[static_cast<size_t>(v) * 4];
+        wv[0] = 1.f;  // padding and unskinned vertices: 1 * identity
+        if (v >= num_vertices) continue;
+        const float* idx = indices + static_cast<size_t>(v) * 4;
+        if (!(idx[0] >= 0.f)) continue;  // applySkinning: `if (indices.x >= 0)` else the vertex passes through
+        uint32_t packed = 0;
+        for (int c = 0; c < 4; ++c) {
+            const int slot = static_cast<int>(idx[c] + 1.f);  // getSkinningMatrixPart: u_skinning[int(v + 1)]
+            if (!(idx[c] >= -1.f) || slot < 0 || slot >= palette_size)
+                return fail(ctx, DMK_ERR_INVALID, "vertex " + std::to_string(v) + " references bone " + std::to_string(idx[c]) +
+                                                      " outside the palette (size " + std::to_string(palette_size) + ")");
+            packed |= static_cast<uint32_t>(slot) << (8 * c);
+            wv[c] = weights[static_cast<size_t>(v) * 4 + c];
+        }
+        slots[v] = packed;
+    }
+    DMK_CUDA(ctx, upload(ctx, &mesh->d_pos, pos));
+    DMK_CUDA(ctx, upload(ctx, &mesh->d_nrm, nrm));
+    DMK_CUDA(ctx, upload(ctx, &mesh->d_tan, tan));
+    DMK_CUDA(ctx, upload(ctx, &mesh->d_weights, w));
+    DMK_CUDA(ctx, upload(ctx, &mesh->d_slots, slots));
+    *out = mesh.release();
+    return DMK_OK;
+}
+void dmk_mesh_destroy(dmk_mesh_t mesh) {
+    if (!mesh) return;
+    cudaSetDevice(mesh->ctx->device);
+    dev_free(mesh->d_pos);
+    dev_free(mesh->d_nrm);
+    dev_free(mesh->d_tan);
+    dev_free(mesh->d_weights);
+    dev_free(mesh->d_slots);
+    delete mesh;
+}
+int dmk_mesh_num_vertices(dmk_mesh_t mesh) { return mesh ? mesh->num_vertices : 0; }
+int dmk_mesh_vertex_pitch(dmk_mesh_t mesh) { return mesh ? mesh->vpad : 0; }
+
+// ------------------------------------------------------------------------------------------------------------
+// crowd
+// ------------------------------------------------------------------------------------------------------------
+dmk_status dmk_crowd_create(dmk_context_t ctx, dmk_skeleton_t skel, dmk_clipset_t clips, dmk_armature_t arm, dmk_mesh_t mesh,
+                            int64_t n, int max_layers, dmk_crowd_t* out) {
+    if (!ctx || !skel || !clips || !out) return fail(ctx, DMK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (n < 0 || n > 0x7fffffff) return fail(ctx, DMK_ERR_INVALID, "num_characters out of range");
+    if (max_layers < 1 || max_layers > kMaxLayers) return fail(ctx, DMK_ERR_INVALID, "max_layers must be in [1, 16]");
+    if (mesh && !arm) return fail(ctx, DMK_ERR_INVALID, "a mesh needs an armature");
+    if (mesh && mesh->palette_size != arm->num_joints + 1)
+        return fail(ctx, DMK_ERR_INVALID, "mesh palette_size does not match the armature");
+    if (skel->data.num_joints == 0) return fail(ctx, DMK_ERR_INVALID, "skeleton has no joints");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    auto crowd = std::make_unique<dmk_crowd_s>();
+    dmk_crowd_s* c = crowd.get();
+    c->ctx = ctx;
+    c->skel = skel;
+    c->clips = clips;
+    c->arm = arm;
+    c->mesh = mesh;
+    c->n = n;
+    c->max_layers = max_layers;
+    const size_t ln = static_cast<size_t>(max_layers) * static_cast<size_t>(n);
+    DMK_CUDA(ctx, dev_alloc(&c->d_clip, ln));
+    DMK_CUDA(ctx, dev_alloc(&c->d_ratio, ln));
+    DMK_CUDA(ctx, dev_alloc(&c->d_weight, ln));
+    DMK_CUDA(ctx, dev_alloc(&c->d_speed, ln));
+    DMK_CUDA(ctx, dev_alloc(&c->d_loop, ln));
+    DMK_CUDA(ctx, dev_alloc(&c->d_looped, ln));
+    DMK_CUDA(ctx, dev_alloc(&c->d_error, 1));
+    DMK_CUDA(ctx, cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), ctx->stream));
+    DMK_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&c->h_error), sizeof(int32_t), cudaHostAllocDefault));
+    *c->h_error = 0;
+    if (arm) {
+        const size_t ps = static_cast<size_t>(arm->num_joints + 1);
+        DMK_CUDA(ctx, dev_alloc(&c->d_palette, static_cast<size_t>(n) * ps * 16));
+        DMK_CUDA(ctx, dev_alloc(&c->d_palette34, static_cast<size_t>(n) * ps * 12));
+    }
+    if (mesh) {
+        DMK_CUDA(ctx, dev_alloc(&c->d_skinned, static_cast<size_t>(n) * static_cast<size_t>(mesh->vpad) * 9));
+        c->plan = plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms);
+    }
+    const size_t words = static_cast<size_t>((n + 31) / 32);
+    DMK_CUDA(ctx, dev_alloc(&c->d_vis_bits, words + 1));
+    DMK_CUDA(ctx, dev_alloc(&c->d_visible_ids, static_cast<size_t>(n) + 1));
+    DMK_CUDA(ctx, dev_alloc(&c->d_visible_count, 1));
+    DMK_CUDA(ctx, dev_alloc(&c->d_scratch, compact_scratch_ints(n)));
+    DMK_CUDA(ctx, cudaMemsetAsync(c->d_visible_count, 0, sizeof(int32_t), ctx->stream));
+    *out = crowd.release();
+    return DMK_OK;
+}
+
+void dmk_crowd_destroy(dmk_crowd_t c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    for (void* p : {(void*)c->d_clip, (void*)c->d_ratio, (void*)c->d_weight, (void*)c->d_speed, (void*)c->d_loop, (void*)c->d_looped,
+                    (void*)c->d_palette, (void*)c->d_palette34, (void*)c->d_skinned, (void*)c->d_models, (void*)c->d_locals,
+                    (void*)c->d_key_indices, (void*)c->d_error, (void*)c->d_world_inverse, (void*)c->d_bbox, (void*)c->d_vis_bits,
+                    (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch})
+        dev_free(p);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_error) cudaFreeHost(c->h_error);
+    delete c;
+}
+int64_t dmk_crowd_size(dmk_crowd_t c) { return c ? c->n : 0; }
+
+dmk_status dmk_crowd_enable_outputs(dmk_crowd_t c, uint32_t outputs) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t n = static_cast<size_t>(c->n);
+    if ((outputs & DMK_OUT_MODELS) && !c->d_models) DMK_CUDA(ctx, dev_alloc(&c->d_models, n * c->skel->data.num_joints * 16));
+    if ((outputs & DMK_OUT_LOCALS) && !c->d_locals) DMK_CUDA(ctx, dev_alloc(&c->d_locals, n * c->skel->data.num_soa() * kSoaFloats));
+    if ((outputs & DMK_OUT_KEY_INDICES) && !c->d_key_indices)
+        DMK_CUDA(ctx, dev_alloc(&c->d_key_indices, n * c->max_layers * 3 * c->skel->data.num_soa() * 4 * 2));
+    return DMK_OK;
+}
+
+static dmk_status ensure_stage(dmk_crowd_t c, size_t bytes) {
+    if (c->h_stage_bytes >= bytes) return DMK_OK;
+    if (c->h_stage) {
+        cudaStreamSynchronize(c->ctx->stream);
+        cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr;
+        c->h_stage_bytes = 0;
+    }
+    DMK_CUDA(c->ctx, cudaHostAlloc(&c->h_stage, bytes, cudaHostAllocDefault));
+    c->h_stage_bytes = bytes;
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_set_layers(dmk_crowd_t c, int num_layers, const int32_t* clip, const float* ratio, const float* weight,
+                                const float* speed, const uint8_t* loop, float threshold) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (num_layers < 1 || num_layers > c->max_layers) return fail(ctx, DMK_ERR_INVALID, "num_layers out of range");
+    if (!clip || !ratio || !weight) return fail(ctx, DMK_ERR_INVALID, "null layer array");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t ln = static_cast<size_t>(num_layers) * static_cast<size_t>(c->n);
+    for (size_t i = 0; i < ln; ++i)
+        if (clip[i] < 0 || clip[i] >= c->clips->num_clips)
+            return fail(ctx, DMK_ERR_INVALID, "layer references clip " + std::to_string(clip[i]) + " outside the clip set");
+    cudaStream_t s = ctx->stream;
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_clip, clip, ln * 4, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_ratio, ratio, ln * 4, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_weight, weight, ln * 4, cudaMemcpyHostToDevice, s));
+    if (speed) {
+        DMK_CUDA(ctx, cudaMemcpyAsync(c->d_speed, speed, ln * 4, cudaMemcpyHostToDevice, s));
+    } else {
+        std::vector<float> ones(ln, 1.f);
+        DMK_CUDA(ctx, cudaMemcpyAsync(c->d_speed, ones.data(), ln * 4, cudaMemcpyHostToDevice, s));
+        DMK_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    c->has_loop = loop != nullptr;
+    if (loop) DMK_CUDA(ctx, cudaMemcpyAsync(c->d_loop, loop, ln, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemsetAsync(c->d_looped, 0, ln, s));
+    DMK_CUDA(ctx, cudaStreamSynchronize(s));  // host arrays are the caller's
+    c->num_layers = num_layers;
+    c->threshold = threshold;
+    c->layers_set = true;
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_update_layers(dmk_crowd_t c, int num_layers, const int32_t* clip, const float* ratio, const float* weight) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!c->layers_set || num_layers != c->num_layers) return fail(ctx, DMK_ERR_INVALID, "call dmk_crowd_set_layers first (same num_layers)");
+    if (!clip || !ratio || !weight) return fail(ctx, DMK_ERR_INVALID, "null layer array");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t bytes = static_cast<size_t>(num_layers) * static_cast<size_t>(c->n) * 4;
+    if (dmk_status st = ensure_stage(c, 3 * bytes)) return st;
+    // the previous frame's copies out of the staging area must have drained before it is overwritten
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    char* h = static_cast<char*>(c->h_stage);
+    std::memcpy(h, clip, bytes);
+    std::memcpy(h + bytes, ratio, bytes);
+    std::memcpy(h + 2 * bytes, weight, bytes);
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_clip, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_ratio, h + bytes, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_weight, h + 2 * bytes, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_set_instances(dmk_crowd_t c, const float* world_inverse, const float* bbox) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!world_inverse || !bbox) return fail(ctx, DMK_ERR_INVALID, "null instance array");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t n = static_cast<size_t>(c->n);
+    if (!c->d_world_inverse) DMK_CUDA(ctx, dev_alloc(&c->d_world_inverse, n * 16));
+    if (!c->d_bbox) DMK_CUDA(ctx, dev_alloc(&c->d_bbox, n * 6));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_world_inverse, world_inverse, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_bbox, bbox, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    c->instances_set = true;
+    return DMK_OK;
+}
+
+dmk_status dmk_frustum_corners(const float* view_proj, float near_depth, float* out_corners) {
+    if (!view_proj || !out_corners) return DMK_ERR_INVALID;
+    frustum_corners_glm(view_proj, near_depth, out_corners);
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_set_camera(dmk_crowd_t c, const float* view_proj, float near_depth) {
+    if (!c) return DMK_ERR_INVALID;
+    if (!view_proj) return fail(c->ctx, DMK_ERR_INVALID, "null view_proj");
+    frustum_corners_glm(view_proj, near_depth, c->corners);
+    c->camera_set = true;
+    return DMK_OK;
+}
+dmk_status dmk_crowd_set_frustum_corners(dmk_crowd_t c, const float* corners) {
+    if (!c) return DMK_ERR_INVALID;
+    if (!corners) return fail(c->ctx, DMK_ERR_INVALID, "null corners");
+    std::memcpy(c->corners, corners, sizeof c->corners);
+    c->camera_set = true;
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    cudaStream_t s = ctx->stream;
+    if ((flags & DMK_STEP_ADVANCE) && !(flags & DMK_STEP_POSE))
+        return fail(ctx, DMK_ERR_UNSUPPORTED, "DMK_STEP_ADVANCE runs inside the pose kernel: combine it with DMK_STEP_POSE");
+    if (flags & DMK_STEP_POSE) {
+        if (!c->layers_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_layers has not been called");
+        // BlendingJob::Validate: threshold > 0 (darmok: "error in the blending job", src/skeleton_ozz.cpp:605-608)
+        if (c->num_layers > 1 && !(c->threshold > 0.f)) return fail(ctx, DMK_ERR_JOB, "error in the blending job");
+        PoseParams p{};
+        p.clips.dir = c->clips->d_dir;
+        for (int k = 0; k < 3; ++k) {
+            p.clips.ratio[k] = c->clips->d_ratio[k];
+            p.clips.value[k] = c->clips->d_value[k];
+            p.clips.stream[k] = c->clips->d_stream[k];
+        }
+        p.clips.duration = c->clips->d_duration;
+        p.clips.num_clips = c->clips->num_clips;
+        p.clips.padded_tracks = c->clips->padded_tracks;
+        p.skel.parents = c->skel->d_parents;
+        p.skel.schedule = c->skel->d_schedule;
+        p.skel.num_joints = c->skel->data.num_joints;
+        p.skel.padded_joints = c->skel->data.num_soa() * 4;
+        p.skel.num_soa = c->skel->data.num_soa();
+        p.skel.rounds = c->skel->rounds;
+        if (c->arm) {
+            p.arm.remap = c->arm->d_remap;
+            p.arm.inv_bind = c->arm->d_inv_bind;
+            p.arm.num_joints = c->arm->num_joints;
+        }
+        p.n = c->n;
+        p.num_layers = c->num_layers;
+        p.clip = c->d_clip;
+        p.ratio = c->d_ratio;
+        p.weight = c->d_weight;
+        p.speed = c->d_speed;
+        p.loop = c->has_loop ? c->d_loop : nullptr;
+        p.looped = c->d_looped;
+        p.threshold = c->threshold;
+        p.dt = dt;
+        p.advance = (flags & DMK_STEP_ADVANCE) ? 1 : 0;
+        p.palette = c->d_palette;
+        p.palette34 = c->d_palette34;
+        p.models = c->d_models;
+        p.locals = c->d_locals;
+        p.key_indices = c->d_key_indices;
+        p.error_flag = c->d_error;
+        DMK_CUDA(ctx, launch_pose(p, ctx->num_sms, s));
+        ++ctx->launches;
+    }
+    if (flags & DMK_STEP_CULL) {
+        if (!c->instances_set || !c->camera_set)
+            return fail(ctx, DMK_ERR_INVALID, "cull needs dmk_crowd_set_instances and dmk_crowd_set_camera");
+        CullParams p{};
+        p.world_inverse = c->d_world_inverse;
+        p.bbox = c->d_bbox;
+        p.n = c->n;
+        p.vis_bits = c->d_vis_bits;
+        std::memcpy(p.corners, c->corners, sizeof p.corners);
+        DMK_CUDA(ctx, launch_cull(p, s));
+        ++ctx->launches;
+        int extra = 0;
+        DMK_CUDA(ctx, launch_compact(c->d_vis_bits, c->n, c->d_visible_ids, c->d_visible_count, c->d_scratch, s, &extra));
+        ctx->launches += extra;
+        c->culled_once = true;
+    }
+    if (flags & DMK_STEP_SKIN) {
+        if (!c->mesh || !c->arm) return fail(ctx, DMK_ERR_INVALID, "skinning needs a mesh and an armature");
+        const bool visible_only = (flags & DMK_STEP_SKIN_VISIBLE_ONLY) != 0;
+        if (visible_only && !c->culled_once) return fail(ctx, DMK_ERR_INVALID, "DMK_STEP_SKIN_VISIBLE_ONLY needs a cull step");
+        SkinParams p{};
+        p.palette34 = c->d_palette34;
+        p.pos = c->mesh->d_pos;
+        p.nrm = c->mesh->d_nrm;
+        p.tan = c->mesh->d_tan;
+        p.weights = c->mesh->d_weights;
+        p.slots = c->mesh->d_slots;
+        p.out = c->d_skinned;
+        p.char_ids = visible_only ? c->d_visible_ids : nullptr;
+        p.char_count = visible_only ? c->d_visible_count : nullptr;
+        p.n = c->n;
+        p.vpad = c->mesh->vpad;
+        p.palette_size = c->mesh->palette_size;
+        p.num_tiles = c->plan.num_tiles;
+        p.tile_vertices = c->plan.tile_vertices;
+        DMK_CUDA(ctx, launch_skin(p, c->plan, s));
+        ++ctx->launches;
+    }
+    if (flags & DMK_STEP_POSE)
+        DMK_CUDA(ctx, cudaMemcpyAsync(c->h_error, c->d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    return DMK_OK;
+}
+
+// ---- results -----------------------------------------------------------------------------------------------
+const float* dmk_crowd_palette_dev(dmk_crowd_t c) { return c ? c->d_palette : nullptr; }
+const float* dmk_crowd_skinned_dev(dmk_crowd_t c) { return c ? c->d_skinned : nullptr; }
+const uint32_t* dmk_crowd_visibility_dev(dmk_crowd_t c) { return c ? c->d_vis_bits : nullptr; }
+const int32_t* dmk_crowd_visible_ids_dev(dmk_crowd_t c) { return c ? c->d_visible_ids : nullptr; }
+const int32_t* dmk_crowd_visible_count_dev(dmk_crowd_t c) { return c ? c->d_visible_count : nullptr; }
+
+static dmk_status finish_and_check(dmk_crowd_t c) {
+    dmk_context_t ctx = c->ctx;
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*c->h_error != 0)
+        return fail(ctx, DMK_ERR_INVALID, "character " + std::to_string(*c->h_error - 1) + " references a clip outside the clip set");
+    return DMK_OK;
+}
+static dmk_status check_range(dmk_crowd_t c, int64_t first, int64_t count, const void* out) {
+    if (!c) return DMK_ERR_INVALID;
+    if (!out || first < 0 || count < 0 || first + count > c->n) return fail(c->ctx, DMK_ERR_INVALID, "character range out of bounds");
+    if (bind(c->ctx)) return DMK_ERR_CUDA;
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_get_palette(dmk_crowd_t c, int64_t first, int64_t count, float* out) {
+    if (dmk_status st = check_range(c, first, count, out)) return st;
+    if (!c->d_palette) return fail(c->ctx, DMK_ERR_INVALID, "crowd has no armature");
+    const size_t per = static_cast<size_t>(c->arm->num_joints + 1) * 16;
+    DMK_CUDA(c->ctx, cudaMemcpyAsync(out, c->d_palette + first * per, count * per * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+    return finish_and_check(c);
+}
+dmk_status dmk_crowd_get_models(dmk_crowd_t c, int64_t first, int64_t count, float* out) {
+    if (dmk_status st = check_range(c, first, count, out)) return st;
+    if (!c->d_models) return fail(c->ctx, DMK_ERR_INVALID, "enable DMK_OUT_MODELS with dmk_crowd_enable_outputs before the step");
+    const size_t per = static_cast<size_t>(c->skel->data.num_joints) * 16;
+    DMK_CUDA(c->ctx, cudaMemcpyAsync(out, c->d_models + first * per, count * per * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+    return finish_and_check(c);
+}
+dmk_status dmk_crowd_get_locals(dmk_crowd_t c, int64_t first, int64_t count, float* out) {
+    if (dmk_status st = check_range(c, first, count, out)) return st;
+    if (!c->d_locals) return fail(c->ctx, DMK_ERR_INVALID, "enable DMK_OUT_LOCALS with dmk_crowd_enable_outputs before the step");
+    const size_t per = static_cast<size_t>(c->skel->data.num_soa()) * kSoaFloats;
+    DMK_CUDA(c->ctx, cudaMemcpyAsync(out, c->d_locals + first * per, count * per * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+    return finish_and_check(c);
+}
+dmk_status dmk_crowd_get_key_indices(dmk_crowd_t c, int64_t first, int64_t count, int32_t* out) {
+    if (dmk_status st = check_range(c, first, count, out)) return st;
+    if (!c->d_key_indices) return fail(c->ctx, DMK_ERR_INVALID, "enable DMK_OUT_KEY_INDICES with dmk_crowd_enable_outputs before the step");
+    // device layout uses the current num_layers as the layer stride
+    const size_t per = static_cast<size_t>(c->num_layers) * 3 * c->skel->data.num_soa() * 4 * 2;
+    DMK_CUDA(c->ctx, cudaMemcpyAsync(out, c->d_key_indices + first * per, count * per * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+    return finish_and_check(c);
+}
+dmk_status dmk_crowd_get_skinned(dmk_crowd_t c, int64_t first, int64_t count, float* out) {
+    if (dmk_status st = check_range(c, first, count, out)) return st;
+    if (!c->d_skinned) return fail(c->ctx, DMK_ERR_INVALID, "crowd has no mesh");
+    const size_t pitch = static_cast<size_t>(c->mesh->vpad) * 9, row = static_cast<size_t>(c->mesh->num_vertices) * 9;
+    DMK_CUDA(c->ctx, cudaMemcpy2DAsync(out, row * 4, c->d_skinned + first * pitch, pitch * 4, row * 4, count, cudaMemcpyDeviceToHost,
+                                       c->ctx->stream));
+    return finish_and_check(c);
+}
+dmk_status dmk_crowd_get_visibility(dmk_crowd_t c, uint32_t* out_bits, int64_t* out_visible_count) {
+    if (!c) return DMK_ERR_INVALID;
+    if (!c->culled_once) return fail(c->ctx, DMK_ERR_INVALID, "no cull step has run");
+    if (bind(c->ctx)) return DMK_ERR_CUDA;
+    const size_t words = static_cast<size_t>((c->n + 31) / 32);
+    if (out_bits) DMK_CUDA(c->ctx, cudaMemcpyAsync(out_bits, c->d_vis_bits, words * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+    int32_t count = 0;
+    DMK_CUDA(c->ctx, cudaMemcpyAsync(&count, c->d_visible_count, 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+    if (dmk_status st = finish_and_check(c)) return st;
+    if (out_visible_count) *out_visible_count = count;
+    return DMK_OK;
+}
+dmk_status dmk_crowd_get_ratios(dmk_crowd_t c, float* out_ratio, uint8_t* out_looped) {
+    if (!c) return DMK_ERR_INVALID;
+    if (!c->layers_set) return fail(c->ctx, DMK_ERR_INVALID, "dmk_crowd_set_layers has not been called");
+    if (bind(c->ctx)) return DMK_ERR_CUDA;
+    const size_t ln = static_cast<size_t>(c->num_layers) * static_cast<size_t>(c->n);
+    if (out_ratio) DMK_CUDA(c->ctx, cudaMemcpyAsync(out_ratio, c->d_ratio, ln * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+    if (out_looped) DMK_CUDA(c->ctx, cudaMemcpyAsync(out_looped, c->d_looped, ln, cudaMemcpyDeviceToHost, c->ctx->stream));
+    return finish_and_check(c);
+}
+
+dmk_status dmk_crowd_pack_visible_palettes(dmk_crowd_t c, float* out_dev, int64_t capacity) {
+    if (!c) return DMK_ERR_INVALID;
+    if (!out_dev || capacity < 0) return fail(c->ctx, DMK_ERR_INVALID, "null output");
+    if (!c->d_palette || !c->culled_once) return fail(c->ctx, DMK_ERR_INVALID, "needs an armature and a cull step");
+    if (bind(c->ctx)) return DMK_ERR_CUDA;
+    DMK_CUDA(c->ctx, launch_pack_palettes(c->d_palette, (c->arm->num_joints + 1) * 16, c->d_visible_ids, c->d_visible_count, capacity,
+                                          out_dev, c->ctx->num_sms, c->ctx->stream));
+    ++c->ctx->launches;
+    return DMK_OK;
+}
+
+// ---- stand-alone cull ----------------------------------------------------------------------------------------
+dmk_status dmk_cull_dev(dmk_context_t ctx, const float* corners_host, const float* world_inverse_dev, const float* bbox_dev, int64_t n,
+                        uint32_t* vis_bits_dev) {
+    if (!ctx) return DMK_ERR_INVALID;
+    if (!corners_host || n < 0 || (n > 0 && (!world_inverse_dev || !bbox_dev || !vis_bits_dev))) return fail(ctx, DMK_ERR_INVALID, "null argument");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    CullParams p{};
+    p.world_inverse = world_inverse_dev;
+    p.bbox = bbox_dev;
+    p.n = n;
+    p.vis_bits = vis_bits_dev;
+    std::memcpy(p.corners, corners_host, sizeof p.corners);
+    DMK_CUDA(ctx, launch_cull(p, ctx->stream));
+    ++ctx->launches;
+    return DMK_OK;
+}
+
+dmk_status dmk_cull_host(dmk_context_t ctx, const float* view_proj, float near_depth, const float* world_inverse, const float* bbox,
+                         int64_t n, uint32_t* vis_bits) {
+    if (!ctx) return DMK_ERR_INVALID;
+    if (!view_proj || n < 0 || (n > 0 && (!world_inverse || !bbox || !vis_bits))) return fail(ctx, DMK_ERR_INVALID, "null argument");
+    if (n == 0) return DMK_OK;
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t words = static_cast<size_t>((n + 31) / 32);
+    const size_t need = static_cast<size_t>(n) * 88 + words * 4 + 256;
+    if (ctx->cull_scratch_bytes < need) {
+        dev_free(ctx->cull_scratch);
+        ctx->cull_scratch = nullptr;
+        ctx->cull_scratch_bytes = 0;
+        DMK_CUDA(ctx, cudaMalloc(&ctx->cull_scratch, need));
+        ctx->cull_scratch_bytes = need;
+    }
+    float* d_wi = static_cast<float*>(ctx->cull_scratch);
+    float* d_bb = d_wi + static_cast<size_t>(n) * 16;
+    uint32_t* d_bits = reinterpret_cast<uint32_t*>(d_bb + static_cast<size_t>(n) * 6 + ((n * 6) % 2 ? 1 : 0));
+    float corners[24];
+    frustum_corners_glm(view_proj, near_depth, corners);
+    DMK_CUDA(ctx, cudaMemcpyAsync(d_wi, world_inverse, static_cast<size_t>(n) * 64, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaMemcpyAsync(d_bb, bbox, static_cast<size_t>(n) * 24, cudaMemcpyHostToDevice, ctx->stream));
+    if (dmk_status st = dmk_cull_dev(ctx, corners, d_wi, d_bb, n, d_bits)) return st;
+    DMK_CUDA(ctx, cudaMemcpyAsync(vis_bits, d_bits, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DMK_OK;
+}
+
+}  // extern "C"

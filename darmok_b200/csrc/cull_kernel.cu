@@ -1,0 +1,214 @@
+// cull_kernel.cu -- K4: FrustumCuller::updateCulled for a whole crowd, one thread per instance.
+//
+// Replaces (paths relative to the darmok repository):
+//   FrustumCuller::updateCulled       src/culling.cpp:264-285
+//   Frustum::operator*=               src/shape.cpp:1317-1324   (camera frustum corners -> entity local space)
+//   Frustum::getPlanes / getPlane     src/shape.cpp:1235-1272   (6 planes from corner triples)
+//   Plane(Triangle), signedDistanceTo src/shape.cpp:423-427, :449-452
+//   Plane::isInFront(BoundingBox)     src/shape.cpp:459-469,  BoundingBox::getCorners :1057-1069
+//   Frustum::canSee                   src/shape.cpp:1213-1223
+//
+// Visibility must be bit-exact with the CPU: this TU is compiled with -fmad=false, uses IEEE sqrt/div and follows
+// glm's scalar operation order.  The only algebraic shortcut is exact: "all 8 box corners
+// have signed distance > 0" is evaluated on the corner that minimises every rounded product -- IEEE rounding is
+// monotonic, so fl(fl(px+py)+pz)-d of that corner is the minimum over the 8 corners (NaN corners never fail the
+// reference's `<= 0` test, and fminf drops them the same way).
+#include "device_types.cuh"
+#include "kernels.cuh"
+
+namespace dmk {
+
+namespace {
+
+struct V3 { float x, y, z; };
+
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ V3 cross3(V3 x, V3 y) {
+    return {x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y};
+}
+__device__ __forceinline__ V3 normalize3(V3 v) {
+    const float inv = __fdiv_rn(1.f, __fsqrt_rn(dot3(v, v)));
+    return {v.x * inv, v.y * inv, v.z * inv};
+}
+
+// true when plane(a, b, c) has the whole box strictly in front (Plane::isInFront(BoundingBox))
+__device__ __forceinline__ bool box_in_front(V3 a, V3 b, V3 c, V3 mn, V3 mx) {
+    const V3 n = normalize3(cross3(sub(b, a), sub(c, a)));   // Plane(Triangle): normal
+    const float d = dot3(n, a);                              //                  distance
+    const V3 nn = normalize3(n);                             // signedDistanceTo normalises again
+    const float px = fminf(nn.x * mn.x, nn.x * mx.x);
+    const float py = fminf(nn.y * mn.y, nn.y * mx.y);
+    const float pz = fminf(nn.z * mn.z, nn.z * mx.z);
+    const float sd_min = ((px + py) + pz) - d;
+    return !(sd_min <= 0.f);
+}
+
+__global__ void __launch_bounds__(256) cull_kernel(const CullParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool visible = false;
+    if (i < p.n) {
+        const float4* m4 = reinterpret_cast<const float4*>(p.world_inverse + i * 16);
+        const float4 c0 = __ldg(m4 + 0), c1 = __ldg(m4 + 1), c2 = __ldg(m4 + 2), c3 = __ldg(m4 + 3);
+        const float2* bb = reinterpret_cast<const float2*>(p.bbox + i * 6);
+        const float2 b0 = __ldg(bb + 0), b1 = __ldg(bb + 1), b2 = __ldg(bb + 2);
+        const V3 mn = {b0.x, b0.y, b1.x}, mx = {b1.y, b2.x, b2.y};
+        V3 c[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            // trans * vec4(corner, 1): (m0*x + m1*y) + (m2*z + m3*w), truncated to vec3
+            const float x = p.corners[k * 3 + 0], y = p.corners[k * 3 + 1], z = p.corners[k * 3 + 2];
+            c[k].x = (c0.x * x + c1.x * y) + (c2.x * z + c3.x * 1.f);
+            c[k].y = (c0.y * x + c1.y * y) + (c2.y * z + c3.y * 1.f);
+            c[k].z = (c0.z * x + c1.z * y) + (c2.z * z + c3.z * 1.f);
+        }
+        // Frustum::CornerType: NBL 0, NBR 1, NTL 2, NTR 3, FBL 4, FBR 5, FTL 6, FTR 7
+        bool culled = box_in_front(c[3], c[1], c[0], mn, mx);        // Near:   NTR NBR NBL
+        culled = culled || box_in_front(c[6], c[4], c[5], mn, mx);   // Far:    FTL FBL FBR
+        culled = culled || box_in_front(c[4], c[0], c[1], mn, mx);   // Bottom: FBL NBL NBR
+        culled = culled || box_in_front(c[7], c[3], c[2], mn, mx);   // Top:    FTR NTR NTL
+        culled = culled || box_in_front(c[2], c[0], c[4], mn, mx);   // Left:   NTL NBL FBL
+        culled = culled || box_in_front(c[7], c[5], c[1], mn, mx);   // Right:  FTR FBR NBR
+        visible = !culled;
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, visible);
+    if ((threadIdx.x & 31) == 0 && i < p.n) p.vis_bits[i >> 5] = bits;
+}
+
+// ---- ordered stream compaction of the visible ids from the bitmask ------------------------------------
+constexpr int kScanBlock = 1024;  // words per block
+
+__global__ void __launch_bounds__(kScanBlock) compact_count_kernel(const uint32_t* __restrict__ bits, int64_t words,
+                                                                   int32_t* __restrict__ block_sums) {
+    __shared__ int warp_sums[32];
+    const int64_t w = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+    int v = w < words ? __popc(bits[w]) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int s = warp_sums[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
+    }
+}
+
+// single block: exclusive scan of the block sums in place; total -> count_out
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int32_t* block_sums, int num_blocks, int32_t* count_out) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < num_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < num_blocks ? block_sums[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int s = warp_tot[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, s, o);
+                if (threadIdx.x >= o) s += t;
+            }
+            warp_tot[threadIdx.x] = s;  // inclusive totals of the warps
+        }
+        __syncthreads();
+        const int warp_off = (threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0;
+        const int carry = carry_s;
+        if (i < num_blocks) block_sums[i] = carry + warp_off + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_off + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count_out[0] = carry_s;
+}
+
+__global__ void __launch_bounds__(kScanBlock) compact_scatter_kernel(const uint32_t* __restrict__ bits, int64_t words,
+                                                                     const int32_t* __restrict__ block_offsets,
+                                                                     int32_t* __restrict__ ids_out) {
+    __shared__ int warp_tot[32];
+    const int64_t w = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+    uint32_t word = w < words ? bits[w] : 0u;
+    const int v = __popc(word);
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int s = warp_tot[threadIdx.x];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (threadIdx.x >= o) s += t;
+        }
+        warp_tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+    int pos = block_offsets[blockIdx.x] + ((threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0) + inc - v;
+    while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        ids_out[pos++] = (int32_t)(w * 32 + b);
+    }
+}
+
+__global__ void pack_palettes_kernel(const float4* __restrict__ palette, int palette_vec4, const int32_t* __restrict__ ids,
+                                     const int32_t* __restrict__ count, int64_t capacity, float4* __restrict__ out) {
+    int64_t total = count[0];
+    if (total > capacity) total = capacity;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    for (int64_t i = warp; i < total; i += warps) {
+        const float4* src = palette + (size_t)ids[i] * palette_vec4;
+        float4* dst = out + (size_t)i * palette_vec4;
+        for (int k = lane; k < palette_vec4; k += 32) dst[k] = __ldg(src + k);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_cull(const CullParams& p, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    const int64_t blocks = (p.n + 255) / 256;
+    cull_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+size_t compact_scratch_ints(int64_t n) {
+    const int64_t words = (n + 31) / 32;
+    return (size_t)((words + kScanBlock - 1) / kScanBlock + 1);
+}
+
+cudaError_t launch_compact(const uint32_t* vis_bits, int64_t n, int32_t* ids_out, int32_t* count_out, int32_t* scratch,
+                           cudaStream_t stream, int* launches) {
+    if (n <= 0) return cudaMemsetAsync(count_out, 0, sizeof(int32_t), stream);
+    const int64_t words = (n + 31) / 32;
+    const int blocks = (int)((words + kScanBlock - 1) / kScanBlock);
+    compact_count_kernel<<<blocks, kScanBlock, 0, stream>>>(vis_bits, words, scratch);
+    compact_scan_kernel<<<1, 1024, 0, stream>>>(scratch, blocks, count_out);
+    compact_scatter_kernel<<<blocks, kScanBlock, 0, stream>>>(vis_bits, words, scratch, ids_out);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_palettes(const float* palette, int palette_floats, const int32_t* ids, const int32_t* count,
+                                 int64_t capacity, float* out, int num_sms, cudaStream_t stream) {
+    pack_palettes_kernel<<<num_sms * 4, 256, 0, stream>>>(reinterpret_cast<const float4*>(palette), palette_floats / 4, ids,
+                                                          count, capacity, reinterpret_cast<float4*>(out));
+    return cudaGetLastError();
+}
+
+}  // namespace dmk

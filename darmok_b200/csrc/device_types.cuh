@@ -1,0 +1,90 @@
+// device_types.cuh -- plain structs shared by the host side of the C ABI and the sm_100a kernels.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dmk {
+
+constexpr int kSoaFloats = 40;      // ozz SoaTransform: T.xyz R.xyzw S.xyz, 4 lanes each
+constexpr int kMaxLayers = 16;
+constexpr int kMaxPalette = 256;    // palette slots are packed as bytes in the skinning kernel
+constexpr uint16_t kIdleTask = 0xffffu;
+
+// Clip set re-laid out for per-track search: keys of one (clip, component, track) are contiguous and sorted.
+struct ClipSetDev {
+    const uint2* dir;        // [num_clips][3][P] : {first key, key count}
+    const float* ratio[3];   // key ratios per component (T, R, S)
+    const uint2* value[3];   // packed key values: T/S = 3 halves; R = 3 int16 + largest (2 bit) + sign (1 bit)
+    const int32_t* stream[3];// index of the key in the ozz key stream (what ozz's sampling cache stores)
+    const float* duration;   // [num_clips]
+    int num_clips;
+    int padded_tracks;       // P = 4 * num_soa
+};
+
+struct SkeletonDev {
+    const int16_t* parents;   // [J]
+    const uint16_t* schedule; // [rounds][32] local-to-model tasks: joint | column << 12, kIdleTask = none
+    int num_joints;           // J
+    int padded_joints;        // P
+    int num_soa;
+    int rounds;
+};
+
+struct ArmatureDev {
+    const int32_t* remap;     // [K] skeleton joint of armature joint k, -1 = unknown name
+    const float* inv_bind;    // [K][12] affine 3x4, column-major columns of 3 (c0 c1 c2 c3)
+    int num_joints;           // K
+};
+
+struct PoseParams {
+    ClipSetDev clips;
+    SkeletonDev skel;
+    ArmatureDev arm;
+    int64_t n;
+    int num_layers;
+    // layer state, [L][N]
+    const int32_t* clip;
+    float* ratio;
+    const float* weight;
+    const float* speed;
+    const uint8_t* loop;      // may be null (all loop)
+    uint8_t* looped;
+    float threshold;
+    float dt;
+    int advance;              // run the clip clocks before sampling
+    // outputs (null = skip)
+    float* palette;           // [N][K+1][16] column-major mat4
+    float* palette34;         // [N][K+1][12] row-major 3x4 (rows of 4), consumed by the skinning kernel
+    float* models;            // [N][J][16] left-handed model matrices
+    float* locals;            // [N][num_soa][40]
+    int32_t* key_indices;     // [N][L][3][P][2]
+    int32_t* error_flag;      // set to character index + 1 when a job would fail
+};
+
+struct SkinParams {
+    const float* palette34;   // [N][PS][12]
+    const float* pos;         // [Vpad][3]
+    const float* nrm;
+    const float* tan;
+    const float* weights;     // [Vpad][4]
+    const uint32_t* slots;    // [Vpad] 4 palette slots packed as bytes
+    float* out;               // [N][Vpad][9]
+    const int32_t* char_ids;  // optional indirection (visible characters), null = identity
+    const int32_t* char_count;// device count when char_ids != null
+    int64_t n;
+    int vpad;                 // vertices per character, multiple of 8
+    int palette_size;         // PS
+    int num_tiles;            // vertex tiles per character
+    int tile_vertices;        // multiple of 8
+};
+
+struct CullParams {
+    const float* world_inverse; // [n][16]
+    const float* bbox;          // [n][6]
+    int64_t n;
+    uint32_t* vis_bits;         // [ceil(n/32)]
+    float corners[24];          // camera frustum corners (world space), Frustum::CornerType order
+};
+
+}  // namespace dmk

@@ -1,0 +1,35 @@
+// kernels.cuh -- launchers of the sm_100a kernels (one per .cu translation unit).
+#pragma once
+
+#include "device_types.cuh"
+
+namespace dmk {
+
+// K1..K3 (pose_kernel.cu, built with -fmad=false)
+size_t pose_smem_bytes(const PoseParams& p);
+cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream);
+
+// K4 (cull_kernel.cu, built with -fmad=false): visibility bitmask; then ordered compaction of visible ids
+cudaError_t launch_cull(const CullParams& p, cudaStream_t stream);
+// ids_out[i] = i-th visible instance (ascending); count_out[0] = number of visible; scratch >= ceil(words/1024)+1 ints
+cudaError_t launch_compact(const uint32_t* vis_bits, int64_t n, int32_t* ids_out, int32_t* count_out,
+                           int32_t* scratch, cudaStream_t stream, int* launches);
+size_t compact_scratch_ints(int64_t n);
+
+// K5 (skin_kernel.cu)
+struct SkinPlan {
+    int threads;        // threads per block (multiple of 32)
+    int num_tiles;      // vertex tiles per character
+    int tile_vertices;  // vertices per tile (multiple of 8)
+    int grid;           // persistent blocks
+    int replicas;       // palette replicas in shared memory (bank-conflict-free gathers)
+    size_t smem;
+};
+SkinPlan plan_skin(int vpad, int palette_size, int num_sms);
+cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t stream);
+
+// K6 payload: gather palettes of the listed characters into a dense buffer
+cudaError_t launch_pack_palettes(const float* palette, int palette_floats, const int32_t* ids, const int32_t* count,
+                                 int64_t capacity, float* out, int num_sms, cudaStream_t stream);
+
+}  // namespace dmk

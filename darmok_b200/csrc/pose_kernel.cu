@@ -1,0 +1,414 @@
+// pose_kernel.cu -- K1..K3: clip clock + keyframe sampling + layer blend + local-to-model + skin palette.
+//
+// One warp per character.  Replaces, per character and per tick (paths relative to the darmok repository):
+//   OzzSkeletalAnimatorAnimationState::update  src/skeleton_ozz.cpp:411-440   (clip clock, ozz SamplingJob)
+//   BlendingJob in state/transition update     src/skeleton_ozz.cpp:556-608, :709-724
+//   LocalToModelJob in SkeletalAnimatorImpl    src/skeleton_ozz.cpp:1034-1039
+//   getJointModelMatrix + palette build        src/skeleton_ozz.cpp:962-977, src/skeleton.cpp:236-249
+//
+// Arithmetic follows the ozz-animation 0.14 scalar ("simd_ref") semantics operation by operation so that key
+// indices are identical and matrices agree with the CPU restatement: this TU is compiled with -fmad=false
+// (no contraction), IEEE division and square root (-prec-div/-prec-sqrt defaults), no flush-to-zero.
+//
+// Data layout: key tracks are SoA per (clip, component, track) and shared by all characters (L1/L2 resident);
+// the per-skeleton tables (parents, level-order schedule, remap, inverse binds) are staged in shared memory once
+// per persistent block; hierarchy concatenation runs level by level, one (joint, column) task per lane.
+#include "device_types.cuh"
+#include "kernels.cuh"
+
+#include <cuda_fp16.h>
+
+namespace dmk {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+
+__device__ __forceinline__ float rcp_exact(float x) { return __fdiv_rn(1.f, x); }
+__device__ __forceinline__ float rsqrt_exact(float x) { return __fdiv_rn(1.f, __fsqrt_rn(x)); }
+
+// Stateless equivalent of ozz's sampling cursor: right = first key (index >= 1) of the
+// track with ratio > t, else the last key; left = right - 1.
+__device__ __forceinline__ void find_keys(const float* __restrict__ ratio, uint2 d, float t, int& left, int& right) {
+    const float* base = ratio + d.x;
+    int a = 1, b = (int)d.y - 1;
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (__ldg(base + m) > t) b = m; else a = m + 1;
+    }
+    right = (int)d.x + a;
+    left = right - 1;
+}
+
+__device__ __forceinline__ float half_bits_to_float(unsigned h) {
+    return __half2float(__ushort_as_half((unsigned short)h));
+}
+
+// Float3 track (translation or scale): DecompressFloat3 + Lerp
+__device__ __forceinline__ void sample_f3(const ClipSetDev& cs, int comp, int clip, int track, float t, float out[3],
+                                          int32_t* key_out) {
+    const uint2 d = __ldg(cs.dir + (size_t)(clip * 3 + comp) * cs.padded_tracks + track);
+    int l, r;
+    find_keys(cs.ratio[comp], d, t, l, r);
+    const float r0 = __ldg(cs.ratio[comp] + l), r1 = __ldg(cs.ratio[comp] + r);
+    const uint2 v0 = __ldg(cs.value[comp] + l), v1 = __ldg(cs.value[comp] + r);
+    if (key_out) {
+        key_out[0] = __ldg(cs.stream[comp] + l);
+        key_out[1] = __ldg(cs.stream[comp] + r);
+    }
+    const float alpha = (t - r0) * rcp_exact(r1 - r0);
+    const float a[3] = {half_bits_to_float(v0.x & 0xffffu), half_bits_to_float(v0.x >> 16), half_bits_to_float(v0.y & 0xffffu)};
+    const float b[3] = {half_bits_to_float(v1.x & 0xffffu), half_bits_to_float(v1.x >> 16), half_bits_to_float(v1.y & 0xffffu)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = (b[c] - a[c]) * alpha + a[c];
+}
+
+// DecompressQuaternion (Appendix A.4) for one key
+__device__ __forceinline__ void decode_quat(uint2 v, float q[4]) {
+    const float kInt2Float = 1.f / (32767.f * 1.4142135623730950488016887242097f);
+    const float f0 = kInt2Float * (float)(short)(v.x & 0xffffu);
+    const float f1 = kInt2Float * (float)(short)(v.x >> 16);
+    const float f2 = kInt2Float * (float)(short)(v.y & 0xffffu);
+    const unsigned largest = (v.y >> 16) & 3u;
+    // the rebuilt lane is zero in ozz's dot product, so the sum is ((f0^2 + f1^2) + f2^2) for every mapping
+    const float dot = (f0 * f0 + f1 * f1) + f2 * f2;
+    float ww0 = 1.f - dot;
+    ww0 = (ww0 > 1e-16f) ? ww0 : 1e-16f;
+    float w0 = ww0 * rsqrt_exact(ww0);
+    if ((v.y >> 18) & 1u) w0 = -w0;
+    q[0] = largest == 0 ? w0 : f0;
+    q[1] = largest == 0 ? f0 : (largest == 1 ? w0 : f1);
+    q[2] = largest <= 1 ? f1 : (largest == 2 ? w0 : f2);
+    q[3] = largest == 3 ? w0 : f2;
+}
+
+// rotation track: decode both keys, NLerpEst
+__device__ __forceinline__ void sample_quat(const ClipSetDev& cs, int clip, int track, float t, float out[4],
+                                            int32_t* key_out) {
+    const uint2 d = __ldg(cs.dir + (size_t)(clip * 3 + 1) * cs.padded_tracks + track);
+    int l, r;
+    find_keys(cs.ratio[1], d, t, l, r);
+    const float r0 = __ldg(cs.ratio[1] + l), r1 = __ldg(cs.ratio[1] + r);
+    const uint2 v0 = __ldg(cs.value[1] + l), v1 = __ldg(cs.value[1] + r);
+    if (key_out) {
+        key_out[0] = __ldg(cs.stream[1] + l);
+        key_out[1] = __ldg(cs.stream[1] + r);
+    }
+    const float alpha = (t - r0) * rcp_exact(r1 - r0);
+    float a[4], b[4], q[4];
+    decode_quat(v0, a);
+    decode_quat(v1, b);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) q[c] = (b[c] - a[c]) * alpha + a[c];
+    const float len2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const float inv_len = rsqrt_exact(len2);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c] = q[c] * inv_len;
+}
+
+struct Xform {  // one joint's local transform
+    float t[3], r[4], s[3];
+};
+
+__device__ __forceinline__ void sample_joint(const ClipSetDev& cs, int clip, int track, float ratio, Xform& x,
+                                             int32_t* key_out /* [3][P][2] base for this layer, or null */) {
+    const int P = cs.padded_tracks;
+    sample_f3(cs, 0, clip, track, ratio, x.t, key_out ? key_out + ((size_t)0 * P + track) * 2 : nullptr);
+    sample_quat(cs, clip, track, ratio, x.r, key_out ? key_out + ((size_t)1 * P + track) * 2 : nullptr);
+    sample_f3(cs, 2, clip, track, ratio, x.s, key_out ? key_out + ((size_t)2 * P + track) * 2 : nullptr);
+}
+
+// OZZ_BLEND_N_PASS for one joint
+__device__ __forceinline__ void blend_n_pass(Xform& acc, const Xform& in, float w) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc.t[c] = acc.t[c] + in.t[c] * w;
+    const float dot = acc.r[0] * in.r[0] + acc.r[1] * in.r[1] + acc.r[2] * in.r[2] + acc.r[3] * in.r[3];
+    const bool neg = (__float_as_uint(dot) >> 31) != 0u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float q = neg ? -in.r[c] : in.r[c];
+        acc.r[c] = acc.r[c] + q * w;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc.s[c] = acc.s[c] + in.s[c] * w;
+}
+
+// SoaFloat4x4::FromAffine for one joint -> 3x4 affine, columns of 3 (m[c*3 + r])
+__device__ __forceinline__ void from_affine(const Xform& x, float* m) {
+    const float qx = x.r[0], qy = x.r[1], qz = x.r[2], qw = x.r[3];
+    const float xx = qx * qx, xy = qx * qy, xz = qx * qz, xw = qx * qw;
+    const float yy = qy * qy, yz = qy * qz, yw = qy * qw;
+    const float zz = qz * qz, zw = qz * qw;
+    const float one = 1.f, two = 2.f;
+    m[0] = x.s[0] * (one - two * (yy + zz));
+    m[1] = x.s[0] * two * (xy + zw);
+    m[2] = x.s[0] * two * (xz - yw);
+    m[3] = x.s[1] * two * (xy - zw);
+    m[4] = x.s[1] * (one - two * (xx + zz));
+    m[5] = x.s[1] * two * (yz + xw);
+    m[6] = x.s[2] * two * (xz + yw);
+    m[7] = x.s[2] * two * (yz - xw);
+    m[8] = x.s[2] * (one - two * (xx + yy));
+    m[9] = x.t[0];
+    m[10] = x.t[1];
+    m[11] = x.t[2];
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PoseParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int J = p.skel.num_joints, P = p.skel.padded_joints, K = p.arm.num_joints, PS = K + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- shared tables, staged once per persistent block ----
+    float* s_inv_bind = reinterpret_cast<float*>(smem_raw);                   // [K][12]
+    float* s_identity = s_inv_bind + (size_t)K * 12;                          // [12] (+4 pad)
+    int32_t* s_remap = reinterpret_cast<int32_t*>(s_identity + 16);           // [K]
+    int16_t* s_parents = reinterpret_cast<int16_t*>(s_remap + ((K + 3) & ~3)); // [P]
+    uint16_t* s_sched = reinterpret_cast<uint16_t*>(s_parents + ((P + 7) & ~7)); // [rounds][32]
+    const int regA = max(P * 12, PS * 16);                                    // locals -> mat4 palette staging
+    const int regB = P * 12;                                                  // model matrices
+    const int regC = PS * 12;                                                 // 3x4 palette staging
+    const int per_warp = (regA + regB + regC + 3) & ~3;
+    float* s_warp0 = reinterpret_cast<float*>(
+        (reinterpret_cast<uintptr_t>(s_sched + (size_t)p.skel.rounds * 32) + 15) & ~uintptr_t(15));
+    float* s_loc = s_warp0 + (size_t)warp * per_warp;  // region A
+    float* s_mod = s_loc + regA;                        // region B
+    float* s_p34 = s_mod + regB;                        // region C
+
+    for (int i = threadIdx.x; i < K * 12; i += blockDim.x) s_inv_bind[i] = p.arm.inv_bind[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_remap[i] = p.arm.remap[i];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_parents[i] = i < J ? p.skel.parents[i] : (int16_t)-1;
+    for (int i = threadIdx.x; i < p.skel.rounds * 32; i += blockDim.x) s_sched[i] = p.skel.schedule[i];
+    if (threadIdx.x < 12) s_identity[threadIdx.x] = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.f : 0.f;
+    __syncthreads();
+
+    const int L = p.num_layers;
+    const int64_t n = p.n;
+    const int64_t warps_total = (int64_t)gridDim.x * kWarpsPerBlock;
+
+    for (int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + warp; c < n; c += warps_total) {
+        // ---- layer state + clip clock: lane l owns layer l, values are broadcast with shuffles ----
+        int my_clip = 0;
+        float my_ratio = 0.f, my_weight = 0.f;
+        bool my_bad = false;
+        if (lane < L) {
+            const int64_t idx = (int64_t)lane * n + c;
+            int ci = p.clip[idx];
+            float t = p.ratio[idx];
+            if (ci < 0 || ci >= p.clips.num_clips) { my_bad = true; ci = 0; }
+            if (p.advance) {
+                // OzzSkeletalAnimatorAnimationState::update (src/skeleton_ozz.cpp:411-428)
+                const bool loop = p.loop ? p.loop[idx] != 0 : true;
+                bool looped = p.looped[idx] != 0;
+                if (!(looped && !loop)) {
+                    float sp = p.speed[idx];
+                    sp = sp == 0.f ? 1.f : sp;
+                    const float duration = __fdiv_rn(__ldg(p.clips.duration + ci), sp);
+                    const float norm_time = t + __fdiv_rn(p.dt, duration);
+                    looped = norm_time > 1.f;
+                    if (!(looped && !loop)) t = fmodf(norm_time, 1.f);
+                    p.looped[idx] = looped ? 1 : 0;
+                    p.ratio[idx] = t;
+                }
+            }
+            // SamplingJob::Run: ratio clamped to [0, 1]
+            float tc = t;
+            tc = (tc < 1.f) ? tc : 1.f;
+            tc = (tc > 0.f) ? tc : 0.f;
+            my_clip = ci;
+            my_ratio = tc;
+            my_weight = p.weight[idx];
+        }
+        if (__any_sync(0xffffffffu, my_bad)) {
+            if (lane == 0) atomicCAS(p.error_flag, 0, (int32_t)min(c + 1, (int64_t)0x7fffffff));
+            continue;
+        }
+        // BlendingJob bookkeeping is independent of the joint: accumulated weight, passes, rest-pose weight
+        float accumulated = 0.f;
+        int num_passes = 0;
+        if (L > 1) {
+            for (int l = 0; l < L; ++l) {
+                const float w = __shfl_sync(0xffffffffu, my_weight, l);
+                if (!(w <= 0.f)) { accumulated += w; ++num_passes; }
+            }
+        }
+        const float bp_weight = p.threshold - accumulated;
+        const bool need_rest = (L > 1) && (bp_weight > 0.f);
+        float norm_weight = accumulated;
+        if (need_rest) norm_weight = (num_passes == 0) ? 1.f : p.threshold;
+        const float inv_weight = rcp_exact(norm_weight);
+
+        int32_t* key_base = p.key_indices ? p.key_indices + (size_t)c * L * 3 * P * 2 : nullptr;
+
+        // ---- K1: sample + blend, lane <-> joint ----
+        for (int j0 = 0; j0 < P; j0 += 32) {
+            const int j = j0 + lane;
+            const bool active = j < P;   // all lanes stay in the loop: layer state is broadcast by shuffle
+            const int jt = active ? j : P - 1;
+            Xform acc;
+            if (L == 1) {
+                // a state with a single clip never runs BlendingJob (src/skeleton_ozz.cpp:552-555, :617-624)
+                const int c0 = __shfl_sync(0xffffffffu, my_clip, 0);
+                const float t0 = __shfl_sync(0xffffffffu, my_ratio, 0);
+                sample_joint(p.clips, c0, jt, t0, acc, active ? key_base : nullptr);
+            } else {
+                Xform rest;
+                bool have_rest = false;
+                int pass = 0;
+#pragma unroll 1
+                for (int l = 0; l < L; ++l) {
+                    const float w = __shfl_sync(0xffffffffu, my_weight, l);
+                    const int cl = __shfl_sync(0xffffffffu, my_clip, l);
+                    const float tl = __shfl_sync(0xffffffffu, my_ratio, l);
+                    const bool contributes = !(w <= 0.f);
+                    const bool is_rest = need_rest && l == 0;
+                    if (!contributes && !is_rest && !key_base) continue;
+                    Xform in;
+                    sample_joint(p.clips, cl, jt, tl, in, (key_base && active) ? key_base + (size_t)l * 3 * P * 2 : nullptr);
+                    if (is_rest) { rest = in; have_rest = true; }
+                    if (!contributes) continue;
+                    if (pass == 0) {  // OZZ_BLEND_1ST_PASS
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) acc.t[k] = in.t[k] * w;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc.r[k] = in.r[k] * w;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) acc.s[k] = in.s[k] * w;
+                    } else {
+                        blend_n_pass(acc, in, w);
+                    }
+                    ++pass;
+                }
+                if (need_rest && have_rest) {  // BlendRestPose
+                    if (pass == 0) acc = rest;
+                    else blend_n_pass(acc, rest, bp_weight);
+                }
+                // Normalize
+                const float len2 = acc.r[0] * acc.r[0] + acc.r[1] * acc.r[1] + acc.r[2] * acc.r[2] + acc.r[3] * acc.r[3];
+                const float inv_len = rsqrt_exact(len2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc.r[k] = acc.r[k] * inv_len;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { acc.t[k] = acc.t[k] * inv_weight; acc.s[k] = acc.s[k] * inv_weight; }
+            }
+            if (!active) continue;
+            if (p.locals) {
+                float* o = p.locals + ((size_t)c * p.skel.num_soa + (j >> 2)) * kSoaFloats + (j & 3);
+                o[0] = acc.t[0]; o[4] = acc.t[1]; o[8] = acc.t[2];
+                o[12] = acc.r[0]; o[16] = acc.r[1]; o[20] = acc.r[2]; o[24] = acc.r[3];
+                o[28] = acc.s[0]; o[32] = acc.s[1]; o[36] = acc.s[2];
+            }
+            from_affine(acc, s_loc + (size_t)j * 12);
+        }
+        __syncwarp();
+
+        // ---- K2: local-to-model, level order; one (joint, column) per lane per round ----
+        for (int rd = 0; rd < p.skel.rounds; ++rd) {
+            const unsigned task = s_sched[rd * 32 + lane];
+            if (task != kIdleTask) {
+                const int j = task & 0xfff, col = task >> 12;
+                const int parent = s_parents[j];
+                const float* pm = parent < 0 ? s_identity : s_mod + (size_t)parent * 12;
+                const float* lc = s_loc + (size_t)j * 12 + col * 3;
+                const float l0 = lc[0], l1 = lc[1], l2 = lc[2], l3 = col == 3 ? 1.f : 0.f;
+                float* o = s_mod + (size_t)j * 12 + col * 3;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)  // ozz Float4x4 product: (a0*x + a1*y) + (a2*z + a3*w)
+                    o[r] = (pm[r] * l0 + pm[3 + r] * l1) + (pm[6 + r] * l2 + pm[9 + r] * l3);
+            }
+            __syncwarp();
+        }
+
+        // ---- K3: flip handedness + palette = model * inverse bind ----
+        float* s_pal = s_loc;  // locals are dead: region A becomes the mat4 palette staging
+        if (p.models) {
+            for (int j = lane; j < J; j += 32) {
+                const float* m = s_mod + (size_t)j * 12;
+                float* o = p.models + ((size_t)c * J + j) * 16;
+                o[0] = m[0]; o[1] = m[1]; o[2] = -m[2]; o[3] = 0.f;
+                o[4] = m[3]; o[5] = m[4]; o[6] = -m[5]; o[7] = 0.f;
+                o[8] = -m[6]; o[9] = -m[7]; o[10] = m[8]; o[11] = 0.f;
+                o[12] = m[9]; o[13] = m[10]; o[14] = -m[11]; o[15] = 1.f;
+            }
+        }
+        if (p.palette || p.palette34) {
+            if (lane < 16) s_pal[lane] = (lane % 5 == 0) ? 1.f : 0.f;  // slot 0 = mat4(1)
+            if (lane < 12) s_p34[lane] = (lane % 5 == 0) ? 1.f : 0.f;  // rows (1,0,0,0) (0,1,0,0) (0,0,1,0)
+            for (int k = lane; k < K; k += 32) {
+                const int jm = s_remap[k];
+                float m[12];
+                if (jm >= 0) {
+                    const float* src = s_mod + (size_t)jm * 12;  // Math::flipHandedness: Z * M * Z
+                    m[0] = src[0]; m[1] = src[1]; m[2] = -src[2];
+                    m[3] = src[3]; m[4] = src[4]; m[5] = -src[5];
+                    m[6] = -src[6]; m[7] = -src[7]; m[8] = src[8];
+                    m[9] = src[9]; m[10] = src[10]; m[11] = -src[11];
+                } else {  // unknown joint name: getJointModelMatrix returns mat4(1)
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) m[e] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
+                }
+                const float* b = s_inv_bind + (size_t)k * 12;
+                float* o = s_pal + (size_t)(k + 1) * 16;
+                float* o34 = s_p34 + (size_t)(k + 1) * 12;
+#pragma unroll
+                for (int col = 0; col < 4; ++col) {
+                    const float b0 = b[col * 3 + 0], b1 = b[col * 3 + 1], b2 = b[col * 3 + 2];
+                    const float b3 = col == 3 ? 1.f : 0.f;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {  // glm mat4 * mat4: ((A0*b0 + A1*b1) + A2*b2) + A3*b3
+                        const float v = ((m[r] * b0 + m[3 + r] * b1) + m[6 + r] * b2) + m[9 + r] * b3;
+                        o[col * 4 + r] = v;
+                        o34[r * 4 + col] = v;
+                    }
+                    o[col * 4 + 3] = b3;
+                }
+            }
+            __syncwarp();
+            if (p.palette) {
+                float4* dst = reinterpret_cast<float4*>(p.palette + (size_t)c * PS * 16);
+                const float4* src = reinterpret_cast<const float4*>(s_pal);
+                for (int i = lane; i < PS * 4; i += 32) dst[i] = src[i];
+            }
+            if (p.palette34) {
+                float4* dst = reinterpret_cast<float4*>(p.palette34 + (size_t)c * PS * 12);
+                const float4* src = reinterpret_cast<const float4*>(s_p34);
+                for (int i = lane; i < PS * 3; i += 32) dst[i] = src[i];
+            }
+        }
+        __syncwarp();  // staging regions are reused by the next character
+    }
+}
+
+}  // namespace
+
+size_t pose_smem_bytes(const PoseParams& p) {
+    const int P = p.skel.padded_joints, K = p.arm.num_joints, PS = K + 1;
+    size_t b = 0;
+    b += (size_t)K * 12 * 4 + 16 * 4;
+    b += (size_t)((K + 3) & ~3) * 4;
+    b += (size_t)((P + 7) & ~7) * 2;
+    b += (size_t)p.skel.rounds * 32 * 2;
+    b += 16;
+    const int regA = P * 12 > PS * 16 ? P * 12 : PS * 16;
+    const size_t per_warp = (size_t)((regA + P * 12 + PS * 12 + 3) & ~3) * 4;
+    b += per_warp * kWarpsPerBlock;
+    return b;
+}
+
+cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    const size_t smem = pose_smem_bytes(p);
+    cudaError_t e = cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pose_kernel, kWarpsPerBlock * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    int64_t blocks = (p.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int64_t cap = (int64_t)num_sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    pose_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace dmk

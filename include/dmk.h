@@ -1,0 +1,199 @@
+/*
+ * dmk.h -- C ABI of libdarmok_b200.so: darmok's per-frame character hot path on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  darmok has no C ABI of its own: the seam is the ozz backend translation
+ * unit (src/skeleton_ozz.cpp, selected by DARMOK_BUILD_OZZ, CMakeLists.txt:366-377) plus FrustumCuller
+ * (src/culling.cpp).  A replacement TU (darmok_b200/host/skeleton_b200.cpp) provides
+ * the same C++ symbols and forwards to the entry points below.  Every entry point cites the reference
+ * interface it replaces (paths relative to the darmok repository).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; no exceptions cross this boundary
+ *   - every function returns dmk_status (0 = ok); dmk_last_error(ctx) holds the message, using the
+ *     reference's own error strings where one exists (src/skeleton_ozz.cpp:39,212,436,607,1038)
+ *   - matrices are column-major float[16] (glm::mat4); ozz data is right-handed, outputs that leave the
+ *     animator are left-handed exactly as OzzUtils::convert does (src/skeleton_ozz.cpp:21-25)
+ *   - a context is single-caller (the reference calls this path from the main thread only,
+ *     src/app.cpp:1050-1081); work is asynchronous on the context's CUDA stream until dmk_sync or a getter
+ *   - host input arrays are copied at the call; "_dev" arguments are device pointers owned by the caller
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with DMK_ERR_CUDA
+ */
+#ifndef DMK_H
+#define DMK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DMK_API __declspec(dllexport)
+#else
+#define DMK_API __attribute__((visibility("default")))
+#endif
+
+typedef int dmk_status;
+enum {
+    DMK_OK = 0,
+    DMK_ERR_INVALID = 1,     /* bad argument */
+    DMK_ERR_FORMAT = 2,      /* archive rejected ("archive does not contain the type", ...) */
+    DMK_ERR_CUDA = 3,        /* CUDA runtime failure / no device */
+    DMK_ERR_UNSUPPORTED = 4, /* valid in the reference but outside this build (see message) */
+    DMK_ERR_JOB = 5          /* "error in the sampling job" / "blending job" / "model job" */
+};
+
+typedef struct dmk_context_s* dmk_context_t;
+typedef struct dmk_skeleton_s* dmk_skeleton_t; /* replaces SkeletonImpl          src/detail/skeleton_ozz.hpp:19-28 */
+typedef struct dmk_clip_s* dmk_clip_t;         /* replaces SkeletalAnimationImpl src/detail/skeleton_ozz.hpp:30-38 */
+typedef struct dmk_clipset_s* dmk_clipset_t;   /* replaces SkeletalAnimationMap  include/darmok/skeleton.hpp:82 */
+typedef struct dmk_armature_s* dmk_armature_t; /* replaces Armature              include/darmok/skeleton.hpp:369-384 */
+typedef struct dmk_mesh_s* dmk_mesh_t;         /* skinned vertex streams of MeshData::exportData, src/mesh_core.cpp:323-365 */
+typedef struct dmk_crowd_s* dmk_crowd_t;       /* N x (SkeletalAnimatorImpl + Skinnable + BoundingBox/Transform) */
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+/* cuda_stream: a cudaStream_t owned by the caller (e.g. torch's current stream) or NULL to create one. */
+DMK_API dmk_status dmk_context_create(int device, void* cuda_stream, dmk_context_t* out);
+DMK_API void dmk_context_destroy(dmk_context_t ctx);
+DMK_API const char* dmk_last_error(dmk_context_t ctx); /* ctx may be NULL: last creation error */
+DMK_API dmk_status dmk_sync(dmk_context_t ctx);
+DMK_API void* dmk_context_stream(dmk_context_t ctx);
+DMK_API const char* dmk_version(void);
+/* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
+DMK_API uint64_t dmk_context_launch_count(dmk_context_t ctx);
+
+/* ---- assets -------------------------------------------------------------------------------------------- */
+/* OzzSkeletonLoader::operator() -> OzzUtils::loadFromData<ozz::animation::Skeleton> (src/skeleton_ozz.cpp:27-44,
+ * :191-200): bytes of an ozz archive holding an "ozz-skeleton" (version 2). */
+DMK_API dmk_status dmk_skeleton_load_ozz(dmk_context_t ctx, const void* bytes, size_t size, dmk_skeleton_t* out);
+DMK_API void dmk_skeleton_destroy(dmk_skeleton_t skel);
+DMK_API int dmk_skeleton_num_joints(dmk_skeleton_t skel);                  /* ozz Skeleton::num_joints   (:57) */
+DMK_API const char* dmk_skeleton_joint_name(dmk_skeleton_t skel, int i);   /* ozz Skeleton::joint_names  (:968) */
+DMK_API int dmk_skeleton_joint_parent(dmk_skeleton_t skel, int i);         /* ozz Skeleton::joint_parents (:983) */
+DMK_API int dmk_skeleton_find_joint(dmk_skeleton_t skel, const char* name); /* linear scan of :968-975; -1 if absent */
+
+/* OzzSkeletalAnimationLoader::operator() (src/skeleton_ozz.cpp:207-216): "ozz-animation" archive (version 6). */
+DMK_API dmk_status dmk_clip_load_ozz(dmk_context_t ctx, const void* bytes, size_t size, dmk_clip_t* out);
+DMK_API void dmk_clip_destroy(dmk_clip_t clip);
+DMK_API float dmk_clip_duration(dmk_clip_t clip);     /* SkeletalAnimation::getDuration (src/skeleton_ozz.cpp:116-119) */
+DMK_API const char* dmk_clip_name(dmk_clip_t clip);   /* SkeletalAnimation::getName     (src/skeleton_ozz.cpp:111-114) */
+DMK_API int dmk_clip_num_tracks(dmk_clip_t clip);
+
+/* The clips an animator may play (SkeletalAnimator::AnimationMap, src/skeleton_ozz.cpp:893-899), re-laid out
+ * into per-track SoA key arrays on the device.  Every clip must have the skeleton's SoA track count. */
+DMK_API dmk_status dmk_clipset_create(dmk_context_t ctx, dmk_skeleton_t skel, const dmk_clip_t* clips, int num_clips,
+                                      dmk_clipset_t* out);
+DMK_API void dmk_clipset_destroy(dmk_clipset_t set);
+
+/* Armature(std::vector<ArmatureJoint>) (include/darmok/skeleton.hpp:363-384): joint names + inverse bind poses.
+ * The name -> skeleton joint lookup of getJointModelMatrix (src/skeleton_ozz.cpp:962-977) is resolved here once;
+ * an unknown name keeps the reference behaviour (identity model matrix).  inv_bind must be affine (bottom row
+ * 0,0,0,1), otherwise DMK_ERR_UNSUPPORTED.  num_joints + 1 must be <= 256 (reference cap: 64,
+ * DARMOK_SKELETON_MAX_BONES include/darmok/skeleton.hpp:21-23). */
+DMK_API dmk_status dmk_armature_create(dmk_context_t ctx, dmk_skeleton_t skel, const char* const* joint_names,
+                                       const float* inv_bind, int num_joints, dmk_armature_t* out);
+DMK_API void dmk_armature_destroy(dmk_armature_t arm);
+DMK_API int dmk_armature_palette_size(dmk_armature_t arm); /* num_joints + 1 (slot 0 = identity, src/skeleton.cpp:238) */
+
+/* Vertex streams in the layout MeshData::exportData writes (src/mesh_core.cpp:323-365, src/vertex.cpp:228-235):
+ * position/normal/tangent float3; indices float4 (bone index into the armature, -1 = unused); weights float4. */
+DMK_API dmk_status dmk_mesh_create(dmk_context_t ctx, const float* position, const float* normal, const float* tangent,
+                                   const float* indices, const float* weights, int num_vertices, int palette_size,
+                                   dmk_mesh_t* out);
+DMK_API void dmk_mesh_destroy(dmk_mesh_t mesh);
+DMK_API int dmk_mesh_num_vertices(dmk_mesh_t mesh);
+DMK_API int dmk_mesh_vertex_pitch(dmk_mesh_t mesh); /* vertices per character in the skinned buffer (V rounded up to 8) */
+
+/* ---- crowd: N characters sharing skeleton / clip set / armature / mesh ---------------------------------- */
+/* armature and mesh may be NULL (palette-only or animation-only crowds). */
+DMK_API dmk_status dmk_crowd_create(dmk_context_t ctx, dmk_skeleton_t skel, dmk_clipset_t clips, dmk_armature_t arm,
+                                    dmk_mesh_t mesh, int64_t num_characters, int max_layers, dmk_crowd_t* out);
+DMK_API void dmk_crowd_destroy(dmk_crowd_t crowd);
+DMK_API int64_t dmk_crowd_size(dmk_crowd_t crowd);
+
+/* Optional per-character outputs that only the host-side getters need (they cost HBM writes per step):
+ * models -> dmk_crowd_get_models, locals -> dmk_crowd_get_locals, key indices -> dmk_crowd_get_key_indices. */
+enum { DMK_OUT_MODELS = 1, DMK_OUT_LOCALS = 2, DMK_OUT_KEY_INDICES = 4 };
+DMK_API dmk_status dmk_crowd_enable_outputs(dmk_crowd_t crowd, uint32_t outputs);
+
+/* Layer state of every character, arrays of [num_layers][N] (layer-major): what the animator state machine
+ * resolves each tick into BlendingJob::Layer{weight, transform} (src/skeleton_ozz.cpp:593-603, :709-714) with
+ * transform = SamplingJob(clip, ratio) (:429-437).  speed = clip speed / state speed product used by the device
+ * clip clock; loop = SkeletalAnimatorAnimation.loop (assets/protobuf/skeleton.proto:18-23), NULL = all looping.
+ * threshold = BlendingJob::threshold (state: definition, :559; transition: bx::kFloatSmallest, :718).
+ * Rest pose of the blend = layer 0 (:719; :600-603 when no clip sits at (0,0)). */
+DMK_API dmk_status dmk_crowd_set_layers(dmk_crowd_t crowd, int num_layers, const int32_t* clip, const float* ratio,
+                                        const float* weight, const float* speed, const uint8_t* loop, float threshold);
+/* per-frame variant for a host-side state machine: pinned staging + async copy of clip/ratio/weight only */
+DMK_API dmk_status dmk_crowd_update_layers(dmk_crowd_t crowd, int num_layers, const int32_t* clip, const float* ratio,
+                                           const float* weight);
+
+/* Transform::getWorldInverse (src/transform.cpp:286-309) + BoundingBox (assets/protobuf/shape.proto:7-10) of each
+ * character entity: world_inverse [N][16], bbox [N][6] = min.xyz, max.xyz (local space). */
+DMK_API dmk_status dmk_crowd_set_instances(dmk_crowd_t crowd, const float* world_inverse, const float* bbox);
+
+/* Camera::getViewProjectionMatrix (src/camera.cpp:196-199) -> Frustum{proj * view} (src/culling.cpp:268,
+ * src/shape.cpp:1141-1163), computed on the host in glm operation order.  near_depth =
+ * Math::getNormalizedNearDepth() (src/math.cpp:32-36): 0, or -1 with homogeneous depth. */
+DMK_API dmk_status dmk_crowd_set_camera(dmk_crowd_t crowd, const float* view_proj, float near_depth);
+/* same, from 8 precomputed frustum corners in Frustum::CornerType order (include/darmok/shape.hpp:372-383) */
+DMK_API dmk_status dmk_crowd_set_frustum_corners(dmk_crowd_t crowd, const float* corners);
+
+enum {
+    DMK_STEP_ADVANCE = 1,   /* clip clocks: OzzSkeletalAnimatorAnimationState::update (src/skeleton_ozz.cpp:411-428) */
+    DMK_STEP_POSE = 2,      /* SamplingJob + BlendingJob + LocalToModelJob + palette (a2, a5, a6, a7, a8) */
+    DMK_STEP_CULL = 4,      /* FrustumCuller::updateCulled (src/culling.cpp:264-285) */
+    DMK_STEP_SKIN = 8,      /* applySkinning for every vertex (darmok_skinning.inc.slang:5-28) */
+    DMK_STEP_SKIN_VISIBLE_ONLY = 16, /* with CULL+SKIN: skin only characters FrustumCuller would not cull */
+    DMK_STEP_ALL = 1 | 2 | 4 | 8
+};
+/* One frame for the whole crowd: replaces the per-entity loops SkeletalAnimationSceneComponent::update
+ * (src/skeleton.cpp:159-184), FrustumCuller::update (src/culling.cpp:258-262) and, per renderable,
+ * SkeletalAnimationRenderComponent::beforeRenderEntity (src/skeleton.cpp:223-251) + the LBS vertex stage. */
+DMK_API dmk_status dmk_crowd_step(dmk_crowd_t crowd, float dt, uint32_t flags);
+
+/* ---- results (device pointers stay valid until the crowd is destroyed) ---------------------------------- */
+/* u_skinning per character: [N][palette_size][16] column-major mat4, slot 0 identity (src/skeleton.cpp:237-249) */
+DMK_API const float* dmk_crowd_palette_dev(dmk_crowd_t crowd);
+/* skinned vertices: [N][vertex_pitch][9] = position.xyz, normal.xyz, tangent.xyz (forward.slang:33-38) */
+DMK_API const float* dmk_crowd_skinned_dev(dmk_crowd_t crowd);
+/* visibility bitmask, bit (i % 32) of word (i / 32) set when character i is NOT culled */
+DMK_API const uint32_t* dmk_crowd_visibility_dev(dmk_crowd_t crowd);
+/* ascending ids of the visible characters and their count (device side; filled by a CULL step) */
+DMK_API const int32_t* dmk_crowd_visible_ids_dev(dmk_crowd_t crowd);
+DMK_API const int32_t* dmk_crowd_visible_count_dev(dmk_crowd_t crowd);
+
+/* Host getters (synchronise the stream).  first/count select a character range. */
+DMK_API dmk_status dmk_crowd_get_palette(dmk_crowd_t crowd, int64_t first, int64_t count, float* out);
+/* SkeletalAnimator::getJointModelMatrix for every joint (src/skeleton_ozz.cpp:962-977): [count][J][16], left-handed */
+DMK_API dmk_status dmk_crowd_get_models(dmk_crowd_t crowd, int64_t first, int64_t count, float* out);
+/* blended local transforms as ozz SoaTransform: [count][num_soa][40] (state/transition getLocals, :617-624, :738-741) */
+DMK_API dmk_status dmk_crowd_get_locals(dmk_crowd_t crowd, int64_t first, int64_t count, float* out);
+/* ozz key-stream indices (left, right) chosen by the sampler: [count][num_layers][3][4*num_soa][2] int32,
+ * component order translation, rotation, scale -- the bit-exact "keyframe indices" of the parity contract */
+DMK_API dmk_status dmk_crowd_get_key_indices(dmk_crowd_t crowd, int64_t first, int64_t count, int32_t* out);
+DMK_API dmk_status dmk_crowd_get_skinned(dmk_crowd_t crowd, int64_t first, int64_t count, float* out); /* [count][V][9] */
+DMK_API dmk_status dmk_crowd_get_visibility(dmk_crowd_t crowd, uint32_t* out_bits, int64_t* out_visible_count);
+/* current clip clocks after ADVANCE: [num_layers][N] */
+DMK_API dmk_status dmk_crowd_get_ratios(dmk_crowd_t crowd, float* out_ratio, uint8_t* out_looped);
+
+/* Gather the palettes of the visible characters (ascending id) into a caller-owned DEVICE buffer of
+ * capacity_characters * palette_size * 16 floats; count is left on the device (dmk_crowd_visible_count_dev).
+ * This is the payload of the one multi-GPU exchange. */
+DMK_API dmk_status dmk_crowd_pack_visible_palettes(dmk_crowd_t crowd, float* out_dev, int64_t capacity_characters);
+
+/* ---- stand-alone batched cull (config 5: instances without animation) ---------------------------------- */
+/* world_inverse_dev [n][16], bbox_dev [n][6] device pointers; vis_bits_dev ceil(n/32) words. */
+DMK_API dmk_status dmk_cull_dev(dmk_context_t ctx, const float* corners_host, const float* world_inverse_dev,
+                                const float* bbox_dev, int64_t n, uint32_t* vis_bits_dev);
+/* host-buffer form (copies in and out; used by the e2e measurement and the parity tests) */
+DMK_API dmk_status dmk_cull_host(dmk_context_t ctx, const float* view_proj, float near_depth, const float* world_inverse,
+                                 const float* bbox, int64_t n, uint32_t* vis_bits);
+/* Frustum::Frustum(mtx) on the host in glm order (src/shape.cpp:1141-1163): out corners[8][3] */
+DMK_API dmk_status dmk_frustum_corners(const float* view_proj, float near_depth, float* out_corners);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMK_H */

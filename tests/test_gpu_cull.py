@@ -1,0 +1,95 @@
+"""CUDA frustum cull (K4) through the C ABI: visibility must equal the oracle's bit for bit."""
+import numpy as np
+import pytest
+
+from tests.common import GpuRig
+from darmok_b200 import capi, synth
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def test_frustum_corners_host_side_match_oracle(ctx):
+    vp = synth.sample_camera_view_proj()
+    for nd in (0.0, -1.0):
+        assert np.array_equal(ctx.frustum_corners(vp, nd), O.frustum_corners(vp, nd))
+
+
+@pytest.mark.parametrize("n,extent", [(1, 5.0), (31, 5.0), (32, 20.0), (33, 20.0), (100_000, 120.0), (1_000_003, 500.0)])
+def test_visibility_bit_exact(ctx, n, extent):
+    inst = synth.make_instances(n, seed=n % 97, extent=extent)
+    vp = synth.sample_camera_view_proj()
+    got = ctx.cull_host(vp, 0.0, inst.world_inverse, inst.bbox)
+    ref = O.cull_batch(O.frustum_corners(vp, 0.0), inst.world_inverse, inst.bbox)
+    assert np.array_equal(got, ref)
+    if n >= 100_000:
+        vis = capi.bits_to_bool(got, n)
+        assert 0 < vis.sum() < n
+
+
+def test_boundary_and_degenerate_boxes(ctx):
+    # boxes exactly touching a frustum plane, zero-size boxes, inverted boxes, NaN entries
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    boxes = np.array([
+        [1.0, -0.1, 0.4, 1.5, 0.1, 0.6],      # touches the right plane: sd == 0 -> not "in front" -> visible
+        [np.nextafter(np.float32(1), np.float32(2)), -0.1, 0.4, 1.5, 0.1, 0.6],
+        [0.2, 0.2, 0.2, 0.2, 0.2, 0.2],       # point box inside
+        [5, 5, 5, 5, 5, 5],                   # point box outside
+        [0.5, 0.5, 0.5, -0.5, -0.5, -0.5],    # inverted
+        [np.nan, 0, 0, 1, 1, 1],
+        [0, 0, 0, np.nan, np.nan, np.nan],
+        [-np.inf, -1, 0, np.inf, 1, 1],
+    ], np.float32)
+    wi = np.tile(ident, (len(boxes), 1))
+    got = ctx.cull_host(ident, 0.0, wi, boxes)
+    ref = O.cull_batch(O.frustum_corners(ident, 0.0), wi, boxes)
+    assert np.array_equal(got, ref)
+
+
+def test_random_matrices_and_boxes_fuzz(ctx):
+    rng = np.random.default_rng(11)
+    n = 50_000
+    wi = rng.normal(size=(n, 16)).astype(np.float32)
+    wi[:, [3, 7, 11]] = 0
+    wi[:, 15] = 1
+    lo = rng.normal(scale=2.0, size=(n, 3))
+    boxes = np.concatenate([lo, lo + rng.uniform(0, 3, (n, 3))], 1).astype(np.float32)
+    vp = synth.sample_camera_view_proj()
+    got = ctx.cull_host(vp, 0.0, wi, boxes)
+    ref = O.cull_batch(O.frustum_corners(vp, 0.0), wi, boxes)
+    assert np.array_equal(got, ref)
+
+
+def test_crowd_cull_and_visible_id_compaction(assets):
+    g = GpuRig(assets, with_mesh=False)
+    try:
+        n = 70_001
+        inst = synth.make_instances(n, seed=2, extent=150.0)
+        cr = synth.make_crowd(n, 1, len(assets.clips), seed=2)
+        crowd = g.crowd(n, 1, mesh=False)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight)
+        crowd.set_instances(inst.world_inverse, inst.bbox)
+        vp = synth.sample_camera_view_proj()
+        crowd.set_camera(vp, 0.0)
+        crowd.step(0.0, capi.STEP_POSE | capi.STEP_CULL)
+        bits, count = crowd.get_visibility()
+        ref = O.cull_batch(O.frustum_corners(vp, 0.0), inst.world_inverse, inst.bbox)
+        assert np.array_equal(bits, ref)
+        vis = capi.bits_to_bool(bits, n)
+        assert count == vis.sum() and 0 < count < n
+        # the compacted ids + packed palettes (payload of the multi-GPU gather) through torch device memory
+        import torch
+        out = torch.zeros((count, 68, 16), dtype=torch.float32, device="cuda")
+        crowd.pack_visible_palettes(out.data_ptr(), count)
+        g.ctx.sync()
+        pal = crowd.get_palette()
+        assert np.array_equal(out.cpu().numpy(), pal[np.nonzero(vis)[0]])
+    finally:
+        g.close()

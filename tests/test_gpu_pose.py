@@ -1,0 +1,193 @@
+"""CUDA pose path (K1-K3) through the C ABI against the oracle: key indices bit-exact, matrices within tolerance."""
+import numpy as np
+import pytest
+
+from tests import common
+from tests.common import FLT_MIN, GpuRig, OracleRig, assert_close, max_ulp_diff
+from darmok_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rigs(assets):
+    g, o = GpuRig(assets), OracleRig(assets)
+    yield g, o, assets
+    g.close()
+
+
+def _oracle_key_indices(o, assets, crowd):
+    """stateless oracle sampler per character/layer -> [N][L][3][P][2]"""
+    L, n = crowd.clip.shape
+    P = o.skel.num_soa * 4
+    out = np.zeros((n, L, 3, P, 2), np.int32)
+    for l in range(L):
+        for i in range(n):
+            _, cache = o.clips[crowd.clip[l, i]].sample_stateless(float(crowd.ratio[l, i]))
+            out[i, l] = cache
+    return out
+
+
+def test_single_layer_pose_matches_oracle(rigs):
+    g, o, a = rigs
+    n = 257
+    cr = synth.make_crowd(n, 1, len(a.clips), seed=1)
+    crowd = g.crowd(n, 1, mesh=False)
+    crowd.enable_outputs(g.capi.OUT_MODELS | g.capi.OUT_LOCALS | g.capi.OUT_KEY_INDICES)
+    crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed)
+    crowd.step(0.0, g.capi.STEP_POSE)
+    ref = o.crowd(n, 1).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, want=("locals", "models", "palette"))
+    # keyframe indices: bit-exact integers (ozz key-stream positions)
+    assert np.array_equal(crowd.get_key_indices(), _oracle_key_indices(o, a, cr))
+    assert_close(crowd.get_locals(), ref["locals"], "locals")
+    flipped = np.stack([[o.O.flip_handedness(m) for m in ch] for ch in ref["models"]])
+    assert_close(crowd.get_models(), flipped, "models")
+    assert_close(crowd.get_palette(), ref["palette"], "palette")
+    # the kernel follows the oracle's operation order without contraction: results are in fact identical
+    assert max_ulp_diff(crowd.get_palette(), ref["palette"]) == 0
+    assert max_ulp_diff(crowd.get_locals(), ref["locals"]) == 0
+
+
+def test_two_layer_transition_blend_matches_oracle(rigs):
+    g, o, a = rigs
+    n = 300
+    cr = synth.make_crowd(n, 2, len(a.clips), seed=2)
+    cr.weight[1, :5] = 0.0          # a skipped layer (weight <= 0)
+    cr.weight[0, 5:10] = 0.0
+    cr.weight[:, 10] = 0.0          # no contributing layer: rest pose (= layer 0) is copied
+    cr.weight[:, 11] = -1.0
+    crowd = g.crowd(n, 2, mesh=False)
+    crowd.enable_outputs(g.capi.OUT_LOCALS | g.capi.OUT_KEY_INDICES)
+    crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+    crowd.step(0.0, g.capi.STEP_POSE)
+    ref = o.crowd(n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, want=("locals", "palette"))
+    assert np.array_equal(crowd.get_key_indices(), _oracle_key_indices(o, a, cr))
+    assert_close(crowd.get_locals(), ref["locals"], "blended locals")
+    assert_close(crowd.get_palette(), ref["palette"], "palette")
+    assert max_ulp_diff(crowd.get_palette(), ref["palette"]) == 0
+
+
+def test_threshold_rest_pose_blend(rigs):
+    # state blend form: accumulated weight below the threshold pulls in the rest pose (layer 0) with the difference
+    g, o, a = rigs
+    n = 64
+    cr = synth.make_crowd(n, 3, len(a.clips), seed=3)
+    cr.weight[:] = np.random.default_rng(0).uniform(0.0, 0.08, cr.weight.shape).astype(np.float32)
+    crowd = g.crowd(n, 3, mesh=False)
+    crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=0.2)
+    crowd.step(0.0, g.capi.STEP_POSE)
+    ref = o.crowd(n, 3).step(cr.clip, cr.ratio, cr.weight, 0.2, want=("palette",))
+    assert_close(crowd.get_palette(), ref["palette"], "palette")
+
+
+def test_blending_job_rejects_zero_threshold(rigs):
+    # a state whose definition leaves threshold at the proto default 0: "error in the blending job" (C7)
+    g, o, a = rigs
+    cr = synth.make_crowd(8, 2, len(a.clips), seed=4)
+    crowd = g.crowd(8, 2, mesh=False)
+    crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=0.0)
+    with pytest.raises(g.capi.DmkError) as e:
+        crowd.step(0.0, g.capi.STEP_POSE)
+    assert e.value.status == g.capi.ERR_JOB and "error in the blending job" in e.value.message
+
+
+def test_clip_clock_advance_matches_reference_semantics(rigs):
+    g, o, a = rigs
+    n = 200
+    rng = np.random.default_rng(5)
+    cr = synth.make_crowd(n, 2, len(a.clips), seed=5)
+    cr.speed[0, :10] = 0.0                      # speed 0 is treated as 1 (src/skeleton_ozz.cpp:398-404)
+    loop = (rng.random((2, n)) < 0.5).astype(np.uint8)
+    crowd = g.crowd(n, 2, mesh=False)
+    crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, loop=loop, threshold=FLT_MIN)
+    t = cr.ratio.copy()
+    looped = np.zeros((2, n), bool)
+    durations = np.array([c.duration for c in o.clips], np.float32)
+    ocrowd = o.crowd(n, 2)
+    for step in range(40):
+        dt = float(np.float32(0.05 + 0.01 * step))
+        crowd.step(dt, g.capi.STEP_ADVANCE | g.capi.STEP_POSE)
+        for l in range(2):
+            for i in range(n):
+                t[l, i], looped[l, i], _ = o.O.clip_clock(float(t[l, i]), looped[l, i], dt, float(durations[cr.clip[l, i]]),
+                                                          float(cr.speed[l, i]), bool(loop[l, i]))
+        gr, gl = crowd.get_ratios()
+        assert np.array_equal(gr, t), f"ratios differ at step {step}"
+        assert np.array_equal(gl.astype(bool), looped), f"looped flags differ at step {step}"
+    ref = ocrowd.step(cr.clip, t, cr.weight, FLT_MIN, want=("palette",))
+    assert_close(crowd.get_palette(), ref["palette"], "palette after 40 ticks")
+    assert looped.any() and not looped.all()
+
+
+def test_edge_ratios_and_time_going_backwards(rigs):
+    g, o, a = rigs
+    special = np.array([0.0, 1.0, -0.25, 1.5, 0.5, np.float32(1.0 / 45.0), np.nextafter(np.float32(1), np.float32(0))], np.float32)
+    n = len(special) * len(a.clips)
+    clip = np.repeat(np.arange(len(a.clips), dtype=np.int32), len(special))[None, :]
+    ratio = np.tile(special, len(a.clips))[None, :]
+    crowd = g.crowd(n, 1, mesh=False)
+    crowd.enable_outputs(g.capi.OUT_KEY_INDICES)
+    crowd.set_layers(clip, ratio, np.ones_like(ratio))
+    crowd.step(0.0, g.capi.STEP_POSE)
+    ref = o.crowd(n, 1).step(clip, ratio, np.ones_like(ratio), FLT_MIN, want=("palette",))
+    assert_close(crowd.get_palette(), ref["palette"], "palette at edge ratios")
+    cr = synth.SynthCrowd(clip, ratio, np.ones_like(ratio), np.ones_like(ratio))
+    assert np.array_equal(crowd.get_key_indices(), _oracle_key_indices(o, a, cr))
+
+
+def test_unknown_armature_joint_gets_identity_model(assets):
+    # getJointModelMatrix returns mat4(1) for a name the skeleton does not have (src/skeleton_ozz.cpp:962-977)
+    names = list(assets.arm.names)
+    names[3] = "no_such_joint"
+    g = GpuRig(assets, with_mesh=False, with_armature=False)
+    try:
+        arm = g.capi.Armature(g.ctx, g.skel, names, assets.arm.inv_bind)
+        g.arm = arm
+        cr = synth.make_crowd(16, 1, len(assets.clips), seed=6)
+        crowd = g.crowd(16, 1, mesh=False)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight)
+        crowd.step(0.0, g.capi.STEP_POSE)
+        o = OracleRig(assets)
+        o.remap = np.array([o.skel.find_joint(nm) for nm in names], np.int32)
+        assert o.remap[3] == -1
+        ref = o.crowd(16, 1).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, want=("palette",))
+        assert_close(crowd.get_palette(), ref["palette"], "palette")
+        assert np.array_equal(crowd.get_palette()[:, 4], np.tile(assets.arm.inv_bind[3], (16, 1)))
+    finally:
+        g.close()
+
+
+def test_archive_errors_use_reference_strings(assets):
+    from darmok_b200 import capi
+    ctx = capi.Context(0)
+    try:
+        with pytest.raises(capi.DmkError) as e:
+            capi.Skeleton(ctx, assets.clips[0].archive)      # an animation archive is not a skeleton
+        assert e.value.status == capi.ERR_FORMAT and e.value.message == "archive does not contain the type"
+        with pytest.raises(capi.DmkError) as e:
+            capi.Clip(ctx, b"\x01garbage")
+        assert e.value.message == "archive does not contain the type"
+        with pytest.raises(capi.DmkError):
+            capi.Clip(ctx, assets.clips[0].archive[:200])    # truncated
+    finally:
+        ctx.close()
+
+
+def test_small_and_odd_skeletons():
+    # joint counts around the SoA / warp boundaries, incl. a single joint and > 64 joints
+    for joints in (1, 4, 5, 31, 32, 33, 100):
+        skel = synth.make_skeleton(joints, seed=joints)
+        clips = [synth.make_clip(skel, "c", seed=joints, duration=0.7)]
+        arm = synth.make_armature(skel, seed=joints)
+        a = common.Assets(skel, clips, arm, synth.make_mesh(8, joints))
+        g, o = GpuRig(a, with_mesh=False), OracleRig(a)
+        try:
+            n = 37
+            cr = synth.make_crowd(n, 2, 1, seed=joints)
+            crowd = g.crowd(n, 2, mesh=False)
+            crowd.set_layers(cr.clip, cr.ratio, cr.weight, threshold=FLT_MIN)
+            crowd.step(0.0, g.capi.STEP_POSE)
+            ref = o.crowd(n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, want=("palette",))
+            assert_close(crowd.get_palette(), ref["palette"], f"palette J={joints}")
+        finally:
+            g.close()

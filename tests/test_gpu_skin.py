@@ -1,0 +1,106 @@
+"""CUDA LBS skinning (K5) through the C ABI against the oracle's restatement of the vertex shader."""
+import numpy as np
+import pytest
+
+from tests import common
+from tests.common import FLT_MIN, GpuRig, OracleRig, assert_close
+from darmok_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(assets, n, layers=2, seed=1):
+    g, o = GpuRig(assets), OracleRig(assets)
+    try:
+        cr = synth.make_crowd(n, layers, len(assets.clips), seed=seed)
+        crowd = g.crowd(n, layers)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+        crowd.step(0.0, g.capi.STEP_POSE | g.capi.STEP_SKIN)
+        ref = o.crowd(n, layers).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, mesh=assets.mesh, want=("palette", "skinned"))
+        return crowd.get_skinned(), ref["skinned"], crowd.get_palette(), ref["palette"]
+    finally:
+        g.close()
+
+
+def test_skinned_vertices_match_oracle(assets):
+    got, ref, pal, ref_pal = _run(assets, 150)
+    assert_close(pal, ref_pal, "palette")
+    assert_close(got, ref, "skinned pos/normal/tangent")
+
+
+def test_unskinned_vertices_pass_through(assets):
+    # indices.x < 0: applySkinning returns the vertex unchanged (darmok_skinning.inc.slang:21-27, C17)
+    got, _, _, _ = _run(assets, 9, layers=1, seed=2)
+    un = assets.mesh.indices[:, 0] < 0
+    assert un.any()
+    m = assets.mesh
+    expect = np.concatenate([m.pos[un], m.nrm[un], m.tan[un]], axis=1)
+    for ch in got:
+        assert np.array_equal(ch[un], expect)
+
+
+@pytest.mark.parametrize("num_vertices", [1, 7, 8, 9, 255, 2560, 2561, 5000, 6007])
+def test_vertex_counts_around_tile_boundaries(num_vertices):
+    base = common.default_assets()
+    a = common.Assets(base.skel, base.clips, base.arm, synth.make_mesh(num_vertices, 67, seed=num_vertices))
+    n = 5 if num_vertices > 3000 else 21
+    got, ref, _, _ = _run(a, n, seed=num_vertices)
+    assert got.shape == (n, num_vertices, 9)
+    assert_close(got, ref, f"skinned V={num_vertices}")
+
+
+def test_single_full_weight_influence_is_matrix_times_vertex(assets):
+    # LBS with one influence of weight 1 equals palette[slot] * vertex exactly as a property of the shader
+    v = 64
+    rng = np.random.default_rng(0)
+    mesh = synth.make_mesh(v, 67, seed=3)
+    mesh.indices[:] = -1.0
+    mesh.indices[:, 0] = rng.integers(0, 67, v)
+    mesh.weights[:] = [1, 0, 0, 0]
+    a = common.Assets(assets.skel, assets.clips, assets.arm, mesh)
+    got, ref, pal, _ = _run(a, 4, layers=1, seed=4)
+    assert_close(got, ref, "skinned")
+    for ch in range(4):
+        m = pal[ch][(mesh.indices[:, 0] + 1).astype(int)].reshape(v, 4, 4).transpose(0, 2, 1).astype(np.float64)
+        pos = np.einsum("vij,vj->vi", m[:, :3, :3], mesh.pos.astype(np.float64)) + m[:, :3, 3]
+        assert np.allclose(got[ch][:, :3], pos, rtol=1e-5, atol=1e-6)
+
+
+def test_mesh_rejects_out_of_range_bone(assets):
+    from darmok_b200 import capi
+    ctx = capi.Context(0)
+    try:
+        m = assets.mesh
+        bad = m.indices.copy()
+        bad[0, 1] = 200.0
+        with pytest.raises(capi.DmkError) as e:
+            capi.Mesh(ctx, m.pos, m.nrm, m.tan, bad, m.weights, 68)
+        assert e.value.status == capi.ERR_INVALID
+    finally:
+        ctx.close()
+
+
+def test_skin_visible_only_leaves_culled_characters_untouched(assets):
+    g, o = GpuRig(assets), OracleRig(assets)
+    try:
+        n = 600
+        cr = synth.make_crowd(n, 1, len(assets.clips), seed=8)
+        inst = synth.make_instances(n, seed=8, extent=40.0)
+        crowd = g.crowd(n, 1)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight)
+        crowd.set_instances(inst.world_inverse, inst.bbox)
+        crowd.set_camera(synth.sample_camera_view_proj(), 0.0)
+        crowd.step(0.0, g.capi.STEP_POSE | g.capi.STEP_SKIN)          # everything skinned at ratio r0
+        before = crowd.get_skinned()
+        ratio2 = ((cr.ratio + 0.37) % 1.0).astype(np.float32)
+        crowd.set_layers(cr.clip, ratio2, cr.weight)
+        crowd.step(0.0, g.capi.STEP_POSE | g.capi.STEP_CULL | g.capi.STEP_SKIN | g.capi.STEP_SKIN_VISIBLE_ONLY)
+        after = crowd.get_skinned()
+        bits, count = crowd.get_visibility()
+        vis = g.capi.bits_to_bool(bits, n)
+        assert 0 < count < n and count == vis.sum()
+        ref = o.crowd(n, 1).step(cr.clip, ratio2, cr.weight, FLT_MIN, mesh=assets.mesh, want=("skinned",))["skinned"]
+        assert_close(after[vis], ref[vis], "visible characters re-skinned")
+        assert np.array_equal(after[~vis], before[~vis])
+    finally:
+        g.close()
