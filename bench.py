@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the character hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one frame of the crowd: clip clocks + keyframe sampling + 2-layer blend + local-to-model + skin
+palette (pose kernel), frustum cull + visible-id compaction, 4-influence LBS of every vertex of every character
+(skin kernel), and the gather of the visible palettes to the render GPU (pack kernel; NCCL over NVLink when N > 1).
+Workload at N=1 = BASELINE.json configs[2]: 100k characters, 67 joints, two-layer blend, 5k vertices x 4 influences,
+positions+normals+tangents.  Weak scaling: every rank owns the same number of characters (no data-path collective
+except the visible-palette gather of configs[3]).
+
+`--impl reference` times the reference's CPU path instead (the oracle port of darmok+ozz: the reference itself
+cannot be compiled here), OpenMP over all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "skinned_characters_per_sec"
+UNIT = "characters/s"
+FLT_MIN = float(np.finfo(np.float32).tiny)
+DT = 1.0 / 60.0
+
+
+def workload_config(args):
+    return {
+        "workload": "BASELINE.json configs[2]: 100k characters x 67 joints, two-layer BlendingJob (transition form), "
+                    "5k verts x 4 influences LBS positions+normals+tangents; + frustum cull and visible-palette gather",
+        "characters_per_gpu": args.chars, "joints": 67, "layers": 2, "clips": args.clips, "vertices": args.verts,
+        "influences": 4, "dt": DT,
+        "l2": "inputs larger than L2: each step streams %.1f GB of skinned vertices per GPU (L2 = 126 MB)"
+              % (args.chars * args.verts * 36 / 1e9),
+    }
+
+
+def make_assets(args):
+    from darmok_b200 import synth
+    skel = synth.make_skeleton(67)
+    clips = [synth.make_clip(skel, f"clip{i}", seed=i, duration=1.5) for i in range(args.clips)]
+    arm = synth.make_armature(skel)
+    mesh = synth.make_mesh(args.verts, 67)
+    return skel, clips, arm, mesh
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (oracle port; the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(args, assets, sample_chars, steps, warmup):
+    """characters/s of the reference CPU path on `sample_chars` characters of the workload, all host threads."""
+    from darmok_b200 import synth
+    from oracle import oracle_py as O
+    skel, clips, arm, mesh = assets
+    oskel = O.Skeleton(skel.archive)
+    oclips = [O.Animation(c.archive) for c in clips]
+    remap = np.array([oskel.find_joint(n) for n in arm.names], np.int32)
+    threads = min(host_threads(), O.max_threads())
+    crowd = O.Crowd(oskel, oclips, remap, arm.inv_bind, sample_chars, 2)
+    cr = synth.make_crowd(sample_chars, 2, len(clips), seed=42)
+    durations = np.array([c.duration for c in clips], np.float32)
+    ratio = cr.ratio.copy()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        # clip clocks (src/skeleton_ozz.cpp:411-428), vectorised: looping clips
+        ratio = np.fmod(ratio + np.float32(DT) / (durations[cr.clip] / cr.speed), np.float32(1.0)).astype(np.float32)
+        crowd.step(cr.clip, ratio, cr.weight, FLT_MIN, mesh=mesh, want=("skin_scratch",), num_threads=threads)
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    return sample_chars * len(times) / total, threads, total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    assets = make_assets(args)
+    # bounded sample: calibrate on a small crowd, then size each step to ~2 s of CPU work
+    probe_rate, threads, _ = cpu_reference_rate(args, assets, 64 * max(1, host_threads()) // 4 + 64, 1, 1)
+    sample = int(max(256, min(args.chars, probe_rate * 2.0)))
+    rate, threads, sec_per_step = cpu_reference_rate(args, assets, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3 * (args.chars / sample), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} characters of the workload per step (sample+blend+L2M+palette+LBS of "
+                                   f"{args.verts} vertices each), OpenMP over {threads} threads; ms_per_step is "
+                                   "extrapolated to the full crowd; oracle port with exact 1/x, 1/sqrt (ozz simd_ref "
+                                   "semantics), not upstream ozz SSE code"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.rows, self.proc, self.thread = [], None, None
+        self.device_index = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t_begin, t_end):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t_begin <= t <= t_end] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from darmok_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    assets = make_assets(args)
+    skel_s, clips_s, arm_s, mesh_s = assets
+    n = args.chars
+
+    with torch.cuda.stream(stream):
+        ctx = capi.Context(local_rank, stream.cuda_stream)
+        skel = capi.Skeleton(ctx, skel_s.archive)
+        clip_objs = [capi.Clip(ctx, c.archive) for c in clips_s]
+        clips = capi.ClipSet(ctx, skel, clip_objs)
+        arm = capi.Armature(ctx, skel, arm_s.names, arm_s.inv_bind)
+        mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size)
+        crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
+        cr = synth.make_crowd(n, 2, len(clips_s), seed=42 + rank)       # varied clips / phases per rank
+        inst = synth.make_instances(n, seed=5 + rank, extent=500.0)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+        crowd.set_instances(inst.world_inverse, inst.bbox)
+        crowd.set_camera(synth.sample_camera_view_proj(), 0.0)
+        ps = arm.palette_size
+        # visible-palette slab: capacity sized from a first cull (+25 % head-room), constant afterwards
+        crowd.step(DT, capi.STEP_POSE | capi.STEP_CULL)
+        _, vis0 = crowd.get_visibility()
+        cap = min(n, int(vis0 * 1.25) + 1024)
+        packed = torch.empty((cap, ps, 16), dtype=torch.float32, device=dev)
+        counts = torch.zeros(world, dtype=torch.int32, device=dev)
+        count_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        gathered = None
+        # device int32 count written by the compaction kernel, viewed as a torch tensor without a copy
+        vis_count = torch.as_tensor(_DevInt32(crowd.visible_count_dev()), device=dev)
+        flags = capi.STEP_ADVANCE | capi.STEP_POSE | capi.STEP_CULL | capi.STEP_SKIN
+
+        def step():
+            nonlocal gathered
+            crowd.step(DT, flags)
+            crowd.pack_visible_palettes(packed.data_ptr(), cap)
+            if world > 1:
+                # the one exchange of the path: visible palettes to the render GPU (rank 0), sizes first
+                dist.all_gather_into_tensor(counts, vis_count)
+                sizes = counts.cpu().tolist()
+                if rank == 0:
+                    if gathered is None or gathered.shape[0] < sum(sizes):
+                        gathered = torch.empty((int(sum(sizes) * 1.25) + 1024, ps, 16), dtype=torch.float32, device=dev)
+                    ops, off = [], sizes[0]
+                    for r in range(1, world):
+                        if sizes[r]:
+                            ops.append(dist.P2POp(dist.irecv, gathered[off:off + sizes[r]], r))
+                        off += sizes[r]
+                    if ops:
+                        for w in dist.batch_isend_irecv(ops):
+                            w.wait()
+                elif sizes[rank]:
+                    for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, packed[:min(sizes[rank], cap)], 0)]):
+                        w.wait()
+
+        for _ in range(args.warmup):
+            step()
+        ctx.enable_kernel_timing(True)
+        ctx.reset_kernel_timing()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.25)
+        launches0 = ctx.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t_end = time.perf_counter()
+        clocks = sampler.stop(t_begin, t_end)
+        elapsed_ms = ev0.elapsed_time(ev1)
+        launches = ctx.launches - launches0
+        if world > 1:
+            t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t.item())
+        skin_ms, skin_n = ctx.kernel_time(capi.KERNEL_SKIN)
+        pose_ms, pose_n = ctx.kernel_time(capi.KERNEL_POSE)
+        cull_ms, cull_n = ctx.kernel_time(capi.KERNEL_CULL)
+        pack_ms, pack_n = ctx.kernel_time(capi.KERNEL_PACK)
+        ctx.enable_kernel_timing(False)
+
+        # ---- e2e: host buffers through the C ABI; H2D of the step's layer state, D2H of its visibility result ----
+        e2e = None
+        if rank == 0 or world > 1:
+            durations = np.array([c.duration for c in clips_s], np.float32)
+            ratio = cr.ratio.copy()
+            vis_bits = np.zeros((n + 31) // 32, np.uint32)
+            e2e_flags = capi.STEP_POSE | capi.STEP_CULL | capi.STEP_SKIN
+            e2e_steps = max(3, min(args.steps, 10))
+
+            def e2e_step():
+                nonlocal ratio
+                # host state machine tick (clip clocks of looping clips) -> layer state for the device
+                ratio = np.fmod(ratio + np.float32(DT) / (durations[cr.clip] / cr.speed), np.float32(1.0)).astype(np.float32)
+                crowd.update_layers(cr.clip, ratio, cr.weight)          # pinned staging + async H2D
+                crowd.step(DT, e2e_flags)
+                crowd.pack_visible_palettes(packed.data_ptr(), cap)
+                b, cnt = crowd.get_visibility()                          # D2H + stream sync
+                return cnt
+
+            e2e_step()
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize(dev)
+            e2e_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t.item())
+            e2e = {"value": n * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(3 * 2 * n * 4),
+                   "d2h_bytes_per_step": int(vis_bits.nbytes + 4), "steps": e2e_steps,
+                   "note": "per step: host clip clocks (numpy) -> dmk_crowd_update_layers (pinned H2D of clip/ratio/weight) -> "
+                           "dmk_crowd_step(POSE|CULL|SKIN) -> pack visible palettes -> dmk_crowd_get_visibility (D2H + sync); "
+                           "skinned vertices and palettes stay on the GPU, as in the reference (vertex-stage consumers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    # algorithmic bytes of the skin kernel per launch: 36 B/vertex out + one 4352 B palette/character
+    alg_bytes = n * (args.verts * 36 + ps * 64)
+    skin_avg_ms = skin_ms / max(1, skin_n)
+    achieved = alg_bytes / (skin_avg_ms * 1e-3) / 1e9 if skin_avg_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "skin_kernel_traffic.json")) as f:
+            tj = json.load(f)
+            if tj.get("characters") == n and tj.get("vertices") == args.verts:
+                traffic = tj.get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    ms_per_step = elapsed_ms / args.steps
+    value = n * world * args.steps / (elapsed_ms * 1e-3)
+
+    # CPU baseline on the host cores of this box (bounded sample), rank 0 at N=1 only
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        probe_rate, threads, _ = cpu_reference_rate(args, assets, 64 * max(1, host_threads()) // 4 + 64, 1, 1)
+        sample = int(max(256, min(n, probe_rate * 4.0)))
+        rate, threads, _ = cpu_reference_rate(args, assets, sample, 3, 1)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{sample} characters x 3 steps of the same workload (sample+blend+L2M+palette+LBS of "
+                                  f"{args.verts} vertices), oracle port (exact 1/x, 1/sqrt), OpenMP {threads} threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "skin_kernel<8> (K5 LBS)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": skin_avg_ms, "launches_timed": int(skin_n)},
+        "cpu_baseline": cpu_baseline,
+        "skinned_vertices_per_sec": value * args.verts, "frames_per_sec_per_gpu": 1e3 / ms_per_step,
+        "kernel_ms_per_step": {"pose": pose_ms / max(1, pose_n), "cull+compact": cull_ms / max(1, cull_n),
+                               "skin": skin_avg_ms, "pack_visible_palettes": pack_ms / max(1, pack_n)},
+        "visible_characters_rank0": int(vis0),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+class _DevInt32:
+    """__cuda_array_interface__ view of one device int32 owned by the library (no copy)."""
+
+    def __init__(self, ptr):
+        self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chars", type=int, default=100_000, help="characters per GPU")
+    ap.add_argument("--verts", type=int, default=5000)
+    ap.add_argument("--clips", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -17,6 +17,7 @@ OK, ERR_INVALID, ERR_FORMAT, ERR_CUDA, ERR_UNSUPPORTED, ERR_JOB = range(6)
 STEP_ADVANCE, STEP_POSE, STEP_CULL, STEP_SKIN, STEP_SKIN_VISIBLE_ONLY = 1, 2, 4, 8, 16
 STEP_ALL = 15
 OUT_MODELS, OUT_LOCALS, OUT_KEY_INDICES = 1, 2, 4
+KERNEL_POSE, KERNEL_CULL, KERNEL_SKIN, KERNEL_PACK = 0, 1, 2, 3
 
 # every symbol include/dmk.h declares: (name, restype, argtypes)
 _vp, _i, _i64, _f, _u32, _sz, _cp = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32, C.c_size_t, C.c_char_p
@@ -28,6 +29,9 @@ SIGNATURES = [
     ("dmk_context_stream", _vp, [_vp]),
     ("dmk_version", _cp, []),
     ("dmk_context_launch_count", C.c_uint64, [_vp]),
+    ("dmk_context_enable_kernel_timing", _i, [_vp, _i]),
+    ("dmk_context_kernel_time", _i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    ("dmk_context_reset_kernel_timing", _i, [_vp]),
     ("dmk_skeleton_load_ozz", _i, [_vp, _vp, _sz, C.POINTER(_vp)]),
     ("dmk_skeleton_destroy", None, [_vp]),
     ("dmk_skeleton_num_joints", _i, [_vp]),
@@ -131,6 +135,17 @@ class Context:
         if self.h:
             lib().dmk_context_destroy(self.h)
             self.h = None
+
+    def enable_kernel_timing(self, on=True):
+        self.check(lib().dmk_context_enable_kernel_timing(self.h, int(on)))
+
+    def reset_kernel_timing(self):
+        self.check(lib().dmk_context_reset_kernel_timing(self.h))
+
+    def kernel_time(self, kernel):
+        ms, n = C.c_double(), C.c_uint64()
+        self.check(lib().dmk_context_kernel_time(self.h, kernel, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def frustum_corners(self, view_proj, near_depth=0.0):
         vp = _f32(view_proj)

@@ -30,6 +30,13 @@ struct dmk_context_s {
     // grow-only scratch of the host-buffer cull entry point
     void* cull_scratch = nullptr;
     size_t cull_scratch_bytes = 0;
+    // optional per-kernel timing
+    bool timing = false;
+    struct Timed { int kernel; cudaEvent_t start, stop; };
+    std::vector<Timed> pending;
+    std::vector<cudaEvent_t> event_pool;
+    double kernel_ms[DMK_KERNEL_COUNT] = {0, 0, 0, 0};
+    uint64_t kernel_launches[DMK_KERNEL_COUNT] = {0, 0, 0, 0};
 };
 
 struct dmk_skeleton_s {
@@ -148,6 +155,44 @@ static dmk_status bind(dmk_context_t ctx) {
 }
 
 namespace {
+// RAII scope that brackets a launch with CUDA events when kernel timing is on
+struct KernelTimer {
+    dmk_context_t ctx;
+    dmk_context_s::Timed t{};
+    bool on;
+    KernelTimer(dmk_context_t c, int kernel) : ctx(c), on(c->timing) {
+        if (!on) return;
+        t.kernel = kernel;
+        for (cudaEvent_t* e : {&t.start, &t.stop}) {
+            if (!ctx->event_pool.empty()) {
+                *e = ctx->event_pool.back();
+                ctx->event_pool.pop_back();
+            } else if (cudaEventCreate(e) != cudaSuccess) {
+                on = false;
+                return;
+            }
+        }
+        cudaEventRecord(t.start, ctx->stream);
+    }
+    ~KernelTimer() {
+        if (!on) return;
+        cudaEventRecord(t.stop, ctx->stream);
+        ctx->pending.push_back(t);
+    }
+};
+void drain_timers(dmk_context_t ctx) {
+    for (auto& t : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t.stop) == cudaSuccess && cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess) {
+            ctx->kernel_ms[t.kernel] += ms;
+            ++ctx->kernel_launches[t.kernel];
+        }
+        ctx->event_pool.push_back(t.start);
+        ctx->event_pool.push_back(t.stop);
+    }
+    ctx->pending.clear();
+}
+
 struct PackedComponent {
     std::vector<float> ratio;
     std::vector<uint2> value;
@@ -237,6 +282,8 @@ void dmk_context_destroy(dmk_context_t ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     dev_free(ctx->cull_scratch);
+    drain_timers(ctx);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -244,6 +291,30 @@ void dmk_context_destroy(dmk_context_t ctx) {
 const char* dmk_last_error(dmk_context_t ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 void* dmk_context_stream(dmk_context_t ctx) { return ctx ? ctx->stream : nullptr; }
 uint64_t dmk_context_launch_count(dmk_context_t ctx) { return ctx ? ctx->launches : 0; }
+
+dmk_status dmk_context_enable_kernel_timing(dmk_context_t ctx, int on) {
+    if (!ctx) return DMK_ERR_INVALID;
+    ctx->timing = on != 0;
+    return DMK_OK;
+}
+dmk_status dmk_context_kernel_time(dmk_context_t ctx, int kernel, double* total_ms, uint64_t* launches) {
+    if (!ctx || kernel < 0 || kernel >= DMK_KERNEL_COUNT) return DMK_ERR_INVALID;
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    drain_timers(ctx);
+    if (total_ms) *total_ms = ctx->kernel_ms[kernel];
+    if (launches) *launches = ctx->kernel_launches[kernel];
+    return DMK_OK;
+}
+dmk_status dmk_context_reset_kernel_timing(dmk_context_t ctx) {
+    if (!ctx) return DMK_ERR_INVALID;
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    drain_timers(ctx);
+    for (int k = 0; k < DMK_KERNEL_COUNT; ++k) {
+        ctx->kernel_ms[k] = 0;
+        ctx->kernel_launches[k] = 0;
+    }
+    return DMK_OK;
+}
 
 dmk_status dmk_sync(dmk_context_t ctx) {
     if (!ctx) return DMK_ERR_INVALID;
@@ -707,7 +778,10 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         p.locals = c->d_locals;
         p.key_indices = c->d_key_indices;
         p.error_flag = c->d_error;
-        DMK_CUDA(ctx, launch_pose(p, ctx->num_sms, s));
+        {
+            KernelTimer timer(ctx, DMK_KERNEL_POSE);
+            DMK_CUDA(ctx, launch_pose(p, ctx->num_sms, s));
+        }
         ++ctx->launches;
     }
     if (flags & DMK_STEP_CULL) {
@@ -719,10 +793,13 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         p.n = c->n;
         p.vis_bits = c->d_vis_bits;
         std::memcpy(p.corners, c->corners, sizeof p.corners);
-        DMK_CUDA(ctx, launch_cull(p, s));
-        ++ctx->launches;
         int extra = 0;
-        DMK_CUDA(ctx, launch_compact(c->d_vis_bits, c->n, c->d_visible_ids, c->d_visible_count, c->d_scratch, s, &extra));
+        {
+            KernelTimer timer(ctx, DMK_KERNEL_CULL);
+            DMK_CUDA(ctx, launch_cull(p, s));
+            DMK_CUDA(ctx, launch_compact(c->d_vis_bits, c->n, c->d_visible_ids, c->d_visible_count, c->d_scratch, s, &extra));
+        }
+        ++ctx->launches;
         ctx->launches += extra;
         c->culled_once = true;
     }
@@ -745,7 +822,10 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         p.palette_size = c->mesh->palette_size;
         p.num_tiles = c->plan.num_tiles;
         p.tile_vertices = c->plan.tile_vertices;
-        DMK_CUDA(ctx, launch_skin(p, c->plan, s));
+        {
+            KernelTimer timer(ctx, DMK_KERNEL_SKIN);
+            DMK_CUDA(ctx, launch_skin(p, c->plan, s));
+        }
         ++ctx->launches;
     }
     if (flags & DMK_STEP_POSE)
@@ -838,8 +918,11 @@ dmk_status dmk_crowd_pack_visible_palettes(dmk_crowd_t c, float* out_dev, int64_
     if (!out_dev || capacity < 0) return fail(c->ctx, DMK_ERR_INVALID, "null output");
     if (!c->d_palette || !c->culled_once) return fail(c->ctx, DMK_ERR_INVALID, "needs an armature and a cull step");
     if (bind(c->ctx)) return DMK_ERR_CUDA;
-    DMK_CUDA(c->ctx, launch_pack_palettes(c->d_palette, (c->arm->num_joints + 1) * 16, c->d_visible_ids, c->d_visible_count, capacity,
-                                          out_dev, c->ctx->num_sms, c->ctx->stream));
+    {
+        KernelTimer timer(c->ctx, DMK_KERNEL_PACK);
+        DMK_CUDA(c->ctx, launch_pack_palettes(c->d_palette, (c->arm->num_joints + 1) * 16, c->d_visible_ids, c->d_visible_count, capacity,
+                                              out_dev, c->ctx->num_sms, c->ctx->stream));
+    }
     ++c->ctx->launches;
     return DMK_OK;
 }

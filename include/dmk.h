@@ -63,6 +63,13 @@ DMK_API const char* dmk_version(void);
 /* number of kernels this library has launched on the context since creation (bench.py gpu_launches) */
 DMK_API uint64_t dmk_context_launch_count(dmk_context_t ctx);
 
+/* Optional per-kernel device timing (CUDA events on the context's stream around each launch; used by bench.py
+ * for the roofline line).  kernel: DMK_KERNEL_*; totals accumulate until reset; the query synchronises. */
+enum { DMK_KERNEL_POSE = 0, DMK_KERNEL_CULL = 1, DMK_KERNEL_SKIN = 2, DMK_KERNEL_PACK = 3, DMK_KERNEL_COUNT = 4 };
+DMK_API dmk_status dmk_context_enable_kernel_timing(dmk_context_t ctx, int on);
+DMK_API dmk_status dmk_context_kernel_time(dmk_context_t ctx, int kernel, double* total_ms, uint64_t* launches);
+DMK_API dmk_status dmk_context_reset_kernel_timing(dmk_context_t ctx);
+
 /* ---- assets -------------------------------------------------------------------------------------------- */
 /* OzzSkeletonLoader::operator() -> OzzUtils::loadFromData<ozz::animation::Skeleton> (src/skeleton_ozz.cpp:27-44,
  * :191-200): bytes of an ozz archive holding an "ozz-skeleton" (version 2). */

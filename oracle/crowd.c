@@ -61,6 +61,10 @@ int64_t orc_crowd_step(orc_crowd* c, const int32_t* clip, const float* ratio, co
         float* layer_buf = (float*)malloc(sizeof(float) * ORC_SOA_FLOATS * (size_t)S * (size_t)(L + 1));
         float* models = (float*)malloc(sizeof(float) * 16 * (size_t)J);
         float* palette = (float*)malloc(sizeof(float) * 16 * (size_t)(K + 1));
+        /* pos != NULL with out_skinned == NULL: skin into a per-thread scratch (CPU baseline timing: the result
+         * stays cache resident, the most favourable case for the CPU) */
+        const int scratch_skin = (!out_skinned && pos && num_vertices > 0);
+        float* scratch = scratch_skin ? (float*)malloc(sizeof(float) * 9 * (size_t)num_vertices) : NULL;
         const float** layer_ptr = (const float**)malloc(sizeof(float*) * (size_t)L);
         float* wts = (float*)malloc(sizeof(float) * (size_t)L);
 #pragma omp for schedule(static)
@@ -89,14 +93,17 @@ int64_t orc_crowd_step(orc_crowd* c, const int32_t* clip, const float* ratio, co
             }
             if (out_locals) memcpy(out_locals + (size_t)i * S * ORC_SOA_FLOATS, locals, sizeof(float) * ORC_SOA_FLOATS * (size_t)S);
             if (out_models) memcpy(out_models + (size_t)i * J * 16, models, sizeof(float) * 16 * (size_t)J);
-            if (out_palette || (out_skinned && num_vertices > 0)) {
+            if (out_palette || scratch_skin || (out_skinned && num_vertices > 0)) {
                 orc_palette(models, J, c->remap, c->inv_bind, K, palette);
                 if (out_palette) memcpy(out_palette + (size_t)i * (K + 1) * 16, palette, sizeof(float) * 16 * (size_t)(K + 1));
                 if (out_skinned && num_vertices > 0)
                     orc_skin(palette, K + 1, pos, nrm, tan, indices, weights, num_vertices,
                              out_skinned + (size_t)i * (size_t)num_vertices * 9);
+                else if (scratch_skin)
+                    orc_skin(palette, K + 1, pos, nrm, tan, indices, weights, num_vertices, scratch);
             }
         }
+        free(scratch);
         free(layer_buf);
         free(models);
         free(palette);

@@ -299,10 +299,11 @@ class Crowd:
         skinned = None
         args = [None] * 5
         v = 0
-        if mesh is not None and "skinned" in want:
+        if mesh is not None and ("skinned" in want or "skin_scratch" in want):
             args = [_f32(mesh.pos), _f32(mesh.nrm), _f32(mesh.tan), _f32(mesh.indices), _f32(mesh.weights)]
             v = args[0].shape[0]
-            skinned = np.zeros((n, v, 9), np.float32)
+            if "skinned" in want:
+                skinned = np.zeros((n, v, 9), np.float32)
         rc = lib().orc_crowd_step(self.h, _p(clip), _p(ratio), _p(weight), threshold, _p(locals_), _p(models), _p(pal),
                                   *[_p(a) for a in args], v, _p(skinned), num_threads or max_threads())
         if rc:
