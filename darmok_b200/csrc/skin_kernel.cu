@@ -12,7 +12,9 @@
 //     position, normal, tangent, weights, packed palette slots -- in registers for the whole launch and loops over
 //     characters, so bind-pose data is read once per CTA, not once per character.
 //   * Per character the 3x4 row-major palette (written by the pose kernel) arrives by cp.async.bulk (TMA bulk
-//     copy) into a double-buffered staging area, signalled by an mbarrier, one character ahead.
+//     copy) into a double-buffered staging area, signalled by an mbarrier, two characters ahead.
+//   * There is no block-wide barrier in the character loop: warps hand replica buffers over through mbarriers
+//     (3-deep ring), so a warp only ever waits for the others to have STARTED the previous character.
 //   * The palette is then replicated 8x into bank-group-private copies: lane L reads copy (L & 7), whose 16-byte
 //     chunks all live in bank group (L & 7), so the random per-vertex gathers (LDS.128) are conflict free
 //     whatever the bone indices are.
@@ -38,17 +40,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    // try_wait suspends the thread in hardware until the phase completes or a time limit passes; the spin bound
+    // turns a protocol bug into a trap instead of a hung GPU
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 22)) __trap();
+    } while (!done);
 }
 // TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -70,17 +78,49 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
+// mbarrier arrive (release at CTA scope): one arrival per warp after its lanes' shared-memory writes
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kNumRepl = 3;   // replica ring: fill(i+1) may overlap compute(i) and the slowest warp's compute(i-1)
+constexpr int kNumStage = 2;  // bulk-copy staging ring
+
+// One vertex: gather 4 palette matrices row by row (row r+1 is in flight while row r is consumed), blend, apply.
+struct Rows4 { float4 q0, q1, q2, q3; };
+
+template <int REPL>
+__device__ __forceinline__ Rows4 load_row(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int r) {
+    Rows4 x;
+    x.q0 = lds128(a0 + r * 16u * REPL);
+    x.q1 = lds128(a1 + r * 16u * REPL);
+    x.q2 = lds128(a2 + r * 16u * REPL);
+    x.q3 = lds128(a3 + r * 16u * REPL);
+    return x;
+}
+
+__device__ __forceinline__ float4 blend_row(const Rows4& x, float w0, float w1, float w2, float w3) {
+    float4 m;
+    m.x = fmaf(w3, x.q3.x, fmaf(w2, x.q2.x, fmaf(w1, x.q1.x, w0 * x.q0.x)));
+    m.y = fmaf(w3, x.q3.y, fmaf(w2, x.q2.y, fmaf(w1, x.q1.y, w0 * x.q0.y)));
+    m.z = fmaf(w3, x.q3.z, fmaf(w2, x.q2.z, fmaf(w1, x.q1.z, w0 * x.q0.z)));
+    m.w = fmaf(w3, x.q3.w, fmaf(w2, x.q2.w, fmaf(w1, x.q1.w, w0 * x.q0.w)));
+    return m;
+}
+
 template <int REPL>
 __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int PS = p.palette_size;
     const uint32_t pal_bytes = (uint32_t)PS * 48u;             // 3x4 floats per slot
     const uint32_t repl_bytes = pal_bytes * REPL;
-    unsigned char* s_repl = smem;                               // [2][PS*3][REPL] float4
-    unsigned char* s_stage = smem + 2 * (size_t)repl_bytes;     // [2][PS*3] float4 (bulk copy destination)
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + 2 * (size_t)pal_bytes);
+    unsigned char* s_repl = smem;                                        // [kNumRepl][PS*3][REPL] float4
+    unsigned char* s_stage = smem + kNumRepl * (size_t)repl_bytes;       // [kNumStage][PS*3] float4 (bulk copy dst)
+    uint64_t* s_tma_bar = reinterpret_cast<uint64_t*>(s_stage + kNumStage * (size_t)pal_bytes);  // [kNumStage]
+    uint64_t* s_full_bar = s_tma_bar + kNumStage;                        // [kNumRepl]
 
     const int tid = threadIdx.x, lane = tid & 31;
+    const int nwarps = blockDim.x >> 5;
     const int tiles_per_pass = min(p.num_tiles, (int)gridDim.x);
     const int ngroups = gridDim.x / tiles_per_pass;
     const int tslot = blockIdx.x % tiles_per_pass, group = blockIdx.x / tiles_per_pass;
@@ -92,14 +132,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
     if (my_count == 0) return;
 
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int k = 0; k < kNumStage; ++k) mbar_init(&s_tma_bar[k], 1);
+        for (int k = 0; k < kNumRepl; ++k) mbar_init(&s_full_bar[k], nwarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    uint32_t issued = 0;  // bulk copies issued so far by thread 0 across tile passes (buffer = issued & 1)
-    uint32_t consumed = 0;
+    // running counts over the whole launch: item q (a character of some tile pass) uses stage q % kNumStage (its
+    // (q / kNumStage)-th use) and replica buffer q % kNumRepl (its (q / kNumRepl)-th use)
+    uint32_t q_issue = 0;  // thread 0: items whose bulk copy has been issued
+    uint32_t q_fill = 0;   // items this thread has replicated
+    uint32_t q_comp = 0;   // items this thread has computed
+
+    const uint32_t lane_off = (uint32_t)(lane & (REPL - 1)) * 16u;
+    const uint32_t repl_base = smem_u32(s_repl) + lane_off;
 
     for (int tile = tslot; tile < p.num_tiles; tile += tiles_per_pass) {
         // ---- this thread's 8 vertices: loaded once, kept in registers for every character ----
@@ -123,77 +169,92 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
             const int64_t k = group + i * ngroups;
             return p.char_ids ? (int64_t)__ldg(p.char_ids + k) : k;
         };
-        auto issue = [&](int64_t i) {  // thread 0 only
+        auto issue = [&](int64_t i) {  // thread 0 only: bulk copy of character i's palette into the staging ring
             if (i < my_count) {
-                const uint32_t b = issued & 1u;
-                mbar_expect_tx(&s_bar[b], pal_bytes);
-                bulk_g2s(s_stage + (size_t)b * pal_bytes, p.palette34 + (size_t)char_of(i) * PS * 12, pal_bytes, &s_bar[b]);
-                ++issued;
+                const uint32_t b = q_issue % kNumStage;
+                mbar_expect_tx(&s_tma_bar[b], pal_bytes);
+                bulk_g2s(s_stage + (size_t)b * pal_bytes, p.palette34 + (size_t)char_of(i) * PS * 12, pal_bytes, &s_tma_bar[b]);
+                ++q_issue;
             }
         };
-        // staging -> 8 bank-group-private replicas; lane L writes replica (L + k) & 7 at step k: conflict free
-        auto replicate = [&](uint32_t b) {
-            const float4* src = reinterpret_cast<const float4*>(s_stage + (size_t)b * pal_bytes);
-            float4* dst = reinterpret_cast<float4*>(s_repl + (size_t)b * repl_bytes);
+        // staging -> 8 bank-group-private replicas; lane L writes replica (L + k) & 7 at step k: conflict free.
+        // Ends with one mbarrier arrival per warp on the replica buffer's "full" barrier.
+        auto fill = [&]() {
+            const uint32_t sb = q_fill % kNumStage, rb = q_fill % kNumRepl;
+            mbar_wait(&s_tma_bar[sb], (q_fill / kNumStage) & 1u);
+            const float4* src = reinterpret_cast<const float4*>(s_stage + (size_t)sb * pal_bytes);
+            float4* dst = reinterpret_cast<float4*>(s_repl + (size_t)rb * repl_bytes);
             for (int t = tid; t < PS * 3; t += blockDim.x) {
                 const float4 val = src[t];
 #pragma unroll
                 for (int k = 0; k < REPL; ++k) dst[t * REPL + ((lane + k) & (REPL - 1))] = val;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full_bar[rb]);
+            ++q_fill;
         };
 
+        // prologue of the tile pass: stage items 0 and 1, replicate item 0.  Every warp has finished its previous
+        // pass's last compute only when it gets here, but another warp may still be computing it: the block-wide
+        // barrier below (once per tile pass, not per character) closes that window.
+        if (tile != tslot) __syncthreads();
         if (tid == 0) { issue(0); issue(1); }
-        mbar_wait(&s_bar[consumed & 1u], (consumed >> 1) & 1u);
-        replicate(consumed & 1u);
-        ++consumed;
-        __syncthreads();
-        if (tid == 0) issue(2);
+        fill();
 
-        const uint32_t lane_off = (uint32_t)(lane & (REPL - 1)) * 16u;
+        int64_t cid = char_of(0);
         for (int64_t i = 0; i < my_count; ++i) {
-            // buffer of character i within this tile pass: the one replicated last
-            const uint32_t cur = (consumed - 1u) & 1u;
+            // (1) every warp has replicated item i  => also: every warp is past compute(i - 2)
+            mbar_wait(&s_full_bar[q_comp % kNumRepl], (q_comp / kNumRepl) & 1u);
+            // (2) so the staging slot of item i is drained and the replica buffer of item i - 2 is free:
+            //     stage item i + 2, replicate item i + 1 (its bulk copy was issued one iteration ago)
+            if (tid == 0) issue(i + 2);
+            if (i + 1 < my_count) fill();
+            const int64_t cid_next = (i + 1 < my_count) ? char_of(i + 1) : 0;
+            // (3) skin this thread's 8 vertices of character i
             if (active) {
-                const uint32_t base = smem_u32(s_repl + (size_t)cur * repl_bytes) + lane_off;
-                float* out = p.out + ((size_t)char_of(i) * p.vpad + v0) * 9;
+                const uint32_t base = repl_base + (q_comp % kNumRepl) * repl_bytes;
+                float* out = p.out + ((size_t)cid * p.vpad + v0) * 9;
                 float res[kVPT * 9];
+                uint32_t a0, a1, a2, a3;
+                auto addr = [&](uint32_t s) {
+                    a0 = base + (s & 0xffu) * (48u * REPL);
+                    a1 = base + ((s >> 8) & 0xffu) * (48u * REPL);
+                    a2 = base + ((s >> 16) & 0xffu) * (48u * REPL);
+                    a3 = base + (s >> 24) * (48u * REPL);
+                };
+                addr(slots[0]);
+                Rows4 cur = load_row<REPL>(a0, a1, a2, a3, 0);
 #pragma unroll
                 for (int v = 0; v < kVPT; ++v) {
-                    const uint32_t s = slots[v];
-                    const uint32_t a0 = base + (s & 0xffu) * (48u * REPL);
-                    const uint32_t a1 = base + ((s >> 8) & 0xffu) * (48u * REPL);
-                    const uint32_t a2 = base + ((s >> 16) & 0xffu) * (48u * REPL);
-                    const uint32_t a3 = base + (s >> 24) * (48u * REPL);
-                    float m[3][4];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {  // row r of M = sum_i w_i * P[slot_i]
-                        const float4 q0 = lds128(a0 + r * 16u * REPL), q1 = lds128(a1 + r * 16u * REPL);
-                        const float4 q2 = lds128(a2 + r * 16u * REPL), q3 = lds128(a3 + r * 16u * REPL);
-                        m[r][0] = fmaf(w3[v], q3.x, fmaf(w2[v], q2.x, fmaf(w1[v], q1.x, w0[v] * q0.x)));
-                        m[r][1] = fmaf(w3[v], q3.y, fmaf(w2[v], q2.y, fmaf(w1[v], q1.y, w0[v] * q0.y)));
-                        m[r][2] = fmaf(w3[v], q3.z, fmaf(w2[v], q2.z, fmaf(w1[v], q1.z, w0[v] * q0.z)));
-                        m[r][3] = fmaf(w3[v], q3.w, fmaf(w2[v], q2.w, fmaf(w1[v], q1.w, w0[v] * q0.w)));
-                    }
+                    float4 m[3];
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        res[v * 9 + r] = fmaf(m[r][2], pz[v], fmaf(m[r][1], py[v], fmaf(m[r][0], px[v], m[r][3])));
-                        res[v * 9 + 3 + r] = fmaf(m[r][2], nz[v], fmaf(m[r][1], ny[v], m[r][0] * nx[v]));
-                        res[v * 9 + 6 + r] = fmaf(m[r][2], tz[v], fmaf(m[r][1], ty[v], m[r][0] * tx[v]));
+                        Rows4 nxt;  // next row (or row 0 of the next vertex) is requested before this one is consumed
+                        if (r < 2) {
+                            nxt = load_row<REPL>(a0, a1, a2, a3, r + 1);
+                        } else if (v + 1 < kVPT) {
+                            addr(slots[v + 1]);
+                            nxt = load_row<REPL>(a0, a1, a2, a3, 0);
+                        }
+                        m[r] = blend_row(cur, w0[v], w1[v], w2[v], w3[v]);
+                        cur = nxt;
+                    }
+                    const float m0[3] = {m[0].x, m[1].x, m[2].x}, m1[3] = {m[0].y, m[1].y, m[2].y};
+                    const float m2[3] = {m[0].z, m[1].z, m[2].z}, m3[3] = {m[0].w, m[1].w, m[2].w};
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        res[v * 9 + r] = fmaf(m2[r], pz[v], fmaf(m1[r], py[v], fmaf(m0[r], px[v], m3[r])));
+                        res[v * 9 + 3 + r] = fmaf(m2[r], nz[v], fmaf(m1[r], ny[v], m0[r] * nx[v]));
+                        res[v * 9 + 6 + r] = fmaf(m2[r], tz[v], fmaf(m1[r], ty[v], m0[r] * tx[v]));
                     }
                     // flush every 32-byte sector that just became complete
 #pragma unroll
                     for (int sct = (v * 9) / 8; sct < ((v + 1) * 9) / 8; ++sct) st_v8(out + sct * 8, res + sct * 8);
                 }
             }
-            if (i + 1 < my_count) {
-                mbar_wait(&s_bar[consumed & 1u], (consumed >> 1) & 1u);
-                replicate(consumed & 1u);
-                ++consumed;
-            }
-            __syncthreads();
-            if (tid == 0) issue(i + 3);
+            ++q_comp;
+            cid = cid_next;
         }
-        // tile pass boundary: every issued copy has been consumed (issue() stops at my_count)
     }
 }
 
@@ -208,7 +269,7 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms) {
     plan.tile_vertices = tv;
     plan.threads = ((tv / kVPT) + 31) / 32 * 32;
     plan.replicas = kRepl;
-    plan.smem = (size_t)2 * palette_size * 48 * (kRepl + 1) + 16;
+    plan.smem = (size_t)palette_size * 48 * (kNumRepl * kRepl + kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
     int occ = 1;
     cudaFuncSetAttribute(skin_kernel<kRepl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skin_kernel<kRepl>, plan.threads, plan.smem) != cudaSuccess || occ < 1)
