@@ -17,6 +17,7 @@ OK, ERR_INVALID, ERR_FORMAT, ERR_CUDA, ERR_UNSUPPORTED, ERR_JOB = range(6)
 STEP_ADVANCE, STEP_POSE, STEP_CULL, STEP_SKIN, STEP_SKIN_VISIBLE_ONLY = 1, 2, 4, 8, 16
 STEP_ALL = 15
 OUT_MODELS, OUT_LOCALS, OUT_KEY_INDICES = 1, 2, 4
+OPT_FORCE_KEY_SEARCH = 1
 KERNEL_POSE, KERNEL_CULL, KERNEL_SKIN, KERNEL_PACK = 0, 1, 2, 3
 
 # every symbol include/dmk.h declares: (name, restype, argtypes)
@@ -56,6 +57,7 @@ SIGNATURES = [
     ("dmk_crowd_destroy", None, [_vp]),
     ("dmk_crowd_size", _i64, [_vp]),
     ("dmk_crowd_enable_outputs", _i, [_vp, _u32]),
+    ("dmk_crowd_set_option", _i, [_vp, _i, _i]),
     ("dmk_crowd_set_layers", _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f]),
     ("dmk_crowd_update_layers", _i, [_vp, _i, _vp, _vp, _vp]),
     ("dmk_crowd_set_instances", _i, [_vp, _vp, _vp]),
@@ -268,6 +270,9 @@ class Crowd:
         if self.h:
             lib().dmk_crowd_destroy(self.h)
             self.h = None
+
+    def set_option(self, option, value):
+        self.ctx.check(lib().dmk_crowd_set_option(self.h, option, value))
 
     def enable_outputs(self, flags):
         self.ctx.check(lib().dmk_crowd_enable_outputs(self.h, flags))

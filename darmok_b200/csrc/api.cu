@@ -62,6 +62,12 @@ struct dmk_clipset_s {
     uint2* d_value[3] = {nullptr, nullptr, nullptr};
     int32_t* d_stream[3] = {nullptr, nullptr, nullptr};
     float* d_duration = nullptr;
+    // bucket table (see ClipSetDev); absent when a clip does not admit one
+    uint2* d_bucket_dir = nullptr;
+    float4* d_bucket_a = nullptr;
+    uint4* d_bucket_b = nullptr;
+    uint2* d_bucket_c = nullptr;
+    bool has_buckets = false;
 };
 
 struct dmk_armature_s {
@@ -111,6 +117,7 @@ struct dmk_crowd_s {
     int32_t *d_visible_ids = nullptr, *d_visible_count = nullptr, *d_scratch = nullptr;
     float corners[24] = {0};
     bool culled_once = false;
+    bool force_search = false;  // tests: exercise the per-track binary search even when a bucket table exists
     SkinPlan plan{};
 };
 
@@ -238,6 +245,52 @@ bool regroup(const std::vector<Key>& keys, int padded, PackedComponent& pc, uint
                 return false;
             }
     return true;
+}
+
+// Bucket table of one clip (see ClipSetDev).  Returns false when no G <= kMaxBuckets separates the keys.
+constexpr int kMinBuckets = 16, kMaxBuckets = 1024;
+struct BucketTable {
+    std::vector<uint2> dir;
+    std::vector<float4> a;
+    std::vector<uint4> b;
+    std::vector<uint2> c;
+};
+bool build_buckets(const PackedComponent* pc, const uint2* dir, int padded, BucketTable& tbl) {
+    for (int G = kMinBuckets; G <= kMaxBuckets; G *= 2) {
+        bool ok = true;
+        const size_t first = tbl.a.size();
+        tbl.a.resize(first + (size_t)3 * G * padded);
+        tbl.b.resize(tbl.a.size());
+        tbl.c.resize(tbl.a.size());
+        for (int comp = 0; comp < 3 && ok; ++comp) {
+            for (int t = 0; t < padded && ok; ++t) {
+                const uint2 d = dir[comp * padded + t];
+                const float* r = pc[comp].ratio.data() + d.x;
+                const uint2* v = pc[comp].value.data() + d.x;
+                const int n = (int)d.y;
+                int base = 1;
+                for (int b = 0; b < G; ++b) {
+                    const float tb = (float)b / (float)G, te = (float)(b + 1) / (float)G;
+                    while (base < n - 1 && !(r[base] > tb)) ++base;  // first key (>= 1) with ratio > tb, else the last
+                    if (!(base >= n - 2 || r[base + 1] >= te)) { ok = false; break; }
+                    const size_t e = first + ((size_t)comp * G + b) * padded + t;
+                    const bool last = base == n - 1;
+                    tbl.a[e] = make_float4(r[base - 1], r[base], last ? -1.f : r[base + 1], 0.f);
+                    std::memcpy(&tbl.a[e].w, &base, sizeof(int));
+                    tbl.b[e] = make_uint4(v[base - 1].x, v[base - 1].y, v[base].x, v[base].y);
+                    tbl.c[e] = last ? v[base] : v[base + 1];
+                }
+            }
+        }
+        if (ok) {
+            tbl.dir.push_back(make_uint2((uint32_t)first, (uint32_t)G));
+            return true;
+        }
+        tbl.a.resize(first);
+        tbl.b.resize(first);
+        tbl.c.resize(first);
+    }
+    return false;
 }
 }  // namespace
 
@@ -430,6 +483,18 @@ dmk_status dmk_clipset_create(dmk_context_t ctx, dmk_skeleton_t skel, const dmk_
             return fail(ctx, DMK_ERR_FORMAT, err);
         set->durations.push_back(a.duration);
     }
+    // bucket tables need every clip's keys regrouped first: rebuild the per-clip views over the packed arrays
+    BucketTable tbl;
+    bool buckets = true;
+    for (int c = 0; c < num_clips && buckets; ++c)
+        buckets = build_buckets(pc, dir.data() + static_cast<size_t>(c) * 3 * padded, padded, tbl);
+    if (buckets) {
+        DMK_CUDA(ctx, upload(ctx, &set->d_bucket_dir, tbl.dir));
+        DMK_CUDA(ctx, upload(ctx, &set->d_bucket_a, tbl.a));
+        DMK_CUDA(ctx, upload(ctx, &set->d_bucket_b, tbl.b));
+        DMK_CUDA(ctx, upload(ctx, &set->d_bucket_c, tbl.c));
+        set->has_buckets = true;
+    }
     DMK_CUDA(ctx, upload(ctx, &set->d_dir, dir));
     for (int k = 0; k < 3; ++k) {
         DMK_CUDA(ctx, upload(ctx, &set->d_ratio[k], pc[k].ratio));
@@ -451,6 +516,10 @@ void dmk_clipset_destroy(dmk_clipset_t set) {
         dev_free(set->d_stream[k]);
     }
     dev_free(set->d_duration);
+    dev_free(set->d_bucket_dir);
+    dev_free(set->d_bucket_a);
+    dev_free(set->d_bucket_b);
+    dev_free(set->d_bucket_c);
     delete set;
 }
 
@@ -615,6 +684,14 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
     delete c;
 }
 int64_t dmk_crowd_size(dmk_crowd_t c) { return c ? c->n : 0; }
+dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
+    if (!c) return DMK_ERR_INVALID;
+    if (option == DMK_OPT_FORCE_KEY_SEARCH) {
+        c->force_search = value != 0;
+        return DMK_OK;
+    }
+    return fail(c->ctx, DMK_ERR_INVALID, "unknown option");
+}
 
 dmk_status dmk_crowd_enable_outputs(dmk_crowd_t c, uint32_t outputs) {
     if (!c) return DMK_ERR_INVALID;
@@ -748,6 +825,12 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
             p.clips.stream[k] = c->clips->d_stream[k];
         }
         p.clips.duration = c->clips->d_duration;
+        if (c->clips->has_buckets && !c->force_search) {
+            p.clips.bucket_dir = c->clips->d_bucket_dir;
+            p.clips.bucket_a = c->clips->d_bucket_a;
+            p.clips.bucket_b = c->clips->d_bucket_b;
+            p.clips.bucket_c = c->clips->d_bucket_c;
+        }
         p.clips.num_clips = c->clips->num_clips;
         p.clips.padded_tracks = c->clips->padded_tracks;
         p.skel.parents = c->skel->d_parents;

@@ -20,6 +20,15 @@ struct ClipSetDev {
     const float* duration;   // [num_clips]
     int num_clips;
     int padded_tracks;       // P = 4 * num_soa
+    // Bucket table (null when a clip has tracks too dense for it: the kernel then searches the tracks above).
+    // Time is cut into G = 2^k buckets per clip such that a bucket holds at most one key boundary of any track, so
+    // for t in bucket b the bracketing keys are (base-1, base) or (base, base+1) with base = first key > b/G.
+    // Entries are laid out [clip][component][bucket][track]: the 32 lanes of a warp (consecutive tracks) read
+    // consecutive entries -- one coalesced request per field instead of a per-lane binary search.
+    const uint2* bucket_dir; // [num_clips] : {first entry, G}
+    const float4* bucket_a;  // {ratio[base-1], ratio[base], ratio[base+1] or -1 when base is the last key, base as int bits}
+    const uint4* bucket_b;   // {value[base-1], value[base]}
+    const uint2* bucket_c;   // value[base+1]
 };
 
 struct SkeletonDev {

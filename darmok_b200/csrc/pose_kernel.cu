@@ -40,6 +40,53 @@ __device__ __forceinline__ void find_keys(const float* __restrict__ ratio, uint2
     left = right - 1;
 }
 
+// The two bracketing keys of one track at ratio t: ratios, packed values and (optionally) the ozz stream indices.
+struct Bracket {
+    float r0, r1;
+    uint2 v0, v1;
+};
+
+__device__ __forceinline__ Bracket fetch_bracket(const ClipSetDev& cs, int comp, int clip, int track, float t,
+                                                 int32_t* key_out) {
+    Bracket k;
+    const int P = cs.padded_tracks;
+    if (cs.bucket_dir) {
+        // bucket table: one coalesced 40-byte entry per (bucket, track)
+        const uint2 bd = __ldg(cs.bucket_dir + clip);
+        const int G = (int)bd.y;
+        int b = (int)(t * (float)G);  // G is a power of two: exact
+        b = b < G - 1 ? b : G - 1;
+        const size_t e = (size_t)bd.x + ((size_t)comp * G + b) * P + track;
+        const float4 a = __ldg(cs.bucket_a + e);
+        const uint4 vb = __ldg(cs.bucket_b + e);
+        const uint2 vc = __ldg(cs.bucket_c + e);
+        const bool lower = (a.y > t) || (a.z < 0.f);
+        k.r0 = lower ? a.x : a.y;
+        k.r1 = lower ? a.y : a.z;
+        k.v0 = lower ? make_uint2(vb.x, vb.y) : make_uint2(vb.z, vb.w);
+        k.v1 = lower ? make_uint2(vb.z, vb.w) : vc;
+        if (key_out) {
+            const uint2 d = __ldg(cs.dir + (size_t)(clip * 3 + comp) * P + track);
+            const int right = (int)d.x + __float_as_int(a.w) + (lower ? 0 : 1);
+            key_out[0] = __ldg(cs.stream[comp] + right - 1);
+            key_out[1] = __ldg(cs.stream[comp] + right);
+        }
+        return k;
+    }
+    const uint2 d = __ldg(cs.dir + (size_t)(clip * 3 + comp) * P + track);
+    int l, r;
+    find_keys(cs.ratio[comp], d, t, l, r);
+    k.r0 = __ldg(cs.ratio[comp] + l);
+    k.r1 = __ldg(cs.ratio[comp] + r);
+    k.v0 = __ldg(cs.value[comp] + l);
+    k.v1 = __ldg(cs.value[comp] + r);
+    if (key_out) {
+        key_out[0] = __ldg(cs.stream[comp] + l);
+        key_out[1] = __ldg(cs.stream[comp] + r);
+    }
+    return k;
+}
+
 __device__ __forceinline__ float half_bits_to_float(unsigned h) {
     return __half2float(__ushort_as_half((unsigned short)h));
 }
@@ -47,15 +94,9 @@ __device__ __forceinline__ float half_bits_to_float(unsigned h) {
 // Float3 track (translation or scale): DecompressFloat3 + Lerp
 __device__ __forceinline__ void sample_f3(const ClipSetDev& cs, int comp, int clip, int track, float t, float out[3],
                                           int32_t* key_out) {
-    const uint2 d = __ldg(cs.dir + (size_t)(clip * 3 + comp) * cs.padded_tracks + track);
-    int l, r;
-    find_keys(cs.ratio[comp], d, t, l, r);
-    const float r0 = __ldg(cs.ratio[comp] + l), r1 = __ldg(cs.ratio[comp] + r);
-    const uint2 v0 = __ldg(cs.value[comp] + l), v1 = __ldg(cs.value[comp] + r);
-    if (key_out) {
-        key_out[0] = __ldg(cs.stream[comp] + l);
-        key_out[1] = __ldg(cs.stream[comp] + r);
-    }
+    const Bracket k = fetch_bracket(cs, comp, clip, track, t, key_out);
+    const float r0 = k.r0, r1 = k.r1;
+    const uint2 v0 = k.v0, v1 = k.v1;
     const float alpha = (t - r0) * rcp_exact(r1 - r0);
     const float a[3] = {half_bits_to_float(v0.x & 0xffffu), half_bits_to_float(v0.x >> 16), half_bits_to_float(v0.y & 0xffffu)};
     const float b[3] = {half_bits_to_float(v1.x & 0xffffu), half_bits_to_float(v1.x >> 16), half_bits_to_float(v1.y & 0xffffu)};
@@ -85,15 +126,9 @@ __device__ __forceinline__ void decode_quat(uint2 v, float q[4]) {
 // rotation track: decode both keys, NLerpEst
 __device__ __forceinline__ void sample_quat(const ClipSetDev& cs, int clip, int track, float t, float out[4],
                                             int32_t* key_out) {
-    const uint2 d = __ldg(cs.dir + (size_t)(clip * 3 + 1) * cs.padded_tracks + track);
-    int l, r;
-    find_keys(cs.ratio[1], d, t, l, r);
-    const float r0 = __ldg(cs.ratio[1] + l), r1 = __ldg(cs.ratio[1] + r);
-    const uint2 v0 = __ldg(cs.value[1] + l), v1 = __ldg(cs.value[1] + r);
-    if (key_out) {
-        key_out[0] = __ldg(cs.stream[1] + l);
-        key_out[1] = __ldg(cs.stream[1] + r);
-    }
+    const Bracket k = fetch_bracket(cs, 1, clip, track, t, key_out);
+    const float r0 = k.r0, r1 = k.r1;
+    const uint2 v0 = k.v0, v1 = k.v1;
     const float alpha = (t - r0) * rcp_exact(r1 - r0);
     float a[4], b[4], q[4];
     decode_quat(v0, a);

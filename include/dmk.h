@@ -118,6 +118,10 @@ DMK_API dmk_status dmk_crowd_create(dmk_context_t ctx, dmk_skeleton_t skel, dmk_
                                     dmk_mesh_t mesh, int64_t num_characters, int max_layers, dmk_crowd_t* out);
 DMK_API void dmk_crowd_destroy(dmk_crowd_t crowd);
 DMK_API int64_t dmk_crowd_size(dmk_crowd_t crowd);
+/* Tuning / test switches.  DMK_OPT_FORCE_KEY_SEARCH: sample with the per-track binary search even when the clip
+ * set carries the bucket table (both paths must give identical key indices). */
+enum { DMK_OPT_FORCE_KEY_SEARCH = 1 };
+DMK_API dmk_status dmk_crowd_set_option(dmk_crowd_t crowd, int option, int value);
 
 /* Optional per-character outputs that only the host-side getters need (they cost HBM writes per step):
  * models -> dmk_crowd_get_models, locals -> dmk_crowd_get_locals, key indices -> dmk_crowd_get_key_indices. */

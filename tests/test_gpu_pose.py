@@ -191,3 +191,43 @@ def test_small_and_odd_skeletons():
             assert_close(crowd.get_palette(), ref["palette"], f"palette J={joints}")
         finally:
             g.close()
+
+
+def test_bucket_table_and_binary_search_agree(rigs):
+    # the coalesced bucket-table lookup and the per-track binary search are two routes to the same key pair
+    g, o, a = rigs
+    n = 500
+    cr = synth.make_crowd(n, 2, len(a.clips), seed=9)
+    cr.ratio[0, :64] = np.arange(64, dtype=np.float32) / 64.0      # bucket boundaries of G = 64
+    cr.ratio[1, :64] = np.nextafter(cr.ratio[0, :64], np.float32(2))
+    out = []
+    for force in (0, 1):
+        crowd = g.crowd(n, 2, mesh=False)
+        crowd.set_option(g.capi.OPT_FORCE_KEY_SEARCH, force)
+        crowd.enable_outputs(g.capi.OUT_KEY_INDICES)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, threshold=FLT_MIN)
+        crowd.step(0.0, g.capi.STEP_POSE)
+        out.append((crowd.get_key_indices(), crowd.get_palette()))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][0], _oracle_key_indices(o, a, cr))
+
+
+def test_dense_clip_falls_back_to_search():
+    # 1501 keys per track: no bucket count <= 1024 isolates the keys, the clip set keeps the binary search
+    skel = synth.make_skeleton(12, seed=3)
+    clips = [synth.make_clip(skel, "dense", seed=1, duration=1.0, hz=1500.0, drop=0.1)]
+    a = common.Assets(skel, clips, synth.make_armature(skel, seed=3), synth.make_mesh(8, 12))
+    g, o = GpuRig(a, with_mesh=False), OracleRig(a)
+    try:
+        n = 256
+        cr = synth.make_crowd(n, 1, 1, seed=10)
+        crowd = g.crowd(n, 1, mesh=False)
+        crowd.enable_outputs(g.capi.OUT_KEY_INDICES)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight)
+        crowd.step(0.0, g.capi.STEP_POSE)
+        assert np.array_equal(crowd.get_key_indices(), _oracle_key_indices(o, a, cr))
+        ref = o.crowd(n, 1).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, want=("palette",))
+        assert_close(crowd.get_palette(), ref["palette"], "palette")
+    finally:
+        g.close()
