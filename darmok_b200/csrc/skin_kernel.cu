@@ -28,7 +28,8 @@ namespace dmk {
 namespace {
 
 constexpr int kVPT = 8;           // vertices per thread: lcm(36 B, 32 B) / 36 B
-constexpr int kMaxThreads = 320;  // 65536 registers / 204
+constexpr int kMaxThreads = 256;  // 8 warps = 2 per SM sub-partition (16K registers each): up to 255 registers per thread;
+                                  // a 3rd warp per sub-partition (any block of 9..12 warps) would cap the kernel at 168
 constexpr int kRepl = 8;          // palette replicas = bank groups of a 16-byte access
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -217,6 +218,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
                 float res[kVPT * 9];
                 uint32_t a0, a1, a2, a3;
                 auto addr = [&](uint32_t s) {
+                    // opaque to the optimiser: otherwise the 32 (vertex, slot) offsets are hoisted out of the
+                    // character loop and cost 24 more live registers than the 8 packed slot words
+                    asm volatile("" : "+r"(s));
                     a0 = base + (s & 0xffu) * (48u * REPL);
                     a1 = base + ((s >> 8) & 0xffu) * (48u * REPL);
                     a2 = base + ((s >> 16) & 0xffu) * (48u * REPL);
