@@ -112,7 +112,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -200,35 +200,23 @@ def run_gpu(args):
         _, vis0 = crowd.get_visibility()
         cap = min(n, int(vis0 * 1.25) + 1024)
         packed = torch.empty((cap, ps, 16), dtype=torch.float32, device=dev)
-        counts = torch.zeros(world, dtype=torch.int32, device=dev)
-        count_t = torch.zeros(1, dtype=torch.int32, device=dev)
-        gathered = None
         # device int32 count written by the compaction kernel, viewed as a torch tensor without a copy
         vis_count = torch.as_tensor(_DevInt32(crowd.visible_count_dev()), device=dev)
-        flags = capi.STEP_ADVANCE | capi.STEP_POSE | capi.STEP_CULL | capi.STEP_SKIN
+        flags_pre = capi.STEP_ADVANCE | capi.STEP_POSE | capi.STEP_CULL
+
+        # the one exchange of the path: visible palettes to the render GPU (rank 0).  Fixed-capacity
+        # slabs + a device-side count per rank: no host synchronisation inside the step.
+        gatherer = None
+        if world > 1:
+            from darmok_b200.parallel import VisiblePaletteGather
+            gatherer = VisiblePaletteGather(cap, ps, dev, dst=0)
 
         def step():
-            nonlocal gathered
-            crowd.step(DT, flags)
+            crowd.step(DT, flags_pre)                       # clocks + pose + cull + compaction
             crowd.pack_visible_palettes(packed.data_ptr(), cap)
-            if world > 1:
-                # the one exchange of the path: visible palettes to the render GPU (rank 0), sizes first
-                dist.all_gather_into_tensor(counts, vis_count)
-                sizes = counts.cpu().tolist()
-                if rank == 0:
-                    if gathered is None or gathered.shape[0] < sum(sizes):
-                        gathered = torch.empty((int(sum(sizes) * 1.25) + 1024, ps, 16), dtype=torch.float32, device=dev)
-                    ops, off = [], sizes[0]
-                    for r in range(1, world):
-                        if sizes[r]:
-                            ops.append(dist.P2POp(dist.irecv, gathered[off:off + sizes[r]], r))
-                        off += sizes[r]
-                    if ops:
-                        for w in dist.batch_isend_irecv(ops):
-                            w.wait()
-                elif sizes[rank]:
-                    for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, packed[:min(sizes[rank], cap)], 0)]):
-                        w.wait()
+            if gatherer is not None:
+                gatherer.gather(packed, vis_count)          # NCCL over NVLink, stream-ordered
+            crowd.step(DT, capi.STEP_SKIN)                  # LBS of every vertex of every character
 
         for _ in range(args.warmup):
             step()
@@ -353,7 +341,7 @@ def run_gpu(args):
                                "skin": skin_avg_ms, "pack_visible_palettes": pack_ms / max(1, pack_n)},
         "visible_characters_rank0": int(vis0),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -366,7 +354,20 @@ class _DevInt32:
         self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
 
 
+def emit(line: dict):
+    """The one JSON line, on the real stdout (fd 1 is pointed at stderr while the run is in progress so that library
+    chatter such as NCCL's version banner cannot get in front of it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -1,0 +1,64 @@
+// ubench_store.cu -- microbenchmark: cost of global store patterns on sm_100a (time + l1tex wavefronts under ncu).
+// Patterns write the same N bytes:  0: st.v8 per lane, lanes 288 B apart (the skin kernel's pattern)
+//                                   1: st.v4 fully coalesced (lane i -> base + 16 i)
+//                                   2: st.v8 coalesced (lane i -> base + 32 i)
+//                                   3: st.v4 x2 per 32 B, lanes 288 B apart
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_store tools/ubench_store.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ void st8(float* p, float v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st4(float* p, float v) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(p), "f"(v) : "memory");
+}
+
+template <int PATTERN>
+__global__ void __launch_bounds__(256) k(float* out, size_t chunks_per_block, float v) {
+    // each block writes chunks of 256 threads * 288 B = 73728 B
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (size_t c = 0; c < chunks_per_block; ++c) {
+        float* base = out + ((size_t)blockIdx.x * chunks_per_block + c) * (256 * 72);
+        float* wbase = base + warp * (32 * 72);
+        if (PATTERN == 0) {
+#pragma unroll
+            for (int s = 0; s < 9; ++s) st8(wbase + lane * 72 + s * 8, v);
+        } else if (PATTERN == 1) {
+#pragma unroll
+            for (int s = 0; s < 18; ++s) st4(wbase + s * 128 + lane * 4, v);
+        } else if (PATTERN == 2) {
+#pragma unroll
+            for (int s = 0; s < 9; ++s) st8(wbase + s * 256 + lane * 8, v);
+        } else {
+#pragma unroll
+            for (int s = 0; s < 9; ++s) { st4(wbase + lane * 72 + s * 8, v); st4(wbase + lane * 72 + s * 8 + 4, v); }
+        }
+    }
+}
+
+int main() {
+    const size_t chunks_per_block = 1600, blocks = 148;
+    const size_t bytes = blocks * chunks_per_block * 256 * 288;
+    float* d;
+    cudaMalloc(&d, bytes);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int pat = 0; pat < 4; ++pat) {
+        float best = 1e9;
+        for (int it = 0; it < 4; ++it) {
+            cudaEventRecord(e0);
+            if (pat == 0) k<0><<<blocks, 256>>>(d, chunks_per_block, 1.f);
+            if (pat == 1) k<1><<<blocks, 256>>>(d, chunks_per_block, 1.f);
+            if (pat == 2) k<2><<<blocks, 256>>>(d, chunks_per_block, 1.f);
+            if (pat == 3) k<3><<<blocks, 256>>>(d, chunks_per_block, 1.f);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (ms < best) best = ms;
+        }
+        printf("pattern %d: %.3f ms  %.1f GB/s  (%zu bytes)\n", pat, best, bytes / best / 1e6, bytes);
+    }
+    printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+}
