@@ -18,6 +18,10 @@ STEP_ADVANCE, STEP_POSE, STEP_CULL, STEP_SKIN, STEP_SKIN_VISIBLE_ONLY = 1, 2, 4,
 STEP_ALL = 15
 OUT_MODELS, OUT_LOCALS, OUT_KEY_INDICES = 1, 2, 4
 OPT_FORCE_KEY_SEARCH = 1
+GROUP_BLEND, GROUP_PASSTHROUGH = 0, 1
+TOP_GROUP0, TOP_TRANSITION, TOP_REST_POSE, TOP_SKIP = 0, 1, 2, 3
+PROGRAM_DTYPE = np.dtype([("n0", "u1"), ("n1", "u1"), ("rest0", "u1"), ("rest1", "u1"), ("mode0", "u1"), ("mode1", "u1"),
+                          ("top", "u1"), ("reserved", "u1"), ("threshold0", "f4"), ("threshold1", "f4"), ("w0", "f4"), ("w1", "f4")])
 KERNEL_POSE, KERNEL_CULL, KERNEL_SKIN, KERNEL_PACK = 0, 1, 2, 3
 
 # every symbol include/dmk.h declares: (name, restype, argtypes)
@@ -59,6 +63,7 @@ SIGNATURES = [
     ("dmk_crowd_enable_outputs", _i, [_vp, _u32]),
     ("dmk_crowd_set_option", _i, [_vp, _i, _i]),
     ("dmk_crowd_set_layers", _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f]),
+    ("dmk_crowd_set_programs", _i, [_vp, _i, _vp, _vp, _vp, _vp]),
     ("dmk_crowd_update_layers", _i, [_vp, _i, _vp, _vp, _vp]),
     ("dmk_crowd_set_instances", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_set_camera", _i, [_vp, _vp, _f]),
@@ -284,6 +289,14 @@ class Crowd:
         self.num_layers = clip.shape[0]
         self.ctx.check(lib().dmk_crowd_set_layers(self.h, self.num_layers, _ptr(clip), _ptr(ratio), _ptr(weight), _ptr(speed),
                                                   _ptr(loop), threshold))
+
+    def set_programs(self, clip, ratio, weight, programs):
+        """programs: structured array of PROGRAM_DTYPE, one per character"""
+        clip = np.ascontiguousarray(clip, np.int32)
+        ratio, weight = _f32(ratio), _f32(weight)
+        programs = np.ascontiguousarray(programs, PROGRAM_DTYPE)
+        self.num_layers = clip.shape[0]
+        self.ctx.check(lib().dmk_crowd_set_programs(self.h, self.num_layers, _ptr(clip), _ptr(ratio), _ptr(weight), _ptr(programs)))
 
     def update_layers(self, clip, ratio, weight):
         self.ctx.check(lib().dmk_crowd_update_layers(self.h, self.num_layers, _ptr(clip), _ptr(ratio), _ptr(weight)))

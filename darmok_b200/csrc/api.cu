@@ -44,6 +44,7 @@ struct dmk_skeleton_s {
     SkeletonData data;
     int16_t* d_parents = nullptr;
     uint16_t* d_schedule = nullptr;
+    float* d_rest = nullptr;  // [P][10]
     int rounds = 0;
 };
 
@@ -102,6 +103,8 @@ struct dmk_crowd_s {
     int32_t* d_clip = nullptr;
     float *d_ratio = nullptr, *d_weight = nullptr, *d_speed = nullptr;
     uint8_t *d_loop = nullptr, *d_looped = nullptr;
+    PoseProgram* d_program = nullptr;  // [n], allocated by dmk_crowd_set_programs
+    bool use_program = false;
     // pinned staging for the per-frame host state machine
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -414,6 +417,13 @@ dmk_status dmk_skeleton_load_ozz(dmk_context_t ctx, const void* bytes, size_t si
     skel->rounds = static_cast<int>(sched.size() / 32);
     DMK_CUDA(ctx, upload(ctx, &skel->d_parents, skel->data.parents));
     DMK_CUDA(ctx, upload(ctx, &skel->d_schedule, sched));
+    {
+        const int P = skel->data.num_soa() * 4;
+        std::vector<float> rest(static_cast<size_t>(P) * 10);
+        for (int j = 0; j < P; ++j)
+            for (int k = 0; k < 10; ++k) rest[static_cast<size_t>(j) * 10 + k] = skel->data.rest_soa[static_cast<size_t>(j / 4) * 40 + k * 4 + (j & 3)];
+        DMK_CUDA(ctx, upload(ctx, &skel->d_rest, rest));
+    }
     *out = skel.release();
     return DMK_OK;
 }
@@ -423,6 +433,7 @@ void dmk_skeleton_destroy(dmk_skeleton_t skel) {
     cudaSetDevice(skel->ctx->device);
     dev_free(skel->d_parents);
     dev_free(skel->d_schedule);
+    dev_free(skel->d_rest);
     delete skel;
 }
 int dmk_skeleton_num_joints(dmk_skeleton_t skel) { return skel ? skel->data.num_joints : 0; }
@@ -675,7 +686,7 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
     for (void* p : {(void*)c->d_clip, (void*)c->d_ratio, (void*)c->d_weight, (void*)c->d_speed, (void*)c->d_loop, (void*)c->d_looped,
-                    (void*)c->d_palette, (void*)c->d_palette34, (void*)c->d_skinned, (void*)c->d_models, (void*)c->d_locals,
+                    (void*)c->d_program, (void*)c->d_palette, (void*)c->d_palette34, (void*)c->d_skinned, (void*)c->d_models, (void*)c->d_locals,
                     (void*)c->d_key_indices, (void*)c->d_error, (void*)c->d_world_inverse, (void*)c->d_bbox, (void*)c->d_vis_bits,
                     (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch})
         dev_free(p);
@@ -747,6 +758,54 @@ dmk_status dmk_crowd_set_layers(dmk_crowd_t c, int num_layers, const int32_t* cl
     c->num_layers = num_layers;
     c->threshold = threshold;
     c->layers_set = true;
+    c->use_program = false;
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_set_programs(dmk_crowd_t c, int num_layers, const int32_t* clip, const float* ratio, const float* weight,
+                                  const dmk_pose_program* programs) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    static_assert(sizeof(dmk_pose_program) == sizeof(PoseProgram), "C ABI struct and device struct must match");
+    if (num_layers < 1 || num_layers > c->max_layers) return fail(ctx, DMK_ERR_INVALID, "num_layers out of range");
+    if (!clip || !ratio || !weight || !programs) return fail(ctx, DMK_ERR_INVALID, "null argument");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t n = static_cast<size_t>(c->n);
+    for (size_t i = 0; i < n; ++i) {
+        const dmk_pose_program& g = programs[i];
+        if (g.top > DMK_TOP_SKIP || g.mode0 > DMK_GROUP_PASSTHROUGH || g.mode1 > DMK_GROUP_PASSTHROUGH || g.num_layers0 + g.num_layers1 > num_layers)
+            return fail(ctx, DMK_ERR_INVALID, "malformed pose program for character " + std::to_string(i));
+        if (g.top == DMK_TOP_SKIP || g.top == DMK_TOP_REST_POSE) continue;
+        const int groups = g.top == DMK_TOP_TRANSITION ? 2 : 1;
+        for (int k = 0; k < groups; ++k) {
+            const int cnt = k ? g.num_layers1 : g.num_layers0, rest = k ? g.rest1 : g.rest0, mode = k ? g.mode1 : g.mode0;
+            const float th = k ? g.threshold1 : g.threshold0;
+            if (cnt < 1 || rest >= cnt) return fail(ctx, DMK_ERR_INVALID, "malformed pose program for character " + std::to_string(i));
+            // BlendingJob::Validate: threshold > 0 (darmok reports "error in the blending job", src/skeleton_ozz.cpp:605-608)
+            if (mode == DMK_GROUP_BLEND && !(th > 0.f)) return fail(ctx, DMK_ERR_JOB, "error in the blending job");
+        }
+        for (int l = 0; l < g.num_layers0 + g.num_layers1; ++l)
+            if (clip[static_cast<size_t>(l) * n + i] < 0 || clip[static_cast<size_t>(l) * n + i] >= c->clips->num_clips)
+                return fail(ctx, DMK_ERR_INVALID, "layer references a clip outside the clip set");
+    }
+    if (!c->d_program) DMK_CUDA(ctx, dev_alloc(&c->d_program, n));
+    const size_t lbytes = static_cast<size_t>(num_layers) * n * 4, pbytes = n * sizeof(PoseProgram);
+    if (dmk_status st = ensure_stage(c, 3 * lbytes + pbytes)) return st;
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // previous copies out of the staging area have drained
+    char* h = static_cast<char*>(c->h_stage);
+    std::memcpy(h, clip, lbytes);
+    std::memcpy(h + lbytes, ratio, lbytes);
+    std::memcpy(h + 2 * lbytes, weight, lbytes);
+    std::memcpy(h + 3 * lbytes, programs, pbytes);
+    cudaStream_t s = ctx->stream;
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_clip, h, lbytes, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_ratio, h + lbytes, lbytes, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_weight, h + 2 * lbytes, lbytes, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_program, h + 3 * lbytes, pbytes, cudaMemcpyHostToDevice, s));
+    c->num_layers = num_layers;
+    c->layers_set = true;
+    c->use_program = true;
+    c->has_loop = false;
     return DMK_OK;
 }
 
@@ -816,7 +875,9 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
     if (flags & DMK_STEP_POSE) {
         if (!c->layers_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_layers has not been called");
         // BlendingJob::Validate: threshold > 0 (darmok: "error in the blending job", src/skeleton_ozz.cpp:605-608)
-        if (c->num_layers > 1 && !(c->threshold > 0.f)) return fail(ctx, DMK_ERR_JOB, "error in the blending job");
+        if (!c->use_program && c->num_layers > 1 && !(c->threshold > 0.f)) return fail(ctx, DMK_ERR_JOB, "error in the blending job");
+        if (c->use_program && (flags & DMK_STEP_ADVANCE))
+            return fail(ctx, DMK_ERR_UNSUPPORTED, "pose programs carry host-resolved ratios: do not combine them with DMK_STEP_ADVANCE");
         PoseParams p{};
         p.clips.dir = c->clips->d_dir;
         for (int k = 0; k < 3; ++k) {
@@ -835,6 +896,7 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         p.clips.padded_tracks = c->clips->padded_tracks;
         p.skel.parents = c->skel->d_parents;
         p.skel.schedule = c->skel->d_schedule;
+        p.skel.rest = c->skel->d_rest;
         p.skel.num_joints = c->skel->data.num_joints;
         p.skel.padded_joints = c->skel->data.num_soa() * 4;
         p.skel.num_soa = c->skel->data.num_soa();
@@ -853,6 +915,7 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         p.loop = c->has_loop ? c->d_loop : nullptr;
         p.looped = c->d_looped;
         p.threshold = c->threshold;
+        p.program = c->use_program ? c->d_program : nullptr;
         p.dt = dt;
         p.advance = (flags & DMK_STEP_ADVANCE) ? 1 : 0;
         p.palette = c->d_palette;

@@ -31,8 +31,25 @@ struct ClipSetDev {
     const uint2* bucket_c;   // value[base+1]
 };
 
+// Per-character pose program: what the animator state machine resolves a tick into.  A character has up to two
+// GROUPS of layers (the previous and the current state of a transition, src/skeleton_ozz.cpp:682-726); a group is
+// either a BlendingJob over its layers (:556-608) or the pass-through of one of them (single-clip state :552-555,
+// :617-624, or the early exit when a clip sits exactly at the blend position :588-593).
+struct PoseProgram {
+    uint8_t n0, n1;        // layers of group 0 = [0, n0), of group 1 = [n0, n0 + n1)
+    uint8_t rest0, rest1;  // blend: index (within the group) of the rest-pose layer; pass-through: the layer to copy
+    uint8_t mode0, mode1;  // kGroupBlend / kGroupPassthrough
+    uint8_t top;           // kTopGroup0 / kTopTransition / kTopRestPose / kTopSkip
+    uint8_t reserved;
+    float threshold0, threshold1;  // BlendingJob::threshold of each group
+    float w0, w1;          // transition layer weights (1 - v, v); threshold is bx::kFloatSmallest
+};
+constexpr uint8_t kGroupBlend = 0, kGroupPassthrough = 1;
+constexpr uint8_t kTopGroup0 = 0, kTopTransition = 1, kTopRestPose = 2, kTopSkip = 3;
+
 struct SkeletonDev {
     const int16_t* parents;   // [J]
+    const float* rest;        // [P][10] rest pose per joint: T.xyz R.xyzw S.xyz (ozz joint_rest_poses, AoS)
     const uint16_t* schedule; // [rounds][32] local-to-model tasks: joint | column << 12, kIdleTask = none
     int num_joints;           // J
     int padded_joints;        // P
@@ -60,6 +77,7 @@ struct PoseParams {
     const uint8_t* loop;      // may be null (all loop)
     uint8_t* looped;
     float threshold;
+    const PoseProgram* program;  // [N] or null: flat mode (one group of num_layers layers, uniform threshold)
     float dt;
     int advance;              // run the clip clocks before sampling
     // outputs (null = skip)

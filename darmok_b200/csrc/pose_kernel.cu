@@ -168,6 +168,103 @@ __device__ __forceinline__ void blend_n_pass(Xform& acc, const Xform& in, float 
     for (int c = 0; c < 3; ++c) acc.s[c] = acc.s[c] + in.s[c] * w;
 }
 
+// Normalize step of BlendingJob for one joint
+__device__ __forceinline__ void blend_normalize(Xform& acc, float inv_weight) {
+    const float len2 = acc.r[0] * acc.r[0] + acc.r[1] * acc.r[1] + acc.r[2] * acc.r[2] + acc.r[3] * acc.r[3];
+    const float inv_len = rsqrt_exact(len2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc.r[k] = acc.r[k] * inv_len;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { acc.t[k] = acc.t[k] * inv_weight; acc.s[k] = acc.s[k] * inv_weight; }
+}
+
+__device__ __forceinline__ void blend_first_pass(Xform& acc, const Xform& in, float w) {  // OZZ_BLEND_1ST_PASS
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc.t[k] = in.t[k] * w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc.r[k] = in.r[k] * w;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc.s[k] = in.s[k] * w;
+}
+
+// One group of layers [begin, begin + count) of a character, for joint jt.  Must be called by the whole warp: the layer
+// state (clip, ratio, weight) lives in lanes 0..L-1 and is broadcast with shuffles.
+__device__ __forceinline__ Xform eval_group(const ClipSetDev& cs, int my_clip, float my_ratio, float my_weight, int begin, int count,
+                                            int mode, int rest_idx, float threshold, int jt, int32_t* key_base, int P) {
+    Xform acc;
+    if (mode == kGroupPassthrough) {
+        // every clip of a state is sampled each tick (:538-545); only one of them is the pose
+        for (int l = begin; l < begin + count; ++l) {
+            const bool chosen = l == begin + rest_idx;
+            if (!chosen && !key_base) continue;
+            const int cl = __shfl_sync(0xffffffffu, my_clip, l);
+            const float tl = __shfl_sync(0xffffffffu, my_ratio, l);
+            Xform in;
+            sample_joint(cs, cl, jt, tl, in, key_base ? key_base + (size_t)l * 3 * P * 2 : nullptr);
+            if (chosen) acc = in;
+        }
+        return acc;
+    }
+    // BlendingJob bookkeeping is independent of the joint: accumulated weight, passes, rest-pose weight
+    float accumulated = 0.f;
+    int num_passes = 0;
+    for (int l = begin; l < begin + count; ++l) {
+        const float w = __shfl_sync(0xffffffffu, my_weight, l);
+        if (!(w <= 0.f)) { accumulated += w; ++num_passes; }
+    }
+    const float bp_weight = threshold - accumulated;
+    const bool need_rest = bp_weight > 0.f;
+    float norm_weight = accumulated;
+    if (need_rest) norm_weight = (num_passes == 0) ? 1.f : threshold;
+    const float inv_weight = rcp_exact(norm_weight);
+    Xform rest;
+    int pass = 0;
+#pragma unroll 1
+    for (int l = begin; l < begin + count; ++l) {
+        const float w = __shfl_sync(0xffffffffu, my_weight, l);
+        const int cl = __shfl_sync(0xffffffffu, my_clip, l);
+        const float tl = __shfl_sync(0xffffffffu, my_ratio, l);
+        const bool contributes = !(w <= 0.f);
+        const bool is_rest = need_rest && l == begin + rest_idx;
+        if (!contributes && !is_rest && !key_base) continue;
+        Xform in;
+        sample_joint(cs, cl, jt, tl, in, key_base ? key_base + (size_t)l * 3 * P * 2 : nullptr);
+        if (is_rest) rest = in;
+        if (!contributes) continue;
+        if (pass == 0) blend_first_pass(acc, in, w);
+        else blend_n_pass(acc, in, w);
+        ++pass;
+    }
+    if (need_rest) {  // BlendRestPose
+        if (pass == 0) acc = rest;
+        else blend_n_pass(acc, rest, bp_weight);
+    }
+    blend_normalize(acc, inv_weight);
+    return acc;
+}
+
+// The transition's BlendingJob: layers (w0, a), (w1, b), rest pose = a (src/skeleton_ozz.cpp:709-724)
+__device__ __forceinline__ Xform blend_two(const Xform& a, const Xform& b, float w0, float w1, float threshold) {
+    Xform acc;
+    float accumulated = 0.f;
+    int pass = 0;
+    if (!(w0 <= 0.f)) { accumulated += w0; blend_first_pass(acc, a, w0); ++pass; }
+    if (!(w1 <= 0.f)) {
+        accumulated += w1;
+        if (pass == 0) blend_first_pass(acc, b, w1);
+        else blend_n_pass(acc, b, w1);
+        ++pass;
+    }
+    const float bp_weight = threshold - accumulated;
+    float norm_weight = accumulated;
+    if (bp_weight > 0.f) {
+        if (pass == 0) { acc = a; norm_weight = 1.f; }
+        else { blend_n_pass(acc, a, bp_weight); norm_weight = threshold; }
+    }
+    blend_normalize(acc, rcp_exact(norm_weight));
+    return acc;
+}
+
 // SoaFloat4x4::FromAffine for one joint -> 3x4 affine, columns of 3 (m[c*3 + r])
 __device__ __forceinline__ void from_affine(const Xform& x, float* m) {
     const float qx = x.r[0], qy = x.r[1], qz = x.r[2], qw = x.r[3];
@@ -222,11 +319,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
     const int64_t warps_total = (int64_t)gridDim.x * kWarpsPerBlock;
 
     for (int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + warp; c < n; c += warps_total) {
+        // ---- pose program of this character (warp-uniform) ----
+        PoseProgram prog;
+        if (p.program) {
+            prog = p.program[c];
+        } else {  // flat mode: one group; a state with a single clip never runs BlendingJob (:552-555, :617-624)
+            prog.n0 = (uint8_t)L; prog.n1 = 0; prog.rest0 = 0; prog.rest1 = 0;
+            prog.mode0 = L == 1 ? kGroupPassthrough : kGroupBlend; prog.mode1 = kGroupPassthrough;
+            prog.top = kTopGroup0; prog.reserved = 0;
+            prog.threshold0 = p.threshold; prog.threshold1 = p.threshold; prog.w0 = 1.f; prog.w1 = 0.f;
+        }
+        if (prog.top == kTopSkip) continue;  // no state: the animator keeps its previous matrices (:1029-1032)
+
         // ---- layer state + clip clock: lane l owns layer l, values are broadcast with shuffles ----
         int my_clip = 0;
         float my_ratio = 0.f, my_weight = 0.f;
         bool my_bad = false;
-        if (lane < L) {
+        const int used_layers = p.program ? prog.n0 + prog.n1 : L;
+        if (lane < used_layers) {
             const int64_t idx = (int64_t)lane * n + c;
             int ci = p.clip[idx];
             float t = p.ratio[idx];
@@ -258,21 +368,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
             if (lane == 0) atomicCAS(p.error_flag, 0, (int32_t)min(c + 1, (int64_t)0x7fffffff));
             continue;
         }
-        // BlendingJob bookkeeping is independent of the joint: accumulated weight, passes, rest-pose weight
-        float accumulated = 0.f;
-        int num_passes = 0;
-        if (L > 1) {
-            for (int l = 0; l < L; ++l) {
-                const float w = __shfl_sync(0xffffffffu, my_weight, l);
-                if (!(w <= 0.f)) { accumulated += w; ++num_passes; }
-            }
-        }
-        const float bp_weight = p.threshold - accumulated;
-        const bool need_rest = (L > 1) && (bp_weight > 0.f);
-        float norm_weight = accumulated;
-        if (need_rest) norm_weight = (num_passes == 0) ? 1.f : p.threshold;
-        const float inv_weight = rcp_exact(norm_weight);
-
         int32_t* key_base = p.key_indices ? p.key_indices + (size_t)c * L * 3 * P * 2 : nullptr;
 
         // ---- K1: sample + blend, lane <-> joint ----
@@ -280,51 +375,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
             const int j = j0 + lane;
             const bool active = j < P;   // all lanes stay in the loop: layer state is broadcast by shuffle
             const int jt = active ? j : P - 1;
+            int32_t* kb = active ? key_base : nullptr;
             Xform acc;
-            if (L == 1) {
-                // a state with a single clip never runs BlendingJob (src/skeleton_ozz.cpp:552-555, :617-624)
-                const int c0 = __shfl_sync(0xffffffffu, my_clip, 0);
-                const float t0 = __shfl_sync(0xffffffffu, my_ratio, 0);
-                sample_joint(p.clips, c0, jt, t0, acc, active ? key_base : nullptr);
+            if (prog.top == kTopRestPose) {  // load-time pose: LocalToModelJob over joint_rest_poses (:901-916)
+                const float* r = p.skel.rest + (size_t)jt * 10;
+                acc.t[0] = r[0]; acc.t[1] = r[1]; acc.t[2] = r[2];
+                acc.r[0] = r[3]; acc.r[1] = r[4]; acc.r[2] = r[5]; acc.r[3] = r[6];
+                acc.s[0] = r[7]; acc.s[1] = r[8]; acc.s[2] = r[9];
             } else {
-                Xform rest;
-                bool have_rest = false;
-                int pass = 0;
-#pragma unroll 1
-                for (int l = 0; l < L; ++l) {
-                    const float w = __shfl_sync(0xffffffffu, my_weight, l);
-                    const int cl = __shfl_sync(0xffffffffu, my_clip, l);
-                    const float tl = __shfl_sync(0xffffffffu, my_ratio, l);
-                    const bool contributes = !(w <= 0.f);
-                    const bool is_rest = need_rest && l == 0;
-                    if (!contributes && !is_rest && !key_base) continue;
-                    Xform in;
-                    sample_joint(p.clips, cl, jt, tl, in, (key_base && active) ? key_base + (size_t)l * 3 * P * 2 : nullptr);
-                    if (is_rest) { rest = in; have_rest = true; }
-                    if (!contributes) continue;
-                    if (pass == 0) {  // OZZ_BLEND_1ST_PASS
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) acc.t[k] = in.t[k] * w;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) acc.r[k] = in.r[k] * w;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) acc.s[k] = in.s[k] * w;
-                    } else {
-                        blend_n_pass(acc, in, w);
-                    }
-                    ++pass;
+                acc = eval_group(p.clips, my_clip, my_ratio, my_weight, 0, prog.n0, prog.mode0, prog.rest0, prog.threshold0, jt, kb, P);
+                if (prog.top == kTopTransition || (kb && prog.n1)) {
+                    const Xform cur = eval_group(p.clips, my_clip, my_ratio, my_weight, prog.n0, prog.n1, prog.mode1, prog.rest1,
+                                                 prog.threshold1, jt, kb, P);
+                    if (prog.top == kTopTransition)  // 2-layer BlendingJob, threshold bx::kFloatSmallest, rest = previous (:709-719)
+                        acc = blend_two(acc, cur, prog.w0, prog.w1, 1.17549435e-38f);
                 }
-                if (need_rest && have_rest) {  // BlendRestPose
-                    if (pass == 0) acc = rest;
-                    else blend_n_pass(acc, rest, bp_weight);
-                }
-                // Normalize
-                const float len2 = acc.r[0] * acc.r[0] + acc.r[1] * acc.r[1] + acc.r[2] * acc.r[2] + acc.r[3] * acc.r[3];
-                const float inv_len = rsqrt_exact(len2);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc.r[k] = acc.r[k] * inv_len;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { acc.t[k] = acc.t[k] * inv_weight; acc.s[k] = acc.s[k] * inv_weight; }
             }
             if (!active) continue;
             if (p.locals) {

@@ -136,6 +136,30 @@ DMK_API dmk_status dmk_crowd_enable_outputs(dmk_crowd_t crowd, uint32_t outputs)
  * Rest pose of the blend = layer 0 (:719; :600-603 when no clip sits at (0,0)). */
 DMK_API dmk_status dmk_crowd_set_layers(dmk_crowd_t crowd, int num_layers, const int32_t* clip, const float* ratio,
                                         const float* weight, const float* speed, const uint8_t* loop, float threshold);
+/* General form: a per-character pose program, what darmok's animator state machine resolves a tick into.
+ * A character has up to two GROUPS of layers -- the previous and the current state of a transition
+ * (OzzSkeletalAnimatorTransition::update, src/skeleton_ozz.cpp:682-726).  A group is a BlendingJob over its layers
+ * (OzzSkeletalAnimatorState::update :556-608, threshold and rest-pose layer from the state definition) or the
+ * pass-through of one layer (single-clip state :552-555/:617-624; early exit when a clip sits exactly at the blend
+ * position :588-593; all clips of the state are still sampled).  top: DMK_TOP_GROUP0 = a plain state or a finished
+ * transition; DMK_TOP_TRANSITION = 2-layer BlendingJob (weight0, weight1) = (1 - v, v), threshold bx::kFloatSmallest,
+ * rest pose = group 0 (:709-719); DMK_TOP_REST_POSE = the load-time pose (LocalToModelJob over joint_rest_poses,
+ * :901-916); DMK_TOP_SKIP = animator without state: matrices are left untouched (:1029-1032).
+ * Layer arrays are [num_layers][N]; group 0 uses layers [0, num_layers0), group 1 the next num_layers1.
+ * Ratios are host-resolved (do not combine with DMK_STEP_ADVANCE).  Copies are staged in pinned memory and async. */
+typedef struct dmk_pose_program {
+    uint8_t num_layers0, num_layers1;
+    uint8_t rest0, rest1;   /* blend: rest-pose layer within the group; pass-through: the layer that is the pose */
+    uint8_t mode0, mode1;   /* DMK_GROUP_* */
+    uint8_t top;            /* DMK_TOP_* */
+    uint8_t reserved;
+    float threshold0, threshold1;
+    float weight0, weight1;
+} dmk_pose_program;
+enum { DMK_GROUP_BLEND = 0, DMK_GROUP_PASSTHROUGH = 1 };
+enum { DMK_TOP_GROUP0 = 0, DMK_TOP_TRANSITION = 1, DMK_TOP_REST_POSE = 2, DMK_TOP_SKIP = 3 };
+DMK_API dmk_status dmk_crowd_set_programs(dmk_crowd_t crowd, int num_layers, const int32_t* clip, const float* ratio,
+                                          const float* weight, const dmk_pose_program* programs);
 /* per-frame variant for a host-side state machine: pinned staging + async copy of clip/ratio/weight only */
 DMK_API dmk_status dmk_crowd_update_layers(dmk_crowd_t crowd, int num_layers, const int32_t* clip, const float* ratio,
                                            const float* weight);

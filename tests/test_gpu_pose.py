@@ -231,3 +231,82 @@ def test_dense_clip_falls_back_to_search():
         assert_close(crowd.get_palette(), ref["palette"], "palette")
     finally:
         g.close()
+
+
+def _reference_program_locals(o, a, clip, ratio, weight, prog, i):
+    """composition of oracle jobs for character i's pose program (what darmok's state machine would run)"""
+    def group(begin, count, mode, rest, threshold):
+        samples = [o.clips[clip[l, i]].sample_stateless(float(ratio[l, i]))[0] for l in range(begin, begin + count)]
+        if mode == 1:
+            return samples[rest]
+        return o.O.blend(samples, weight[begin:begin + count, i], samples[rest], threshold)
+    g0 = group(0, prog["n0"], prog["mode0"], prog["rest0"], float(prog["threshold0"]))
+    if prog["top"] == 1:
+        g1 = group(prog["n0"], prog["n1"], prog["mode1"], prog["rest1"], float(prog["threshold1"]))
+        return o.O.blend([g0, g1], [prog["w0"], prog["w1"]], g0, FLT_MIN)
+    return g0
+
+
+def test_pose_programs_states_transitions_rest_and_skip(rigs):
+    g, o, a = rigs
+    capi = g.capi
+    n, L = 120, 9
+    rng = np.random.default_rng(21)
+    clip = rng.integers(0, len(a.clips), (L, n)).astype(np.int32)
+    ratio = rng.random((L, n)).astype(np.float32)
+    weight = rng.uniform(-0.2, 1.0, (L, n)).astype(np.float32)
+    prog = np.zeros(n, capi.PROGRAM_DTYPE)
+    for i in range(n):
+        kind = i % 6
+        n0 = int(rng.integers(1, 6))
+        n1 = int(rng.integers(1, L - n0 + 1))
+        prog[i]["n0"], prog[i]["rest0"], prog[i]["threshold0"] = n0, rng.integers(0, n0), rng.choice([0.2, 1.0, FLT_MIN])
+        prog[i]["n1"], prog[i]["rest1"], prog[i]["threshold1"] = n1, rng.integers(0, n1), rng.choice([0.2, 1.0, FLT_MIN])
+        prog[i]["mode0"], prog[i]["mode1"] = rng.integers(0, 2), rng.integers(0, 2)
+        if kind in (0, 1):
+            prog[i]["top"] = capi.TOP_GROUP0
+        elif kind in (2, 3):
+            prog[i]["top"] = capi.TOP_TRANSITION
+            v = rng.uniform(-0.1, 1.1)          # ease(t) is not clamped (C8): weights may leave [0, 1]
+            prog[i]["w0"], prog[i]["w1"] = 1.0 - v, v
+        elif kind == 4:
+            prog[i]["top"] = capi.TOP_REST_POSE
+        else:
+            prog[i]["top"] = capi.TOP_SKIP
+    crowd = g.crowd(n, L, mesh=False)
+    crowd.enable_outputs(capi.OUT_LOCALS)
+    # first a rest-pose pass for everybody (what SkeletalAnimatorImpl::load does), so that SKIP has something to keep
+    rest_prog = np.zeros(n, capi.PROGRAM_DTYPE)
+    rest_prog["top"] = capi.TOP_REST_POSE
+    crowd.set_programs(clip, ratio, weight, rest_prog)
+    crowd.step(0.0, capi.STEP_POSE)
+    rest_models = o.skel.local_to_model(o.skel.rest_pose())
+    rest_pal = o.O.palette(rest_models, o.remap, o.inv_bind)
+    assert_close(crowd.get_palette(), np.tile(rest_pal, (n, 1, 1)), "rest-pose palette")
+    crowd.set_programs(clip, ratio, weight, prog)
+    crowd.step(0.0, capi.STEP_POSE)
+    pal, loc = crowd.get_palette(), crowd.get_locals()
+    for i in range(n):
+        top = prog[i]["top"]
+        if top in (capi.TOP_SKIP, capi.TOP_REST_POSE):
+            assert_close(pal[i], rest_pal, f"character {i} keeps/gets the rest pose")
+            continue
+        ref_loc = _reference_program_locals(o, a, clip, ratio, weight, prog[i], i)
+        assert_close(loc[i], ref_loc, f"locals of character {i} (top {top})")
+        assert_close(pal[i], o.O.palette(o.skel.local_to_model(ref_loc), o.remap, o.inv_bind), f"palette of character {i}")
+
+
+def test_pose_program_validation(rigs):
+    g, o, a = rigs
+    capi = g.capi
+    crowd = g.crowd(2, 4, mesh=False)
+    clip = np.zeros((4, 2), np.int32)
+    z = np.zeros((4, 2), np.float32)
+    prog = np.zeros(2, capi.PROGRAM_DTYPE)
+    prog["n0"], prog["threshold0"] = 2, 0.0           # blend group with threshold 0
+    with pytest.raises(capi.DmkError) as e:
+        crowd.set_programs(clip, z, z, prog)
+    assert e.value.status == capi.ERR_JOB and "error in the blending job" in e.value.message
+    prog["threshold0"], prog["n0"], prog["n1"] = 1.0, 3, 3      # more layers than the crowd holds
+    with pytest.raises(capi.DmkError):
+        crowd.set_programs(clip, z, z, prog)
