@@ -636,7 +636,7 @@ dmk_status dmk_crowd_create(dmk_context_t ctx, dmk_skeleton_t skel, dmk_clipset_
     if (!ctx || !skel || !clips || !out) return fail(ctx, DMK_ERR_INVALID, "null argument");
     *out = nullptr;
     if (n < 0 || n > 0x7fffffff) return fail(ctx, DMK_ERR_INVALID, "num_characters out of range");
-    if (max_layers < 1 || max_layers > kMaxLayers) return fail(ctx, DMK_ERR_INVALID, "max_layers must be in [1, 16]");
+    if (max_layers < 1 || max_layers > kMaxLayers) return fail(ctx, DMK_ERR_INVALID, "max_layers must be in [1, 32]");
     if (mesh && !arm) return fail(ctx, DMK_ERR_INVALID, "a mesh needs an armature");
     if (mesh && mesh->palette_size != arm->num_joints + 1)
         return fail(ctx, DMK_ERR_INVALID, "mesh palette_size does not match the armature");

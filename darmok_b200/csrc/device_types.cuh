@@ -7,7 +7,7 @@
 namespace dmk {
 
 constexpr int kSoaFloats = 40;      // ozz SoaTransform: T.xyz R.xyzw S.xyz, 4 lanes each
-constexpr int kMaxLayers = 16;
+constexpr int kMaxLayers = 32;      // layer state lives in the lanes of the character's warp
 constexpr int kMaxPalette = 256;    // palette slots are packed as bytes in the skinning kernel
 constexpr uint16_t kIdleTask = 0xffffu;
 

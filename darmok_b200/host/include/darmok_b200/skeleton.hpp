@@ -1,0 +1,299 @@
+// darmok_b200/skeleton.hpp -- darmok's skeleton / animator / skinning API over the B200 C ABI (include/dmk.h).
+//
+// This header mirrors include/darmok/skeleton.hpp (paths relative to the darmok repository): same class names,
+// method names, argument meaning and error strings for the character hot path, so that the translation unit
+// src/skeleton_ozz.cpp can be replaced by darmok_b200/host/src/skeleton_b200.cpp:
+//
+//   Skeleton, SkeletalAnimation                      include/darmok/skeleton.hpp:30-56
+//   ISkeletalAnimatorState / ISkeletalAnimatorTransition                        :60-80
+//   ISkeletalAnimatorListener (6 callbacks)                                     :100-111
+//   SkeletalAnimator (play/stop/pause/update/getJointModelMatrix ...)           :259-301
+//   ArmatureJoint, Armature, Skinnable                                          :363-406
+//   SkeletalAnimationSceneComponent::update (per-entity tick, batched here)     src/skeleton.cpp:159-184
+//   SkeletalAnimationRenderComponent::beforeRenderEntity (palette)              src/skeleton.cpp:223-251
+//   FrustumCuller::update / shouldEntityBeCulled                                src/culling.cpp:258-290
+//
+// The definitions are plain structs with the field names of assets/protobuf/skeleton.proto (the reference uses the
+// generated protobuf classes; protobuf is not part of the hot path).  What stays on the host is control flow per
+// animator (clocks, blend weights, tweens, transitions, listener events: src/skeleton_ozz.cpp:411-440, 491-610,
+// 682-726, 783-889, 1044-1087, src/skeleton.cpp:306-364); everything per joint / per vertex runs on the device.
+#pragma once
+
+#include "easing.hpp"
+#include "glm_lite.hpp"
+
+#include <cstdint>
+#include <expected>
+#include <filesystem>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+struct dmk_context_s;
+struct dmk_skeleton_s;
+struct dmk_clip_s;
+struct dmk_clipset_s;
+struct dmk_armature_s;
+struct dmk_mesh_s;
+struct dmk_crowd_s;
+
+namespace darmok {
+
+template <typename T, typename E>
+using expected = std::expected<T, E>;
+template <typename E>
+using unexpected = std::unexpected<E>;
+
+// ---- definitions (assets/protobuf/skeleton.proto:8-64) -----------------------------------------------------------
+struct SkeletalAnimatorAnimationDefinition {
+    std::string name;
+    glm::vec2 blend_position{0.f, 0.f};
+    float speed = 0.f;   // proto3 default; 0 is treated as 1 (src/skeleton_ozz.cpp:398-404)
+    bool loop = false;   // the JSON reader defaults to true (src/skeleton.cpp:473-528)
+};
+struct SkeletalAnimatorTweenDefinition {
+    EasingType easing = EasingType::Linear;
+    float duration = 0.f;
+};
+struct SkeletalAnimatorStateDefinition {
+    enum BlendType { Cartesian = 0, Directional = 1 };
+    std::string name;
+    std::vector<SkeletalAnimatorAnimationDefinition> animations;
+    BlendType blend = Cartesian;
+    float threshold = 0.f;  // 0 makes ozz's BlendingJob fail: "error in the blending job" (C7)
+    SkeletalAnimatorTweenDefinition tween;
+    std::string next_state;
+    float speed = 1.f;
+};
+struct SkeletalAnimatorTransitionDefinition {
+    std::string src_state, dst_state;
+    SkeletalAnimatorTweenDefinition tween;
+    float offset = 0.f;
+};
+struct SkeletalAnimatorDefinition {
+    std::string skeleton_path, animation_pattern;
+    std::vector<SkeletalAnimatorStateDefinition> states;
+    std::vector<SkeletalAnimatorTransitionDefinition> transitions;
+};
+
+// ---- device context shared by the assets -------------------------------------------------------------------------
+class DeviceContext final {
+public:
+    static expected<std::shared_ptr<DeviceContext>, std::string> create(int device = 0, void* cudaStream = nullptr) noexcept;
+    ~DeviceContext() noexcept;
+    dmk_context_s* handle() const noexcept { return _ctx; }
+    std::string lastError() const noexcept;
+private:
+    explicit DeviceContext(dmk_context_s* ctx) noexcept : _ctx{ctx} {}
+    dmk_context_s* _ctx;
+};
+
+// ---- assets --------------------------------------------------------------------------------------------------------
+class Skeleton final {
+public:
+    // bytes of an ozz archive holding an ozz-skeleton (OzzSkeletonLoader, src/skeleton_ozz.cpp:191-200)
+    static expected<std::shared_ptr<Skeleton>, std::string> load(const std::shared_ptr<DeviceContext>& ctx, const void* bytes, size_t size) noexcept;
+    ~Skeleton() noexcept;
+    std::string toString() const noexcept;          // "Skeleton <n> joints" (src/skeleton_ozz.cpp:54-58)
+    int getNumJoints() const noexcept;
+    std::string_view getJointName(int i) const noexcept;
+    int getJointParent(int i) const noexcept;
+    dmk_skeleton_s* handle() const noexcept { return _h; }
+    const std::shared_ptr<DeviceContext>& context() const noexcept { return _ctx; }
+private:
+    Skeleton(std::shared_ptr<DeviceContext> ctx, dmk_skeleton_s* h) noexcept : _ctx{std::move(ctx)}, _h{h} {}
+    std::shared_ptr<DeviceContext> _ctx;
+    dmk_skeleton_s* _h;
+};
+
+class SkeletalAnimation final {
+public:
+    static expected<std::shared_ptr<SkeletalAnimation>, std::string> load(const std::shared_ptr<DeviceContext>& ctx, const void* bytes, size_t size) noexcept;
+    ~SkeletalAnimation() noexcept;
+    std::string toString() const noexcept;          // "SkeletalAnimation <name>"
+    std::string_view getName() const noexcept;
+    float getDuration() const noexcept;
+    dmk_clip_s* handle() const noexcept { return _h; }
+private:
+    SkeletalAnimation(std::shared_ptr<DeviceContext> ctx, dmk_clip_s* h) noexcept : _ctx{std::move(ctx)}, _h{h} {}
+    std::shared_ptr<DeviceContext> _ctx;
+    dmk_clip_s* _h;
+};
+
+using SkeletalAnimationMap = std::unordered_map<std::string, std::shared_ptr<SkeletalAnimation>>;
+
+// ILoader<T>::operator()(path) -> expected<shared_ptr<T>, string> (include/darmok/loader.hpp); bytes come from a data loader
+using DataLoader = std::function<expected<std::vector<uint8_t>, std::string>(const std::filesystem::path&)>;
+expected<std::vector<uint8_t>, std::string> loadFileData(const std::filesystem::path& path) noexcept;
+
+class B200SkeletonLoader final {   // replaces OzzSkeletonLoader
+public:
+    B200SkeletonLoader(std::shared_ptr<DeviceContext> ctx, DataLoader dataLoader = loadFileData) noexcept;
+    expected<std::shared_ptr<Skeleton>, std::string> operator()(const std::filesystem::path& path) noexcept;
+private:
+    std::shared_ptr<DeviceContext> _ctx;
+    DataLoader _dataLoader;
+};
+class B200SkeletalAnimationLoader final {   // replaces OzzSkeletalAnimationLoader
+public:
+    B200SkeletalAnimationLoader(std::shared_ptr<DeviceContext> ctx, DataLoader dataLoader = loadFileData) noexcept;
+    expected<std::shared_ptr<SkeletalAnimation>, std::string> operator()(const std::filesystem::path& path) noexcept;
+private:
+    std::shared_ptr<DeviceContext> _ctx;
+    DataLoader _dataLoader;
+};
+
+struct ArmatureJoint final {
+    std::string name;
+    glm::mat4 inverseBindPose{1.f};
+};
+class Armature final {
+public:
+    explicit Armature(std::vector<ArmatureJoint> joints) noexcept : _joints{std::move(joints)} {}
+    const std::vector<ArmatureJoint>& getJoints() const noexcept { return _joints; }
+private:
+    std::vector<ArmatureJoint> _joints;
+};
+
+// vertex streams of one skinned mesh in MeshData::exportData layout (src/mesh_core.cpp:323-365)
+struct SkinnedMeshData {
+    std::vector<float> position, normal, tangent;   // 3 floats per vertex
+    std::vector<float> indices, weights;             // 4 floats per vertex
+    int numVertices() const noexcept { return static_cast<int>(position.size() / 3); }
+};
+
+class Skinnable {
+public:
+    Skinnable(const std::shared_ptr<Armature>& armature = nullptr) noexcept : _armature{armature} {}
+    std::shared_ptr<Armature> getArmature() const noexcept { return _armature; }
+    void setArmature(const std::shared_ptr<Armature>& armature) noexcept { _armature = armature; }
+private:
+    std::shared_ptr<Armature> _armature;
+};
+
+// ---- animator ------------------------------------------------------------------------------------------------------
+class ISkeletalAnimatorState {
+public:
+    virtual ~ISkeletalAnimatorState() = default;
+    virtual float getNormalizedTime() const = 0;
+    virtual float getDuration() const = 0;
+    virtual std::string_view getName() const = 0;
+};
+class ISkeletalAnimatorTransition {
+public:
+    virtual ~ISkeletalAnimatorTransition() = default;
+    virtual float getNormalizedTime() const = 0;
+    virtual float getDuration() const = 0;
+    virtual const ISkeletalAnimatorState& getCurrentState() const = 0;
+    virtual const ISkeletalAnimatorState& getPreviousState() const = 0;
+};
+
+class SkeletalAnimator;
+class ISkeletalAnimatorListener {
+public:
+    virtual ~ISkeletalAnimatorListener() = default;
+    virtual void onAnimatorDestroyed(SkeletalAnimator&) {}
+    virtual void onAnimatorStateLooped(SkeletalAnimator&, std::string_view) {}
+    virtual void onAnimatorStateFinished(SkeletalAnimator&, std::string_view) {}
+    virtual void onAnimatorStateStarted(SkeletalAnimator&, std::string_view) {}
+    virtual void onAnimatorTransitionFinished(SkeletalAnimator&) {}
+    virtual void onAnimatorTransitionStarted(SkeletalAnimator&) {}
+};
+
+enum class SkeletalAnimatorPlaybackState { Stopped, Playing, Paused };
+
+namespace detail {
+class AnimatorCore;   // host state machine: resolves a tick into a pose program (skeleton_b200.cpp)
+struct PoseRequest;
+}
+class SkeletalAnimationSceneComponent;
+
+class SkeletalAnimator final {
+public:
+    using Definition = SkeletalAnimatorDefinition;
+    using AnimationMap = SkeletalAnimationMap;
+    using PlaybackState = SkeletalAnimatorPlaybackState;
+
+    SkeletalAnimator(std::shared_ptr<Skeleton> skel, AnimationMap anims, Definition def) noexcept;
+    ~SkeletalAnimator() noexcept;
+    SkeletalAnimator(const SkeletalAnimator&) = delete;
+    SkeletalAnimator& operator=(const SkeletalAnimator&) = delete;
+
+    SkeletalAnimator& addListener(std::unique_ptr<ISkeletalAnimatorListener> listener) noexcept;
+    SkeletalAnimator& addListener(ISkeletalAnimatorListener& listener) noexcept;
+    bool removeListener(const ISkeletalAnimatorListener& listener) noexcept;
+
+    SkeletalAnimator& setPlaybackSpeed(float speed) noexcept;
+    float getPlaybackSpeed() const noexcept;
+    SkeletalAnimator& setBlendPosition(const glm::vec2& value) noexcept;
+    const glm::vec2& getBlendPosition() const noexcept;
+    const Definition& getDefinition() const noexcept;
+    const ISkeletalAnimatorState* getCurrentState() const noexcept;            // OptionalRef in darmok
+    const ISkeletalAnimatorTransition* getCurrentTransition() const noexcept;
+    float getStateDuration(const std::string& name) const noexcept;
+
+    bool play(std::string_view name, float speedFactor = 1.F) noexcept;
+    void stop() noexcept;
+    void pause() noexcept;
+    PlaybackState getPlaybackState() noexcept;
+
+    // skinning target: the armature (and optionally the mesh) whose palette / skinned vertices the device produces.
+    // Must be set before the first update(); one armature per animator.
+    expected<void, std::string> setSkinning(const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh = nullptr) noexcept;
+
+    glm::mat4 getJointModelMatrix(const std::string& node) const noexcept;
+    std::vector<glm::mat4> getSkinningPalette() const noexcept;   // what beforeRenderEntity uploads as u_skinning
+    std::vector<float> getSkinnedVertices() const noexcept;       // [V][9] position, normal, tangent
+
+    // stand-alone use: ticks the state machine and runs a one-character device step
+    expected<void, std::string> update(float deltaTime) noexcept;
+
+private:
+    friend class SkeletalAnimationSceneComponent;
+    struct Device;
+    std::shared_ptr<Skeleton> _skeleton;
+    AnimationMap _animations;
+    std::unique_ptr<detail::AnimatorCore> _core;
+    std::unique_ptr<Device> _device;       // own one-character crowd (stand-alone mode)
+    SkeletalAnimationSceneComponent* _batch = nullptr;
+    int64_t _batchIndex = -1;
+    std::shared_ptr<Armature> _armature;
+    std::optional<SkinnedMeshData> _mesh;
+    mutable std::vector<glm::mat4> _modelsCache;
+    mutable bool _modelsValid = false;
+    expected<void, std::string> ensureDevice() noexcept;
+};
+
+// Batched replacement of SkeletalAnimationSceneComponent::update (src/skeleton.cpp:159-184), FrustumCuller
+// (src/culling.cpp:258-290) and SkeletalAnimationRenderComponent (src/skeleton.cpp:223-251) for animators that share
+// skeleton, clips, armature and mesh: one device step per frame instead of one virtual call per entity.
+class SkeletalAnimationSceneComponent final {
+public:
+    SkeletalAnimationSceneComponent(std::shared_ptr<Skeleton> skel, SkeletalAnimator::AnimationMap anims, SkeletalAnimator::Definition def,
+                                    std::shared_ptr<Armature> armature, const SkinnedMeshData* mesh = nullptr) noexcept;
+    ~SkeletalAnimationSceneComponent() noexcept;
+
+    // creates the animators (entities); must be called once before update()
+    expected<void, std::string> init(int64_t numAnimators) noexcept;
+    SkeletalAnimator& getAnimator(int64_t index) noexcept;
+    int64_t size() const noexcept;
+
+    // per-entity Transform::getWorldInverse + BoundingBox, camera view-projection (FrustumCuller inputs)
+    expected<void, std::string> setInstances(const float* worldInverse, const float* bbox) noexcept;
+    expected<void, std::string> setCamera(const glm::mat4& viewProj, float normalizedNearDepth = 0.f) noexcept;
+
+    expected<void, std::string> update(float deltaTime) noexcept;          // ISceneComponent::update
+    bool shouldEntityBeCulled(int64_t index) noexcept;                      // ICameraComponent::shouldEntityBeCulled
+
+    dmk_crowd_s* crowd() const noexcept;
+private:
+    friend class SkeletalAnimator;
+    struct Impl;
+    std::unique_ptr<Impl> _impl;
+};
+
+}  // namespace darmok

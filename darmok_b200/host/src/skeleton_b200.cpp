@@ -1,0 +1,460 @@
+// skeleton_b200.cpp -- the translation unit that takes the place of darmok's src/skeleton_ozz.cpp (+ the batched
+// parts of src/skeleton.cpp and src/culling.cpp): the public skeleton API implemented over the C ABI of
+// libdarmok_b200.so.  No arithmetic of the hot path happens here; this file owns handles, resolves the host state
+// machine (animator_core.cpp) into pose programs and moves them through include/dmk.h.
+#include "darmok_b200/skeleton.hpp"
+
+#include "darmok_b200/animator_core.hpp"
+
+#include "dmk.h"
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+
+namespace darmok {
+
+namespace {
+constexpr int kMaxLayers = 32;
+
+// PoseRequest of one animator -> slot `index` of the layer arrays [numLayers][n] + program
+void writeRequest(const detail::PoseRequest& req, int64_t index, int64_t n, int32_t* clip, float* ratio, float* weight,
+                  dmk_pose_program& prog) {
+    std::memset(&prog, 0, sizeof prog);
+    auto writeGroup = [&](const detail::GroupRequest& g, int first) {
+        for (size_t l = 0; l < g.layers.size(); ++l) {
+            const size_t at = static_cast<size_t>(first + static_cast<int>(l)) * static_cast<size_t>(n) + static_cast<size_t>(index);
+            clip[at] = g.layers[l].clip;
+            ratio[at] = g.layers[l].ratio;
+            weight[at] = g.layers[l].weight;
+        }
+    };
+    if (req.top == detail::PoseRequest::Skip) {
+        prog.top = DMK_TOP_SKIP;
+        return;
+    }
+    prog.top = req.top == detail::PoseRequest::Transition ? DMK_TOP_TRANSITION : DMK_TOP_GROUP0;
+    prog.num_layers0 = static_cast<uint8_t>(req.group0.layers.size());
+    prog.rest0 = static_cast<uint8_t>(req.group0.rest);
+    prog.mode0 = req.group0.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND;
+    prog.threshold0 = req.group0.threshold;
+    writeGroup(req.group0, 0);
+    if (req.top == detail::PoseRequest::Transition) {
+        prog.num_layers1 = static_cast<uint8_t>(req.group1.layers.size());
+        prog.rest1 = static_cast<uint8_t>(req.group1.rest);
+        prog.mode1 = req.group1.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND;
+        prog.threshold1 = req.group1.threshold;
+        prog.weight0 = req.w0;
+        prog.weight1 = req.w1;
+        writeGroup(req.group1, static_cast<int>(req.group0.layers.size()));
+    }
+}
+int layersOf(const detail::PoseRequest& req) {
+    if (req.top == detail::PoseRequest::Skip) return 0;
+    int n = static_cast<int>(req.group0.layers.size());
+    if (req.top == detail::PoseRequest::Transition) n += static_cast<int>(req.group1.layers.size());
+    return n;
+}
+
+// deterministic clip order of an AnimationMap: sorted by map key
+std::vector<std::pair<std::string, std::shared_ptr<SkeletalAnimation>>> sortedClips(const SkeletalAnimationMap& anims) {
+    std::vector<std::pair<std::string, std::shared_ptr<SkeletalAnimation>>> v(anims.begin(), anims.end());
+    std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    return v;
+}
+}  // namespace
+
+// ---- DeviceContext ---------------------------------------------------------------------------------------------------
+expected<std::shared_ptr<DeviceContext>, std::string> DeviceContext::create(int device, void* cudaStream) noexcept {
+    dmk_context_t ctx = nullptr;
+    if (dmk_context_create(device, cudaStream, &ctx) != DMK_OK) return unexpected<std::string>{dmk_last_error(nullptr)};
+    return std::shared_ptr<DeviceContext>(new DeviceContext(ctx));
+}
+DeviceContext::~DeviceContext() noexcept { dmk_context_destroy(_ctx); }
+std::string DeviceContext::lastError() const noexcept { return dmk_last_error(_ctx); }
+
+// ---- Skeleton / SkeletalAnimation / loaders -----------------------------------------------------------------------------
+expected<std::shared_ptr<Skeleton>, std::string> Skeleton::load(const std::shared_ptr<DeviceContext>& ctx, const void* bytes, size_t size) noexcept {
+    dmk_skeleton_t h = nullptr;
+    if (dmk_skeleton_load_ozz(ctx->handle(), bytes, size, &h) != DMK_OK) return unexpected<std::string>{ctx->lastError()};
+    return std::shared_ptr<Skeleton>(new Skeleton(ctx, h));
+}
+Skeleton::~Skeleton() noexcept { dmk_skeleton_destroy(_h); }
+std::string Skeleton::toString() const noexcept { return "Skeleton " + std::to_string(getNumJoints()) + " joints"; }
+int Skeleton::getNumJoints() const noexcept { return dmk_skeleton_num_joints(_h); }
+std::string_view Skeleton::getJointName(int i) const noexcept {
+    const char* n = dmk_skeleton_joint_name(_h, i);
+    return n ? std::string_view{n} : std::string_view{};
+}
+int Skeleton::getJointParent(int i) const noexcept { return dmk_skeleton_joint_parent(_h, i); }
+
+expected<std::shared_ptr<SkeletalAnimation>, std::string> SkeletalAnimation::load(const std::shared_ptr<DeviceContext>& ctx, const void* bytes,
+                                                                                  size_t size) noexcept {
+    dmk_clip_t h = nullptr;
+    if (dmk_clip_load_ozz(ctx->handle(), bytes, size, &h) != DMK_OK) return unexpected<std::string>{ctx->lastError()};
+    return std::shared_ptr<SkeletalAnimation>(new SkeletalAnimation(ctx, h));
+}
+SkeletalAnimation::~SkeletalAnimation() noexcept { dmk_clip_destroy(_h); }
+std::string SkeletalAnimation::toString() const noexcept { return "SkeletalAnimation " + std::string(getName()); }
+std::string_view SkeletalAnimation::getName() const noexcept { return dmk_clip_name(_h); }
+float SkeletalAnimation::getDuration() const noexcept { return dmk_clip_duration(_h); }
+
+expected<std::vector<uint8_t>, std::string> loadFileData(const std::filesystem::path& path) noexcept {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) return unexpected<std::string>{"could not open " + path.string()};
+    std::vector<uint8_t> data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    return data;
+}
+B200SkeletonLoader::B200SkeletonLoader(std::shared_ptr<DeviceContext> ctx, DataLoader dataLoader) noexcept
+    : _ctx{std::move(ctx)}, _dataLoader{std::move(dataLoader)} {}
+expected<std::shared_ptr<Skeleton>, std::string> B200SkeletonLoader::operator()(const std::filesystem::path& path) noexcept {
+    auto data = _dataLoader(path);
+    if (!data) return unexpected<std::string>{data.error()};
+    return Skeleton::load(_ctx, data->data(), data->size());
+}
+B200SkeletalAnimationLoader::B200SkeletalAnimationLoader(std::shared_ptr<DeviceContext> ctx, DataLoader dataLoader) noexcept
+    : _ctx{std::move(ctx)}, _dataLoader{std::move(dataLoader)} {}
+expected<std::shared_ptr<SkeletalAnimation>, std::string> B200SkeletalAnimationLoader::operator()(const std::filesystem::path& path) noexcept {
+    auto data = _dataLoader(path);
+    if (!data) return unexpected<std::string>{data.error()};
+    return SkeletalAnimation::load(_ctx, data->data(), data->size());
+}
+
+// ---- device objects of one (skeleton, clips, armature, mesh) combination --------------------------------------------------
+struct SkeletalAnimator::Device {
+    std::shared_ptr<DeviceContext> ctx;
+    dmk_clipset_t clips = nullptr;
+    dmk_armature_t armature = nullptr;
+    dmk_mesh_t mesh = nullptr;
+    dmk_crowd_t crowd = nullptr;
+    int64_t n = 0;
+    int paletteSize = 0, numVertices = 0;
+    bool hasInstances = false, hasCamera = false;
+    std::vector<int32_t> clip;
+    std::vector<float> ratio, weight;
+    std::vector<dmk_pose_program> programs;
+    std::vector<uint32_t> visibility;
+    bool visibilityValid = false;
+
+    ~Device() {
+        dmk_crowd_destroy(crowd);
+        dmk_mesh_destroy(mesh);
+        dmk_armature_destroy(armature);
+        dmk_clipset_destroy(clips);
+    }
+
+    static expected<std::unique_ptr<Device>, std::string> create(const std::shared_ptr<Skeleton>& skel, const SkeletalAnimationMap& anims,
+                                                                 const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh,
+                                                                 int64_t n) noexcept {
+        auto dev = std::make_unique<Device>();
+        dev->ctx = skel->context();
+        dev->n = n;
+        dmk_context_t ctx = dev->ctx->handle();
+        auto err = [&]() { return unexpected<std::string>{dev->ctx->lastError()}; };
+        std::vector<dmk_clip_t> handles;
+        for (const auto& [name, anim] : sortedClips(anims)) handles.push_back(anim->handle());
+        if (handles.empty()) return unexpected<std::string>{"animator has no animations"};
+        if (dmk_clipset_create(ctx, skel->handle(), handles.data(), static_cast<int>(handles.size()), &dev->clips)) return err();
+        if (armature) {
+            std::vector<const char*> names;
+            std::vector<float> invBind;
+            for (const auto& j : armature->getJoints()) {
+                names.push_back(j.name.c_str());
+                const float* m = glm::value_ptr(j.inverseBindPose);
+                invBind.insert(invBind.end(), m, m + 16);
+            }
+            if (dmk_armature_create(ctx, skel->handle(), names.data(), invBind.data(), static_cast<int>(names.size()), &dev->armature)) return err();
+            dev->paletteSize = dmk_armature_palette_size(dev->armature);
+            if (mesh) {
+                if (dmk_mesh_create(ctx, mesh->position.data(), mesh->normal.data(), mesh->tangent.data(), mesh->indices.data(), mesh->weights.data(),
+                                    mesh->numVertices(), dev->paletteSize, &dev->mesh))
+                    return err();
+                dev->numVertices = mesh->numVertices();
+            }
+        }
+        if (dmk_crowd_create(ctx, skel->handle(), dev->clips, dev->armature, dev->mesh, n, kMaxLayers, &dev->crowd)) return err();
+        if (dmk_crowd_enable_outputs(dev->crowd, DMK_OUT_MODELS)) return err();
+        // SkeletalAnimatorImpl::load runs LocalToModelJob over the rest pose (src/skeleton_ozz.cpp:901-916, C13)
+        dev->clip.assign(static_cast<size_t>(n), 0);
+        dev->ratio.assign(static_cast<size_t>(n), 0.f);
+        dev->weight.assign(static_cast<size_t>(n), 0.f);
+        dev->programs.assign(static_cast<size_t>(n), dmk_pose_program{});
+        for (auto& p : dev->programs) p.top = DMK_TOP_REST_POSE;
+        if (dmk_crowd_set_programs(dev->crowd, 1, dev->clip.data(), dev->ratio.data(), dev->weight.data(), dev->programs.data()) ||
+            dmk_crowd_step(dev->crowd, 0.f, DMK_STEP_POSE | (dev->mesh ? DMK_STEP_SKIN : 0)))
+            return err();
+        return dev;
+    }
+
+    // runs the programs currently held in the host arrays
+    expected<void, std::string> run(int numLayers, bool cull) noexcept {
+        // a zero blend threshold comes back as DMK_ERR_JOB "error in the blending job" (src/skeleton_ozz.cpp:605-608)
+        if (dmk_crowd_set_programs(crowd, numLayers, clip.data(), ratio.data(), weight.data(), programs.data())) return unexpected<std::string>{ctx->lastError()};
+        uint32_t flags = DMK_STEP_POSE;
+        if (mesh) flags |= DMK_STEP_SKIN;
+        if (cull && hasInstances && hasCamera) flags |= DMK_STEP_CULL;
+        if (dmk_crowd_step(crowd, 0.f, flags)) return unexpected<std::string>{ctx->lastError()};
+        visibilityValid = false;
+        return {};
+    }
+};
+
+// ---- SkeletalAnimator ---------------------------------------------------------------------------------------------------
+namespace {
+struct ListenerSet {
+    std::vector<std::unique_ptr<ISkeletalAnimatorListener>> owned;
+    std::vector<ISkeletalAnimatorListener*> all;
+};
+std::unordered_map<const SkeletalAnimator*, ListenerSet>& listenerRegistry() {
+    static std::unordered_map<const SkeletalAnimator*, ListenerSet> reg;
+    return reg;
+}
+void bindEvents(SkeletalAnimator& animator, detail::AnimatorCore& core) {
+    // listeners are copied before a fan-out, as the reference does (_listeners.copy(), src/skeleton_ozz.cpp:810,1046)
+    auto each = [&animator](auto fn) {
+        auto itr = listenerRegistry().find(&animator);
+        if (itr == listenerRegistry().end()) return;
+        const auto copy = itr->second.all;
+        for (auto* l : copy) fn(*l);
+    };
+    core.events.stateLooped = [&animator, each](std::string_view s) { each([&](auto& l) { l.onAnimatorStateLooped(animator, s); }); };
+    core.events.stateFinished = [&animator, each](std::string_view s) { each([&](auto& l) { l.onAnimatorStateFinished(animator, s); }); };
+    core.events.stateStarted = [&animator, each](std::string_view s) { each([&](auto& l) { l.onAnimatorStateStarted(animator, s); }); };
+    core.events.transitionFinished = [&animator, each]() { each([&](auto& l) { l.onAnimatorTransitionFinished(animator); }); };
+    core.events.transitionStarted = [&animator, each]() { each([&](auto& l) { l.onAnimatorTransitionStarted(animator); }); };
+}
+}  // namespace
+
+SkeletalAnimator::SkeletalAnimator(std::shared_ptr<Skeleton> skel, AnimationMap anims, Definition def) noexcept
+    : _skeleton{std::move(skel)}, _animations{std::move(anims)} {
+    std::vector<detail::ClipInfo> clips;
+    for (const auto& [name, anim] : sortedClips(_animations)) clips.push_back({name, anim->getDuration()});
+    _core = std::make_unique<detail::AnimatorCore>(std::move(clips), std::move(def));
+}
+
+SkeletalAnimator::~SkeletalAnimator() noexcept {
+    auto itr = listenerRegistry().find(this);
+    if (itr != listenerRegistry().end()) {
+        const auto copy = itr->second.all;
+        for (auto* l : copy) l->onAnimatorDestroyed(*this);   // src/skeleton_ozz.cpp:233-242
+        listenerRegistry().erase(this);
+    }
+}
+
+SkeletalAnimator& SkeletalAnimator::addListener(std::unique_ptr<ISkeletalAnimatorListener> listener) noexcept {
+    auto& set = listenerRegistry()[this];
+    set.all.push_back(listener.get());
+    set.owned.push_back(std::move(listener));
+    bindEvents(*this, *_core);
+    return *this;
+}
+SkeletalAnimator& SkeletalAnimator::addListener(ISkeletalAnimatorListener& listener) noexcept {
+    listenerRegistry()[this].all.push_back(&listener);
+    bindEvents(*this, *_core);
+    return *this;
+}
+bool SkeletalAnimator::removeListener(const ISkeletalAnimatorListener& listener) noexcept {
+    auto itr = listenerRegistry().find(this);
+    if (itr == listenerRegistry().end()) return false;
+    auto& all = itr->second.all;
+    const auto before = all.size();
+    all.erase(std::remove(all.begin(), all.end(), &listener), all.end());
+    auto& owned = itr->second.owned;
+    owned.erase(std::remove_if(owned.begin(), owned.end(), [&](const auto& p) { return p.get() == &listener; }), owned.end());
+    return all.size() != before;
+}
+
+SkeletalAnimator& SkeletalAnimator::setPlaybackSpeed(float speed) noexcept { _core->setPlaybackSpeed(speed); return *this; }
+float SkeletalAnimator::getPlaybackSpeed() const noexcept { return _core->getPlaybackSpeed(); }
+SkeletalAnimator& SkeletalAnimator::setBlendPosition(const glm::vec2& value) noexcept { _core->setBlendPosition(value); return *this; }
+const glm::vec2& SkeletalAnimator::getBlendPosition() const noexcept { return _core->getBlendPosition(); }
+const SkeletalAnimator::Definition& SkeletalAnimator::getDefinition() const noexcept { return _core->getDefinition(); }
+const ISkeletalAnimatorState* SkeletalAnimator::getCurrentState() const noexcept { return _core->getCurrentState(); }
+const ISkeletalAnimatorTransition* SkeletalAnimator::getCurrentTransition() const noexcept { return _core->getCurrentTransition(); }
+float SkeletalAnimator::getStateDuration(const std::string& name) const noexcept { return _core->getStateDuration(name); }
+bool SkeletalAnimator::play(std::string_view name, float speedFactor) noexcept { return _core->play(name, speedFactor); }
+void SkeletalAnimator::stop() noexcept { _core->stop(); }
+void SkeletalAnimator::pause() noexcept { _core->pause(); }
+SkeletalAnimator::PlaybackState SkeletalAnimator::getPlaybackState() noexcept { return _core->getPlaybackState(); }
+
+expected<void, std::string> SkeletalAnimator::setSkinning(const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh) noexcept {
+    if (_device || _batch) return unexpected<std::string>{"setSkinning must be called before the first update"};
+    _armature = armature;
+    if (mesh) _mesh = *mesh; else _mesh.reset();
+    return {};
+}
+
+expected<void, std::string> SkeletalAnimator::ensureDevice() noexcept {
+    if (_device || _batch) return {};
+    auto dev = Device::create(_skeleton, _animations, _armature, _mesh ? &*_mesh : nullptr, 1);
+    if (!dev) return unexpected<std::string>{dev.error()};
+    _device = std::move(*dev);
+    return {};
+}
+
+expected<void, std::string> SkeletalAnimator::update(float deltaTime) noexcept {
+    if (_batch) return unexpected<std::string>{"this animator is ticked by its SkeletalAnimationSceneComponent"};
+    if (auto r = ensureDevice(); !r) return r;
+    const bool active = _core->hasActiveStateOrTransition();
+    detail::PoseRequest req;
+    if (auto r = _core->update(deltaTime, req); !r) return r;
+    if (!active) return {};   // no state: SkeletalAnimatorImpl::update returns before the model job (:1029-1032)
+    const int layers = std::max(1, layersOf(req));
+    if (layers > kMaxLayers) return unexpected<std::string>{"state blends more clips than the device supports"};
+    Device& d = *_device;
+    d.clip.assign(static_cast<size_t>(layers), 0);
+    d.ratio.assign(static_cast<size_t>(layers), 0.f);
+    d.weight.assign(static_cast<size_t>(layers), 0.f);
+    writeRequest(req, 0, 1, d.clip.data(), d.ratio.data(), d.weight.data(), d.programs[0]);
+    if (auto r = d.run(layers, false); !r) return r;
+    _modelsValid = false;
+    _core->afterUpdate();
+    return {};
+}
+
+glm::mat4 SkeletalAnimator::getJointModelMatrix(const std::string& node) const noexcept {
+    // src/skeleton_ozz.cpp:962-977: identity without skeleton or for an unknown joint name
+    if (!_skeleton) return glm::mat4(1.f);
+    const int joint = dmk_skeleton_find_joint(_skeleton->handle(), node.c_str());
+    if (joint < 0) return glm::mat4(1.f);
+    if (!_batch && !_device && !const_cast<SkeletalAnimator*>(this)->ensureDevice()) return glm::mat4(1.f);
+    dmk_crowd_t crowd = _batch ? _batch->crowd() : _device->crowd;
+    if (!crowd) return glm::mat4(1.f);
+    if (!_modelsValid) {
+        _modelsCache.assign(static_cast<size_t>(_skeleton->getNumJoints()), glm::mat4(1.f));
+        if (dmk_crowd_get_models(crowd, _batch ? _batchIndex : 0, 1, glm::value_ptr(_modelsCache[0])) != DMK_OK) return glm::mat4(1.f);
+        _modelsValid = true;
+    }
+    return _modelsCache[static_cast<size_t>(joint)];
+}
+
+std::vector<glm::mat4> SkeletalAnimator::getSkinningPalette() const noexcept {
+    // SkeletalAnimationRenderComponent::beforeRenderEntity (src/skeleton.cpp:236-249): [mat4(1)] + model * inverseBindPose
+    if (!_batch && !_device) const_cast<SkeletalAnimator*>(this)->ensureDevice();
+    dmk_crowd_t crowd = _batch ? _batch->crowd() : (_device ? _device->crowd : nullptr);
+    const int ps = _armature ? static_cast<int>(_armature->getJoints().size()) + 1 : 0;
+    std::vector<glm::mat4> out(static_cast<size_t>(ps), glm::mat4(1.f));
+    if (crowd && ps) dmk_crowd_get_palette(crowd, _batch ? _batchIndex : 0, 1, glm::value_ptr(out[0]));
+    return out;
+}
+
+std::vector<float> SkeletalAnimator::getSkinnedVertices() const noexcept {
+    if (!_batch && !_device) const_cast<SkeletalAnimator*>(this)->ensureDevice();
+    dmk_crowd_t crowd = _batch ? _batch->crowd() : (_device ? _device->crowd : nullptr);
+    const int v = _mesh ? _mesh->numVertices() : 0;
+    std::vector<float> out(static_cast<size_t>(v) * 9, 0.f);
+    if (crowd && v) dmk_crowd_get_skinned(crowd, _batch ? _batchIndex : 0, 1, out.data());
+    return out;
+}
+
+// ---- SkeletalAnimationSceneComponent (batched) ----------------------------------------------------------------------------
+struct SkeletalAnimationSceneComponent::Impl {
+    std::shared_ptr<Skeleton> skeleton;
+    SkeletalAnimator::AnimationMap anims;
+    SkeletalAnimator::Definition def;
+    std::shared_ptr<Armature> armature;
+    std::optional<SkinnedMeshData> mesh;
+    std::unique_ptr<SkeletalAnimator::Device> device;
+    std::vector<std::unique_ptr<SkeletalAnimator>> animators;
+    std::vector<detail::PoseRequest> requests;
+    std::vector<char> active;
+};
+
+SkeletalAnimationSceneComponent::SkeletalAnimationSceneComponent(std::shared_ptr<Skeleton> skel, SkeletalAnimator::AnimationMap anims,
+                                                                 SkeletalAnimator::Definition def, std::shared_ptr<Armature> armature,
+                                                                 const SkinnedMeshData* mesh) noexcept
+    : _impl{std::make_unique<Impl>()} {
+    _impl->skeleton = std::move(skel);
+    _impl->anims = std::move(anims);
+    _impl->def = std::move(def);
+    _impl->armature = std::move(armature);
+    if (mesh) _impl->mesh = *mesh;
+}
+SkeletalAnimationSceneComponent::~SkeletalAnimationSceneComponent() noexcept = default;
+
+expected<void, std::string> SkeletalAnimationSceneComponent::init(int64_t numAnimators) noexcept {
+    if (_impl->device) return unexpected<std::string>{"already initialised"};
+    auto dev = SkeletalAnimator::Device::create(_impl->skeleton, _impl->anims, _impl->armature, _impl->mesh ? &*_impl->mesh : nullptr, numAnimators);
+    if (!dev) return unexpected<std::string>{dev.error()};
+    _impl->device = std::move(*dev);
+    for (int64_t i = 0; i < numAnimators; ++i) {
+        auto a = std::make_unique<SkeletalAnimator>(_impl->skeleton, _impl->anims, _impl->def);
+        a->_batch = this;
+        a->_batchIndex = i;
+        a->_armature = _impl->armature;
+        a->_mesh = _impl->mesh;
+        _impl->animators.push_back(std::move(a));
+    }
+    _impl->requests.resize(static_cast<size_t>(numAnimators));
+    _impl->active.resize(static_cast<size_t>(numAnimators));
+    return {};
+}
+SkeletalAnimator& SkeletalAnimationSceneComponent::getAnimator(int64_t index) noexcept { return *_impl->animators[static_cast<size_t>(index)]; }
+int64_t SkeletalAnimationSceneComponent::size() const noexcept { return static_cast<int64_t>(_impl->animators.size()); }
+dmk_crowd_s* SkeletalAnimationSceneComponent::crowd() const noexcept { return _impl->device ? _impl->device->crowd : nullptr; }
+
+expected<void, std::string> SkeletalAnimationSceneComponent::setInstances(const float* worldInverse, const float* bbox) noexcept {
+    if (!_impl->device) return unexpected<std::string>{"not initialised"};
+    if (dmk_crowd_set_instances(_impl->device->crowd, worldInverse, bbox)) return unexpected<std::string>{_impl->device->ctx->lastError()};
+    _impl->device->hasInstances = true;
+    return {};
+}
+expected<void, std::string> SkeletalAnimationSceneComponent::setCamera(const glm::mat4& viewProj, float normalizedNearDepth) noexcept {
+    if (!_impl->device) return unexpected<std::string>{"not initialised"};
+    if (dmk_crowd_set_camera(_impl->device->crowd, glm::value_ptr(viewProj), normalizedNearDepth)) return unexpected<std::string>{_impl->device->ctx->lastError()};
+    _impl->device->hasCamera = true;
+    return {};
+}
+
+expected<void, std::string> SkeletalAnimationSceneComponent::update(float deltaTime) noexcept {
+    // src/skeleton.cpp:159-184: every animator ticks and errors are collected; here the per-entity device work of all of
+    // them is one crowd step (pose programs of the whole crowd -> one pose launch, one cull launch, one skin launch)
+    if (!_impl->device) return unexpected<std::string>{"not initialised"};
+    auto& d = *_impl->device;
+    const int64_t n = d.n;
+    std::vector<std::string> errors;
+    int layers = 1;
+    for (int64_t i = 0; i < n; ++i) {
+        auto& a = *_impl->animators[static_cast<size_t>(i)];
+        _impl->active[static_cast<size_t>(i)] = a._core->hasActiveStateOrTransition();
+        auto& req = _impl->requests[static_cast<size_t>(i)];
+        if (auto r = a._core->update(deltaTime, req); !r) {
+            errors.push_back(r.error());
+            req = detail::PoseRequest{};   // a failed animator keeps its previous matrices this frame
+            _impl->active[static_cast<size_t>(i)] = 0;
+        }
+        layers = std::max(layers, layersOf(req));
+    }
+    if (layers > kMaxLayers) return unexpected<std::string>{"state blends more clips than the device supports"};
+    d.clip.assign(static_cast<size_t>(layers) * static_cast<size_t>(n), 0);
+    d.ratio.assign(d.clip.size(), 0.f);
+    d.weight.assign(d.clip.size(), 0.f);
+    for (int64_t i = 0; i < n; ++i)
+        writeRequest(_impl->requests[static_cast<size_t>(i)], i, n, d.clip.data(), d.ratio.data(), d.weight.data(), d.programs[static_cast<size_t>(i)]);
+    if (auto r = d.run(layers, true); !r) return r;
+    for (int64_t i = 0; i < n; ++i) {
+        auto& a = *_impl->animators[static_cast<size_t>(i)];
+        a._modelsValid = false;
+        if (_impl->active[static_cast<size_t>(i)]) a._core->afterUpdate();
+    }
+    if (!errors.empty()) {
+        std::string joined;
+        for (const auto& e : errors) joined += (joined.empty() ? "" : "\n") + e;
+        return unexpected<std::string>{joined};
+    }
+    return {};
+}
+
+bool SkeletalAnimationSceneComponent::shouldEntityBeCulled(int64_t index) noexcept {
+    // FrustumCuller::shouldEntityBeCulled (src/culling.cpp:287-290): membership in the culled set of the last update
+    if (!_impl->device || !_impl->device->hasInstances || !_impl->device->hasCamera) return false;
+    auto& d = *_impl->device;
+    if (!d.visibilityValid) {
+        d.visibility.assign(static_cast<size_t>((d.n + 31) / 32), 0u);
+        if (dmk_crowd_get_visibility(d.crowd, d.visibility.data(), nullptr) != DMK_OK) return false;
+        d.visibilityValid = true;
+    }
+    return ((d.visibility[static_cast<size_t>(index >> 5)] >> (index & 31)) & 1u) == 0u;
+}
+
+}  // namespace darmok

@@ -1,0 +1,446 @@
+// animator_test.cpp -- scripted animator scenarios run twice: through the host shim (darmok_b200/host) and through the
+// oracle's restatement of darmok's animator (oracle/animator_ref.cpp), compared tick by tick.
+//
+//   animator_test <assets_dir> cpu   host state machine only: every PoseRequest is evaluated with the oracle's jobs and
+//                                    the resulting model matrices must equal the reference animator's exactly
+//   animator_test <assets_dir> gpu   full path: SkeletalAnimator / SkeletalAnimationSceneComponent on the device through
+//                                    the C ABI; joint matrices, palette, skinned vertices, culling against the oracle
+//
+// <assets_dir> is written by tests/test_host_shim.py: skeleton.ozz, <clip>.ozz, armature.bin/.txt, mesh.bin
+#include "darmok_b200/animator_core.hpp"
+#include "darmok_b200/skeleton.hpp"
+
+#include "animator_ref.hpp"
+#include "dmk_oracle.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+using namespace darmok;
+
+static int g_failures = 0;
+#define CHECK(cond, ...)                                 \
+    do {                                                 \
+        if (!(cond)) {                                   \
+            std::printf("FAIL %s:%d: ", __FILE__, __LINE__); \
+            std::printf(__VA_ARGS__);                    \
+            std::printf("\n");                           \
+            if (++g_failures > 20) std::exit(1);         \
+        }                                                \
+    } while (0)
+
+static std::vector<uint8_t> readFile(const std::string& path) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) { std::printf("cannot open %s\n", path.c_str()); std::exit(2); }
+    return std::vector<uint8_t>((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+}
+
+static const char* kClipNames[] = {"Idle01", "Run01_Backward", "Run01_BackwardLeft", "Run01_BackwardRight", "Run01_Forward",
+                                   "Run01_ForwardLeft", "Run01_ForwardRight", "Run01_Left", "Run01_Right", "Talk01"};
+static const float kBlendPos[9][2] = {{0, 0}, {0, -1}, {1, -1}, {-1, -1}, {0, 1}, {-1, 1}, {1, 1}, {-1, 0}, {1, 0}};
+
+// the animator of samples/ozz/assets/animator.json, plus a few states that exercise the quirks
+static void buildDefinitions(SkeletalAnimatorDefinition& def, orc::AnimatorDef& ref) {
+    auto addState = [&](const std::string& name, std::vector<std::pair<std::string, std::pair<float, float>>> anims, int blend, float threshold,
+                        float tweenDuration, bool loop, const std::string& next, float speed, float clipSpeed) {
+        SkeletalAnimatorStateDefinition s;
+        orc::StateDef r;
+        s.name = r.name = name;
+        for (auto& a : anims) {
+            SkeletalAnimatorAnimationDefinition ad;
+            ad.name = a.first;
+            ad.blend_position = glm::vec2(a.second.first, a.second.second);
+            ad.loop = loop;
+            ad.speed = clipSpeed;
+            s.animations.push_back(ad);
+            r.animations.push_back({a.first, {a.second.first, a.second.second}, clipSpeed, loop});
+        }
+        s.blend = static_cast<SkeletalAnimatorStateDefinition::BlendType>(blend);
+        r.blend = blend;
+        s.threshold = r.threshold = threshold;
+        s.tween.duration = r.tween.duration = tweenDuration;
+        s.next_state = r.next_state = next;
+        s.speed = r.speed = speed;
+        def.states.push_back(s);
+        ref.states.push_back(r);
+    };
+    std::vector<std::pair<std::string, std::pair<float, float>>> loco;
+    for (int i = 0; i < 9; ++i) loco.push_back({kClipNames[i], {kBlendPos[i][0], kBlendPos[i][1]}});
+    addState("locomotion", loco, 1, 0.2f, 0.5f, true, "", 1.f, 0.f);
+    addState("talk", {{"Talk01", {0, 0}}}, 0, 0.f, 0.f, true, "", 1.f, 0.f);
+    addState("greet", {{"Talk01", {0, 0}}}, 0, 0.f, 0.f, false, "locomotion", 1.f, 2.f);   // non looping, auto next state
+    std::vector<std::pair<std::string, std::pair<float, float>>> cart = {{"Run01_Left", {-1, 0}}, {"Run01_Right", {1, 0}}, {"Run01_Forward", {0, 1}}};
+    addState("strafe", cart, 0, 1.f, 0.25f, true, "", 1.5f, 0.f);                          // Cartesian, no clip at (0, 0)
+    addState("broken", cart, 0, 0.f, 0.25f, true, "", 1.f, 0.f);                           // threshold 0: BlendingJob rejects (C7)
+    addState("ghost", {{"NoSuchClip", {0, 0}}}, 0, 1.f, 0.f, true, "", 1.f, 0.f);           // no known animation: cannot be created
+    auto addTransition = [&](const std::string& src, const std::string& dst, float duration, float offset, int easing) {
+        SkeletalAnimatorTransitionDefinition t;
+        t.src_state = src; t.dst_state = dst; t.tween.duration = duration; t.offset = offset;
+        t.tween.easing = static_cast<EasingType>(easing);
+        def.transitions.push_back(t);
+        ref.transitions.push_back({src, dst, {easing, duration}, offset});
+    };
+    addTransition("locomotion", "talk", 0.5f, 0.f, 0);
+    addTransition("talk", "locomotion", 0.5f, 0.1f, 4);     // QuadraticInOut with an offset
+    addTransition("", "strafe", 0.3f, 0.f, 16);             // *>strafe, SinusoidalInOut
+    addTransition("greet", "", 0.2f, 0.f, 0);               // greet>*
+}
+
+struct Action {
+    enum Kind { Tick, Play, Stop, Blend, Speed, Pause } kind;
+    std::string name;
+    float a = 0.f, b = 0.f;
+};
+static std::vector<Action> scenario() {
+    std::vector<Action> s;
+    auto ticks = [&](int n, float dt) { for (int i = 0; i < n; ++i) s.push_back({Action::Tick, "", dt, 0}); };
+    s.push_back({Action::Play, "run", 1.f, 0});             // C16: no such state
+    ticks(3, 1 / 60.f);
+    s.push_back({Action::Play, "ghost", 1.f, 0});           // state without a known clip
+    s.push_back({Action::Play, "locomotion", 1.f, 0});
+    ticks(8, 1 / 60.f);                                     // blend position (0,0) == Idle01's: early exit
+    s.push_back({Action::Blend, "", 0.3f, 0.7f});
+    ticks(45, 1 / 60.f);                                    // tweened blend position, directional gradient bands
+    s.push_back({Action::Blend, "", -1.f, 0.f});
+    ticks(20, 1 / 30.f);
+    s.push_back({Action::Play, "locomotion", 2.f, 0});      // same state: only the speed changes, returns false
+    ticks(10, 1 / 30.f);
+    s.push_back({Action::Play, "talk", 1.f, 0});            // locomotion>talk
+    ticks(12, 1 / 30.f);
+    s.push_back({Action::Play, "locomotion", 1.f, 0});      // replace a running transition: its current state becomes the source
+    ticks(25, 1 / 30.f);
+    s.push_back({Action::Speed, "", 0.5f, 0});
+    s.push_back({Action::Play, "strafe", 1.f, 0});          // *>strafe
+    s.push_back({Action::Blend, "", 0.25f, 0.5f});
+    ticks(30, 1 / 30.f);
+    s.push_back({Action::Blend, "", 1.f, 0.f});             // lands exactly on Run01_Right after the tween
+    ticks(30, 1 / 15.f);
+    s.push_back({Action::Pause, "", 0, 0});
+    ticks(2, 1 / 30.f);
+    s.push_back({Action::Speed, "", 1.f, 0});
+    s.push_back({Action::Play, "greet", 1.f, 0});           // non looping at clip speed 2, then auto "locomotion" through greet>*
+    ticks(70, 1 / 30.f);
+    s.push_back({Action::Stop, "", 0, 0});
+    ticks(3, 1 / 30.f);
+    s.push_back({Action::Play, "broken", 1.f, 0});          // "error in the blending job"
+    ticks(2, 1 / 30.f);
+    s.push_back({Action::Stop, "", 0, 0});
+    s.push_back({Action::Play, "talk", 1.f, 0});
+    ticks(4, 0.4f);                                         // long steps: loops
+    return s;
+}
+
+struct EventLog : ISkeletalAnimatorListener {
+    std::vector<std::string> events;
+    void onAnimatorStateLooped(SkeletalAnimator&, std::string_view s) override { events.push_back("looped:" + std::string(s)); }
+    void onAnimatorStateFinished(SkeletalAnimator&, std::string_view s) override { events.push_back("finished:" + std::string(s)); }
+    void onAnimatorStateStarted(SkeletalAnimator&, std::string_view s) override { events.push_back("started:" + std::string(s)); }
+    void onAnimatorTransitionFinished(SkeletalAnimator&) override { events.push_back("transition_finished"); }
+    void onAnimatorTransitionStarted(SkeletalAnimator&) override { events.push_back("transition_started"); }
+};
+
+struct OracleAssets {
+    orc_skeleton* skel = nullptr;
+    std::vector<orc_animation*> anims;
+    std::vector<orc::NamedAnimation> named;   // sorted by name, like the shim's clip table
+};
+static OracleAssets loadOracle(const std::string& dir) {
+    OracleAssets o;
+    char err[256];
+    auto sk = readFile(dir + "/skeleton.ozz");
+    o.skel = orc_skeleton_load(sk.data(), sk.size(), err, sizeof err);
+    if (!o.skel) { std::printf("oracle skeleton: %s\n", err); std::exit(2); }
+    std::vector<std::string> names(std::begin(kClipNames), std::end(kClipNames));
+    std::sort(names.begin(), names.end());
+    for (const auto& n : names) {
+        auto data = readFile(dir + "/" + n + ".ozz");
+        orc_animation* a = orc_animation_load(data.data(), data.size(), err, sizeof err);
+        if (!a) { std::printf("oracle animation %s: %s\n", n.c_str(), err); std::exit(2); }
+        o.anims.push_back(a);
+        o.named.push_back({n, a});
+    }
+    return o;
+}
+
+// evaluates one group of a PoseRequest with the oracle's jobs (what the device does)
+static std::vector<float> evalGroup(const OracleAssets& o, const detail::GroupRequest& g) {
+    const int S = o.skel->num_soa;
+    std::vector<std::vector<float>> samples;
+    for (const auto& l : g.layers) {
+        samples.emplace_back((size_t)S * 40);
+        orc_sample_stateless(o.anims[l.clip], l.ratio, samples.back().data(), S, nullptr);
+    }
+    if (g.passthrough) return samples[g.rest];
+    std::vector<const float*> ptrs;
+    std::vector<float> w;
+    for (size_t i = 0; i < samples.size(); ++i) { ptrs.push_back(samples[i].data()); w.push_back(g.layers[i].weight); }
+    std::vector<float> out((size_t)S * 40);
+    if (!orc_blend((int)ptrs.size(), ptrs.data(), w.data(), samples[g.rest].data(), g.threshold, S, out.data())) out.clear();
+    return out;
+}
+
+static void applyAction(const Action& a, auto& shim, orc::RefAnimator& ref, int step) {
+    switch (a.kind) {
+    case Action::Play: {
+        const bool r1 = shim.play(a.name, a.a), r2 = ref.play(a.name, a.a);
+        CHECK(r1 == r2, "step %d play(%s): shim %d ref %d", step, a.name.c_str(), r1, r2);
+        break;
+    }
+    case Action::Stop: shim.stop(); ref.stop(); break;
+    case Action::Blend: shim.setBlendPosition(glm::vec2(a.a, a.b)); ref.setBlendPosition({a.a, a.b}); break;
+    case Action::Speed: shim.setPlaybackSpeed(a.a); ref.setPlaybackSpeed(a.a); break;
+    case Action::Pause: shim.pause(); break;   // only changes getPlaybackState (C10)
+    default: break;
+    }
+}
+
+static int runCpu(const std::string& dir) {
+    OracleAssets o = loadOracle(dir);
+    SkeletalAnimatorDefinition def;
+    orc::AnimatorDef rdef;
+    buildDefinitions(def, rdef);
+    std::vector<detail::ClipInfo> clips;
+    for (const auto& n : o.named) clips.push_back({n.name, n.anim->duration});
+    detail::AnimatorCore core(clips, def);
+    std::vector<std::string> events;
+    core.events.stateLooped = [&](std::string_view s) { events.push_back("looped:" + std::string(s)); };
+    core.events.stateFinished = [&](std::string_view s) { events.push_back("finished:" + std::string(s)); };
+    core.events.stateStarted = [&](std::string_view s) { events.push_back("started:" + std::string(s)); };
+    core.events.transitionFinished = [&] { events.push_back("transition_finished"); };
+    core.events.transitionStarted = [&] { events.push_back("transition_started"); };
+    orc::RefAnimator ref(o.skel, o.named, rdef);
+
+    const int J = o.skel->num_joints, S = o.skel->num_soa;
+    std::vector<float> models((size_t)J * 16);
+    orc_local_to_model(o.skel, o.skel->rest, models.data());
+    int step = 0, ticks = 0, poses = 0, transitions = 0, blends = 0, passthroughs = 0, errors = 0;
+    for (const Action& a : scenario()) {
+        ++step;
+        if (a.kind != Action::Tick) { applyAction(a, core, ref, step); continue; }
+        ++ticks;
+        const bool active = core.hasActiveStateOrTransition();
+        detail::PoseRequest req;
+        auto r = core.update(a.a, req);
+        std::string refErr;
+        const bool refOk = ref.update(a.a, refErr);
+        CHECK(r.has_value() == refOk, "step %d: shim ok=%d ref ok=%d (%s)", step, (int)r.has_value(), (int)refOk, refErr.c_str());
+        if (!r) {
+            ++errors;
+            CHECK(r.error() == refErr, "step %d: error '%s' vs '%s'", step, r.error().c_str(), refErr.c_str());
+            continue;
+        }
+        if (active) {
+            if (req.top != detail::PoseRequest::Skip) {
+                ++poses;
+                std::vector<float> locals = evalGroup(o, req.group0);
+                (req.group0.passthrough ? passthroughs : blends)++;
+                if (req.top == detail::PoseRequest::Transition) {
+                    ++transitions;
+                    std::vector<float> cur = evalGroup(o, req.group1);
+                    const float* ptrs[2] = {locals.data(), cur.data()};
+                    const float w[2] = {req.w0, req.w1};
+                    std::vector<float> out((size_t)S * 40);
+                    CHECK(orc_blend(2, ptrs, w, locals.data(), FLT_MIN, S, out.data()), "step %d: transition blend failed", step);
+                    locals = out;
+                }
+                orc_local_to_model(o.skel, locals.data(), models.data());
+            }
+            core.afterUpdate();
+        }
+        CHECK(std::memcmp(models.data(), ref.models().data(), models.size() * 4) == 0, "step %d: model matrices differ from the reference animator", step);
+        CHECK(events == ref.events, "step %d: listener events differ (%zu vs %zu)", step, events.size(), ref.events.size());
+        const auto* cs = core.getCurrentState();
+        const auto* rs = ref.currentState();
+        CHECK((cs != nullptr) == (rs != nullptr), "step %d: current state presence", step);
+        if (cs && rs) {
+            CHECK(cs->getName() == rs->getName(), "step %d: state %s vs %s", step, std::string(cs->getName()).c_str(), rs->getName().c_str());
+            CHECK(cs->getNormalizedTime() == rs->getNormalizedTime(), "step %d: normalized time %g vs %g", step, cs->getNormalizedTime(), rs->getNormalizedTime());
+            CHECK(cs->getDuration() == rs->getDuration(), "step %d: duration %g vs %g", step, cs->getDuration(), rs->getDuration());
+        }
+        CHECK((core.getCurrentTransition() != nullptr) == (ref.currentTransition() != nullptr), "step %d: transition presence", step);
+        if (core.getCurrentTransition() && ref.currentTransition())
+            CHECK(core.getCurrentTransition()->getNormalizedTime() == ref.currentTransition()->getNormalizedTime(), "step %d: transition time", step);
+    }
+    for (const char* n : {"locomotion", "talk", "greet", "strafe", "nope"})
+        CHECK(core.getStateDuration(n) == ref.getStateDuration(n), "getStateDuration(%s): %g vs %g", n, core.getStateDuration(n), ref.getStateDuration(n));
+    // every easing curve, specialised (shim) against general (oracle) form
+    for (int type = 0; type < 32; ++type)
+        for (int i = -4; i <= 44; ++i) {
+            const float p = i / 40.f;
+            const float a = ease01(static_cast<EasingType>(type), p), b = orc::ease(type, p, 0.f, 1.f);
+            CHECK(a == b || (std::isnan(a) && std::isnan(b)), "easing %d at %g: %.9g vs %.9g", type, p, a, b);
+        }
+    std::printf("cpu: %d ticks, %d poses (%d blends, %d passthroughs, %d in transition), %d job errors, %zu events, %d failures\n", ticks, poses, blends,
+                passthroughs, transitions, errors, events.size(), g_failures);
+    CHECK(transitions > 20 && blends > 50 && passthroughs > 20 && errors == 2 && events.size() > 10, "scenario lost coverage");
+    return g_failures ? 1 : 0;
+}
+
+static bool close(float a, float e) {
+    const double err = std::fabs((double)a - (double)e);
+    return err <= 1e-6 || err <= 1e-5 * std::fabs((double)e);
+}
+
+static int runGpu(const std::string& dir) {
+    OracleAssets o = loadOracle(dir);
+    SkeletalAnimatorDefinition def;
+    orc::AnimatorDef rdef;
+    buildDefinitions(def, rdef);
+    auto ctxr = DeviceContext::create(0);
+    if (!ctxr) { std::printf("no device: %s\n", ctxr.error().c_str()); return 3; }
+    auto ctx = *ctxr;
+    B200SkeletonLoader skelLoader(ctx);
+    B200SkeletalAnimationLoader animLoader(ctx);
+    auto skel = skelLoader(dir + "/skeleton.ozz");
+    CHECK(skel.has_value(), "skeleton load: %s", skel ? "" : skel.error().c_str());
+    CHECK((*skel)->toString() == "Skeleton " + std::to_string(o.skel->num_joints) + " joints", "toString: %s", (*skel)->toString().c_str());
+    auto bad = skelLoader(dir + "/Idle01.ozz");
+    CHECK(!bad && bad.error() == "archive does not contain the type", "wrong archive type must keep darmok's message");
+    SkeletalAnimationMap anims;
+    for (const char* n : kClipNames) {
+        auto a = animLoader(dir + "/" + std::string(n) + ".ozz");
+        CHECK(a.has_value(), "animation %s", n);
+        CHECK((*a)->getName() == n, "animation name %s", std::string((*a)->getName()).c_str());
+        anims[n] = *a;
+    }
+    // armature + mesh
+    const int J = o.skel->num_joints;
+    auto armBytes = readFile(dir + "/armature.bin");
+    std::ifstream namesIn(dir + "/armature.txt");
+    std::vector<ArmatureJoint> joints;
+    std::vector<int32_t> remap;
+    std::vector<float> invBind(armBytes.size() / 4);
+    std::memcpy(invBind.data(), armBytes.data(), armBytes.size());
+    for (size_t k = 0; k < invBind.size() / 16; ++k) {
+        ArmatureJoint j;
+        std::getline(namesIn, j.name);
+        std::memcpy(glm::value_ptr(j.inverseBindPose), invBind.data() + k * 16, 64);
+        remap.push_back(orc_skeleton_find_joint(o.skel, j.name.c_str()));
+        joints.push_back(j);
+    }
+    auto armature = std::make_shared<Armature>(joints);
+    const int K = (int)joints.size();
+    auto meshBytes = readFile(dir + "/mesh.bin");
+    const int V = (int)(meshBytes.size() / 4 / 17);
+    SkinnedMeshData mesh;
+    {
+        const float* f = reinterpret_cast<const float*>(meshBytes.data());
+        mesh.position.assign(f, f + V * 3);
+        mesh.normal.assign(f + V * 3, f + V * 6);
+        mesh.tangent.assign(f + V * 6, f + V * 9);
+        mesh.indices.assign(f + V * 9, f + V * 13);
+        mesh.weights.assign(f + V * 13, f + V * 17);
+    }
+
+    // ---- one stand-alone animator through the whole scenario ----
+    {
+        SkeletalAnimator animator(*skel, anims, def);
+        CHECK(animator.setSkinning(armature, &mesh).has_value(), "setSkinning");
+        EventLog log;
+        animator.addListener(log);
+        orc::RefAnimator ref(o.skel, o.named, rdef);
+        std::vector<float> flipped(16), palette((size_t)(K + 1) * 16), skinned((size_t)V * 9);
+        int step = 0, checked = 0;
+        for (const Action& a : scenario()) {
+            ++step;
+            if (a.kind != Action::Tick) { applyAction(a, animator, ref, step); continue; }
+            auto r = animator.update(a.a);
+            std::string refErr;
+            const bool refOk = ref.update(a.a, refErr);
+            CHECK(r.has_value() == refOk, "step %d: update ok %d vs %d", step, (int)r.has_value(), (int)refOk);
+            if (!r) { CHECK(r.error() == refErr, "step %d: '%s' vs '%s'", step, r.error().c_str(), refErr.c_str()); continue; }
+            CHECK(log.events == ref.events, "step %d: events differ", step);
+            if (step % 3 && step > 6) continue;   // matrices are read back every third tick
+            ++checked;
+            for (int j = 0; j < J; ++j) {
+                const glm::mat4 m = animator.getJointModelMatrix(o.skel->names[j]);
+                orc_flip_handedness(ref.models().data() + (size_t)j * 16, flipped.data());
+                for (int e = 0; e < 16; ++e) CHECK(close(glm::value_ptr(m)[e], flipped[e]), "step %d joint %d elem %d: %g vs %g", step, j, e, glm::value_ptr(m)[e], flipped[e]);
+            }
+            orc_palette(ref.models().data(), J, remap.data(), invBind.data(), K, palette.data());
+            const auto pal = animator.getSkinningPalette();
+            for (size_t e = 0; e < palette.size(); ++e) CHECK(close(glm::value_ptr(pal[0])[e], palette[e]), "step %d palette %zu", step, e);
+            orc_skin(palette.data(), K + 1, mesh.position.data(), mesh.normal.data(), mesh.tangent.data(), mesh.indices.data(), mesh.weights.data(), V, skinned.data());
+            const auto sk = animator.getSkinnedVertices();
+            for (size_t e = 0; e < skinned.size(); ++e) CHECK(close(sk[e], skinned[e]), "step %d skinned %zu: %g vs %g", step, e, sk[e], skinned[e]);
+        }
+        CHECK(animator.getJointModelMatrix("no_such_joint") == glm::mat4(1.f), "unknown joint must give identity (C12)");
+        CHECK(animator.getPlaybackState() == SkeletalAnimatorPlaybackState::Paused, "pause toggled once and a state is playing");
+        std::printf("gpu: stand-alone animator, %d ticks compared with matrices/palette/skin, %zu events\n", checked, log.events.size());
+    }
+
+    // ---- batched scene component: many animators in different situations, one device step per frame ----
+    {
+        const int64_t n = 300;
+        SkeletalAnimationSceneComponent scene(*skel, anims, def, armature, nullptr);
+        CHECK(scene.init(n).has_value(), "scene init");
+        std::vector<std::unique_ptr<orc::RefAnimator>> refs;
+        for (int64_t i = 0; i < n; ++i) refs.push_back(std::make_unique<orc::RefAnimator>(o.skel, o.named, rdef));
+        const char* states[] = {"locomotion", "talk", "strafe", "greet"};
+        for (int frame = 0; frame < 50; ++frame) {
+            for (int64_t i = 0; i < n; ++i) {
+                auto& a = scene.getAnimator(i);
+                if (frame == (int)(i % 7)) { a.play(states[i % 4]); refs[i]->play(states[i % 4]); }
+                if (frame == 20 + (int)(i % 5)) { a.play(states[(i + 1) % 4]); refs[i]->play(states[(i + 1) % 4]); }
+                if (frame % 10 == (int)(i % 10)) {
+                    const float bx = std::sin(0.1f * (float)(i + frame)), by = std::cos(0.07f * (float)(i * 3 + frame));
+                    a.setBlendPosition(glm::vec2(bx, by));
+                    refs[i]->setBlendPosition({bx, by});
+                }
+            }
+            auto r = scene.update(1 / 30.f);
+            CHECK(r.has_value(), "scene update frame %d: %s", frame, r ? "" : r.error().c_str());
+            for (int64_t i = 0; i < n; ++i) {
+                std::string err;
+                refs[i]->update(1 / 30.f, err);
+            }
+            if (frame % 7 != 6) continue;
+            std::vector<float> flipped(16);
+            for (int64_t i = 0; i < n; i += 13) {
+                auto& a = scene.getAnimator(i);
+                for (int j = 0; j < J; j += 5) {
+                    const glm::mat4 m = a.getJointModelMatrix(o.skel->names[j]);
+                    orc_flip_handedness(refs[i]->models().data() + (size_t)j * 16, flipped.data());
+                    for (int e = 0; e < 16; ++e) CHECK(close(glm::value_ptr(m)[e], flipped[e]), "frame %d animator %ld joint %d", frame, (long)i, j);
+                }
+            }
+        }
+        // culling through the scene component against the oracle
+        std::vector<float> wi((size_t)n * 16, 0.f), bbox((size_t)n * 6);
+        for (int64_t i = 0; i < n; ++i) {
+            float* m = &wi[(size_t)i * 16];
+            m[0] = m[5] = m[10] = m[15] = 1.f;
+            m[12] = -(float)((i % 40) - 20) * 1.5f;   // world = translate(x, 0, z): inverse translates back
+            m[14] = -(float)(i / 40) * 3.f;
+            const float b[6] = {-0.3f, 0.f, -0.3f, 0.3f, 1.8f, 0.3f};
+            std::memcpy(&bbox[(size_t)i * 6], b, sizeof b);
+        }
+        glm::mat4 vp(1.f);
+        const float vpv[16] = {0.974279f, 0, 0, 0, 0, 1.732051f, 0, 0, 0, 0, 1.0003f, 1, 0, -1.5f, 1.7f, 2.0f};
+        std::memcpy(glm::value_ptr(vp), vpv, sizeof vpv);
+        CHECK(scene.setInstances(wi.data(), bbox.data()).has_value(), "setInstances");
+        CHECK(scene.setCamera(vp, 0.f).has_value(), "setCamera");
+        CHECK(scene.update(1 / 30.f).has_value(), "scene update with cull");
+        float corners[24];
+        orc_frustum_corners(vpv, 0.f, corners);
+        int culled = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const bool ref = !orc_cull_visible(corners, &wi[(size_t)i * 16], &bbox[(size_t)i * 6]);
+            CHECK(scene.shouldEntityBeCulled(i) == ref, "cull of entity %ld", (long)i);
+            culled += ref;
+        }
+        CHECK(culled > 0 && culled < n, "cull test must see both outcomes (%d of %ld culled)", culled, (long)n);
+        std::printf("gpu: scene component, %ld animators x 51 frames, %d culled\n", (long)n, culled);
+    }
+    std::printf("gpu: %d failures\n", g_failures);
+    return g_failures ? 1 : 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) { std::printf("usage: animator_test <assets_dir> cpu|gpu\n"); return 2; }
+    return std::string(argv[2]) == "gpu" ? runGpu(argv[1]) : runCpu(argv[1]);
+}

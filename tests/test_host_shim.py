@@ -1,0 +1,60 @@
+"""Host shim (darmok_b200/host: SkeletalAnimator / SkeletalAnimationSceneComponent over the C ABI) against the oracle's
+restatement of darmok's animator (oracle/animator_ref.cpp).  The comparison itself is the C++ program
+tests/cpp/animator_test.cpp; this file generates the assets, builds it and runs its two modes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from darmok_b200 import build, synth
+from oracle import oracle_py
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLIPS = ["Idle01", "Run01_Backward", "Run01_BackwardLeft", "Run01_BackwardRight", "Run01_Forward", "Run01_ForwardLeft",
+         "Run01_ForwardRight", "Run01_Left", "Run01_Right", "Talk01"]   # samples/ozz/assets/animator.json
+
+
+@pytest.fixture(scope="module")
+def binary():
+    build.build()
+    oracle_py.build()
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "animator_test"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return os.path.join(ROOT, "tests", "cpp", "animator_test")
+
+
+@pytest.fixture(scope="module")
+def assets_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("shim_assets")
+    skel = synth.make_skeleton(67)
+    (d / "skeleton.ozz").write_bytes(skel.archive)
+    durations = [1.0, 0.8, 0.8, 0.8, 0.75, 0.8, 0.8, 0.9, 0.9, 2.5]
+    for i, (name, dur) in enumerate(zip(CLIPS, durations)):
+        (d / f"{name}.ozz").write_bytes(synth.make_clip(skel, name, seed=100 + i, duration=dur).archive)
+    arm = synth.make_armature(skel)
+    arm.names[5] = "not_a_joint"     # getJointModelMatrix gives identity for it
+    (d / "armature.bin").write_bytes(arm.inv_bind.astype("<f4").tobytes())
+    (d / "armature.txt").write_text("\n".join(arm.names) + "\n")
+    mesh = synth.make_mesh(333, 67, seed=4, unskinned_fraction=0.05)
+    (d / "mesh.bin").write_bytes(np.concatenate([mesh.pos.ravel(), mesh.nrm.ravel(), mesh.tan.ravel(), mesh.indices.ravel(),
+                                                 mesh.weights.ravel()]).astype("<f4").tobytes())
+    return str(d)
+
+
+def _run(binary, assets_dir, mode):
+    r = subprocess.run([binary, assets_dir, mode], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    return r.stdout
+
+
+def test_state_machine_matches_reference_animator_on_cpu(binary, assets_dir):
+    out = _run(binary, assets_dir, "cpu")
+    assert "0 failures" in out
+
+
+@pytest.mark.gpu
+def test_animator_and_scene_component_on_device(binary, assets_dir):
+    out = _run(binary, assets_dir, "gpu")
+    assert "gpu: 0 failures" in out
