@@ -665,7 +665,7 @@ dmk_status dmk_crowd_create(dmk_context_t ctx, dmk_skeleton_t skel, dmk_clipset_
     if (arm) {
         const size_t ps = static_cast<size_t>(arm->num_joints + 1);
         DMK_CUDA(ctx, dev_alloc(&c->d_palette, static_cast<size_t>(n) * ps * 16));
-        DMK_CUDA(ctx, dev_alloc(&c->d_palette34, static_cast<size_t>(n) * ps * 12));
+        DMK_CUDA(ctx, dev_alloc(&c->d_palette34, static_cast<size_t>(n) * ps * 16));
     }
     if (mesh) {
         DMK_CUDA(ctx, dev_alloc(&c->d_skinned, static_cast<size_t>(n) * static_cast<size_t>(mesh->vpad) * 9));

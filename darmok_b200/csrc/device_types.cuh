@@ -82,7 +82,7 @@ struct PoseParams {
     int advance;              // run the clip clocks before sampling
     // outputs (null = skip)
     float* palette;           // [N][K+1][16] column-major mat4
-    float* palette34;         // [N][K+1][12] row-major 3x4 (rows of 4), consumed by the skinning kernel
+    float* palette34;         // [N][K+1][16] row-major 3x4 (rows of 4) + one zero row: 2 sectors per slot, for the skinning kernel
     float* models;            // [N][J][16] left-handed model matrices
     float* locals;            // [N][num_soa][40]
     int32_t* key_indices;     // [N][L][3][P][2]
@@ -90,7 +90,7 @@ struct PoseParams {
 };
 
 struct SkinParams {
-    const float* palette34;   // [N][PS][12]
+    const float* palette34;   // [N][PS][16] (3 rows used)
     const float* pos;         // [Vpad][3]
     const float* nrm;
     const float* tan;

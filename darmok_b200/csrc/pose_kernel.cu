@@ -23,6 +23,12 @@ namespace dmk {
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
+constexpr int kMS = 13;  // shared-memory stride of a 3x4 matrix in floats: odd, so lanes on consecutive joints hit distinct banks
+
+__device__ __forceinline__ void st_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h)
+                 : "memory");
+}
 
 __device__ __forceinline__ float rcp_exact(float x) { return __fdiv_rn(1.f, x); }
 __device__ __forceinline__ float rsqrt_exact(float x) { return __fdiv_rn(1.f, __fsqrt_rn(x)); }
@@ -292,22 +298,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // ---- shared tables, staged once per persistent block ----
-    float* s_inv_bind = reinterpret_cast<float*>(smem_raw);                   // [K][12]
-    float* s_identity = s_inv_bind + (size_t)K * 12;                          // [12] (+4 pad)
+    float* s_inv_bind = reinterpret_cast<float*>(smem_raw);                   // [K][kMS]
+    float* s_identity = s_inv_bind + (size_t)K * kMS;                         // [12] (+4 pad)
     int32_t* s_remap = reinterpret_cast<int32_t*>(s_identity + 16);           // [K]
     int16_t* s_parents = reinterpret_cast<int16_t*>(s_remap + ((K + 3) & ~3)); // [P]
     uint16_t* s_sched = reinterpret_cast<uint16_t*>(s_parents + ((P + 7) & ~7)); // [rounds][32]
-    const int regA = max(P * 12, PS * 16);                                    // locals -> mat4 palette staging
-    const int regB = P * 12;                                                  // model matrices
-    const int regC = PS * 12;                                                 // 3x4 palette staging
-    const int per_warp = (regA + regB + regC + 3) & ~3;
+    const int per_warp = (2 * P * kMS + 3) & ~3;                              // local + model matrices of one character
     float* s_warp0 = reinterpret_cast<float*>(
         (reinterpret_cast<uintptr_t>(s_sched + (size_t)p.skel.rounds * 32) + 15) & ~uintptr_t(15));
-    float* s_loc = s_warp0 + (size_t)warp * per_warp;  // region A
-    float* s_mod = s_loc + regA;                        // region B
-    float* s_p34 = s_mod + regB;                        // region C
+    float* s_loc = s_warp0 + (size_t)warp * per_warp;  // [P][kMS] local matrices
+    float* s_mod = s_loc + (size_t)P * kMS;             // [P][kMS] model matrices
 
-    for (int i = threadIdx.x; i < K * 12; i += blockDim.x) s_inv_bind[i] = p.arm.inv_bind[i];
+    for (int i = threadIdx.x; i < K * 12; i += blockDim.x) s_inv_bind[(i / 12) * kMS + i % 12] = p.arm.inv_bind[i];
     for (int i = threadIdx.x; i < K; i += blockDim.x) s_remap[i] = p.arm.remap[i];
     for (int i = threadIdx.x; i < P; i += blockDim.x) s_parents[i] = i < J ? p.skel.parents[i] : (int16_t)-1;
     for (int i = threadIdx.x; i < p.skel.rounds * 32; i += blockDim.x) s_sched[i] = p.skel.schedule[i];
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
                 o[12] = acc.r[0]; o[16] = acc.r[1]; o[20] = acc.r[2]; o[24] = acc.r[3];
                 o[28] = acc.s[0]; o[32] = acc.s[1]; o[36] = acc.s[2];
             }
-            from_affine(acc, s_loc + (size_t)j * 12);
+            from_affine(acc, s_loc + (size_t)j * kMS);
         }
         __syncwarp();
 
@@ -408,10 +410,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
             if (task != kIdleTask) {
                 const int j = task & 0xfff, col = task >> 12;
                 const int parent = s_parents[j];
-                const float* pm = parent < 0 ? s_identity : s_mod + (size_t)parent * 12;
-                const float* lc = s_loc + (size_t)j * 12 + col * 3;
+                const float* pm = parent < 0 ? s_identity : s_mod + (size_t)parent * kMS;
+                const float* lc = s_loc + (size_t)j * kMS + col * 3;
                 const float l0 = lc[0], l1 = lc[1], l2 = lc[2], l3 = col == 3 ? 1.f : 0.f;
-                float* o = s_mod + (size_t)j * 12 + col * 3;
+                float* o = s_mod + (size_t)j * kMS + col * 3;
 #pragma unroll
                 for (int r = 0; r < 3; ++r)  // ozz Float4x4 product: (a0*x + a1*y) + (a2*z + a3*w)
                     o[r] = (pm[r] * l0 + pm[3 + r] * l1) + (pm[6 + r] * l2 + pm[9 + r] * l3);
@@ -420,10 +422,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
         }
 
         // ---- K3: flip handedness + palette = model * inverse bind ----
-        float* s_pal = s_loc;  // locals are dead: region A becomes the mat4 palette staging
         if (p.models) {
             for (int j = lane; j < J; j += 32) {
-                const float* m = s_mod + (size_t)j * 12;
+                const float* m = s_mod + (size_t)j * kMS;
                 float* o = p.models + ((size_t)c * J + j) * 16;
                 o[0] = m[0]; o[1] = m[1]; o[2] = -m[2]; o[3] = 0.f;
                 o[4] = m[3]; o[5] = m[4]; o[6] = -m[5]; o[7] = 0.f;
@@ -432,13 +433,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
             }
         }
         if (p.palette || p.palette34) {
-            if (lane < 16) s_pal[lane] = (lane % 5 == 0) ? 1.f : 0.f;  // slot 0 = mat4(1)
-            if (lane < 12) s_p34[lane] = (lane % 5 == 0) ? 1.f : 0.f;  // rows (1,0,0,0) (0,1,0,0) (0,0,1,0)
+            // Each lane owns whole palette slots and writes them as 256-bit full-sector stores (a mat4 = 2 sectors; the
+            // 3x4 row-major copy for the skinning kernel is padded to 4 rows = 2 sectors as well): no staging pass.
+            float* pal = p.palette ? p.palette + (size_t)c * PS * 16 : nullptr;
+            float* p34 = p.palette34 ? p.palette34 + (size_t)c * PS * 16 : nullptr;
+            if (lane == 0) {  // slot 0 = mat4(1) (src/skeleton.cpp:238)
+                if (pal) { st_v8(pal, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(pal + 8, 0, 0, 1, 0, 0, 0, 0, 1); }
+                if (p34) { st_v8(p34, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(p34 + 8, 0, 0, 1, 0, 0, 0, 0, 0); }
+            }
             for (int k = lane; k < K; k += 32) {
                 const int jm = s_remap[k];
                 float m[12];
                 if (jm >= 0) {
-                    const float* src = s_mod + (size_t)jm * 12;  // Math::flipHandedness: Z * M * Z
+                    const float* src = s_mod + (size_t)jm * kMS;  // Math::flipHandedness: Z * M * Z
                     m[0] = src[0]; m[1] = src[1]; m[2] = -src[2];
                     m[3] = src[3]; m[4] = src[4]; m[5] = -src[5];
                     m[6] = -src[6]; m[7] = -src[7]; m[8] = src[8];
@@ -447,51 +454,43 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
 #pragma unroll
                     for (int e = 0; e < 12; ++e) m[e] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
                 }
-                const float* b = s_inv_bind + (size_t)k * 12;
-                float* o = s_pal + (size_t)(k + 1) * 16;
-                float* o34 = s_p34 + (size_t)(k + 1) * 12;
+                const float* b = s_inv_bind + (size_t)k * kMS;
+                float v[4][3];  // [column][row]
 #pragma unroll
                 for (int col = 0; col < 4; ++col) {
                     const float b0 = b[col * 3 + 0], b1 = b[col * 3 + 1], b2 = b[col * 3 + 2];
                     const float b3 = col == 3 ? 1.f : 0.f;
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) {  // glm mat4 * mat4: ((A0*b0 + A1*b1) + A2*b2) + A3*b3
-                        const float v = ((m[r] * b0 + m[3 + r] * b1) + m[6 + r] * b2) + m[9 + r] * b3;
-                        o[col * 4 + r] = v;
-                        o34[r * 4 + col] = v;
-                    }
-                    o[col * 4 + 3] = b3;
+                    for (int r = 0; r < 3; ++r)  // glm mat4 * mat4: ((A0*b0 + A1*b1) + A2*b2) + A3*b3
+                        v[col][r] = ((m[r] * b0 + m[3 + r] * b1) + m[6 + r] * b2) + m[9 + r] * b3;
+                }
+                if (pal) {
+                    float* o = pal + (size_t)(k + 1) * 16;
+                    st_v8(o, v[0][0], v[0][1], v[0][2], 0.f, v[1][0], v[1][1], v[1][2], 0.f);
+                    st_v8(o + 8, v[2][0], v[2][1], v[2][2], 0.f, v[3][0], v[3][1], v[3][2], 1.f);
+                }
+                if (p34) {
+                    float* o = p34 + (size_t)(k + 1) * 16;
+                    st_v8(o, v[0][0], v[1][0], v[2][0], v[3][0], v[0][1], v[1][1], v[2][1], v[3][1]);
+                    st_v8(o + 8, v[0][2], v[1][2], v[2][2], v[3][2], 0.f, 0.f, 0.f, 0.f);
                 }
             }
-            __syncwarp();
-            if (p.palette) {
-                float4* dst = reinterpret_cast<float4*>(p.palette + (size_t)c * PS * 16);
-                const float4* src = reinterpret_cast<const float4*>(s_pal);
-                for (int i = lane; i < PS * 4; i += 32) dst[i] = src[i];
-            }
-            if (p.palette34) {
-                float4* dst = reinterpret_cast<float4*>(p.palette34 + (size_t)c * PS * 12);
-                const float4* src = reinterpret_cast<const float4*>(s_p34);
-                for (int i = lane; i < PS * 3; i += 32) dst[i] = src[i];
-            }
         }
-        __syncwarp();  // staging regions are reused by the next character
+        __syncwarp();  // the matrix arrays are reused by the next character
     }
 }
 
 }  // namespace
 
 size_t pose_smem_bytes(const PoseParams& p) {
-    const int P = p.skel.padded_joints, K = p.arm.num_joints, PS = K + 1;
+    const int P = p.skel.padded_joints, K = p.arm.num_joints;
     size_t b = 0;
-    b += (size_t)K * 12 * 4 + 16 * 4;
+    b += (size_t)K * kMS * 4 + 16 * 4;
     b += (size_t)((K + 3) & ~3) * 4;
     b += (size_t)((P + 7) & ~7) * 2;
     b += (size_t)p.skel.rounds * 32 * 2;
     b += 16;
-    const int regA = P * 12 > PS * 16 ? P * 12 : PS * 16;
-    const size_t per_warp = (size_t)((regA + P * 12 + PS * 12 + 3) & ~3) * 4;
-    b += per_warp * kWarpsPerBlock;
+    b += (size_t)((2 * P * kMS + 3) & ~3) * 4 * kWarpsPerBlock;
     return b;
 }
 

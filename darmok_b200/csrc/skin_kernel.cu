@@ -113,8 +113,8 @@ template <int REPL>
 __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int PS = p.palette_size;
-    const uint32_t pal_bytes = (uint32_t)PS * 48u;             // 3x4 floats per slot
-    const uint32_t repl_bytes = pal_bytes * REPL;
+    const uint32_t pal_bytes = (uint32_t)PS * 64u;             // staged palette: 3 rows of 4 floats + 1 pad row per slot
+    const uint32_t repl_bytes = (uint32_t)PS * 48u * REPL;     // replicated: the 3 rows only
     unsigned char* s_repl = smem;                                        // [kNumRepl][PS*3][REPL] float4
     unsigned char* s_stage = smem + kNumRepl * (size_t)repl_bytes;       // [kNumStage][PS*3] float4 (bulk copy dst)
     uint64_t* s_tma_bar = reinterpret_cast<uint64_t*>(s_stage + kNumStage * (size_t)pal_bytes);  // [kNumStage]
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
             if (i < my_count) {
                 const uint32_t b = q_issue % kNumStage;
                 mbar_expect_tx(&s_tma_bar[b], pal_bytes);
-                bulk_g2s(s_stage + (size_t)b * pal_bytes, p.palette34 + (size_t)char_of(i) * PS * 12, pal_bytes, &s_tma_bar[b]);
+                bulk_g2s(s_stage + (size_t)b * pal_bytes, p.palette34 + (size_t)char_of(i) * PS * 16, pal_bytes, &s_tma_bar[b]);
                 ++q_issue;
             }
         };
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
             const float4* src = reinterpret_cast<const float4*>(s_stage + (size_t)sb * pal_bytes);
             float4* dst = reinterpret_cast<float4*>(s_repl + (size_t)rb * repl_bytes);
             for (int t = tid; t < PS * 3; t += blockDim.x) {
-                const float4 val = src[t];
+                const float4 val = src[(t / 3) * 4 + t % 3];
 #pragma unroll
                 for (int k = 0; k < REPL; ++k) dst[t * REPL + ((lane + k) & (REPL - 1))] = val;
             }
@@ -273,7 +273,7 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms) {
     plan.tile_vertices = tv;
     plan.threads = ((tv / kVPT) + 31) / 32 * 32;
     plan.replicas = kRepl;
-    plan.smem = (size_t)palette_size * 48 * (kNumRepl * kRepl + kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
+    plan.smem = (size_t)palette_size * (48 * kNumRepl * kRepl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
     int occ = 1;
     cudaFuncSetAttribute(skin_kernel<kRepl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skin_kernel<kRepl>, plan.threads, plan.smem) != cudaSuccess || occ < 1)
