@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Side measurements for the BASELINE.json configs that bench.py does not time (bench.py = configs[2], --gpus N = configs[3]):
+
+  config 1  samples/ozz single character: the oracle (reference CPU plumbing) per character tick, 9-clip locomotion blend
+  config 2  10k characters, 67 joints, single looping clip, palette only, 1 GPU
+  config 5  10M-instance frustum/AABB cull, visibility compared bit for bit with the oracle on a 2M-instance prefix
+
+Prints one JSON line per config (also appended to gpurun_out/configs.jsonl)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+FLT_MIN = float(np.finfo(np.float32).tiny)
+
+
+def emit(d):
+    line = json.dumps(d)
+    print(line, flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "a") as f:
+        f.write(line + "\n")
+
+
+def config1():
+    from darmok_b200 import synth
+    from oracle import oracle_py as O
+    skel = synth.make_skeleton(67)
+    clips = [synth.make_clip(skel, f"c{i}", seed=i, duration=0.8 + 0.05 * i) for i in range(9)]
+    arm = synth.make_armature(skel)
+    oskel = O.Skeleton(skel.archive)
+    oclips = [O.Animation(c.archive) for c in clips]
+    remap = np.array([oskel.find_joint(n) for n in arm.names], np.int32)
+    crowd = O.Crowd(oskel, oclips, remap, arm.inv_bind, 1, 9)
+    clip = np.arange(9, dtype=np.int32)[:, None]
+    weight = np.full((9, 1), 1 / 9, np.float32)
+    ratio = np.zeros((9, 1), np.float32)
+    ticks = 20000
+    t0 = time.perf_counter()
+    for i in range(ticks):
+        ratio = np.float32((ratio + 1 / 60.0) % 1.0)
+        crowd.step(clip, ratio, weight, 0.2, want=("palette",), num_threads=1)
+    dt = time.perf_counter() - t0
+    emit({"config": 1, "what": "oracle (CPU reference plumbing): 1 character, 9-clip state blend + local-to-model + palette per tick",
+          "us_per_character_tick": dt / ticks * 1e6, "note": "includes the ctypes call overhead of one Python call per tick"})
+
+
+def config2():
+    import torch
+    from darmok_b200 import capi, synth
+    skel_s = synth.make_skeleton(67)
+    clips_s = [synth.make_clip(skel_s, "loop", seed=0, duration=1.5)]
+    arm_s = synth.make_armature(skel_s)
+    n = 10_000
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx = capi.Context(0, stream.cuda_stream)
+        skel = capi.Skeleton(ctx, skel_s.archive)
+        clip_objs = [capi.Clip(ctx, c.archive) for c in clips_s]
+        clips = capi.ClipSet(ctx, skel, clip_objs)
+        arm = capi.Armature(ctx, skel, arm_s.names, arm_s.inv_bind)
+        crowd = capi.Crowd(ctx, skel, clips, arm, None, n, 1)
+        cr = synth.make_crowd(n, 1, 1, seed=42)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed)
+        flags = capi.STEP_ADVANCE | capi.STEP_POSE
+        for _ in range(20):
+            crowd.step(1 / 60, flags)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 500
+        e0.record(stream)
+        for _ in range(steps):
+            crowd.step(1 / 60, flags)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    emit({"config": 2, "what": "10k characters x 67 joints, single looping clip, palette only (clocks + sample + L2M + palette)",
+          "us_per_step": ms * 1e3, "characters_per_sec": n / (ms * 1e-3), "algorithmic_GBps": n * 4384 / (ms * 1e-3) / 1e9,
+          "note": "one kernel launch per step; launch/latency bound at this size (HBM floor is 6.7 us)"})
+
+
+def config5():
+    import torch
+    from darmok_b200 import capi, synth
+    from oracle import oracle_py as O
+    n = 10_000_000
+    inst = synth.make_instances(n, seed=5, extent=500.0)
+    vp = synth.sample_camera_view_proj()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx = capi.Context(0, stream.cuda_stream)
+        corners = ctx.frustum_corners(vp, 0.0)
+        wi = torch.from_numpy(inst.world_inverse).cuda()
+        bb = torch.from_numpy(inst.bbox).cuda()
+        bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+        for _ in range(5):
+            ctx.cull_dev(corners, wi.data_ptr(), bb.data_ptr(), n, bits.data_ptr())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 50
+        e0.record(stream)
+        for _ in range(steps):
+            ctx.cull_dev(corners, wi.data_ptr(), bb.data_ptr(), n, bits.data_ptr())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        got = bits.cpu().numpy().view(np.uint32)
+        t0 = time.perf_counter()
+        host_bits = ctx.cull_host(vp, 0.0, inst.world_inverse, inst.bbox)
+        e2e_s = time.perf_counter() - t0
+    m = 2_000_000
+    t0 = time.perf_counter()
+    ref = O.cull_batch(O.frustum_corners(vp, 0.0), inst.world_inverse[:m], inst.bbox[:m])
+    cpu_s = time.perf_counter() - t0
+    exact = bool(np.array_equal(got[: m // 32], ref[: m // 32])) and bool(np.array_equal(host_bits, got))
+    visible = int(np.unpackbits(got.view(np.uint8)).sum())
+    peak = 6542.4
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except (OSError, KeyError):
+        pass
+    gbps = n * 88.125 / (ms * 1e-3) / 1e9
+    emit({"config": 5, "what": "10M-instance frustum vs local-AABB cull (culling.cpp semantics), 1 GPU", "ms_per_launch": ms,
+          "instances_per_sec": n / (ms * 1e-3), "algorithmic_GBps": gbps, "frac_of_measured_hbm_peak": gbps / peak, "visible": visible,
+          "visibility_bit_exact_vs_oracle": exact, "oracle_checked_instances": m,
+          "e2e_host_buffers": {"seconds": e2e_s, "instances_per_sec": n / e2e_s, "h2d_bytes": n * 88, "d2h_bytes": int(host_bits.nbytes)},
+          "cpu_oracle": {"instances_per_sec": m / cpu_s, "threads": O.max_threads()}})
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["1", "2", "5"]
+    if "1" in which:
+        config1()
+    if "2" in which:
+        config2()
+    if "5" in which:
+        config5()
