@@ -66,6 +66,7 @@ SIGNATURES = [
     ("dmk_crowd_set_programs", _i, [_vp, _i, _vp, _vp, _vp, _vp]),
     ("dmk_crowd_update_layers", _i, [_vp, _i, _vp, _vp, _vp]),
     ("dmk_crowd_set_instances", _i, [_vp, _vp, _vp]),
+    ("dmk_crowd_set_transforms", _i, [_vp, _vp, _vp, _vp, _vp]),
     ("dmk_crowd_set_camera", _i, [_vp, _vp, _f]),
     ("dmk_crowd_set_frustum_corners", _i, [_vp, _vp]),
     ("dmk_crowd_step", _i, [_vp, _f, _u32]),
@@ -83,6 +84,7 @@ SIGNATURES = [
     ("dmk_crowd_get_ratios", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_pack_visible_palettes", _i, [_vp, _vp, _i64]),
     ("dmk_cull_dev", _i, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    ("dmk_cull_trs_dev", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     ("dmk_cull_host", _i, [_vp, _vp, _f, _vp, _vp, _i64, _vp]),
     ("dmk_frustum_corners", _i, [_vp, _f, _vp]),
 ]
@@ -166,6 +168,11 @@ class Context:
         bits = np.zeros((n + 31) // 32, np.uint32)
         self.check(lib().dmk_cull_host(self.h, _ptr(vp), near_depth, _ptr(wi), _ptr(bb), n, _ptr(bits)))
         return bits
+
+    def cull_trs_dev(self, corners, position_ptr, rotation_ptr, scale_ptr, bbox_ptr, n, vis_bits_ptr, world_inverse_out_ptr=None):
+        c = _f32(corners)
+        self.check(lib().dmk_cull_trs_dev(self.h, _ptr(c), position_ptr, rotation_ptr, scale_ptr, bbox_ptr, n, vis_bits_ptr,
+                                          world_inverse_out_ptr))
 
     def cull_dev(self, corners, world_inverse_ptr, bbox_ptr, n, vis_bits_ptr):
         c = _f32(corners)
@@ -304,6 +311,10 @@ class Crowd:
     def set_instances(self, world_inverse, bbox):
         wi, bb = _f32(world_inverse), _f32(bbox)
         self.ctx.check(lib().dmk_crowd_set_instances(self.h, _ptr(wi), _ptr(bb)))
+
+    def set_transforms(self, position, rotation, scale, bbox):
+        p, q, s, b = _f32(position), _f32(rotation), _f32(scale), _f32(bbox)
+        self.ctx.check(lib().dmk_crowd_set_transforms(self.h, _ptr(p), _ptr(q), _ptr(s), _ptr(b)))
 
     def set_camera(self, view_proj, near_depth=0.0):
         vp = _f32(view_proj)

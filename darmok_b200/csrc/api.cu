@@ -116,6 +116,8 @@ struct dmk_crowd_s {
     int32_t* h_error = nullptr;  // pinned
     // cull
     float *d_world_inverse = nullptr, *d_bbox = nullptr;
+    float *d_position = nullptr, *d_rotation = nullptr, *d_scale = nullptr;
+    bool use_trs = false;
     uint32_t* d_vis_bits = nullptr;
     int32_t *d_visible_ids = nullptr, *d_visible_count = nullptr, *d_scratch = nullptr;
     float corners[24] = {0};
@@ -687,7 +689,7 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
     cudaStreamSynchronize(c->ctx->stream);
     for (void* p : {(void*)c->d_clip, (void*)c->d_ratio, (void*)c->d_weight, (void*)c->d_speed, (void*)c->d_loop, (void*)c->d_looped,
                     (void*)c->d_program, (void*)c->d_palette, (void*)c->d_palette34, (void*)c->d_skinned, (void*)c->d_models, (void*)c->d_locals,
-                    (void*)c->d_key_indices, (void*)c->d_error, (void*)c->d_world_inverse, (void*)c->d_bbox, (void*)c->d_vis_bits,
+                    (void*)c->d_key_indices, (void*)c->d_error, (void*)c->d_world_inverse, (void*)c->d_bbox, (void*)c->d_position, (void*)c->d_rotation, (void*)c->d_scale, (void*)c->d_vis_bits,
                     (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch})
         dev_free(p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -841,6 +843,27 @@ dmk_status dmk_crowd_set_instances(dmk_crowd_t c, const float* world_inverse, co
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_bbox, bbox, n * 24, cudaMemcpyHostToDevice, ctx->stream));
     DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     c->instances_set = true;
+    c->use_trs = false;
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_set_transforms(dmk_crowd_t c, const float* position, const float* rotation, const float* scale, const float* bbox) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!position || !rotation || !scale || !bbox) return fail(ctx, DMK_ERR_INVALID, "null transform array");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t n = static_cast<size_t>(c->n);
+    if (!c->d_position) DMK_CUDA(ctx, dev_alloc(&c->d_position, n * 3));
+    if (!c->d_rotation) DMK_CUDA(ctx, dev_alloc(&c->d_rotation, n * 4));
+    if (!c->d_scale) DMK_CUDA(ctx, dev_alloc(&c->d_scale, n * 3));
+    if (!c->d_bbox) DMK_CUDA(ctx, dev_alloc(&c->d_bbox, n * 6));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_position, position, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_rotation, rotation, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_scale, scale, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_bbox, bbox, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    c->instances_set = true;
+    c->use_trs = true;
     return DMK_OK;
 }
 
@@ -934,7 +957,13 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         if (!c->instances_set || !c->camera_set)
             return fail(ctx, DMK_ERR_INVALID, "cull needs dmk_crowd_set_instances and dmk_crowd_set_camera");
         CullParams p{};
-        p.world_inverse = c->d_world_inverse;
+        if (c->use_trs) {
+            p.position = c->d_position;
+            p.rotation = c->d_rotation;
+            p.scale = c->d_scale;
+        } else {
+            p.world_inverse = c->d_world_inverse;
+        }
         p.bbox = c->d_bbox;
         p.n = c->n;
         p.vis_bits = c->d_vis_bits;
@@ -1081,6 +1110,26 @@ dmk_status dmk_cull_dev(dmk_context_t ctx, const float* corners_host, const floa
     if (bind(ctx)) return DMK_ERR_CUDA;
     CullParams p{};
     p.world_inverse = world_inverse_dev;
+    p.bbox = bbox_dev;
+    p.n = n;
+    p.vis_bits = vis_bits_dev;
+    std::memcpy(p.corners, corners_host, sizeof p.corners);
+    DMK_CUDA(ctx, launch_cull(p, ctx->stream));
+    ++ctx->launches;
+    return DMK_OK;
+}
+
+dmk_status dmk_cull_trs_dev(dmk_context_t ctx, const float* corners_host, const float* position_dev, const float* rotation_dev,
+                            const float* scale_dev, const float* bbox_dev, int64_t n, uint32_t* vis_bits_dev, float* world_inverse_out_dev) {
+    if (!ctx) return DMK_ERR_INVALID;
+    if (!corners_host || n < 0 || (n > 0 && (!position_dev || !rotation_dev || !scale_dev || !bbox_dev || !vis_bits_dev)))
+        return fail(ctx, DMK_ERR_INVALID, "null argument");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    CullParams p{};
+    p.position = position_dev;
+    p.rotation = rotation_dev;
+    p.scale = scale_dev;
+    p.world_inverse_out = world_inverse_out_dev;
     p.bbox = bbox_dev;
     p.n = n;
     p.vis_bits = vis_bits_dev;

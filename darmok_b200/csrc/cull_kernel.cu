@@ -44,12 +44,68 @@ __device__ __forceinline__ bool box_in_front(V3 a, V3 b, V3 c, V3 mn, V3 mx) {
     return !(sd_min <= 0.f);
 }
 
+// Transform::update for an entity without parent (src/transform.cpp:286-309): world inverse =
+// glm::inverse(glm::translate(p) * glm::mat4_cast(q) * glm::scale(s)), all in glm's scalar operation order.
+// The two products only add exact zeros to R[c][r] * s[c] and to p, so the local matrix is [R * diag(s) | p].
+__device__ __forceinline__ void world_inverse_from_trs(const float* __restrict__ pos, const float* __restrict__ rot,
+                                                       const float* __restrict__ scl, int64_t i, float4& o0, float4& o1, float4& o2, float4& o3) {
+    const float px = __ldg(pos + i * 3), py = __ldg(pos + i * 3 + 1), pz = __ldg(pos + i * 3 + 2);
+    const float4 q = __ldg(reinterpret_cast<const float4*>(rot) + i);
+    const float sx = __ldg(scl + i * 3), sy = __ldg(scl + i * 3 + 1), sz = __ldg(scl + i * 3 + 2);
+    const float qxx = q.x * q.x, qyy = q.y * q.y, qzz = q.z * q.z, qxz = q.x * q.z, qxy = q.x * q.y, qyz = q.y * q.z;
+    const float qwx = q.w * q.x, qwy = q.w * q.y, qwz = q.w * q.z;
+    float m[4][4];  // m[column][row]
+    m[0][0] = (1.f - 2.f * (qyy + qzz)) * sx; m[0][1] = (2.f * (qxy + qwz)) * sx;       m[0][2] = (2.f * (qxz - qwy)) * sx;       m[0][3] = 0.f;
+    m[1][0] = (2.f * (qxy - qwz)) * sy;       m[1][1] = (1.f - 2.f * (qxx + qzz)) * sy; m[1][2] = (2.f * (qyz + qwx)) * sy;       m[1][3] = 0.f;
+    m[2][0] = (2.f * (qxz + qwy)) * sz;       m[2][1] = (2.f * (qyz - qwx)) * sz;       m[2][2] = (1.f - 2.f * (qxx + qyy)) * sz; m[2][3] = 0.f;
+    m[3][0] = px; m[3][1] = py; m[3][2] = pz; m[3][3] = 1.f;
+    // glm::detail::compute_inverse<4, 4>
+    const float c00 = m[2][2] * m[3][3] - m[3][2] * m[2][3], c02 = m[1][2] * m[3][3] - m[3][2] * m[1][3];
+    const float c03 = m[1][2] * m[2][3] - m[2][2] * m[1][3], c04 = m[2][1] * m[3][3] - m[3][1] * m[2][3];
+    const float c06 = m[1][1] * m[3][3] - m[3][1] * m[1][3], c07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
+    const float c08 = m[2][1] * m[3][2] - m[3][1] * m[2][2], c10 = m[1][1] * m[3][2] - m[3][1] * m[1][2];
+    const float c11 = m[1][1] * m[2][2] - m[2][1] * m[1][2], c12 = m[2][0] * m[3][3] - m[3][0] * m[2][3];
+    const float c14 = m[1][0] * m[3][3] - m[3][0] * m[1][3], c15 = m[1][0] * m[2][3] - m[2][0] * m[1][3];
+    const float c16 = m[2][0] * m[3][2] - m[3][0] * m[2][2], c18 = m[1][0] * m[3][2] - m[3][0] * m[1][2];
+    const float c19 = m[1][0] * m[2][2] - m[2][0] * m[1][2], c20 = m[2][0] * m[3][1] - m[3][0] * m[2][1];
+    const float c22 = m[1][0] * m[3][1] - m[3][0] * m[1][1], c23 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+    const float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+    const float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+    const float v0[4] = {m[1][0], m[0][0], m[0][0], m[0][0]}, v1[4] = {m[1][1], m[0][1], m[0][1], m[0][1]};
+    const float v2[4] = {m[1][2], m[0][2], m[0][2], m[0][2]}, v3[4] = {m[1][3], m[0][3], m[0][3], m[0][3]};
+    float inv[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float sa = (k & 1) ? -1.f : 1.f, sb = -sa;
+        inv[0][k] = ((v1[k] * f0[k] - v2[k] * f1[k]) + v3[k] * f2[k]) * sa;
+        inv[1][k] = ((v0[k] * f0[k] - v2[k] * f3[k]) + v3[k] * f4[k]) * sb;
+        inv[2][k] = ((v0[k] * f1[k] - v1[k] * f3[k]) + v3[k] * f5[k]) * sa;
+        inv[3][k] = ((v0[k] * f2[k] - v1[k] * f4[k]) + v2[k] * f5[k]) * sb;
+    }
+    const float d0 = m[0][0] * inv[0][0], d1 = m[0][1] * inv[1][0], d2 = m[0][2] * inv[2][0], d3 = m[0][3] * inv[3][0];
+    const float ood = __fdiv_rn(1.f, (d0 + d1) + (d2 + d3));
+    o0 = make_float4(inv[0][0] * ood, inv[0][1] * ood, inv[0][2] * ood, inv[0][3] * ood);
+    o1 = make_float4(inv[1][0] * ood, inv[1][1] * ood, inv[1][2] * ood, inv[1][3] * ood);
+    o2 = make_float4(inv[2][0] * ood, inv[2][1] * ood, inv[2][2] * ood, inv[2][3] * ood);
+    o3 = make_float4(inv[3][0] * ood, inv[3][1] * ood, inv[3][2] * ood, inv[3][3] * ood);
+}
+
+template <bool FROM_TRS>
 __global__ void __launch_bounds__(256) cull_kernel(const CullParams p) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool visible = false;
     if (i < p.n) {
-        const float4* m4 = reinterpret_cast<const float4*>(p.world_inverse + i * 16);
-        const float4 c0 = __ldg(m4 + 0), c1 = __ldg(m4 + 1), c2 = __ldg(m4 + 2), c3 = __ldg(m4 + 3);
+        float4 c0, c1, c2, c3;
+        if (FROM_TRS) {
+            world_inverse_from_trs(p.position, p.rotation, p.scale, i, c0, c1, c2, c3);
+            if (p.world_inverse_out) {
+                float4* o = reinterpret_cast<float4*>(p.world_inverse_out + i * 16);
+                o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+            }
+        } else {
+            const float4* m4 = reinterpret_cast<const float4*>(p.world_inverse + i * 16);
+            c0 = __ldg(m4 + 0); c1 = __ldg(m4 + 1); c2 = __ldg(m4 + 2); c3 = __ldg(m4 + 3);
+        }
         const float2* bb = reinterpret_cast<const float2*>(p.bbox + i * 6);
         const float2 b0 = __ldg(bb + 0), b1 = __ldg(bb + 1), b2 = __ldg(bb + 2);
         const V3 mn = {b0.x, b0.y, b1.x}, mx = {b1.y, b2.x, b2.y};
@@ -183,7 +239,8 @@ __global__ void pack_palettes_kernel(const float4* __restrict__ palette, int pal
 cudaError_t launch_cull(const CullParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int64_t blocks = (p.n + 255) / 256;
-    cull_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+    if (p.position) cull_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    else cull_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -107,6 +107,11 @@ struct SkinParams {
 };
 
 struct CullParams {
+    // either world_inverse, or (position, rotation, scale) from which Transform::update's world inverse is derived
+    const float* position;      // [n][3] or null
+    const float* rotation;      // [n][4] quaternion x, y, z, w
+    const float* scale;         // [n][3]
+    float* world_inverse_out;   // [n][16] optional: the derived matrices, for other consumers
     const float* world_inverse; // [n][16]
     const float* bbox;          // [n][6]
     int64_t n;

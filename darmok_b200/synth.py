@@ -398,3 +398,27 @@ def make_instances(n, seed=5, extent=500.0) -> SynthInstances:
     # bbox is in the entity's LOCAL space (culling.cpp:274-282 brings the frustum to local space)
     bbox = np.concatenate([-half, half], 1).astype(np.float32)
     return SynthInstances(wi, bbox)
+
+
+@dataclass
+class SynthTransforms:
+    position: np.ndarray   # f32 [N,3]
+    rotation: np.ndarray   # f32 [N,4] quaternion x, y, z, w
+    scale: np.ndarray      # f32 [N,3]
+    bbox: np.ndarray       # f32 [N,6]
+
+
+def make_transforms(n, seed=5, extent=500.0, uniform_scale=False) -> SynthTransforms:
+    """What darmok's Transform holds for each entity of the config-5 field: translation on the ground plane, yaw plus a
+    small tilt, scale; local-space bounding box of a character."""
+    rng = np.random.default_rng(seed)
+    s = rng.uniform(0.5, 2.0, (n, 1 if uniform_scale else 3))
+    s = np.repeat(s, 3, axis=1) if uniform_scale else s
+    pos = np.stack([rng.uniform(-extent, extent, n), rng.uniform(-1, 1, n), rng.uniform(-extent, extent, n)], 1)
+    yaw = quat_axis_angle(np.tile([0.0, 1.0, 0.0], (n, 1)), rng.uniform(0, 2 * np.pi, n))
+    tilt = quat_axis_angle(rng.normal(size=(n, 3)), rng.uniform(0, 0.2, n))
+    q = quat_mul(yaw, tilt)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    half = np.array([0.3, 0.9, 0.3])
+    bbox = np.concatenate([np.tile(-half, (n, 1)), np.tile(half, (n, 1))], 1)
+    return SynthTransforms(pos.astype(np.float32), q.astype(np.float32), s.astype(np.float32), bbox.astype(np.float32))

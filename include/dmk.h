@@ -168,6 +168,14 @@ DMK_API dmk_status dmk_crowd_update_layers(dmk_crowd_t crowd, int num_layers, co
  * character entity: world_inverse [N][16], bbox [N][6] = min.xyz, max.xyz (local space). */
 DMK_API dmk_status dmk_crowd_set_instances(dmk_crowd_t crowd, const float* world_inverse, const float* bbox);
 
+/* "Next" row: instead of precomputed world inverses, hand over what Transform holds --
+ * position, rotation (quaternion x, y, z, w) and scale of each parent-less entity -- and let the cull kernel run
+ * Transform::update itself (src/transform.cpp:286-309: glm::inverse(translate * mat4_cast * scale), glm operation
+ * order).  40 B/instance instead of 64 B, and no host loop over 10M transforms.  position [N][3], rotation [N][4],
+ * scale [N][3], bbox [N][6]. */
+DMK_API dmk_status dmk_crowd_set_transforms(dmk_crowd_t crowd, const float* position, const float* rotation, const float* scale,
+                                            const float* bbox);
+
 /* Camera::getViewProjectionMatrix (src/camera.cpp:196-199) -> Frustum{proj * view} (src/culling.cpp:268,
  * src/shape.cpp:1141-1163), computed on the host in glm operation order.  near_depth =
  * Math::getNormalizedNearDepth() (src/math.cpp:32-36): 0, or -1 with homogeneous depth. */
@@ -222,6 +230,11 @@ DMK_API dmk_status dmk_crowd_pack_visible_palettes(dmk_crowd_t crowd, float* out
 /* world_inverse_dev [n][16], bbox_dev [n][6] device pointers; vis_bits_dev ceil(n/32) words. */
 DMK_API dmk_status dmk_cull_dev(dmk_context_t ctx, const float* corners_host, const float* world_inverse_dev,
                                 const float* bbox_dev, int64_t n, uint32_t* vis_bits_dev);
+/* same, from position / rotation (x, y, z, w) / scale device arrays; world_inverse_out_dev (optional, [n][16]) receives
+ * the matrices Transform::getWorldInverse would return */
+DMK_API dmk_status dmk_cull_trs_dev(dmk_context_t ctx, const float* corners_host, const float* position_dev, const float* rotation_dev,
+                                    const float* scale_dev, const float* bbox_dev, int64_t n, uint32_t* vis_bits_dev,
+                                    float* world_inverse_out_dev);
 /* host-buffer form (copies in and out; used by the e2e measurement and the parity tests) */
 DMK_API dmk_status dmk_cull_host(dmk_context_t ctx, const float* view_proj, float near_depth, const float* world_inverse,
                                  const float* bbox, int64_t n, uint32_t* vis_bits);

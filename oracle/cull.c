@@ -160,3 +160,53 @@ int orc_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * "next" row: Transform::update (src/transform.cpp:286-309) for an entity without parent:
+ *   _localMatrix  = Math::transform(position, rotation, scale) = glm::translate(p) * glm::mat4_cast(q) * glm::scale(s)
+ *   _localInverse = glm::inverse(_localMatrix);   _worldInverse = _localInverse
+ * in glm's operation order (mat3_cast of glm/gtc/quaternion.inl; products as orc_mat4_mul; inverse as orc_mat4_inverse).
+ * rotation is (x, y, z, w).
+ * ---------------------------------------------------------------------------------------------- */
+void orc_transform_local_matrix(const float* p, const float* q, const float* s, float* out) {
+    const float qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+    const float qxx = qx * qx, qyy = qy * qy, qzz = qz * qz, qxz = qx * qz, qxy = qx * qy, qyz = qy * qz;
+    const float qwx = qw * qx, qwy = qw * qy, qwz = qw * qz;
+    float r[16] = {0}, t[16] = {0}, sc[16] = {0}, tr[16];
+    r[0] = 1.f - 2.f * (qyy + qzz); r[1] = 2.f * (qxy + qwz);       r[2] = 2.f * (qxz - qwy);
+    r[4] = 2.f * (qxy - qwz);       r[5] = 1.f - 2.f * (qxx + qzz); r[6] = 2.f * (qyz + qwx);
+    r[8] = 2.f * (qxz + qwy);       r[9] = 2.f * (qyz - qwx);       r[10] = 1.f - 2.f * (qxx + qyy);
+    r[15] = 1.f;
+    t[0] = t[5] = t[10] = t[15] = 1.f;
+    t[12] = p[0]; t[13] = p[1]; t[14] = p[2];
+    sc[0] = s[0]; sc[5] = s[1]; sc[10] = s[2]; sc[15] = 1.f;
+    orc_mat4_mul(t, r, tr);
+    orc_mat4_mul(tr, sc, out);
+}
+
+void orc_transform_world_inverse(const float* p, const float* q, const float* s, float* out) {
+    float local[16];
+    orc_transform_local_matrix(p, q, s, local);
+    orc_mat4_inverse(local, out);
+}
+
+void orc_cull_batch_trs(const float* corners, const float* position, const float* rotation, const float* scale,
+                        const float* bbox, int64_t n, uint32_t* vis_bits, float* world_inverse_out, int num_threads) {
+    const int64_t words = (n + 31) / 32;
+    if (num_threads < 1) num_threads = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(num_threads)
+#endif
+    for (int64_t w = 0; w < words; ++w) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int64_t i = w * 32 + b;
+            if (i >= n) break;
+            float wi[16];
+            orc_transform_world_inverse(position + i * 3, rotation + i * 4, scale + i * 3, wi);
+            if (world_inverse_out) memcpy(world_inverse_out + i * 16, wi, sizeof wi);
+            if (orc_cull_visible(corners, wi, bbox + i * 6)) bits |= (1u << b);
+        }
+        vis_bits[w] = bits;
+    }
+}

@@ -142,6 +142,12 @@ int orc_cull_visible(const float* corners, const float* world_inverse, const flo
 void orc_cull_batch(const float* corners, const float* world_inverse, const float* bbox, int64_t n,
                     uint32_t* vis_bits, int num_threads);
 
+/* "next" row 8(f)-1: Transform::update (src/transform.cpp:286-309) without parent, then the cull on its world inverse */
+void orc_transform_local_matrix(const float* position, const float* rotation_xyzw, const float* scale, float* out16);
+void orc_transform_world_inverse(const float* position, const float* rotation_xyzw, const float* scale, float* out16);
+void orc_cull_batch_trs(const float* corners, const float* position, const float* rotation, const float* scale,
+                        const float* bbox, int64_t n, uint32_t* vis_bits, float* world_inverse_out, int num_threads);
+
 /* ---- clip clock (OzzSkeletalAnimatorAnimationState::update, src/skeleton_ozz.cpp:411-440) ----
  * Returns 1 when the clip is to be re-sampled this tick, 0 when it holds (finished, non looping). */
 int orc_clip_clock(float* normalized_time, int* looped, float dt, float clip_duration, float speed, int loop);

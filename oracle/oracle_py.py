@@ -73,6 +73,9 @@ def lib():
         L.orc_cull_visible.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_cull_visible.restype = C.c_int
         L.orc_cull_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+        L.orc_transform_world_inverse.argtypes = [C.c_void_p] * 4
+        L.orc_transform_local_matrix.argtypes = [C.c_void_p] * 4
+        L.orc_cull_batch_trs.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_clip_clock.argtypes = [c_float_p, c_i32_p, C.c_float, C.c_float, C.c_float, C.c_int]
         L.orc_clip_clock.restype = C.c_int
         L.orc_crowd_create.restype = C.c_void_p
@@ -259,6 +262,29 @@ def cull_batch(corners, world_inverse, bbox, num_threads=None):
     bits = np.zeros((n + 31) // 32, np.uint32)
     lib().orc_cull_batch(_p(c), _p(w), _p(b), n, _p(bits), num_threads or max_threads())
     return bits
+
+
+def transform_world_inverse(position, rotation, scale):
+    p, q, s = _f32(position), _f32(rotation), _f32(scale)
+    out = np.zeros(16, np.float32)
+    lib().orc_transform_world_inverse(_p(p), _p(q), _p(s), _p(out))
+    return out
+
+
+def transform_local_matrix(position, rotation, scale):
+    p, q, s = _f32(position), _f32(rotation), _f32(scale)
+    out = np.zeros(16, np.float32)
+    lib().orc_transform_local_matrix(_p(p), _p(q), _p(s), _p(out))
+    return out
+
+
+def cull_batch_trs(corners, position, rotation, scale, bbox, num_threads=None, want_world_inverse=False):
+    c, p, q, s, b = (_f32(a) for a in (corners, position, rotation, scale, bbox))
+    n = p.shape[0]
+    bits = np.zeros((n + 31) // 32, np.uint32)
+    wi = np.zeros((n, 16), np.float32) if want_world_inverse else None
+    lib().orc_cull_batch_trs(_p(c), _p(p), _p(q), _p(s), _p(b), n, _p(bits), _p(wi), num_threads or max_threads())
+    return (bits, wi) if want_world_inverse else bits
 
 
 def clip_clock(t, looped, dt, duration, speed, loop):

@@ -93,3 +93,47 @@ def test_crowd_cull_and_visible_id_compaction(assets):
         assert np.array_equal(out.cpu().numpy(), pal[np.nonzero(vis)[0]])
     finally:
         g.close()
+
+
+def test_transform_update_on_device_world_inverse_and_visibility():
+    # Transform::update (src/transform.cpp:286-309) fused into the cull: world inverse from
+    # position / rotation / scale in glm order, visibility bit-exact, matrices identical to the oracle's
+    import torch
+    n = 200_003
+    tr = synth.make_transforms(n, seed=9, extent=150.0)
+    vp = synth.sample_camera_view_proj()
+    corners = O.frustum_corners(vp, 0.0)
+    ref_bits, ref_wi = O.cull_batch_trs(corners, tr.position, tr.rotation, tr.scale, tr.bbox, want_world_inverse=True)
+    c = capi.Context(0)
+    try:
+        dev = [torch.from_numpy(a).cuda() for a in (tr.position, tr.rotation, tr.scale, tr.bbox)]
+        bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+        wi = torch.zeros((n, 16), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        c.cull_trs_dev(corners, *[d.data_ptr() for d in dev], n, bits.data_ptr(), wi.data_ptr())
+        c.sync()
+        assert np.array_equal(bits.cpu().numpy().view(np.uint32), ref_bits)
+        assert np.array_equal(wi.cpu().numpy(), ref_wi)       # same operation order, no contraction: identical matrices
+        vis = capi.bits_to_bool(ref_bits, n)
+        assert 0 < vis.sum() < n
+    finally:
+        c.close()
+
+
+def test_crowd_cull_from_transforms(assets):
+    g = GpuRig(assets, with_mesh=False)
+    try:
+        n = 5000
+        tr = synth.make_transforms(n, seed=3, extent=40.0)
+        cr = synth.make_crowd(n, 1, len(assets.clips), seed=2)
+        crowd = g.crowd(n, 1, mesh=False)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight)
+        crowd.set_transforms(tr.position, tr.rotation, tr.scale, tr.bbox)
+        vp = synth.sample_camera_view_proj()
+        crowd.set_camera(vp, 0.0)
+        crowd.step(0.0, capi.STEP_POSE | capi.STEP_CULL)
+        bits, count = crowd.get_visibility()
+        ref = O.cull_batch_trs(O.frustum_corners(vp, 0.0), tr.position, tr.rotation, tr.scale, tr.bbox)
+        assert np.array_equal(bits, ref) and 0 < count < n
+    finally:
+        g.close()

@@ -67,3 +67,21 @@ def test_batch_equals_scalar_and_has_both_outcomes():
     one = np.array([O.cull_visible(corners, inst.world_inverse[i], inst.bbox[i]) for i in range(4000)])
     assert np.array_equal(vis, one)
     assert 0 < vis.sum() < 4000
+
+
+def test_transform_update_world_inverse():
+    # Transform::update (src/transform.cpp:286-309) without parent: inverse(translate * mat4_cast * scale)
+    tr = synth.make_transforms(50, seed=1)
+    for i in range(50):
+        local = O.transform_local_matrix(tr.position[i], tr.rotation[i], tr.scale[i]).reshape(4, 4).T.astype(np.float64)
+        x, y, z, w = tr.rotation[i].astype(np.float64)
+        r = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert np.allclose(local[:3, :3], r * tr.scale[i][None, :], atol=1e-6)
+        assert np.array_equal(local[:3, 3].astype(np.float32), tr.position[i]) and np.array_equal(local[3], [0, 0, 0, 1])
+        wi = O.transform_world_inverse(tr.position[i], tr.rotation[i], tr.scale[i]).reshape(4, 4).T.astype(np.float64)
+        assert np.allclose(wi @ local, np.eye(4), atol=5e-3)   # float32 inverse, positions up to 500
+    # identity transform: exact identity
+    ident = O.transform_world_inverse([0, 0, 0], [0, 0, 0, 1], [1, 1, 1])
+    assert np.array_equal(ident, np.eye(4, dtype=np.float32).reshape(16))
