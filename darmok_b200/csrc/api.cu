@@ -106,8 +106,11 @@ struct dmk_crowd_s {
     PoseProgram* d_program = nullptr;  // [n], allocated by dmk_crowd_set_programs
     bool use_program = false;
     // pinned staging for the per-frame host state machine
-    void* h_stage = nullptr;
-    size_t h_stage_bytes = 0;
+    // two pinned staging buffers used alternately: the host may fill one while the copies out of the other are in flight
+    void* h_stage[2] = {nullptr, nullptr};
+    size_t h_stage_bytes[2] = {0, 0};
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    int stage_next = 0;
     // results
     float *d_palette = nullptr, *d_palette34 = nullptr, *d_skinned = nullptr;
     float *d_models = nullptr, *d_locals = nullptr;
@@ -692,7 +695,10 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
                     (void*)c->d_key_indices, (void*)c->d_error, (void*)c->d_world_inverse, (void*)c->d_bbox, (void*)c->d_position, (void*)c->d_rotation, (void*)c->d_scale, (void*)c->d_vis_bits,
                     (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch})
         dev_free(p);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (int b = 0; b < 2; ++b) {
+        if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]);
+        if (c->stage_done[b]) cudaEventDestroy(c->stage_done[b]);
+    }
     if (c->h_error) cudaFreeHost(c->h_error);
     delete c;
 }
@@ -718,16 +724,25 @@ dmk_status dmk_crowd_enable_outputs(dmk_crowd_t c, uint32_t outputs) {
     return DMK_OK;
 }
 
-static dmk_status ensure_stage(dmk_crowd_t c, size_t bytes) {
-    if (c->h_stage_bytes >= bytes) return DMK_OK;
-    if (c->h_stage) {
-        cudaStreamSynchronize(c->ctx->stream);
-        cudaFreeHost(c->h_stage);
-        c->h_stage = nullptr;
-        c->h_stage_bytes = 0;
+// Returns a pinned staging buffer of at least `bytes` that no in-flight copy is reading; stage_release() must be
+// called after the copies out of it have been enqueued.
+static dmk_status stage_acquire(dmk_crowd_t c, size_t bytes, char** out) {
+    const int b = c->stage_next;
+    if (c->stage_done[b]) DMK_CUDA(c->ctx, cudaEventSynchronize(c->stage_done[b]));
+    else DMK_CUDA(c->ctx, cudaEventCreateWithFlags(&c->stage_done[b], cudaEventDisableTiming));
+    if (c->h_stage_bytes[b] < bytes) {
+        if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]);
+        c->h_stage[b] = nullptr;
+        c->h_stage_bytes[b] = 0;
+        DMK_CUDA(c->ctx, cudaHostAlloc(&c->h_stage[b], bytes, cudaHostAllocDefault));
+        c->h_stage_bytes[b] = bytes;
     }
-    DMK_CUDA(c->ctx, cudaHostAlloc(&c->h_stage, bytes, cudaHostAllocDefault));
-    c->h_stage_bytes = bytes;
+    *out = static_cast<char*>(c->h_stage[b]);
+    return DMK_OK;
+}
+static dmk_status stage_release(dmk_crowd_t c) {
+    DMK_CUDA(c->ctx, cudaEventRecord(c->stage_done[c->stage_next], c->ctx->stream));
+    c->stage_next ^= 1;
     return DMK_OK;
 }
 
@@ -792,9 +807,8 @@ dmk_status dmk_crowd_set_programs(dmk_crowd_t c, int num_layers, const int32_t* 
     }
     if (!c->d_program) DMK_CUDA(ctx, dev_alloc(&c->d_program, n));
     const size_t lbytes = static_cast<size_t>(num_layers) * n * 4, pbytes = n * sizeof(PoseProgram);
-    if (dmk_status st = ensure_stage(c, 3 * lbytes + pbytes)) return st;
-    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // previous copies out of the staging area have drained
-    char* h = static_cast<char*>(c->h_stage);
+    char* h = nullptr;
+    if (dmk_status st = stage_acquire(c, 3 * lbytes + pbytes, &h)) return st;
     std::memcpy(h, clip, lbytes);
     std::memcpy(h + lbytes, ratio, lbytes);
     std::memcpy(h + 2 * lbytes, weight, lbytes);
@@ -804,6 +818,7 @@ dmk_status dmk_crowd_set_programs(dmk_crowd_t c, int num_layers, const int32_t* 
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_ratio, h + lbytes, lbytes, cudaMemcpyHostToDevice, s));
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_weight, h + 2 * lbytes, lbytes, cudaMemcpyHostToDevice, s));
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_program, h + 3 * lbytes, pbytes, cudaMemcpyHostToDevice, s));
+    if (dmk_status st = stage_release(c)) return st;
     c->num_layers = num_layers;
     c->layers_set = true;
     c->use_program = true;
@@ -818,17 +833,15 @@ dmk_status dmk_crowd_update_layers(dmk_crowd_t c, int num_layers, const int32_t*
     if (!clip || !ratio || !weight) return fail(ctx, DMK_ERR_INVALID, "null layer array");
     if (bind(ctx)) return DMK_ERR_CUDA;
     const size_t bytes = static_cast<size_t>(num_layers) * static_cast<size_t>(c->n) * 4;
-    if (dmk_status st = ensure_stage(c, 3 * bytes)) return st;
-    // the previous frame's copies out of the staging area must have drained before it is overwritten
-    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    char* h = static_cast<char*>(c->h_stage);
+    char* h = nullptr;
+    if (dmk_status st = stage_acquire(c, 3 * bytes, &h)) return st;
     std::memcpy(h, clip, bytes);
     std::memcpy(h + bytes, ratio, bytes);
     std::memcpy(h + 2 * bytes, weight, bytes);
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_clip, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_ratio, h + bytes, bytes, cudaMemcpyHostToDevice, ctx->stream));
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_weight, h + 2 * bytes, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return DMK_OK;
+    return stage_release(c);
 }
 
 dmk_status dmk_crowd_set_instances(dmk_crowd_t c, const float* world_inverse, const float* bbox) {
