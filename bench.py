@@ -41,6 +41,7 @@ def workload_config(args):
                     "5k verts x 4 influences LBS positions+normals+tangents; + frustum cull and visible-palette gather",
         "characters_per_gpu": args.chars, "joints": 67, "layers": 2, "clips": args.clips, "vertices": args.verts,
         "influences": 4, "dt": DT,
+        "gather": "visible palettes -> rank 0 over NCCL send/recv on a side stream, overlapped with the skinning kernel (reserved SMs: %d)" % max(args.reserve_sms, 0),
         "l2": "inputs larger than L2: each step streams %.1f GB of skinned vertices per GPU (L2 = 126 MB)"
               % (args.chars * args.verts * 36 / 1e9),
     }
@@ -173,6 +174,8 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if args.reserve_sms > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.reserve_sms))   # the gather must fit the SMs left to it
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -207,16 +210,30 @@ def run_gpu(args):
         # the one exchange of the path: visible palettes to the render GPU (rank 0).  Fixed-capacity
         # slabs + a device-side count per rank: no host synchronisation inside the step.
         gatherer = None
+        comm_stream = None
         if world > 1:
             from darmok_b200.parallel import VisiblePaletteGather
             gatherer = VisiblePaletteGather(cap, ps, dev, dst=0)
+            if args.reserve_sms > 0:
+                # the gather runs on its own stream, on SMs the persistent skinning grid leaves free, concurrently with
+                # the skinning kernel (it only depends on pose + cull + pack)
+                crowd.set_option(capi.OPT_SKIN_RESERVED_SMS, args.reserve_sms)
+                comm_stream = torch.cuda.Stream(device=dev)
+                packed_ready = torch.cuda.Event()
 
         def step():
             crowd.step(DT, flags_pre)                       # clocks + pose + cull + compaction
             crowd.pack_visible_palettes(packed.data_ptr(), cap)
-            if gatherer is not None:
-                gatherer.gather(packed, vis_count)          # NCCL over NVLink, stream-ordered
+            if gatherer is not None and comm_stream is None:
+                gatherer.gather(packed, vis_count)          # NCCL over NVLink, stream-ordered, before the skinning
+            if comm_stream is not None:
+                packed_ready.record(stream)
             crowd.step(DT, capi.STEP_SKIN)                  # LBS of every vertex of every character
+            if comm_stream is not None:
+                comm_stream.wait_event(packed_ready)        # depends on the pack only; enqueued after the skin launch
+                with torch.cuda.stream(comm_stream):
+                    gatherer.gather(packed, vis_count)
+                stream.wait_stream(comm_stream)             # next frame's pack must not overwrite the slab in flight
 
         for _ in range(args.warmup):
             step()
@@ -386,8 +403,12 @@ def main():
     ap.add_argument("--verts", type=int, default=5000)
     ap.add_argument("--clips", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs left to the NCCL gather so that it overlaps the skinning")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.reserve_sms < 0:   # auto: the render GPU ingests (N - 1) slabs while it skins
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        args.reserve_sms = 0 if world <= 1 else min(8, 2 * (world - 1))
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

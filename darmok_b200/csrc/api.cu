@@ -709,6 +709,11 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
         c->force_search = value != 0;
         return DMK_OK;
     }
+    if (option == DMK_OPT_SKIN_RESERVED_SMS) {
+        if (value < 0 || value >= c->ctx->num_sms) return fail(c->ctx, DMK_ERR_INVALID, "reserved SM count out of range");
+        if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - value);
+        return DMK_OK;
+    }
     return fail(c->ctx, DMK_ERR_INVALID, "unknown option");
 }
 

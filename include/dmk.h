@@ -120,7 +120,12 @@ DMK_API void dmk_crowd_destroy(dmk_crowd_t crowd);
 DMK_API int64_t dmk_crowd_size(dmk_crowd_t crowd);
 /* Tuning / test switches.  DMK_OPT_FORCE_KEY_SEARCH: sample with the per-track binary search even when the clip
  * set carries the bucket table (both paths must give identical key indices). */
-enum { DMK_OPT_FORCE_KEY_SEARCH = 1 };
+enum {
+    DMK_OPT_FORCE_KEY_SEARCH = 1,
+    /* Leave `value` SMs out of the persistent skinning grid so that a collective enqueued on another stream (the
+     * visible-palette gather over NVLink) runs concurrently with the skinning kernel instead of after it. */
+    DMK_OPT_SKIN_RESERVED_SMS = 2
+};
 DMK_API dmk_status dmk_crowd_set_option(dmk_crowd_t crowd, int option, int value);
 
 /* Optional per-character outputs that only the host-side getters need (they cost HBM writes per step):
