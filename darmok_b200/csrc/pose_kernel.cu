@@ -22,7 +22,7 @@ namespace dmk {
 
 namespace {
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 4;   // maximum; skeletons with many joints run fewer warps per block (shared memory)
 constexpr int kMS = 13;  // shared-memory stride of a 3x4 matrix in floats: odd, so lanes on consecutive joints hit distinct banks
 
 __device__ __forceinline__ void st_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
@@ -318,9 +318,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
 
     const int L = p.num_layers;
     const int64_t n = p.n;
-    const int64_t warps_total = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * warps_per_block;
 
-    for (int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + warp; c < n; c += warps_total) {
+    for (int64_t c = (int64_t)blockIdx.x * warps_per_block + warp; c < n; c += warps_total) {
         // ---- pose program of this character (warp-uniform) ----
         PoseProgram prog;
         if (p.program) {
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
 
 }  // namespace
 
-size_t pose_smem_bytes(const PoseParams& p) {
+static size_t pose_smem_bytes_for(const PoseParams& p, int warps) {
     const int P = p.skel.padded_joints, K = p.arm.num_joints;
     size_t b = 0;
     b += (size_t)K * kMS * 4 + 16 * 4;
@@ -490,23 +491,27 @@ size_t pose_smem_bytes(const PoseParams& p) {
     b += (size_t)((P + 7) & ~7) * 2;
     b += (size_t)p.skel.rounds * 32 * 2;
     b += 16;
-    b += (size_t)((2 * P * kMS + 3) & ~3) * 4 * kWarpsPerBlock;
+    b += (size_t)((2 * P * kMS + 3) & ~3) * 4 * warps;
     return b;
 }
 
+size_t pose_smem_bytes(const PoseParams& p) { return pose_smem_bytes_for(p, kWarpsPerBlock); }
+
 cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    const size_t smem = pose_smem_bytes(p);
+    int warps = kWarpsPerBlock;
+    while (warps > 1 && pose_smem_bytes_for(p, warps) > 200 * 1024) warps >>= 1;
+    const size_t smem = pose_smem_bytes_for(p, warps);
     cudaError_t e = cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pose_kernel, kWarpsPerBlock * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pose_kernel, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    int64_t blocks = (p.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int64_t blocks = (p.n + warps - 1) / warps;
     const int64_t cap = (int64_t)num_sms * per_sm;
     if (blocks > cap) blocks = cap;
-    pose_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+    pose_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

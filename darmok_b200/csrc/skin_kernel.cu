@@ -264,6 +264,22 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
 
 }  // namespace
 
+namespace {
+constexpr size_t kMaxSmem = 227 * 1024;   // per-CTA shared memory limit on sm_100
+size_t skin_smem_bytes(int palette_size, int repl) {
+    return (size_t)palette_size * (48 * kNumRepl * repl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
+}
+template <typename F>
+auto with_kernel(int repl, F&& f) {
+    switch (repl) {
+    case 8: return f(skin_kernel<8>);
+    case 4: return f(skin_kernel<4>);
+    case 2: return f(skin_kernel<2>);
+    default: return f(skin_kernel<1>);
+    }
+}
+}  // namespace
+
 SkinPlan plan_skin(int vpad, int palette_size, int num_sms) {
     SkinPlan plan{};
     const int max_tile = kMaxThreads * kVPT;
@@ -272,12 +288,16 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms) {
     tv = (tv + kVPT - 1) / kVPT * kVPT;
     plan.tile_vertices = tv;
     plan.threads = ((tv / kVPT) + 31) / 32 * 32;
+    // 8 replicas make the gathers conflict free; palettes too large for that (> 181 slots) fall back to fewer replicas
     plan.replicas = kRepl;
-    plan.smem = (size_t)palette_size * (48 * kNumRepl * kRepl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
+    while (plan.replicas > 1 && skin_smem_bytes(palette_size, plan.replicas) > kMaxSmem) plan.replicas /= 2;
+    plan.smem = skin_smem_bytes(palette_size, plan.replicas);
     int occ = 1;
-    cudaFuncSetAttribute(skin_kernel<kRepl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skin_kernel<kRepl>, plan.threads, plan.smem) != cudaSuccess || occ < 1)
-        occ = 1;
+    with_kernel(plan.replicas, [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, plan.threads, plan.smem) != cudaSuccess || occ < 1) occ = 1;
+        return 0;
+    });
     int grid = num_sms * occ;
     const int tpp = plan.num_tiles < grid ? plan.num_tiles : grid;
     grid = grid / tpp * tpp;
@@ -287,10 +307,12 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms) {
 
 cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t stream) {
     if (p.n <= 0 || p.vpad <= 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(skin_kernel<kRepl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-    if (e != cudaSuccess) return e;
-    skin_kernel<kRepl><<<plan.grid, plan.threads, plan.smem, stream>>>(p);
-    return cudaGetLastError();
+    return with_kernel(plan.replicas, [&](auto kernel) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
+        return cudaGetLastError();
+    });
 }
 
 }  // namespace dmk

@@ -176,6 +176,7 @@ def test_archive_errors_use_reference_strings(assets):
 def test_small_and_odd_skeletons():
     # joint counts around the SoA / warp boundaries, incl. a single joint and > 64 joints
     for joints in (1, 4, 5, 31, 32, 33, 100):
+
         skel = synth.make_skeleton(joints, seed=joints)
         clips = [synth.make_clip(skel, "c", seed=joints, duration=0.7)]
         arm = synth.make_armature(skel, seed=joints)
@@ -310,3 +311,27 @@ def test_pose_program_validation(rigs):
     prog["threshold0"], prog["n0"], prog["n1"] = 1.0, 3, 3      # more layers than the crowd holds
     with pytest.raises(capi.DmkError):
         crowd.set_programs(clip, z, z, prog)
+
+
+@pytest.mark.parametrize("joints", [600, 1024])
+def test_max_joint_skeleton_models(joints):
+    # ozz allows 1024 joints: fewer warps per block (shared memory), no armature (palettes are capped at 256 slots)
+    skel = synth.make_skeleton(joints, seed=joints, max_depth=40)
+    clips = [synth.make_clip(skel, "c", seed=joints, duration=0.5, hz=10.0)]
+    a = common.Assets(skel, clips, synth.make_armature(synth.make_skeleton(4)), synth.make_mesh(8, 4))
+    g = GpuRig(a, with_mesh=False, with_armature=False)
+    try:
+        n = 9
+        cr = synth.make_crowd(n, 2, 1, seed=joints)
+        crowd = g.crowd(n, 2, mesh=False)
+        crowd.enable_outputs(g.capi.OUT_MODELS)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, threshold=FLT_MIN)
+        crowd.step(0.0, g.capi.STEP_POSE)
+        from oracle import oracle_py as O
+        oskel, oclip = O.Skeleton(skel.archive), O.Animation(clips[0].archive)
+        ref = O.Crowd(oskel, [oclip], np.zeros(0, np.int32), np.zeros((0, 16), np.float32), n, 2).step(
+            cr.clip, cr.ratio, cr.weight, FLT_MIN, want=("models",))["models"]
+        flipped = np.stack([[O.flip_handedness(m) for m in ch] for ch in ref])
+        assert_close(crowd.get_models(), flipped, f"models J={joints}")
+    finally:
+        g.close()

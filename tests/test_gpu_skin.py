@@ -104,3 +104,13 @@ def test_skin_visible_only_leaves_culled_characters_untouched(assets):
         assert np.array_equal(after[~vis], before[~vis])
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("joints", [200, 255])
+def test_large_palettes_fall_back_to_fewer_replicas(joints):
+    # 8 replicas of a 201/256-slot palette do not fit shared memory: the kernel runs with 4 / 2 replicas
+    skel = synth.make_skeleton(joints, seed=joints, max_depth=20)
+    clips = [synth.make_clip(skel, "c", seed=1, duration=0.5)]
+    a = common.Assets(skel, clips, synth.make_armature(skel, seed=1), synth.make_mesh(700, joints, seed=2))
+    got, ref, _, _ = _run(a, 6, layers=1, seed=3)
+    assert_close(got, ref, f"skinned with {joints + 1} palette slots")
