@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdarmok_b200.so")
 
 OK, ERR_INVALID, ERR_FORMAT, ERR_CUDA, ERR_UNSUPPORTED, ERR_JOB = range(6)
-STEP_ADVANCE, STEP_POSE, STEP_CULL, STEP_SKIN, STEP_SKIN_VISIBLE_ONLY = 1, 2, 4, 8, 16
+STEP_ADVANCE, STEP_POSE, STEP_CULL, STEP_SKIN, STEP_SKIN_VISIBLE_ONLY, STEP_READBACK_VISIBILITY = 1, 2, 4, 8, 16, 32
 STEP_ALL = 15
 OUT_MODELS, OUT_LOCALS, OUT_KEY_INDICES = 1, 2, 4
 OPT_FORCE_KEY_SEARCH = 1
@@ -82,6 +82,7 @@ SIGNATURES = [
     ("dmk_crowd_get_key_indices", _i, [_vp, _i64, _i64, _vp]),
     ("dmk_crowd_get_skinned", _i, [_vp, _i64, _i64, _vp]),
     ("dmk_crowd_get_visibility", _i, [_vp, _vp, C.POINTER(_i64)]),
+    ("dmk_crowd_collect_visibility", _i, [_vp, _vp, C.POINTER(_i64)]),
     ("dmk_crowd_get_ratios", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_pack_visible_palettes", _i, [_vp, _vp, _i64]),
     ("dmk_cull_dev", _i, [_vp, _vp, _vp, _vp, _i64, _vp]),
@@ -353,6 +354,12 @@ class Crowd:
         bits = np.zeros((self.n + 31) // 32, np.uint32)
         cnt = C.c_int64()
         self.ctx.check(lib().dmk_crowd_get_visibility(self.h, _ptr(bits), C.byref(cnt)))
+        return bits, cnt.value
+
+    def collect_visibility(self, bits=None):
+        bits = np.zeros((self.n + 31) // 32, np.uint32) if bits is None else bits
+        cnt = C.c_int64()
+        self.ctx.check(lib().dmk_crowd_collect_visibility(self.h, _ptr(bits), C.byref(cnt)))
         return bits, cnt.value
 
     def get_ratios(self):

@@ -123,6 +123,10 @@ struct dmk_crowd_s {
     bool use_trs = false;
     uint32_t* d_vis_bits = nullptr;
     int32_t *d_visible_ids = nullptr, *d_visible_count = nullptr, *d_scratch = nullptr;
+    // pinned ring for DMK_STEP_READBACK_VISIBILITY: [words] bits + 1 count, two frames deep
+    uint32_t* h_vis[2] = {nullptr, nullptr};
+    cudaEvent_t vis_ready[2] = {nullptr, nullptr};
+    int vis_head = 0, vis_pending = 0;
     float corners[24] = {0};
     bool culled_once = false;
     bool force_search = false;  // tests: exercise the per-track binary search even when a bucket table exists
@@ -696,6 +700,8 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
                     (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch})
         dev_free(p);
     for (int b = 0; b < 2; ++b) {
+        if (c->h_vis[b]) cudaFreeHost(c->h_vis[b]);
+        if (c->vis_ready[b]) cudaEventDestroy(c->vis_ready[b]);
         if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]);
         if (c->stage_done[b]) cudaEventDestroy(c->stage_done[b]);
     }
@@ -995,6 +1001,19 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         ++ctx->launches;
         ctx->launches += extra;
         c->culled_once = true;
+        if (flags & DMK_STEP_READBACK_VISIBILITY) {
+            if (c->vis_pending == 2) return fail(ctx, DMK_ERR_INVALID, "two visibility read-backs are already outstanding: collect one first");
+            const int b = (c->vis_head + c->vis_pending) & 1;
+            const size_t words = static_cast<size_t>((c->n + 31) / 32);
+            for (int k = 0; k < 2 && !c->h_vis[1]; ++k) {   // both ring slots at first use: pinned allocation synchronises
+                DMK_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&c->h_vis[k]), (words + 1) * 4, cudaHostAllocDefault));
+                DMK_CUDA(ctx, cudaEventCreateWithFlags(&c->vis_ready[k], cudaEventDisableTiming));
+            }
+            DMK_CUDA(ctx, cudaMemcpyAsync(c->h_vis[b], c->d_vis_bits, words * 4, cudaMemcpyDeviceToHost, s));
+            DMK_CUDA(ctx, cudaMemcpyAsync(c->h_vis[b] + words, c->d_visible_count, 4, cudaMemcpyDeviceToHost, s));
+            DMK_CUDA(ctx, cudaEventRecord(c->vis_ready[b], s));
+            ++c->vis_pending;
+        }
     }
     if (flags & DMK_STEP_SKIN) {
         if (!c->mesh || !c->arm) return fail(ctx, DMK_ERR_INVALID, "skinning needs a mesh and an armature");
@@ -1094,6 +1113,19 @@ dmk_status dmk_crowd_get_visibility(dmk_crowd_t c, uint32_t* out_bits, int64_t* 
     DMK_CUDA(c->ctx, cudaMemcpyAsync(&count, c->d_visible_count, 4, cudaMemcpyDeviceToHost, c->ctx->stream));
     if (dmk_status st = finish_and_check(c)) return st;
     if (out_visible_count) *out_visible_count = count;
+    return DMK_OK;
+}
+dmk_status dmk_crowd_collect_visibility(dmk_crowd_t c, uint32_t* out_bits, int64_t* out_visible_count) {
+    if (!c) return DMK_ERR_INVALID;
+    if (c->vis_pending == 0) return fail(c->ctx, DMK_ERR_INVALID, "no step with DMK_STEP_READBACK_VISIBILITY is outstanding");
+    if (bind(c->ctx)) return DMK_ERR_CUDA;
+    const int b = c->vis_head;
+    DMK_CUDA(c->ctx, cudaEventSynchronize(c->vis_ready[b]));
+    const size_t words = static_cast<size_t>((c->n + 31) / 32);
+    if (out_bits) std::memcpy(out_bits, c->h_vis[b], words * 4);
+    if (out_visible_count) *out_visible_count = static_cast<int32_t>(c->h_vis[b][words]);
+    c->vis_head ^= 1;
+    --c->vis_pending;
     return DMK_OK;
 }
 dmk_status dmk_crowd_get_ratios(dmk_crowd_t c, float* out_ratio, uint8_t* out_looped) {

@@ -194,6 +194,8 @@ enum {
     DMK_STEP_CULL = 4,      /* FrustumCuller::updateCulled (src/culling.cpp:264-285) */
     DMK_STEP_SKIN = 8,      /* applySkinning for every vertex (darmok_skinning.inc.slang:5-28) */
     DMK_STEP_SKIN_VISIBLE_ONLY = 16, /* with CULL+SKIN: skin only characters FrustumCuller would not cull */
+    DMK_STEP_READBACK_VISIBILITY = 32, /* with CULL: also enqueue the D2H copy of the bitmask + count into pinned memory,
+                                         * right behind the cull (collect it with dmk_crowd_collect_visibility) */
     DMK_STEP_ALL = 1 | 2 | 4 | 8
 };
 /* One frame for the whole crowd: replaces the per-entity loops SkeletalAnimationSceneComponent::update
@@ -223,6 +225,10 @@ DMK_API dmk_status dmk_crowd_get_locals(dmk_crowd_t crowd, int64_t first, int64_
 DMK_API dmk_status dmk_crowd_get_key_indices(dmk_crowd_t crowd, int64_t first, int64_t count, int32_t* out);
 DMK_API dmk_status dmk_crowd_get_skinned(dmk_crowd_t crowd, int64_t first, int64_t count, float* out); /* [count][V][9] */
 DMK_API dmk_status dmk_crowd_get_visibility(dmk_crowd_t crowd, uint32_t* out_bits, int64_t* out_visible_count);
+/* Pipelined frame loops: result of the OLDEST step issued with DMK_STEP_READBACK_VISIBILITY that has not been collected
+ * yet (at most two may be outstanding).  Waits only for that step's cull + copy, not for work enqueued after it, so the
+ * next frame can already be running: FrustumCuller's set for frame k is read while frame k + 1 executes. */
+DMK_API dmk_status dmk_crowd_collect_visibility(dmk_crowd_t crowd, uint32_t* out_bits, int64_t* out_visible_count);
 /* current clip clocks after ADVANCE: [num_layers][N] */
 DMK_API dmk_status dmk_crowd_get_ratios(dmk_crowd_t crowd, float* out_ratio, uint8_t* out_looped);
 

@@ -137,3 +137,32 @@ def test_crowd_cull_from_transforms(assets):
         assert np.array_equal(bits, ref) and 0 < count < n
     finally:
         g.close()
+
+
+def test_pipelined_visibility_readback(assets):
+    # two frames in flight: the result of frame k is collected after frame k + 1 has been submitted
+    g = GpuRig(assets, with_mesh=False)
+    try:
+        n = 3000
+        cr = synth.make_crowd(n, 1, len(assets.clips), seed=2)
+        crowd = g.crowd(n, 1, mesh=False)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight)
+        vp = synth.sample_camera_view_proj()
+        crowd.set_camera(vp, 0.0)
+        corners = O.frustum_corners(vp, 0.0)
+        frames = [synth.make_instances(n, seed=s, extent=30.0 + 10 * s) for s in range(4)]
+        flags = capi.STEP_POSE | capi.STEP_CULL | capi.STEP_READBACK_VISIBILITY
+        crowd.set_instances(frames[0].world_inverse, frames[0].bbox)
+        crowd.step(0.0, flags)
+        for k in range(1, 4):
+            crowd.set_instances(frames[k].world_inverse, frames[k].bbox)
+            crowd.step(0.0, flags)                                    # frame k submitted ...
+            bits, count = crowd.collect_visibility()                  # ... then frame k - 1 collected
+            ref = O.cull_batch(corners, frames[k - 1].world_inverse, frames[k - 1].bbox)
+            assert np.array_equal(bits, ref) and count == capi.bits_to_bool(ref, n).sum()
+        bits, _ = crowd.collect_visibility()
+        assert np.array_equal(bits, O.cull_batch(corners, frames[3].world_inverse, frames[3].bbox))
+        with pytest.raises(capi.DmkError):
+            crowd.collect_visibility()
+    finally:
+        g.close()
