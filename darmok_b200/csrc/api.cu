@@ -114,6 +114,7 @@ struct dmk_crowd_s {
     // results
     float *d_palette = nullptr, *d_palette34 = nullptr, *d_skinned = nullptr;
     float *d_models = nullptr, *d_locals = nullptr;
+    float* d_local_matrices = nullptr;  // [n][P][16] sampling kernel -> model kernel
     int32_t* d_key_indices = nullptr;
     int32_t* d_error = nullptr;
     int32_t* h_error = nullptr;  // pinned
@@ -667,6 +668,7 @@ dmk_status dmk_crowd_create(dmk_context_t ctx, dmk_skeleton_t skel, dmk_clipset_
     DMK_CUDA(ctx, dev_alloc(&c->d_speed, ln));
     DMK_CUDA(ctx, dev_alloc(&c->d_loop, ln));
     DMK_CUDA(ctx, dev_alloc(&c->d_looped, ln));
+    DMK_CUDA(ctx, dev_alloc(&c->d_local_matrices, static_cast<size_t>(n) * skel->data.num_soa() * 4 * 16));
     DMK_CUDA(ctx, dev_alloc(&c->d_error, 1));
     DMK_CUDA(ctx, cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), ctx->stream));
     DMK_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&c->h_error), sizeof(int32_t), cudaHostAllocDefault));
@@ -695,7 +697,7 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
     for (void* p : {(void*)c->d_clip, (void*)c->d_ratio, (void*)c->d_weight, (void*)c->d_speed, (void*)c->d_loop, (void*)c->d_looped,
-                    (void*)c->d_program, (void*)c->d_palette, (void*)c->d_palette34, (void*)c->d_skinned, (void*)c->d_models, (void*)c->d_locals,
+                    (void*)c->d_program, (void*)c->d_local_matrices, (void*)c->d_palette, (void*)c->d_palette34, (void*)c->d_skinned, (void*)c->d_models, (void*)c->d_locals,
                     (void*)c->d_key_indices, (void*)c->d_error, (void*)c->d_world_inverse, (void*)c->d_bbox, (void*)c->d_position, (void*)c->d_rotation, (void*)c->d_scale, (void*)c->d_vis_bits,
                     (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch})
         dev_free(p);
@@ -971,11 +973,13 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         p.locals = c->d_locals;
         p.key_indices = c->d_key_indices;
         p.error_flag = c->d_error;
+        p.scratch = c->d_local_matrices;
+        int pose_launches = 0;
         {
             KernelTimer timer(ctx, DMK_KERNEL_POSE);
-            DMK_CUDA(ctx, launch_pose(p, ctx->num_sms, s));
+            DMK_CUDA(ctx, launch_pose(p, ctx->num_sms, s, &pose_launches));
         }
-        ++ctx->launches;
+        ctx->launches += pose_launches;
     }
     if (flags & DMK_STEP_CULL) {
         if (!c->instances_set || !c->camera_set)

@@ -193,18 +193,20 @@ __device__ __forceinline__ void blend_first_pass(Xform& acc, const Xform& in, fl
     for (int k = 0; k < 3; ++k) acc.s[k] = in.s[k] * w;
 }
 
-// One group of layers [begin, begin + count) of a character, for joint jt.  Must be called by the whole warp: the layer
-// state (clip, ratio, weight) lives in lanes 0..L-1 and is broadcast with shuffles.
-__device__ __forceinline__ Xform eval_group(const ClipSetDev& cs, int my_clip, float my_ratio, float my_weight, int begin, int count,
-                                            int mode, int rest_idx, float threshold, int jt, int32_t* key_base, int P) {
+// One group of layers [begin, begin + count) of a character, for joint jt.  `layer(l, clip, ratio, weight)` yields the
+// resolved state of layer l (clip index validated, ratio clamped to [0, 1] as SamplingJob::Run does).
+template <typename LayerFn>
+__device__ __forceinline__ Xform eval_group(const ClipSetDev& cs, const LayerFn& layer, int begin, int count, int mode, int rest_idx,
+                                            float threshold, int jt, int32_t* key_base, int P) {
     Xform acc;
     if (mode == kGroupPassthrough) {
         // every clip of a state is sampled each tick (:538-545); only one of them is the pose
         for (int l = begin; l < begin + count; ++l) {
             const bool chosen = l == begin + rest_idx;
             if (!chosen && !key_base) continue;
-            const int cl = __shfl_sync(0xffffffffu, my_clip, l);
-            const float tl = __shfl_sync(0xffffffffu, my_ratio, l);
+            int cl;
+            float tl, wl;
+            layer(l, cl, tl, wl);
             Xform in;
             sample_joint(cs, cl, jt, tl, in, key_base ? key_base + (size_t)l * 3 * P * 2 : nullptr);
             if (chosen) acc = in;
@@ -215,7 +217,9 @@ __device__ __forceinline__ Xform eval_group(const ClipSetDev& cs, int my_clip, f
     float accumulated = 0.f;
     int num_passes = 0;
     for (int l = begin; l < begin + count; ++l) {
-        const float w = __shfl_sync(0xffffffffu, my_weight, l);
+        int cl;
+        float tl, w;
+        layer(l, cl, tl, w);
         if (!(w <= 0.f)) { accumulated += w; ++num_passes; }
     }
     const float bp_weight = threshold - accumulated;
@@ -227,9 +231,9 @@ __device__ __forceinline__ Xform eval_group(const ClipSetDev& cs, int my_clip, f
     int pass = 0;
 #pragma unroll 1
     for (int l = begin; l < begin + count; ++l) {
-        const float w = __shfl_sync(0xffffffffu, my_weight, l);
-        const int cl = __shfl_sync(0xffffffffu, my_clip, l);
-        const float tl = __shfl_sync(0xffffffffu, my_ratio, l);
+        int cl;
+        float tl, w;
+        layer(l, cl, tl, w);
         const bool contributes = !(w <= 0.f);
         const bool is_rest = need_rest && l == begin + rest_idx;
         if (!contributes && !is_rest && !key_base) continue;
@@ -292,7 +296,105 @@ __device__ __forceinline__ void from_affine(const Xform& x, float* m) {
     m[11] = x.t[2];
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PoseParams p) {
+__device__ __forceinline__ PoseProgram load_program(const PoseParams& p, int64_t c) {
+    PoseProgram prog;
+    if (p.program) {
+        prog = p.program[c];
+    } else {  // flat mode: one group; a state with a single clip never runs BlendingJob (:552-555, :617-624)
+        const int L = p.num_layers;
+        prog.n0 = (uint8_t)L; prog.n1 = 0; prog.rest0 = 0; prog.rest1 = 0;
+        prog.mode0 = L == 1 ? kGroupPassthrough : kGroupBlend; prog.mode1 = kGroupPassthrough;
+        prog.top = kTopGroup0; prog.reserved = 0;
+        prog.threshold0 = p.threshold; prog.threshold1 = p.threshold; prog.w0 = 1.f; prog.w1 = 0.f;
+    }
+    return prog;
+}
+
+// ---- K0: clip clocks, one thread per (layer, character) -----------------------------------------------------------
+// OzzSkeletalAnimatorAnimationState::update (src/skeleton_ozz.cpp:411-428)
+__global__ void __launch_bounds__(256) advance_kernel(const PoseParams p) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.n * p.num_layers) return;
+    const int ci = p.clip[idx];
+    if (ci < 0 || ci >= p.clips.num_clips) return;  // reported by the sampling kernel
+    const bool loop = p.loop ? p.loop[idx] != 0 : true;
+    bool looped = p.looped[idx] != 0;
+    if (looped && !loop) return;
+    float t = p.ratio[idx];
+    float sp = p.speed[idx];
+    sp = sp == 0.f ? 1.f : sp;
+    const float duration = __fdiv_rn(__ldg(p.clips.duration + ci), sp);
+    const float norm_time = t + __fdiv_rn(p.dt, duration);
+    looped = norm_time > 1.f;
+    if (!(looped && !loop)) t = fmodf(norm_time, 1.f);
+    p.looped[idx] = looped ? 1 : 0;
+    p.ratio[idx] = t;
+}
+
+// ---- K1: sample + blend, one thread per (character, joint) ----------------------------------------------------------
+// Flat mapping: every lane of every warp carries a joint (a 67-joint skeleton would waste a third of a
+// warp-per-character layout), small register footprint, many warps per SM to cover the L2 latency of the table reads.
+// Output: the joint's local 3x4 matrix (SoaFloat4x4::FromAffine), 16 floats per joint so that a thread writes two whole
+// sectors (256-bit stores); the model kernel reads them back coalesced.
+__global__ void __launch_bounds__(256) sample_kernel(const PoseParams p) {
+    const int P = p.skel.padded_joints;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= p.n * P) return;
+    const int64_t c = tid / P;
+    const int j = (int)(tid - c * P);
+    const PoseProgram prog = load_program(p, c);
+    if (prog.top == kTopSkip) return;  // no state: the animator keeps its previous matrices (:1029-1032)
+    const int64_t n = p.n;
+    const int L = p.num_layers;
+    bool bad = false;
+    auto layer = [&](int l, int& clip, float& ratio, float& weight) {
+        const int64_t idx = (int64_t)l * n + c;
+        int ci = __ldg(p.clip + idx);
+        if (ci < 0 || ci >= p.clips.num_clips) { bad = true; ci = 0; }
+        float t = p.ratio[idx];
+        t = (t < 1.f) ? t : 1.f;   // SamplingJob::Run clamps the ratio to [0, 1]
+        t = (t > 0.f) ? t : 0.f;
+        clip = ci;
+        ratio = t;
+        weight = __ldg(p.weight + idx);
+    };
+    int32_t* kb = p.key_indices ? p.key_indices + (size_t)c * L * 3 * P * 2 : nullptr;
+    Xform acc;
+    if (prog.top == kTopRestPose) {  // load-time pose: LocalToModelJob over joint_rest_poses (:901-916)
+        const float* r = p.skel.rest + (size_t)j * 10;
+        acc.t[0] = r[0]; acc.t[1] = r[1]; acc.t[2] = r[2];
+        acc.r[0] = r[3]; acc.r[1] = r[4]; acc.r[2] = r[5]; acc.r[3] = r[6];
+        acc.s[0] = r[7]; acc.s[1] = r[8]; acc.s[2] = r[9];
+    } else {
+        acc = eval_group(p.clips, layer, 0, prog.n0, prog.mode0, prog.rest0, prog.threshold0, j, kb, P);
+        if (prog.top == kTopTransition || (kb && prog.n1)) {
+            const Xform cur = eval_group(p.clips, layer, prog.n0, prog.n1, prog.mode1, prog.rest1, prog.threshold1, j, kb, P);
+            if (prog.top == kTopTransition)  // 2-layer BlendingJob, threshold bx::kFloatSmallest, rest = previous (:709-719)
+                acc = blend_two(acc, cur, prog.w0, prog.w1, 1.17549435e-38f);
+        }
+    }
+    if (bad && j == 0) atomicCAS(p.error_flag, 0, (int32_t)min(c + 1, (int64_t)0x7fffffff));
+    if (p.locals) {
+        float* o = p.locals + ((size_t)c * p.skel.num_soa + (j >> 2)) * kSoaFloats + (j & 3);
+        o[0] = acc.t[0]; o[4] = acc.t[1]; o[8] = acc.t[2];
+        o[12] = acc.r[0]; o[16] = acc.r[1]; o[20] = acc.r[2]; o[24] = acc.r[3];
+        o[28] = acc.s[0]; o[32] = acc.s[1]; o[36] = acc.s[2];
+    }
+    float m[12];
+    from_affine(acc, m);
+    float* out = p.scratch + (size_t)tid * 16;
+    st_v8(out, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
+    st_v8(out + 8, m[8], m[9], m[10], m[11], 0.f, 0.f, 0.f, 0.f);
+}
+
+__device__ __forceinline__ void ld_v8(const float* p, float* v) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
+// ---- K2 + K3: local-to-model and skin palette, one warp per character ------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) model_kernel(const PoseParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int J = p.skel.num_joints, P = p.skel.padded_joints, K = p.arm.num_joints, PS = K + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -316,92 +418,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) pose_kernel(const PosePar
     if (threadIdx.x < 12) s_identity[threadIdx.x] = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.f : 0.f;
     __syncthreads();
 
-    const int L = p.num_layers;
     const int64_t n = p.n;
     const int warps_per_block = blockDim.x >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * warps_per_block;
 
     for (int64_t c = (int64_t)blockIdx.x * warps_per_block + warp; c < n; c += warps_total) {
-        // ---- pose program of this character (warp-uniform) ----
-        PoseProgram prog;
-        if (p.program) {
-            prog = p.program[c];
-        } else {  // flat mode: one group; a state with a single clip never runs BlendingJob (:552-555, :617-624)
-            prog.n0 = (uint8_t)L; prog.n1 = 0; prog.rest0 = 0; prog.rest1 = 0;
-            prog.mode0 = L == 1 ? kGroupPassthrough : kGroupBlend; prog.mode1 = kGroupPassthrough;
-            prog.top = kTopGroup0; prog.reserved = 0;
-            prog.threshold0 = p.threshold; prog.threshold1 = p.threshold; prog.w0 = 1.f; prog.w1 = 0.f;
-        }
-        if (prog.top == kTopSkip) continue;  // no state: the animator keeps its previous matrices (:1029-1032)
+        if (p.program && p.program[c].top == kTopSkip) continue;
 
-        // ---- layer state + clip clock: lane l owns layer l, values are broadcast with shuffles ----
-        int my_clip = 0;
-        float my_ratio = 0.f, my_weight = 0.f;
-        bool my_bad = false;
-        const int used_layers = p.program ? prog.n0 + prog.n1 : L;
-        if (lane < used_layers) {
-            const int64_t idx = (int64_t)lane * n + c;
-            int ci = p.clip[idx];
-            float t = p.ratio[idx];
-            if (ci < 0 || ci >= p.clips.num_clips) { my_bad = true; ci = 0; }
-            if (p.advance) {
-                // OzzSkeletalAnimatorAnimationState::update (src/skeleton_ozz.cpp:411-428)
-                const bool loop = p.loop ? p.loop[idx] != 0 : true;
-                bool looped = p.looped[idx] != 0;
-                if (!(looped && !loop)) {
-                    float sp = p.speed[idx];
-                    sp = sp == 0.f ? 1.f : sp;
-                    const float duration = __fdiv_rn(__ldg(p.clips.duration + ci), sp);
-                    const float norm_time = t + __fdiv_rn(p.dt, duration);
-                    looped = norm_time > 1.f;
-                    if (!(looped && !loop)) t = fmodf(norm_time, 1.f);
-                    p.looped[idx] = looped ? 1 : 0;
-                    p.ratio[idx] = t;
-                }
-            }
-            // SamplingJob::Run: ratio clamped to [0, 1]
-            float tc = t;
-            tc = (tc < 1.f) ? tc : 1.f;
-            tc = (tc > 0.f) ? tc : 0.f;
-            my_clip = ci;
-            my_ratio = tc;
-            my_weight = p.weight[idx];
-        }
-        if (__any_sync(0xffffffffu, my_bad)) {
-            if (lane == 0) atomicCAS(p.error_flag, 0, (int32_t)min(c + 1, (int64_t)0x7fffffff));
-            continue;
-        }
-        int32_t* key_base = p.key_indices ? p.key_indices + (size_t)c * L * 3 * P * 2 : nullptr;
-
-        // ---- K1: sample + blend, lane <-> joint ----
-        for (int j0 = 0; j0 < P; j0 += 32) {
-            const int j = j0 + lane;
-            const bool active = j < P;   // all lanes stay in the loop: layer state is broadcast by shuffle
-            const int jt = active ? j : P - 1;
-            int32_t* kb = active ? key_base : nullptr;
-            Xform acc;
-            if (prog.top == kTopRestPose) {  // load-time pose: LocalToModelJob over joint_rest_poses (:901-916)
-                const float* r = p.skel.rest + (size_t)jt * 10;
-                acc.t[0] = r[0]; acc.t[1] = r[1]; acc.t[2] = r[2];
-                acc.r[0] = r[3]; acc.r[1] = r[4]; acc.r[2] = r[5]; acc.r[3] = r[6];
-                acc.s[0] = r[7]; acc.s[1] = r[8]; acc.s[2] = r[9];
-            } else {
-                acc = eval_group(p.clips, my_clip, my_ratio, my_weight, 0, prog.n0, prog.mode0, prog.rest0, prog.threshold0, jt, kb, P);
-                if (prog.top == kTopTransition || (kb && prog.n1)) {
-                    const Xform cur = eval_group(p.clips, my_clip, my_ratio, my_weight, prog.n0, prog.n1, prog.mode1, prog.rest1,
-                                                 prog.threshold1, jt, kb, P);
-                    if (prog.top == kTopTransition)  // 2-layer BlendingJob, threshold bx::kFloatSmallest, rest = previous (:709-719)
-                        acc = blend_two(acc, cur, prog.w0, prog.w1, 1.17549435e-38f);
-                }
-            }
-            if (!active) continue;
-            if (p.locals) {
-                float* o = p.locals + ((size_t)c * p.skel.num_soa + (j >> 2)) * kSoaFloats + (j & 3);
-                o[0] = acc.t[0]; o[4] = acc.t[1]; o[8] = acc.t[2];
-                o[12] = acc.r[0]; o[16] = acc.r[1]; o[20] = acc.r[2]; o[24] = acc.r[3];
-                o[28] = acc.s[0]; o[32] = acc.s[1]; o[36] = acc.s[2];
-            }
-            from_affine(acc, s_loc + (size_t)j * kMS);
+        // ---- local matrices written by the sampling kernel: coalesced 256-bit loads -> shared memory ----
+        for (int j = lane; j < J; j += 32) {
+            float v[16];
+            const float* src = p.scratch + ((size_t)c * P + j) * 16;
+            ld_v8(src, v);
+            ld_v8(src + 8, v + 8);
+            float* d = s_loc + (size_t)j * kMS;
+#pragma unroll
+            for (int e = 0; e < 12; ++e) d[e] = v[e];
         }
         __syncwarp();
 
@@ -497,21 +529,32 @@ static size_t pose_smem_bytes_for(const PoseParams& p, int warps) {
 
 size_t pose_smem_bytes(const PoseParams& p) { return pose_smem_bytes_for(p, kWarpsPerBlock); }
 
-cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream, int* launches) {
     if (p.n <= 0) return cudaSuccess;
+    if (p.advance) {
+        const int64_t total = p.n * p.num_layers;
+        advance_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+        if (launches) ++*launches;
+    }
+    {
+        const int64_t total = p.n * p.skel.padded_joints;
+        sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+        if (launches) ++*launches;
+    }
     int warps = kWarpsPerBlock;
     while (warps > 1 && pose_smem_bytes_for(p, warps) > 200 * 1024) warps >>= 1;
     const size_t smem = pose_smem_bytes_for(p, warps);
-    cudaError_t e = cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(model_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pose_kernel, warps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, model_kernel, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     int64_t blocks = (p.n + warps - 1) / warps;
     const int64_t cap = (int64_t)num_sms * per_sm;
     if (blocks > cap) blocks = cap;
-    pose_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(p);
+    model_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(p);
+    if (launches) ++*launches;
     return cudaGetLastError();
 }
 
