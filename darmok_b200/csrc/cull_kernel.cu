@@ -28,7 +28,7 @@ __device__ __forceinline__ V3 cross3(V3 x, V3 y) {
     return {x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y};
 }
 __device__ __forceinline__ V3 normalize3(V3 v) {
-    const float inv = __fdiv_rn(1.f, __fsqrt_rn(dot3(v, v)));
+    const float inv = __frcp_rn(__fsqrt_rn(dot3(v, v)));   // correctly rounded 1 / sqrt: glm::inversesqrt = 1 / sqrt(x)
     return {v.x * inv, v.y * inv, v.z * inv};
 }
 
@@ -83,7 +83,7 @@ __device__ __forceinline__ void world_inverse_from_trs(const float* __restrict__
         inv[3][k] = ((v0[k] * f2[k] - v1[k] * f4[k]) + v2[k] * f5[k]) * sb;
     }
     const float d0 = m[0][0] * inv[0][0], d1 = m[0][1] * inv[1][0], d2 = m[0][2] * inv[2][0], d3 = m[0][3] * inv[3][0];
-    const float ood = __fdiv_rn(1.f, (d0 + d1) + (d2 + d3));
+    const float ood = __frcp_rn((d0 + d1) + (d2 + d3));
     o0 = make_float4(inv[0][0] * ood, inv[0][1] * ood, inv[0][2] * ood, inv[0][3] * ood);
     o1 = make_float4(inv[1][0] * ood, inv[1][1] * ood, inv[1][2] * ood, inv[1][3] * ood);
     o2 = make_float4(inv[2][0] * ood, inv[2][1] * ood, inv[2][2] * ood, inv[2][3] * ood);

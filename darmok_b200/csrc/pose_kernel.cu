@@ -30,8 +30,9 @@ __device__ __forceinline__ void st_v8(float* p, float a, float b, float c, float
                  : "memory");
 }
 
-__device__ __forceinline__ float rcp_exact(float x) { return __fdiv_rn(1.f, x); }
-__device__ __forceinline__ float rsqrt_exact(float x) { return __fdiv_rn(1.f, __fsqrt_rn(x)); }
+// 1/x and 1/sqrt(x) of the scalar reference (simd_ref RcpEst / RSqrtEst): correctly rounded reciprocal == 1.f / x
+__device__ __forceinline__ float rcp_exact(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float rsqrt_exact(float x) { return __frcp_rn(__fsqrt_rn(x)); }
 
 // Stateless equivalent of ozz's sampling cursor: right = first key (index >= 1) of the
 // track with ratio > t, else the last key; left = right - 1.
@@ -62,7 +63,7 @@ __device__ __forceinline__ Bracket fetch_bracket(const ClipSetDev& cs, int comp,
         const int G = (int)bd.y;
         int b = (int)(t * (float)G);  // G is a power of two: exact
         b = b < G - 1 ? b : G - 1;
-        const size_t e = (size_t)bd.x + ((size_t)comp * G + b) * P + track;
+        const uint32_t e = bd.x + (uint32_t)((comp * G + b) * P + track);  // tables hold < 2^32 entries
         const float4 a = __ldg(cs.bucket_a + e);
         const uint4 vb = __ldg(cs.bucket_b + e);
         const uint2 vc = __ldg(cs.bucket_c + e);
