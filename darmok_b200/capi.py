@@ -55,6 +55,8 @@ SIGNATURES = [
     ("dmk_armature_destroy", None, [_vp]),
     ("dmk_armature_palette_size", _i, [_vp]),
     ("dmk_mesh_create", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
+    ("dmk_mesh_create_ex", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u32, C.POINTER(_vp)]),
+    ("dmk_mesh_vertex_order", _i, [_vp, _vp]),
     ("dmk_mesh_destroy", None, [_vp]),
     ("dmk_mesh_num_vertices", _i, [_vp]),
     ("dmk_mesh_vertex_pitch", _i, [_vp]),
@@ -254,14 +256,19 @@ class Armature:
             self.h = None
 
 
+MESH_SORT_BY_INFLUENCES = 1
+
+
 class Mesh:
-    def __init__(self, ctx: Context, pos, nrm, tan, indices, weights, palette_size):
+    def __init__(self, ctx: Context, pos, nrm, tan, indices, weights, palette_size, flags=0):
         self.ctx = ctx
         pos, nrm, tan, indices, weights = (_f32(a) for a in (pos, nrm, tan, indices, weights))
         h = C.c_void_p()
-        ctx.check(lib().dmk_mesh_create(ctx.h, _ptr(pos), _ptr(nrm), _ptr(tan), _ptr(indices), _ptr(weights), pos.shape[0],
-                                        palette_size, C.byref(h)))
+        ctx.check(lib().dmk_mesh_create_ex(ctx.h, _ptr(pos), _ptr(nrm), _ptr(tan), _ptr(indices), _ptr(weights), pos.shape[0],
+                                           palette_size, flags, C.byref(h)))
         self.h = h
+        self.order = np.zeros(pos.shape[0], np.int32)
+        ctx.check(lib().dmk_mesh_vertex_order(h, _ptr(self.order)))
         self.num_vertices = lib().dmk_mesh_num_vertices(h)
         self.vertex_pitch = lib().dmk_mesh_vertex_pitch(h)
 

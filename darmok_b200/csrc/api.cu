@@ -86,6 +86,8 @@ struct dmk_mesh_s {
     int palette_size = 0;
     float *d_pos = nullptr, *d_nrm = nullptr, *d_tan = nullptr, *d_weights = nullptr;
     uint32_t* d_slots = nullptr;
+    std::vector<int32_t> order;  // order[i] = caller's index of the vertex stored at position i
+    bool sorted = false;
 };
 
 struct dmk_crowd_s {
@@ -583,6 +585,17 @@ int dmk_armature_palette_size(dmk_armature_t arm) { return arm ? arm->num_joints
 
 dmk_status dmk_mesh_create(dmk_context_t ctx, const float* position, const float* normal, const float* tangent, const float* indices,
                            const float* weights, int num_vertices, int palette_size, dmk_mesh_t* out) {
+    return dmk_mesh_create_ex(ctx, position, normal, tangent, indices, weights, num_vertices, palette_size, 0, out);
+}
+
+dmk_status dmk_mesh_vertex_order(dmk_mesh_t mesh, int32_t* out_order) {
+    if (!mesh || !out_order) return DMK_ERR_INVALID;
+    std::copy(mesh->order.begin(), mesh->order.end(), out_order);
+    return DMK_OK;
+}
+
+dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const float* normal, const float* tangent, const float* indices,
+                              const float* weights, int num_vertices, int palette_size, uint32_t flags, dmk_mesh_t* out) {
     if (!ctx || !out || num_vertices < 0 || (num_vertices > 0 && (!position || !normal || !tangent || !indices || !weights)))
         return fail(ctx, DMK_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -597,13 +610,43 @@ dmk_status dmk_mesh_create(dmk_context_t ctx, const float* position, const float
     std::vector<float> pos(static_cast<size_t>(vpad) * 3, 0.f), nrm(pos.size(), 0.f), tan(pos.size(), 0.f);
     std::vector<float> w(static_cast<size_t>(vpad) * 4, 0.f);
     std::vector<uint32_t> slots(vpad, 0u);
-    std::copy(position, position + static_cast<size_t>(num_vertices) * 3, pos.begin());
-    std::copy(normal, normal + static_cast<size_t>(num_vertices) * 3, nrm.begin());
-    std::copy(tangent, tangent + static_cast<size_t>(num_vertices) * 3, tan.begin());
-    for (int v = 0; v < vpad; ++v) {
-        float* wv = &w[static_cast<size_t>(v) * 4];
+    // storage order: the caller's, or grouped by the number of non-zero weights (stable, most influences first)
+    mesh->order.resize(static_cast<size_t>(num_vertices));
+    for (int v = 0; v < num_vertices; ++v) mesh->order[static_cast<size_t>(v)] = v;
+    if (flags & DMK_MESH_SORT_BY_INFLUENCES) {
+        auto count = [&](int v) {
+            const float* idx = indices + static_cast<size_t>(v) * 4;
+            if (!(idx[0] >= 0.f)) return 1;
+            int n = 1;
+            for (int c = 1; c < 4; ++c) n += weights[static_cast<size_t>(v) * 4 + c] != 0.f ? 1 : 0;
+            return n;
+        };
+        std::stable_sort(mesh->order.begin(), mesh->order.end(), [&](int a, int b) { return count(a) > count(b); });
+        // Every thread of the skinning kernel owns 8 consecutive stored vertices and a warp executes the k-th vertex of its
+        // 32 threads together.  Fill the storage "column major" over those 8-vertex blocks: sorted vertex i goes to block
+        // i % B, slot i / B.  Then slot k of (almost) every block holds vertices with the same influence count -- the
+        // gathers of an absent influence are skipped by whole warps -- and every thread, warp and tile gets the same mix.
+        const size_t V = mesh->order.size(), B = static_cast<size_t>(vpad) / 8;
+        std::vector<int32_t> dealt(V);
+        size_t next = 0;
+        for (size_t slot = 0; slot < 8; ++slot)
+            for (size_t blk = 0; blk < B; ++blk) {
+                const size_t pos = blk * 8 + slot;
+                if (pos < V) dealt[pos] = mesh->order[next++];
+            }
+        mesh->order = dealt;
+        mesh->sorted = true;
+    }
+    for (int s = 0; s < vpad; ++s) {
+        float* wv = &w[static_cast<size_t>(s) * 4];
         wv[0] = 1.f;  // padding and unskinned vertices: 1 * identity
-        if (v >= num_vertices) continue;
+        if (s >= num_vertices) continue;
+        const int v = mesh->order[static_cast<size_t>(s)];
+        for (int k = 0; k < 3; ++k) {
+            pos[static_cast<size_t>(s) * 3 + k] = position[static_cast<size_t>(v) * 3 + k];
+            nrm[static_cast<size_t>(s) * 3 + k] = normal[static_cast<size_t>(v) * 3 + k];
+            tan[static_cast<size_t>(s) * 3 + k] = tangent[static_cast<size_t>(v) * 3 + k];
+        }
         const float* idx = indices + static_cast<size_t>(v) * 4;
         if (!(idx[0] >= 0.f)) continue;  // applySkinning: `if (indices.x >= 0)` else the vertex passes through
         uint32_t packed = 0;
@@ -615,7 +658,7 @@ dmk_status dmk_mesh_create(dmk_context_t ctx, const float* position, const float
             packed |= static_cast<uint32_t>(slot) << (8 * c);
             wv[c] = weights[static_cast<size_t>(v) * 4 + c];
         }
-        slots[v] = packed;
+        slots[s] = packed;
     }
     DMK_CUDA(ctx, upload(ctx, &mesh->d_pos, pos));
     DMK_CUDA(ctx, upload(ctx, &mesh->d_nrm, nrm));
@@ -1038,6 +1081,7 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         p.palette_size = c->mesh->palette_size;
         p.num_tiles = c->plan.num_tiles;
         p.tile_vertices = c->plan.tile_vertices;
+        p.skip_zero_weights = c->mesh->sorted ? 1 : 0;
         {
             KernelTimer timer(ctx, DMK_KERNEL_SKIN);
             DMK_CUDA(ctx, launch_skin(p, c->plan, s));

@@ -105,6 +105,7 @@ struct SkinParams {
     int palette_size;         // PS
     int num_tiles;            // vertex tiles per character
     int tile_vertices;        // multiple of 8
+    int skip_zero_weights;    // mesh is grouped by influence count: predicate the gathers of absent influences
 };
 
 struct CullParams {

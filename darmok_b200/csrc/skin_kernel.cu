@@ -79,6 +79,26 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
+// Predicated gather: an influence with zero weight contributes w * P = 0, so its rows are not fetched.  A quarter-warp
+// whose 8 lanes all skip costs no shared-memory wavefront (meshes whose vertices are grouped by influence count --
+// DMK_MESH_SORT_BY_INFLUENCES, or any mesh with spatially coherent skinning -- gather proportionally fewer bytes).
+__device__ __forceinline__ float4 lds128_if(uint32_t addr, uint32_t take) {
+    float4 v;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "setp.ne.u32 P1, %5, 0;\n"
+        "mov.f32 %0, 0f00000000;\n"
+        "mov.f32 %1, 0f00000000;\n"
+        "mov.f32 %2, 0f00000000;\n"
+        "mov.f32 %3, 0f00000000;\n"
+        "@P1 ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+        "}\n"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "r"(addr), "r"(take));
+    return v;
+}
+
 // mbarrier arrive (release at CTA scope): one arrival per warp after its lanes' shared-memory writes
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -90,13 +110,19 @@ constexpr int kNumStage = 2;  // bulk-copy staging ring
 // One vertex: gather 4 palette matrices row by row (row r+1 is in flight while row r is consumed), blend, apply.
 struct Rows4 { float4 q0, q1, q2, q3; };
 
-template <int REPL>
-__device__ __forceinline__ Rows4 load_row(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int r) {
-    Rows4 x;
+template <int REPL, bool SKIP>
+__device__ __forceinline__ Rows4 load_row(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int r, uint32_t used) {
+    Rows4 x;   // `used`: bit k set when influence k has a non-zero weight (influence 0 always is fetched)
     x.q0 = lds128(a0 + r * 16u * REPL);
-    x.q1 = lds128(a1 + r * 16u * REPL);
-    x.q2 = lds128(a2 + r * 16u * REPL);
-    x.q3 = lds128(a3 + r * 16u * REPL);
+    if (SKIP) {
+        x.q1 = lds128_if(a1 + r * 16u * REPL, used & 2u);
+        x.q2 = lds128_if(a2 + r * 16u * REPL, used & 4u);
+        x.q3 = lds128_if(a3 + r * 16u * REPL, used & 8u);
+    } else {
+        x.q1 = lds128(a1 + r * 16u * REPL);
+        x.q2 = lds128(a2 + r * 16u * REPL);
+        x.q3 = lds128(a3 + r * 16u * REPL);
+    }
     return x;
 }
 
@@ -109,7 +135,7 @@ __device__ __forceinline__ float4 blend_row(const Rows4& x, float w0, float w1, 
     return m;
 }
 
-template <int REPL>
+template <int REPL, bool SKIP>
 __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int PS = p.palette_size;
@@ -165,6 +191,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
             w0[v] = w.x; w1[v] = w.y; w2[v] = w.z; w3[v] = w.w;
             slots[v] = __ldg(p.slots + vi);
         }
+        uint32_t used[kVPT];
+#pragma unroll
+        for (int v = 0; v < kVPT; ++v) used[v] = 1u | (w1[v] != 0.f ? 2u : 0u) | (w2[v] != 0.f ? 4u : 0u) | (w3[v] != 0.f ? 8u : 0u);
 
         auto char_of = [&](int64_t i) -> int64_t {
             const int64_t k = group + i * ngroups;
@@ -227,7 +256,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
                     a3 = base + (s >> 24) * (48u * REPL);
                 };
                 addr(slots[0]);
-                Rows4 cur = load_row<REPL>(a0, a1, a2, a3, 0);
+                Rows4 cur = load_row<REPL, SKIP>(a0, a1, a2, a3, 0, used[0]);
 #pragma unroll
                 for (int v = 0; v < kVPT; ++v) {
                     float4 m[3];
@@ -235,10 +264,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
                     for (int r = 0; r < 3; ++r) {
                         Rows4 nxt;  // next row (or row 0 of the next vertex) is requested before this one is consumed
                         if (r < 2) {
-                            nxt = load_row<REPL>(a0, a1, a2, a3, r + 1);
+                            nxt = load_row<REPL, SKIP>(a0, a1, a2, a3, r + 1, used[v]);
                         } else if (v + 1 < kVPT) {
                             addr(slots[v + 1]);
-                            nxt = load_row<REPL>(a0, a1, a2, a3, 0);
+                            nxt = load_row<REPL, SKIP>(a0, a1, a2, a3, 0, used[v + 1]);
                         }
                         m[r] = blend_row(cur, w0[v], w1[v], w2[v], w3[v]);
                         cur = nxt;
@@ -270,12 +299,13 @@ size_t skin_smem_bytes(int palette_size, int repl) {
     return (size_t)palette_size * (48 * kNumRepl * repl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
 }
 template <typename F>
-auto with_kernel(int repl, F&& f) {
+auto with_kernel(int repl, bool skip, F&& f) {
+    if (skip && repl == 8) return f(skin_kernel<8, true>);   // meshes grouped by influence count
     switch (repl) {
-    case 8: return f(skin_kernel<8>);
-    case 4: return f(skin_kernel<4>);
-    case 2: return f(skin_kernel<2>);
-    default: return f(skin_kernel<1>);
+    case 8: return f(skin_kernel<8, false>);
+    case 4: return f(skin_kernel<4, false>);
+    case 2: return f(skin_kernel<2, false>);
+    default: return f(skin_kernel<1, false>);
     }
 }
 }  // namespace
@@ -293,7 +323,7 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms) {
     while (plan.replicas > 1 && skin_smem_bytes(palette_size, plan.replicas) > kMaxSmem) plan.replicas /= 2;
     plan.smem = skin_smem_bytes(palette_size, plan.replicas);
     int occ = 1;
-    with_kernel(plan.replicas, [&](auto kernel) {
+    with_kernel(plan.replicas, false, [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, plan.threads, plan.smem) != cudaSuccess || occ < 1) occ = 1;
         return 0;
@@ -307,7 +337,7 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms) {
 
 cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t stream) {
     if (p.n <= 0 || p.vpad <= 0) return cudaSuccess;
-    return with_kernel(plan.replicas, [&](auto kernel) {
+    return with_kernel(plan.replicas, p.skip_zero_weights != 0, [&](auto kernel) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (e != cudaSuccess) return e;
         kernel<<<plan.grid, plan.threads, plan.smem, stream>>>(p);

@@ -108,6 +108,15 @@ DMK_API int dmk_armature_palette_size(dmk_armature_t arm); /* num_joints + 1 (sl
 DMK_API dmk_status dmk_mesh_create(dmk_context_t ctx, const float* position, const float* normal, const float* tangent,
                                    const float* indices, const float* weights, int num_vertices, int palette_size,
                                    dmk_mesh_t* out);
+/* Same with options.  DMK_MESH_SORT_BY_INFLUENCES stores (and skins) the vertices grouped by their number of non-zero
+ * weights, so that warps skip the palette fetches of absent influences; the skinned buffer is then in the order given by
+ * dmk_mesh_vertex_order (out[i] = index, in the caller's arrays, of the vertex at position i) and the caller remaps its
+ * index buffer once, as after any vertex-cache optimisation.  Without the flag the caller's order is kept. */
+enum { DMK_MESH_SORT_BY_INFLUENCES = 1 };
+DMK_API dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const float* normal, const float* tangent,
+                                      const float* indices, const float* weights, int num_vertices, int palette_size,
+                                      uint32_t flags, dmk_mesh_t* out);
+DMK_API dmk_status dmk_mesh_vertex_order(dmk_mesh_t mesh, int32_t* out_order);
 DMK_API void dmk_mesh_destroy(dmk_mesh_t mesh);
 DMK_API int dmk_mesh_num_vertices(dmk_mesh_t mesh);
 DMK_API int dmk_mesh_vertex_pitch(dmk_mesh_t mesh); /* vertices per character in the skinned buffer (V rounded up to 8) */

@@ -114,3 +114,28 @@ def test_large_palettes_fall_back_to_fewer_replicas(joints):
     a = common.Assets(skel, clips, synth.make_armature(skel, seed=1), synth.make_mesh(700, joints, seed=2))
     got, ref, _, _ = _run(a, 6, layers=1, seed=3)
     assert_close(got, ref, f"skinned with {joints + 1} palette slots")
+
+
+def test_sorted_mesh_option_permutes_output(assets):
+    # DMK_MESH_SORT_BY_INFLUENCES: same results, in the order dmk_mesh_vertex_order reports
+    from darmok_b200 import capi
+    g, o = GpuRig(assets, with_mesh=False), OracleRig(assets)
+    try:
+        m = assets.mesh
+        g.mesh = capi.Mesh(g.ctx, m.pos, m.nrm, m.tan, m.indices, m.weights, g.arm.palette_size, flags=capi.MESH_SORT_BY_INFLUENCES)
+        order = g.mesh.order
+        assert sorted(order.tolist()) == list(range(m.pos.shape[0]))
+        counts = np.where(m.indices[:, 0] >= 0, (m.weights != 0).sum(axis=1).clip(1), 1)[order]
+        assert set(counts.tolist()) == {1, 2, 3, 4}
+        v = len(order) // 8 * 8
+        per_slot = counts[:v].reshape(-1, 8)          # [8-vertex block][slot]: a slot holds (almost) one influence count
+        assert sum(len(set(per_slot[:, k].tolist())) for k in range(8)) <= 8 + 3
+        n = 40
+        cr = synth.make_crowd(n, 2, len(assets.clips), seed=12)
+        crowd = g.crowd(n, 2)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+        crowd.step(0.0, capi.STEP_POSE | capi.STEP_SKIN)
+        ref = o.crowd(n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, mesh=m, want=("skinned",))["skinned"]
+        assert_close(crowd.get_skinned(), ref[:, order], "skinned (sorted order)")
+    finally:
+        g.close()

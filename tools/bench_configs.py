@@ -131,6 +131,46 @@ def config5():
           "cpu_oracle": {"instances_per_sec": m / cpu_s, "threads": O.max_threads()}})
 
 
+def config3_sorted():
+    """config 3's skinning kernel with the opt-in vertex order (DMK_MESH_SORT_BY_INFLUENCES): same 36 B/vertex written, fewer
+    palette gathers.  Reported next to bench.py's number, which keeps the caller's vertex order."""
+    import torch
+    from darmok_b200 import capi, synth
+    n, verts = 100_000, 5000
+    skel_s = synth.make_skeleton(67)
+    clips_s = [synth.make_clip(skel_s, f"clip{i}", seed=i, duration=1.5) for i in range(8)]
+    arm_s = synth.make_armature(skel_s)
+    mesh_s = synth.make_mesh(verts, 67)
+    out = {}
+    for name, flags in (("caller_order", 0), ("sorted_by_influences", capi.MESH_SORT_BY_INFLUENCES)):
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            ctx = capi.Context(0, stream.cuda_stream)
+            skel = capi.Skeleton(ctx, skel_s.archive)
+            clip_objs = [capi.Clip(ctx, c.archive) for c in clips_s]
+            clips = capi.ClipSet(ctx, skel, clip_objs)
+            arm = capi.Armature(ctx, skel, arm_s.names, arm_s.inv_bind)
+            mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size, flags=flags)
+            crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
+            cr = synth.make_crowd(n, 2, 8, seed=42)
+            crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+            crowd.step(1 / 60, capi.STEP_POSE)
+            for _ in range(3):
+                crowd.step(1 / 60, capi.STEP_SKIN)
+            ctx.enable_kernel_timing(True)
+            ctx.reset_kernel_timing()
+            for _ in range(10):
+                crowd.step(1 / 60, capi.STEP_SKIN)
+            ms, cnt = ctx.kernel_time(capi.KERNEL_SKIN)
+            ms /= cnt
+            gbps = n * (verts * 36 + arm.palette_size * 64) / (ms * 1e-3) / 1e9
+            out[name] = {"skin_ms": ms, "algorithmic_GBps": gbps, "frac_of_6542.4": gbps / 6542.4}
+            for o in (crowd, mesh, arm, clips, *clip_objs, skel, ctx):
+                o.close()
+        torch.cuda.empty_cache()
+    emit({"config": "3 (skin kernel only)", "what": "100k characters x 5k vertices, mean 3.0 influences/vertex (10/20/30/40 %)", **out})
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["1", "2", "5"]
     if "1" in which:
@@ -139,3 +179,5 @@ if __name__ == "__main__":
         config2()
     if "5" in which:
         config5()
+    if "3s" in which:
+        config3_sorted()
