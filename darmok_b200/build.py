@@ -29,6 +29,7 @@ UNITS = [
     ("ozz_io.cpp", []),
     ("pose_kernel.cu", ["-fmad=false"]),
     ("cull_kernel.cu", ["-fmad=false"]),
+    ("animator_kernel.cu", ["-fmad=false"]),
     ("skin_kernel.cu", []),
 ]
 

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdarmok_b200.so")
 OK, ERR_INVALID, ERR_FORMAT, ERR_CUDA, ERR_UNSUPPORTED, ERR_JOB = range(6)
 STEP_ADVANCE, STEP_POSE, STEP_CULL, STEP_SKIN, STEP_SKIN_VISIBLE_ONLY, STEP_READBACK_VISIBILITY = 1, 2, 4, 8, 16, 32
 STEP_ALL = 15
+STEP_ANIMATOR = 64
+ANIM_NONE, ANIM_STOP = -2, -1
 OUT_MODELS, OUT_LOCALS, OUT_KEY_INDICES = 1, 2, 4
 OPT_FORCE_KEY_SEARCH = 1
 OPT_SKIN_RESERVED_SMS = 2
@@ -23,7 +25,13 @@ GROUP_BLEND, GROUP_PASSTHROUGH = 0, 1
 TOP_GROUP0, TOP_TRANSITION, TOP_REST_POSE, TOP_SKIP = 0, 1, 2, 3
 PROGRAM_DTYPE = np.dtype([("n0", "u1"), ("n1", "u1"), ("rest0", "u1"), ("rest1", "u1"), ("mode0", "u1"), ("mode1", "u1"),
                           ("top", "u1"), ("reserved", "u1"), ("threshold0", "f4"), ("threshold1", "f4"), ("w0", "f4"), ("w1", "f4")])
-KERNEL_POSE, KERNEL_CULL, KERNEL_SKIN, KERNEL_PACK = 0, 1, 2, 3
+KERNEL_POSE, KERNEL_CULL, KERNEL_SKIN, KERNEL_PACK, KERNEL_ANIMATOR = 0, 1, 2, 3, 4
+ANIM_CLIP_DTYPE = np.dtype([("clip", "i4"), ("blend_x", "f4"), ("blend_y", "f4"), ("speed", "f4"), ("loop", "i4")])
+ANIM_STATE_DTYPE = np.dtype([("first_clip", "i4"), ("num_clips", "i4"), ("blend_type", "i4"), ("threshold", "f4"), ("tween_easing", "i4"),
+                             ("tween_duration", "f4"), ("next_state", "i4"), ("speed", "f4")])
+ANIM_TRANSITION_DTYPE = np.dtype([("src_state", "i4"), ("dst_state", "i4"), ("easing", "i4"), ("duration", "f4"), ("offset", "f4")])
+ANIM_EVENTS_DTYPE = np.dtype([("cmd_started", "i2"), ("cmd_transition_started", "i2"), ("transition_finished", "i2"), ("prev_finished", "i2"),
+                              ("looped", "i2"), ("finished", "i2"), ("auto_started", "i2"), ("auto_transition_started", "i2")])
 
 # every symbol include/dmk.h declares: (name, restype, argtypes)
 _vp, _i, _i64, _f, _u32, _sz, _cp = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32, C.c_size_t, C.c_char_p
@@ -68,6 +76,12 @@ SIGNATURES = [
     ("dmk_crowd_set_layers", _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f]),
     ("dmk_crowd_set_programs", _i, [_vp, _i, _vp, _vp, _vp, _vp]),
     ("dmk_crowd_update_layers", _i, [_vp, _i, _vp, _vp, _vp]),
+    ("dmk_crowd_set_animator", _i, [_vp, _vp, _i, _vp, _i, _vp, _i]),
+    ("dmk_crowd_animator_commands", _i, [_vp, _vp, _vp]),
+    ("dmk_crowd_animator_set_inputs", _i, [_vp, _vp, _vp]),
+    ("dmk_crowd_get_animator_events", _i, [_vp, _vp, _vp]),
+    ("dmk_crowd_get_animator_state", _i, [_vp, _vp, _vp, _vp, _vp]),
+    ("dmk_crowd_get_programs", _i, [_vp, _i, _vp, _vp, _vp, _vp]),
     ("dmk_crowd_set_instances", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_set_transforms", _i, [_vp, _vp, _vp, _vp, _vp]),
     ("dmk_crowd_set_camera", _i, [_vp, _vp, _f]),
@@ -316,6 +330,46 @@ class Crowd:
 
     def update_layers(self, clip, ratio, weight):
         self.ctx.check(lib().dmk_crowd_update_layers(self.h, self.num_layers, _ptr(clip), _ptr(ratio), _ptr(weight)))
+
+    # ---- device-side animators ----
+    def set_animator(self, states, clips, transitions):
+        states = np.ascontiguousarray(states, ANIM_STATE_DTYPE)
+        clips = np.ascontiguousarray(clips, ANIM_CLIP_DTYPE)
+        transitions = np.ascontiguousarray(transitions, ANIM_TRANSITION_DTYPE)
+        self.ctx.check(lib().dmk_crowd_set_animator(self.h, _ptr(states), len(states), _ptr(clips), len(clips),
+                                                    _ptr(transitions) if len(transitions) else None, len(transitions)))
+
+    def animator_commands(self, state, speed=None):
+        state = np.ascontiguousarray(state, np.int32)
+        assert state.shape == (self.n,)
+        speed = None if speed is None else _f32(speed)
+        self.ctx.check(lib().dmk_crowd_animator_commands(self.h, _ptr(state), None if speed is None else _ptr(speed)))
+
+    def animator_set_inputs(self, blend_xy=None, speed=None):
+        blend_xy = None if blend_xy is None else _f32(blend_xy)
+        speed = None if speed is None else _f32(speed)
+        assert blend_xy is None or blend_xy.shape == (self.n, 2)
+        self.ctx.check(lib().dmk_crowd_animator_set_inputs(self.h, None if blend_xy is None else _ptr(blend_xy),
+                                                           None if speed is None else _ptr(speed)))
+
+    def animator_events(self):
+        ev = np.empty(self.n, ANIM_EVENTS_DTYPE)
+        status = np.empty(self.n, np.int32)
+        self.ctx.check(lib().dmk_crowd_get_animator_events(self.h, _ptr(ev), _ptr(status)))
+        return ev, status
+
+    def animator_state(self):
+        state, trans = np.empty(self.n, np.int32), np.empty(self.n, np.int32)
+        st, tt = np.empty(self.n, np.float32), np.empty(self.n, np.float32)
+        self.ctx.check(lib().dmk_crowd_get_animator_state(self.h, _ptr(state), _ptr(st), _ptr(trans), _ptr(tt)))
+        return state, st, trans, tt
+
+    def programs(self, num_layers):
+        clip = np.empty((num_layers, self.n), np.int32)
+        ratio, weight = np.empty((num_layers, self.n), np.float32), np.empty((num_layers, self.n), np.float32)
+        prog = np.empty(self.n, PROGRAM_DTYPE)
+        self.ctx.check(lib().dmk_crowd_get_programs(self.h, num_layers, _ptr(clip), _ptr(ratio), _ptr(weight), _ptr(prog)))
+        return clip, ratio, weight, prog
 
     def set_instances(self, world_inverse, bbox):
         wi, bb = _f32(world_inverse), _f32(bbox)

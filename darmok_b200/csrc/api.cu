@@ -9,9 +9,11 @@
 #include "ozz_io.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -35,8 +37,8 @@ struct dmk_context_s {
     struct Timed { int kernel; cudaEvent_t start, stop; };
     std::vector<Timed> pending;
     std::vector<cudaEvent_t> event_pool;
-    double kernel_ms[DMK_KERNEL_COUNT] = {0, 0, 0, 0};
-    uint64_t kernel_launches[DMK_KERNEL_COUNT] = {0, 0, 0, 0};
+    double kernel_ms[DMK_KERNEL_COUNT] = {};
+    uint64_t kernel_launches[DMK_KERNEL_COUNT] = {};
 };
 
 struct dmk_skeleton_s {
@@ -134,6 +136,19 @@ struct dmk_crowd_s {
     bool culled_once = false;
     bool force_search = false;  // tests: exercise the per-track binary search even when a bucket table exists
     SkinPlan plan{};
+    // device-side animators (dmk_crowd_set_animator)
+    AnimStateDef* d_anim_states = nullptr;
+    AnimClipDef* d_anim_clips = nullptr;
+    AnimTransitionDef* d_anim_transitions = nullptr;
+    float* d_anim_tables = nullptr;
+    uint32_t* d_anim_slots = nullptr;
+    int32_t* d_anim_transition = nullptr;
+    float* d_anim_transition_time = nullptr;
+    AnimEvents* d_anim_events = nullptr;
+    int32_t *d_anim_cmd = nullptr, *d_anim_status = nullptr;
+    float *d_anim_cmd_speed = nullptr, *d_anim_blend = nullptr, *d_anim_speed = nullptr;
+    int anim_num_states = 0, anim_num_transitions = 0, anim_layers = 0;
+    bool animator_set = false, animator_ticked = false;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -742,7 +757,10 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
     for (void* p : {(void*)c->d_clip, (void*)c->d_ratio, (void*)c->d_weight, (void*)c->d_speed, (void*)c->d_loop, (void*)c->d_looped,
                     (void*)c->d_program, (void*)c->d_local_matrices, (void*)c->d_palette, (void*)c->d_palette34, (void*)c->d_skinned, (void*)c->d_models, (void*)c->d_locals,
                     (void*)c->d_key_indices, (void*)c->d_error, (void*)c->d_world_inverse, (void*)c->d_bbox, (void*)c->d_position, (void*)c->d_rotation, (void*)c->d_scale, (void*)c->d_vis_bits,
-                    (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch})
+                    (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch, (void*)c->d_anim_states, (void*)c->d_anim_clips,
+                    (void*)c->d_anim_transitions, (void*)c->d_anim_tables, (void*)c->d_anim_slots, (void*)c->d_anim_transition,
+                    (void*)c->d_anim_transition_time, (void*)c->d_anim_events, (void*)c->d_anim_cmd, (void*)c->d_anim_status,
+                    (void*)c->d_anim_cmd_speed, (void*)c->d_anim_blend, (void*)c->d_anim_speed})
         dev_free(p);
     for (int b = 0; b < 2; ++b) {
         if (c->h_vis[b]) cudaFreeHost(c->h_vis[b]);
@@ -900,6 +918,228 @@ dmk_status dmk_crowd_update_layers(dmk_crowd_t c, int num_layers, const int32_t*
     return stage_release(c);
 }
 
+// ---- device-side animators ------------------------------------------------------------
+// OzzSkeletalAnimatorState::calcDuration (src/skeleton_ozz.cpp:487-518): least common multiple of the clip durations in
+// decimal fixed point.  For a duration without a fractional part the reference converts ceil(-log10(0)) = +inf to int,
+// which x86 turns into INT_MIN so that pow(10, INT_MIN) = 0 and the factor stays 1; that outcome is kept here.
+static float anim_state_duration(const std::vector<float>& clip_durations) {
+    if (clip_durations.empty()) return 0.f;
+    int f = 1;
+    for (float d : clip_durations) {
+        const float frac = d - std::floor(d);
+        if (!(frac > 0.f)) continue;
+        const int places = static_cast<int>(std::ceil(-std::log10(frac)));
+        f = std::max(f, static_cast<int>(std::pow(10, places)));
+    }
+    int d = static_cast<int>(std::round(clip_durations[0] * f));
+    for (size_t i = 1; i < clip_durations.size(); ++i) d = std::lcm(d, static_cast<int>(std::round(clip_durations[i] * f)));
+    return static_cast<float>(d) / f;
+}
+
+static AnimatorParams animator_params(dmk_crowd_t c, float dt) {
+    AnimatorParams a{};
+    a.states = c->d_anim_states;
+    a.clips = c->d_anim_clips;
+    a.transitions = c->d_anim_transitions;
+    a.num_states = c->anim_num_states;
+    a.num_transitions = c->anim_num_transitions;
+    a.tables = c->d_anim_tables;
+    a.slots = c->d_anim_slots;
+    a.transition_def = c->d_anim_transition;
+    a.transition_time = c->d_anim_transition_time;
+    a.cmd_state = c->d_anim_cmd;
+    a.cmd_speed = c->d_anim_cmd_speed;
+    a.in_blend = c->d_anim_blend;
+    a.in_speed = c->d_anim_speed;
+    a.events = c->d_anim_events;
+    a.status = c->d_anim_status;
+    a.n = c->n;
+    a.num_layers = c->anim_layers;
+    a.dt = dt;
+    a.clip = c->d_clip;
+    a.ratio = c->d_ratio;
+    a.weight = c->d_weight;
+    a.program = c->d_program;
+    return a;
+}
+
+// glm::length / glm::angle as calcBlendWeight calls them (src/skeleton.cpp:312-325): no normalisation before the acos
+static float anim_length(float x, float y) { return std::sqrt(x * x + y * y); }
+static float anim_angle(float ax, float ay, float bx, float by) { return std::acos(std::min(std::max(ax * bx + ay * by, -1.f), 1.f)); }
+
+dmk_status dmk_crowd_set_animator(dmk_crowd_t c, const dmk_anim_state_def* states, int num_states, const dmk_anim_clip_def* clips,
+                                  int num_clips, const dmk_anim_transition_def* transitions, int num_transitions) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!states || !clips || num_states < 1 || num_states > 32767 || num_clips < 1 || num_transitions < 0 || (num_transitions && !transitions))
+        return fail(ctx, DMK_ERR_INVALID, "malformed animator definition");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    std::vector<AnimClipDef> hc(static_cast<size_t>(num_clips));
+    for (int i = 0; i < num_clips; ++i) {
+        if (clips[i].clip < 0 || clips[i].clip >= c->clips->num_clips)
+            return fail(ctx, DMK_ERR_INVALID, "animation " + std::to_string(i) + " references a clip outside the clip set");
+        hc[i] = AnimClipDef{clips[i].clip, clips[i].blend_x, clips[i].blend_y, clips[i].speed, clips[i].loop ? 1 : 0,
+                            c->clips->durations[static_cast<size_t>(clips[i].clip)]};
+    }
+    std::vector<AnimStateDef> hs(static_cast<size_t>(num_states));
+    std::vector<float> tables(1, 0.f);   // never empty, so the upload always yields a pointer
+    int max_clips = 0;
+    for (int i = 0; i < num_states; ++i) {
+        const dmk_anim_state_def& d = states[i];
+        if (d.num_clips < 1 || d.num_clips > kMaxStateClips || d.first_clip < 0 || d.first_clip + d.num_clips > num_clips)
+            return fail(ctx, DMK_ERR_INVALID, "state " + std::to_string(i) + ": clip range must hold 1.." + std::to_string(kMaxStateClips) + " animations");
+        if (d.next_state < -1 || d.next_state >= num_states || d.blend_type < 0 || d.blend_type > 1 || d.tween_easing < 0 || d.tween_easing > 31)
+            return fail(ctx, DMK_ERR_INVALID, "state " + std::to_string(i) + ": next_state, blend_type or easing out of range");
+        max_clips = std::max(max_clips, d.num_clips);
+        std::vector<float> durations;
+        int rest = -1;
+        for (int k = 0; k < d.num_clips; ++k) {
+            const AnimClipDef& cd = hc[static_cast<size_t>(d.first_clip + k)];
+            const float speed = cd.speed == 0.f ? 1.f : cd.speed;
+            durations.push_back(cd.duration / speed);
+            if (cd.blend_x == 0.f && cd.blend_y == 0.f) rest = k;
+        }
+        int table = -1;
+        if (d.blend_type == 1) {   // Directional: the clip-pair constants of the gradient bands
+            table = static_cast<int>(tables.size());
+            const AnimClipDef* sc = &hc[static_cast<size_t>(d.first_clip)];
+            for (int k = 0; k < d.num_clips; ++k) tables.push_back(anim_length(sc[k].blend_x, sc[k].blend_y));
+            for (int a = 0; a < d.num_clips; ++a)
+                for (int b = 0; b < d.num_clips; ++b) tables.push_back(anim_angle(sc[b].blend_x, sc[b].blend_y, sc[a].blend_x, sc[a].blend_y));
+        }
+        hs[i] = AnimStateDef{d.first_clip, d.num_clips, d.blend_type, d.threshold, d.tween_easing, d.tween_duration, d.next_state, d.speed,
+                             anim_state_duration(durations), rest < 0 ? 0 : rest, table};
+    }
+    if (2 * max_clips > c->max_layers)
+        return fail(ctx, DMK_ERR_INVALID, "the crowd needs max_layers >= " + std::to_string(2 * max_clips) + " for this animator (two states blend in a transition)");
+    std::vector<AnimTransitionDef> ht(static_cast<size_t>(num_transitions));
+    for (int i = 0; i < num_transitions; ++i) {
+        const dmk_anim_transition_def& t = transitions[i];
+        if (t.src_state < -1 || t.src_state >= num_states || t.dst_state < -1 || t.dst_state >= num_states || t.easing < 0 || t.easing > 31)
+            return fail(ctx, DMK_ERR_INVALID, "transition " + std::to_string(i) + ": state or easing out of range");
+        ht[i] = AnimTransitionDef{t.src_state, t.dst_state, t.easing, t.duration, t.offset};
+    }
+    for (void* p : {(void*)c->d_anim_states, (void*)c->d_anim_clips, (void*)c->d_anim_transitions, (void*)c->d_anim_tables}) dev_free(p);
+    c->d_anim_states = nullptr; c->d_anim_clips = nullptr; c->d_anim_transitions = nullptr; c->d_anim_tables = nullptr;
+    DMK_CUDA(ctx, upload(ctx, &c->d_anim_tables, tables));
+    DMK_CUDA(ctx, upload(ctx, &c->d_anim_states, hs));
+    DMK_CUDA(ctx, upload(ctx, &c->d_anim_clips, hc));
+    DMK_CUDA(ctx, upload(ctx, &c->d_anim_transitions, ht));
+    const size_t n = static_cast<size_t>(c->n);
+    if (!c->d_anim_slots) {
+        DMK_CUDA(ctx, dev_alloc(&c->d_anim_slots, static_cast<size_t>(kNumSlots) * kSlotWords * n));
+        DMK_CUDA(ctx, dev_alloc(&c->d_anim_transition, n));
+        DMK_CUDA(ctx, dev_alloc(&c->d_anim_transition_time, n));
+        DMK_CUDA(ctx, dev_alloc(&c->d_anim_events, n));
+        DMK_CUDA(ctx, dev_alloc(&c->d_anim_cmd, n));
+        DMK_CUDA(ctx, dev_alloc(&c->d_anim_status, n));
+        DMK_CUDA(ctx, dev_alloc(&c->d_anim_cmd_speed, n));
+        DMK_CUDA(ctx, dev_alloc(&c->d_anim_blend, 2 * n));
+        DMK_CUDA(ctx, dev_alloc(&c->d_anim_speed, n));
+    }
+    if (!c->d_program) DMK_CUDA(ctx, dev_alloc(&c->d_program, n));
+    DMK_CUDA(ctx, launch_animator_init(animator_params(c, 0.f), c->d_anim_cmd_speed, c->d_anim_blend, c->d_anim_speed, ctx->stream));
+    DMK_CUDA(ctx, cudaMemsetAsync(c->d_anim_status, 0, n * sizeof(int32_t), ctx->stream));
+    DMK_CUDA(ctx, cudaMemsetAsync(c->d_anim_events, 0xff, n * sizeof(AnimEvents), ctx->stream));
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the upload sources are locals
+    ++ctx->launches;
+    c->anim_num_states = num_states;
+    c->anim_num_transitions = num_transitions;
+    c->anim_layers = 2 * max_clips;
+    c->animator_set = true;
+    c->animator_ticked = false;
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_animator_commands(dmk_crowd_t c, const int32_t* state, const float* speed) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!c->animator_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_animator has not been called");
+    if (!state) return fail(ctx, DMK_ERR_INVALID, "null command array");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t n = static_cast<size_t>(c->n);
+    // an unknown state name is "nothing happens" in the reference (play() returns false): ids outside the table do the same
+    char* h = nullptr;
+    if (dmk_status st = stage_acquire(c, 2 * n * 4, &h)) return st;
+    std::memcpy(h, state, n * 4);
+    float* hs = reinterpret_cast<float*>(h + n * 4);
+    if (speed) std::memcpy(hs, speed, n * 4);
+    else std::fill(hs, hs + n, 1.f);
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_anim_cmd, h, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_anim_cmd_speed, hs, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return stage_release(c);
+}
+
+dmk_status dmk_crowd_animator_set_inputs(dmk_crowd_t c, const float* blend_xy, const float* speed) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!c->animator_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_animator has not been called");
+    if (!blend_xy && !speed) return DMK_OK;
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t n = static_cast<size_t>(c->n);
+    char* h = nullptr;
+    if (dmk_status st = stage_acquire(c, 3 * n * 4, &h)) return st;
+    if (blend_xy) {
+        std::memcpy(h, blend_xy, 2 * n * 4);
+        DMK_CUDA(ctx, cudaMemcpyAsync(c->d_anim_blend, h, 2 * n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (speed) {
+        std::memcpy(h + 2 * n * 4, speed, n * 4);
+        DMK_CUDA(ctx, cudaMemcpyAsync(c->d_anim_speed, h + 2 * n * 4, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return stage_release(c);
+}
+
+dmk_status dmk_crowd_get_animator_events(dmk_crowd_t c, dmk_anim_events* out_events, int32_t* out_status) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    static_assert(sizeof(dmk_anim_events) == sizeof(AnimEvents), "C ABI struct and device struct must match");
+    if (!c->animator_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_animator has not been called");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t n = static_cast<size_t>(c->n);
+    if (out_events) DMK_CUDA(ctx, cudaMemcpyAsync(out_events, c->d_anim_events, n * sizeof(AnimEvents), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) DMK_CUDA(ctx, cudaMemcpyAsync(out_status, c->d_anim_status, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_get_animator_state(dmk_crowd_t c, int32_t* out_state, float* out_state_time, int32_t* out_transition,
+                                        float* out_transition_time) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!c->animator_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_animator has not been called");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t n = static_cast<size_t>(c->n);
+    int32_t* d = nullptr;   // 4 arrays of n words
+    DMK_CUDA(ctx, dev_alloc(&d, 4 * n));
+    cudaError_t e = launch_animator_query(animator_params(c, 0.f), d, reinterpret_cast<float*>(d + n), d + 2 * n, reinterpret_cast<float*>(d + 3 * n),
+                                          ctx->stream);
+    ++ctx->launches;
+    void* outs[4] = {out_state, out_state_time, out_transition, out_transition_time};
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k)
+        if (outs[k]) e = cudaMemcpyAsync(outs[k], d + k * n, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(d);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "animator state query");
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_get_programs(dmk_crowd_t c, int num_layers, int32_t* out_clip, float* out_ratio, float* out_weight,
+                                  dmk_pose_program* out_programs) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (num_layers < 0 || num_layers > c->max_layers) return fail(ctx, DMK_ERR_INVALID, "num_layers out of range");
+    if (out_programs && !c->d_program) return fail(ctx, DMK_ERR_INVALID, "the crowd has no pose programs");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t n = static_cast<size_t>(c->n), ln = static_cast<size_t>(num_layers) * n;
+    if (out_clip) DMK_CUDA(ctx, cudaMemcpyAsync(out_clip, c->d_clip, ln * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_ratio) DMK_CUDA(ctx, cudaMemcpyAsync(out_ratio, c->d_ratio, ln * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_weight) DMK_CUDA(ctx, cudaMemcpyAsync(out_weight, c->d_weight, ln * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_programs) DMK_CUDA(ctx, cudaMemcpyAsync(out_programs, c->d_program, n * sizeof(PoseProgram), cudaMemcpyDeviceToHost, ctx->stream));
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DMK_OK;
+}
+
 dmk_status dmk_crowd_set_instances(dmk_crowd_t c, const float* world_inverse, const float* bbox) {
     if (!c) return DMK_ERR_INVALID;
     dmk_context_t ctx = c->ctx;
@@ -964,6 +1204,21 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
     cudaStream_t s = ctx->stream;
     if ((flags & DMK_STEP_ADVANCE) && !(flags & DMK_STEP_POSE))
         return fail(ctx, DMK_ERR_UNSUPPORTED, "DMK_STEP_ADVANCE runs inside the pose kernel: combine it with DMK_STEP_POSE");
+    if (flags & DMK_STEP_ANIMATOR) {
+        if (!c->animator_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_animator has not been called");
+        if (flags & DMK_STEP_ADVANCE) return fail(ctx, DMK_ERR_UNSUPPORTED, "the device animators own the clip clocks: do not combine them with DMK_STEP_ADVANCE");
+        const AnimatorParams a = animator_params(c, dt);
+        {
+            KernelTimer timer(ctx, DMK_KERNEL_ANIMATOR);
+            DMK_CUDA(ctx, launch_animator(a, s));
+        }
+        ++ctx->launches;
+        c->num_layers = c->anim_layers;
+        c->layers_set = true;
+        c->use_program = true;
+        c->has_loop = false;
+        c->animator_ticked = true;
+    }
     if (flags & DMK_STEP_POSE) {
         if (!c->layers_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_layers has not been called");
         // BlendingJob::Validate: threshold > 0 (darmok: "error in the blending job", src/skeleton_ozz.cpp:605-608)

@@ -122,3 +122,87 @@ struct CullParams {
 };
 
 }  // namespace dmk
+
+// ---- device-side animator: darmok's animator state machine, one thread per character --------
+namespace dmk {
+
+constexpr int kMaxStateClips = 16;
+
+struct AnimClipDef {      // SkeletalAnimatorAnimation (assets/protobuf/skeleton.proto:18-23) resolved against the clip set
+    int32_t clip;         // index into the clip set
+    float blend_x, blend_y;
+    float speed;          // 0 counts as 1 (src/skeleton_ozz.cpp:398-404)
+    int32_t loop;
+    float duration;       // clip duration (seconds)
+};
+struct AnimStateDef {     // SkeletalAnimatorState (:30-46)
+    int32_t first_clip, num_clips;
+    int32_t blend_type;   // 0 Cartesian, 1 Directional
+    float threshold;
+    int32_t tween_easing;
+    float tween_duration;
+    int32_t next_state;   // -1 = none
+    float speed;
+    float duration;       // OzzSkeletalAnimatorState::calcDuration (host, once per definition)
+    int32_t rest_clip;    // last clip whose blend position is exactly (0, 0), else 0
+    int32_t table;        // Directional states: offset into AnimatorParams::tables of [m] |blend_position| followed by
+                          // [m][m] angle(blend_position j, blend_position i) at i * m + j; -1 otherwise
+};
+struct AnimTransitionDef {  // SkeletalAnimatorTransition (:48-53); -1 = any state
+    int32_t src_state, dst_state;
+    int32_t easing;
+    float duration;
+    float offset;
+};
+
+// Animator state lives in HBM as structure-of-arrays words so that a warp's accesses coalesce and a character only
+// touches what its situation needs (a plain single-clip state reads ~8 words; a 9-clip transition ~60).
+// One "slot" = OzzSkeletalAnimatorState + its OzzSkeletalAnimatorAnimationStates; every character has three:
+// _state, and the transition's previous / current states.  Word w of slot s of character c: slots[(s * kSlotWords + w) * N + c].
+enum AnimSlot { kSlotState = 0, kSlotPrev = 1, kSlotCur = 2, kNumSlots = 3 };
+enum AnimSlotWord {
+    kWDef = 0,        // int: state definition index, -1 = none
+    kWClipLooped,     // uint: bit per clip
+    kWBlendX, kWBlendY, kWOldBlendX, kWOldBlendY,
+    kWNormalizedTime, kWTweenTime, kWSpeed,
+    kWLooped,         // int
+    kWClipTime,       // kMaxStateClips floats
+    kSlotWords = kWClipTime + kMaxStateClips
+};
+struct AnimEvents {          // listener events of one tick, in the reference's order (src/skeleton_ozz.cpp:783-856, 1044-1087)
+    int16_t cmd_started;     // play() command: onAnimatorStateStarted(state), -1 = none
+    int16_t cmd_transition_started;
+    int16_t transition_finished;  // 1: onAnimatorTransitionFinished + onAnimatorStateFinished(prev_finished)
+    int16_t prev_finished;
+    int16_t looped;          // onAnimatorStateLooped(state), -1 = none
+    int16_t finished;        // onAnimatorStateFinished(state), -1 = none
+    int16_t auto_started;    // next_state play: onAnimatorStateStarted
+    int16_t auto_transition_started;
+};
+
+struct AnimatorParams {
+    const AnimStateDef* states;
+    const AnimClipDef* clips;
+    const AnimTransitionDef* transitions;
+    int num_states, num_transitions;
+    const float* tables;         // per-definition constants of calcBlendWeight (src/skeleton.cpp:306-344)
+    uint32_t* slots;             // [kNumSlots][kSlotWords][N]
+    int32_t* transition_def;     // [N] running transition's definition, -1 = none
+    float* transition_time;      // [N] its normalized time
+    int32_t* cmd_state;          // [N] pending command: -2 none, -1 stop, >= 0 play(state); reset by the kernel
+    const float* cmd_speed;      // [N]
+    const float* in_blend;       // [N][2] setBlendPosition
+    const float* in_speed;       // [N] setPlaybackSpeed
+    AnimEvents* events;          // [N]
+    int32_t* status;             // [N] 0 ok, 1 "error in the blending job" (pose left untouched), written every tick
+    int64_t n;
+    int num_layers;              // rows of the layer arrays
+    float dt;
+    // outputs: the layer arrays and programs the pose kernels consume
+    int32_t* clip;
+    float* ratio;
+    float* weight;
+    PoseProgram* program;
+};
+
+}  // namespace dmk

@@ -8,6 +8,12 @@
 
 #include <cmath>
 
+#ifdef __CUDACC__
+#define DMK_HD __host__ __device__
+#else
+#define DMK_HD
+#endif
+
 namespace darmok {
 
 enum class EasingType : int {  // assets/protobuf/easing.proto:6-38
@@ -18,20 +24,20 @@ enum class EasingType : int {  // assets/protobuf/easing.proto:6-38
 };
 
 namespace easing_detail {
-constexpr float kHalfPi = 1.57079632679489661923f, kPi = 3.14159265358979323846f, kTwoPi = 6.28318530717958647692f;
+constexpr float kHalfPi = 1.57079632679489661923f, kPi = 3.14159265358979323846f, kTwoPi = 6.28318530717958647692f;  // constexpr: usable in device code
 
-inline float bounce_out(float p, float c) {  // c = end - start, start = 0
+DMK_HD inline float bounce_out(float p, float c) {  // c = end - start, start = 0
     if (p < 1 / 2.75f) return c * (7.5625f * p * p);
     if (p < 2.0f / 2.75f) { p -= 1.5f / 2.75f; return c * (7.5625f * p * p + .75f); }
     if (p < 2.5f / 2.75f) { p -= 2.25f / 2.75f; return c * (7.5625f * p * p + .9375f); }
     p -= 2.625f / 2.75f;
     return c * (7.5625f * p * p + .984375f);
 }
-inline float bounce_in(float p, float c) { return c - bounce_out(1 - p, c); }
+DMK_HD inline float bounce_in(float p, float c) { return c - bounce_out(1 - p, c); }
 }  // namespace easing_detail
 
 // Easing::apply(type, p, 0.F, 1.F)
-inline float ease01(EasingType type, float p) {
+DMK_HD inline float ease01(EasingType type, float p) {
     using namespace easing_detail;
     switch (type) {
     case EasingType::Stepped: return 0.f;

@@ -65,7 +65,7 @@ DMK_API uint64_t dmk_context_launch_count(dmk_context_t ctx);
 
 /* Optional per-kernel device timing (CUDA events on the context's stream around each launch; used by bench.py
  * for the roofline line).  kernel: DMK_KERNEL_*; totals accumulate until reset; the query synchronises. */
-enum { DMK_KERNEL_POSE = 0, DMK_KERNEL_CULL = 1, DMK_KERNEL_SKIN = 2, DMK_KERNEL_PACK = 3, DMK_KERNEL_COUNT = 4 };
+enum { DMK_KERNEL_POSE = 0, DMK_KERNEL_CULL = 1, DMK_KERNEL_SKIN = 2, DMK_KERNEL_PACK = 3, DMK_KERNEL_ANIMATOR = 4, DMK_KERNEL_COUNT = 5 };
 DMK_API dmk_status dmk_context_enable_kernel_timing(dmk_context_t ctx, int on);
 DMK_API dmk_status dmk_context_kernel_time(dmk_context_t ctx, int kernel, double* total_ms, uint64_t* launches);
 DMK_API dmk_status dmk_context_reset_kernel_timing(dmk_context_t ctx);
@@ -178,6 +178,64 @@ DMK_API dmk_status dmk_crowd_set_programs(dmk_crowd_t crowd, int num_layers, con
 DMK_API dmk_status dmk_crowd_update_layers(dmk_crowd_t crowd, int num_layers, const int32_t* clip, const float* ratio,
                                            const float* weight);
 
+/* ---- "next" row: the animator state machine itself on the device ---------------------
+ * Instead of resolving every SkeletalAnimator on the host each frame and uploading layers + programs, hand over the
+ * SkeletalAnimatorDefinition once; DMK_STEP_ANIMATOR then ticks one animator per character on the GPU
+ * (SkeletalAnimatorImpl::update / afterUpdate, src/skeleton_ozz.cpp:1006-1087; state update :535-610; transition
+ * :682-726; play :783-856; calcBlendWeights src/skeleton.cpp:306-364) and writes the layer rows and pose programs the
+ * POSE step consumes.  Per frame only commands (play / stop), blend positions and playback speeds cross the bus.
+ * Field names follow assets/protobuf/skeleton.proto:18-53; names are resolved to indices by the caller. */
+typedef struct dmk_anim_clip_def {   /* SkeletalAnimatorAnimation */
+    int32_t clip;                    /* index into the clip set */
+    float blend_x, blend_y;          /* blend_position */
+    float speed;                     /* 0 counts as 1 (src/skeleton_ozz.cpp:398-404) */
+    int32_t loop;
+} dmk_anim_clip_def;
+typedef struct dmk_anim_state_def {  /* SkeletalAnimatorState */
+    int32_t first_clip, num_clips;   /* range in the clip-def array, 1..16 clips */
+    int32_t blend_type;              /* 0 Cartesian, 1 Directional */
+    float threshold;
+    int32_t tween_easing;            /* assets/protobuf/easing.proto value */
+    float tween_duration;
+    int32_t next_state;              /* -1 = none */
+    float speed;
+} dmk_anim_state_def;
+typedef struct dmk_anim_transition_def {   /* SkeletalAnimatorTransition; state -1 = any ("" in the proto) */
+    int32_t src_state, dst_state;
+    int32_t easing;
+    float duration;
+    float offset;
+} dmk_anim_transition_def;
+/* Listener events of one tick in the reference's order: play() command, then afterUpdate (src/skeleton_ozz.cpp:1044-1087) */
+typedef struct dmk_anim_events {
+    int16_t cmd_started;             /* onAnimatorStateStarted(state) raised by the play command, -1 = none */
+    int16_t cmd_transition_started;  /* 1: onAnimatorTransitionStarted followed it */
+    int16_t transition_finished;     /* 1: onAnimatorTransitionFinished + onAnimatorStateFinished(prev_finished) */
+    int16_t prev_finished;
+    int16_t looped;                  /* onAnimatorStateLooped(state), -1 = none */
+    int16_t finished;                /* onAnimatorStateFinished(state), -1 = none */
+    int16_t auto_started;            /* next_state: onAnimatorStateStarted(state), -1 = none */
+    int16_t auto_transition_started;
+} dmk_anim_events;
+/* Needs max_layers >= 2 * (largest num_clips): a transition blends two states.  All animators start stopped. */
+DMK_API dmk_status dmk_crowd_set_animator(dmk_crowd_t crowd, const dmk_anim_state_def* states, int num_states,
+                                          const dmk_anim_clip_def* clips, int num_clips,
+                                          const dmk_anim_transition_def* transitions, int num_transitions);
+/* Commands executed at the start of the next DMK_STEP_ANIMATOR, per character: state >= 0 = play(state, speed),
+ * DMK_ANIM_STOP = stop(), DMK_ANIM_NONE = nothing.  speed NULL = 1 (play()'s default stateSpeed). */
+enum { DMK_ANIM_NONE = -2, DMK_ANIM_STOP = -1 };
+DMK_API dmk_status dmk_crowd_animator_commands(dmk_crowd_t crowd, const int32_t* state, const float* speed);
+/* setBlendPosition / setPlaybackSpeed for every character: blend_xy [N][2] and/or speed [N] (NULL = unchanged) */
+DMK_API dmk_status dmk_crowd_animator_set_inputs(dmk_crowd_t crowd, const float* blend_xy, const float* speed);
+/* After a step: events [N]; status [N] = 0, or 1 where update() returned "error in the blending job" (pose kept) */
+DMK_API dmk_status dmk_crowd_get_animator_events(dmk_crowd_t crowd, dmk_anim_events* out_events, int32_t* out_status);
+/* getCurrentState / getCurrentTransition: state [N] (-1 = none), transition [N] (-1 = none), their normalized times */
+DMK_API dmk_status dmk_crowd_get_animator_state(dmk_crowd_t crowd, int32_t* out_state, float* out_state_time,
+                                                int32_t* out_transition, float* out_transition_time);
+/* The layer rows and programs currently on the device (whoever wrote them): [num_layers][N] each, programs [N] */
+DMK_API dmk_status dmk_crowd_get_programs(dmk_crowd_t crowd, int num_layers, int32_t* out_clip, float* out_ratio,
+                                          float* out_weight, dmk_pose_program* out_programs);
+
 /* Transform::getWorldInverse (src/transform.cpp:286-309) + BoundingBox (assets/protobuf/shape.proto:7-10) of each
  * character entity: world_inverse [N][16], bbox [N][6] = min.xyz, max.xyz (local space). */
 DMK_API dmk_status dmk_crowd_set_instances(dmk_crowd_t crowd, const float* world_inverse, const float* bbox);
@@ -205,6 +263,7 @@ enum {
     DMK_STEP_SKIN_VISIBLE_ONLY = 16, /* with CULL+SKIN: skin only characters FrustumCuller would not cull */
     DMK_STEP_READBACK_VISIBILITY = 32, /* with CULL: also enqueue the D2H copy of the bitmask + count into pinned memory,
                                          * right behind the cull (collect it with dmk_crowd_collect_visibility) */
+    DMK_STEP_ANIMATOR = 64, /* tick the device animators (dmk_crowd_set_animator) before POSE; excludes ADVANCE */
     DMK_STEP_ALL = 1 | 2 | 4 | 8
 };
 /* One frame for the whole crowd: replaces the per-entity loops SkeletalAnimationSceneComponent::update

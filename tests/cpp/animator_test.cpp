@@ -12,12 +12,15 @@
 
 #include "animator_ref.hpp"
 #include "dmk_oracle.h"
+#include "dmk.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <sstream>
 
 using namespace darmok;
@@ -285,6 +288,238 @@ static bool close(float a, float e) {
     return err <= 1e-6 || err <= 1e-5 * std::fabs((double)e);
 }
 
+
+// ---- the animator state machines themselves on the device (dmk_crowd_set_animator), straight
+// through the C ABI.  Every character is driven by its own script; each tick is compared with the oracle's RefAnimator
+// (events, error status, current state / transition and their clocks, model matrices) and with the host shim's
+// AnimatorCore (the resolved layers and pose program, bit for bit where no libm function is involved).
+#define DMK_OK_OR_FAIL(expr)                                                                              \
+    do {                                                                                                  \
+        if ((expr) != DMK_OK) { CHECK(false, "%s: %s", #expr, dmk_last_error(ctx)); return; }             \
+    } while (0)
+
+static void runDeviceAnimators(const std::string& dir, const OracleAssets& o, const SkeletalAnimatorDefinition& def, const orc::AnimatorDef& rdef) {
+    dmk_context_t ctx = nullptr;
+    if (dmk_context_create(0, nullptr, &ctx) != DMK_OK) { CHECK(false, "context"); return; }
+    dmk_skeleton_t skel = nullptr;
+    auto skelBytes = readFile(dir + "/skeleton.ozz");
+    DMK_OK_OR_FAIL(dmk_skeleton_load_ozz(ctx, skelBytes.data(), skelBytes.size(), &skel));
+    std::vector<dmk_clip_t> clips;
+    std::vector<detail::ClipInfo> clipInfo;
+    for (const auto& n : o.named) {   // clip index = position in the name-sorted table, like the shim's
+        auto bytes = readFile(dir + "/" + n.name + ".ozz");
+        dmk_clip_t clip = nullptr;
+        DMK_OK_OR_FAIL(dmk_clip_load_ozz(ctx, bytes.data(), bytes.size(), &clip));
+        clips.push_back(clip);
+        clipInfo.push_back({n.name, n.anim->duration});
+    }
+    dmk_clipset_t clipset = nullptr;
+    DMK_OK_OR_FAIL(dmk_clipset_create(ctx, skel, clips.data(), (int)clips.size(), &clipset));
+
+    // flatten the definition: names -> indices; a state without any known animation cannot be created (src/skeleton_ozz.cpp:469-485)
+    // and is left out, so play() of it is "no command"
+    std::vector<dmk_anim_state_def> dstates;
+    std::vector<dmk_anim_clip_def> dclips;
+    std::vector<dmk_anim_transition_def> dtrans;
+    std::vector<std::string> stateNames;
+    auto clipIndex = [&](const std::string& name) {
+        for (size_t i = 0; i < o.named.size(); ++i) if (o.named[i].name == name) return (int)i;
+        return -1;
+    };
+    for (const auto& s : def.states) {
+        bool any = false;
+        for (const auto& a : s.animations) any = any || clipIndex(a.name) >= 0;
+        if (any) stateNames.push_back(s.name);
+    }
+    auto stateIndex = [&](const std::string& name) {
+        for (size_t i = 0; i < stateNames.size(); ++i) if (stateNames[i] == name) return (int)i;
+        return -1;
+    };
+    for (const auto& s : def.states) {
+        if (stateIndex(s.name) < 0) continue;
+        dmk_anim_state_def d{};
+        d.first_clip = (int)dclips.size();
+        for (const auto& a : s.animations) {
+            const int ci = clipIndex(a.name);
+            if (ci < 0) continue;
+            dclips.push_back({ci, a.blend_position.x, a.blend_position.y, a.speed, a.loop ? 1 : 0});
+        }
+        d.num_clips = (int)dclips.size() - d.first_clip;
+        d.blend_type = (int)s.blend;
+        d.threshold = s.threshold;
+        d.tween_easing = (int)s.tween.easing;
+        d.tween_duration = s.tween.duration;
+        d.next_state = s.next_state.empty() ? -1 : stateIndex(s.next_state);
+        d.speed = s.speed;
+        dstates.push_back(d);
+    }
+    for (const auto& t : def.transitions)
+        dtrans.push_back({t.src_state.empty() ? -1 : stateIndex(t.src_state), t.dst_state.empty() ? -1 : stateIndex(t.dst_state), (int)t.tween.easing,
+                          t.tween.duration, t.offset});
+
+    const int64_t n = 330;
+    const int J = o.skel->num_joints, L = 18;
+    dmk_crowd_t crowd = nullptr;
+    DMK_OK_OR_FAIL(dmk_crowd_create(ctx, skel, clipset, nullptr, nullptr, n, L, &crowd));
+    DMK_OK_OR_FAIL(dmk_crowd_enable_outputs(crowd, DMK_OUT_MODELS));
+    CHECK(dmk_crowd_step(crowd, 0.f, DMK_STEP_ANIMATOR) == DMK_ERR_INVALID, "animator step before dmk_crowd_set_animator must fail");
+    {   // a crowd too small for a transition between two 9-clip states is refused
+        dmk_crowd_t small = nullptr;
+        DMK_OK_OR_FAIL(dmk_crowd_create(ctx, skel, clipset, nullptr, nullptr, 4, 9, &small));
+        CHECK(dmk_crowd_set_animator(small, dstates.data(), (int)dstates.size(), dclips.data(), (int)dclips.size(), dtrans.data(), (int)dtrans.size()) == DMK_ERR_INVALID,
+              "max_layers < 2 * clips per state must be refused");
+        dmk_crowd_destroy(small);
+    }
+    DMK_OK_OR_FAIL(dmk_crowd_set_animator(crowd, dstates.data(), (int)dstates.size(), dclips.data(), (int)dclips.size(), dtrans.data(), (int)dtrans.size()));
+    DMK_OK_OR_FAIL(dmk_crowd_step(crowd, 0.f, DMK_STEP_ANIMATOR | DMK_STEP_POSE));   // all stopped: every program is SKIP
+
+    std::vector<std::unique_ptr<orc::RefAnimator>> refs;
+    std::vector<std::unique_ptr<detail::AnimatorCore>> cores;
+    std::vector<std::vector<std::string>> devEvents((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        refs.push_back(std::make_unique<orc::RefAnimator>(o.skel, o.named, rdef));
+        cores.push_back(std::make_unique<detail::AnimatorCore>(clipInfo, def));
+    }
+    const char* names[] = {"locomotion", "talk", "strafe", "greet"};
+    std::vector<int32_t> cmd((size_t)n), status((size_t)n), dstate((size_t)n), dtransition((size_t)n);
+    std::vector<float> cmdSpeed((size_t)n), blend((size_t)n * 2, 0.f), speed((size_t)n, 1.f), stateTime((size_t)n), transTime((size_t)n);
+    std::vector<dmk_anim_events> ev((size_t)n);
+    std::vector<int32_t> lclip((size_t)L * n);
+    std::vector<float> lratio((size_t)L * n), lweight((size_t)L * n), models((size_t)n * J * 16);
+    std::vector<dmk_pose_program> prog((size_t)n);
+    long exactWeights = 0, closeWeights = 0, transitionsSeen = 0, errorsSeen = 0, blendsSeen = 0, matricesChecked = 0, eventsSeen = 0;
+    const float dt = 1 / 30.f;
+    for (int frame = 0; frame < 64; ++frame) {
+        bool anyCmd = false, inputs = false;
+        for (int64_t i = 0; i < n; ++i) {
+            cmd[i] = DMK_ANIM_NONE;
+            cmdSpeed[i] = 1.f;
+            auto play = [&](const std::string& name, float sp) {
+                cmd[i] = stateIndex(name) >= 0 ? stateIndex(name) : DMK_ANIM_NONE;
+                cmdSpeed[i] = sp;
+                refs[i]->play(name, sp);
+                cores[i]->play(name, sp);
+                anyCmd = true;
+            };
+            if (frame == (int)(i % 7)) play(names[i % 4], 1.f);
+            else if (frame == 20 + (int)(i % 5)) play(names[(i + 1) % 4], 1.f);
+            else if (frame == 27 && i % 11 == 0) play(names[(i + 1) % 4], 2.f);   // same state again: only its speed changes
+            else if (frame == 36 + (int)(i % 3) && i % 6 == 0) { cmd[i] = DMK_ANIM_STOP; refs[i]->stop(); cores[i]->stop(); anyCmd = true; }
+            else if (frame == 44 && i % 4 == 1) play("broken", 1.f);              // threshold 0: "error in the blending job"
+            else if (frame == 50 && i % 4 == 1) play("talk", 1.f);
+            else if (frame == 46 && i % 9 == 2) play("no_such_state", 1.f);       // C16: nothing happens
+            if (frame % 10 == (int)(i % 10)) {
+                const float bx = std::sin(0.1f * (float)(i + frame)), by = std::cos(0.07f * (float)(i * 3 + frame));
+                blend[2 * i] = (i % 13 == 5) ? 1.f : bx;    // some land exactly on a clip's blend position after the tween
+                blend[2 * i + 1] = (i % 13 == 5) ? 0.f : by;
+                refs[i]->setBlendPosition({blend[2 * i], blend[2 * i + 1]});
+                cores[i]->setBlendPosition(glm::vec2(blend[2 * i], blend[2 * i + 1]));
+                inputs = true;
+            }
+            if (frame == 15 && i % 3 == 0) {
+                speed[i] = 0.5f + 0.25f * (float)(i % 5);
+                refs[i]->setPlaybackSpeed(speed[i]);
+                cores[i]->setPlaybackSpeed(speed[i]);
+                inputs = true;
+            }
+        }
+        if (anyCmd) DMK_OK_OR_FAIL(dmk_crowd_animator_commands(crowd, cmd.data(), cmdSpeed.data()));
+        if (inputs) DMK_OK_OR_FAIL(dmk_crowd_animator_set_inputs(crowd, blend.data(), speed.data()));
+        DMK_OK_OR_FAIL(dmk_crowd_step(crowd, dt, DMK_STEP_ANIMATOR | DMK_STEP_POSE));
+        DMK_OK_OR_FAIL(dmk_crowd_get_animator_events(crowd, ev.data(), status.data()));
+        DMK_OK_OR_FAIL(dmk_crowd_get_animator_state(crowd, dstate.data(), stateTime.data(), dtransition.data(), transTime.data()));
+        DMK_OK_OR_FAIL(dmk_crowd_get_programs(crowd, L, lclip.data(), lratio.data(), lweight.data(), prog.data()));
+        const bool readMatrices = frame % 6 == 5 || frame == 63;
+        if (readMatrices) DMK_OK_OR_FAIL(dmk_crowd_get_models(crowd, 0, n, models.data()));
+        for (int64_t i = 0; i < n; ++i) {
+            std::string err;
+            const bool refOk = refs[i]->update(dt, err);
+            const bool active = cores[i]->hasActiveStateOrTransition();
+            detail::PoseRequest req;
+            const auto r = cores[i]->update(dt, req);
+            if (r && active) cores[i]->afterUpdate();
+            CHECK(refOk == (status[i] == 0), "frame %d animator %ld: status %d, reference ok=%d (%s)", frame, (long)i, status[i], (int)refOk, err.c_str());
+            errorsSeen += !refOk;
+            // listener events in the reference's order
+            auto& log = devEvents[(size_t)i];
+            const dmk_anim_events& e = ev[(size_t)i];
+            if (e.cmd_started >= 0) log.push_back("started:" + stateNames[(size_t)e.cmd_started]);
+            if (e.cmd_transition_started) log.push_back("transition_started");
+            if (e.transition_finished) { log.push_back("transition_finished"); log.push_back("finished:" + stateNames[(size_t)e.prev_finished]); }
+            if (e.looped >= 0) log.push_back("looped:" + stateNames[(size_t)e.looped]);
+            if (e.finished >= 0) log.push_back("finished:" + stateNames[(size_t)e.finished]);
+            if (e.auto_started >= 0) log.push_back("started:" + stateNames[(size_t)e.auto_started]);
+            if (e.auto_transition_started) log.push_back("transition_started");
+            CHECK(log == refs[i]->events, "frame %d animator %ld: listener events differ (%zu vs %zu)", frame, (long)i, log.size(), refs[i]->events.size());
+            // current state / transition and their clocks (exact: only +, *, /, fmod)
+            const auto* rs = refs[i]->currentState();
+            CHECK((rs != nullptr) == (dstate[i] >= 0), "frame %d animator %ld: current state presence", frame, (long)i);
+            if (rs && dstate[i] >= 0) {
+                CHECK(stateNames[(size_t)dstate[i]] == rs->getName(), "frame %d animator %ld: state %s vs %s", frame, (long)i, stateNames[(size_t)dstate[i]].c_str(), rs->getName().c_str());
+                CHECK(stateTime[i] == rs->getNormalizedTime(), "frame %d animator %ld: state clock %.9g vs %.9g", frame, (long)i, stateTime[i], rs->getNormalizedTime());
+            }
+            const auto* rt = refs[i]->currentTransition();
+            CHECK((rt != nullptr) == (dtransition[i] >= 0), "frame %d animator %ld: transition presence", frame, (long)i);
+            if (rt && dtransition[i] >= 0) CHECK(transTime[i] == rt->getNormalizedTime(), "frame %d animator %ld: transition clock", frame, (long)i);
+            // resolved program against the host shim's PoseRequest
+            const dmk_pose_program& g = prog[(size_t)i];
+            if (!r || !active || req.top == detail::PoseRequest::Skip) {
+                CHECK(g.top == DMK_TOP_SKIP, "frame %d animator %ld: program top %d, expected SKIP", frame, (long)i, g.top);
+            } else {
+                const bool tr = req.top == detail::PoseRequest::Transition;
+                transitionsSeen += tr;
+                CHECK(g.top == (tr ? DMK_TOP_TRANSITION : DMK_TOP_GROUP0), "frame %d animator %ld: program top %d", frame, (long)i, g.top);
+                int row = 0;
+                for (int k = 0; k < (tr ? 2 : 1); ++k) {
+                    const detail::GroupRequest& gr = k ? req.group1 : req.group0;
+                    const int cnt = k ? g.num_layers1 : g.num_layers0, rest = k ? g.rest1 : g.rest0, mode = k ? g.mode1 : g.mode0;
+                    const float th = k ? g.threshold1 : g.threshold0;
+                    CHECK(cnt == (int)gr.layers.size() && rest == gr.rest && mode == (gr.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND) && th == gr.threshold,
+                          "frame %d animator %ld group %d: count %d/%zu rest %d/%d mode %d", frame, (long)i, k, cnt, gr.layers.size(), rest, gr.rest, mode);
+                    blendsSeen += !gr.passthrough;
+                    for (size_t l = 0; l < gr.layers.size() && (int)l < cnt; ++l, ++row) {
+                        const size_t at = (size_t)row * n + i;
+                        CHECK(lclip[at] == gr.layers[l].clip, "frame %d animator %ld row %d: clip %d vs %d", frame, (long)i, row, lclip[at], gr.layers[l].clip);
+                        CHECK(lratio[at] == gr.layers[l].ratio, "frame %d animator %ld row %d: ratio %.9g vs %.9g", frame, (long)i, row, lratio[at], gr.layers[l].ratio);
+                        if (gr.passthrough) continue;
+                        if (lweight[at] == gr.layers[l].weight) ++exactWeights;
+                        else {
+                            ++closeWeights;
+                            CHECK(std::fabs(lweight[at] - gr.layers[l].weight) <= 2e-6f * std::fmax(1.f, std::fabs(gr.layers[l].weight)),
+                                  "frame %d animator %ld row %d: weight %.9g vs %.9g", frame, (long)i, row, lweight[at], gr.layers[l].weight);
+                        }
+                    }
+                }
+                if (tr) CHECK(std::fabs(g.weight0 - req.w0) <= 1e-6f && std::fabs(g.weight1 - req.w1) <= 1e-6f, "frame %d animator %ld: transition weights %.9g/%.9g vs %.9g/%.9g",
+                              frame, (long)i, g.weight0, g.weight1, req.w0, req.w1);
+            }
+            // model matrices against the reference animator
+            if (readMatrices && i % 3 == 0) {
+                const float* m = &models[(size_t)i * J * 16];
+                const float* e16 = refs[i]->models().data();
+                bool everPosed = false;
+                for (const auto& s : refs[i]->events) everPosed = everPosed || s.rfind("started:", 0) == 0;
+                if (!everPosed) continue;   // the reference shows its load-time rest pose; the raw crowd has not been told to
+                float flipped[16];   // dmk_crowd_get_models hands out what getJointModelMatrix does: OzzUtils::convert's left-handed matrix
+                for (int j = 0; j < J; ++j) {
+                    orc_flip_handedness(e16 + (size_t)j * 16, flipped);
+                    for (int x = 0; x < 16; ++x) CHECK(close(m[j * 16 + x], flipped[x]), "frame %d animator %ld joint %d element %d: %g vs %g", frame, (long)i, j, x, m[j * 16 + x], flipped[x]);
+                }
+                ++matricesChecked;
+            }
+        }
+    }
+    for (const auto& l : devEvents) eventsSeen += (long)l.size();
+    std::printf("gpu: device animators, %ld characters x 64 frames: %ld transitions, %ld blends, %ld job errors, %ld events, %ld characters' matrices; "
+                "blend weights %ld exact, %ld within 2e-6\n", (long)n, transitionsSeen, blendsSeen, errorsSeen, eventsSeen, matricesChecked, exactWeights, closeWeights);
+    CHECK(transitionsSeen > 1000 && blendsSeen > 3000 && errorsSeen > 100 && eventsSeen > 1500 && matricesChecked > 500, "device animator scenario lost coverage");
+    dmk_crowd_destroy(crowd);
+    dmk_clipset_destroy(clipset);
+    for (auto c : clips) dmk_clip_destroy(c);
+    dmk_skeleton_destroy(skel);
+    dmk_context_destroy(ctx);
+}
+
 static int runGpu(const std::string& dir) {
     OracleAssets o = loadOracle(dir);
     SkeletalAnimatorDefinition def;
@@ -436,6 +671,7 @@ static int runGpu(const std::string& dir) {
         CHECK(culled > 0 && culled < n, "cull test must see both outcomes (%d of %ld culled)", culled, (long)n);
         std::printf("gpu: scene component, %ld animators x 51 frames, %d culled\n", (long)n, culled);
     }
+    runDeviceAnimators(dir, o, def, rdef);
     std::printf("gpu: %d failures\n", g_failures);
     return g_failures ? 1 : 0;
 }

@@ -4,6 +4,8 @@
   config 1  samples/ozz single character: the oracle (reference CPU plumbing) per character tick, 9-clip locomotion blend
   config 2  10k characters, 67 joints, single looping clip, palette only, 1 GPU
   config 5  10M-instance frustum/AABB cull, visibility compared bit for bit with the oracle on a 2M-instance prefix
+  3s        config 3's skinning kernel with the opt-in vertex order
+  3a        100k device-side animators with the samples/ozz animator definition: animator kernel and pose time
 
 Prints one JSON line per config (also appended to gpurun_out/configs.jsonl)."""
 import json
@@ -171,6 +173,74 @@ def config3_sorted():
     emit({"config": "3 (skin kernel only)", "what": "100k characters x 5k vertices, mean 3.0 influences/vertex (10/20/30/40 %)", **out})
 
 
+def sample_animator(capi):
+    """samples/ozz/assets/animator.json flattened: locomotion (9 clips, Directional), talk, greet (non looping -> locomotion),
+    strafe (3 clips, Cartesian) and its transitions; clip ids 0..9"""
+    pos = [(0, 0), (0, -1), (1, -1), (-1, -1), (0, 1), (-1, 1), (1, 1), (-1, 0), (1, 0)]
+    clips = np.zeros(14, capi.ANIM_CLIP_DTYPE)
+    for i, (x, y) in enumerate(pos):
+        clips[i] = (i, x, y, 0, 1)
+    clips[9] = (9, 0, 0, 0, 1)
+    clips[10] = (9, 0, 0, 2, 0)
+    clips[11], clips[12], clips[13] = (7, -1, 0, 0, 1), (8, 1, 0, 0, 1), (4, 0, 1, 0, 1)
+    states = np.zeros(4, capi.ANIM_STATE_DTYPE)
+    states[0] = (0, 9, 1, 0.2, 0, 0.5, -1, 1.0)
+    states[1] = (9, 1, 0, 0.0, 0, 0.0, -1, 1.0)
+    states[2] = (10, 1, 0, 0.0, 0, 0.0, 0, 1.0)
+    states[3] = (11, 3, 0, 1.0, 0, 0.25, -1, 1.5)
+    tr = np.zeros(4, capi.ANIM_TRANSITION_DTYPE)
+    tr[0], tr[1], tr[2], tr[3] = (0, 1, 0, 0.5, 0.0), (1, 0, 4, 0.5, 0.1), (-1, 3, 16, 0.3, 0.0), (2, -1, 0, 0.2, 0.0)
+    return states, clips, tr
+
+
+def config3_animators():
+    import torch
+    from darmok_b200 import capi, synth
+    n = 100_000
+    skel_s = synth.make_skeleton(67)
+    clips_s = [synth.make_clip(skel_s, f"clip{i}", seed=i, duration=0.75 + 0.05 * i) for i in range(10)]
+    arm_s = synth.make_armature(skel_s)
+    rng = np.random.default_rng(7)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx = capi.Context(0, stream.cuda_stream)
+        skel = capi.Skeleton(ctx, skel_s.archive)
+        clip_objs = [capi.Clip(ctx, c.archive) for c in clips_s]
+        clips = capi.ClipSet(ctx, skel, clip_objs)
+        arm = capi.Armature(ctx, skel, arm_s.names, arm_s.inv_bind)
+        crowd = capi.Crowd(ctx, skel, clips, arm, None, n, 18)
+        crowd.set_animator(*sample_animator(capi))
+        crowd.animator_commands(rng.integers(0, 4, n).astype(np.int32))
+        crowd.animator_set_inputs(blend_xy=rng.uniform(-1, 1, (n, 2)).astype(np.float32))
+        flags = capi.STEP_ANIMATOR | capi.STEP_POSE
+        for f in range(10):
+            crowd.step(1 / 60, flags)
+        ctx.enable_kernel_timing(True)
+        ctx.reset_kernel_timing()
+        frames, h2d = 60, 0
+        t0 = time.perf_counter()
+        for f in range(frames):
+            if f % 10 == 0:   # a tenth of the crowd changes state and blend position every ten frames
+                cmd = np.where(rng.random(n) < 0.1, rng.integers(0, 4, n), capi.ANIM_NONE).astype(np.int32)
+                crowd.animator_commands(cmd)
+                crowd.animator_set_inputs(blend_xy=rng.uniform(-1, 1, (n, 2)).astype(np.float32))
+                h2d += n * 16
+            crowd.step(1 / 60, flags)
+        ctx.sync()
+        wall = (time.perf_counter() - t0) / frames
+        anim_ms, cnt = ctx.kernel_time(capi.KERNEL_ANIMATOR)
+        pose_ms, pcnt = ctx.kernel_time(capi.KERNEL_POSE)
+        clip, ratio, weight, prog = crowd.programs(18)
+        layers = float((prog["n0"].astype(int) + prog["n1"]).mean())
+        in_transition = float((prog["top"] == capi.TOP_TRANSITION).mean())
+    emit({"config": "3a (device animators)", "what": "100k SkeletalAnimators of the samples/ozz definition ticked on the GPU, then sampled/blended/concatenated",
+          "animator_kernel_us": anim_ms / cnt * 1e3, "animator_state_bytes_per_character": 336,
+          "animator_GBps": n * (2 * 336 + 16 + 24 + layers * 12) / (anim_ms / cnt * 1e-3) / 1e9,
+          "pose_ms": pose_ms / pcnt, "mean_layers_per_character": layers, "fraction_in_transition": in_transition,
+          "wall_ms_per_frame_with_host_calls": wall * 1e3, "h2d_bytes_per_frame": h2d / frames,
+          "note": "per frame only commands / blend positions cross the bus; the host-resolved path uploads 3 x 4 B x layers + 24 B per character"})
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["1", "2", "5"]
     if "1" in which:
@@ -181,3 +251,5 @@ if __name__ == "__main__":
         config5()
     if "3s" in which:
         config3_sorted()
+    if "3a" in which:
+        config3_animators()
