@@ -30,6 +30,8 @@ ANIM_CLIP_DTYPE = np.dtype([("clip", "i4"), ("blend_x", "f4"), ("blend_y", "f4")
 ANIM_STATE_DTYPE = np.dtype([("first_clip", "i4"), ("num_clips", "i4"), ("blend_type", "i4"), ("threshold", "f4"), ("tween_easing", "i4"),
                              ("tween_duration", "f4"), ("next_state", "i4"), ("speed", "f4")])
 ANIM_TRANSITION_DTYPE = np.dtype([("src_state", "i4"), ("dst_state", "i4"), ("easing", "i4"), ("duration", "f4"), ("offset", "f4")])
+ANIM_STATE_INFO_DTYPE = np.dtype([("state", "i4"), ("transition", "i4"), ("previous_state", "i4"), ("state_time", "f4"),
+                                  ("transition_time", "f4"), ("previous_time", "f4"), ("state_speed", "f4"), ("previous_speed", "f4")])
 ANIM_EVENTS_DTYPE = np.dtype([("cmd_started", "i2"), ("cmd_transition_started", "i2"), ("transition_finished", "i2"), ("prev_finished", "i2"),
                               ("looped", "i2"), ("finished", "i2"), ("auto_started", "i2"), ("auto_transition_started", "i2")])
 
@@ -80,7 +82,7 @@ SIGNATURES = [
     ("dmk_crowd_animator_commands", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_animator_set_inputs", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_get_animator_events", _i, [_vp, _vp, _vp]),
-    ("dmk_crowd_get_animator_state", _i, [_vp, _vp, _vp, _vp, _vp]),
+    ("dmk_crowd_get_animator_state", _i, [_vp, _vp]),
     ("dmk_crowd_get_programs", _i, [_vp, _i, _vp, _vp, _vp, _vp]),
     ("dmk_crowd_set_instances", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_set_transforms", _i, [_vp, _vp, _vp, _vp, _vp]),
@@ -359,10 +361,10 @@ class Crowd:
         return ev, status
 
     def animator_state(self):
-        state, trans = np.empty(self.n, np.int32), np.empty(self.n, np.int32)
-        st, tt = np.empty(self.n, np.float32), np.empty(self.n, np.float32)
-        self.ctx.check(lib().dmk_crowd_get_animator_state(self.h, _ptr(state), _ptr(st), _ptr(trans), _ptr(tt)))
-        return state, st, trans, tt
+        """structured array of ANIM_STATE_INFO_DTYPE, one per character"""
+        info = np.empty(self.n, ANIM_STATE_INFO_DTYPE)
+        self.ctx.check(lib().dmk_crowd_get_animator_state(self.h, _ptr(info)))
+        return info
 
     def programs(self, num_layers):
         clip = np.empty((num_layers, self.n), np.int32)

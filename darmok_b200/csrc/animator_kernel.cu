@@ -330,16 +330,22 @@ __global__ void __launch_bounds__(128) animator_kernel(const AnimatorParams p) {
     p.status[c] = status;
 }
 
-__global__ void animator_query_kernel(const AnimatorParams p, int32_t* state, float* state_time, int32_t* transition, float* transition_time) {
+__global__ void animator_query_kernel(const AnimatorParams p, AnimStateInfo* out) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.n) return;
     const int t = p.transition_def[c];
     const Slot s = slot_of(p, t >= 0 ? kSlotCur : kSlotState, c);   // getCurrentState (src/skeleton_ozz.cpp:867-878)
-    const int def = s.geti(kWDef);
-    state[c] = def;
-    state_time[c] = def >= 0 ? s.getf(kWNormalizedTime) : 0.f;
-    transition[c] = t;
-    transition_time[c] = t >= 0 ? p.transition_time[c] : 0.f;
+    const Slot pv = slot_of(p, kSlotPrev, c);
+    AnimStateInfo o;
+    o.state = s.geti(kWDef);
+    o.transition = t;
+    o.previous_state = t >= 0 ? pv.geti(kWDef) : -1;
+    o.state_time = o.state >= 0 ? s.getf(kWNormalizedTime) : 0.f;
+    o.transition_time = t >= 0 ? p.transition_time[c] : 0.f;
+    o.previous_time = t >= 0 ? pv.getf(kWNormalizedTime) : 0.f;
+    o.state_speed = o.state >= 0 ? s.getf(kWSpeed) : 0.f;
+    o.previous_speed = t >= 0 ? pv.getf(kWSpeed) : 0.f;
+    out[c] = o;
 }
 
 __global__ void animator_init_kernel(const AnimatorParams p, float* cmd_speed, float* in_blend, float* in_speed) {
@@ -362,10 +368,9 @@ cudaError_t launch_animator_init(const AnimatorParams& p, float* cmd_speed, floa
     return cudaGetLastError();
 }
 
-cudaError_t launch_animator_query(const AnimatorParams& p, int32_t* state, float* state_time, int32_t* transition, float* transition_time,
-                                  cudaStream_t stream) {
+cudaError_t launch_animator_query(const AnimatorParams& p, AnimStateInfo* out, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    animator_query_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(p, state, state_time, transition, transition_time);
+    animator_query_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(p, out);
     return cudaGetLastError();
 }
 

@@ -145,6 +145,7 @@ struct dmk_crowd_s {
     int32_t* d_anim_transition = nullptr;
     float* d_anim_transition_time = nullptr;
     AnimEvents* d_anim_events = nullptr;
+    AnimStateInfo* d_anim_info = nullptr;
     int32_t *d_anim_cmd = nullptr, *d_anim_status = nullptr;
     float *d_anim_cmd_speed = nullptr, *d_anim_blend = nullptr, *d_anim_speed = nullptr;
     int anim_num_states = 0, anim_num_transitions = 0, anim_layers = 0;
@@ -759,7 +760,7 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
                     (void*)c->d_key_indices, (void*)c->d_error, (void*)c->d_world_inverse, (void*)c->d_bbox, (void*)c->d_position, (void*)c->d_rotation, (void*)c->d_scale, (void*)c->d_vis_bits,
                     (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch, (void*)c->d_anim_states, (void*)c->d_anim_clips,
                     (void*)c->d_anim_transitions, (void*)c->d_anim_tables, (void*)c->d_anim_slots, (void*)c->d_anim_transition,
-                    (void*)c->d_anim_transition_time, (void*)c->d_anim_events, (void*)c->d_anim_cmd, (void*)c->d_anim_status,
+                    (void*)c->d_anim_transition_time, (void*)c->d_anim_events, (void*)c->d_anim_info, (void*)c->d_anim_cmd, (void*)c->d_anim_status,
                     (void*)c->d_anim_cmd_speed, (void*)c->d_anim_blend, (void*)c->d_anim_speed})
         dev_free(p);
     for (int b = 0; b < 2; ++b) {
@@ -1103,24 +1104,19 @@ dmk_status dmk_crowd_get_animator_events(dmk_crowd_t c, dmk_anim_events* out_eve
     return DMK_OK;
 }
 
-dmk_status dmk_crowd_get_animator_state(dmk_crowd_t c, int32_t* out_state, float* out_state_time, int32_t* out_transition,
-                                        float* out_transition_time) {
+dmk_status dmk_crowd_get_animator_state(dmk_crowd_t c, dmk_anim_state* out_states) {
     if (!c) return DMK_ERR_INVALID;
     dmk_context_t ctx = c->ctx;
+    static_assert(sizeof(dmk_anim_state) == sizeof(AnimStateInfo), "C ABI struct and device struct must match");
     if (!c->animator_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_animator has not been called");
+    if (!out_states) return fail(ctx, DMK_ERR_INVALID, "null output");
     if (bind(ctx)) return DMK_ERR_CUDA;
     const size_t n = static_cast<size_t>(c->n);
-    int32_t* d = nullptr;   // 4 arrays of n words
-    DMK_CUDA(ctx, dev_alloc(&d, 4 * n));
-    cudaError_t e = launch_animator_query(animator_params(c, 0.f), d, reinterpret_cast<float*>(d + n), d + 2 * n, reinterpret_cast<float*>(d + 3 * n),
-                                          ctx->stream);
+    if (!c->d_anim_info) DMK_CUDA(ctx, dev_alloc(&c->d_anim_info, n));
+    DMK_CUDA(ctx, launch_animator_query(animator_params(c, 0.f), c->d_anim_info, ctx->stream));
     ++ctx->launches;
-    void* outs[4] = {out_state, out_state_time, out_transition, out_transition_time};
-    for (int k = 0; k < 4 && e == cudaSuccess; ++k)
-        if (outs[k]) e = cudaMemcpyAsync(outs[k], d + k * n, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    dev_free(d);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "animator state query");
+    DMK_CUDA(ctx, cudaMemcpyAsync(out_states, c->d_anim_info, n * sizeof(AnimStateInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DMK_OK;
 }
 

@@ -169,6 +169,10 @@ enum AnimSlotWord {
     kWClipTime,       // kMaxStateClips floats
     kSlotWords = kWClipTime + kMaxStateClips
 };
+struct AnimStateInfo {        // = dmk_anim_state
+    int32_t state, transition, previous_state;
+    float state_time, transition_time, previous_time, state_speed, previous_speed;
+};
 struct AnimEvents {          // listener events of one tick, in the reference's order (src/skeleton_ozz.cpp:783-856, 1044-1087)
     int16_t cmd_started;     // play() command: onAnimatorStateStarted(state), -1 = none
     int16_t cmd_transition_started;

@@ -37,7 +37,6 @@ cudaError_t launch_pack_palettes(const float* palette, int palette_floats, const
 namespace dmk {
 // device-side animator state machine (animator_kernel.cu, built with -fmad=false)
 cudaError_t launch_animator_init(const AnimatorParams& p, float* cmd_speed, float* in_blend, float* in_speed, cudaStream_t stream);
-cudaError_t launch_animator_query(const AnimatorParams& p, int32_t* state, float* state_time, int32_t* transition, float* transition_time,
-                                  cudaStream_t stream);
+cudaError_t launch_animator_query(const AnimatorParams& p, AnimStateInfo* out, cudaStream_t stream);
 cudaError_t launch_animator(const AnimatorParams& p, cudaStream_t stream);
 }  // namespace dmk

@@ -115,6 +115,7 @@ public:
     bool play(std::string_view name, float stateSpeed = 1.f) noexcept;
     void stop() noexcept { _state.reset(); }
     void pause() noexcept { _paused = !_paused; }
+    bool isPaused() const noexcept { return _paused; }
     SkeletalAnimatorPlaybackState getPlaybackState() const noexcept;
     void setPlaybackSpeed(float speed) noexcept { _speed = speed; }
     float getPlaybackSpeed() const noexcept { return _speed; }

@@ -265,8 +265,21 @@ private:
     std::optional<SkinnedMeshData> _mesh;
     mutable std::vector<glm::mat4> _modelsCache;
     mutable bool _modelsValid = false;
+    mutable uint64_t _modelsFrame = 0;
     expected<void, std::string> ensureDevice() noexcept;
+    // AnimatorExecution::Device: the state machine lives on the GPU; these mirror what was read back last
+    struct DeviceViews;
+    mutable std::unique_ptr<DeviceViews> _views;
+    bool onDevice() const noexcept;
 };
+
+// Where the animators of a SkeletalAnimationSceneComponent tick.
+//   Host    every SkeletalAnimator's state machine runs on the CPU each frame (animator_core.cpp) and the resolved pose
+//           programs are uploaded: exact reference semantics call by call.
+//   Device  the state machines run in one kernel (dmk_crowd_set_animator); play() / stop() /
+//           setBlendPosition() / setPlaybackSpeed() are queued and take effect at the next update(), one command per
+//           animator and frame (the last one wins); listener events of a frame are delivered at the end of update().
+enum class AnimatorExecution { Host, Device };
 
 // Batched replacement of SkeletalAnimationSceneComponent::update (src/skeleton.cpp:159-184), FrustumCuller
 // (src/culling.cpp:258-290) and SkeletalAnimationRenderComponent (src/skeleton.cpp:223-251) for animators that share
@@ -278,7 +291,7 @@ public:
     ~SkeletalAnimationSceneComponent() noexcept;
 
     // creates the animators (entities); must be called once before update()
-    expected<void, std::string> init(int64_t numAnimators) noexcept;
+    expected<void, std::string> init(int64_t numAnimators, AnimatorExecution execution = AnimatorExecution::Host) noexcept;
     SkeletalAnimator& getAnimator(int64_t index) noexcept;
     int64_t size() const noexcept;
 

@@ -199,6 +199,68 @@ struct SkeletalAnimator::Device {
     }
 };
 
+// ---- SkeletalAnimationSceneComponent state (declared early: device-executed animators route through it) ------------------
+struct SkeletalAnimationSceneComponent::Impl {
+    std::shared_ptr<Skeleton> skeleton;
+    SkeletalAnimator::AnimationMap anims;
+    SkeletalAnimator::Definition def;
+    std::shared_ptr<Armature> armature;
+    std::optional<SkinnedMeshData> mesh;
+    std::unique_ptr<SkeletalAnimator::Device> device;
+    std::vector<std::unique_ptr<SkeletalAnimator>> animators;
+    std::vector<detail::PoseRequest> requests;
+    std::vector<char> active;
+    uint64_t frame = 0;   // bumped by every update(): invalidates the animators' cached matrices
+
+    // AnimatorExecution::Device
+    bool deviceAnimators = false;
+    std::vector<std::string> stateNames;   // device state index -> name (states that can be created, in definition order)
+    std::vector<float> stateDuration;      // calcDuration of each (without the state speed)
+    std::vector<float> transitionDuration;
+    std::vector<int32_t> cmd;
+    std::vector<float> cmdSpeed, blend, speed;
+    bool cmdDirty = false, inputsDirty = false;
+    std::vector<dmk_anim_state> info;
+    bool infoValid = false;
+    std::vector<dmk_anim_events> events;
+    std::vector<int32_t> status;
+
+    int stateIndex(std::string_view name) const noexcept {
+        for (size_t i = 0; i < stateNames.size(); ++i)
+            if (stateNames[i] == name) return static_cast<int>(i);
+        return -1;
+    }
+    const dmk_anim_state* stateOf(int64_t index) noexcept {
+        if (!infoValid) {
+            info.resize(static_cast<size_t>(device->n));
+            if (dmk_crowd_get_animator_state(device->crowd, info.data()) != DMK_OK) return nullptr;
+            infoValid = true;
+        }
+        return &info[static_cast<size_t>(index)];
+    }
+    expected<void, std::string> setupDeviceAnimators() noexcept;
+};
+
+struct SkeletalAnimator::DeviceViews {
+    struct State final : ISkeletalAnimatorState {
+        std::string name;
+        float time = 0.f, duration = 0.f;
+        float getNormalizedTime() const override { return time; }
+        float getDuration() const override { return duration; }
+        std::string_view getName() const override { return name; }
+    };
+    struct Transition final : ISkeletalAnimatorTransition {
+        State current, previous;
+        float time = 0.f, duration = 0.f;
+        float getNormalizedTime() const override { return time; }
+        float getDuration() const override { return duration; }
+        const ISkeletalAnimatorState& getCurrentState() const override { return current; }
+        const ISkeletalAnimatorState& getPreviousState() const override { return previous; }
+    };
+    State state;
+    Transition transition;
+};
+
 // ---- SkeletalAnimator ---------------------------------------------------------------------------------------------------
 namespace {
 struct ListenerSet {
@@ -264,18 +326,85 @@ bool SkeletalAnimator::removeListener(const ISkeletalAnimatorListener& listener)
     return all.size() != before;
 }
 
-SkeletalAnimator& SkeletalAnimator::setPlaybackSpeed(float speed) noexcept { _core->setPlaybackSpeed(speed); return *this; }
+bool SkeletalAnimator::onDevice() const noexcept { return _batch && _batch->_impl->deviceAnimators; }
+
+SkeletalAnimator& SkeletalAnimator::setPlaybackSpeed(float speed) noexcept {
+    _core->setPlaybackSpeed(speed);
+    if (onDevice()) {
+        _batch->_impl->speed[static_cast<size_t>(_batchIndex)] = speed;
+        _batch->_impl->inputsDirty = true;
+    }
+    return *this;
+}
 float SkeletalAnimator::getPlaybackSpeed() const noexcept { return _core->getPlaybackSpeed(); }
-SkeletalAnimator& SkeletalAnimator::setBlendPosition(const glm::vec2& value) noexcept { _core->setBlendPosition(value); return *this; }
+SkeletalAnimator& SkeletalAnimator::setBlendPosition(const glm::vec2& value) noexcept {
+    _core->setBlendPosition(value);
+    if (onDevice()) {
+        _batch->_impl->blend[static_cast<size_t>(_batchIndex) * 2] = value.x;
+        _batch->_impl->blend[static_cast<size_t>(_batchIndex) * 2 + 1] = value.y;
+        _batch->_impl->inputsDirty = true;
+    }
+    return *this;
+}
 const glm::vec2& SkeletalAnimator::getBlendPosition() const noexcept { return _core->getBlendPosition(); }
 const SkeletalAnimator::Definition& SkeletalAnimator::getDefinition() const noexcept { return _core->getDefinition(); }
-const ISkeletalAnimatorState* SkeletalAnimator::getCurrentState() const noexcept { return _core->getCurrentState(); }
-const ISkeletalAnimatorTransition* SkeletalAnimator::getCurrentTransition() const noexcept { return _core->getCurrentTransition(); }
+const ISkeletalAnimatorState* SkeletalAnimator::getCurrentState() const noexcept {
+    if (!onDevice()) return _core->getCurrentState();
+    auto& im = *_batch->_impl;
+    const dmk_anim_state* st = im.stateOf(_batchIndex);
+    if (!st || st->state < 0) return nullptr;
+    if (!_views) _views = std::make_unique<DeviceViews>();
+    auto& v = _views->state;
+    v.name = im.stateNames[static_cast<size_t>(st->state)];
+    v.time = st->state_time;
+    v.duration = im.stateDuration[static_cast<size_t>(st->state)] * st->state_speed;   // multiplies (C2)
+    return &v;
+}
+const ISkeletalAnimatorTransition* SkeletalAnimator::getCurrentTransition() const noexcept {
+    if (!onDevice()) return _core->getCurrentTransition();
+    auto& im = *_batch->_impl;
+    const dmk_anim_state* st = im.stateOf(_batchIndex);
+    if (!st || st->transition < 0) return nullptr;
+    if (!_views) _views = std::make_unique<DeviceViews>();
+    auto& t = _views->transition;
+    t.time = st->transition_time;
+    t.duration = im.transitionDuration[static_cast<size_t>(st->transition)];
+    t.current.name = im.stateNames[static_cast<size_t>(st->state)];
+    t.current.time = st->state_time;
+    t.current.duration = im.stateDuration[static_cast<size_t>(st->state)] * st->state_speed;
+    t.previous.name = im.stateNames[static_cast<size_t>(st->previous_state)];
+    t.previous.time = st->previous_time;
+    t.previous.duration = im.stateDuration[static_cast<size_t>(st->previous_state)] * st->previous_speed;
+    return &t;
+}
 float SkeletalAnimator::getStateDuration(const std::string& name) const noexcept { return _core->getStateDuration(name); }
-bool SkeletalAnimator::play(std::string_view name, float speedFactor) noexcept { return _core->play(name, speedFactor); }
-void SkeletalAnimator::stop() noexcept { _core->stop(); }
+bool SkeletalAnimator::play(std::string_view name, float speedFactor) noexcept {
+    if (!onDevice()) return _core->play(name, speedFactor);
+    auto& im = *_batch->_impl;
+    const int state = im.stateIndex(name);
+    if (state < 0) return false;   // unknown state (C16), or one without a known animation
+    const size_t i = static_cast<size_t>(_batchIndex);
+    int current = im.cmd[i] >= 0 ? im.cmd[i] : -1;   // a command queued this frame counts as the state being played
+    if (current < 0)
+        if (const dmk_anim_state* st = im.stateOf(_batchIndex)) current = (im.cmd[i] == DMK_ANIM_STOP && st->transition < 0) ? -1 : st->state;
+    im.cmd[i] = state;
+    im.cmdSpeed[i] = speedFactor;
+    im.cmdDirty = true;
+    return current != state;   // playing the current state again only changes its speed and returns false (:789-794)
+}
+void SkeletalAnimator::stop() noexcept {
+    if (!onDevice()) return _core->stop();
+    _batch->_impl->cmd[static_cast<size_t>(_batchIndex)] = DMK_ANIM_STOP;
+    _batch->_impl->cmdDirty = true;
+}
 void SkeletalAnimator::pause() noexcept { _core->pause(); }
-SkeletalAnimator::PlaybackState SkeletalAnimator::getPlaybackState() noexcept { return _core->getPlaybackState(); }
+SkeletalAnimator::PlaybackState SkeletalAnimator::getPlaybackState() noexcept {
+    if (!onDevice()) return _core->getPlaybackState();
+    // src/skeleton_ozz.cpp:880-889: Stopped without _state -- which is also the case while a transition runs (C10)
+    const dmk_anim_state* st = _batch->_impl->stateOf(_batchIndex);
+    if (!st || st->transition >= 0 || st->state < 0) return PlaybackState::Stopped;
+    return _core->isPaused() ? PlaybackState::Paused : PlaybackState::Playing;
+}
 
 expected<void, std::string> SkeletalAnimator::setSkinning(const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh) noexcept {
     if (_device || _batch) return unexpected<std::string>{"setSkinning must be called before the first update"};
@@ -320,7 +449,9 @@ glm::mat4 SkeletalAnimator::getJointModelMatrix(const std::string& node) const n
     if (!_batch && !_device && !const_cast<SkeletalAnimator*>(this)->ensureDevice()) return glm::mat4(1.f);
     dmk_crowd_t crowd = _batch ? _batch->crowd() : _device->crowd;
     if (!crowd) return glm::mat4(1.f);
+    if (_batch && _modelsFrame != _batch->_impl->frame) _modelsValid = false;
     if (!_modelsValid) {
+        if (_batch) _modelsFrame = _batch->_impl->frame;
         _modelsCache.assign(static_cast<size_t>(_skeleton->getNumJoints()), glm::mat4(1.f));
         if (dmk_crowd_get_models(crowd, _batch ? _batchIndex : 0, 1, glm::value_ptr(_modelsCache[0])) != DMK_OK) return glm::mat4(1.f);
         _modelsValid = true;
@@ -348,18 +479,6 @@ std::vector<float> SkeletalAnimator::getSkinnedVertices() const noexcept {
 }
 
 // ---- SkeletalAnimationSceneComponent (batched) ----------------------------------------------------------------------------
-struct SkeletalAnimationSceneComponent::Impl {
-    std::shared_ptr<Skeleton> skeleton;
-    SkeletalAnimator::AnimationMap anims;
-    SkeletalAnimator::Definition def;
-    std::shared_ptr<Armature> armature;
-    std::optional<SkinnedMeshData> mesh;
-    std::unique_ptr<SkeletalAnimator::Device> device;
-    std::vector<std::unique_ptr<SkeletalAnimator>> animators;
-    std::vector<detail::PoseRequest> requests;
-    std::vector<char> active;
-};
-
 SkeletalAnimationSceneComponent::SkeletalAnimationSceneComponent(std::shared_ptr<Skeleton> skel, SkeletalAnimator::AnimationMap anims,
                                                                  SkeletalAnimator::Definition def, std::shared_ptr<Armature> armature,
                                                                  const SkinnedMeshData* mesh) noexcept
@@ -372,11 +491,74 @@ SkeletalAnimationSceneComponent::SkeletalAnimationSceneComponent(std::shared_ptr
 }
 SkeletalAnimationSceneComponent::~SkeletalAnimationSceneComponent() noexcept = default;
 
-expected<void, std::string> SkeletalAnimationSceneComponent::init(int64_t numAnimators) noexcept {
+expected<void, std::string> SkeletalAnimationSceneComponent::Impl::setupDeviceAnimators() noexcept {
+    // flatten the definition: names -> indices.  Clip ids follow the device clip set (name-sorted, as Device::create
+    // builds it); animations the provider does not know are dropped and a state without any cannot be created
+    // (src/skeleton_ozz.cpp:469-485) -- such a state is left out, play() of it does nothing.
+    std::vector<std::string> clipNames;
+    for (const auto& [name, anim] : sortedClips(anims)) clipNames.push_back(name);
+    auto clipIndex = [&](const std::string& name) {
+        const auto itr = std::lower_bound(clipNames.begin(), clipNames.end(), name);
+        return itr != clipNames.end() && *itr == name ? static_cast<int>(itr - clipNames.begin()) : -1;
+    };
+    std::vector<detail::ClipInfo> clipInfo;
+    for (const auto& [name, anim] : sortedClips(anims)) clipInfo.push_back({name, anim->getDuration()});
+    const detail::AnimatorCore probe(clipInfo, def);
+    stateNames.clear();
+    for (const auto& s : def.states)
+        if (std::any_of(s.animations.begin(), s.animations.end(), [&](const auto& a) { return clipIndex(a.name) >= 0; })) stateNames.push_back(s.name);
+    std::vector<dmk_anim_state_def> states;
+    std::vector<dmk_anim_clip_def> clips;
+    std::vector<dmk_anim_transition_def> transitions;
+    stateDuration.clear();
+    for (const auto& s : def.states) {
+        if (stateIndex(s.name) < 0) continue;
+        dmk_anim_state_def d{};
+        d.first_clip = static_cast<int>(clips.size());
+        for (const auto& a : s.animations)
+            if (const int ci = clipIndex(a.name); ci >= 0) clips.push_back({ci, a.blend_position.x, a.blend_position.y, a.speed, a.loop ? 1 : 0});
+        d.num_clips = static_cast<int>(clips.size()) - d.first_clip;
+        d.blend_type = static_cast<int>(s.blend);
+        d.threshold = s.threshold;
+        d.tween_easing = static_cast<int>(s.tween.easing);
+        d.tween_duration = s.tween.duration;
+        d.next_state = s.next_state.empty() ? -1 : stateIndex(s.next_state);
+        d.speed = s.speed;
+        states.push_back(d);
+        // getStateDuration() = calcDuration * definition speed; keep calcDuration alone
+        stateDuration.push_back(s.speed != 0.f ? probe.getStateDuration(s.name) / s.speed : 0.f);
+    }
+    transitionDuration.clear();
+    for (const auto& t : def.transitions) {
+        // a transition naming a state that cannot exist can never match
+        const int src = t.src_state.empty() ? -1 : stateIndex(t.src_state), dst = t.dst_state.empty() ? -1 : stateIndex(t.dst_state);
+        if ((!t.src_state.empty() && src < 0) || (!t.dst_state.empty() && dst < 0)) continue;
+        transitions.push_back({src, dst, static_cast<int>(t.tween.easing), t.tween.duration, t.offset});
+        transitionDuration.push_back(t.tween.duration);
+    }
+    if (states.empty()) return unexpected<std::string>{"the animator definition has no state with a known animation"};
+    if (dmk_crowd_set_animator(device->crowd, states.data(), static_cast<int>(states.size()), clips.data(), static_cast<int>(clips.size()),
+                               transitions.data(), static_cast<int>(transitions.size())))
+        return unexpected<std::string>{device->ctx->lastError()};
+    const size_t n = static_cast<size_t>(device->n);
+    cmd.assign(n, DMK_ANIM_NONE);
+    cmdSpeed.assign(n, 1.f);
+    blend.assign(2 * n, 0.f);
+    speed.assign(n, 1.f);
+    deviceAnimators = true;
+    return {};
+}
+
+expected<void, std::string> SkeletalAnimationSceneComponent::init(int64_t numAnimators, AnimatorExecution execution) noexcept {
     if (_impl->device) return unexpected<std::string>{"already initialised"};
     auto dev = SkeletalAnimator::Device::create(_impl->skeleton, _impl->anims, _impl->armature, _impl->mesh ? &*_impl->mesh : nullptr, numAnimators);
     if (!dev) return unexpected<std::string>{dev.error()};
     _impl->device = std::move(*dev);
+    if (execution == AnimatorExecution::Device)
+        if (auto r = _impl->setupDeviceAnimators(); !r) {
+            _impl->device.reset();
+            return r;
+        }
     for (int64_t i = 0; i < numAnimators; ++i) {
         auto a = std::make_unique<SkeletalAnimator>(_impl->skeleton, _impl->anims, _impl->def);
         a->_batch = this;
@@ -413,29 +595,71 @@ expected<void, std::string> SkeletalAnimationSceneComponent::update(float deltaT
     auto& d = *_impl->device;
     const int64_t n = d.n;
     std::vector<std::string> errors;
-    int layers = 1;
-    for (int64_t i = 0; i < n; ++i) {
-        auto& a = *_impl->animators[static_cast<size_t>(i)];
-        _impl->active[static_cast<size_t>(i)] = a._core->hasActiveStateOrTransition();
-        auto& req = _impl->requests[static_cast<size_t>(i)];
-        if (auto r = a._core->update(deltaTime, req); !r) {
-            errors.push_back(r.error());
-            req = detail::PoseRequest{};   // a failed animator keeps its previous matrices this frame
-            _impl->active[static_cast<size_t>(i)] = 0;
+    ++_impl->frame;
+    if (_impl->deviceAnimators) {
+        // the state machines tick on the device: only this frame's commands and inputs are uploaded
+        auto& im = *_impl;
+        auto err = [&]() { return unexpected<std::string>{d.ctx->lastError()}; };
+        if (im.cmdDirty) {
+            if (dmk_crowd_animator_commands(d.crowd, im.cmd.data(), im.cmdSpeed.data())) return err();
+            std::fill(im.cmd.begin(), im.cmd.end(), static_cast<int32_t>(DMK_ANIM_NONE));
+            std::fill(im.cmdSpeed.begin(), im.cmdSpeed.end(), 1.f);
+            im.cmdDirty = false;
         }
-        layers = std::max(layers, layersOf(req));
-    }
-    if (layers > kMaxLayers) return unexpected<std::string>{"state blends more clips than the device supports"};
-    d.clip.assign(static_cast<size_t>(layers) * static_cast<size_t>(n), 0);
-    d.ratio.assign(d.clip.size(), 0.f);
-    d.weight.assign(d.clip.size(), 0.f);
-    for (int64_t i = 0; i < n; ++i)
-        writeRequest(_impl->requests[static_cast<size_t>(i)], i, n, d.clip.data(), d.ratio.data(), d.weight.data(), d.programs[static_cast<size_t>(i)]);
-    if (auto r = d.run(layers, true); !r) return r;
-    for (int64_t i = 0; i < n; ++i) {
-        auto& a = *_impl->animators[static_cast<size_t>(i)];
-        a._modelsValid = false;
-        if (_impl->active[static_cast<size_t>(i)]) a._core->afterUpdate();
+        if (im.inputsDirty) {
+            if (dmk_crowd_animator_set_inputs(d.crowd, im.blend.data(), im.speed.data())) return err();
+            im.inputsDirty = false;
+        }
+        uint32_t flags = DMK_STEP_ANIMATOR | DMK_STEP_POSE;
+        if (d.mesh) flags |= DMK_STEP_SKIN;
+        if (d.hasInstances && d.hasCamera) flags |= DMK_STEP_CULL;
+        if (dmk_crowd_step(d.crowd, deltaTime, flags)) return err();
+        d.visibilityValid = false;
+        im.infoValid = false;
+        im.events.resize(static_cast<size_t>(n));
+        im.status.resize(static_cast<size_t>(n));
+        if (dmk_crowd_get_animator_events(d.crowd, im.events.data(), im.status.data())) return err();
+        for (int64_t i = 0; i < n; ++i) {
+            if (im.status[static_cast<size_t>(i)]) errors.push_back("error in the blending job");
+            const dmk_anim_events& e = im.events[static_cast<size_t>(i)];
+            if (e.cmd_started < 0 && !e.transition_finished && e.looped < 0 && e.finished < 0) continue;
+            const auto itr = listenerRegistry().find(im.animators[static_cast<size_t>(i)].get());
+            if (itr == listenerRegistry().end()) continue;
+            SkeletalAnimator& a = *im.animators[static_cast<size_t>(i)];
+            const auto listeners = itr->second.all;   // copied before the fan-out, as the reference does
+            auto name = [&](int16_t s) { return std::string_view{im.stateNames[static_cast<size_t>(s)]}; };
+            for (auto* l : listeners) {   // the reference's order: play(), then afterUpdate (src/skeleton_ozz.cpp:783-856, 1044-1087)
+                if (e.cmd_started >= 0) l->onAnimatorStateStarted(a, name(e.cmd_started));
+                if (e.cmd_transition_started) l->onAnimatorTransitionStarted(a);
+                if (e.transition_finished) { l->onAnimatorTransitionFinished(a); l->onAnimatorStateFinished(a, name(e.prev_finished)); }
+                if (e.looped >= 0) l->onAnimatorStateLooped(a, name(e.looped));
+                if (e.finished >= 0) l->onAnimatorStateFinished(a, name(e.finished));
+                if (e.auto_started >= 0) l->onAnimatorStateStarted(a, name(e.auto_started));
+                if (e.auto_transition_started) l->onAnimatorTransitionStarted(a);
+            }
+        }
+    } else {
+        int layers = 1;
+        for (int64_t i = 0; i < n; ++i) {
+            auto& a = *_impl->animators[static_cast<size_t>(i)];
+            _impl->active[static_cast<size_t>(i)] = a._core->hasActiveStateOrTransition();
+            auto& req = _impl->requests[static_cast<size_t>(i)];
+            if (auto r = a._core->update(deltaTime, req); !r) {
+                errors.push_back(r.error());
+                req = detail::PoseRequest{};   // a failed animator keeps its previous matrices this frame
+                _impl->active[static_cast<size_t>(i)] = 0;
+            }
+            layers = std::max(layers, layersOf(req));
+        }
+        if (layers > kMaxLayers) return unexpected<std::string>{"state blends more clips than the device supports"};
+        d.clip.assign(static_cast<size_t>(layers) * static_cast<size_t>(n), 0);
+        d.ratio.assign(d.clip.size(), 0.f);
+        d.weight.assign(d.clip.size(), 0.f);
+        for (int64_t i = 0; i < n; ++i)
+            writeRequest(_impl->requests[static_cast<size_t>(i)], i, n, d.clip.data(), d.ratio.data(), d.weight.data(), d.programs[static_cast<size_t>(i)]);
+        if (auto r = d.run(layers, true); !r) return r;
+        for (int64_t i = 0; i < n; ++i)
+            if (_impl->active[static_cast<size_t>(i)]) _impl->animators[static_cast<size_t>(i)]->_core->afterUpdate();
     }
     if (!errors.empty()) {
         std::string joined;

@@ -229,9 +229,18 @@ DMK_API dmk_status dmk_crowd_animator_commands(dmk_crowd_t crowd, const int32_t*
 DMK_API dmk_status dmk_crowd_animator_set_inputs(dmk_crowd_t crowd, const float* blend_xy, const float* speed);
 /* After a step: events [N]; status [N] = 0, or 1 where update() returned "error in the blending job" (pose kept) */
 DMK_API dmk_status dmk_crowd_get_animator_events(dmk_crowd_t crowd, dmk_anim_events* out_events, int32_t* out_status);
-/* getCurrentState / getCurrentTransition: state [N] (-1 = none), transition [N] (-1 = none), their normalized times */
-DMK_API dmk_status dmk_crowd_get_animator_state(dmk_crowd_t crowd, int32_t* out_state, float* out_state_time,
-                                                int32_t* out_transition, float* out_transition_time);
+/* getCurrentState / getCurrentTransition of every character (src/skeleton_ozz.cpp:858-889) */
+typedef struct dmk_anim_state {
+    int32_t state;            /* the running transition's current state, else _state; -1 = none */
+    int32_t transition;       /* running transition's definition index, -1 = none (then _state is unset: C10) */
+    int32_t previous_state;   /* the transition's previous state, -1 = none */
+    float state_time;         /* getNormalizedTime() of each */
+    float transition_time;
+    float previous_time;
+    float state_speed;        /* state speed factor: getDuration() = definition duration * speed (C2) */
+    float previous_speed;
+} dmk_anim_state;
+DMK_API dmk_status dmk_crowd_get_animator_state(dmk_crowd_t crowd, dmk_anim_state* out_states);
 /* The layer rows and programs currently on the device (whoever wrote them): [num_layers][N] each, programs [N] */
 DMK_API dmk_status dmk_crowd_get_programs(dmk_crowd_t crowd, int num_layers, int32_t* out_clip, float* out_ratio,
                                           float* out_weight, dmk_pose_program* out_programs);

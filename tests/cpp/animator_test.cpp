@@ -381,8 +381,9 @@ static void runDeviceAnimators(const std::string& dir, const OracleAssets& o, co
         cores.push_back(std::make_unique<detail::AnimatorCore>(clipInfo, def));
     }
     const char* names[] = {"locomotion", "talk", "strafe", "greet"};
-    std::vector<int32_t> cmd((size_t)n), status((size_t)n), dstate((size_t)n), dtransition((size_t)n);
-    std::vector<float> cmdSpeed((size_t)n), blend((size_t)n * 2, 0.f), speed((size_t)n, 1.f), stateTime((size_t)n), transTime((size_t)n);
+    std::vector<int32_t> cmd((size_t)n), status((size_t)n);
+    std::vector<dmk_anim_state> info((size_t)n);
+    std::vector<float> cmdSpeed((size_t)n), blend((size_t)n * 2, 0.f), speed((size_t)n, 1.f);
     std::vector<dmk_anim_events> ev((size_t)n);
     std::vector<int32_t> lclip((size_t)L * n);
     std::vector<float> lratio((size_t)L * n), lweight((size_t)L * n), models((size_t)n * J * 16);
@@ -427,7 +428,7 @@ static void runDeviceAnimators(const std::string& dir, const OracleAssets& o, co
         if (inputs) DMK_OK_OR_FAIL(dmk_crowd_animator_set_inputs(crowd, blend.data(), speed.data()));
         DMK_OK_OR_FAIL(dmk_crowd_step(crowd, dt, DMK_STEP_ANIMATOR | DMK_STEP_POSE));
         DMK_OK_OR_FAIL(dmk_crowd_get_animator_events(crowd, ev.data(), status.data()));
-        DMK_OK_OR_FAIL(dmk_crowd_get_animator_state(crowd, dstate.data(), stateTime.data(), dtransition.data(), transTime.data()));
+        DMK_OK_OR_FAIL(dmk_crowd_get_animator_state(crowd, info.data()));
         DMK_OK_OR_FAIL(dmk_crowd_get_programs(crowd, L, lclip.data(), lratio.data(), lweight.data(), prog.data()));
         const bool readMatrices = frame % 6 == 5 || frame == 63;
         if (readMatrices) DMK_OK_OR_FAIL(dmk_crowd_get_models(crowd, 0, n, models.data()));
@@ -453,14 +454,21 @@ static void runDeviceAnimators(const std::string& dir, const OracleAssets& o, co
             CHECK(log == refs[i]->events, "frame %d animator %ld: listener events differ (%zu vs %zu)", frame, (long)i, log.size(), refs[i]->events.size());
             // current state / transition and their clocks (exact: only +, *, /, fmod)
             const auto* rs = refs[i]->currentState();
-            CHECK((rs != nullptr) == (dstate[i] >= 0), "frame %d animator %ld: current state presence", frame, (long)i);
-            if (rs && dstate[i] >= 0) {
-                CHECK(stateNames[(size_t)dstate[i]] == rs->getName(), "frame %d animator %ld: state %s vs %s", frame, (long)i, stateNames[(size_t)dstate[i]].c_str(), rs->getName().c_str());
-                CHECK(stateTime[i] == rs->getNormalizedTime(), "frame %d animator %ld: state clock %.9g vs %.9g", frame, (long)i, stateTime[i], rs->getNormalizedTime());
+            const dmk_anim_state& di = info[(size_t)i];
+            CHECK((rs != nullptr) == (di.state >= 0), "frame %d animator %ld: current state presence", frame, (long)i);
+            if (rs && di.state >= 0) {
+                CHECK(stateNames[(size_t)di.state] == rs->getName(), "frame %d animator %ld: state %s vs %s", frame, (long)i, stateNames[(size_t)di.state].c_str(), rs->getName().c_str());
+                CHECK(di.state_time == rs->getNormalizedTime(), "frame %d animator %ld: state clock %.9g vs %.9g", frame, (long)i, di.state_time, rs->getNormalizedTime());
+                const float duration = cores[i]->getStateDuration(std::string(rs->getName())) / dstates[(size_t)di.state].speed * di.state_speed;
+                CHECK(std::fabs(duration - rs->getDuration()) <= 1e-6f * rs->getDuration(), "frame %d animator %ld: state duration %g vs %g", frame, (long)i, duration, rs->getDuration());
             }
-            const auto* rt = refs[i]->currentTransition();
-            CHECK((rt != nullptr) == (dtransition[i] >= 0), "frame %d animator %ld: transition presence", frame, (long)i);
-            if (rt && dtransition[i] >= 0) CHECK(transTime[i] == rt->getNormalizedTime(), "frame %d animator %ld: transition clock", frame, (long)i);
+            auto* rt = const_cast<orc::RefTransition*>(refs[i]->currentTransition());
+            CHECK((rt != nullptr) == (di.transition >= 0), "frame %d animator %ld: transition presence", frame, (long)i);
+            if (rt && di.transition >= 0) {
+                CHECK(di.transition_time == rt->getNormalizedTime(), "frame %d animator %ld: transition clock", frame, (long)i);
+                CHECK(di.previous_state >= 0 && stateNames[(size_t)di.previous_state] == rt->previous().getName() && di.previous_time == rt->previous().getNormalizedTime(),
+                      "frame %d animator %ld: previous state of the transition", frame, (long)i);
+            }
             // resolved program against the host shim's PoseRequest
             const dmk_pose_program& g = prog[(size_t)i];
             if (!r || !active || req.top == detail::PoseRequest::Skip) {
@@ -672,11 +680,101 @@ static int runGpu(const std::string& dir) {
         std::printf("gpu: scene component, %ld animators x 51 frames, %d culled\n", (long)n, culled);
     }
     runDeviceAnimators(dir, o, def, rdef);
+
+    // ---- the same scene component with AnimatorExecution::Device: darmok's API on top of the device-side state machines ----
+    {
+        const int64_t n = 240;
+        std::vector<EventLog> logs((size_t)n);   // listeners outlive the animators (onAnimatorDestroyed)
+        SkeletalAnimationSceneComponent scene(*skel, anims, def, armature, nullptr);
+        CHECK(scene.init(n, AnimatorExecution::Device).has_value(), "scene init (device animators)");
+        std::vector<std::unique_ptr<orc::RefAnimator>> refs;
+        for (int64_t i = 0; i < n; ++i) {
+            refs.push_back(std::make_unique<orc::RefAnimator>(o.skel, o.named, rdef));
+            if (i % 2 == 0) scene.getAnimator(i).addListener(logs[(size_t)i]);
+        }
+        const char* states[] = {"locomotion", "talk", "strafe", "greet"};
+        long stateChecks = 0, transitionChecks = 0, eventCount = 0;
+        for (int frame = 0; frame < 56; ++frame) {
+            for (int64_t i = 0; i < n; ++i) {
+                auto& a = scene.getAnimator(i);
+                auto play = [&](const char* name, float sp) {
+                    const bool r1 = a.play(name, sp), r2 = refs[i]->play(name, sp);
+                    CHECK(r1 == r2, "frame %d animator %ld play(%s): %d vs %d", frame, (long)i, name, (int)r1, (int)r2);
+                };
+                if (frame == (int)(i % 7)) play(states[i % 4], 1.f);
+                else if (frame == 18 + (int)(i % 5)) play(states[(i + 1) % 4], 1.f);
+                else if (frame == 26 && i % 5 == 0) play(states[(i + 1) % 4], 1.75f);   // current state again: false, speed changes
+                else if (frame == 30 && i % 9 == 0) play("run", 1.f);                   // C16
+                else if (frame == 33 && i % 6 == 1) { a.stop(); refs[i]->stop(); }
+                else if (frame == 41 && i % 4 == 2) play("broken", 1.f);
+                if (frame % 8 == (int)(i % 8)) {
+                    const float bx = std::sin(0.13f * (float)(i + frame)), by = std::cos(0.05f * (float)(i * 2 + frame));
+                    a.setBlendPosition(glm::vec2(bx, by));
+                    refs[i]->setBlendPosition({bx, by});
+                }
+                if (frame == 12 && i % 3 == 1) { a.setPlaybackSpeed(1.5f); refs[i]->setPlaybackSpeed(1.5f); }
+                if (frame == 5 && i % 10 == 3) a.pause();
+            }
+            const auto r = scene.update(1 / 30.f);
+            int refErrors = 0;
+            for (int64_t i = 0; i < n; ++i) {
+                std::string err;
+                refErrors += !refs[i]->update(1 / 30.f, err);
+            }
+            CHECK(r.has_value() == (refErrors == 0), "frame %d: scene update ok=%d, reference errors=%d", frame, (int)r.has_value(), refErrors);
+            if (!r) {
+                const long lines = 1 + std::count(r.error().begin(), r.error().end(), '\n');
+                CHECK(lines == refErrors && r.error().rfind("error in the blending job", 0) == 0, "frame %d: %ld error lines vs %d", frame, lines, refErrors);
+            }
+            for (int64_t i = 0; i < n; ++i) {
+                auto& a = scene.getAnimator(i);
+                if (i % 2 == 0) CHECK(logs[(size_t)i].events == refs[i]->events, "frame %d animator %ld: listener events differ (%zu vs %zu)", frame, (long)i, logs[(size_t)i].events.size(), refs[i]->events.size());
+                if ((i + frame) % 3) continue;
+                const auto* cs = a.getCurrentState();
+                const auto* rs = refs[i]->currentState();
+                CHECK((cs != nullptr) == (rs != nullptr), "frame %d animator %ld: current state presence", frame, (long)i);
+                if (cs && rs) {
+                    ++stateChecks;
+                    CHECK(cs->getName() == rs->getName() && cs->getNormalizedTime() == rs->getNormalizedTime(), "frame %d animator %ld: state %s@%g vs %s@%g", frame, (long)i,
+                          std::string(cs->getName()).c_str(), cs->getNormalizedTime(), rs->getName().c_str(), rs->getNormalizedTime());
+                    CHECK(std::fabs(cs->getDuration() - rs->getDuration()) <= 1e-6f * rs->getDuration(), "frame %d animator %ld: duration %g vs %g", frame, (long)i, cs->getDuration(), rs->getDuration());
+                }
+                const auto* ct = a.getCurrentTransition();
+                auto* rt = const_cast<orc::RefTransition*>(refs[i]->currentTransition());
+                CHECK((ct != nullptr) == (rt != nullptr), "frame %d animator %ld: transition presence", frame, (long)i);
+                if (ct && rt) {
+                    ++transitionChecks;
+                    CHECK(ct->getNormalizedTime() == rt->getNormalizedTime() && ct->getPreviousState().getName() == rt->previous().getName() &&
+                              ct->getCurrentState().getName() == rt->current().getName() && ct->getPreviousState().getNormalizedTime() == rt->previous().getNormalizedTime(),
+                          "frame %d animator %ld: transition view", frame, (long)i);
+                }
+                // Stopped without _state, which includes a running transition (C10)
+                const bool hasState = rs && !rt;
+                const auto expected = !hasState ? SkeletalAnimatorPlaybackState::Stopped : (i % 10 == 3 && frame >= 5 ? SkeletalAnimatorPlaybackState::Paused : SkeletalAnimatorPlaybackState::Playing);
+                CHECK(a.getPlaybackState() == expected, "frame %d animator %ld: playback state", frame, (long)i);
+            }
+            if (frame % 9 != 8) continue;
+            std::vector<float> flipped(16);
+            for (int64_t i = 0; i < n; i += 7) {
+                auto& a = scene.getAnimator(i);
+                for (int j = 0; j < J; j += 4) {
+                    const glm::mat4 m = a.getJointModelMatrix(o.skel->names[j]);
+                    orc_flip_handedness(refs[i]->models().data() + (size_t)j * 16, flipped.data());
+                    for (int e = 0; e < 16; ++e) CHECK(close(glm::value_ptr(m)[e], flipped[e]), "frame %d animator %ld joint %d (device animators)", frame, (long)i, j);
+                }
+            }
+        }
+        for (const auto& l : logs) eventCount += (long)l.events.size();
+        CHECK(stateChecks > 2000 && transitionChecks > 200 && eventCount > 400, "device scene scenario lost coverage (%ld, %ld, %ld)", stateChecks, transitionChecks, eventCount);
+        std::printf("gpu: scene component with device animators, %ld animators x 56 frames: %ld state views, %ld transition views, %ld listener events\n", (long)n, stateChecks,
+                    transitionChecks, eventCount);
+    }
     std::printf("gpu: %d failures\n", g_failures);
     return g_failures ? 1 : 0;
 }
 
 int main(int argc, char** argv) {
     if (argc < 3) { std::printf("usage: animator_test <assets_dir> cpu|gpu\n"); return 2; }
+    std::setvbuf(stdout, nullptr, _IOLBF, 0);   // keep the progress lines if a section dies
     return std::string(argv[2]) == "gpu" ? runGpu(argv[1]) : runCpu(argv[1]);
 }

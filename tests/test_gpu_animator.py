@@ -131,8 +131,9 @@ def test_animator_path_equals_explicit_programs(rigs):
         mirror.step(0.0, capi.STEP_POSE)
         np.testing.assert_array_equal(crowd.get_palette(), mirror.get_palette())
     assert seen_finished == n and seen_transition > n
-    state, st, trans, tt = crowd.animator_state()
-    assert (state == 0).all() and (trans == -1).all()
+    info = crowd.animator_state()
+    assert (info["state"] == 0).all() and (info["transition"] == -1).all() and (info["previous_state"] == -1).all()
+    assert (info["state_speed"] == 1).all()
 
 
 def test_animator_argument_errors(rigs):

@@ -45,7 +45,7 @@ def assets_dir(tmp_path_factory):
 def _run(binary, assets_dir, mode):
     r = subprocess.run([binary, assets_dir, mode], capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:])
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert r.returncode == 0, f"exit code {r.returncode}\n" + r.stdout[-3000:] + r.stderr[-1000:]
     return r.stdout
 
 
