@@ -21,6 +21,7 @@ ANIM_NONE, ANIM_STOP = -2, -1
 OUT_MODELS, OUT_LOCALS, OUT_KEY_INDICES = 1, 2, 4
 OPT_FORCE_KEY_SEARCH = 1
 OPT_SKIN_RESERVED_SMS = 2
+OPT_KEEP_WORLD_INVERSE = 3
 GROUP_BLEND, GROUP_PASSTHROUGH = 0, 1
 TOP_GROUP0, TOP_TRANSITION, TOP_REST_POSE, TOP_SKIP = 0, 1, 2, 3
 PROGRAM_DTYPE = np.dtype([("n0", "u1"), ("n1", "u1"), ("rest0", "u1"), ("rest1", "u1"), ("mode0", "u1"), ("mode1", "u1"),
@@ -86,6 +87,10 @@ SIGNATURES = [
     ("dmk_crowd_get_programs", _i, [_vp, _i, _vp, _vp, _vp, _vp]),
     ("dmk_crowd_set_instances", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_set_transforms", _i, [_vp, _vp, _vp, _vp, _vp]),
+    ("dmk_crowd_set_transform_nodes", _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    ("dmk_crowd_get_transform_nodes", _i, [_vp, _vp, _vp]),
+    ("dmk_crowd_get_world_inverses", _i, [_vp, _i64, _i64, _vp]),
+    ("dmk_crowd_world_inverse_dev", _vp, [_vp]),
     ("dmk_crowd_set_camera", _i, [_vp, _vp, _f]),
     ("dmk_crowd_set_frustum_corners", _i, [_vp, _vp]),
     ("dmk_crowd_step", _i, [_vp, _f, _u32]),
@@ -380,6 +385,24 @@ class Crowd:
     def set_transforms(self, position, rotation, scale, bbox):
         p, q, s, b = _f32(position), _f32(rotation), _f32(scale), _f32(bbox)
         self.ctx.check(lib().dmk_crowd_set_transforms(self.h, _ptr(p), _ptr(q), _ptr(s), _ptr(b)))
+
+    def set_transform_nodes(self, position, rotation, scale, node_parent, entity_parent):
+        """group transforms the entities hang under (Transform::update with parents); empty arrays detach"""
+        p, q, s = _f32(position), _f32(rotation), _f32(scale)
+        npar, epar = np.ascontiguousarray(node_parent, np.int32), np.ascontiguousarray(entity_parent, np.int32)
+        self.num_nodes = p.shape[0]
+        self.ctx.check(lib().dmk_crowd_set_transform_nodes(self.h, self.num_nodes, _ptr(p), _ptr(q), _ptr(s), _ptr(npar), _ptr(epar)))
+
+    def get_transform_nodes(self):
+        world, inv = np.empty((self.num_nodes, 16), np.float32), np.empty((self.num_nodes, 16), np.float32)
+        self.ctx.check(lib().dmk_crowd_get_transform_nodes(self.h, _ptr(world), _ptr(inv)))
+        return world, inv
+
+    def get_world_inverses(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        out = np.empty((count, 16), np.float32)
+        self.ctx.check(lib().dmk_crowd_get_world_inverses(self.h, first, count, _ptr(out)))
+        return out
 
     def set_camera(self, view_proj, near_depth=0.0):
         vp = _f32(view_proj)

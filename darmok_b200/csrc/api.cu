@@ -126,6 +126,11 @@ struct dmk_crowd_s {
     float *d_world_inverse = nullptr, *d_bbox = nullptr;
     float *d_position = nullptr, *d_rotation = nullptr, *d_scale = nullptr;
     bool use_trs = false;
+    // group nodes the entities' Transforms hang under (dmk_crowd_set_transform_nodes)
+    int num_nodes = 0;
+    float *d_node_position = nullptr, *d_node_rotation = nullptr, *d_node_scale = nullptr, *d_node_world = nullptr, *d_node_world_inverse = nullptr;
+    int32_t *d_node_parent = nullptr, *d_entity_parent = nullptr;
+    bool keep_world_inverse = false;   // dmk_crowd_get_world_inverses was asked for: the cull also stores what it derives
     uint32_t* d_vis_bits = nullptr;
     int32_t *d_visible_ids = nullptr, *d_visible_count = nullptr, *d_scratch = nullptr;
     // pinned ring for DMK_STEP_READBACK_VISIBILITY: [words] bits + 1 count, two frames deep
@@ -760,7 +765,8 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
                     (void*)c->d_key_indices, (void*)c->d_error, (void*)c->d_world_inverse, (void*)c->d_bbox, (void*)c->d_position, (void*)c->d_rotation, (void*)c->d_scale, (void*)c->d_vis_bits,
                     (void*)c->d_visible_ids, (void*)c->d_visible_count, (void*)c->d_scratch, (void*)c->d_anim_states, (void*)c->d_anim_clips,
                     (void*)c->d_anim_transitions, (void*)c->d_anim_tables, (void*)c->d_anim_slots, (void*)c->d_anim_transition,
-                    (void*)c->d_anim_transition_time, (void*)c->d_anim_events, (void*)c->d_anim_info, (void*)c->d_anim_cmd, (void*)c->d_anim_status,
+                    (void*)c->d_anim_transition_time, (void*)c->d_anim_events, (void*)c->d_anim_info, (void*)c->d_node_position, (void*)c->d_node_rotation,
+                    (void*)c->d_node_scale, (void*)c->d_node_world, (void*)c->d_node_world_inverse, (void*)c->d_node_parent, (void*)c->d_entity_parent, (void*)c->d_anim_cmd, (void*)c->d_anim_status,
                     (void*)c->d_anim_cmd_speed, (void*)c->d_anim_blend, (void*)c->d_anim_speed})
         dev_free(p);
     for (int b = 0; b < 2; ++b) {
@@ -782,6 +788,12 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
     if (option == DMK_OPT_SKIN_RESERVED_SMS) {
         if (value < 0 || value >= c->ctx->num_sms) return fail(c->ctx, DMK_ERR_INVALID, "reserved SM count out of range");
         if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - value);
+        return DMK_OK;
+    }
+    if (option == DMK_OPT_KEEP_WORLD_INVERSE) {
+        if (bind(c->ctx)) return DMK_ERR_CUDA;
+        if (value && !c->d_world_inverse) DMK_CUDA(c->ctx, dev_alloc(&c->d_world_inverse, static_cast<size_t>(c->n) * 16));
+        c->keep_world_inverse = value != 0;
         return DMK_OK;
     }
     return fail(c->ctx, DMK_ERR_INVALID, "unknown option");
@@ -1172,6 +1184,75 @@ dmk_status dmk_crowd_set_transforms(dmk_crowd_t c, const float* position, const 
     return DMK_OK;
 }
 
+dmk_status dmk_crowd_set_transform_nodes(dmk_crowd_t c, int num_nodes, const float* position, const float* rotation, const float* scale,
+                                         const int32_t* node_parent, const int32_t* entity_parent) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (num_nodes < 0) return fail(ctx, DMK_ERR_INVALID, "negative node count");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // a running cull may still read the old arrays
+    for (void* p : {(void*)c->d_node_position, (void*)c->d_node_rotation, (void*)c->d_node_scale, (void*)c->d_node_world,
+                    (void*)c->d_node_world_inverse, (void*)c->d_node_parent, (void*)c->d_entity_parent})
+        dev_free(p);
+    c->d_node_position = c->d_node_rotation = c->d_node_scale = c->d_node_world = c->d_node_world_inverse = nullptr;
+    c->d_node_parent = c->d_entity_parent = nullptr;
+    c->num_nodes = 0;
+    if (num_nodes == 0) return DMK_OK;
+    if (!position || !rotation || !scale || !node_parent || !entity_parent) return fail(ctx, DMK_ERR_INVALID, "null node array");
+    const size_t m = static_cast<size_t>(num_nodes), n = static_cast<size_t>(c->n);
+    for (size_t i = 0; i < m; ++i) {   // a forest: parents in range, no cycles, bounded depth
+        int depth = 0;
+        for (int k = static_cast<int>(i); k >= 0; k = node_parent[k]) {
+            if (k >= num_nodes) return fail(ctx, DMK_ERR_INVALID, "node " + std::to_string(i) + ": parent index out of range");
+            if (++depth > 32) return fail(ctx, DMK_ERR_INVALID, "node " + std::to_string(i) + ": parent chain deeper than 32 (or cyclic)");
+        }
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (entity_parent[i] < -1 || entity_parent[i] >= num_nodes)
+            return fail(ctx, DMK_ERR_INVALID, "entity " + std::to_string(i) + ": parent node out of range");
+    cudaStream_t s = ctx->stream;
+    DMK_CUDA(ctx, dev_alloc(&c->d_node_position, m * 3));
+    DMK_CUDA(ctx, dev_alloc(&c->d_node_rotation, m * 4));
+    DMK_CUDA(ctx, dev_alloc(&c->d_node_scale, m * 3));
+    DMK_CUDA(ctx, dev_alloc(&c->d_node_world, m * 16));
+    DMK_CUDA(ctx, dev_alloc(&c->d_node_world_inverse, m * 16));
+    DMK_CUDA(ctx, dev_alloc(&c->d_node_parent, m));
+    DMK_CUDA(ctx, dev_alloc(&c->d_entity_parent, n));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_node_position, position, m * 12, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_node_rotation, rotation, m * 16, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_node_scale, scale, m * 12, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_node_parent, node_parent, m * 4, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_entity_parent, entity_parent, n * 4, cudaMemcpyHostToDevice, s));
+    DMK_CUDA(ctx, cudaStreamSynchronize(s));
+    c->num_nodes = num_nodes;
+    return DMK_OK;
+}
+
+dmk_status dmk_crowd_get_world_inverses(dmk_crowd_t c, int64_t first, int64_t count, float* out) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!out || first < 0 || count < 0 || first + count > c->n) return fail(ctx, DMK_ERR_INVALID, "character range out of bounds");
+    if (!c->d_world_inverse || !c->culled_once || (c->use_trs && !c->keep_world_inverse))
+        return fail(ctx, DMK_ERR_INVALID, "needs DMK_OPT_KEEP_WORLD_INVERSE (or dmk_crowd_set_instances) and a cull step");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    DMK_CUDA(ctx, cudaMemcpyAsync(out, c->d_world_inverse + first * 16, static_cast<size_t>(count) * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DMK_OK;
+}
+const float* dmk_crowd_world_inverse_dev(dmk_crowd_t c) { return c ? c->d_world_inverse : nullptr; }
+
+dmk_status dmk_crowd_get_transform_nodes(dmk_crowd_t c, float* out_world, float* out_world_inverse) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!c->num_nodes || !c->culled_once) return fail(ctx, DMK_ERR_INVALID, "needs dmk_crowd_set_transform_nodes and a cull step");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    const size_t bytes = static_cast<size_t>(c->num_nodes) * 64;
+    if (out_world) DMK_CUDA(ctx, cudaMemcpyAsync(out_world, c->d_node_world, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_world_inverse) DMK_CUDA(ctx, cudaMemcpyAsync(out_world_inverse, c->d_node_world_inverse, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DMK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DMK_OK;
+}
+
 dmk_status dmk_frustum_corners(const float* view_proj, float near_depth, float* out_corners) {
     if (!view_proj || !out_corners) return DMK_ERR_INVALID;
     frustum_corners_glm(view_proj, near_depth, out_corners);
@@ -1279,10 +1360,19 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         if (!c->instances_set || !c->camera_set)
             return fail(ctx, DMK_ERR_INVALID, "cull needs dmk_crowd_set_instances and dmk_crowd_set_camera");
         CullParams p{};
+        int node_launches = 0;
         if (c->use_trs) {
             p.position = c->d_position;
             p.rotation = c->d_rotation;
             p.scale = c->d_scale;
+            if (c->num_nodes) {
+                DMK_CUDA(ctx, launch_transform_nodes(c->d_node_position, c->d_node_rotation, c->d_node_scale, c->d_node_parent, c->num_nodes,
+                                                     c->d_node_world, c->d_node_world_inverse, s));
+                node_launches = 1;
+                p.entity_parent = c->d_entity_parent;
+                p.node_world_inverse = c->d_node_world_inverse;
+            }
+            if (c->keep_world_inverse) p.world_inverse_out = c->d_world_inverse;
         } else {
             p.world_inverse = c->d_world_inverse;
         }
@@ -1296,8 +1386,7 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
             DMK_CUDA(ctx, launch_cull(p, s));
             DMK_CUDA(ctx, launch_compact(c->d_vis_bits, c->n, c->d_visible_ids, c->d_visible_count, c->d_scratch, s, &extra));
         }
-        ++ctx->launches;
-        ctx->launches += extra;
+        ctx->launches += 1 + extra + node_launches;
         c->culled_once = true;
         if (flags & DMK_STEP_READBACK_VISIBILITY) {
             if (c->vis_pending == 2) return fail(ctx, DMK_ERR_INVALID, "two visibility read-backs are already outstanding: collect one first");

@@ -44,22 +44,24 @@ __device__ __forceinline__ bool box_in_front(V3 a, V3 b, V3 c, V3 mn, V3 mx) {
     return !(sd_min <= 0.f);
 }
 
-// Transform::update for an entity without parent (src/transform.cpp:286-309): world inverse =
-// glm::inverse(glm::translate(p) * glm::mat4_cast(q) * glm::scale(s)), all in glm's scalar operation order.
+// Transform::update (src/transform.cpp:286-309): _localMatrix = glm::translate(p) * glm::mat4_cast(q) * glm::scale(s),
+// _localInverse = glm::inverse(_localMatrix), all in glm's scalar operation order.  m[column][row].
 // The two products only add exact zeros to R[c][r] * s[c] and to p, so the local matrix is [R * diag(s) | p].
-__device__ __forceinline__ void world_inverse_from_trs(const float* __restrict__ pos, const float* __restrict__ rot,
-                                                       const float* __restrict__ scl, int64_t i, float4& o0, float4& o1, float4& o2, float4& o3) {
+__device__ __forceinline__ void local_from_trs(const float* __restrict__ pos, const float* __restrict__ rot, const float* __restrict__ scl, int64_t i,
+                                               float m[4][4]) {
     const float px = __ldg(pos + i * 3), py = __ldg(pos + i * 3 + 1), pz = __ldg(pos + i * 3 + 2);
     const float4 q = __ldg(reinterpret_cast<const float4*>(rot) + i);
     const float sx = __ldg(scl + i * 3), sy = __ldg(scl + i * 3 + 1), sz = __ldg(scl + i * 3 + 2);
     const float qxx = q.x * q.x, qyy = q.y * q.y, qzz = q.z * q.z, qxz = q.x * q.z, qxy = q.x * q.y, qyz = q.y * q.z;
     const float qwx = q.w * q.x, qwy = q.w * q.y, qwz = q.w * q.z;
-    float m[4][4];  // m[column][row]
     m[0][0] = (1.f - 2.f * (qyy + qzz)) * sx; m[0][1] = (2.f * (qxy + qwz)) * sx;       m[0][2] = (2.f * (qxz - qwy)) * sx;       m[0][3] = 0.f;
     m[1][0] = (2.f * (qxy - qwz)) * sy;       m[1][1] = (1.f - 2.f * (qxx + qzz)) * sy; m[1][2] = (2.f * (qyz + qwx)) * sy;       m[1][3] = 0.f;
     m[2][0] = (2.f * (qxz + qwy)) * sz;       m[2][1] = (2.f * (qyz - qwx)) * sz;       m[2][2] = (1.f - 2.f * (qxx + qyy)) * sz; m[2][3] = 0.f;
     m[3][0] = px; m[3][1] = py; m[3][2] = pz; m[3][3] = 1.f;
-    // glm::detail::compute_inverse<4, 4>
+}
+
+// glm::detail::compute_inverse<4, 4>
+__device__ __forceinline__ void inverse_glm(const float m[4][4], float o[4][4]) {
     const float c00 = m[2][2] * m[3][3] - m[3][2] * m[2][3], c02 = m[1][2] * m[3][3] - m[3][2] * m[1][3];
     const float c03 = m[1][2] * m[2][3] - m[2][2] * m[1][3], c04 = m[2][1] * m[3][3] - m[3][1] * m[2][3];
     const float c06 = m[1][1] * m[3][3] - m[3][1] * m[1][3], c07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
@@ -84,10 +86,76 @@ __device__ __forceinline__ void world_inverse_from_trs(const float* __restrict__
     }
     const float d0 = m[0][0] * inv[0][0], d1 = m[0][1] * inv[1][0], d2 = m[0][2] * inv[2][0], d3 = m[0][3] * inv[3][0];
     const float ood = __frcp_rn((d0 + d1) + (d2 + d3));
-    o0 = make_float4(inv[0][0] * ood, inv[0][1] * ood, inv[0][2] * ood, inv[0][3] * ood);
-    o1 = make_float4(inv[1][0] * ood, inv[1][1] * ood, inv[1][2] * ood, inv[1][3] * ood);
-    o2 = make_float4(inv[2][0] * ood, inv[2][1] * ood, inv[2][2] * ood, inv[2][3] * ood);
-    o3 = make_float4(inv[3][0] * ood, inv[3][1] * ood, inv[3][2] * ood, inv[3][3] * ood);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o[c][r] = inv[c][r] * ood;
+}
+
+// glm::mat4 * glm::mat4: Result[j] = ((A[0] * B[j][0] + A[1] * B[j][1]) + A[2] * B[j][2]) + A[3] * B[j][3]; o may alias a or b
+__device__ __forceinline__ void mul_glm(const float a[4][4], const float b[4][4], float o[4][4]) {
+    float r[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[j][i] = ((a[0][i] * b[j][0] + a[1][i] * b[j][1]) + a[2][i] * b[j][2]) + a[3][i] * b[j][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[j][i] = r[j][i];
+}
+
+// Transform::update of the group nodes the crowd's entities hang under (src/transform.cpp:300-305):
+//   world = parent.world * local,   worldInverse = localInverse * parent.worldInverse,   the parent first.
+// One thread per node walks its ancestor chain and multiplies from the root down: the same products in the same order as
+// the reference's recursion, recomputed per node instead of shared (a few hundred nodes against 1e5..1e7 entities).
+constexpr int kMaxTransformDepth = 32;
+
+__global__ void __launch_bounds__(128) transform_nodes_kernel(const float* __restrict__ pos, const float* __restrict__ rot,
+                                                              const float* __restrict__ scl, const int32_t* __restrict__ parent, int num_nodes,
+                                                              float* __restrict__ world, float* __restrict__ world_inverse) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= num_nodes) return;
+    int chain[kMaxTransformDepth];
+    int depth = 0;
+    for (int k = node; k >= 0 && depth < kMaxTransformDepth; k = parent[k]) chain[depth++] = k;
+    float w[4][4], wi[4][4], local[4][4], local_inverse[4][4];
+    local_from_trs(pos, rot, scl, chain[depth - 1], w);
+    inverse_glm(w, wi);
+    for (int d = depth - 2; d >= 0; --d) {
+        local_from_trs(pos, rot, scl, chain[d], local);
+        inverse_glm(local, local_inverse);
+        mul_glm(w, local, w);
+        mul_glm(local_inverse, wi, wi);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        reinterpret_cast<float4*>(world + (size_t)node * 16)[c] = make_float4(w[c][0], w[c][1], w[c][2], w[c][3]);
+        reinterpret_cast<float4*>(world_inverse + (size_t)node * 16)[c] = make_float4(wi[c][0], wi[c][1], wi[c][2], wi[c][3]);
+    }
+}
+
+__device__ __forceinline__ void world_inverse_from_trs(const CullParams& p, int64_t i, float4& o0, float4& o1, float4& o2, float4& o3) {
+    float m[4][4], inv[4][4];
+    local_from_trs(p.position, p.rotation, p.scale, i, m);
+    inverse_glm(m, inv);
+    if (p.entity_parent) {   // uniform branch: the crowd either hangs under group nodes or not
+        const int node = __ldg(p.entity_parent + i);
+        if (node >= 0) {
+            float pw[4][4];
+            const float4* src = reinterpret_cast<const float4*>(p.node_world_inverse + (size_t)node * 16);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 v = __ldg(src + c);
+                pw[c][0] = v.x; pw[c][1] = v.y; pw[c][2] = v.z; pw[c][3] = v.w;
+            }
+            mul_glm(inv, pw, inv);
+        }
+    }
+    o0 = make_float4(inv[0][0], inv[0][1], inv[0][2], inv[0][3]);
+    o1 = make_float4(inv[1][0], inv[1][1], inv[1][2], inv[1][3]);
+    o2 = make_float4(inv[2][0], inv[2][1], inv[2][2], inv[2][3]);
+    o3 = make_float4(inv[3][0], inv[3][1], inv[3][2], inv[3][3]);
 }
 
 template <bool FROM_TRS>
@@ -97,7 +165,7 @@ __global__ void __launch_bounds__(256) cull_kernel(const CullParams p) {
     if (i < p.n) {
         float4 c0, c1, c2, c3;
         if (FROM_TRS) {
-            world_inverse_from_trs(p.position, p.rotation, p.scale, i, c0, c1, c2, c3);
+            world_inverse_from_trs(p, i, c0, c1, c2, c3);
             if (p.world_inverse_out) {
                 float4* o = reinterpret_cast<float4*>(p.world_inverse_out + i * 16);
                 o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
@@ -241,6 +309,13 @@ cudaError_t launch_cull(const CullParams& p, cudaStream_t stream) {
     const int64_t blocks = (p.n + 255) / 256;
     if (p.position) cull_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p);
     else cull_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transform_nodes(const float* pos, const float* rot, const float* scl, const int32_t* parent, int num_nodes, float* world,
+                                   float* world_inverse, cudaStream_t stream) {
+    if (num_nodes <= 0) return cudaSuccess;
+    transform_nodes_kernel<<<(num_nodes + 127) / 128, 128, 0, stream>>>(pos, rot, scl, parent, num_nodes, world, world_inverse);
     return cudaGetLastError();
 }
 

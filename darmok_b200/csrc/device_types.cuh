@@ -114,6 +114,8 @@ struct CullParams {
     const float* rotation;      // [n][4] quaternion x, y, z, w
     const float* scale;         // [n][3]
     float* world_inverse_out;   // [n][16] optional: the derived matrices, for other consumers
+    const int32_t* entity_parent;       // [n] or null: group node each entity's Transform hangs under, -1 = none
+    const float* node_world_inverse;    // [num_nodes][16] from transform_nodes_kernel
     const float* world_inverse; // [n][16]
     const float* bbox;          // [n][6]
     int64_t n;

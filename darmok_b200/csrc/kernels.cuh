@@ -11,6 +11,9 @@ cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream, i
 
 // K4 (cull_kernel.cu, built with -fmad=false): visibility bitmask; then ordered compaction of visible ids
 cudaError_t launch_cull(const CullParams& p, cudaStream_t stream);
+// Transform::update over the group nodes (parents first), any node order, chains up to 32 deep
+cudaError_t launch_transform_nodes(const float* pos, const float* rot, const float* scl, const int32_t* parent, int num_nodes, float* world,
+                                   float* world_inverse, cudaStream_t stream);
 // ids_out[i] = i-th visible instance (ascending); count_out[0] = number of visible; scratch >= ceil(words/1024)+1 ints
 cudaError_t launch_compact(const uint32_t* vis_bits, int64_t n, int32_t* ids_out, int32_t* count_out,
                            int32_t* scratch, cudaStream_t stream, int* launches);

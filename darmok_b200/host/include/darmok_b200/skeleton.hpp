@@ -297,6 +297,13 @@ public:
 
     // per-entity Transform::getWorldInverse + BoundingBox, camera view-projection (FrustumCuller inputs)
     expected<void, std::string> setInstances(const float* worldInverse, const float* bbox) noexcept;
+    // alternative to setInstances: what each entity's Transform holds (position [N][3], rotation xyzw [N][4], scale
+    // [N][3]); Transform::update (src/transform.cpp:286-309) then runs on the device inside the cull
+    expected<void, std::string> setTransforms(const float* position, const float* rotation, const float* scale, const float* bbox) noexcept;
+    // parents of those Transforms: numNodes group transforms forming a forest (nodeParent, -1 = root) and the node each
+    // entity hangs under (entityParent [N], -1 = none); numNodes = 0 detaches
+    expected<void, std::string> setTransformNodes(int numNodes, const float* position, const float* rotation, const float* scale,
+                                                  const int32_t* nodeParent, const int32_t* entityParent) noexcept;
     expected<void, std::string> setCamera(const glm::mat4& viewProj, float normalizedNearDepth = 0.f) noexcept;
 
     expected<void, std::string> update(float deltaTime) noexcept;          // ISceneComponent::update

@@ -581,6 +581,21 @@ expected<void, std::string> SkeletalAnimationSceneComponent::setInstances(const 
     _impl->device->hasInstances = true;
     return {};
 }
+expected<void, std::string> SkeletalAnimationSceneComponent::setTransforms(const float* position, const float* rotation, const float* scale,
+                                                                           const float* bbox) noexcept {
+    if (!_impl->device) return unexpected<std::string>{"not initialised"};
+    if (dmk_crowd_set_transforms(_impl->device->crowd, position, rotation, scale, bbox)) return unexpected<std::string>{_impl->device->ctx->lastError()};
+    _impl->device->hasInstances = true;
+    return {};
+}
+expected<void, std::string> SkeletalAnimationSceneComponent::setTransformNodes(int numNodes, const float* position, const float* rotation,
+                                                                               const float* scale, const int32_t* nodeParent,
+                                                                               const int32_t* entityParent) noexcept {
+    if (!_impl->device) return unexpected<std::string>{"not initialised"};
+    if (dmk_crowd_set_transform_nodes(_impl->device->crowd, numNodes, position, rotation, scale, nodeParent, entityParent))
+        return unexpected<std::string>{_impl->device->ctx->lastError()};
+    return {};
+}
 expected<void, std::string> SkeletalAnimationSceneComponent::setCamera(const glm::mat4& viewProj, float normalizedNearDepth) noexcept {
     if (!_impl->device) return unexpected<std::string>{"not initialised"};
     if (dmk_crowd_set_camera(_impl->device->crowd, glm::value_ptr(viewProj), normalizedNearDepth)) return unexpected<std::string>{_impl->device->ctx->lastError()};

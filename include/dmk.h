@@ -133,7 +133,11 @@ enum {
     DMK_OPT_FORCE_KEY_SEARCH = 1,
     /* Leave `value` SMs out of the persistent skinning grid so that a collective enqueued on another stream (the
      * visible-palette gather over NVLink) runs concurrently with the skinning kernel instead of after it. */
-    DMK_OPT_SKIN_RESERVED_SMS = 2
+    DMK_OPT_SKIN_RESERVED_SMS = 2,
+    /* With dmk_crowd_set_transforms: also store the world inverse the cull derives for each entity (64 B/entity more
+     * written per CULL step) so that dmk_crowd_get_world_inverses / dmk_crowd_world_inverse_dev can hand it on, e.g. to
+     * the renderer's per-entity uniforms. */
+    DMK_OPT_KEEP_WORLD_INVERSE = 3
 };
 DMK_API dmk_status dmk_crowd_set_option(dmk_crowd_t crowd, int option, int value);
 
@@ -256,6 +260,21 @@ DMK_API dmk_status dmk_crowd_set_instances(dmk_crowd_t crowd, const float* world
  * scale [N][3], bbox [N][6]. */
 DMK_API dmk_status dmk_crowd_set_transforms(dmk_crowd_t crowd, const float* position, const float* rotation, const float* scale,
                                             const float* bbox);
+
+/* Entities whose Transform has a parent (src/transform.cpp:300-305): num_nodes group transforms (position [M][3],
+ * rotation [M][4], scale [M][3]) forming a forest through node_parent [M] (-1 = root; any order; chains up to 32
+ * deep), and for each crowd entity the node its Transform hangs under, entity_parent [N] (-1 = none).  Every CULL
+ * step first runs Transform::update over the nodes on the device (world = parent.world * local, worldInverse =
+ * localInverse * parent.worldInverse, parents first), then each entity's worldInverse = localInverse *
+ * node.worldInverse.  Needs dmk_crowd_set_transforms.  num_nodes = 0 detaches the crowd again. */
+DMK_API dmk_status dmk_crowd_set_transform_nodes(dmk_crowd_t crowd, int num_nodes, const float* position, const float* rotation,
+                                                 const float* scale, const int32_t* node_parent, const int32_t* entity_parent);
+/* Transform::getWorldMatrix / getWorldInverse of the nodes after the last CULL step: [M][16] each (either may be NULL) */
+DMK_API dmk_status dmk_crowd_get_transform_nodes(dmk_crowd_t crowd, float* out_world, float* out_world_inverse);
+/* the entities' world inverses the last CULL step derived (dmk_crowd_set_transforms path, after
+ * dmk_crowd_set_option(DMK_OPT_KEEP_WORLD_INVERSE, 1)): [count][16] */
+DMK_API dmk_status dmk_crowd_get_world_inverses(dmk_crowd_t crowd, int64_t first, int64_t count, float* out);
+DMK_API const float* dmk_crowd_world_inverse_dev(dmk_crowd_t crowd);
 
 /* Camera::getViewProjectionMatrix (src/camera.cpp:196-199) -> Frustum{proj * view} (src/culling.cpp:268,
  * src/shape.cpp:1141-1163), computed on the host in glm operation order.  near_depth =

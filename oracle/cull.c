@@ -210,3 +210,56 @@ void orc_cull_batch_trs(const float* corners, const float* position, const float
         vis_bits[w] = bits;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Transform::update with a parent (src/transform.cpp:286-309):
+ *   _worldMatrix  = _parent->getWorldMatrix() * _localMatrix
+ *   _worldInverse = _localInverse * _parent->getWorldInverse()
+ * the parent being updated first (recursively).  Nodes may come in any order; parent[i] = -1 for a root.
+ * ---------------------------------------------------------------------------------------------- */
+static void node_update(int i, const float* pos, const float* rot, const float* scale, const int32_t* parent, unsigned char* done,
+                        float* world, float* world_inverse) {
+    if (done[i]) return;
+    float local[16], local_inverse[16];
+    orc_transform_local_matrix(pos + (size_t)i * 3, rot + (size_t)i * 4, scale + (size_t)i * 3, local);
+    orc_mat4_inverse(local, local_inverse);
+    if (parent[i] >= 0) {
+        node_update(parent[i], pos, rot, scale, parent, done, world, world_inverse);
+        orc_mat4_mul(world + (size_t)parent[i] * 16, local, world + (size_t)i * 16);
+        orc_mat4_mul(local_inverse, world_inverse + (size_t)parent[i] * 16, world_inverse + (size_t)i * 16);
+    } else {
+        memcpy(world + (size_t)i * 16, local, sizeof local);
+        memcpy(world_inverse + (size_t)i * 16, local_inverse, sizeof local_inverse);
+    }
+    done[i] = 1;
+}
+
+void orc_transform_nodes(int num_nodes, const float* position, const float* rotation, const float* scale, const int32_t* parent,
+                         float* out_world, float* out_world_inverse) {
+    unsigned char done[num_nodes > 0 ? num_nodes : 1];
+    memset(done, 0, sizeof done);
+    for (int i = 0; i < num_nodes; ++i) node_update(i, position, rotation, scale, parent, done, out_world, out_world_inverse);
+}
+
+void orc_cull_batch_trs_parented(const float* corners, const float* position, const float* rotation, const float* scale,
+                                 const float* bbox, int64_t n, const int32_t* entity_parent, const float* node_world_inverse,
+                                 uint32_t* vis_bits, float* world_inverse_out, int num_threads) {
+    const int64_t words = (n + 31) / 32;
+    if (num_threads < 1) num_threads = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(num_threads)
+#endif
+    for (int64_t w = 0; w < words; ++w) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int64_t i = w * 32 + b;
+            if (i >= n) break;
+            float wi[16];
+            orc_transform_world_inverse(position + i * 3, rotation + i * 4, scale + i * 3, wi);
+            if (entity_parent[i] >= 0) orc_mat4_mul(wi, node_world_inverse + (size_t)entity_parent[i] * 16, wi);
+            if (world_inverse_out) memcpy(world_inverse_out + i * 16, wi, sizeof wi);
+            if (orc_cull_visible(corners, wi, bbox + i * 6)) bits |= (1u << b);
+        }
+        vis_bits[w] = bits;
+    }
+}

@@ -148,6 +148,15 @@ void orc_transform_world_inverse(const float* position, const float* rotation_xy
 void orc_cull_batch_trs(const float* corners, const float* position, const float* rotation, const float* scale,
                         const float* bbox, int64_t n, uint32_t* vis_bits, float* world_inverse_out, int num_threads);
 
+/* Transform::update with parents (src/transform.cpp:300-305): world = parent.world * local, worldInverse = localInverse *
+ * parent.worldInverse.  parent[i] = -1 for a root; any node order. */
+void orc_transform_nodes(int num_nodes, const float* position, const float* rotation_xyzw, const float* scale, const int32_t* parent,
+                         float* out_world, float* out_world_inverse);
+/* entities whose Transform has a parent among those nodes (entity_parent[i] = -1: none) */
+void orc_cull_batch_trs_parented(const float* corners, const float* position, const float* rotation, const float* scale,
+                                 const float* bbox, int64_t n, const int32_t* entity_parent, const float* node_world_inverse,
+                                 uint32_t* vis_bits, float* world_inverse_out, int num_threads);
+
 /* ---- clip clock (OzzSkeletalAnimatorAnimationState::update, src/skeleton_ozz.cpp:411-440) ----
  * Returns 1 when the clip is to be re-sampled this tick, 0 when it holds (finished, non looping). */
 int orc_clip_clock(float* normalized_time, int* looped, float dt, float clip_duration, float speed, int loop);

@@ -76,6 +76,10 @@ def lib():
         L.orc_transform_world_inverse.argtypes = [C.c_void_p] * 4
         L.orc_transform_local_matrix.argtypes = [C.c_void_p] * 4
         L.orc_cull_batch_trs.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_transform_nodes.argtypes = [C.c_int] + [C.c_void_p] * 6
+        L.orc_transform_nodes.restype = None
+        L.orc_cull_batch_trs_parented.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_cull_batch_trs_parented.restype = None
         L.orc_clip_clock.argtypes = [c_float_p, c_i32_p, C.c_float, C.c_float, C.c_float, C.c_int]
         L.orc_clip_clock.restype = C.c_int
         L.orc_crowd_create.restype = C.c_void_p
@@ -285,6 +289,26 @@ def cull_batch_trs(corners, position, rotation, scale, bbox, num_threads=None, w
     wi = np.zeros((n, 16), np.float32) if want_world_inverse else None
     lib().orc_cull_batch_trs(_p(c), _p(p), _p(q), _p(s), _p(b), n, _p(bits), _p(wi), num_threads or max_threads())
     return (bits, wi) if want_world_inverse else bits
+
+
+def transform_nodes(position, rotation, scale, parent):
+    """Transform::update over a forest (src/transform.cpp:286-309): (world [M][16], world_inverse [M][16])"""
+    p, q, s = _f32(position), _f32(rotation), _f32(scale)
+    par = np.ascontiguousarray(parent, np.int32)
+    m = p.shape[0]
+    world, inv = np.zeros((m, 16), np.float32), np.zeros((m, 16), np.float32)
+    lib().orc_transform_nodes(m, _p(p), _p(q), _p(s), _p(par), _p(world), _p(inv))
+    return world, inv
+
+
+def cull_batch_trs_parented(corners, position, rotation, scale, bbox, entity_parent, node_world_inverse, num_threads=None):
+    c, p, q, s, b, nwi = (_f32(a) for a in (corners, position, rotation, scale, bbox, node_world_inverse))
+    ep = np.ascontiguousarray(entity_parent, np.int32)
+    n = p.shape[0]
+    bits = np.zeros((n + 31) // 32, np.uint32)
+    wi = np.zeros((n, 16), np.float32)
+    lib().orc_cull_batch_trs_parented(_p(c), _p(p), _p(q), _p(s), _p(b), n, _p(ep), _p(nwi), _p(bits), _p(wi), num_threads or max_threads())
+    return bits, wi
 
 
 def clip_clock(t, looped, dt, duration, speed, loop):

@@ -677,6 +677,31 @@ static int runGpu(const std::string& dir) {
             culled += ref;
         }
         CHECK(culled > 0 && culled < n, "cull test must see both outcomes (%d of %ld culled)", culled, (long)n);
+        // the same entities described by their Transforms, hanging under two group nodes (Transform::update on the device)
+        std::vector<float> pos((size_t)n * 3), rot((size_t)n * 4), scl((size_t)n * 3, 1.f);
+        std::vector<int32_t> eparent((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            pos[(size_t)i * 3] = (float)((i % 40) - 20) * 1.5f; pos[(size_t)i * 3 + 1] = 0.f; pos[(size_t)i * 3 + 2] = (float)(i / 40) * 3.f;
+            const float h = 0.01f * (float)(i % 17);
+            rot[(size_t)i * 4] = 0.f; rot[(size_t)i * 4 + 1] = std::sin(h); rot[(size_t)i * 4 + 2] = 0.f; rot[(size_t)i * 4 + 3] = std::cos(h);
+            eparent[(size_t)i] = (int32_t)(i % 3) - 1;
+        }
+        const float npos[6] = {0.5f, 0.f, 1.f, -2.f, 0.25f, 0.f}, nrot[8] = {0, 0, 0, 1, 0, 0.0998334f, 0, 0.9950042f}, nscl[6] = {1, 1, 1, 1.25f, 1.25f, 1.25f};
+        const int32_t nparent[2] = {-1, 0};
+        CHECK(scene.setTransforms(pos.data(), rot.data(), scl.data(), bbox.data()).has_value(), "setTransforms");
+        CHECK(scene.setTransformNodes(2, npos, nrot, nscl, nparent, eparent.data()).has_value(), "setTransformNodes");
+        CHECK(scene.update(1 / 30.f).has_value(), "scene update with Transform-driven cull");
+        std::vector<float> nodeWorld(32), nodeInv(32);
+        orc_transform_nodes(2, npos, nrot, nscl, nparent, nodeWorld.data(), nodeInv.data());
+        std::vector<uint32_t> refBits((size_t)(n + 31) / 32);
+        orc_cull_batch_trs_parented(corners, pos.data(), rot.data(), scl.data(), bbox.data(), n, eparent.data(), nodeInv.data(), refBits.data(), nullptr, 1);
+        int culledTrs = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const bool ref = !((refBits[(size_t)i >> 5] >> (i & 31)) & 1u);
+            CHECK(scene.shouldEntityBeCulled(i) == ref, "Transform-driven cull of entity %ld", (long)i);
+            culledTrs += ref;
+        }
+        CHECK(culledTrs > 0 && culledTrs < n, "Transform-driven cull must see both outcomes (%d of %ld culled)", culledTrs, (long)n);
         std::printf("gpu: scene component, %ld animators x 51 frames, %d culled\n", (long)n, culled);
     }
     runDeviceAnimators(dir, o, def, rdef);

@@ -139,6 +139,50 @@ def test_crowd_cull_from_transforms(assets):
         g.close()
 
 
+def test_crowd_cull_under_transform_hierarchy(assets):
+    # Transform::update with parents (src/transform.cpp:300-305): node world / world inverse matrices and the entities'
+    # composed world inverses identical to the oracle's, visibility bit-exact
+    from tests.test_oracle_cull import make_forest
+    g = GpuRig(assets, with_mesh=False)
+    try:
+        n, m = 20_011, 77
+        tr = synth.make_transforms(n, seed=4, extent=30.0)
+        npos, nq, nscl, nparent = make_forest(m, seed=8)
+        rng = np.random.default_rng(2)
+        eparent = rng.integers(-1, m, n).astype(np.int32)
+        cr = synth.make_crowd(n, 1, len(assets.clips), seed=2)
+        crowd = g.crowd(n, 1, mesh=False)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight)
+        crowd.set_transforms(tr.position, tr.rotation, tr.scale, tr.bbox)
+        crowd.set_transform_nodes(npos, nq, nscl, nparent, eparent)
+        crowd.set_option(capi.OPT_KEEP_WORLD_INVERSE, 1)
+        vp = synth.sample_camera_view_proj()
+        crowd.set_camera(vp, 0.0)
+        crowd.step(0.0, capi.STEP_POSE | capi.STEP_CULL)
+        ref_world, ref_inv = O.transform_nodes(npos, nq, nscl, nparent)
+        world, inv = crowd.get_transform_nodes()
+        assert np.array_equal(world, ref_world) and np.array_equal(inv, ref_inv)
+        ref_bits, ref_wi = O.cull_batch_trs_parented(O.frustum_corners(vp, 0.0), tr.position, tr.rotation, tr.scale, tr.bbox, eparent, ref_inv)
+        assert np.array_equal(crowd.get_world_inverses(), ref_wi)
+        bits, count = crowd.get_visibility()
+        assert np.array_equal(bits, ref_bits) and 0 < count < n
+        # detaching gives the parent-less result again
+        crowd.set_transform_nodes(np.zeros((0, 3)), np.zeros((0, 4)), np.zeros((0, 3)), np.zeros(0), np.zeros(0))
+        crowd.step(0.0, capi.STEP_CULL)
+        bits, count = crowd.get_visibility()
+        assert np.array_equal(bits, O.cull_batch_trs(O.frustum_corners(vp, 0.0), tr.position, tr.rotation, tr.scale, tr.bbox))
+        # malformed forests are refused
+        bad = nparent.copy()
+        bad[3], bad[int(nparent[3]) if nparent[3] >= 0 else 5] = 5, 3
+        cyc = np.array([1, 0], np.int32)
+        with pytest.raises(capi.DmkError, match="deeper than 32"):
+            crowd.set_transform_nodes(npos[:2], nq[:2], nscl[:2], cyc, np.full(n, -1, np.int32))
+        with pytest.raises(capi.DmkError, match="parent node out of range"):
+            crowd.set_transform_nodes(npos, nq, nscl, nparent, np.full(n, m, np.int32))
+    finally:
+        g.close()
+
+
 def test_pipelined_visibility_readback(assets):
     # two frames in flight: the result of frame k is collected after frame k + 1 has been submitted
     g = GpuRig(assets, with_mesh=False)

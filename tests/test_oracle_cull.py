@@ -85,3 +85,58 @@ def test_transform_update_world_inverse():
     # identity transform: exact identity
     ident = O.transform_world_inverse([0, 0, 0], [0, 0, 0, 1], [1, 1, 1])
     assert np.array_equal(ident, np.eye(4, dtype=np.float32).reshape(16))
+
+
+def make_forest(m, seed=0):
+    """random transform forest in shuffled order (a parent may come after its child), depth <= 6"""
+    rng = np.random.default_rng(seed)
+    parent = np.full(m, -1, np.int32)
+    depth = np.zeros(m, np.int32)
+    order = rng.permutation(m)
+    for k, i in enumerate(order):
+        if k and rng.random() < 0.75:
+            cand = order[rng.integers(0, k)]
+            if depth[cand] < 5:
+                parent[i], depth[i] = cand, depth[cand] + 1
+    q = rng.normal(size=(m, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True).astype(np.float32)
+    pos = rng.uniform(-20, 20, (m, 3)).astype(np.float32)
+    scl = rng.uniform(0.5, 2.0, (m, 3)).astype(np.float32)
+    return pos, q, scl, parent
+
+
+def test_transform_hierarchy_matches_explicit_products():
+    # Transform::update with _parent (src/transform.cpp:300-305): world = parent.world * local,
+    # worldInverse = localInverse * parent.worldInverse, parents first
+    pos, q, scl, parent = make_forest(60, seed=3)
+    world, inv = O.transform_nodes(pos, q, scl, parent)
+    assert (parent >= 0).sum() > 30 and (parent == -1).sum() >= 1
+
+    def chain(i):
+        local = O.transform_local_matrix(pos[i], q[i], scl[i])
+        linv = O.transform_world_inverse(pos[i], q[i], scl[i])
+        if parent[i] < 0:
+            return local, linv
+        pw, pi = chain(parent[i])
+        return O.mat4_mul(pw, local), O.mat4_mul(linv, pi)
+
+    for i in range(60):
+        w, wi = chain(i)
+        assert np.array_equal(world[i], w) and np.array_equal(inv[i], wi), f"node {i}"
+        a = world[i].reshape(4, 4).T.astype(np.float64) @ inv[i].reshape(4, 4).T.astype(np.float64)
+        assert np.allclose(a, np.eye(4), atol=2e-3)
+
+
+def test_parented_cull_equals_cull_on_composed_inverse():
+    pos, q, scl, parent = make_forest(12, seed=5)
+    _, node_inv = O.transform_nodes(pos, q, scl, parent)
+    tr = synth.make_transforms(500, seed=9)
+    rng = np.random.default_rng(1)
+    ep = rng.integers(-1, 12, 500).astype(np.int32)
+    corners = O.frustum_corners(synth.sample_camera_view_proj(), 0.0)
+    bits, wi = O.cull_batch_trs_parented(corners, tr.position, tr.rotation, tr.scale, tr.bbox, ep, node_inv)
+    ref = O.cull_batch(corners, wi, tr.bbox)
+    assert np.array_equal(bits, ref)
+    free = ep < 0
+    bits_free, wi_free = O.cull_batch_trs(corners, tr.position, tr.rotation, tr.scale, tr.bbox, want_world_inverse=True)
+    assert np.array_equal(wi[free], wi_free[free])
