@@ -103,6 +103,7 @@ SIGNATURES = [
     ("dmk_crowd_get_models", _i, [_vp, _i64, _i64, _vp]),
     ("dmk_crowd_get_locals", _i, [_vp, _i64, _i64, _vp]),
     ("dmk_crowd_get_key_indices", _i, [_vp, _i64, _i64, _vp]),
+    ("dmk_crowd_get_bone_matrices", _i, [_vp, _i64, _i64, _vp, _vp, _vp]),
     ("dmk_crowd_get_skinned", _i, [_vp, _i64, _i64, _vp]),
     ("dmk_crowd_get_visibility", _i, [_vp, _vp, C.POINTER(_i64)]),
     ("dmk_crowd_collect_visibility", _i, [_vp, _vp, C.POINTER(_i64)]),
@@ -431,6 +432,15 @@ class Crowd:
     def get_key_indices(self, first=0, count=None):
         count = self.n - first if count is None else count
         return self._get(lib().dmk_crowd_get_key_indices, (self.num_layers, 3, self.skel.num_soa * 4, 2), np.int32, first, count)
+
+    def get_bone_matrices(self, direction=(1, 0, 0), first=0, count=None):
+        """getJointModelMatrixes(dir): (matrices [count][J][16], has_bone [J])"""
+        count = self.n - first if count is None else count
+        j = self.skel.num_joints
+        d = _f32(direction)
+        out, has = np.empty((count, j, 16), np.float32), np.empty(j, np.uint8)
+        self.ctx.check(lib().dmk_crowd_get_bone_matrices(self.h, first, count, _ptr(d), _ptr(out), _ptr(has)))
+        return out, has
 
     def get_skinned(self, first=0, count=None):
         count = self.n - first if count is None else count

@@ -1483,6 +1483,39 @@ dmk_status dmk_crowd_get_key_indices(dmk_crowd_t c, int64_t first, int64_t count
     DMK_CUDA(c->ctx, cudaMemcpyAsync(out, c->d_key_indices + first * per, count * per * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
     return finish_and_check(c);
 }
+dmk_status dmk_crowd_get_bone_matrices(dmk_crowd_t c, int64_t first, int64_t count, const float* dir, float* out, uint8_t* out_has_bone) {
+    if (dmk_status st = check_range(c, first, count, out)) return st;
+    dmk_context_t ctx = c->ctx;
+    if (!dir) return fail(ctx, DMK_ERR_INVALID, "null direction");
+    if (!c->d_models) return fail(ctx, DMK_ERR_INVALID, "enable DMK_OUT_MODELS with dmk_crowd_enable_outputs before the step");
+    const int J = c->skel->data.num_joints;
+    std::vector<int16_t> first_child(static_cast<size_t>(J), -1);
+    for (int i = 0; i < J; ++i) {
+        const int p = c->skel->data.parents[static_cast<size_t>(i)];
+        if (p >= 0 && first_child[static_cast<size_t>(p)] < 0) first_child[static_cast<size_t>(p)] = static_cast<int16_t>(i);
+    }
+    if (out_has_bone)
+        for (int i = 0; i < J; ++i) out_has_bone[i] = first_child[static_cast<size_t>(i)] >= 0;
+    if (count == 0) return DMK_OK;
+    int16_t* d_first = nullptr;
+    float* d_out = nullptr;
+    DMK_CUDA(ctx, upload(ctx, &d_first, first_child));
+    cudaError_t e = dev_alloc(&d_out, static_cast<size_t>(count) * J * 16);
+    // angleAxis(pi, axis) of glm::rotation's opposite-direction case: sin / cos of pi / 2 in float, from the host's libm
+    const float half = 3.14159265358979323846264338327950288f * 0.5f;
+    if (e == cudaSuccess)
+        e = launch_bone_matrices(c->d_models + first * J * 16, d_first, J, count, dir, std::sin(half), std::cos(half), d_out, ctx->stream);
+    ++ctx->launches;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, static_cast<size_t>(count) * J * 64, cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    dev_free(d_first);
+    dev_free(d_out);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "bone matrices");
+    if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "bone matrices");
+    if (*c->h_error != 0)
+        return fail(ctx, DMK_ERR_INVALID, "character " + std::to_string(*c->h_error - 1) + " references a clip outside the clip set");
+    return DMK_OK;
+}
 dmk_status dmk_crowd_get_skinned(dmk_crowd_t c, int64_t first, int64_t count, float* out) {
     if (dmk_status st = check_range(c, first, count, out)) return st;
     if (!c->d_skinned) return fail(c->ctx, DMK_ERR_INVALID, "crowd has no mesh");

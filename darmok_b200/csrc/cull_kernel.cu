@@ -47,17 +47,18 @@ __device__ __forceinline__ bool box_in_front(V3 a, V3 b, V3 c, V3 mn, V3 mx) {
 // Transform::update (src/transform.cpp:286-309): _localMatrix = glm::translate(p) * glm::mat4_cast(q) * glm::scale(s),
 // _localInverse = glm::inverse(_localMatrix), all in glm's scalar operation order.  m[column][row].
 // The two products only add exact zeros to R[c][r] * s[c] and to p, so the local matrix is [R * diag(s) | p].
-__device__ __forceinline__ void local_from_trs(const float* __restrict__ pos, const float* __restrict__ rot, const float* __restrict__ scl, int64_t i,
-                                               float m[4][4]) {
-    const float px = __ldg(pos + i * 3), py = __ldg(pos + i * 3 + 1), pz = __ldg(pos + i * 3 + 2);
-    const float4 q = __ldg(reinterpret_cast<const float4*>(rot) + i);
-    const float sx = __ldg(scl + i * 3), sy = __ldg(scl + i * 3 + 1), sz = __ldg(scl + i * 3 + 2);
+__device__ __forceinline__ void local_from_values(float px, float py, float pz, float4 q, float sx, float sy, float sz, float m[4][4]) {
     const float qxx = q.x * q.x, qyy = q.y * q.y, qzz = q.z * q.z, qxz = q.x * q.z, qxy = q.x * q.y, qyz = q.y * q.z;
     const float qwx = q.w * q.x, qwy = q.w * q.y, qwz = q.w * q.z;
     m[0][0] = (1.f - 2.f * (qyy + qzz)) * sx; m[0][1] = (2.f * (qxy + qwz)) * sx;       m[0][2] = (2.f * (qxz - qwy)) * sx;       m[0][3] = 0.f;
     m[1][0] = (2.f * (qxy - qwz)) * sy;       m[1][1] = (1.f - 2.f * (qxx + qzz)) * sy; m[1][2] = (2.f * (qyz + qwx)) * sy;       m[1][3] = 0.f;
     m[2][0] = (2.f * (qxz + qwy)) * sz;       m[2][1] = (2.f * (qyz - qwx)) * sz;       m[2][2] = (1.f - 2.f * (qxx + qyy)) * sz; m[2][3] = 0.f;
     m[3][0] = px; m[3][1] = py; m[3][2] = pz; m[3][3] = 1.f;
+}
+__device__ __forceinline__ void local_from_trs(const float* __restrict__ pos, const float* __restrict__ rot, const float* __restrict__ scl, int64_t i,
+                                               float m[4][4]) {
+    local_from_values(__ldg(pos + i * 3), __ldg(pos + i * 3 + 1), __ldg(pos + i * 3 + 2), __ldg(reinterpret_cast<const float4*>(rot) + i),
+                      __ldg(scl + i * 3), __ldg(scl + i * 3 + 1), __ldg(scl + i * 3 + 2), m);
 }
 
 // glm::detail::compute_inverse<4, 4>
@@ -309,6 +310,63 @@ cudaError_t launch_cull(const CullParams& p, cudaStream_t stream) {
     const int64_t blocks = (p.n + 255) / 256;
     if (p.position) cull_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p);
     else cull_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// SkeletalAnimatorImpl::getJointModelMatrixes(dir) (src/skeleton_ozz.cpp:979-1004): the debug-bone matrix from joint p to its
+// first child, Math::transform(parentPos, glm::rotation(dir, normalize(diff)), vec3(length(diff))).  models are the
+// converted (left-handed) joint matrices the crowd keeps for getJointModelMatrix.  One thread per (character, joint).
+__global__ void __launch_bounds__(128) bone_matrices_kernel(const float* __restrict__ models, const int16_t* __restrict__ first_child, int num_joints,
+                                                            int64_t count, float dx, float dy, float dz, float half_turn_sin, float half_turn_cos,
+                                                            float* __restrict__ out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= count * num_joints) return;
+    const int64_t c = tid / num_joints;
+    const int p = (int)(tid - c * num_joints);
+    float4* o = reinterpret_cast<float4*>(out + tid * 16);
+    const int child = first_child[p];
+    if (child < 0) {
+        o[0] = o[1] = o[2] = o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float4 pp = __ldg(reinterpret_cast<const float4*>(models + (c * num_joints + p) * 16) + 3);
+    const float4 cp = __ldg(reinterpret_cast<const float4*>(models + (c * num_joints + child) * 16) + 3);
+    const float fx = cp.x - pp.x, fy = cp.y - pp.y, fz = cp.z - pp.z;
+    const float len2 = (fx * fx + fy * fy) + fz * fz;
+    const float inv = __frcp_rn(__fsqrt_rn(len2));   // glm::normalize = v * inversesqrt(dot(v, v))
+    const float nx = fx * inv, ny = fy * inv, nz = fz * inv;
+    // glm::rotation(orig = dir, dest = n) (glm/gtx/quaternion.inl)
+    const float eps = 1.1920929e-07f;
+    const float cos_theta = (dx * nx + dy * ny) + dz * nz;
+    float4 q;
+    if (cos_theta >= 1.f - eps) {
+        q = make_float4(0.f, 0.f, 0.f, 1.f);
+    } else if (cos_theta < -1.f + eps) {
+        float ax = 0.f * dz - dy * 1.f, ay = 1.f * dx - dz * 0.f, az = 0.f * dy - dx * 0.f;   // cross((0,0,1), dir)
+        if ((ax * ax + ay * ay) + az * az < eps) {                                             // cross((1,0,0), dir)
+            ax = 0.f * dz - dy * 0.f; ay = 0.f * dx - dz * 1.f; az = 1.f * dy - dx * 0.f;
+        }
+        const float ainv = __frcp_rn(__fsqrt_rn((ax * ax + ay * ay) + az * az));
+        q = make_float4(ax * ainv * half_turn_sin, ay * ainv * half_turn_sin, az * ainv * half_turn_sin, half_turn_cos);
+    } else {
+        const float ax = dy * nz - ny * dz, ay = dz * nx - nz * dx, az = dx * ny - nx * dy;
+        const float s = __fsqrt_rn((1.f + cos_theta) * 2.f);
+        const float invs = __frcp_rn(s);
+        q = make_float4(ax * invs, ay * invs, az * invs, s * 0.5f);
+    }
+    const float len = __fsqrt_rn(len2);
+    float m[4][4];
+    local_from_values(pp.x, pp.y, pp.z, q, len, len, len, m);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = make_float4(m[k][0], m[k][1], m[k][2], m[k][3]);
+}
+
+cudaError_t launch_bone_matrices(const float* models, const int16_t* first_child, int num_joints, int64_t count, const float* dir, float half_turn_sin,
+                                 float half_turn_cos, float* out, cudaStream_t stream) {
+    const int64_t threads = count * num_joints;
+    if (threads <= 0) return cudaSuccess;
+    bone_matrices_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(models, first_child, num_joints, count, dir[0], dir[1], dir[2],
+                                                                                half_turn_sin, half_turn_cos, out);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,9 @@ cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream, i
 
 // K4 (cull_kernel.cu, built with -fmad=false): visibility bitmask; then ordered compaction of visible ids
 cudaError_t launch_cull(const CullParams& p, cudaStream_t stream);
+// getJointModelMatrixes(dir): debug-bone matrices [count][J][16] from the converted joint matrices [count][J][16]
+cudaError_t launch_bone_matrices(const float* models, const int16_t* first_child, int num_joints, int64_t count, const float* dir, float half_turn_sin,
+                                 float half_turn_cos, float* out, cudaStream_t stream);
 // Transform::update over the group nodes (parents first), any node order, chains up to 32 deep
 cudaError_t launch_transform_nodes(const float* pos, const float* rot, const float* scl, const int32_t* parent, int num_nodes, float* world,
                                    float* world_inverse, cudaStream_t stream);

@@ -246,6 +246,8 @@ public:
     expected<void, std::string> setSkinning(const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh = nullptr) noexcept;
 
     glm::mat4 getJointModelMatrix(const std::string& node) const noexcept;
+    // debug-bone matrices keyed by joint name (src/skeleton_ozz.cpp:979-1004), what RenderableSkeleton::update consumes
+    std::unordered_map<std::string, glm::mat4> getJointModelMatrixes(const glm::vec3& dir = {1.f, 0.f, 0.f}) const noexcept;
     std::vector<glm::mat4> getSkinningPalette() const noexcept;   // what beforeRenderEntity uploads as u_skinning
     std::vector<float> getSkinnedVertices() const noexcept;       // [V][9] position, normal, tangent
 

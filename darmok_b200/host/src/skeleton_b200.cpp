@@ -459,6 +459,23 @@ glm::mat4 SkeletalAnimator::getJointModelMatrix(const std::string& node) const n
     return _modelsCache[static_cast<size_t>(joint)];
 }
 
+std::unordered_map<std::string, glm::mat4> SkeletalAnimator::getJointModelMatrixes(const glm::vec3& dir) const noexcept {
+    std::unordered_map<std::string, glm::mat4> out;
+    if (!_skeleton) return out;
+    if (!_batch && !_device && !const_cast<SkeletalAnimator*>(this)->ensureDevice()) return out;
+    dmk_crowd_t crowd = _batch ? _batch->crowd() : _device->crowd;
+    if (!crowd) return out;
+    const int J = _skeleton->getNumJoints();
+    std::vector<glm::mat4> bones(static_cast<size_t>(J));
+    std::vector<uint8_t> has(static_cast<size_t>(J));
+    const float d[3] = {dir.x, dir.y, dir.z};
+    if (dmk_crowd_get_bone_matrices(crowd, _batch ? _batchIndex : 0, 1, d, glm::value_ptr(bones[0]), has.data()) != DMK_OK) return out;
+    out.reserve(static_cast<size_t>(J));
+    for (int j = 0; j < J; ++j)
+        if (has[static_cast<size_t>(j)]) out.emplace(std::string(_skeleton->getJointName(j)), bones[static_cast<size_t>(j)]);
+    return out;
+}
+
 std::vector<glm::mat4> SkeletalAnimator::getSkinningPalette() const noexcept {
     // SkeletalAnimationRenderComponent::beforeRenderEntity (src/skeleton.cpp:236-249): [mat4(1)] + model * inverseBindPose
     if (!_batch && !_device) const_cast<SkeletalAnimator*>(this)->ensureDevice();

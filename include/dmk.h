@@ -321,6 +321,14 @@ DMK_API dmk_status dmk_crowd_get_locals(dmk_crowd_t crowd, int64_t first, int64_
 DMK_API dmk_status dmk_crowd_get_key_indices(dmk_crowd_t crowd, int64_t first, int64_t count, int32_t* out);
 DMK_API dmk_status dmk_crowd_get_skinned(dmk_crowd_t crowd, int64_t first, int64_t count, float* out); /* [count][V][9] */
 DMK_API dmk_status dmk_crowd_get_visibility(dmk_crowd_t crowd, uint32_t* out_bits, int64_t* out_visible_count);
+/* SkeletalAnimator::getJointModelMatrixes(dir) (src/skeleton_ozz.cpp:979-1004), the matrices RenderableSkeleton draws its
+ * debug bones with (src/skeleton.cpp:62-113): for every joint that has a child, Math::transform(jointPos,
+ * glm::rotation(dir, normalize(childPos - jointPos)), vec3(|childPos - jointPos|)) towards its FIRST child (the
+ * reference's map is keyed by the parent's name and emplace keeps the first).  dir [3] (the reference's default is
+ * (1, 0, 0)); out [count][J][16], zero for leaves; out_has_bone [J] (may be NULL): 1 where the map has an entry.
+ * Needs DMK_OUT_MODELS. */
+DMK_API dmk_status dmk_crowd_get_bone_matrices(dmk_crowd_t crowd, int64_t first, int64_t count, const float* dir, float* out,
+                                               uint8_t* out_has_bone);
 /* Pipelined frame loops: result of the OLDEST step issued with DMK_STEP_READBACK_VISIBILITY that has not been collected
  * yet (at most two may be outstanding).  Waits only for that step's cull + copy, not for work enqueued after it, so the
  * next frame can already be running: FrustumCuller's set for frame k is read while frame k + 1 executes. */

@@ -124,6 +124,11 @@ void orc_palette(const float* models, int num_joints, const int32_t* remap, cons
 /* name -> joint index by linear string compare (src/skeleton_ozz.cpp:968-975); -1 if absent */
 int orc_skeleton_find_joint(const orc_skeleton* s, const char* name);
 
+/* SkeletalAnimator::getJointModelMatrixes(dir) (src/skeleton_ozz.cpp:979-1004): the debug-bone matrix of every joint that has
+ * a child (bone to its FIRST child, keyed by the parent's name); out 16 floats per joint, has[j] = 0 for leaves.
+ * models are the right-handed ozz matrices. */
+void orc_bone_matrices(const orc_skeleton* s, const float* models, const float* dir, float* out, uint8_t* has);
+
 /* ---- LBS vertex shader (assets/shaders/core/darmok_skinning.inc.slang:5-28, forward.slang:33-38) ----
  * indices/weights are float4 per vertex; out = 9 floats per vertex: pos.xyz, normal.xyz, tangent.xyz. */
 void orc_skin(const float* palette, int palette_size, const float* pos, const float* nrm, const float* tan,

@@ -76,6 +76,8 @@ def lib():
         L.orc_transform_world_inverse.argtypes = [C.c_void_p] * 4
         L.orc_transform_local_matrix.argtypes = [C.c_void_p] * 4
         L.orc_cull_batch_trs.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_bone_matrices.argtypes = [C.c_void_p] * 5
+        L.orc_bone_matrices.restype = None
         L.orc_transform_nodes.argtypes = [C.c_int] + [C.c_void_p] * 6
         L.orc_transform_nodes.restype = None
         L.orc_cull_batch_trs_parented.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -289,6 +291,15 @@ def cull_batch_trs(corners, position, rotation, scale, bbox, num_threads=None, w
     wi = np.zeros((n, 16), np.float32) if want_world_inverse else None
     lib().orc_cull_batch_trs(_p(c), _p(p), _p(q), _p(s), _p(b), n, _p(bits), _p(wi), num_threads or max_threads())
     return (bits, wi) if want_world_inverse else bits
+
+
+def bone_matrices(skel, models, direction=(1, 0, 0)):
+    """getJointModelMatrixes(dir): (matrices [J][16], has [J])"""
+    m, d = _f32(models), _f32(direction)
+    j = skel.num_joints
+    out, has = np.zeros((j, 16), np.float32), np.zeros(j, np.uint8)
+    lib().orc_bone_matrices(skel.h, _p(m), _p(d), _p(out), _p(has))
+    return out, has
 
 
 def transform_nodes(position, rotation, scale, parent):

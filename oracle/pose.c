@@ -243,3 +243,76 @@ void orc_skin(const float* palette, int palette_size, const float* pos, const fl
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * SkeletalAnimatorImpl::getJointModelMatrixes(dir) (src/skeleton_ozz.cpp:979-1004), the debug-bone matrices
+ * RenderableSkeleton draws (src/skeleton.cpp:62-113): for every joint i with a parent p, keyed by the PARENT's name
+ * (unordered_map::emplace: the first child of a parent wins):
+ *   parentPos = convert(models[p])[3], childPos = convert(models[i])[3], diff = childPos - parentPos
+ *   mat = Math::transform(parentPos, glm::rotation(dir, normalize(diff)), vec3(length(diff)))
+ * glm::rotation (glm/gtx/quaternion.inl, restated from the published source; glm is not in the container):
+ * identity when cos >= 1 - eps, a half turn about a perpendicular axis when cos < -1 + eps, else Stan Melax's form.
+ * out: 16 floats per joint (entry of joint p = the bone from p to its first child), has[p] = 0 for joints without children.
+ * ---------------------------------------------------------------------------------------------- */
+static void glm_rotation(const float* orig, const float* dest, float* q /* x y z w */) {
+    const float eps = 1.1920929e-07f; /* glm::epsilon<float>() */
+    const float cos_theta = (orig[0] * dest[0] + orig[1] * dest[1]) + orig[2] * dest[2];
+    float axis[3];
+    if (cos_theta >= 1.f - eps) {
+        q[0] = q[1] = q[2] = 0.f;
+        q[3] = 1.f;
+        return;
+    }
+    if (cos_theta < -1.f + eps) {
+        /* cross((0,0,1), orig), or cross((1,0,0), orig) when that is (nearly) zero */
+        axis[0] = 0.f * orig[2] - orig[1] * 1.f;
+        axis[1] = 1.f * orig[0] - orig[2] * 0.f;
+        axis[2] = 0.f * orig[1] - orig[0] * 0.f;
+        if ((axis[0] * axis[0] + axis[1] * axis[1]) + axis[2] * axis[2] < eps) {
+            axis[0] = 0.f * orig[2] - orig[1] * 0.f;
+            axis[1] = 0.f * orig[0] - orig[2] * 1.f;
+            axis[2] = 1.f * orig[1] - orig[0] * 0.f;
+        }
+        const float inv = 1.f / sqrtf((axis[0] * axis[0] + axis[1] * axis[1]) + axis[2] * axis[2]);
+        /* angleAxis(pi, axis): s = sin(pi / 2), w = cos(pi / 2) in float */
+        const float half = 3.14159265358979323846264338327950288f * 0.5f;
+        const float s = sinf(half);
+        q[0] = axis[0] * inv * s;
+        q[1] = axis[1] * inv * s;
+        q[2] = axis[2] * inv * s;
+        q[3] = cosf(half);
+        return;
+    }
+    axis[0] = orig[1] * dest[2] - dest[1] * orig[2];
+    axis[1] = orig[2] * dest[0] - dest[2] * orig[0];
+    axis[2] = orig[0] * dest[1] - dest[0] * orig[1];
+    const float s = sqrtf((1.f + cos_theta) * 2.f);
+    const float invs = 1.f / s;
+    q[0] = axis[0] * invs;
+    q[1] = axis[1] * invs;
+    q[2] = axis[2] * invs;
+    q[3] = s * 0.5f;
+}
+
+void orc_bone_matrices(const orc_skeleton* s, const float* models, const float* dir, float* out, uint8_t* has) {
+    const int n = s->num_joints;
+    memset(out, 0, (size_t)n * 16 * sizeof(float));
+    memset(has, 0, (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const int p = s->parents[i];
+        if (p == ORC_NO_PARENT || has[p]) continue; /* emplace keeps the first child's entry */
+        float pm[16], cm[16];
+        orc_flip_handedness(models + (size_t)p * 16, pm);
+        orc_flip_handedness(models + (size_t)i * 16, cm);
+        const float diff[3] = {cm[12] - pm[12], cm[13] - pm[13], cm[14] - pm[14]};
+        const float len2 = (diff[0] * diff[0] + diff[1] * diff[1]) + diff[2] * diff[2];
+        const float inv = 1.f / sqrtf(len2); /* glm::normalize = v * inversesqrt(dot(v, v)) */
+        const float nd[3] = {diff[0] * inv, diff[1] * inv, diff[2] * inv};
+        float q[4];
+        glm_rotation(dir, nd, q);
+        const float len = sqrtf(len2); /* glm::length */
+        const float scale[3] = {len, len, len};
+        orc_transform_local_matrix(pm + 12, q, scale, out + (size_t)p * 16);
+        has[p] = 1;
+    }
+}

@@ -612,6 +612,26 @@ static int runGpu(const std::string& dir) {
             for (size_t e = 0; e < skinned.size(); ++e) CHECK(close(sk[e], skinned[e]), "step %d skinned %zu: %g vs %g", step, e, sk[e], skinned[e]);
         }
         CHECK(animator.getJointModelMatrix("no_such_joint") == glm::mat4(1.f), "unknown joint must give identity (C12)");
+        {   // debug bones (getJointModelMatrixes, src/skeleton_ozz.cpp:979-1004) against the oracle on the reference animator's matrices
+            std::vector<float> bones((size_t)J * 16);
+            std::vector<uint8_t> has((size_t)J);
+            const float dir[3] = {1.f, 0.f, 0.f};
+            orc_bone_matrices(o.skel, ref.models().data(), dir, bones.data(), has.data());
+            const auto map = animator.getJointModelMatrixes();
+            size_t expected = 0;
+            for (int j = 0; j < J; ++j) {
+                if (!has[(size_t)j]) { CHECK(!map.contains(o.skel->names[j]), "leaf joint %d has no bone entry", j); continue; }
+                ++expected;
+                const auto itr = map.find(o.skel->names[j]);
+                CHECK(itr != map.end(), "bone entry of joint %d", j);
+                if (itr == map.end()) continue;
+                for (int e = 0; e < 16; ++e) {
+                    const float a = glm::value_ptr(itr->second)[e], b = bones[(size_t)j * 16 + e];
+                    CHECK(std::fabs(a - b) <= 2e-5f + 2e-4f * std::fabs(b), "bone %d element %d: %g vs %g", j, e, a, b);
+                }
+            }
+            CHECK(map.size() == expected && expected > 10, "bone map size %zu vs %zu", map.size(), expected);
+        }
         CHECK(animator.getPlaybackState() == SkeletalAnimatorPlaybackState::Paused, "pause toggled once and a state is playing");
         std::printf("gpu: stand-alone animator, %d ticks compared with matrices/palette/skin, %zu events\n", checked, log.events.size());
     }

@@ -335,3 +335,38 @@ def test_max_joint_skeleton_models(joints):
         assert_close(crowd.get_models(), flipped, f"models J={joints}")
     finally:
         g.close()
+
+
+@pytest.mark.gpu
+def test_debug_bone_matrices(assets):
+    # SkeletalAnimator::getJointModelMatrixes(dir) (src/skeleton_ozz.cpp:979-1004) for a whole crowd
+    from darmok_b200 import capi
+    from oracle import oracle_py as O
+    g, o = GpuRig(assets, with_mesh=False), OracleRig(assets)
+    try:
+        n = 301
+        cr = synth.make_crowd(n, 2, len(assets.clips), seed=11)
+        crowd = g.crowd(n, 2, mesh=False)
+        crowd.enable_outputs(capi.OUT_MODELS)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, threshold=0.1)
+        crowd.step(0.0, capi.STEP_POSE)
+        models = crowd.get_models()            # converted (left-handed) matrices, as getJointModelMatrix returns them
+        ref_models = o.crowd(n, 2).step(cr.clip, cr.ratio, cr.weight, 0.1, want=("models",))["models"]
+        for direction in ((1, 0, 0), (0.6, 0, 0.8)):
+            bones, has = crowd.get_bone_matrices(direction)
+            assert has.sum() > 10 and (has == 0).sum() > 0
+            for c in range(0, n, 13):
+                # same arithmetic on the same joint matrices: bit-identical (flipHandedness is an exact sign flip)
+                ozz = np.stack([O.flip_handedness(m) for m in models[c]])
+                exact, ref_has = O.bone_matrices(o.skel, ozz, direction)
+                assert np.array_equal(has, ref_has)
+                assert np.array_equal(bones[c], exact), f"character {c}"
+                # and against the oracle's own pose chain within the pose tolerance (the bone direction is a difference of
+                # two joint positions, so their 1e-6 errors show up relative to the bone length)
+                full, _ = O.bone_matrices(o.skel, ref_models[c], direction)
+                assert np.allclose(bones[c], full, rtol=2e-4, atol=2e-5), f"character {c}"
+        part, _ = crowd.get_bone_matrices((1, 0, 0), first=7, count=5)
+        full, _ = crowd.get_bone_matrices((1, 0, 0))
+        assert np.array_equal(part, full[7:12])
+    finally:
+        g.close()

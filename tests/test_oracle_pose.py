@@ -150,3 +150,37 @@ def test_crowd_step_equals_composition_of_jobs(assets):
         assert np.array_equal(res["palette"][i], pal)
         m = assets.mesh
         assert np.array_equal(res["skinned"][i], O.skin(pal, m.pos, m.nrm, m.tan, m.indices, m.weights))
+
+
+def test_bone_matrices_map_the_direction_onto_the_child(assets):
+    # getJointModelMatrixes(dir) (src/skeleton_ozz.cpp:979-1004): Math::transform(parentPos, rotation(dir, normalize(diff)), |diff|)
+    skel = O.Skeleton(assets.skel.archive)
+    clip = O.Animation(assets.clips[1].archive)
+    ctx = O.SamplingContext(skel.num_joints)
+    locals_, _ = ctx.sample(clip, 0.37, skel.num_soa)
+    models = skel.local_to_model(locals_)
+    parents = skel.parents()
+    for direction in ((1, 0, 0), (0, 1, 0), (0, 0, -1)):
+        mats, has = O.bone_matrices(skel, models, direction)
+        first_child = {}
+        for i, p in enumerate(parents):
+            if p >= 0:
+                first_child.setdefault(int(p), i)
+        assert set(np.flatnonzero(has)) == set(first_child)
+        assert not mats[has == 0].any()
+        d = np.array([*direction, 1.0])
+        for p, c in first_child.items():
+            m = mats[p].reshape(4, 4).T.astype(np.float64)
+            pm, cm = O.flip_handedness(models[p]), O.flip_handedness(models[c])
+            assert np.array_equal(mats[p][12:15], pm[12:15])                       # origin at the parent joint
+            assert np.allclose((m @ d)[:3], cm[12:15], atol=2e-5), (p, c)           # dir lands on the child joint
+            length = np.linalg.norm(cm[12:15].astype(np.float64) - pm[12:15])
+            assert np.allclose(np.linalg.norm(m[:3, :3], axis=0), length, rtol=1e-5)
+    # opposite direction: the half turn about a perpendicular axis still maps dir onto the child
+    root_child = next(i for i, p in enumerate(parents) if p == 0)
+    pm, cm = O.flip_handedness(models[0]), O.flip_handedness(models[root_child])
+    diff = (cm[12:15] - pm[12:15]).astype(np.float64)
+    opposite = (-diff / np.linalg.norm(diff)).astype(np.float32)
+    mats, _ = O.bone_matrices(skel, models, opposite)
+    m = mats[0].reshape(4, 4).T.astype(np.float64)
+    assert np.allclose((m @ np.array([*opposite, 1.0]))[:3], cm[12:15], atol=1e-4)
