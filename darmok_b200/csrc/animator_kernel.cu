@@ -234,8 +234,40 @@ __device__ __forceinline__ void set_group(PoseProgram& prog, int k, const GroupO
     else { prog.n1 = (uint8_t)g.count; prog.rest1 = (uint8_t)g.rest; prog.mode1 = mode; prog.threshold1 = g.threshold; }
 }
 
-__global__ void __launch_bounds__(128) animator_kernel(const AnimatorParams p) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Characters of one block are regrouped by situation (state, or transition into a state, or a pending command) before the
+// tick so that a warp's lanes run the same control flow: with one thread per character in id order a warp executed the
+// union of ~4 situations at 4.9 active lanes per instruction (ncu).  The regrouping stays inside the block's window of
+// consecutive ids, so the structure-of-arrays accesses still fall into the same few cache lines.
+constexpr int kAnimBlock = 256;
+constexpr int kAnimKeys = 64;
+
+__global__ void __launch_bounds__(kAnimBlock) animator_kernel(const AnimatorParams p) {
+    __shared__ int key_count[kAnimKeys];
+    __shared__ uint16_t order[kAnimBlock];
+    const int64_t block_base = (int64_t)blockIdx.x * kAnimBlock;
+    {
+        if (threadIdx.x < kAnimKeys) key_count[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t mine = block_base + threadIdx.x;
+        int key = kAnimKeys - 1;   // past the end of the crowd: sorted last, exits below
+        if (mine < p.n) {
+            const int t = p.transition_def[mine];
+            const int def = slot_of(p, t >= 0 ? kSlotCur : kSlotState, mine).geti(kWDef);
+            if (p.cmd_state[mine] != -2) key = kAnimKeys - 2;                      // commands restructure: keep them together
+            else if (def < 0) key = 0;                                             // nothing playing
+            else key = 1 + min(2 * def + (t >= 0 ? 1 : 0), kAnimKeys - 4);         // (state, in transition)
+        }
+        const int rank = atomicAdd(&key_count[key], 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {   // exclusive scan of 64 counters
+            int sum = 0;
+            for (int k = 0; k < kAnimKeys; ++k) { const int v = key_count[k]; key_count[k] = sum; sum += v; }
+        }
+        __syncthreads();
+        order[key_count[key] + rank] = (uint16_t)threadIdx.x;
+        __syncthreads();
+    }
+    const int64_t c = block_base + order[threadIdx.x];
     if (c >= p.n) return;
     const Slot st = slot_of(p, kSlotState, c), prev = slot_of(p, kSlotPrev, c), cur = slot_of(p, kSlotCur, c);
     Character a;
@@ -376,7 +408,7 @@ cudaError_t launch_animator_query(const AnimatorParams& p, AnimStateInfo* out, c
 
 cudaError_t launch_animator(const AnimatorParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    animator_kernel<<<(unsigned)((p.n + 127) / 128), 128, 0, stream>>>(p);
+    animator_kernel<<<(unsigned)((p.n + kAnimBlock - 1) / kAnimBlock), kAnimBlock, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
