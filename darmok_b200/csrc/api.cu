@@ -1456,7 +1456,8 @@ static dmk_status check_range(dmk_crowd_t c, int64_t first, int64_t count, const
 
 dmk_status dmk_crowd_get_palette(dmk_crowd_t c, int64_t first, int64_t count, float* out) {
     if (dmk_status st = check_range(c, first, count, out)) return st;
-    if (!c->d_palette) return fail(c->ctx, DMK_ERR_INVALID, "crowd has no armature");
+    if (!c->arm) return fail(c->ctx, DMK_ERR_INVALID, "crowd has no armature");
+    if (count == 0) return DMK_OK;
     const size_t per = static_cast<size_t>(c->arm->num_joints + 1) * 16;
     DMK_CUDA(c->ctx, cudaMemcpyAsync(out, c->d_palette + first * per, count * per * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
     return finish_and_check(c);
@@ -1518,7 +1519,8 @@ dmk_status dmk_crowd_get_bone_matrices(dmk_crowd_t c, int64_t first, int64_t cou
 }
 dmk_status dmk_crowd_get_skinned(dmk_crowd_t c, int64_t first, int64_t count, float* out) {
     if (dmk_status st = check_range(c, first, count, out)) return st;
-    if (!c->d_skinned) return fail(c->ctx, DMK_ERR_INVALID, "crowd has no mesh");
+    if (!c->mesh) return fail(c->ctx, DMK_ERR_INVALID, "crowd has no mesh");
+    if (count == 0) return DMK_OK;
     const size_t pitch = static_cast<size_t>(c->mesh->vpad) * 9, row = static_cast<size_t>(c->mesh->num_vertices) * 9;
     DMK_CUDA(c->ctx, cudaMemcpy2DAsync(out, row * 4, c->d_skinned + first * pitch, pitch * 4, row * 4, count, cudaMemcpyDeviceToHost,
                                        c->ctx->stream));
@@ -1562,7 +1564,8 @@ dmk_status dmk_crowd_get_ratios(dmk_crowd_t c, float* out_ratio, uint8_t* out_lo
 dmk_status dmk_crowd_pack_visible_palettes(dmk_crowd_t c, float* out_dev, int64_t capacity) {
     if (!c) return DMK_ERR_INVALID;
     if (!out_dev || capacity < 0) return fail(c->ctx, DMK_ERR_INVALID, "null output");
-    if (!c->d_palette || !c->culled_once) return fail(c->ctx, DMK_ERR_INVALID, "needs an armature and a cull step");
+    if (!c->arm || !c->culled_once) return fail(c->ctx, DMK_ERR_INVALID, "needs an armature and a cull step");
+    if (c->n == 0) return DMK_OK;
     if (bind(c->ctx)) return DMK_ERR_CUDA;
     {
         KernelTimer timer(c->ctx, DMK_KERNEL_PACK);
