@@ -129,9 +129,10 @@ def lib():
     """Loads the in-tree shared library.  Raises loudly if it has not been built (python -m darmok_b200.build)."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -m darmok_b200.build` (there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        path = os.environ.get("DMK_LIBRARY", LIB_PATH)   # DMK_LIBRARY: an experimental build (tools/build_variant.py)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} is missing: run `python -m darmok_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(path)
         for name, res, args in SIGNATURES:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args

@@ -53,11 +53,17 @@ struct Bracket {
     uint2 v0, v1;
 };
 
+// F: compile-time shape of the sampling path, so that the common case carries no dead branches:
+//   kBuckets  the clip set has a bucket table (else per-track binary search)
+//   kKeys     the ozz key-stream indices are written out (parity tests only)
+enum : int { kBuckets = 1, kKeys = 2 };
+
+template <int F>
 __device__ __forceinline__ Bracket fetch_bracket(const ClipSetDev& cs, int comp, int clip, int track, float t,
                                                  int32_t* key_out) {
     Bracket k;
     const int P = cs.padded_tracks;
-    if (cs.bucket_dir) {
+    if (F & kBuckets) {
         // bucket table: one coalesced 40-byte entry per (bucket, track)
         const uint2 bd = __ldg(cs.bucket_dir + clip);
         const int G = (int)bd.y;
@@ -72,7 +78,7 @@ __device__ __forceinline__ Bracket fetch_bracket(const ClipSetDev& cs, int comp,
         k.r1 = lower ? a.y : a.z;
         k.v0 = lower ? make_uint2(vb.x, vb.y) : make_uint2(vb.z, vb.w);
         k.v1 = lower ? make_uint2(vb.z, vb.w) : vc;
-        if (key_out) {
+        if (F & kKeys) {
             const uint2 d = __ldg(cs.dir + (size_t)(clip * 3 + comp) * P + track);
             const int right = (int)d.x + __float_as_int(a.w) + (lower ? 0 : 1);
             key_out[0] = __ldg(cs.stream[comp] + right - 1);
@@ -87,7 +93,7 @@ __device__ __forceinline__ Bracket fetch_bracket(const ClipSetDev& cs, int comp,
     k.r1 = __ldg(cs.ratio[comp] + r);
     k.v0 = __ldg(cs.value[comp] + l);
     k.v1 = __ldg(cs.value[comp] + r);
-    if (key_out) {
+    if (F & kKeys) {
         key_out[0] = __ldg(cs.stream[comp] + l);
         key_out[1] = __ldg(cs.stream[comp] + r);
     }
@@ -99,9 +105,10 @@ __device__ __forceinline__ float half_bits_to_float(unsigned h) {
 }
 
 // Float3 track (translation or scale): DecompressFloat3 + Lerp
+template <int F>
 __device__ __forceinline__ void sample_f3(const ClipSetDev& cs, int comp, int clip, int track, float t, float out[3],
                                           int32_t* key_out) {
-    const Bracket k = fetch_bracket(cs, comp, clip, track, t, key_out);
+    const Bracket k = fetch_bracket<F>(cs, comp, clip, track, t, key_out);
     const float r0 = k.r0, r1 = k.r1;
     const uint2 v0 = k.v0, v1 = k.v1;
     const float alpha = (t - r0) * rcp_exact(r1 - r0);
@@ -131,9 +138,10 @@ __device__ __forceinline__ void decode_quat(uint2 v, float q[4]) {
 }
 
 // rotation track: decode both keys, NLerpEst
+template <int F>
 __device__ __forceinline__ void sample_quat(const ClipSetDev& cs, int clip, int track, float t, float out[4],
                                             int32_t* key_out) {
-    const Bracket k = fetch_bracket(cs, 1, clip, track, t, key_out);
+    const Bracket k = fetch_bracket<F>(cs, 1, clip, track, t, key_out);
     const float r0 = k.r0, r1 = k.r1;
     const uint2 v0 = k.v0, v1 = k.v1;
     const float alpha = (t - r0) * rcp_exact(r1 - r0);
@@ -152,12 +160,13 @@ struct Xform {  // one joint's local transform
     float t[3], r[4], s[3];
 };
 
+template <int F>
 __device__ __forceinline__ void sample_joint(const ClipSetDev& cs, int clip, int track, float ratio, Xform& x,
-                                             int32_t* key_out /* [3][P][2] base for this layer, or null */) {
+                                             int32_t* key_out /* [3][P][2] base for this layer (kKeys) */) {
     const int P = cs.padded_tracks;
-    sample_f3(cs, 0, clip, track, ratio, x.t, key_out ? key_out + ((size_t)0 * P + track) * 2 : nullptr);
-    sample_quat(cs, clip, track, ratio, x.r, key_out ? key_out + ((size_t)1 * P + track) * 2 : nullptr);
-    sample_f3(cs, 2, clip, track, ratio, x.s, key_out ? key_out + ((size_t)2 * P + track) * 2 : nullptr);
+    sample_f3<F>(cs, 0, clip, track, ratio, x.t, (F & kKeys) ? key_out + ((size_t)0 * P + track) * 2 : nullptr);
+    sample_quat<F>(cs, clip, track, ratio, x.r, (F & kKeys) ? key_out + ((size_t)1 * P + track) * 2 : nullptr);
+    sample_f3<F>(cs, 2, clip, track, ratio, x.s, (F & kKeys) ? key_out + ((size_t)2 * P + track) * 2 : nullptr);
 }
 
 // OZZ_BLEND_N_PASS for one joint
@@ -196,7 +205,7 @@ __device__ __forceinline__ void blend_first_pass(Xform& acc, const Xform& in, fl
 
 // One group of layers [begin, begin + count) of a character, for joint jt.  `layer(l, clip, ratio, weight)` yields the
 // resolved state of layer l (clip index validated, ratio clamped to [0, 1] as SamplingJob::Run does).
-template <typename LayerFn>
+template <int F, typename LayerFn>
 __device__ __forceinline__ Xform eval_group(const ClipSetDev& cs, const LayerFn& layer, int begin, int count, int mode, int rest_idx,
                                             float threshold, int jt, int32_t* key_base, int P) {
     Xform acc;
@@ -204,12 +213,12 @@ __device__ __forceinline__ Xform eval_group(const ClipSetDev& cs, const LayerFn&
         // every clip of a state is sampled each tick (:538-545); only one of them is the pose
         for (int l = begin; l < begin + count; ++l) {
             const bool chosen = l == begin + rest_idx;
-            if (!chosen && !key_base) continue;
+            if (!chosen && !(F & kKeys)) continue;
             int cl;
             float tl, wl;
             layer(l, cl, tl, wl);
             Xform in;
-            sample_joint(cs, cl, jt, tl, in, key_base ? key_base + (size_t)l * 3 * P * 2 : nullptr);
+            sample_joint<F>(cs, cl, jt, tl, in, (F & kKeys) ? key_base + (size_t)l * 3 * P * 2 : nullptr);
             if (chosen) acc = in;
         }
         return acc;
@@ -237,9 +246,9 @@ __device__ __forceinline__ Xform eval_group(const ClipSetDev& cs, const LayerFn&
         layer(l, cl, tl, w);
         const bool contributes = !(w <= 0.f);
         const bool is_rest = need_rest && l == begin + rest_idx;
-        if (!contributes && !is_rest && !key_base) continue;
+        if (!contributes && !is_rest && !(F & kKeys)) continue;
         Xform in;
-        sample_joint(cs, cl, jt, tl, in, key_base ? key_base + (size_t)l * 3 * P * 2 : nullptr);
+        sample_joint<F>(cs, cl, jt, tl, in, (F & kKeys) ? key_base + (size_t)l * 3 * P * 2 : nullptr);
         if (is_rest) rest = in;
         if (!contributes) continue;
         if (pass == 0) blend_first_pass(acc, in, w);
@@ -337,7 +346,14 @@ __global__ void __launch_bounds__(256) advance_kernel(const PoseParams p) {
 // warp-per-character layout), small register footprint, many warps per SM to cover the L2 latency of the table reads.
 // Output: the joint's local 3x4 matrix (SoaFloat4x4::FromAffine), 16 floats per joint so that a thread writes two whole
 // sectors (256-bit stores); the model kernel reads them back coalesced.
-__global__ void __launch_bounds__(256) sample_kernel(const PoseParams p) {
+#ifndef DMK_SAMPLE_MIN_BLOCKS
+#define DMK_SAMPLE_MIN_BLOCKS 8   // 64 registers: 32 resident warps per SM hide the L2 latency of the table reads (measured best)
+#endif
+#ifndef DMK_SAMPLE_BLOCK
+#define DMK_SAMPLE_BLOCK 128
+#endif
+template <int F>
+__global__ void __launch_bounds__(DMK_SAMPLE_BLOCK, DMK_SAMPLE_MIN_BLOCKS) sample_kernel(const PoseParams p) {
     const int P = p.skel.padded_joints;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= p.n * P) return;
@@ -359,7 +375,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const PoseParams p) {
         ratio = t;
         weight = __ldg(p.weight + idx);
     };
-    int32_t* kb = p.key_indices ? p.key_indices + (size_t)c * L * 3 * P * 2 : nullptr;
+    int32_t* kb = (F & kKeys) ? p.key_indices + (size_t)c * L * 3 * P * 2 : nullptr;
     Xform acc;
     if (prog.top == kTopRestPose) {  // load-time pose: LocalToModelJob over joint_rest_poses (:901-916)
         const float* r = p.skel.rest + (size_t)j * 10;
@@ -367,9 +383,9 @@ __global__ void __launch_bounds__(256) sample_kernel(const PoseParams p) {
         acc.r[0] = r[3]; acc.r[1] = r[4]; acc.r[2] = r[5]; acc.r[3] = r[6];
         acc.s[0] = r[7]; acc.s[1] = r[8]; acc.s[2] = r[9];
     } else {
-        acc = eval_group(p.clips, layer, 0, prog.n0, prog.mode0, prog.rest0, prog.threshold0, j, kb, P);
-        if (prog.top == kTopTransition || (kb && prog.n1)) {
-            const Xform cur = eval_group(p.clips, layer, prog.n0, prog.n1, prog.mode1, prog.rest1, prog.threshold1, j, kb, P);
+        acc = eval_group<F>(p.clips, layer, 0, prog.n0, prog.mode0, prog.rest0, prog.threshold0, j, kb, P);
+        if (prog.top == kTopTransition || ((F & kKeys) && prog.n1)) {
+            const Xform cur = eval_group<F>(p.clips, layer, prog.n0, prog.n1, prog.mode1, prog.rest1, prog.threshold1, j, kb, P);
             if (prog.top == kTopTransition)  // 2-layer BlendingJob, threshold bx::kFloatSmallest, rest = previous (:709-719)
                 acc = blend_two(acc, cur, prog.w0, prog.w1, 1.17549435e-38f);
         }
@@ -539,7 +555,15 @@ cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream, i
     }
     {
         const int64_t total = p.n * p.skel.padded_joints;
-        sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+        constexpr int kBlock = DMK_SAMPLE_BLOCK;
+        const unsigned grid = (unsigned)((total + kBlock - 1) / kBlock);
+        const int shape = (p.clips.bucket_dir ? kBuckets : 0) | (p.key_indices ? kKeys : 0);
+        switch (shape) {
+        case 0: sample_kernel<0><<<grid, kBlock, 0, stream>>>(p); break;
+        case kBuckets: sample_kernel<kBuckets><<<grid, kBlock, 0, stream>>>(p); break;
+        case kKeys: sample_kernel<kKeys><<<grid, kBlock, 0, stream>>>(p); break;
+        default: sample_kernel<kBuckets | kKeys><<<grid, kBlock, 0, stream>>>(p); break;
+        }
         if (launches) ++*launches;
     }
     int warps = kWarpsPerBlock;
