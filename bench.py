@@ -417,6 +417,10 @@ def main():
     if args.reserve_sms < 0:   # auto: the render GPU ingests (N - 1) slabs while it skins
         world = int(os.environ.get("WORLD_SIZE", "1"))
         args.reserve_sms = 0 if world <= 1 else min(8, 2 * (world - 1))
+    elif 0 < args.reserve_sms < world - 1:
+        # measured on 8 B200: with NCCL_MAX_CTAS=4 the grouped send/recv towards 7 peers never completes (the run ends in
+        # the 600 s NCCL watchdog); 6 completes but no longer hides behind the skinning kernel; 8 is the sweet spot
+        sys.exit("--reserve-sms must be 0 or at least world_size - 1: NCCL needs a CTA per peer of the gather")
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)
