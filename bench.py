@@ -414,8 +414,8 @@ def main():
     ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs left to the NCCL gather so that it overlaps the skinning")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.reserve_sms < 0:   # auto: the render GPU ingests (N - 1) slabs while it skins
-        world = int(os.environ.get("WORLD_SIZE", "1"))
         args.reserve_sms = 0 if world <= 1 else min(8, 2 * (world - 1))
     elif 0 < args.reserve_sms < world - 1:
         # measured on 8 B200: with NCCL_MAX_CTAS=4 the grouped send/recv towards 7 peers never completes (the run ends in
