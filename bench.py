@@ -176,7 +176,9 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if args.reserve_sms > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(args.reserve_sms))   # the gather must fit the SMs left to it
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a stuck collective ends the run after two minutes instead of NCCL's ten-minute default
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.Stream(device=dev)
@@ -415,12 +417,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.reserve_sms < 0:   # auto: the render GPU ingests (N - 1) slabs while it skins
-        args.reserve_sms = 0 if world <= 1 else min(8, 2 * (world - 1))
-    elif 0 < args.reserve_sms < world - 1:
-        # measured on 8 B200: with NCCL_MAX_CTAS=4 the grouped send/recv towards 7 peers never completes (the run ends in
-        # the 600 s NCCL watchdog); 6 completes but no longer hides behind the skinning kernel; 8 is the sweet spot
-        sys.exit("--reserve-sms must be 0 or at least world_size - 1: NCCL needs a CTA per peer of the gather")
+    if args.reserve_sms < 0:   # auto
+        args.reserve_sms = 0 if world <= 1 else 8
+    elif world > 1 and 0 < args.reserve_sms < 8:
+        # measured on 2, 4 and 8 B200: NCCL_MAX_CTAS = 8 hides the gather behind the skinning kernel at
+        # every N; 6 completes but no longer overlaps; 2 and 4 left the grouped send/recv stuck until NCCL's watchdog fired
+        sys.exit("--reserve-sms must be 0 or at least 8 (fewer NCCL CTAs stall or hang the visible-palette gather)")
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)
