@@ -175,6 +175,15 @@ static dmk_status cuda_fail(dmk_context_t ctx, cudaError_t e, const char* what) 
         if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #expr); \
     } while (0)
 
+// Owner of a handle under construction: a failing create call releases the device memory it has allocated so far through
+// the handle's own destroy function.
+template <typename T, void (*Destroy)(T*)>
+struct HandleDeleter {
+    void operator()(T* p) const { Destroy(p); }
+};
+template <typename T, void (*Destroy)(T*)>
+using Building = std::unique_ptr<T, HandleDeleter<T, Destroy>>;
+
 template <typename T>
 static cudaError_t dev_alloc(T** p, size_t count) {
     *p = nullptr;
@@ -418,7 +427,7 @@ dmk_status dmk_sync(dmk_context_t ctx) {
 dmk_status dmk_skeleton_load_ozz(dmk_context_t ctx, const void* bytes, size_t size, dmk_skeleton_t* out) {
     if (!ctx || !out) return fail(ctx, DMK_ERR_INVALID, "null argument");
     *out = nullptr;
-    auto skel = std::make_unique<dmk_skeleton_s>();
+    Building<dmk_skeleton_s, dmk_skeleton_destroy> skel(new dmk_skeleton_s());
     skel->ctx = ctx;
     std::string err;
     if (!parse_skeleton(bytes, size, skel->data, err)) return fail(ctx, DMK_ERR_FORMAT, err);
@@ -507,7 +516,7 @@ dmk_status dmk_clipset_create(dmk_context_t ctx, dmk_skeleton_t skel, const dmk_
     *out = nullptr;
     if (bind(ctx)) return DMK_ERR_CUDA;
     const int padded = skel->data.num_soa() * 4;
-    auto set = std::make_unique<dmk_clipset_s>();
+    Building<dmk_clipset_s, dmk_clipset_destroy> set(new dmk_clipset_s());
     set->ctx = ctx;
     set->num_clips = num_clips;
     set->padded_tracks = padded;
@@ -578,7 +587,7 @@ dmk_status dmk_armature_create(dmk_context_t ctx, dmk_skeleton_t skel, const cha
     if (num_joints + 1 > kMaxPalette)
         return fail(ctx, DMK_ERR_UNSUPPORTED, "armature has more than 255 joints (palette slots are bytes; the reference caps at 64)");
     if (bind(ctx)) return DMK_ERR_CUDA;
-    auto arm = std::make_unique<dmk_armature_s>();
+    Building<dmk_armature_s, dmk_armature_destroy> arm(new dmk_armature_s());
     arm->ctx = ctx;
     arm->num_joints = num_joints;
     std::vector<float> ib(static_cast<size_t>(num_joints) * 12);
@@ -622,7 +631,7 @@ dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const fl
     *out = nullptr;
     if (palette_size < 1 || palette_size > kMaxPalette) return fail(ctx, DMK_ERR_INVALID, "palette_size must be in [1, 256]");
     if (bind(ctx)) return DMK_ERR_CUDA;
-    auto mesh = std::make_unique<dmk_mesh_s>();
+    Building<dmk_mesh_s, dmk_mesh_destroy> mesh(new dmk_mesh_s());
     mesh->ctx = ctx;
     mesh->num_vertices = num_vertices;
     mesh->palette_size = palette_size;
@@ -716,7 +725,7 @@ dmk_status dmk_crowd_create(dmk_context_t ctx, dmk_skeleton_t skel, dmk_clipset_
         return fail(ctx, DMK_ERR_INVALID, "mesh palette_size does not match the armature");
     if (skel->data.num_joints == 0) return fail(ctx, DMK_ERR_INVALID, "skeleton has no joints");
     if (bind(ctx)) return DMK_ERR_CUDA;
-    auto crowd = std::make_unique<dmk_crowd_s>();
+    Building<dmk_crowd_s, dmk_crowd_destroy> crowd(new dmk_crowd_s());
     dmk_crowd_s* c = crowd.get();
     c->ctx = ctx;
     c->skel = skel;
