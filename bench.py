@@ -204,6 +204,13 @@ def run_gpu(args):
         crowd.step(DT, capi.STEP_POSE | capi.STEP_CULL)
         _, vis0 = crowd.get_visibility()
         cap = min(n, int(vis0 * 1.25) + 1024)
+        if world > 1:
+            # every rank sees a different part of the scene, so the head-room differs: agree on the largest.  The slabs of
+            # the gather must have ONE size on all ranks -- a send shorter or longer than the receive posted for it leaves
+            # NCCL's step FIFOs out of phase and the exchange stalls a few frames later
+            agreed = torch.tensor([cap], dtype=torch.int64, device=dev)
+            dist.all_reduce(agreed, op=dist.ReduceOp.MAX)
+            cap = int(agreed.item())
         packed = torch.empty((cap, ps, 16), dtype=torch.float32, device=dev)
         # device int32 count written by the compaction kernel, viewed as a torch tensor without a copy
         vis_count = torch.as_tensor(_DevInt32(crowd.visible_count_dev()), device=dev)
@@ -420,9 +427,9 @@ def main():
     if args.reserve_sms < 0:   # auto
         args.reserve_sms = 0 if world <= 1 else 8
     elif world > 1 and 0 < args.reserve_sms < 8:
-        # measured on 2, 4 and 8 B200: NCCL_MAX_CTAS = 8 hides the gather behind the skinning kernel at
-        # every N; 6 completes but no longer overlaps; 2 and 4 left the grouped send/recv stuck until NCCL's watchdog fired
-        sys.exit("--reserve-sms must be 0 or at least 8 (fewer NCCL CTAs stall or hang the visible-palette gather)")
+        # measured on 4 and 8 B200: with NCCL_MAX_CTAS = 8 the gather hides behind the skinning kernel;
+        # with 6 it completes but no longer overlaps
+        sys.exit("--reserve-sms must be 0 or at least 8 (with fewer NCCL CTAs the visible-palette gather no longer overlaps)")
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

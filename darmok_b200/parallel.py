@@ -31,6 +31,12 @@ class VisiblePaletteGather:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.capacity, self.palette_size = capacity, palette_size
+        # the slabs are exchanged with fixed-size send/recv pairs: a rank with another capacity would post a transfer of
+        # another length than its peer expects (NCCL: undefined, in practice a stall a few frames later)
+        shapes = [None] * self.world
+        dist.all_gather_object(shapes, (int(capacity), int(palette_size)), group=group)
+        if len(set(shapes)) != 1:
+            raise ValueError(f"VisiblePaletteGather: capacity / palette size differ across ranks: {shapes}")
         self.counts = torch.zeros(self.world, dtype=torch.int32, device=device)
         self.slab = None
         if self.rank == dst:

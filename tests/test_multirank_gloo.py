@@ -53,3 +53,26 @@ def test_visible_palette_gather_world2(tmp_path):
     assert counts.tolist() == [3, 5]
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"recv{r}.npy"), np.load(tmp_path / f"sent{r}.npy"))
+
+
+def _mismatch_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        try:
+            VisiblePaletteGather(8 + rank, 3, torch.device("cpu"), dst=0)   # every rank proposes another capacity
+            outcome = "accepted"
+        except ValueError as e:
+            outcome = str(e)
+        with open(os.path.join(out_dir, f"outcome{rank}.txt"), "w") as f:
+            f.write(outcome)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_refuses_unequal_slab_capacities(tmp_path):
+    # fixed-size send/recv pairs: ranks that disagree on the slab size must fail at construction, not stall frames later
+    world = 2
+    mp.spawn(_mismatch_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert "differ across ranks" in (tmp_path / f"outcome{r}.txt").read_text()
