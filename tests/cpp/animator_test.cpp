@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <memory>
 #include <sstream>
@@ -818,8 +819,52 @@ static int runGpu(const std::string& dir) {
     return g_failures ? 1 : 0;
 }
 
+// host cost of the per-character animator tick the device-side state machines replace (no device needed):
+// N AnimatorCores of the samples/ozz definition in random states, one frame = one update() + afterUpdate() each
+static int runHostBench(const std::string& dir, int n) {
+    OracleAssets o = loadOracle(dir);
+    SkeletalAnimatorDefinition def;
+    orc::AnimatorDef rdef;
+    buildDefinitions(def, rdef);
+    std::vector<detail::ClipInfo> clips;
+    for (const auto& a : o.named) clips.push_back({a.name, a.anim->duration});
+    std::vector<std::unique_ptr<detail::AnimatorCore>> cores;
+    const char* states[] = {"locomotion", "talk", "strafe", "greet"};
+    uint32_t rng = 12345u;
+    auto next = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+    for (int i = 0; i < n; ++i) {
+        cores.push_back(std::make_unique<detail::AnimatorCore>(clips, def));
+        cores.back()->play(states[next() % 4]);
+        cores.back()->setBlendPosition(glm::vec2((float)(next() % 2001) / 1000.f - 1.f, (float)(next() % 2001) / 1000.f - 1.f));
+    }
+    detail::PoseRequest req;
+    auto frame = [&](int f) {
+        size_t layers = 0;
+        for (int i = 0; i < n; ++i) {
+            auto& c = *cores[(size_t)i];
+            if (f % 10 == 0 && next() % 10 == 0) c.play(states[next() % 4]);
+            const bool active = c.hasActiveStateOrTransition();
+            if (c.update(1 / 60.f, req) && active) c.afterUpdate();
+            layers += req.group0.layers.size() + req.group1.layers.size();
+        }
+        return layers;
+    };
+    for (int f = 0; f < 5; ++f) frame(f);
+    const int frames = 30;
+    size_t layers = 0;
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int f = 0; f < frames; ++f) layers += frame(5 + f);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double ms = ((double)(t1.tv_sec - t0.tv_sec) * 1e3 + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-6) / frames;
+    std::printf("hostbench: %d animators, %.2f ms per frame on one host thread (%.0f ns per animator tick, %.1f layers per animator)\n", n, ms,
+                ms * 1e6 / n, (double)layers / frames / n);
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 3) { std::printf("usage: animator_test <assets_dir> cpu|gpu\n"); return 2; }
+    if (argc < 3) { std::printf("usage: animator_test <assets_dir> cpu|gpu|hostbench [n]\n"); return 2; }
+    if (std::string(argv[2]) == "hostbench") return runHostBench(argv[1], argc > 3 ? std::atoi(argv[3]) : 100000);
     std::setvbuf(stdout, nullptr, _IOLBF, 0);   // keep the progress lines if a section dies
     return std::string(argv[2]) == "gpu" ? runGpu(argv[1]) : runCpu(argv[1]);
 }

@@ -54,6 +54,12 @@ def test_state_machine_matches_reference_animator_on_cpu(binary, assets_dir):
     assert "0 failures" in out
 
 
+def test_host_tick_benchmark_mode_runs(binary, assets_dir):
+    # the CPU cost of the per-character animator tick that the device-side state machines remove
+    r = subprocess.run([binary, assets_dir, "hostbench", "2000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ns per animator tick" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_animator_and_scene_component_on_device(binary, assets_dir):
     out = _run(binary, assets_dir, "gpu")
