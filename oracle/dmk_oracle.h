@@ -7,7 +7,8 @@
  *
  * PARITY STATUS
  *   - cull (Frustum/Plane/BoundingBox): pinned by the reference's own KATs
- *     (test/src/shape_test.cpp:52-59 and :61-84), see tests/test_oracle_cull.py.
+ *     (test/src/shape_test.cpp:52-59 and :61-84), see tests/test_oracle_cull.py.  The matrix conventions of the
+ *     Transform restatement (translate / mat4_cast / scale) are pinned by the third KAT there (:9-50).
  *   - sampling / blending / local-to-model / palette / LBS: "parity unpinned".
  *     The arithmetic lives in ozz-animation, fetched by the reference at configure time
  *     (CMake/ozzAnimationConfig.cmake:2-5, GIT_TAG master = unpinned) and ABSENT from

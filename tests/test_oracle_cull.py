@@ -140,3 +140,39 @@ def test_parented_cull_equals_cull_on_composed_inverse():
     free = ep < 0
     bits_free, wi_free = O.cull_batch_trs(corners, tr.position, tr.rotation, tr.scale, tr.bbox, want_world_inverse=True)
     assert np.array_equal(wi[free], wi_free[free])
+
+
+def test_math_transform_conventions_match_reference_plane_kat():
+    """test/src/shape_test.cpp:9-50 ("Plane transform") pins what Transform::update builds its matrices from: the
+    translation column of Math::transform, the diagonal of glm::scale, and the rotation sense / component order of
+    glm::mat4_cast(glm::quat).  Plane::operator*= (src/shape.cpp:527-537) restated: origin = normal * distance;
+    origin' = M * (origin, 1) / w; normal' = M * (normal, 0); distance' = dot(normal', origin')."""
+    ident_q, one = [0, 0, 0, 1], [1, 1, 1]
+
+    def apply(plane, m16):
+        m = np.asarray(m16, np.float32).reshape(4, 4).T
+        normal, distance = plane
+        origin = m @ np.append(normal * np.float32(distance), np.float32(1))
+        origin = origin[:3] / origin[3]
+        normal = (m @ np.append(normal, np.float32(0)))[:3]
+        return normal, np.float32(np.dot(normal, origin))
+
+    plane = (np.array([0, 0, 1], np.float32), np.float32(1))
+    plane = apply(plane, O.transform_local_matrix([1, 0, 0], ident_q, one))          # Math::transform(vec3(1, 0, 0))
+    assert np.array_equal(plane[0], [0, 0, 1]) and plane[1] == 1
+    plane = apply(plane, O.transform_local_matrix([0, 0, 3], ident_q, one))
+    assert np.array_equal(plane[0], [0, 0, 1]) and plane[1] == 4
+    scale = O.transform_local_matrix([0, 0, 0], ident_q, [2, 3, 4])                   # glm::scale(mat4(1), vec3(2, 3, 4))
+    plane = apply(plane, scale)
+    assert np.array_equal(plane[0], [0, 0, 4]) and plane[1] == 64
+    # glm::quat(glm::radians(vec3(0, -90, 0))): a pure rotation about y, (x, y, z, w) = (0, sin(-45 deg), 0, cos(-45 deg))
+    half = np.radians(-90.0) / 2
+    roty = O.transform_local_matrix([0, 0, 0], [0, np.sin(half), 0, np.cos(half)], one)
+    plane = apply((np.array([0, 0, 1], np.float32), np.float32(1)), roty)
+    assert np.allclose(plane[0], [-1, 0, 0], atol=1e-6) and np.isclose(plane[1], 1, atol=1e-6)
+    plane = apply(plane, scale)
+    assert np.allclose(plane[0], [-2, 0, 0], atol=1e-6) and np.isclose(plane[1], 4, atol=1e-5)
+    plane = apply((np.array([0, 0, 1], np.float32), np.float32(0)), roty)
+    assert np.allclose(plane[0], [-1, 0, 0], atol=1e-6) and np.isclose(plane[1], 0, atol=1e-6)
+    plane = apply((np.array([0, 0, -1], np.float32), np.float32(1)), roty)
+    assert np.allclose(plane[0], [1, 0, 0], atol=1e-6) and np.isclose(plane[1], 1, atol=1e-6)
