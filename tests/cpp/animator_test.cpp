@@ -18,6 +18,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <fstream>
@@ -278,6 +279,32 @@ static int runCpu(const std::string& dir) {
             const float a = ease01(static_cast<EasingType>(type), p), b = orc::ease(type, p, 0.f, 1.f);
             CHECK(a == b || (std::isnan(a) && std::isnan(b)), "easing %d at %g: %.9g vs %.9g", type, p, a, b);
         }
+    // ... and both against the REFERENCE's own include/darmok/easing.hpp (compiled where it lies into oracle/_ref by
+    // `make -C oracle ref`; vectors written by tests/golden/make_easing_golden.py): [32 types][(0,1),(2,-3)][49 positions]
+    {
+        const char* gd = std::getenv("DMK_GOLDEN_DIR");
+        CHECK(gd != nullptr, "DMK_GOLDEN_DIR is not set (tests/test_host_shim.py sets it to tests/golden)");
+        const std::vector<uint8_t> raw = gd ? readFile(std::string(gd) + "/easing_reference.f32") : std::vector<uint8_t>();
+        CHECK(raw.size() == 32u * 2 * 49 * 4, "easing_reference.f32 has %zu bytes", raw.size());
+        const float* g = reinterpret_cast<const float*>(raw.data());
+        const float ranges[2][2] = {{0.f, 1.f}, {2.f, -3.f}};
+        int pinned = 0;
+        if (raw.size() == 32u * 2 * 49 * 4)
+            for (int type = 0; type < 32; ++type)
+                for (int r = 0; r < 2; ++r)
+                    for (int i = -4; i <= 44; ++i) {
+                        const float p = i / 40.f, want = g[(type * 2 + r) * 49 + (i + 4)];
+                        const float b = orc::ease(type, p, ranges[r][0], ranges[r][1]);
+                        CHECK(b == want || (std::isnan(b) && std::isnan(want)), "oracle easing %d [%g,%g] at %g: %.9g, reference %.9g", type, ranges[r][0],
+                              ranges[r][1], p, b, want);
+                        if (r == 0) {
+                            const float a = ease01(static_cast<EasingType>(type), p);
+                            CHECK(a == want || (std::isnan(a) && std::isnan(want)), "shim easing %d at %g: %.9g, reference %.9g", type, p, a, want);
+                        }
+                        ++pinned;
+                    }
+        std::printf("cpu: %d easing values equal to the reference's easing.hpp\n", pinned);
+    }
     std::printf("cpu: %d ticks, %d poses (%d blends, %d passthroughs, %d in transition), %d job errors, %zu events, %d failures\n", ticks, poses, blends,
                 passthroughs, transitions, errors, events.size(), g_failures);
     CHECK(transitions > 20 && blends > 50 && passthroughs > 20 && errors == 2 && events.size() > 10, "scenario lost coverage");

@@ -43,7 +43,8 @@ def assets_dir(tmp_path_factory):
 
 
 def _run(binary, assets_dir, mode):
-    r = subprocess.run([binary, assets_dir, mode], capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, DMK_GOLDEN_DIR=os.path.join(ROOT, "tests", "golden"))
+    r = subprocess.run([binary, assets_dir, mode], capture_output=True, text=True, timeout=600, env=env)
     print(r.stdout[-3000:])
     assert r.returncode == 0, f"exit code {r.returncode}\n" + r.stdout[-3000:] + r.stderr[-1000:]
     return r.stdout
@@ -52,6 +53,7 @@ def _run(binary, assets_dir, mode):
 def test_state_machine_matches_reference_animator_on_cpu(binary, assets_dir):
     out = _run(binary, assets_dir, "cpu")
     assert "0 failures" in out
+    assert "3136 easing values equal to the reference's easing.hpp" in out
 
 
 def test_host_tick_benchmark_mode_runs(binary, assets_dir):
