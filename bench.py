@@ -35,13 +35,24 @@ FLT_MIN = float(np.finfo(np.float32).tiny)
 DT = 1.0 / 60.0
 
 
+def gather_description(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return "one GPU: visible palettes packed into a dense device buffer, no exchange"
+    how = ("pack kernel + NCCL send/recv" if getattr(args, "gather", "nccl") == "nccl"
+           else "one pack+transfer kernel storing into rank 0's HBM over NVLink (CUDA IPC peer memory, no NCCL in the frame loop)")
+    where = ("on a side stream, overlapped with the skinning kernel (reserved SMs: %d)" % args.reserve_sms if args.reserve_sms > 0
+             else "in-stream between cull and skinning")
+    return "visible palettes -> rank 0: %s, %s" % (how, where)
+
+
 def workload_config(args):
     return {
         "workload": "BASELINE.json configs[2]: 100k characters x 67 joints, two-layer BlendingJob (transition form), "
                     "5k verts x 4 influences LBS positions+normals+tangents; + frustum cull and visible-palette gather",
         "characters_per_gpu": args.chars, "joints": 67, "layers": 2, "clips": args.clips, "vertices": args.verts,
         "influences": 4, "dt": DT,
-        "gather": "visible palettes -> rank 0 over NCCL send/recv on a side stream, overlapped with the skinning kernel (reserved SMs: %d)" % max(args.reserve_sms, 0),
+        "gather": gather_description(args),
         "l2": "inputs larger than L2: each step streams %.1f GB of skinned vertices per GPU (L2 = 126 MB)"
               % (args.chars * args.verts * 36 / 1e9),
     }
@@ -219,10 +230,17 @@ def run_gpu(args):
         # the one exchange of the path: visible palettes to the render GPU (rank 0).  Fixed-capacity
         # slabs + a device-side count per rank: no host synchronisation inside the step.
         gatherer = None
+        peer = None
         comm_stream = None
         if world > 1:
-            from darmok_b200.parallel import VisiblePaletteGather
-            gatherer = VisiblePaletteGather(cap, ps, dev, dst=0)
+            from darmok_b200.parallel import PeerPaletteExchange, VisiblePaletteGather
+            if args.gather == "peer":
+                # pack + transfer in one kernel of ours, storing into rank 0's slab over NVLink: no NCCL in the frame loop
+                peer = PeerPaletteExchange(ctx, cap, ps, dst=0)
+                peer_ctas = 4 * args.reserve_sms if args.reserve_sms > 0 else 0
+                cull_done, pushed = torch.cuda.Event(), torch.cuda.Event()
+            else:
+                gatherer = VisiblePaletteGather(cap, ps, dev, dst=0)
             if args.reserve_sms > 0:
                 # the gather runs on its own stream, on SMs the persistent skinning grid leaves free, concurrently with
                 # the skinning kernel (it only depends on pose + cull + pack)
@@ -230,7 +248,26 @@ def run_gpu(args):
                 comm_stream = torch.cuda.Stream(device=dev)
                 packed_ready = torch.cuda.Event()
 
+        def step_peer():
+            crowd.step(DT, flags_pre)                       # clocks + pose + cull + compaction
+            side = comm_stream if comm_stream is not None else stream
+            if comm_stream is not None:
+                cull_done.record(stream)
+            crowd.step(DT, capi.STEP_SKIN)                  # LBS of every vertex of every character
+            if comm_stream is not None:
+                comm_stream.wait_event(cull_done)           # the push depends on pose + cull only; enqueued after the skin launch
+            frame = peer.push(crowd, peer_ctas, side.cuda_stream)
+            if comm_stream is not None:
+                pushed.record(comm_stream)
+            if peer.is_owner:                               # the render GPU: wait for the frame of all ranks, consume, release
+                peer.wait(frame, side.cuda_stream)
+                peer.release(frame, side.cuda_stream)
+            if comm_stream is not None:
+                stream.wait_event(pushed)                   # the next frame's pose overwrites the palettes the push reads
+
         def step():
+            if peer is not None:
+                return step_peer()
             crowd.step(DT, flags_pre)                       # clocks + pose + cull + compaction
             crowd.pack_visible_palettes(packed.data_ptr(), cap)
             if gatherer is not None and comm_stream is None:
@@ -272,6 +309,9 @@ def run_gpu(args):
             t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             elapsed_ms = float(t.item())
+        if peer is not None:
+            torch.cuda.synchronize(dev)
+            peer.status()                                   # raises if a bounded wait of the exchange expired
         skin_ms, skin_n = ctx.kernel_time(capi.KERNEL_SKIN)
         pose_ms, pose_n = ctx.kernel_time(capi.KERNEL_POSE)
         cull_ms, cull_n = ctx.kernel_time(capi.KERNEL_CULL)
@@ -420,7 +460,10 @@ def main():
     ap.add_argument("--verts", type=int, default=5000)
     ap.add_argument("--clips", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs left to the NCCL gather so that it overlaps the skinning")
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs left to the gather so that it overlaps the skinning")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+                    help="N > 1: visible-palette transport: pack kernel + NCCL send/recv, or the pack+transfer kernel storing into rank 0's "
+                         "memory over NVLink (dmk_exchange_*; not yet measured on hardware, see DESIGN.md section 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -31,6 +31,7 @@ UNITS = [
     ("cull_kernel.cu", ["-fmad=false"]),
     ("animator_kernel.cu", ["-fmad=false"]),
     ("skin_kernel.cu", []),
+    ("exchange_kernel.cu", []),
 ]
 
 

@@ -109,6 +109,16 @@ SIGNATURES = [
     ("dmk_crowd_collect_visibility", _i, [_vp, _vp, C.POINTER(_i64)]),
     ("dmk_crowd_get_ratios", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_pack_visible_palettes", _i, [_vp, _vp, _i64]),
+    ("dmk_exchange_create", _i, [_vp, _i, _i, _i64, _i, _vp, C.POINTER(_vp)]),
+    ("dmk_exchange_open", _i, [_vp, _i, _i, _i64, _i, _vp, C.POINTER(_vp)]),
+    ("dmk_exchange_attach", _i, [_vp, _vp, _i, C.POINTER(_vp)]),
+    ("dmk_exchange_destroy", None, [_vp]),
+    ("dmk_exchange_set_timeout_ms", _i, [_vp, _i64]),
+    ("dmk_crowd_push_visible_palettes", _i, [_vp, _vp, _u32, _i, _vp]),
+    ("dmk_exchange_wait", _i, [_vp, _u32, _vp]),
+    ("dmk_exchange_frame_dev", _i, [_vp, _u32, C.POINTER(_vp), C.POINTER(_vp)]),
+    ("dmk_exchange_release", _i, [_vp, _u32, _vp]),
+    ("dmk_exchange_status", _i, [_vp, _vp, C.POINTER(_i)]),
     ("dmk_cull_dev", _i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     ("dmk_cull_trs_dev", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     ("dmk_cull_host", _i, [_vp, _vp, _f, _vp, _vp, _i64, _vp]),
@@ -468,6 +478,9 @@ class Crowd:
     def pack_visible_palettes(self, out_dev_ptr, capacity):
         self.ctx.check(lib().dmk_crowd_pack_visible_palettes(self.h, out_dev_ptr, capacity))
 
+    def push_visible_palettes(self, exchange: "Exchange", frame: int, num_ctas: int = 0, stream=None):
+        self.ctx.check(lib().dmk_crowd_push_visible_palettes(self.h, exchange.h, frame, num_ctas, stream))
+
     # raw device pointers (ints)
     def palette_dev(self):
         return lib().dmk_crowd_palette_dev(self.h)
@@ -487,3 +500,62 @@ class Crowd:
 
 def bits_to_bool(bits: np.ndarray, n: int) -> np.ndarray:
     return np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
+
+
+EXCHANGE_HANDLE_BYTES = 64
+EXCHANGE_MAX_RANKS = 64
+
+
+class Exchange:
+    """Visible-palette exchange over peer memory (include/dmk.h, dmk_exchange_*).  Build one with create (render rank),
+    open (another process, from the render rank's handle) or attach (same process)."""
+
+    def __init__(self, ctx: Context, h, world, rank, capacity, palette_size, handle=None):
+        self.ctx, self.h, self.world, self.rank, self.capacity, self.palette_size, self.handle = ctx, h, world, rank, capacity, palette_size, handle
+
+    @classmethod
+    def create(cls, ctx: Context, world, rank, capacity, palette_size):
+        h = C.c_void_p()
+        handle = (C.c_uint8 * EXCHANGE_HANDLE_BYTES)()
+        ctx.check(lib().dmk_exchange_create(ctx.h, world, rank, capacity, palette_size, handle, C.byref(h)))
+        return cls(ctx, h, world, rank, capacity, palette_size, bytes(handle))
+
+    @classmethod
+    def open(cls, ctx: Context, world, rank, capacity, palette_size, handle: bytes):
+        if len(handle) != EXCHANGE_HANDLE_BYTES:
+            raise ValueError("bad exchange handle")
+        h = C.c_void_p()
+        buf = (C.c_uint8 * EXCHANGE_HANDLE_BYTES).from_buffer_copy(handle)
+        ctx.check(lib().dmk_exchange_open(ctx.h, world, rank, capacity, palette_size, buf, C.byref(h)))
+        return cls(ctx, h, world, rank, capacity, palette_size)
+
+    def attach(self, ctx: Context, rank):
+        h = C.c_void_p()
+        ctx.check(lib().dmk_exchange_attach(self.h, ctx.h, rank, C.byref(h)))
+        return Exchange(ctx, h, self.world, rank, self.capacity, self.palette_size)
+
+    def set_timeout_ms(self, ms):
+        self.ctx.check(lib().dmk_exchange_set_timeout_ms(self.h, ms))
+
+    def wait(self, frame, stream=None):
+        self.ctx.check(lib().dmk_exchange_wait(self.h, frame, stream))
+
+    def release(self, frame, stream=None):
+        self.ctx.check(lib().dmk_exchange_release(self.h, frame, stream))
+
+    def frame_dev(self, frame):
+        """(slab pointer, counts pointer) of the frame's buffer on the render rank, as ints"""
+        slab, counts = C.c_void_p(), C.c_void_p()
+        self.ctx.check(lib().dmk_exchange_frame_dev(self.h, frame, C.byref(slab), C.byref(counts)))
+        return slab.value, counts.value
+
+    def status(self, stream=None):
+        """synchronises the stream; raises DmkError when a bounded wait of the exchange expired"""
+        err = C.c_int()
+        self.ctx.check(lib().dmk_exchange_status(self.h, stream, C.byref(err)))
+        return err.value
+
+    def close(self):
+        if self.h:
+            lib().dmk_exchange_destroy(self.h)
+            self.h = None

@@ -341,6 +341,48 @@ DMK_API dmk_status dmk_crowd_get_ratios(dmk_crowd_t crowd, float* out_ratio, uin
  * This is the payload of the one multi-GPU exchange. */
 DMK_API dmk_status dmk_crowd_pack_visible_palettes(dmk_crowd_t crowd, float* out_dev, int64_t capacity_characters);
 
+/* ---- multi-GPU: the visible-palette exchange over peer memory (NVLink / NVSwitch) ----------------------- */
+/* The reference is one process on one GPU: beforeRenderEntity hands the palette to the renderer as a uniform
+ * (src/skeleton.cpp:223-251).  With the crowd sharded one process per GPU the palettes of the
+ * characters FrustumCuller left visible have to reach the render GPU; this is that exchange, without NCCL: the render
+ * rank owns a slab [2 buffers][world][capacity][palette_size][16] in its HBM, exports it with CUDA IPC, and every rank
+ * packs AND transfers in one kernel, storing its visible palettes into slab[frame & 1][rank] over NVLink and publishing
+ * {count, frame} behind a system-scope release.  The render rank waits on the device for a frame of all ranks
+ * (dmk_exchange_wait), reads it, and releases the buffer (dmk_exchange_release); a producer may be at most two frames
+ * ahead of the last release.  Frames are numbered 1, 2, 3, ... and every rank pushes every frame.  Every device-side
+ * wait is bounded (default 30 s): on expiry the exchange gives up and dmk_exchange_status reports it.
+ * cuda_stream arguments: the stream to enqueue on (NULL = the context's stream); the exchange usually runs on a side
+ * stream, concurrently with the skinning kernel (DMK_OPT_SKIN_RESERVED_SMS leaves it SMs). */
+typedef struct dmk_exchange_s* dmk_exchange_t;
+#define DMK_EXCHANGE_HANDLE_BYTES 64
+#define DMK_EXCHANGE_MAX_RANKS 64
+/* render rank: allocates the slab; handle_out (DMK_EXCHANGE_HANDLE_BYTES) is what the other processes open */
+DMK_API dmk_status dmk_exchange_create(dmk_context_t ctx, int world, int rank, int64_t capacity_characters, int palette_size,
+                                       uint8_t* handle_out, dmk_exchange_t* out);
+/* another process (any GPU of the box with peer access to the render GPU): maps the render rank's slab */
+DMK_API dmk_status dmk_exchange_open(dmk_context_t ctx, int world, int rank, int64_t capacity_characters, int palette_size,
+                                     const uint8_t* handle, dmk_exchange_t* out);
+/* same process as the owner (several logical ranks on one GPU or several GPUs driven by one process): shares the mapping */
+DMK_API dmk_status dmk_exchange_attach(dmk_exchange_t owner, dmk_context_t ctx, int rank, dmk_exchange_t* out);
+DMK_API void dmk_exchange_destroy(dmk_exchange_t exchange); /* owner last: the others unmap first */
+/* bound of every device-side wait, milliseconds (default 30000) */
+DMK_API dmk_status dmk_exchange_set_timeout_ms(dmk_exchange_t exchange, int64_t milliseconds);
+/* Pack + transfer: palettes of the crowd's visible characters (ascending id, at most capacity) -> slab[frame & 1][rank]
+ * on the render GPU, then publish.  frame must be the previous frame of this exchange + 1.  num_ctas: blocks of 256
+ * threads (0 = 4 per SM); keep it within the SMs left to the side stream. */
+DMK_API dmk_status dmk_crowd_push_visible_palettes(dmk_crowd_t crowd, dmk_exchange_t exchange, uint32_t frame, int num_ctas,
+                                                   void* cuda_stream);
+/* render rank: enqueue the device-side wait for `frame` of every rank; afterwards (stream order) the frame's palettes
+ * and counts are readable */
+DMK_API dmk_status dmk_exchange_wait(dmk_exchange_t exchange, uint32_t frame, void* cuda_stream);
+/* render rank: device pointers of a frame's buffer: slab [world][capacity][palette_size][16], counts int32 [world] */
+DMK_API dmk_status dmk_exchange_frame_dev(dmk_exchange_t exchange, uint32_t frame, float** out_slab_dev, int32_t** out_counts_dev);
+/* render rank: the frame has been read; its buffer may be overwritten by frame + 2 */
+DMK_API dmk_status dmk_exchange_release(dmk_exchange_t exchange, uint32_t frame, void* cuda_stream);
+/* synchronises the given stream and reports expired waits: *out_error = 0 ok, 1 this rank's push gave up waiting for a
+ * release, 2 the render rank gave up waiting for a rank (DMK_ERR_CUDA is returned as well when it is not 0) */
+DMK_API dmk_status dmk_exchange_status(dmk_exchange_t exchange, void* cuda_stream, int* out_error);
+
 /* ---- stand-alone batched cull (config 5: instances without animation) ---------------------------------- */
 /* world_inverse_dev [n][16], bbox_dev [n][6] device pointers; vis_bits_dev ceil(n/32) words. */
 DMK_API dmk_status dmk_cull_dev(dmk_context_t ctx, const float* corners_host, const float* world_inverse_dev,
