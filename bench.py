@@ -175,6 +175,70 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlClockSampler:
+    """Same contract as ClockSampler, through NVML directly (pynvml): a sample every 5 ms, so that a timed region of a
+    few hundred milliseconds holds dozens of samples instead of the one or two `nvidia-smi -lms 100` delivers.  start()
+    returns False when NVML is not usable; the caller then falls back to nvidia-smi."""
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
+
+    def __init__(self, device_index, pci_bus_id=None):
+        self.device_index, self.pci_bus_id = device_index, pci_bus_id
+        self.rows, self.thread, self.stop_flag, self.nv, self.handle = [], None, threading.Event(), None, None
+
+    def start(self) -> bool:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = None
+            if self.pci_bus_id:
+                try:
+                    handle = nv.nvmlDeviceGetHandleByPciBusId(self.pci_bus_id.encode())
+                except Exception:
+                    handle = None
+            if handle is None:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.device_index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+            self.masks = [(name, int(getattr(nv, attr, bit))) for name, attr, bit in self.REASONS]
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.get_reasons(handle)
+            self.nv, self.handle = nv, handle
+        except Exception:
+            return False
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+        return True
+
+    def _poll(self):
+        nv, h = self.nv, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(self.get_reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self, t_begin, t_end):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        rows = [r for r in self.rows if t_begin <= r[0] <= t_end] or self.rows[-3:]
+        sm = [r[1] for r in rows]
+        reasons = sorted({name for _, _, bits in rows for name, mask in self.masks if bits & mask})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "source": "nvml, 5 ms period"}
+
+
+def make_clock_sampler(device_index, pci_bus_id=None):
+    s = NvmlClockSampler(device_index, pci_bus_id)
+    if s.start():
+        return s
+    s = ClockSampler(device_index)
+    s.start()
+    return s
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -288,8 +352,12 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        try:
+            pr = torch.cuda.get_device_properties(dev)
+            bus_id = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        except Exception:
+            bus_id = None
+        sampler = make_clock_sampler(local_rank, bus_id)
         time.sleep(0.25)
         launches0 = ctx.launches
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
