@@ -91,6 +91,12 @@ SIGNATURES = [
     ("dmk_crowd_get_transform_nodes", _i, [_vp, _vp, _vp]),
     ("dmk_crowd_get_world_inverses", _i, [_vp, _i64, _i64, _vp]),
     ("dmk_crowd_world_inverse_dev", _vp, [_vp]),
+    ("dmk_crowd_add_skin", _i, [_vp, _vp, _vp, C.POINTER(_i)]),
+    ("dmk_crowd_num_skins", _i, [_vp]),
+    ("dmk_crowd_skin_palette_dev", _vp, [_vp, _i]),
+    ("dmk_crowd_skin_skinned_dev", _vp, [_vp, _i]),
+    ("dmk_crowd_get_skin_palette", _i, [_vp, _i, _i64, _i64, _vp]),
+    ("dmk_crowd_get_skin_skinned", _i, [_vp, _i, _i64, _i64, _vp]),
     ("dmk_crowd_set_camera", _i, [_vp, _vp, _f]),
     ("dmk_crowd_set_frustum_corners", _i, [_vp, _vp]),
     ("dmk_crowd_step", _i, [_vp, _f, _u32]),
@@ -456,6 +462,30 @@ class Crowd:
     def get_skinned(self, first=0, count=None):
         count = self.n - first if count is None else count
         return self._get(lib().dmk_crowd_get_skinned, (self.mesh.num_vertices, 9), np.float32, first, count)
+
+    def add_skin(self, arm: "Armature", mesh: "Mesh | None" = None) -> int:
+        """a further (armature, mesh) pair animated by the same characters; returns its skin index (1, 2, ...)"""
+        if not hasattr(self, "skins"):
+            self.skins = [(self.arm, self.mesh)]
+        idx = C.c_int()
+        self.ctx.check(lib().dmk_crowd_add_skin(self.h, arm.h, mesh.h if mesh else None, C.byref(idx)))
+        self.skins.append((arm, mesh))
+        assert idx.value == len(self.skins) - 1 == lib().dmk_crowd_num_skins(self.h) - 1
+        return idx.value
+
+    def get_skin_palette(self, skin, first=0, count=None):
+        count = self.n - first if count is None else count
+        arm = self.skins[skin][0] if hasattr(self, "skins") else self.arm
+        out = np.zeros((count, arm.palette_size, 16), np.float32)
+        self.ctx.check(lib().dmk_crowd_get_skin_palette(self.h, skin, first, count, _ptr(out)))
+        return out
+
+    def get_skin_skinned(self, skin, first=0, count=None):
+        count = self.n - first if count is None else count
+        mesh = self.skins[skin][1] if hasattr(self, "skins") else self.mesh
+        out = np.zeros((count, mesh.num_vertices, 9), np.float32)
+        self.ctx.check(lib().dmk_crowd_get_skin_skinned(self.h, skin, first, count, _ptr(out)))
+        return out
 
     def get_visibility(self):
         bits = np.zeros((self.n + 31) // 32, np.uint32)

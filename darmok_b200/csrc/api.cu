@@ -141,6 +141,15 @@ struct dmk_crowd_s {
     bool culled_once = false;
     bool force_search = false;  // tests: exercise the per-track binary search even when a bucket table exists
     SkinPlan plan{};
+    // further (armature, mesh) pairs skinned from the same animator (dmk_crowd_add_skin); skin 0 is the pair above
+    struct ExtraSkin {
+        dmk_armature_t arm = nullptr;
+        dmk_mesh_t mesh = nullptr;
+        float *d_palette = nullptr, *d_palette34 = nullptr, *d_skinned = nullptr;
+        SkinPlan plan{};
+    };
+    std::vector<ExtraSkin> extra_skins;
+    int reserved_sms = 0;
     // device-side animators (dmk_crowd_set_animator)
     AnimStateDef* d_anim_states = nullptr;
     AnimClipDef* d_anim_clips = nullptr;
@@ -799,6 +808,11 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
                     (void*)c->d_node_scale, (void*)c->d_node_world, (void*)c->d_node_world_inverse, (void*)c->d_node_parent, (void*)c->d_entity_parent, (void*)c->d_anim_cmd, (void*)c->d_anim_status,
                     (void*)c->d_anim_cmd_speed, (void*)c->d_anim_blend, (void*)c->d_anim_speed})
         dev_free(p);
+    for (auto& x : c->extra_skins) {
+        dev_free(x.d_palette);
+        dev_free(x.d_palette34);
+        dev_free(x.d_skinned);
+    }
     for (int b = 0; b < 2; ++b) {
         if (c->h_vis[b]) cudaFreeHost(c->h_vis[b]);
         if (c->vis_ready[b]) cudaEventDestroy(c->vis_ready[b]);
@@ -817,7 +831,10 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
     }
     if (option == DMK_OPT_SKIN_RESERVED_SMS) {
         if (value < 0 || value >= c->ctx->num_sms) return fail(c->ctx, DMK_ERR_INVALID, "reserved SM count out of range");
+        c->reserved_sms = value;
         if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - value);
+        for (auto& x : c->extra_skins)
+            if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - value);
         return DMK_OK;
     }
     if (option == DMK_OPT_KEEP_WORLD_INVERSE) {
@@ -1383,6 +1400,19 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         {
             KernelTimer timer(ctx, DMK_KERNEL_POSE);
             DMK_CUDA(ctx, launch_pose(p, ctx->num_sms, s, &pose_launches));
+            // every further armature: its own palette from the same local matrices (beforeRenderEntity runs once per Skinnable)
+            for (const auto& x : c->extra_skins) {
+                PoseParams q = p;
+                q.arm.remap = x.arm->d_remap;
+                q.arm.inv_bind = x.arm->d_inv_bind;
+                q.arm.num_joints = x.arm->num_joints;
+                q.palette = x.d_palette;
+                q.palette34 = x.d_palette34;
+                q.models = nullptr;
+                q.locals = nullptr;
+                q.key_indices = nullptr;
+                DMK_CUDA(ctx, launch_model(q, ctx->num_sms, s, &pose_launches));
+            }
         }
         ctx->launches += pose_launches;
     }
@@ -1433,30 +1463,55 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         }
     }
     if (flags & DMK_STEP_SKIN) {
-        if (!c->mesh || !c->arm) return fail(ctx, DMK_ERR_INVALID, "skinning needs a mesh and an armature");
+        bool any_mesh = c->mesh != nullptr;
+        for (const auto& x : c->extra_skins) any_mesh = any_mesh || x.mesh != nullptr;
+        if (!any_mesh || !c->arm) return fail(ctx, DMK_ERR_INVALID, "skinning needs a mesh and an armature");
         const bool visible_only = (flags & DMK_STEP_SKIN_VISIBLE_ONLY) != 0;
         if (visible_only && !c->culled_once) return fail(ctx, DMK_ERR_INVALID, "DMK_STEP_SKIN_VISIBLE_ONLY needs a cull step");
         SkinParams p{};
-        p.palette34 = c->d_palette34;
-        p.pos = c->mesh->d_pos;
-        p.nrm = c->mesh->d_nrm;
-        p.tan = c->mesh->d_tan;
-        p.weights = c->mesh->d_weights;
-        p.slots = c->mesh->d_slots;
-        p.out = c->d_skinned;
         p.char_ids = visible_only ? c->d_visible_ids : nullptr;
         p.char_count = visible_only ? c->d_visible_count : nullptr;
         p.n = c->n;
-        p.vpad = c->mesh->vpad;
-        p.palette_size = c->mesh->palette_size;
-        p.num_tiles = c->plan.num_tiles;
-        p.tile_vertices = c->plan.tile_vertices;
-        p.skip_zero_weights = c->mesh->sorted ? 1 : 0;
-        {
-            KernelTimer timer(ctx, DMK_KERNEL_SKIN);
-            DMK_CUDA(ctx, launch_skin(p, c->plan, s));
+        if (c->mesh) {
+            p.palette34 = c->d_palette34;
+            p.pos = c->mesh->d_pos;
+            p.nrm = c->mesh->d_nrm;
+            p.tan = c->mesh->d_tan;
+            p.weights = c->mesh->d_weights;
+            p.slots = c->mesh->d_slots;
+            p.out = c->d_skinned;
+            p.vpad = c->mesh->vpad;
+            p.palette_size = c->mesh->palette_size;
+            p.num_tiles = c->plan.num_tiles;
+            p.tile_vertices = c->plan.tile_vertices;
+            p.skip_zero_weights = c->mesh->sorted ? 1 : 0;
+            {
+                KernelTimer timer(ctx, DMK_KERNEL_SKIN);
+                DMK_CUDA(ctx, launch_skin(p, c->plan, s));
+            }
+            ++ctx->launches;
         }
-        ++ctx->launches;
+        for (const auto& x : c->extra_skins) {
+            if (!x.mesh) continue;
+            SkinParams q = p;
+            q.palette34 = x.d_palette34;
+            q.pos = x.mesh->d_pos;
+            q.nrm = x.mesh->d_nrm;
+            q.tan = x.mesh->d_tan;
+            q.weights = x.mesh->d_weights;
+            q.slots = x.mesh->d_slots;
+            q.out = x.d_skinned;
+            q.vpad = x.mesh->vpad;
+            q.palette_size = x.mesh->palette_size;
+            q.num_tiles = x.plan.num_tiles;
+            q.tile_vertices = x.plan.tile_vertices;
+            q.skip_zero_weights = x.mesh->sorted ? 1 : 0;
+            {
+                KernelTimer timer(ctx, DMK_KERNEL_SKIN);
+                DMK_CUDA(ctx, launch_skin(q, x.plan, s));
+            }
+            ++ctx->launches;
+        }
     }
     if (flags & DMK_STEP_POSE)
         DMK_CUDA(ctx, cudaMemcpyAsync(c->h_error, c->d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -1556,6 +1611,79 @@ dmk_status dmk_crowd_get_skinned(dmk_crowd_t c, int64_t first, int64_t count, fl
                                        c->ctx->stream));
     return finish_and_check(c);
 }
+// ---- several skinned meshes per character -----------------------------------------------------------------------
+dmk_status dmk_crowd_add_skin(dmk_crowd_t c, dmk_armature_t arm, dmk_mesh_t mesh, int* out_skin) {
+    if (!c) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (!arm) return fail(ctx, DMK_ERR_INVALID, "a skin needs an armature");
+    if (arm->ctx != ctx || (mesh && mesh->ctx != ctx)) return fail(ctx, DMK_ERR_INVALID, "armature / mesh belong to another context");
+    if (mesh && mesh->palette_size != arm->num_joints + 1) return fail(ctx, DMK_ERR_INVALID, "mesh palette_size does not match the armature");
+    if (!c->arm) return fail(ctx, DMK_ERR_INVALID, "the crowd was created without an armature: pass the first one to dmk_crowd_create");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    dmk_crowd_s::ExtraSkin x;
+    x.arm = arm;
+    x.mesh = mesh;
+    const size_t ps = static_cast<size_t>(arm->num_joints + 1), n = static_cast<size_t>(c->n);
+    cudaError_t e = dev_alloc(&x.d_palette, n * ps * 16);
+    if (e == cudaSuccess) e = dev_alloc(&x.d_palette34, n * ps * 16);
+    if (e == cudaSuccess && mesh) e = dev_alloc(&x.d_skinned, n * static_cast<size_t>(mesh->vpad) * 9);
+    if (e != cudaSuccess) {
+        dev_free(x.d_palette);
+        dev_free(x.d_palette34);
+        dev_free(x.d_skinned);
+        return cuda_fail(ctx, e, "dmk_crowd_add_skin allocation");
+    }
+    if (mesh) x.plan = plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms - c->reserved_sms);
+    c->extra_skins.push_back(x);
+    if (out_skin) *out_skin = static_cast<int>(c->extra_skins.size());
+    return DMK_OK;
+}
+int dmk_crowd_num_skins(dmk_crowd_t c) { return c ? (c->arm ? 1 : 0) + static_cast<int>(c->extra_skins.size()) : 0; }
+namespace {
+struct SkinView {
+    dmk_armature_t arm = nullptr;
+    dmk_mesh_t mesh = nullptr;
+    float *palette = nullptr, *skinned = nullptr;
+};
+bool skin_view(dmk_crowd_t c, int skin, SkinView* v) {
+    if (skin == 0) {
+        *v = {c->arm, c->mesh, c->d_palette, c->d_skinned};
+        return c->arm != nullptr;
+    }
+    if (skin < 0 || static_cast<size_t>(skin) > c->extra_skins.size()) return false;
+    const auto& x = c->extra_skins[static_cast<size_t>(skin) - 1];
+    *v = {x.arm, x.mesh, x.d_palette, x.d_skinned};
+    return true;
+}
+}  // namespace
+const float* dmk_crowd_skin_palette_dev(dmk_crowd_t c, int skin) {
+    SkinView v;
+    return c && skin_view(c, skin, &v) ? v.palette : nullptr;
+}
+const float* dmk_crowd_skin_skinned_dev(dmk_crowd_t c, int skin) {
+    SkinView v;
+    return c && skin_view(c, skin, &v) ? v.skinned : nullptr;
+}
+dmk_status dmk_crowd_get_skin_palette(dmk_crowd_t c, int skin, int64_t first, int64_t count, float* out) {
+    if (dmk_status st = check_range(c, first, count, out)) return st;
+    SkinView v;
+    if (!skin_view(c, skin, &v)) return fail(c->ctx, DMK_ERR_INVALID, "no such skin");
+    if (count == 0) return DMK_OK;
+    const size_t per = static_cast<size_t>(v.arm->num_joints + 1) * 16;
+    DMK_CUDA(c->ctx, cudaMemcpyAsync(out, v.palette + first * per, count * per * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+    return finish_and_check(c);
+}
+dmk_status dmk_crowd_get_skin_skinned(dmk_crowd_t c, int skin, int64_t first, int64_t count, float* out) {
+    if (dmk_status st = check_range(c, first, count, out)) return st;
+    SkinView v;
+    if (!skin_view(c, skin, &v)) return fail(c->ctx, DMK_ERR_INVALID, "no such skin");
+    if (!v.mesh) return fail(c->ctx, DMK_ERR_INVALID, "the skin has no mesh");
+    if (count == 0) return DMK_OK;
+    const size_t pitch = static_cast<size_t>(v.mesh->vpad) * 9, row = static_cast<size_t>(v.mesh->num_vertices) * 9;
+    DMK_CUDA(c->ctx, cudaMemcpy2DAsync(out, row * 4, v.skinned + first * pitch, pitch * 4, row * 4, count, cudaMemcpyDeviceToHost, c->ctx->stream));
+    return finish_and_check(c);
+}
+
 dmk_status dmk_crowd_get_visibility(dmk_crowd_t c, uint32_t* out_bits, int64_t* out_visible_count) {
     if (!c) return DMK_ERR_INVALID;
     if (!c->culled_once) return fail(c->ctx, DMK_ERR_INVALID, "no cull step has run");

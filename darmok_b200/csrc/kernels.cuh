@@ -8,6 +8,8 @@ namespace dmk {
 // K1..K3 (pose_kernel.cu, built with -fmad=false)
 size_t pose_smem_bytes(const PoseParams& p);
 cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream, int* launches);
+// K2 + K3 only, from the local matrices of the last sampling launch (p.scratch): further armatures of the same crowd
+cudaError_t launch_model(const PoseParams& p, int num_sms, cudaStream_t stream, int* launches);
 
 // K4 (cull_kernel.cu, built with -fmad=false): visibility bitmask; then ordered compaction of visible ids
 cudaError_t launch_cull(const CullParams& p, cudaStream_t stream);

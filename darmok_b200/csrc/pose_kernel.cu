@@ -566,6 +566,13 @@ cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream, i
         }
         if (launches) ++*launches;
     }
+    return launch_model(p, num_sms, stream, launches);
+}
+
+// local-to-model + flip + palette from the local matrices a sampling launch left in p.scratch: the second half of the pose
+// path, also run on its own for every further armature of a crowd (one Armature per Skinnable mesh, src/skeleton.cpp:223-251)
+cudaError_t launch_model(const PoseParams& p, int num_sms, cudaStream_t stream, int* launches) {
+    if (p.n <= 0) return cudaSuccess;
     int warps = kWarpsPerBlock;
     while (warps > 1 && pose_smem_bytes_for(p, warps) > 200 * 1024) warps >>= 1;
     const size_t smem = pose_smem_bytes_for(p, warps);

@@ -166,6 +166,14 @@ struct SkinnedMeshData {
     int numVertices() const noexcept { return static_cast<int>(position.size() / 3); }
 };
 
+// One Skinnable of a character: the armature whose palette is built and (optionally) the mesh it skins.  darmok hangs one
+// entity with Renderable + Skinnable per assimp mesh under the entity that owns the SkeletalAnimator
+// (src/scene_assimp.cpp:187-193,696-721); shared by every animator of a batch, never copied per character.
+struct SkinTarget {
+    std::shared_ptr<Armature> armature;
+    std::shared_ptr<const SkinnedMeshData> mesh;
+};
+
 class Skinnable {
 public:
     Skinnable(const std::shared_ptr<Armature>& armature = nullptr) noexcept : _armature{armature} {}
@@ -241,15 +249,18 @@ public:
     void pause() noexcept;
     PlaybackState getPlaybackState() noexcept;
 
-    // skinning target: the armature (and optionally the mesh) whose palette / skinned vertices the device produces.
-    // Must be set before the first update(); one armature per animator.
+    // skinning targets: the armatures (and optionally the meshes) whose palettes / skinned vertices the device produces,
+    // one per Skinnable entity under the animator's entity.  setSkinning defines skin 0, addSkinning every further one
+    // (returns its index); both must be called before the first update().
     expected<void, std::string> setSkinning(const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh = nullptr) noexcept;
+    expected<int, std::string> addSkinning(const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh = nullptr) noexcept;
+    int getSkinCount() const noexcept { return static_cast<int>(_skins.size()); }
 
     glm::mat4 getJointModelMatrix(const std::string& node) const noexcept;
     // debug-bone matrices keyed by joint name (src/skeleton_ozz.cpp:979-1004), what RenderableSkeleton::update consumes
     std::unordered_map<std::string, glm::mat4> getJointModelMatrixes(const glm::vec3& dir = {1.f, 0.f, 0.f}) const noexcept;
-    std::vector<glm::mat4> getSkinningPalette() const noexcept;   // what beforeRenderEntity uploads as u_skinning
-    std::vector<float> getSkinnedVertices() const noexcept;       // [V][9] position, normal, tangent
+    std::vector<glm::mat4> getSkinningPalette(int skin = 0) const noexcept;   // what beforeRenderEntity uploads as u_skinning
+    std::vector<float> getSkinnedVertices(int skin = 0) const noexcept;       // [V][9] position, normal, tangent
 
     // stand-alone use: ticks the state machine and runs a one-character device step
     expected<void, std::string> update(float deltaTime) noexcept;
@@ -263,8 +274,7 @@ private:
     std::unique_ptr<Device> _device;       // own one-character crowd (stand-alone mode)
     SkeletalAnimationSceneComponent* _batch = nullptr;
     int64_t _batchIndex = -1;
-    std::shared_ptr<Armature> _armature;
-    std::optional<SkinnedMeshData> _mesh;
+    std::vector<SkinTarget> _skins;        // [0] = setSkinning's; shared pointers, the data is not copied per animator
     mutable std::vector<glm::mat4> _modelsCache;
     mutable bool _modelsValid = false;
     mutable uint64_t _modelsFrame = 0;
@@ -291,6 +301,10 @@ public:
     SkeletalAnimationSceneComponent(std::shared_ptr<Skeleton> skel, SkeletalAnimator::AnimationMap anims, SkeletalAnimator::Definition def,
                                     std::shared_ptr<Armature> armature, const SkinnedMeshData* mesh = nullptr) noexcept;
     ~SkeletalAnimationSceneComponent() noexcept;
+
+    // a further Skinnable of every character (its own armature, optionally its own mesh); before init().  Returns the skin
+    // index SkeletalAnimator::getSkinningPalette / getSkinnedVertices and dmk_crowd_skin_*_dev take.
+    expected<int, std::string> addSkin(std::shared_ptr<Armature> armature, const SkinnedMeshData* mesh = nullptr) noexcept;
 
     // creates the animators (entities); must be called once before update()
     expected<void, std::string> init(int64_t numAnimators, AnimatorExecution execution = AnimatorExecution::Host) noexcept;

@@ -136,16 +136,41 @@ struct SkeletalAnimator::Device {
     std::vector<uint32_t> visibility;
     bool visibilityValid = false;
 
+    bool anyMesh = false;   // some skin has vertices: steps include DMK_STEP_SKIN
+
     ~Device() {
         dmk_crowd_destroy(crowd);
+        for (auto& [arm, msh] : extraSkins) {
+            dmk_mesh_destroy(msh);
+            dmk_armature_destroy(arm);
+        }
         dmk_mesh_destroy(mesh);
         dmk_armature_destroy(armature);
         dmk_clipset_destroy(clips);
     }
 
+    // armature + mesh handles of the skins after the first (dmk_crowd_add_skin); destroyed after the crowd
+    std::vector<std::pair<dmk_armature_t, dmk_mesh_t>> extraSkins;
+
+    static bool makeArmature(dmk_context_t ctx, const std::shared_ptr<Skeleton>& skel, const Armature& armature, dmk_armature_t* out) noexcept {
+        std::vector<const char*> names;
+        std::vector<float> invBind;
+        for (const auto& j : armature.getJoints()) {
+            names.push_back(j.name.c_str());
+            const float* m = glm::value_ptr(j.inverseBindPose);
+            invBind.insert(invBind.end(), m, m + 16);
+        }
+        return dmk_armature_create(ctx, skel->handle(), names.data(), invBind.data(), static_cast<int>(names.size()), out) == DMK_OK;
+    }
+    static bool makeMesh(dmk_context_t ctx, const SkinnedMeshData& mesh, int paletteSize, dmk_mesh_t* out) noexcept {
+        return dmk_mesh_create(ctx, mesh.position.data(), mesh.normal.data(), mesh.tangent.data(), mesh.indices.data(), mesh.weights.data(),
+                               mesh.numVertices(), paletteSize, out) == DMK_OK;
+    }
+
     static expected<std::unique_ptr<Device>, std::string> create(const std::shared_ptr<Skeleton>& skel, const SkeletalAnimationMap& anims,
-                                                                 const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh,
-                                                                 int64_t n) noexcept {
+                                                                 const std::vector<SkinTarget>& skins, int64_t n) noexcept {
+        const std::shared_ptr<Armature> armature = skins.empty() ? nullptr : skins[0].armature;
+        const SkinnedMeshData* mesh = skins.empty() ? nullptr : skins[0].mesh.get();
         auto dev = std::make_unique<Device>();
         dev->ctx = skel->context();
         dev->n = n;
@@ -156,23 +181,24 @@ struct SkeletalAnimator::Device {
         if (handles.empty()) return unexpected<std::string>{"animator has no animations"};
         if (dmk_clipset_create(ctx, skel->handle(), handles.data(), static_cast<int>(handles.size()), &dev->clips)) return err();
         if (armature) {
-            std::vector<const char*> names;
-            std::vector<float> invBind;
-            for (const auto& j : armature->getJoints()) {
-                names.push_back(j.name.c_str());
-                const float* m = glm::value_ptr(j.inverseBindPose);
-                invBind.insert(invBind.end(), m, m + 16);
-            }
-            if (dmk_armature_create(ctx, skel->handle(), names.data(), invBind.data(), static_cast<int>(names.size()), &dev->armature)) return err();
+            if (!makeArmature(ctx, skel, *armature, &dev->armature)) return err();
             dev->paletteSize = dmk_armature_palette_size(dev->armature);
             if (mesh) {
-                if (dmk_mesh_create(ctx, mesh->position.data(), mesh->normal.data(), mesh->tangent.data(), mesh->indices.data(), mesh->weights.data(),
-                                    mesh->numVertices(), dev->paletteSize, &dev->mesh))
-                    return err();
+                if (!makeMesh(ctx, *mesh, dev->paletteSize, &dev->mesh)) return err();
                 dev->numVertices = mesh->numVertices();
             }
         }
         if (dmk_crowd_create(ctx, skel->handle(), dev->clips, dev->armature, dev->mesh, n, kMaxLayers, &dev->crowd)) return err();
+        for (size_t k = 1; k < skins.size(); ++k) {
+            if (!skins[k].armature) return unexpected<std::string>{"a skin needs an armature"};
+            dev->extraSkins.emplace_back(nullptr, nullptr);
+            auto& [arm, msh] = dev->extraSkins.back();
+            if (!makeArmature(ctx, skel, *skins[k].armature, &arm)) return err();
+            if (skins[k].mesh && !makeMesh(ctx, *skins[k].mesh, dmk_armature_palette_size(arm), &msh)) return err();
+            if (dmk_crowd_add_skin(dev->crowd, arm, msh, nullptr)) return err();
+            dev->anyMesh = dev->anyMesh || msh != nullptr;
+        }
+        dev->anyMesh = dev->anyMesh || dev->mesh != nullptr;
         if (dmk_crowd_enable_outputs(dev->crowd, DMK_OUT_MODELS)) return err();
         // SkeletalAnimatorImpl::load runs LocalToModelJob over the rest pose (src/skeleton_ozz.cpp:901-916, C13)
         dev->clip.assign(static_cast<size_t>(n), 0);
@@ -181,7 +207,7 @@ struct SkeletalAnimator::Device {
         dev->programs.assign(static_cast<size_t>(n), dmk_pose_program{});
         for (auto& p : dev->programs) p.top = DMK_TOP_REST_POSE;
         if (dmk_crowd_set_programs(dev->crowd, 1, dev->clip.data(), dev->ratio.data(), dev->weight.data(), dev->programs.data()) ||
-            dmk_crowd_step(dev->crowd, 0.f, DMK_STEP_POSE | (dev->mesh ? DMK_STEP_SKIN : 0)))
+            dmk_crowd_step(dev->crowd, 0.f, DMK_STEP_POSE | (dev->anyMesh ? DMK_STEP_SKIN : 0)))
             return err();
         return dev;
     }
@@ -191,7 +217,7 @@ struct SkeletalAnimator::Device {
         // a zero blend threshold comes back as DMK_ERR_JOB "error in the blending job" (src/skeleton_ozz.cpp:605-608)
         if (dmk_crowd_set_programs(crowd, numLayers, clip.data(), ratio.data(), weight.data(), programs.data())) return unexpected<std::string>{ctx->lastError()};
         uint32_t flags = DMK_STEP_POSE;
-        if (mesh) flags |= DMK_STEP_SKIN;
+        if (anyMesh) flags |= DMK_STEP_SKIN;
         if (cull && hasInstances && hasCamera) flags |= DMK_STEP_CULL;
         if (dmk_crowd_step(crowd, 0.f, flags)) return unexpected<std::string>{ctx->lastError()};
         visibilityValid = false;
@@ -204,8 +230,7 @@ struct SkeletalAnimationSceneComponent::Impl {
     std::shared_ptr<Skeleton> skeleton;
     SkeletalAnimator::AnimationMap anims;
     SkeletalAnimator::Definition def;
-    std::shared_ptr<Armature> armature;
-    std::optional<SkinnedMeshData> mesh;
+    std::vector<SkinTarget> skins;   // [0] = the constructor's armature / mesh
     std::unique_ptr<SkeletalAnimator::Device> device;
     std::vector<std::unique_ptr<SkeletalAnimator>> animators;
     std::vector<detail::PoseRequest> requests;
@@ -408,14 +433,23 @@ SkeletalAnimator::PlaybackState SkeletalAnimator::getPlaybackState() noexcept {
 
 expected<void, std::string> SkeletalAnimator::setSkinning(const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh) noexcept {
     if (_device || _batch) return unexpected<std::string>{"setSkinning must be called before the first update"};
-    _armature = armature;
-    if (mesh) _mesh = *mesh; else _mesh.reset();
+    if (_skins.empty()) _skins.emplace_back();
+    _skins[0].armature = armature;
+    _skins[0].mesh = mesh ? std::make_shared<const SkinnedMeshData>(*mesh) : nullptr;
     return {};
+}
+
+expected<int, std::string> SkeletalAnimator::addSkinning(const std::shared_ptr<Armature>& armature, const SkinnedMeshData* mesh) noexcept {
+    if (_device || _batch) return unexpected<std::string>{"addSkinning must be called before the first update"};
+    if (_skins.empty() || !_skins[0].armature) return unexpected<std::string>{"call setSkinning for the first armature"};
+    if (!armature) return unexpected<std::string>{"a skin needs an armature"};
+    _skins.push_back({armature, mesh ? std::make_shared<const SkinnedMeshData>(*mesh) : nullptr});
+    return static_cast<int>(_skins.size()) - 1;
 }
 
 expected<void, std::string> SkeletalAnimator::ensureDevice() noexcept {
     if (_device || _batch) return {};
-    auto dev = Device::create(_skeleton, _animations, _armature, _mesh ? &*_mesh : nullptr, 1);
+    auto dev = Device::create(_skeleton, _animations, _skins, 1);
     if (!dev) return unexpected<std::string>{dev.error()};
     _device = std::move(*dev);
     return {};
@@ -476,22 +510,25 @@ std::unordered_map<std::string, glm::mat4> SkeletalAnimator::getJointModelMatrix
     return out;
 }
 
-std::vector<glm::mat4> SkeletalAnimator::getSkinningPalette() const noexcept {
-    // SkeletalAnimationRenderComponent::beforeRenderEntity (src/skeleton.cpp:236-249): [mat4(1)] + model * inverseBindPose
+std::vector<glm::mat4> SkeletalAnimator::getSkinningPalette(int skin) const noexcept {
+    // SkeletalAnimationRenderComponent::beforeRenderEntity (src/skeleton.cpp:236-249): [mat4(1)] + model * inverseBindPose,
+    // once per Skinnable (= skin) of the character
     if (!_batch && !_device) const_cast<SkeletalAnimator*>(this)->ensureDevice();
     dmk_crowd_t crowd = _batch ? _batch->crowd() : (_device ? _device->crowd : nullptr);
-    const int ps = _armature ? static_cast<int>(_armature->getJoints().size()) + 1 : 0;
+    const bool known = skin >= 0 && static_cast<size_t>(skin) < _skins.size() && _skins[static_cast<size_t>(skin)].armature;
+    const int ps = known ? static_cast<int>(_skins[static_cast<size_t>(skin)].armature->getJoints().size()) + 1 : 0;
     std::vector<glm::mat4> out(static_cast<size_t>(ps), glm::mat4(1.f));
-    if (crowd && ps) dmk_crowd_get_palette(crowd, _batch ? _batchIndex : 0, 1, glm::value_ptr(out[0]));
+    if (crowd && ps) dmk_crowd_get_skin_palette(crowd, skin, _batch ? _batchIndex : 0, 1, glm::value_ptr(out[0]));
     return out;
 }
 
-std::vector<float> SkeletalAnimator::getSkinnedVertices() const noexcept {
+std::vector<float> SkeletalAnimator::getSkinnedVertices(int skin) const noexcept {
     if (!_batch && !_device) const_cast<SkeletalAnimator*>(this)->ensureDevice();
     dmk_crowd_t crowd = _batch ? _batch->crowd() : (_device ? _device->crowd : nullptr);
-    const int v = _mesh ? _mesh->numVertices() : 0;
+    const bool known = skin >= 0 && static_cast<size_t>(skin) < _skins.size() && _skins[static_cast<size_t>(skin)].mesh;
+    const int v = known ? _skins[static_cast<size_t>(skin)].mesh->numVertices() : 0;
     std::vector<float> out(static_cast<size_t>(v) * 9, 0.f);
-    if (crowd && v) dmk_crowd_get_skinned(crowd, _batch ? _batchIndex : 0, 1, out.data());
+    if (crowd && v) dmk_crowd_get_skin_skinned(crowd, skin, _batch ? _batchIndex : 0, 1, out.data());
     return out;
 }
 
@@ -503,10 +540,17 @@ SkeletalAnimationSceneComponent::SkeletalAnimationSceneComponent(std::shared_ptr
     _impl->skeleton = std::move(skel);
     _impl->anims = std::move(anims);
     _impl->def = std::move(def);
-    _impl->armature = std::move(armature);
-    if (mesh) _impl->mesh = *mesh;
+    _impl->skins.push_back({std::move(armature), mesh ? std::make_shared<const SkinnedMeshData>(*mesh) : nullptr});
 }
 SkeletalAnimationSceneComponent::~SkeletalAnimationSceneComponent() noexcept = default;
+
+expected<int, std::string> SkeletalAnimationSceneComponent::addSkin(std::shared_ptr<Armature> armature, const SkinnedMeshData* mesh) noexcept {
+    if (_impl->device) return unexpected<std::string>{"addSkin must be called before init"};
+    if (!_impl->skins[0].armature) return unexpected<std::string>{"the component was created without an armature"};
+    if (!armature) return unexpected<std::string>{"a skin needs an armature"};
+    _impl->skins.push_back({std::move(armature), mesh ? std::make_shared<const SkinnedMeshData>(*mesh) : nullptr});
+    return static_cast<int>(_impl->skins.size()) - 1;
+}
 
 expected<void, std::string> SkeletalAnimationSceneComponent::Impl::setupDeviceAnimators() noexcept {
     // flatten the definition: names -> indices.  Clip ids follow the device clip set (name-sorted, as Device::create
@@ -568,7 +612,7 @@ expected<void, std::string> SkeletalAnimationSceneComponent::Impl::setupDeviceAn
 
 expected<void, std::string> SkeletalAnimationSceneComponent::init(int64_t numAnimators, AnimatorExecution execution) noexcept {
     if (_impl->device) return unexpected<std::string>{"already initialised"};
-    auto dev = SkeletalAnimator::Device::create(_impl->skeleton, _impl->anims, _impl->armature, _impl->mesh ? &*_impl->mesh : nullptr, numAnimators);
+    auto dev = SkeletalAnimator::Device::create(_impl->skeleton, _impl->anims, _impl->skins, numAnimators);
     if (!dev) return unexpected<std::string>{dev.error()};
     _impl->device = std::move(*dev);
     if (execution == AnimatorExecution::Device)
@@ -580,8 +624,7 @@ expected<void, std::string> SkeletalAnimationSceneComponent::init(int64_t numAni
         auto a = std::make_unique<SkeletalAnimator>(_impl->skeleton, _impl->anims, _impl->def);
         a->_batch = this;
         a->_batchIndex = i;
-        a->_armature = _impl->armature;
-        a->_mesh = _impl->mesh;
+        a->_skins = _impl->skins;   // shared pointers: armatures and meshes are not copied per animator
         _impl->animators.push_back(std::move(a));
     }
     _impl->requests.resize(static_cast<size_t>(numAnimators));
@@ -643,7 +686,7 @@ expected<void, std::string> SkeletalAnimationSceneComponent::update(float deltaT
             im.inputsDirty = false;
         }
         uint32_t flags = DMK_STEP_ANIMATOR | DMK_STEP_POSE;
-        if (d.mesh) flags |= DMK_STEP_SKIN;
+        if (d.anyMesh) flags |= DMK_STEP_SKIN;
         if (d.hasInstances && d.hasCamera) flags |= DMK_STEP_CULL;
         if (dmk_crowd_step(d.crowd, deltaTime, flags)) return err();
         d.visibilityValid = false;

@@ -294,6 +294,20 @@ enum {
     DMK_STEP_ANIMATOR = 64, /* tick the device animators (dmk_crowd_set_animator) before POSE; excludes ADVANCE */
     DMK_STEP_ALL = 1 | 2 | 4 | 8
 };
+/* Several skinned meshes per character.  In darmok one character is an entity with the SkeletalAnimator and any number
+ * of descendant entities with Renderable + Skinnable, each with ITS OWN Armature (one per assimp mesh,
+ * src/scene_assimp.cpp:187-193,696-721); beforeRenderEntity finds the animator by walking the transform parents
+ * (src/skeleton.cpp:214-221) and builds one palette per Skinnable from the same joint matrices (:236-249).
+ * dmk_crowd_create takes the first (armature, mesh) pair = skin 0; every further pair is added here and gets its own
+ * palette (and skinned vertices when mesh is not NULL) in every POSE / SKIN step.  out_skin: its index (1, 2, ...). */
+DMK_API dmk_status dmk_crowd_add_skin(dmk_crowd_t crowd, dmk_armature_t armature, dmk_mesh_t mesh, int* out_skin);
+DMK_API int dmk_crowd_num_skins(dmk_crowd_t crowd);
+/* palette / skinned vertices of one skin, laid out like dmk_crowd_palette_dev / dmk_crowd_skinned_dev (skin 0 = those) */
+DMK_API const float* dmk_crowd_skin_palette_dev(dmk_crowd_t crowd, int skin);
+DMK_API const float* dmk_crowd_skin_skinned_dev(dmk_crowd_t crowd, int skin);
+DMK_API dmk_status dmk_crowd_get_skin_palette(dmk_crowd_t crowd, int skin, int64_t first, int64_t count, float* out);
+DMK_API dmk_status dmk_crowd_get_skin_skinned(dmk_crowd_t crowd, int skin, int64_t first, int64_t count, float* out);
+
 /* One frame for the whole crowd: replaces the per-entity loops SkeletalAnimationSceneComponent::update
  * (src/skeleton.cpp:159-184), FrustumCuller::update (src/culling.cpp:258-262) and, per renderable,
  * SkeletalAnimationRenderComponent::beforeRenderEntity (src/skeleton.cpp:223-251) + the LBS vertex stage. */

@@ -611,6 +611,19 @@ static int runGpu(const std::string& dir) {
     {
         SkeletalAnimator animator(*skel, anims, def);
         CHECK(animator.setSkinning(armature, &mesh).has_value(), "setSkinning");
+        // a second Skinnable of the same character: its own (partial, reversed) armature, palette only
+        const int K2 = std::min(K, 12);
+        std::vector<ArmatureJoint> joints2(joints.rend() - K2, joints.rend());
+        std::vector<int32_t> remap2;
+        std::vector<float> invBind2;
+        for (const auto& j : joints2) {
+            remap2.push_back(orc_skeleton_find_joint(o.skel, j.name.c_str()));
+            const float* m = glm::value_ptr(j.inverseBindPose);
+            invBind2.insert(invBind2.end(), m, m + 16);
+        }
+        const auto skin2 = animator.addSkinning(std::make_shared<Armature>(joints2));
+        CHECK(skin2.has_value() && *skin2 == 1 && animator.getSkinCount() == 2, "addSkinning");
+        std::vector<float> palette2((size_t)(K2 + 1) * 16);
         EventLog log;
         animator.addListener(log);
         orc::RefAnimator ref(o.skel, o.named, rdef);
@@ -635,6 +648,11 @@ static int runGpu(const std::string& dir) {
             orc_palette(ref.models().data(), J, remap.data(), invBind.data(), K, palette.data());
             const auto pal = animator.getSkinningPalette();
             for (size_t e = 0; e < palette.size(); ++e) CHECK(close(glm::value_ptr(pal[0])[e], palette[e]), "step %d palette %zu", step, e);
+            orc_palette(ref.models().data(), J, remap2.data(), invBind2.data(), K2, palette2.data());
+            const auto pal2 = animator.getSkinningPalette(1);
+            CHECK(pal2.size() == (size_t)K2 + 1, "second skin's palette has %zu slots", pal2.size());
+            for (size_t e = 0; e < palette2.size() && pal2.size() == (size_t)K2 + 1; ++e)
+                CHECK(close(glm::value_ptr(pal2[0])[e], palette2[e]), "step %d palette of skin 1, element %zu", step, e);
             orc_skin(palette.data(), K + 1, mesh.position.data(), mesh.normal.data(), mesh.tangent.data(), mesh.indices.data(), mesh.weights.data(), V, skinned.data());
             const auto sk = animator.getSkinnedVertices();
             for (size_t e = 0; e < skinned.size(); ++e) CHECK(close(sk[e], skinned[e]), "step %d skinned %zu: %g vs %g", step, e, sk[e], skinned[e]);
