@@ -22,6 +22,7 @@ OUT_MODELS, OUT_LOCALS, OUT_KEY_INDICES = 1, 2, 4
 OPT_FORCE_KEY_SEARCH = 1
 OPT_SKIN_RESERVED_SMS = 2
 OPT_KEEP_WORLD_INVERSE = 3
+OPT_SKIN_PLANAR_OUTPUT = 4
 GROUP_BLEND, GROUP_PASSTHROUGH = 0, 1
 TOP_GROUP0, TOP_TRANSITION, TOP_REST_POSE, TOP_SKIP = 0, 1, 2, 3
 PROGRAM_DTYPE = np.dtype([("n0", "u1"), ("n1", "u1"), ("rest0", "u1"), ("rest1", "u1"), ("mode0", "u1"), ("mode1", "u1"),

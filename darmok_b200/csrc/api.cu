@@ -150,6 +150,7 @@ struct dmk_crowd_s {
     };
     std::vector<ExtraSkin> extra_skins;
     int reserved_sms = 0;
+    int skin_variant = 0;   // DMK_OPT_SKIN_PLANAR_OUTPUT
     // device-side animators (dmk_crowd_set_animator)
     AnimStateDef* d_anim_states = nullptr;
     AnimClipDef* d_anim_clips = nullptr;
@@ -832,9 +833,23 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
     if (option == DMK_OPT_SKIN_RESERVED_SMS) {
         if (value < 0 || value >= c->ctx->num_sms) return fail(c->ctx, DMK_ERR_INVALID, "reserved SM count out of range");
         c->reserved_sms = value;
-        if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - value);
+        if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - value, c->skin_variant);
         for (auto& x : c->extra_skins)
-            if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - value);
+            if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - value, c->skin_variant);
+        return DMK_OK;
+    }
+    if (option == DMK_OPT_SKIN_PLANAR_OUTPUT) {
+        if (value < 0 || value > 2) return fail(c->ctx, DMK_ERR_INVALID, "DMK_OPT_SKIN_PLANAR_OUTPUT takes 0, 1 or 2");
+        if (value) {
+            auto supported = [&](dmk_mesh_t m) { return !m || (!m->sorted && plan_skin(m->vpad, m->palette_size, c->ctx->num_sms, value).replicas == 8); };
+            bool ok = supported(c->mesh);
+            for (auto& x : c->extra_skins) ok = ok && supported(x.mesh);
+            if (!ok) return fail(c->ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots and a mesh in the caller's vertex order");
+        }
+        c->skin_variant = value;
+        if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - c->reserved_sms, value);
+        for (auto& x : c->extra_skins)
+            if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - c->reserved_sms, value);
         return DMK_OK;
     }
     if (option == DMK_OPT_KEEP_WORLD_INVERSE) {
@@ -1602,14 +1617,31 @@ dmk_status dmk_crowd_get_bone_matrices(dmk_crowd_t c, int64_t first, int64_t cou
         return fail(ctx, DMK_ERR_INVALID, "character " + std::to_string(*c->h_error - 1) + " references a clip outside the clip set");
     return DMK_OK;
 }
+// [count][V][9] on the host from either device layout
+static dmk_status read_skinned(dmk_crowd_t c, dmk_mesh_t mesh, const float* d_skinned, int64_t first, int64_t count, float* out) {
+    const size_t vpad = static_cast<size_t>(mesh->vpad), nv = static_cast<size_t>(mesh->num_vertices);
+    const size_t pitch = vpad * 9, row = nv * 9;
+    if (!c->skin_variant) {
+        DMK_CUDA(c->ctx, cudaMemcpy2DAsync(out, row * 4, d_skinned + first * pitch, pitch * 4, row * 4, count, cudaMemcpyDeviceToHost, c->ctx->stream));
+        return finish_and_check(c);
+    }
+    // planar on the device: [9][vpad] per character
+    std::vector<float> planes(static_cast<size_t>(count) * pitch);
+    DMK_CUDA(c->ctx, cudaMemcpyAsync(planes.data(), d_skinned + first * pitch, planes.size() * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+    if (dmk_status st = finish_and_check(c)) return st;
+    for (size_t i = 0; i < static_cast<size_t>(count); ++i)
+        for (size_t k = 0; k < 9; ++k) {
+            const float* src = planes.data() + i * pitch + k * vpad;
+            float* dst = out + i * row + k;
+            for (size_t v = 0; v < nv; ++v) dst[v * 9] = src[v];
+        }
+    return DMK_OK;
+}
 dmk_status dmk_crowd_get_skinned(dmk_crowd_t c, int64_t first, int64_t count, float* out) {
     if (dmk_status st = check_range(c, first, count, out)) return st;
     if (!c->mesh) return fail(c->ctx, DMK_ERR_INVALID, "crowd has no mesh");
     if (count == 0) return DMK_OK;
-    const size_t pitch = static_cast<size_t>(c->mesh->vpad) * 9, row = static_cast<size_t>(c->mesh->num_vertices) * 9;
-    DMK_CUDA(c->ctx, cudaMemcpy2DAsync(out, row * 4, c->d_skinned + first * pitch, pitch * 4, row * 4, count, cudaMemcpyDeviceToHost,
-                                       c->ctx->stream));
-    return finish_and_check(c);
+    return read_skinned(c, c->mesh, c->d_skinned, first, count, out);
 }
 // ---- several skinned meshes per character -----------------------------------------------------------------------
 dmk_status dmk_crowd_add_skin(dmk_crowd_t c, dmk_armature_t arm, dmk_mesh_t mesh, int* out_skin) {
@@ -1633,7 +1665,13 @@ dmk_status dmk_crowd_add_skin(dmk_crowd_t c, dmk_armature_t arm, dmk_mesh_t mesh
         dev_free(x.d_skinned);
         return cuda_fail(ctx, e, "dmk_crowd_add_skin allocation");
     }
-    if (mesh) x.plan = plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms - c->reserved_sms);
+    if (mesh && c->skin_variant && (mesh->sorted || plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms, c->skin_variant).replicas != 8)) {
+        dev_free(x.d_palette);
+        dev_free(x.d_palette34);
+        dev_free(x.d_skinned);
+        return fail(ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots and a mesh in the caller's vertex order");
+    }
+    if (mesh) x.plan = plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms - c->reserved_sms, c->skin_variant);
     c->extra_skins.push_back(x);
     if (out_skin) *out_skin = static_cast<int>(c->extra_skins.size());
     return DMK_OK;
@@ -1679,9 +1717,7 @@ dmk_status dmk_crowd_get_skin_skinned(dmk_crowd_t c, int skin, int64_t first, in
     if (!skin_view(c, skin, &v)) return fail(c->ctx, DMK_ERR_INVALID, "no such skin");
     if (!v.mesh) return fail(c->ctx, DMK_ERR_INVALID, "the skin has no mesh");
     if (count == 0) return DMK_OK;
-    const size_t pitch = static_cast<size_t>(v.mesh->vpad) * 9, row = static_cast<size_t>(v.mesh->num_vertices) * 9;
-    DMK_CUDA(c->ctx, cudaMemcpy2DAsync(out, row * 4, v.skinned + first * pitch, pitch * 4, row * 4, count, cudaMemcpyDeviceToHost, c->ctx->stream));
-    return finish_and_check(c);
+    return read_skinned(c, v.mesh, v.skinned, first, count, out);
 }
 
 dmk_status dmk_crowd_get_visibility(dmk_crowd_t c, uint32_t* out_bits, int64_t* out_visible_count) {

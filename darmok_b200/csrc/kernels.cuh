@@ -32,8 +32,9 @@ struct SkinPlan {
     int grid;           // persistent blocks
     int replicas;       // palette replicas in shared memory (bank-conflict-free gathers)
     size_t smem;
+    int variant;        // 0: interleaved [V][9] output, 8 vertices per thread; 1 / 2: planar [9][V] output, 4 per thread, <= 320 / 448 threads
 };
-SkinPlan plan_skin(int vpad, int palette_size, int num_sms);
+SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant = 0);
 cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t stream);
 
 // K6 payload: gather palettes of the listed characters into a dense buffer

@@ -73,6 +73,10 @@ __device__ __forceinline__ void st_v8(float* p, const float* v) {
                  : "memory");
 }
 
+__device__ __forceinline__ void st_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -135,8 +139,16 @@ __device__ __forceinline__ float4 blend_row(const Rows4& x, float w0, float w1, 
     return m;
 }
 
-template <int REPL, bool SKIP>
-__global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p) {
+// VPT / PLANAR / MAXT: the shape of the output side.
+//   VPT = 8, PLANAR = false (default): [V][9] interleaved vertices, 8 per thread, 256-bit full-sector stores 288 B apart.
+//   VPT = 4, PLANAR = true: nine component planes [9][V] per character (dmk.h DMK_OPT_SKIN_PLANAR_OUTPUT); a thread's
+//     4 consecutive vertices are 16 contiguous bytes of every plane, so each warp store covers 512 contiguous bytes --
+//     whole 128-byte lines instead of 32 scattered sectors -- and half the vertices per thread leave room for 10 (MAXT =
+//     320, up to 204 registers) or 14 warps (MAXT = 448, up to 144 registers) per SM instead of 7.
+template <int REPL, bool SKIP, int VPT = 8, bool PLANAR = false, int MAXT = kMaxThreads>
+__global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
+    static_assert(PLANAR ? VPT == 4 : VPT == 8, "interleaved output needs 8 vertices per thread (9 whole sectors); planar uses 4 (st.v4 per plane)");
+    constexpr int kVPT = VPT;   // shadows the file-level constant inside this kernel
     extern __shared__ __align__(128) unsigned char smem[];
     const int PS = p.palette_size;
     const uint32_t pal_bytes = (uint32_t)PS * 64u;             // staged palette: 3 rows of 4 floats + 1 pad row per slot
@@ -281,8 +293,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_kernel(const SkinParams p
                         res[v * 9 + 6 + r] = fmaf(m2[r], tz[v], fmaf(m1[r], ty[v], m0[r] * tx[v]));
                     }
                     // flush every 32-byte sector that just became complete
+                    if (!PLANAR) {
 #pragma unroll
-                    for (int sct = (v * 9) / 8; sct < ((v + 1) * 9) / 8; ++sct) st_v8(out + sct * 8, res + sct * 8);
+                        for (int sct = (v * 9) / 8; sct < ((v + 1) * 9) / 8; ++sct) st_v8(out + sct * 8, res + sct * 8);
+                    }
+                }
+                if (PLANAR) {
+                    // component planes: plane c holds component c (position.xyz, normal.xyz, tangent.xyz) of every vertex of
+                    // the character; this thread's 4 vertices are 16 contiguous bytes of each
+                    float* plane = p.out + (size_t)cid * 9 * p.vpad + v0;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) st_v4(plane + (size_t)c * p.vpad, res[c], res[9 + c], res[18 + c], res[27 + c]);
                 }
             }
             ++q_comp;
@@ -299,7 +320,9 @@ size_t skin_smem_bytes(int palette_size, int repl) {
     return (size_t)palette_size * (48 * kNumRepl * repl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
 }
 template <typename F>
-auto with_kernel(int repl, bool skip, F&& f) {
+auto with_kernel(int repl, bool skip, int variant, F&& f) {
+    if (variant == 1) return f(skin_kernel<8, false, 4, true, 320>);   // planar output, up to 10 warps
+    if (variant == 2) return f(skin_kernel<8, false, 4, true, 448>);   // planar output, up to 14 warps
     if (skip && repl == 8) return f(skin_kernel<8, true>);   // meshes grouped by influence count
     switch (repl) {
     case 8: return f(skin_kernel<8, false>);
@@ -310,20 +333,23 @@ auto with_kernel(int repl, bool skip, F&& f) {
 }
 }  // namespace
 
-SkinPlan plan_skin(int vpad, int palette_size, int num_sms) {
+SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant) {
     SkinPlan plan{};
-    const int max_tile = kMaxThreads * kVPT;
+    plan.variant = variant;
+    const int vpt = variant ? 4 : kVPT;
+    const int max_threads = variant == 1 ? 320 : variant == 2 ? 448 : kMaxThreads;
+    const int max_tile = max_threads * vpt;
     plan.num_tiles = (vpad + max_tile - 1) / max_tile;
     int tv = (vpad + plan.num_tiles - 1) / plan.num_tiles;
-    tv = (tv + kVPT - 1) / kVPT * kVPT;
+    tv = (tv + kVPT - 1) / kVPT * kVPT;      // multiple of 8 for either shape
     plan.tile_vertices = tv;
-    plan.threads = ((tv / kVPT) + 31) / 32 * 32;
+    plan.threads = ((tv / vpt) + 31) / 32 * 32;
     // 8 replicas make the gathers conflict free; palettes too large for that (> 181 slots) fall back to fewer replicas
     plan.replicas = kRepl;
     while (plan.replicas > 1 && skin_smem_bytes(palette_size, plan.replicas) > kMaxSmem) plan.replicas /= 2;
     plan.smem = skin_smem_bytes(palette_size, plan.replicas);
     int occ = 1;
-    with_kernel(plan.replicas, false, [&](auto kernel) {
+    with_kernel(plan.replicas, false, variant, [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, plan.threads, plan.smem) != cudaSuccess || occ < 1) occ = 1;
         return 0;
@@ -337,7 +363,7 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms) {
 
 cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t stream) {
     if (p.n <= 0 || p.vpad <= 0) return cudaSuccess;
-    return with_kernel(plan.replicas, p.skip_zero_weights != 0, [&](auto kernel) {
+    return with_kernel(plan.replicas, p.skip_zero_weights != 0, plan.variant, [&](auto kernel) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (e != cudaSuccess) return e;
         kernel<<<plan.grid, plan.threads, plan.smem, stream>>>(p);

@@ -137,7 +137,14 @@ enum {
     /* With dmk_crowd_set_transforms: also store the world inverse the cull derives for each entity (64 B/entity more
      * written per CULL step) so that dmk_crowd_get_world_inverses / dmk_crowd_world_inverse_dev can hand it on, e.g. to
      * the renderer's per-entity uniforms. */
-    DMK_OPT_KEEP_WORLD_INVERSE = 3
+    DMK_OPT_KEEP_WORLD_INVERSE = 3,
+    /* Layout of the skinned vertices.  0 (default): interleaved [N][vertex_pitch][9].  1 or 2: nine component planes per
+     * character, [N][9][vertex_pitch] (plane 0..2 position.xyz, 3..5 normal.xyz, 6..8 tangent.xyz), for consumers that
+     * pull vertices from buffers; the skinning kernel then keeps 4 vertices per thread and writes whole 128-byte lines
+     * (1: up to 10 warps per SM, 2: up to 14).  The host getters (dmk_crowd_get_skinned, dmk_crowd_get_skin_skinned)
+     * return [count][V][9] whatever the device layout is.  DMK_ERR_UNSUPPORTED for palettes above 181 slots and for
+     * influence-sorted meshes.  EXPERIMENTAL: compiled and tested against the reference layout, not yet timed. */
+    DMK_OPT_SKIN_PLANAR_OUTPUT = 4
 };
 DMK_API dmk_status dmk_crowd_set_option(dmk_crowd_t crowd, int option, int value);
 
@@ -316,7 +323,8 @@ DMK_API dmk_status dmk_crowd_step(dmk_crowd_t crowd, float dt, uint32_t flags);
 /* ---- results (device pointers stay valid until the crowd is destroyed) ---------------------------------- */
 /* u_skinning per character: [N][palette_size][16] column-major mat4, slot 0 identity (src/skeleton.cpp:237-249) */
 DMK_API const float* dmk_crowd_palette_dev(dmk_crowd_t crowd);
-/* skinned vertices: [N][vertex_pitch][9] = position.xyz, normal.xyz, tangent.xyz (forward.slang:33-38) */
+/* skinned vertices: [N][vertex_pitch][9] = position.xyz, normal.xyz, tangent.xyz (forward.slang:33-38); nine planes
+ * [N][9][vertex_pitch] under DMK_OPT_SKIN_PLANAR_OUTPUT */
 DMK_API const float* dmk_crowd_skinned_dev(dmk_crowd_t crowd);
 /* visibility bitmask, bit (i % 32) of word (i / 32) set when character i is NOT culled */
 DMK_API const uint32_t* dmk_crowd_visibility_dev(dmk_crowd_t crowd);

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Stand-alone check of the planar-output skinning kernels (DMK_OPT_SKIN_PLANAR_OUTPUT = 1, 2), run by
+tests/test_gpu_zz_skin_planar.py in a child process (a device fault here must not poison the parity suite's CUDA context).
+
+For every variant and a set of vertex counts around the tile boundaries of both shapes: the skinned vertices returned by
+the host getter must be bit-identical to the default kernel's (same per-vertex arithmetic, only the thread shape and the
+store layout differ) and within the north-star tolerance of the oracle; the device buffer itself must be nine component
+planes [N][9][vertex_pitch]; DMK_STEP_SKIN_VISIBLE_ONLY must skin exactly the visible characters.
+
+    python tests/skin_planar_check.py          exit code 0 = all checks passed
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from darmok_b200 import capi, synth  # noqa: E402
+from tests import common  # noqa: E402
+from tests.common import FLT_MIN, assert_close  # noqa: E402
+
+
+class _Dev:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def main():
+    import torch
+    from oracle import oracle_py as O
+    dev = torch.device("cuda", 0)
+    base = common.default_assets()
+    oskel = O.Skeleton(base.skel.archive)
+    oclips = [O.Animation(c.archive) for c in base.clips]
+    remap = np.array([oskel.find_joint(nm) for nm in base.arm.names], np.int32)
+    ctx = capi.Context(0)
+    skel = capi.Skeleton(ctx, base.skel.archive)
+    clip_objs = [capi.Clip(ctx, c.archive) for c in base.clips]
+    clips = capi.ClipSet(ctx, skel, clip_objs)
+    arm = capi.Armature(ctx, skel, base.arm.names, base.arm.inv_bind)
+    checked = 0
+    for num_vertices in (1, 4, 7, 9, 1249, 1256, 1281, 1792, 1793, 5000, 6007):
+        mesh_s = synth.make_mesh(num_vertices, 67, seed=num_vertices, unskinned_fraction=0.02)
+        mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size)
+        n = 7 if num_vertices > 3000 else 37
+        cr = synth.make_crowd(n, 2, len(base.clips), seed=num_vertices)
+        inst = synth.make_instances(n, seed=3, extent=30.0)
+        crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+        crowd.set_instances(inst.world_inverse, inst.bbox)
+        crowd.set_camera(synth.sample_camera_view_proj(), 0.0)
+        crowd.step(0.0, capi.STEP_POSE | capi.STEP_CULL | capi.STEP_SKIN)
+        reference = crowd.get_skinned()
+        ref = O.Crowd(oskel, oclips, remap, base.arm.inv_bind, n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, mesh=mesh_s, want=("skinned",))
+        assert_close(reference, ref["skinned"], f"default kernel V={num_vertices}")
+        bits, count = crowd.get_visibility()
+        visible = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
+        vpad = (num_vertices + 7) // 8 * 8
+        for variant in (1, 2):
+            crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
+            torch.as_tensor(_Dev(crowd.skinned_dev(), (n * vpad * 9,), "<f4"), device=dev).fill_(float("nan"))
+            crowd.step(0.0, capi.STEP_SKIN)
+            got = crowd.get_skinned()
+            assert np.array_equal(got, reference), f"variant {variant} V={num_vertices}: differs from the default kernel"
+            planes = torch.as_tensor(_Dev(crowd.skinned_dev(), (n, 9, vpad), "<f4"), device=dev).cpu().numpy()
+            assert np.array_equal(planes[:, :, :num_vertices].transpose(0, 2, 1), reference), f"variant {variant}: device layout is not [N][9][pitch]"
+            # only the visible characters
+            torch.as_tensor(_Dev(crowd.skinned_dev(), (n * vpad * 9,), "<f4"), device=dev).fill_(float("nan"))
+            crowd.step(0.0, capi.STEP_SKIN | capi.STEP_SKIN_VISIBLE_ONLY)
+            got = crowd.get_skinned()
+            assert np.array_equal(got[visible], reference[visible]) and np.isnan(got[~visible]).all(), f"variant {variant}: visible-only"
+            checked += 1
+        crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, 0)
+        crowd.step(0.0, capi.STEP_SKIN)
+        assert np.array_equal(crowd.get_skinned(), reference), "back to the interleaved layout"
+        crowd.close()
+        mesh.close()
+    # refused where the layout cannot be honoured: influence-sorted meshes
+    mesh_s = synth.make_mesh(100, 67, seed=1)
+    mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size, flags=capi.MESH_SORT_BY_INFLUENCES)
+    crowd = capi.Crowd(ctx, skel, clips, arm, mesh, 3, 2)
+    try:
+        crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, 1)
+        raise AssertionError("planar output on a sorted mesh was accepted")
+    except capi.DmkError as e:
+        assert e.status == capi.ERR_UNSUPPORTED
+    crowd.close()
+    mesh.close()
+    print(f"planar skinning: {checked} (variant, vertex count) cases bit-identical to the default kernel")
+    for o in (arm, clips, *clip_objs, skel, ctx):
+        o.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -144,7 +144,8 @@ def config3_sorted():
     arm_s = synth.make_armature(skel_s)
     mesh_s = synth.make_mesh(verts, 67)
     out = {}
-    for name, flags in (("caller_order", 0), ("sorted_by_influences", capi.MESH_SORT_BY_INFLUENCES)):
+    for name, flags, variant in (("caller_order", 0, 0), ("sorted_by_influences", capi.MESH_SORT_BY_INFLUENCES, 0),
+                                 ("planar_output_10_warps", 0, 1), ("planar_output_14_warps", 0, 2)):
         stream = torch.cuda.Stream()
         with torch.cuda.stream(stream):
             ctx = capi.Context(0, stream.cuda_stream)
@@ -156,6 +157,8 @@ def config3_sorted():
             crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
             cr = synth.make_crowd(n, 2, 8, seed=42)
             crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+            if variant:
+                crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)   # nine component planes, 4 vertices per thread
             crowd.step(1 / 60, capi.STEP_POSE)
             for _ in range(3):
                 crowd.step(1 / 60, capi.STEP_SKIN)

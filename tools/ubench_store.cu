@@ -3,6 +3,7 @@
 //                                   1: st.v4 fully coalesced (lane i -> base + 16 i)
 //                                   2: st.v8 coalesced (lane i -> base + 32 i)
 //                                   3: st.v4 x2 per 32 B, lanes 288 B apart
+//                                   4: st.v8 per lane, lanes 96 B apart (three attribute planes of float3, 8 vertices per thread)
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_store tools/ubench_store.cu
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -30,9 +31,15 @@ __global__ void __launch_bounds__(256) k(float* out, size_t chunks_per_block, fl
         } else if (PATTERN == 2) {
 #pragma unroll
             for (int s = 0; s < 9; ++s) st8(wbase + s * 256 + lane * 8, v);
-        } else {
+        } else if (PATTERN == 3) {
 #pragma unroll
             for (int s = 0; s < 9; ++s) { st4(wbase + lane * 72 + s * 8, v); st4(wbase + lane * 72 + s * 8 + 4, v); }
+        } else {
+            // plane a of the chunk = 256 threads * 24 floats; a warp's part of it is 32 * 24 floats
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int s = 0; s < 3; ++s) st8(base + a * (256 * 24) + warp * (32 * 24) + lane * 24 + s * 8, v);
         }
     }
 }
@@ -44,7 +51,7 @@ int main() {
     cudaMalloc(&d, bytes);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int pat = 0; pat < 4; ++pat) {
+    for (int pat = 0; pat < 5; ++pat) {
         float best = 1e9;
         for (int it = 0; it < 4; ++it) {
             cudaEventRecord(e0);
@@ -52,6 +59,7 @@ int main() {
             if (pat == 1) k<1><<<blocks, 256>>>(d, chunks_per_block, 1.f);
             if (pat == 2) k<2><<<blocks, 256>>>(d, chunks_per_block, 1.f);
             if (pat == 3) k<3><<<blocks, 256>>>(d, chunks_per_block, 1.f);
+            if (pat == 4) k<4><<<blocks, 256>>>(d, chunks_per_block, 1.f);
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1);
