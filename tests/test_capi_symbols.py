@@ -59,3 +59,13 @@ def test_product_code_never_touches_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                     text = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert "oracle" not in text.lower() or f == "synth.py", f"{os.path.join(dirpath, f)} mentions the oracle"
+
+
+def test_header_is_plain_c99(tmp_path):
+    # the drop-in boundary is a C ABI: include/dmk.h must compile as C, not only as C++
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "dmk.h"\nint main(void) { return DMK_OK; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
