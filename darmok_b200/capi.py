@@ -297,6 +297,7 @@ class Armature:
 
 
 MESH_SORT_BY_INFLUENCES = 1
+MESH_SORT_BLOCKS_OF_4 = 2
 
 
 class Mesh:

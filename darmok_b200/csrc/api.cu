@@ -90,6 +90,7 @@ struct dmk_mesh_s {
     uint32_t* d_slots = nullptr;
     std::vector<int32_t> order;  // order[i] = caller's index of the vertex stored at position i
     bool sorted = false;
+    int sort_block = 0;          // vertices per thread the influence grouping was dealt for (8 or 4)
 };
 
 struct dmk_crowd_s {
@@ -687,16 +688,19 @@ dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const fl
         // 32 threads together.  Fill the storage "column major" over those 8-vertex blocks: sorted vertex i goes to block
         // i % B, slot i / B.  Then slot k of (almost) every block holds vertices with the same influence count -- the
         // gathers of an absent influence are skipped by whole warps -- and every thread, warp and tile gets the same mix.
-        const size_t V = mesh->order.size(), B = static_cast<size_t>(vpad) / 8;
+        // (4-vertex blocks for the 4-vertices-per-thread shapes, DMK_MESH_SORT_BLOCKS_OF_4.)
+        const size_t per = (flags & DMK_MESH_SORT_BLOCKS_OF_4) ? 4 : 8;
+        const size_t V = mesh->order.size(), B = static_cast<size_t>(vpad) / per;
         std::vector<int32_t> dealt(V);
         size_t next = 0;
-        for (size_t slot = 0; slot < 8; ++slot)
+        for (size_t slot = 0; slot < per; ++slot)
             for (size_t blk = 0; blk < B; ++blk) {
-                const size_t pos = blk * 8 + slot;
+                const size_t pos = blk * per + slot;
                 if (pos < V) dealt[pos] = mesh->order[next++];
             }
         mesh->order = dealt;
         mesh->sorted = true;
+        mesh->sort_block = static_cast<int>(per);
     }
     for (int s = 0; s < vpad; ++s) {
         float* wv = &w[static_cast<size_t>(s) * 4];
@@ -841,10 +845,10 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
     if (option == DMK_OPT_SKIN_PLANAR_OUTPUT) {
         if (value < 0 || value > 2) return fail(c->ctx, DMK_ERR_INVALID, "DMK_OPT_SKIN_PLANAR_OUTPUT takes 0, 1 or 2");
         if (value) {
-            auto supported = [&](dmk_mesh_t m) { return !m || (!m->sorted && plan_skin(m->vpad, m->palette_size, c->ctx->num_sms, value).replicas == 8); };
+            auto supported = [&](dmk_mesh_t m) { return !m || plan_skin(m->vpad, m->palette_size, c->ctx->num_sms, value).replicas == 8; };
             bool ok = supported(c->mesh);
             for (auto& x : c->extra_skins) ok = ok && supported(x.mesh);
-            if (!ok) return fail(c->ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots and a mesh in the caller's vertex order");
+            if (!ok) return fail(c->ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots");
         }
         c->skin_variant = value;
         if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - c->reserved_sms, value);
@@ -1665,11 +1669,11 @@ dmk_status dmk_crowd_add_skin(dmk_crowd_t c, dmk_armature_t arm, dmk_mesh_t mesh
         dev_free(x.d_skinned);
         return cuda_fail(ctx, e, "dmk_crowd_add_skin allocation");
     }
-    if (mesh && c->skin_variant && (mesh->sorted || plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms, c->skin_variant).replicas != 8)) {
+    if (mesh && c->skin_variant && plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms, c->skin_variant).replicas != 8) {
         dev_free(x.d_palette);
         dev_free(x.d_palette34);
         dev_free(x.d_skinned);
-        return fail(ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots and a mesh in the caller's vertex order");
+        return fail(ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots");
     }
     if (mesh) x.plan = plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms - c->reserved_sms, c->skin_variant);
     c->extra_skins.push_back(x);

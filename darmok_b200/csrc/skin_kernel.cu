@@ -321,8 +321,8 @@ size_t skin_smem_bytes(int palette_size, int repl) {
 }
 template <typename F>
 auto with_kernel(int repl, bool skip, int variant, F&& f) {
-    if (variant == 1) return f(skin_kernel<8, false, 4, true, 320>);   // planar output, up to 10 warps
-    if (variant == 2) return f(skin_kernel<8, false, 4, true, 448>);   // planar output, up to 14 warps
+    if (variant == 1) return skip ? f(skin_kernel<8, true, 4, true, 320>) : f(skin_kernel<8, false, 4, true, 320>);   // planar output, up to 10 warps
+    if (variant == 2) return skip ? f(skin_kernel<8, true, 4, true, 448>) : f(skin_kernel<8, false, 4, true, 448>);   // planar output, up to 14 warps
     if (skip && repl == 8) return f(skin_kernel<8, true>);   // meshes grouped by influence count
     switch (repl) {
     case 8: return f(skin_kernel<8, false>);

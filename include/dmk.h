@@ -112,7 +112,13 @@ DMK_API dmk_status dmk_mesh_create(dmk_context_t ctx, const float* position, con
  * weights, so that warps skip the palette fetches of absent influences; the skinned buffer is then in the order given by
  * dmk_mesh_vertex_order (out[i] = index, in the caller's arrays, of the vertex at position i) and the caller remaps its
  * index buffer once, as after any vertex-cache optimisation.  Without the flag the caller's order is kept. */
-enum { DMK_MESH_SORT_BY_INFLUENCES = 1 };
+enum {
+    DMK_MESH_SORT_BY_INFLUENCES = 1,
+    /* with DMK_MESH_SORT_BY_INFLUENCES: group for the 4-vertices-per-thread skinning shapes of
+     * DMK_OPT_SKIN_PLANAR_OUTPUT instead of the default 8-vertices-per-thread kernel (either kernel is correct on either
+     * grouping; the matching one skips more gathers) */
+    DMK_MESH_SORT_BLOCKS_OF_4 = 2
+};
 DMK_API dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const float* normal, const float* tangent,
                                       const float* indices, const float* weights, int num_vertices, int palette_size,
                                       uint32_t flags, dmk_mesh_t* out);
@@ -142,8 +148,7 @@ enum {
      * character, [N][9][vertex_pitch] (plane 0..2 position.xyz, 3..5 normal.xyz, 6..8 tangent.xyz), for consumers that
      * pull vertices from buffers; the skinning kernel then keeps 4 vertices per thread and writes whole 128-byte lines
      * (1: up to 10 warps per SM, 2: up to 14).  The host getters (dmk_crowd_get_skinned, dmk_crowd_get_skin_skinned)
-     * return [count][V][9] whatever the device layout is.  DMK_ERR_UNSUPPORTED for palettes above 181 slots and for
-     * influence-sorted meshes.  EXPERIMENTAL: compiled and tested against the reference layout, not yet timed. */
+     * return [count][V][9] whatever the device layout is.  DMK_ERR_UNSUPPORTED for palettes above 181 slots.  EXPERIMENTAL: compiled and tested against the reference layout, not yet timed. */
     DMK_OPT_SKIN_PLANAR_OUTPUT = 4
 };
 DMK_API dmk_status dmk_crowd_set_option(dmk_crowd_t crowd, int option, int value);

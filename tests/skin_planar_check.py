@@ -77,17 +77,24 @@ def main():
         assert np.array_equal(crowd.get_skinned(), reference), "back to the interleaved layout"
         crowd.close()
         mesh.close()
-    # refused where the layout cannot be honoured: influence-sorted meshes
-    mesh_s = synth.make_mesh(100, 67, seed=1)
-    mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size, flags=capi.MESH_SORT_BY_INFLUENCES)
-    crowd = capi.Crowd(ctx, skel, clips, arm, mesh, 3, 2)
-    try:
-        crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, 1)
-        raise AssertionError("planar output on a sorted mesh was accepted")
-    except capi.DmkError as e:
-        assert e.status == capi.ERR_UNSUPPORTED
-    crowd.close()
-    mesh.close()
+    # influence-sorted meshes (either grouping) with the predicated gathers: the same vertices, in the mesh's stored order
+    mesh_s = synth.make_mesh(2000, 67, seed=1)
+    n = 11
+    cr = synth.make_crowd(n, 2, len(base.clips), seed=77)
+    ref = O.Crowd(oskel, oclips, remap, base.arm.inv_bind, n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, mesh=mesh_s, want=("skinned",))
+    for flags in (capi.MESH_SORT_BY_INFLUENCES, capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4):
+        mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size, flags=flags)
+        order = mesh.order
+        assert sorted(order.tolist()) == list(range(2000))
+        crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+        for variant in (0, 1, 2):
+            crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
+            crowd.step(0.0, capi.STEP_POSE | capi.STEP_SKIN)
+            assert_close(crowd.get_skinned(), ref["skinned"][:, order], f"sorted mesh (flags {flags}), variant {variant}")
+            checked += 1
+        crowd.close()
+        mesh.close()
     print(f"planar skinning: {checked} (variant, vertex count) cases bit-identical to the default kernel")
     for o in (arm, clips, *clip_objs, skel, ctx):
         o.close()
