@@ -60,3 +60,30 @@ def test_cuda_path_matches_golden_vectors():
     finally:
         for o in (crowd, mesh, arm, clips, *clip_objs, skel, ctx):
             o.close()
+
+
+def test_scenario_animator_is_the_reference_sample_animator():
+    """tests/cpp/animator_test.cpp drives the animator of samples/ozz/assets/animator.json (summary committed by
+    tests/golden/make_sample_animator_golden.py): same clips, blend positions, blend type, threshold, tween and transition
+    durations for the states the sample defines."""
+    import json
+    import re
+    gold = json.load(open(os.path.join(HERE, "golden", "sample_animator.json")))
+    src = open(os.path.join(HERE, "cpp", "animator_test.cpp")).read()
+    names = re.search(r"kClipNames\[\] = \{(.*?)\};", src, re.S).group(1)
+    names = re.findall(r'"(\w+)"', names)
+    pos = re.search(r"kBlendPos\[9\]\[2\] = \{(.*?)\};", src, re.S).group(1)
+    pos = [[int(a), int(b)] for a, b in re.findall(r"\{(-?\d+), (-?\d+)\}", pos)]
+    loco = gold["states"]["locomotion"]
+    assert [[n, p] for n, p in zip(names[:9], pos)] == loco["clips"]
+    assert gold["states"]["talk"]["clips"] == [[names[9], [0, 0]]]
+    # addState("locomotion", loco, 1 = Directional, threshold, tween duration, ...)
+    m = re.search(r'addState\("locomotion", loco, (\d), ([\d.]+)f, ([\d.]+)f', src)
+    assert loco["blend"] == "Directional" and m.group(1) == "1"
+    assert float(m.group(2)) == loco["threshold"] and float(m.group(3)) == loco["tween_duration"]
+    for key, duration in gold["transitions"].items():
+        a, b = key.split(">")
+        t = re.search(rf'addTransition\("{a}", "{b}", ([\d.]+)f', src)
+        assert t and float(t.group(1)) == duration, key
+    from tests.test_host_shim import CLIPS
+    assert CLIPS == names
