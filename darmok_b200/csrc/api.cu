@@ -843,7 +843,7 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
         return DMK_OK;
     }
     if (option == DMK_OPT_SKIN_PLANAR_OUTPUT) {
-        if (value < 0 || value > 2) return fail(c->ctx, DMK_ERR_INVALID, "DMK_OPT_SKIN_PLANAR_OUTPUT takes 0, 1 or 2");
+        if (value < 0 || value > 3) return fail(c->ctx, DMK_ERR_INVALID, "DMK_OPT_SKIN_PLANAR_OUTPUT takes 0, 1, 2 or 3");
         if (value) {
             auto supported = [&](dmk_mesh_t m) { return !m || plan_skin(m->vpad, m->palette_size, c->ctx->num_sms, value).replicas == 8; };
             bool ok = supported(c->mesh);
@@ -1629,16 +1629,26 @@ static dmk_status read_skinned(dmk_crowd_t c, dmk_mesh_t mesh, const float* d_sk
         DMK_CUDA(c->ctx, cudaMemcpy2DAsync(out, row * 4, d_skinned + first * pitch, pitch * 4, row * 4, count, cudaMemcpyDeviceToHost, c->ctx->stream));
         return finish_and_check(c);
     }
-    // planar on the device: [9][vpad] per character
+    // on the device: nine component planes [9][vpad] (1, 2) or three float3 streams [3][vpad][3] (3) per character
     std::vector<float> planes(static_cast<size_t>(count) * pitch);
     DMK_CUDA(c->ctx, cudaMemcpyAsync(planes.data(), d_skinned + first * pitch, planes.size() * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
     if (dmk_status st = finish_and_check(c)) return st;
-    for (size_t i = 0; i < static_cast<size_t>(count); ++i)
+    for (size_t i = 0; i < static_cast<size_t>(count); ++i) {
+        if (c->skin_variant == 3) {
+            for (size_t a = 0; a < 3; ++a) {
+                const float* src = planes.data() + i * pitch + a * vpad * 3;
+                float* dst = out + i * row + a * 3;
+                for (size_t v = 0; v < nv; ++v)
+                    for (size_t r = 0; r < 3; ++r) dst[v * 9 + r] = src[v * 3 + r];
+            }
+            continue;
+        }
         for (size_t k = 0; k < 9; ++k) {
             const float* src = planes.data() + i * pitch + k * vpad;
             float* dst = out + i * row + k;
             for (size_t v = 0; v < nv; ++v) dst[v * 9] = src[v];
         }
+    }
     return DMK_OK;
 }
 dmk_status dmk_crowd_get_skinned(dmk_crowd_t c, int64_t first, int64_t count, float* out) {

@@ -145,9 +145,13 @@ __device__ __forceinline__ float4 blend_row(const Rows4& x, float w0, float w1, 
 //     4 consecutive vertices are 16 contiguous bytes of every plane, so each warp store covers 512 contiguous bytes --
 //     whole 128-byte lines instead of 32 scattered sectors -- and half the vertices per thread leave room for 10 (MAXT =
 //     320, up to 204 registers) or 14 warps (MAXT = 448, up to 144 registers) per SM instead of 7.
-template <int REPL, bool SKIP, int VPT = 8, bool PLANAR = false, int MAXT = kMaxThreads>
+//   VPT = 8, STREAMS = true: three float3 streams per character, [N][3][V][3] (positions, normals, tangents: the usual
+//     non-interleaved vertex-buffer layout); a thread's 8 vertices are 96 contiguous bytes = 3 whole sectors of each stream,
+//     flushed as they complete like the interleaved sectors; a warp store then touches 24 lines instead of 32.
+template <int REPL, bool SKIP, int VPT = 8, bool PLANAR = false, int MAXT = kMaxThreads, bool STREAMS = false>
 __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
     static_assert(PLANAR ? VPT == 4 : VPT == 8, "interleaved output needs 8 vertices per thread (9 whole sectors); planar uses 4 (st.v4 per plane)");
+    static_assert(!(PLANAR && STREAMS), "one output layout at a time");
     constexpr int kVPT = VPT;   // shadows the file-level constant inside this kernel
     extern __shared__ __align__(128) unsigned char smem[];
     const int PS = p.palette_size;
@@ -288,14 +292,23 @@ __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
                     const float m2[3] = {m[0].z, m[1].z, m[2].z}, m3[3] = {m[0].w, m[1].w, m[2].w};
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        res[v * 9 + r] = fmaf(m2[r], pz[v], fmaf(m1[r], py[v], fmaf(m0[r], px[v], m3[r])));
-                        res[v * 9 + 3 + r] = fmaf(m2[r], nz[v], fmaf(m1[r], ny[v], m0[r] * nx[v]));
-                        res[v * 9 + 6 + r] = fmaf(m2[r], tz[v], fmaf(m1[r], ty[v], m0[r] * tx[v]));
+                        // interleaved / planar: vertex-major (v * 9 + attribute * 3 + r); streams: attribute-major (a * 24 + v * 3 + r)
+                        res[STREAMS ? v * 3 + r : v * 9 + r] = fmaf(m2[r], pz[v], fmaf(m1[r], py[v], fmaf(m0[r], px[v], m3[r])));
+                        res[STREAMS ? kVPT * 3 + v * 3 + r : v * 9 + 3 + r] = fmaf(m2[r], nz[v], fmaf(m1[r], ny[v], m0[r] * nx[v]));
+                        res[STREAMS ? kVPT * 6 + v * 3 + r : v * 9 + 6 + r] = fmaf(m2[r], tz[v], fmaf(m1[r], ty[v], m0[r] * tx[v]));
                     }
                     // flush every 32-byte sector that just became complete
-                    if (!PLANAR) {
+                    if (!PLANAR && !STREAMS) {
 #pragma unroll
                         for (int sct = (v * 9) / 8; sct < ((v + 1) * 9) / 8; ++sct) st_v8(out + sct * 8, res + sct * 8);
+                    }
+                    if (STREAMS) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            float* stream = p.out + (((size_t)cid * 3 + a) * p.vpad + v0) * 3;
+#pragma unroll
+                            for (int sct = (v * 3) / 8; sct < ((v + 1) * 3) / 8; ++sct) st_v8(stream + sct * 8, res + a * kVPT * 3 + sct * 8);
+                        }
                     }
                 }
                 if (PLANAR) {
@@ -321,6 +334,7 @@ size_t skin_smem_bytes(int palette_size, int repl) {
 }
 template <typename F>
 auto with_kernel(int repl, bool skip, int variant, F&& f) {
+    if (variant == 3) return skip ? f(skin_kernel<8, true, 8, false, kMaxThreads, true>) : f(skin_kernel<8, false, 8, false, kMaxThreads, true>);   // three float3 streams
     if (variant == 1) return skip ? f(skin_kernel<8, true, 4, true, 320>) : f(skin_kernel<8, false, 4, true, 320>);   // planar output, up to 10 warps
     if (variant == 2) return skip ? f(skin_kernel<8, true, 4, true, 448>) : f(skin_kernel<8, false, 4, true, 448>);   // planar output, up to 14 warps
     if (skip && repl == 8) return f(skin_kernel<8, true>);   // meshes grouped by influence count
@@ -336,7 +350,7 @@ auto with_kernel(int repl, bool skip, int variant, F&& f) {
 SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant) {
     SkinPlan plan{};
     plan.variant = variant;
-    const int vpt = variant ? 4 : kVPT;
+    const int vpt = (variant == 1 || variant == 2) ? 4 : kVPT;
     const int max_threads = variant == 1 ? 320 : variant == 2 ? 448 : kMaxThreads;
     const int max_tile = max_threads * vpt;
     plan.num_tiles = (vpad + max_tile - 1) / max_tile;

@@ -147,7 +147,8 @@ enum {
     /* Layout of the skinned vertices.  0 (default): interleaved [N][vertex_pitch][9].  1 or 2: nine component planes per
      * character, [N][9][vertex_pitch] (plane 0..2 position.xyz, 3..5 normal.xyz, 6..8 tangent.xyz), for consumers that
      * pull vertices from buffers; the skinning kernel then keeps 4 vertices per thread and writes whole 128-byte lines
-     * (1: up to 10 warps per SM, 2: up to 14).  The host getters (dmk_crowd_get_skinned, dmk_crowd_get_skin_skinned)
+     * (1: up to 10 warps per SM, 2: up to 14).  3: three float3 streams per character, [N][3][vertex_pitch][3] (positions,
+     * normals, tangents: the usual non-interleaved vertex-buffer layout), same thread shape as the default.  The host getters (dmk_crowd_get_skinned, dmk_crowd_get_skin_skinned)
      * return [count][V][9] whatever the device layout is.  DMK_ERR_UNSUPPORTED for palettes above 181 slots.  EXPERIMENTAL: compiled and tested against the reference layout, not yet timed. */
     DMK_OPT_SKIN_PLANAR_OUTPUT = 4
 };

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Stand-alone check of the planar-output skinning kernels (DMK_OPT_SKIN_PLANAR_OUTPUT = 1, 2), run by
+"""Stand-alone check of the non-interleaved skinning kernels (DMK_OPT_SKIN_PLANAR_OUTPUT = 1, 2, 3), run by
 tests/test_gpu_zz_skin_planar.py in a child process (a device fault here must not poison the parity suite's CUDA context).
 
 For every variant and a set of vertex counts around the tile boundaries of both shapes: the skinned vertices returned by
@@ -58,14 +58,19 @@ def main():
         bits, count = crowd.get_visibility()
         visible = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
         vpad = (num_vertices + 7) // 8 * 8
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
             torch.as_tensor(_Dev(crowd.skinned_dev(), (n * vpad * 9,), "<f4"), device=dev).fill_(float("nan"))
             crowd.step(0.0, capi.STEP_SKIN)
             got = crowd.get_skinned()
             assert np.array_equal(got, reference), f"variant {variant} V={num_vertices}: differs from the default kernel"
-            planes = torch.as_tensor(_Dev(crowd.skinned_dev(), (n, 9, vpad), "<f4"), device=dev).cpu().numpy()
-            assert np.array_equal(planes[:, :, :num_vertices].transpose(0, 2, 1), reference), f"variant {variant}: device layout is not [N][9][pitch]"
+            if variant == 3:   # three float3 streams
+                streams = torch.as_tensor(_Dev(crowd.skinned_dev(), (n, 3, vpad, 3), "<f4"), device=dev).cpu().numpy()
+                assert np.array_equal(streams[:, :, :num_vertices].transpose(0, 2, 1, 3).reshape(n, num_vertices, 9), reference), \
+                    "variant 3: device layout is not [N][3][pitch][3]"
+            else:
+                planes = torch.as_tensor(_Dev(crowd.skinned_dev(), (n, 9, vpad), "<f4"), device=dev).cpu().numpy()
+                assert np.array_equal(planes[:, :, :num_vertices].transpose(0, 2, 1), reference), f"variant {variant}: device layout is not [N][9][pitch]"
             # only the visible characters
             torch.as_tensor(_Dev(crowd.skinned_dev(), (n * vpad * 9,), "<f4"), device=dev).fill_(float("nan"))
             crowd.step(0.0, capi.STEP_SKIN | capi.STEP_SKIN_VISIBLE_ONLY)
@@ -88,7 +93,7 @@ def main():
         assert sorted(order.tolist()) == list(range(2000))
         crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
         crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
             crowd.step(0.0, capi.STEP_POSE | capi.STEP_SKIN)
             assert_close(crowd.get_skinned(), ref["skinned"][:, order], f"sorted mesh (flags {flags}), variant {variant}")

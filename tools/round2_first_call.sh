@@ -12,7 +12,7 @@ timeout 300 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.
 timeout 300 python tools/bench_configs.py 3s > gpurun_out/r02_skin_variants.jsonl 2> gpurun_out/r02_skin_variants.err
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench_store.bin tools/ubench_store.cu && timeout 120 tools/ubench_store.bin > gpurun_out/r02_ubench_store.log 2>&1
 # ncu: one full capture per skinning shape (only after the plain runs above), launch 6 = a steady-state skin launch
-for shape in "" planar1 planar2; do
+for shape in "" planar1 planar2 planar3; do
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:skin_kernel -s 2 -c 1 -f -o gpurun_out/r02_skin_${shape:-default} \
       python tools/skin_only.py $shape > gpurun_out/r02_ncu_skin_${shape:-default}.log 2>&1
 done
