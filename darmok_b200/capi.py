@@ -477,15 +477,17 @@ class Crowd:
 
     def get_skin_palette(self, skin, first=0, count=None):
         count = self.n - first if count is None else count
-        arm = self.skins[skin][0] if hasattr(self, "skins") else self.arm
+        skins = getattr(self, "skins", [(self.arm, self.mesh)])
+        arm = skins[skin][0] if 0 <= skin < len(skins) else self.arm   # an unknown skin is the library's error to report
         out = np.zeros((count, arm.palette_size, 16), np.float32)
         self.ctx.check(lib().dmk_crowd_get_skin_palette(self.h, skin, first, count, _ptr(out)))
         return out
 
     def get_skin_skinned(self, skin, first=0, count=None):
         count = self.n - first if count is None else count
-        mesh = self.skins[skin][1] if hasattr(self, "skins") else self.mesh
-        out = np.zeros((count, mesh.num_vertices, 9), np.float32)
+        skins = getattr(self, "skins", [(self.arm, self.mesh)])
+        mesh = skins[skin][1] if 0 <= skin < len(skins) else None
+        out = np.zeros((count, mesh.num_vertices if mesh else 1, 9), np.float32)
         self.ctx.check(lib().dmk_crowd_get_skin_skinned(self.h, skin, first, count, _ptr(out)))
         return out
 
