@@ -61,6 +61,7 @@ def main():
         for variant in (1, 2, 3):
             crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
             torch.as_tensor(_Dev(crowd.skinned_dev(), (n * vpad * 9,), "<f4"), device=dev).fill_(float("nan"))
+            torch.cuda.synchronize()   # torch's stream is not the context's: the fill must have landed before the step
             crowd.step(0.0, capi.STEP_SKIN)
             got = crowd.get_skinned()
             assert np.array_equal(got, reference), f"variant {variant} V={num_vertices}: differs from the default kernel"
@@ -73,6 +74,7 @@ def main():
                 assert np.array_equal(planes[:, :, :num_vertices].transpose(0, 2, 1), reference), f"variant {variant}: device layout is not [N][9][pitch]"
             # only the visible characters
             torch.as_tensor(_Dev(crowd.skinned_dev(), (n * vpad * 9,), "<f4"), device=dev).fill_(float("nan"))
+            torch.cuda.synchronize()   # torch's stream is not the context's: the fill must have landed before the step
             crowd.step(0.0, capi.STEP_SKIN | capi.STEP_SKIN_VISIBLE_ONLY)
             got = crowd.get_skinned()
             assert np.array_equal(got[visible], reference[visible]) and np.isnan(got[~visible]).all(), f"variant {variant}: visible-only"
