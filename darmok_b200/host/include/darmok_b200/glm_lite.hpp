@@ -30,6 +30,8 @@ struct vec3 {
     constexpr vec3() = default;
     constexpr explicit vec3(float v) : x(v), y(v), z(v) {}
     constexpr vec3(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
+    float& operator[](int i) { return (&x)[i]; }
+    const float& operator[](int i) const { return (&x)[i]; }
 };
 
 struct vec4 {

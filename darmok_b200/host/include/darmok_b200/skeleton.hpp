@@ -166,6 +166,26 @@ struct SkinnedMeshData {
     int numVertices() const noexcept { return static_cast<int>(position.size() / 3); }
 };
 
+// MeshData's per-vertex skinning input (include/darmok/mesh_core.hpp:148-162): any number of (bone, weight) pairs, bone =
+// index into the mesh's bone list = Armature joint order (src/skeleton_assimp.cpp:1129-1150).
+struct MeshDataWeight final {
+    size_t boneIndex = 0;
+    float value = 0.F;
+};
+struct MeshDataVertex final {
+    glm::vec3 position{0.f};
+    glm::vec3 normal{0.f, 1.f, 0.f};
+    glm::vec3 tangent{0.f};
+    std::vector<MeshDataWeight> weights;
+};
+// The influence packing of MeshData::exportData (src/mesh_core.cpp:336-356): weights sorted by descending value (std::sort,
+// like the reference: the order of equal weights is the library's), weights <= 0 dropped, the first four kept;
+// indices[j] = bone index as float, unused = -1; weights start as (1, 0, 0, 0), so a vertex without any positive weight
+// keeps weight 1 on index -1 (= the shader's pass-through, darmok_skinning.inc.slang:21-27).
+void packVertexInfluences(const std::vector<MeshDataWeight>& weights, float outIndices[4], float outWeights[4]) noexcept;
+// position / normal / tangent and the packed influences of every vertex, as exportData writes them
+SkinnedMeshData makeSkinnedMeshData(const std::vector<MeshDataVertex>& vertices) noexcept;
+
 // One Skinnable of a character: the armature whose palette is built and (optionally) the mesh it skins.  darmok hangs one
 // entity with Renderable + Skinnable per assimp mesh under the entity that owns the SkeletalAnimator
 // (src/scene_assimp.cpp:187-193,696-721); shared by every animator of a batch, never copied per character.

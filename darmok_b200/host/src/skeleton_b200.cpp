@@ -120,6 +120,38 @@ expected<std::shared_ptr<SkeletalAnimation>, std::string> B200SkeletalAnimationL
     return SkeletalAnimation::load(_ctx, data->data(), data->size());
 }
 
+// ---- MeshData::exportData's influence packing (src/mesh_core.cpp:336-356) ---------------------------------------------------
+void packVertexInfluences(const std::vector<MeshDataWeight>& weights, float outIndices[4], float outWeights[4]) noexcept {
+    outWeights[0] = 1.f; outWeights[1] = 0.f; outWeights[2] = 0.f; outWeights[3] = 0.f;   // glm::vec4 weights{ 1, 0, 0, 0 }
+    for (int k = 0; k < 4; ++k) outIndices[k] = -1.f;                                      // glm::vec4 indices{ -1 }
+    int j = 0;
+    auto weightVector = weights;
+    std::sort(weightVector.begin(), weightVector.end(), [](auto& a, auto& b) { return a.value > b.value; });
+    for (auto& weight : weightVector) {
+        if (weight.value <= 0.f) continue;
+        outIndices[j] = static_cast<float>(weight.boneIndex);
+        outWeights[j] = weight.value;
+        if (++j > 3) break;
+    }
+}
+
+SkinnedMeshData makeSkinnedMeshData(const std::vector<MeshDataVertex>& vertices) noexcept {
+    SkinnedMeshData out;
+    const size_t n = vertices.size();
+    out.position.reserve(n * 3); out.normal.reserve(n * 3); out.tangent.reserve(n * 3);
+    out.indices.resize(n * 4); out.weights.resize(n * 4);
+    for (size_t i = 0; i < n; ++i) {
+        const MeshDataVertex& v = vertices[i];
+        for (int k = 0; k < 3; ++k) {
+            out.position.push_back(v.position[k]);
+            out.normal.push_back(v.normal[k]);
+            out.tangent.push_back(v.tangent[k]);
+        }
+        packVertexInfluences(v.weights, &out.indices[i * 4], &out.weights[i * 4]);
+    }
+    return out;
+}
+
 // ---- device objects of one (skeleton, clips, armature, mesh) combination --------------------------------------------------
 struct SkeletalAnimator::Device {
     std::shared_ptr<DeviceContext> ctx;

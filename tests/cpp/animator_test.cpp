@@ -15,6 +15,7 @@
 #include "dmk.h"
 
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -272,6 +273,27 @@ static int runCpu(const std::string& dir) {
     }
     for (const char* n : {"locomotion", "talk", "greet", "strafe", "nope"})
         CHECK(core.getStateDuration(n) == ref.getStateDuration(n), "getStateDuration(%s): %g vs %g", n, core.getStateDuration(n), ref.getStateDuration(n));
+    // MeshData::exportData's influence packing (src/mesh_core.cpp:336-356): known answers derived from the reference's loop
+    {
+        auto pack = [](std::vector<MeshDataWeight> w) {
+            std::array<float, 8> o{};
+            packVertexInfluences(w, o.data(), o.data() + 4);
+            return o;
+        };
+        using A = std::array<float, 8>;
+        CHECK((pack({{3, 0.2f}, {1, 0.5f}, {7, 0.3f}}) == A{1, 7, 3, -1, 0.5f, 0.3f, 0.2f, 0}), "packing: sorted by descending weight, unused index -1");
+        CHECK((pack({}) == A{-1, -1, -1, -1, 1, 0, 0, 0}), "packing: no influence keeps weights (1, 0, 0, 0) on index -1");
+        CHECK((pack({{2, 0.f}, {4, -0.1f}, {5, 0.4f}}) == A{5, -1, -1, -1, 0.4f, 0, 0, 0}), "packing: weights <= 0 are dropped");
+        CHECK((pack({{0, .1f}, {1, .2f}, {2, .3f}, {3, .25f}, {4, .15f}}) == A{2, 3, 1, 4, .3f, .25f, .2f, .15f}),
+              "packing: the four largest are kept as they are (no renormalisation)");
+        std::vector<MeshDataVertex> verts(2);
+        verts[0].position = glm::vec3(1.f, 2.f, 3.f);
+        verts[0].weights = {{6, 1.f}};
+        verts[1].tangent = glm::vec3(0.f, 0.f, 1.f);
+        const SkinnedMeshData md = makeSkinnedMeshData(verts);
+        CHECK(md.numVertices() == 2 && md.position[1] == 2.f && md.normal[1] == 1.f && md.normal[4] == 1.f && md.tangent[5] == 1.f, "mesh data streams");
+        CHECK(md.indices[0] == 6.f && md.indices[1] == -1.f && md.weights[0] == 1.f && md.indices[4] == -1.f && md.weights[4] == 1.f, "mesh data influences");
+    }
     // every easing curve, specialised (shim) against general (oracle) form
     for (int type = 0; type < 32; ++type)
         for (int i = -4; i <= 44; ++i) {
