@@ -77,6 +77,7 @@ SIGNATURES = [
     ("dmk_crowd_size", _i64, [_vp]),
     ("dmk_crowd_enable_outputs", _i, [_vp, _u32]),
     ("dmk_crowd_set_option", _i, [_vp, _i, _i]),
+    ("dmk_skin_plan", _i, [_i, _i, _i, _i, C.POINTER(_i64)]),
     ("dmk_crowd_set_layers", _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f]),
     ("dmk_crowd_set_programs", _i, [_vp, _i, _vp, _vp, _vp, _vp]),
     ("dmk_crowd_update_layers", _i, [_vp, _i, _vp, _vp, _vp]),
@@ -593,3 +594,13 @@ class Exchange:
         if self.h:
             lib().dmk_exchange_destroy(self.h)
             self.h = None
+
+
+def skin_plan(vertex_pitch, palette_size=68, num_sms=148, layout=0):
+    """dmk_skin_plan as a dict (works without a device)"""
+    out = (C.c_int64 * 7)()
+    st = lib().dmk_skin_plan(vertex_pitch, palette_size, num_sms, layout, out)
+    if st:
+        raise DmkError(st, lib().dmk_last_error(None).decode())
+    keys = ("threads", "num_tiles", "tile_vertices", "grid", "replicas", "smem", "vertices_per_thread")
+    return dict(zip(keys, [int(x) for x in out]))

@@ -865,6 +865,21 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
     return fail(c->ctx, DMK_ERR_INVALID, "unknown option");
 }
 
+dmk_status dmk_skin_plan(int vertex_pitch, int palette_size, int num_sms, int layout, int64_t* out7) {
+    if (!out7 || vertex_pitch < 8 || vertex_pitch % 8 || palette_size < 1 || palette_size > kMaxPalette || num_sms < 1 || layout < 0 || layout > 3)
+        return fail(nullptr, DMK_ERR_INVALID, "dmk_skin_plan: argument out of range");
+    const SkinPlan plan = plan_skin(vertex_pitch, palette_size, num_sms, layout);
+    cudaGetLastError();   // without a device the occupancy query fails and the plan assumes one block per SM
+    out7[0] = plan.threads;
+    out7[1] = plan.num_tiles;
+    out7[2] = plan.tile_vertices;
+    out7[3] = plan.grid;
+    out7[4] = plan.replicas;
+    out7[5] = static_cast<int64_t>(plan.smem);
+    out7[6] = (layout == 1 || layout == 2) ? 4 : 8;
+    return DMK_OK;
+}
+
 dmk_status dmk_crowd_enable_outputs(dmk_crowd_t c, uint32_t outputs) {
     if (!c) return DMK_ERR_INVALID;
     dmk_context_t ctx = c->ctx;

@@ -153,6 +153,11 @@ enum {
     DMK_OPT_SKIN_PLANAR_OUTPUT = 4
 };
 DMK_API dmk_status dmk_crowd_set_option(dmk_crowd_t crowd, int option, int value);
+/* Launch shape the skinning kernel would use for a mesh of `vertex_pitch` vertices (multiple of 8), a palette of
+ * `palette_size` slots, `num_sms` SMs and output layout `layout` (DMK_OPT_SKIN_PLANAR_OUTPUT value): out[0] threads per
+ * block, [1] vertex tiles per character, [2] vertices per tile, [3] persistent blocks, [4] palette replicas in shared
+ * memory, [5] shared-memory bytes, [6] vertices per thread.  Needs no device (occupancy is taken as one block per SM then). */
+DMK_API dmk_status dmk_skin_plan(int vertex_pitch, int palette_size, int num_sms, int layout, int64_t* out7);
 
 /* Optional per-character outputs that only the host-side getters need (they cost HBM writes per step):
  * models -> dmk_crowd_get_models, locals -> dmk_crowd_get_locals, key indices -> dmk_crowd_get_key_indices. */
