@@ -268,7 +268,11 @@ DMK_API dmk_status dmk_crowd_get_programs(dmk_crowd_t crowd, int num_layers, int
                                           float* out_weight, dmk_pose_program* out_programs);
 
 /* Transform::getWorldInverse (src/transform.cpp:286-309) + BoundingBox (assets/protobuf/shape.proto:7-10) of each
- * character entity: world_inverse [N][16], bbox [N][6] = min.xyz, max.xyz (local space). */
+ * character entity: world_inverse [N][16], bbox [N][6] = min.xyz, max.xyz (local space).  An entity without a Transform
+ * is culled against the untransformed frustum (src/culling.cpp:275-278): pass the identity.  FrustumCuller only visits
+ * entities that have a BoundingBox (filter at src/culling.cpp:36-44); one without is never culled there, so a caller
+ * ignores its visibility bit (there is no box value that means "always visible": a NaN box is culled, as in the reference,
+ * because `sd <= 0` is false for NaN). */
 DMK_API dmk_status dmk_crowd_set_instances(dmk_crowd_t crowd, const float* world_inverse, const float* bbox);
 
 /* "Next" row: instead of precomputed world inverses, hand over what Transform holds --
