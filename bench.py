@@ -29,6 +29,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+SKIN_KERNEL_NAMES = {0: "skin_kernel<8> (K5 LBS)", 1: "skin_kernel<8, planar, 4 vertices/thread, <= 320 threads> (K5 LBS)",
+                     2: "skin_kernel<8, planar, 4 vertices/thread, <= 448 threads> (K5 LBS)", 3: "skin_kernel<8, three float3 streams> (K5 LBS)"}
+SKIN_LAYOUTS = {0: "interleaved [V][9]", 1: "nine component planes [9][V]", 2: "nine component planes [9][V]", 3: "three float3 streams [3][V][3]"}
 METRIC = "skinned_characters_per_sec"
 UNIT = "characters/s"
 FLT_MIN = float(np.finfo(np.float32).tiny)
@@ -51,7 +54,7 @@ def workload_config(args):
         "workload": "BASELINE.json configs[2]: 100k characters x 67 joints, two-layer BlendingJob (transition form), "
                     "5k verts x 4 influences LBS positions+normals+tangents; + frustum cull and visible-palette gather",
         "characters_per_gpu": args.chars, "joints": 67, "layers": 2, "clips": args.clips, "vertices": args.verts,
-        "influences": 4, "dt": DT,
+        "influences": 4, "dt": DT, "skinned_layout": SKIN_LAYOUTS[getattr(args, "skin_layout", 0)],
         "gather": gather_description(args),
         "l2": "inputs larger than L2: each step streams %.1f GB of skinned vertices per GPU (L2 = 126 MB)"
               % (args.chars * args.verts * 36 / 1e9),
@@ -269,6 +272,8 @@ def run_gpu(args):
         arm = capi.Armature(ctx, skel, arm_s.names, arm_s.inv_bind)
         mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size)
         crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
+        if args.skin_layout:
+            crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, args.skin_layout)
         cr = synth.make_crowd(n, 2, len(clips_s), seed=42 + rank)       # varied clips / phases per rank
         inst = synth.make_instances(n, seed=5 + rank, extent=500.0)
         crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
@@ -483,7 +488,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "skin_kernel<8> (K5 LBS)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": SKIN_KERNEL_NAMES[args.skin_layout], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": skin_avg_ms, "launches_timed": int(skin_n)},
         "cpu_baseline": cpu_baseline,
@@ -529,6 +534,9 @@ def main():
     ap.add_argument("--clips", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs left to the gather so that it overlaps the skinning")
+    ap.add_argument("--skin-layout", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="DMK_OPT_SKIN_PLANAR_OUTPUT: 0 interleaved [V][9] (default), 1 / 2 nine component planes (10 / 14 warps), 3 three float3 "
+                         "streams; not yet measured on hardware, see DESIGN.md section 9")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
                     help="N > 1: visible-palette transport: pack kernel + NCCL send/recv, or the pack+transfer kernel storing into rank 0's "
                          "memory over NVLink (dmk_exchange_*; not yet measured on hardware, see DESIGN.md section 5)")
