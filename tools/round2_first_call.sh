@@ -9,6 +9,7 @@ timeout 900 python -m pytest tests -q -m gpu -rxX > gpurun_out/r02_pytest_gpu.lo
 timeout 200 python tests/peer_exchange_check.py > gpurun_out/r02_peer_exchange_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_peer_exchange_check.log
 timeout 300 python tests/skin_planar_check.py > gpurun_out/r02_skin_planar_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_skin_planar_check.log
 timeout 300 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
+for layout in 1 2 3; do timeout 200 python bench.py --skin-layout $layout --no-cpu-baseline > gpurun_out/r02_bench_layout$layout.json 2> gpurun_out/r02_bench_layout$layout.err; done
 timeout 300 python tools/bench_configs.py 3s > gpurun_out/r02_skin_variants.jsonl 2> gpurun_out/r02_skin_variants.err
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench_store.bin tools/ubench_store.cu && timeout 120 tools/ubench_store.bin > gpurun_out/r02_ubench_store.log 2>&1
 # ncu: one full capture per skinning shape (only after the plain runs above), launch 6 = a steady-state skin launch
