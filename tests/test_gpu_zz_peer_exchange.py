@@ -21,3 +21,12 @@ def test_peer_exchange_three_logical_ranks_on_one_gpu():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "identical to the ranks' own visible palettes" in r.stdout
     assert "gives up after its timeout" in r.stdout and "never publishes" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="peer-memory exchange not yet verified on hardware (round 1 GPU budget spent)", strict=False)
+def test_peer_exchange_two_processes_over_cuda_ipc():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "peer_exchange_ipc_check.py")], capture_output=True, text=True, timeout=400)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "identical to what the ranks sent" in r.stdout
