@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02_build.log 2>&1
 timeout 900 python -m pytest tests -q -m gpu -rxX > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02_pytest_gpu.log
 timeout 200 python tests/peer_exchange_check.py > gpurun_out/r02_peer_exchange_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_peer_exchange_check.log
+timeout 300 python tests/peer_exchange_ipc_check.py > gpurun_out/r02_peer_exchange_ipc_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_peer_exchange_ipc_check.log
 timeout 300 python tests/skin_planar_check.py > gpurun_out/r02_skin_planar_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_skin_planar_check.log
 timeout 300 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
 for layout in 1 2 3; do timeout 200 python bench.py --skin-layout $layout --no-cpu-baseline > gpurun_out/r02_bench_layout$layout.json 2> gpurun_out/r02_bench_layout$layout.err; done
@@ -17,4 +18,4 @@ for shape in "" planar1 planar2 planar3; do
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:skin_kernel -s 2 -c 1 -f -o gpurun_out/r02_skin_${shape:-default} \
       python tools/skin_only.py $shape > gpurun_out/r02_ncu_skin_${shape:-default}.log 2>&1
 done
-tail -3 gpurun_out/r02_pytest_gpu.log gpurun_out/r02_peer_exchange_check.log gpurun_out/r02_skin_planar_check.log gpurun_out/r02_skin_variants.jsonl
+tail -3 gpurun_out/r02_pytest_gpu.log gpurun_out/r02_peer_exchange_check.log gpurun_out/r02_peer_exchange_ipc_check.log gpurun_out/r02_skin_planar_check.log gpurun_out/r02_skin_variants.jsonl
