@@ -12,6 +12,7 @@ timeout 300 python tests/skin_planar_check.py > gpurun_out/r02_skin_planar_check
 timeout 300 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
 for layout in 1 2 3; do timeout 200 python bench.py --skin-layout $layout --no-cpu-baseline > gpurun_out/r02_bench_layout$layout.json 2> gpurun_out/r02_bench_layout$layout.err; done
 timeout 300 python tools/bench_configs.py 3s > gpurun_out/r02_skin_variants.jsonl 2> gpurun_out/r02_skin_variants.err
+timeout 300 python tools/bench_pipelined.py > gpurun_out/r02_pipelined.json 2> gpurun_out/r02_pipelined.err
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench_store.bin tools/ubench_store.cu && timeout 120 tools/ubench_store.bin > gpurun_out/r02_ubench_store.log 2>&1
 # ncu: one full capture per skinning shape (only after the plain runs above), launch 6 = a steady-state skin launch
 for shape in "" planar1 planar2 planar3; do
