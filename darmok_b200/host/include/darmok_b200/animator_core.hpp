@@ -70,8 +70,13 @@ public:
     void afterFinished() noexcept { _speed = _def.speed; }
     // blend weights of the state's clips for a blend position (calcBlendWeights, src/skeleton.cpp:346-364)
     std::vector<float> calcBlendWeights(const glm::vec2& pos) const noexcept;
+    // what getLocals() holds (src/skeleton_ozz.cpp:617-624): the group of the last update that succeeded; null before the first
+    const GroupRequest* lastGood() const noexcept { return _hasLastGood ? &_lastGood : nullptr; }
 private:
     StateMachineState(const SkeletalAnimatorStateDefinition& def, std::vector<ClipState> clips) noexcept;
+    expected<void, std::string> updateImpl(float deltaTime, const glm::vec2& blendPosition, GroupRequest& out) noexcept;
+    GroupRequest _lastGood;
+    bool _hasLastGood = false;
     float calcDuration() const noexcept;
     float calcBlendWeight(const glm::vec2& pos, const glm::vec2& animPos) const noexcept;
     SkeletalAnimatorStateDefinition _def;
@@ -98,8 +103,10 @@ private:
     SkeletalAnimatorTransitionDefinition _def;
     StateMachineState _current, _previous;
     float _normalizedTime = 0.f;
-    bool _everBlended = false;
+    bool _everBlended = false;   // the transition's BlendingJob has run at least once: _locals holds its last output
     GroupRequest _lastCurrent;   // the current state's last resolved group (a finished transition keeps showing it)
+    GroupRequest _initialPrevious;      // what _locals starts as: the previous state's locals when the transition was created (:658-665)
+    bool _hasInitialPrevious = false;   // false: that state had never been updated (zero-initialised locals in darmok)
 };
 
 struct AnimatorEvents {   // listener fan-out, bound by SkeletalAnimator

@@ -111,6 +111,15 @@ std::vector<float> StateMachineState::calcBlendWeights(const glm::vec2& pos) con
 }
 
 expected<void, std::string> StateMachineState::update(float deltaTime, const glm::vec2& blendPosition, GroupRequest& out) noexcept {
+    auto r = updateImpl(deltaTime, blendPosition, out);
+    if (r) {   // getLocals() now holds this group's result; a failed BlendingJob leaves the state's locals as they were
+        _lastGood = out;
+        _hasLastGood = true;
+    }
+    return r;
+}
+
+expected<void, std::string> StateMachineState::updateImpl(float deltaTime, const glm::vec2& blendPosition, GroupRequest& out) noexcept {
     // src/skeleton_ozz.cpp:535-610
     deltaTime *= _speed;
     for (auto& clip : _clips) clip.update(deltaTime);
@@ -160,7 +169,13 @@ expected<void, std::string> StateMachineState::update(float deltaTime, const glm
 
 // ---- TransitionState: OzzSkeletalAnimatorTransition -------------------------------------------------------------------
 TransitionState::TransitionState(const SkeletalAnimatorTransitionDefinition& def, StateMachineState current, StateMachineState previous) noexcept
-    : _def{def}, _current{std::move(current)}, _previous{std::move(previous)} {}
+    : _def{def}, _current{std::move(current)}, _previous{std::move(previous)} {
+    // _locals{ _previousState.getLocals() } (src/skeleton_ozz.cpp:658-665): a copy taken now, not a view
+    if (const GroupRequest* g = _previous.lastGood()) {
+        _initialPrevious = *g;
+        _hasInitialPrevious = true;
+    }
+}
 
 expected<void, std::string> TransitionState::update(float deltaTime, const glm::vec2& blendPosition, PoseRequest& out) noexcept {
     // src/skeleton_ozz.cpp:682-726
@@ -178,10 +193,19 @@ expected<void, std::string> TransitionState::update(float deltaTime, const glm::
     float currentStateDeltaTime = deltaTime;
     if (_normalizedTime == 0.f) currentStateDeltaTime += _def.offset;
     if (auto r = _current.update(currentStateDeltaTime, blendPosition, out.group1); !r) {
-        // a failing current state is swallowed (C8): the job is not run and the last blended locals stay in place
-        out.top = PoseRequest::Skip;
+        // a failing current state is swallowed (C8): the BlendingJob is not run and _locals stays what it was -- the last
+        // blend's output (same matrices as last tick), or, before the first blend, the copy of the previous state's locals
+        // taken at construction.  A previous state that had never been updated leaves zero-initialised locals in darmok;
+        // that pose cannot be expressed here and the matrices are kept (documented deviation).
+        if (!_everBlended && _hasInitialPrevious) {
+            out.top = PoseRequest::Group0;
+            out.group0 = _initialPrevious;
+        } else {
+            out.top = PoseRequest::Skip;
+        }
         return {};
     }
+    _everBlended = true;
     _lastCurrent = out.group1;
     _normalizedTime += deltaTime / getDuration();
     const float v = ease01(_def.tween.easing, _normalizedTime);

@@ -29,6 +29,8 @@ float bounceOut(float position, float start, float end) {
 float bounceIn(float position, float start, float end) { return (end - start) - bounceOut((1 - position), 0.f, (end - start)) + start; }
 }  // namespace
 
+int g_unsampledHolds = 0;
+
 float ease(int type, float position, float start, float end) {
     const float d = end - start;
     switch (type) {
@@ -141,7 +143,7 @@ RefAnimationState::RefAnimationState(const orc_skeleton* skel, const AnimationDe
     : _def(def), _animation(anim), _sampling(orc_sampling_context_create(skel->num_joints)),
       _locals((size_t)skel->num_soa * ORC_SOA_FLOATS, 0.f) {}
 RefAnimationState::RefAnimationState(RefAnimationState&& o) noexcept
-    : _def(std::move(o._def)), _normalizedTime(o._normalizedTime), _looped(o._looped), _animation(o._animation), _sampling(o._sampling),
+    : _def(std::move(o._def)), _normalizedTime(o._normalizedTime), _looped(o._looped), _sampledOnce(o._sampledOnce), _animation(o._animation), _sampling(o._sampling),
       _locals(std::move(o._locals)) {
     o._sampling = nullptr;
 }
@@ -151,6 +153,7 @@ RefAnimationState& RefAnimationState::operator=(RefAnimationState&& o) noexcept 
         _def = std::move(o._def);
         _normalizedTime = o._normalizedTime;
         _looped = o._looped;
+        _sampledOnce = o._sampledOnce;
         _animation = o._animation;
         _sampling = o._sampling;
         _locals = std::move(o._locals);
@@ -171,8 +174,12 @@ bool RefAnimationState::update(float dt, std::string& err) {
     const float normDeltaTime = dt / getDuration();
     const float normTime = _normalizedTime + normDeltaTime;
     _looped = normTime > 1.f;
-    if (hasFinished()) return true;
+    if (hasFinished()) {
+        if (!_sampledOnce) ++g_unsampledHolds;
+        return true;
+    }
     _normalizedTime = std::fmod(normTime, 1.f);
+    _sampledOnce = true;
     if (!orc_sample(_animation, _sampling, _normalizedTime, _locals.data(), (int)(_locals.size() / ORC_SOA_FLOATS), nullptr)) {
         err = "error in the sampling job";
         return false;
@@ -257,6 +264,12 @@ bool RefState::hasFinished() const {
 }
 
 bool RefState::update(float dt, Vec2 blendPosition, std::string& err) {
+    const bool ok = updateImpl(dt, blendPosition, err);
+    if (ok) _everUpdated = true;   // the locals are no longer the zero-initialised buffer
+    return ok;
+}
+
+bool RefState::updateImpl(float dt, Vec2 blendPosition, std::string& err) {
     dt *= _speed;
     for (auto& anim : _animationStates)
         if (!anim.update(dt, err)) return false;
@@ -302,7 +315,8 @@ bool RefState::update(float dt, Vec2 blendPosition, std::string& err) {
 
 // ---- OzzSkeletalAnimatorTransition ----------------------------------------------------------------------------------------
 RefTransition::RefTransition(const orc_skeleton* skel, const TransitionDef& def, RefState current, RefState previous)
-    : _skel(skel), _def(def), _currentState(std::move(current)), _previousState(std::move(previous)), _locals(_previousState.getLocals()) {}
+    : _skel(skel), _def(def), _currentState(std::move(current)), _previousState(std::move(previous)), _locals(_previousState.getLocals()),
+      _startedFromZeroLocals(!_previousState.everUpdated()) {}
 
 bool RefTransition::update(float dt, Vec2 blendPosition, std::string& err) {
     if (hasFinished()) {
@@ -313,7 +327,11 @@ bool RefTransition::update(float dt, Vec2 blendPosition, std::string& err) {
     float currentStateDeltaTime = dt;
     if (_normalizedTime == 0.f) currentStateDeltaTime += _def.offset;
     std::string swallowed;
-    if (!_currentState.update(currentStateDeltaTime, blendPosition, swallowed)) return true;
+    if (!_currentState.update(currentStateDeltaTime, blendPosition, swallowed)) {
+        if (!_everBlended && _startedFromZeroLocals) ++g_unsampledHolds;   // the zero-initialised locals become the pose
+        return true;
+    }
+    _everBlended = true;
     _normalizedTime += dt / _def.tween.duration;
     const float v = tween(_def.tween, _normalizedTime);
     const float* layers[2] = {_previousState.getLocals().data(), _currentState.getLocals().data()};

@@ -54,6 +54,10 @@ struct AnimatorDef {
 };
 
 float ease(int type, float position, float start, float end);
+// Number of times a non-looping clip ran past its end on its very FIRST tick: darmok then never samples it and the state
+// keeps the zero-initialised locals (src/skeleton_ozz.cpp:411-428).  The product shows the clip's ratio-0 pose instead
+// (documented deviation); tests that generate random inputs stop a sequence when this counter moves.
+extern int g_unsampledHolds;
 
 struct NamedAnimation {
     std::string name;
@@ -75,6 +79,7 @@ private:
     AnimationDef _def;
     float _normalizedTime = 0.f;
     bool _looped = false;
+    bool _sampledOnce = false;    // test bookkeeping only (see g_unsampledHolds)
     const orc_animation* _animation;
     orc_sampling_context* _sampling;
     std::vector<float> _locals;   // SoaTransform[num_soa]
@@ -84,9 +89,11 @@ class RefState {
 public:
     static std::optional<RefState> create(const orc_skeleton* skel, const StateDef& def, const std::vector<NamedAnimation>& anims);
     bool update(float dt, Vec2 blendPosition, std::string& err);
+    bool updateImpl(float dt, Vec2 blendPosition, std::string& err);
     const std::string& getName() const { return _def.name; }
     const std::vector<float>& getLocals() const;
     bool hasLooped() const { return _looped; }
+    bool everUpdated() const { return _everUpdated; }   // test bookkeeping only (see g_unsampledHolds)
     bool hasFinished() const;
     float getDuration() const { return _duration * _speed; }
     float getNormalizedTime() const { return _normalizedTime; }
@@ -104,6 +111,7 @@ private:
     Vec2 _blendPos, _oldBlendPos;
     float _normalizedTime = 0.f, _normalizedTweenTime = 0.f, _duration = 0.f;
     bool _looped = false;
+    bool _everUpdated = false;
     float _speed = 1.f;
     std::vector<float> _locals;
 };
@@ -124,6 +132,7 @@ private:
     RefState _currentState, _previousState;
     std::vector<float> _locals;
     float _normalizedTime = 0.f;
+    bool _startedFromZeroLocals = false, _everBlended = false;   // test bookkeeping only (see g_unsampledHolds)
 };
 
 class RefAnimator {

@@ -204,11 +204,14 @@ static void applyAction(const Action& a, auto& shim, orc::RefAnimator& ref, int 
     }
 }
 
-static int runCpu(const std::string& dir) {
-    OracleAssets o = loadOracle(dir);
-    SkeletalAnimatorDefinition def;
-    orc::AnimatorDef rdef;
-    buildDefinitions(def, rdef);
+struct ScenarioStats {
+    int ticks = 0, poses = 0, transitions = 0, blends = 0, passthroughs = 0, errors = 0;
+    size_t events = 0;
+};
+// One animator through a list of actions, twice: the shim's state machine (its pose requests evaluated with the oracle's jobs,
+// as the device evaluates them) and the literal restatement of darmok's animator; everything observable must be identical.
+static ScenarioStats runScenarioCpu(const OracleAssets& o, const SkeletalAnimatorDefinition& def, const orc::AnimatorDef& rdef,
+                                    const std::vector<Action>& actions, const char* label, bool stopAtUnsampledHold = false) {
     std::vector<detail::ClipInfo> clips;
     for (const auto& n : o.named) clips.push_back({n.name, n.anim->duration});
     detail::AnimatorCore core(clips, def);
@@ -224,7 +227,8 @@ static int runCpu(const std::string& dir) {
     std::vector<float> models((size_t)J * 16);
     orc_local_to_model(o.skel, o.skel->rest, models.data());
     int step = 0, ticks = 0, poses = 0, transitions = 0, blends = 0, passthroughs = 0, errors = 0;
-    for (const Action& a : scenario()) {
+    for (const Action& a : actions) {
+        if (stopAtUnsampledHold && g_failures) break;   // fuzzing: the first difference is the interesting one
         ++step;
         if (a.kind != Action::Tick) { applyAction(a, core, ref, step); continue; }
         ++ticks;
@@ -232,11 +236,13 @@ static int runCpu(const std::string& dir) {
         detail::PoseRequest req;
         auto r = core.update(a.a, req);
         std::string refErr;
+        const int holdsBefore = orc::g_unsampledHolds;
         const bool refOk = ref.update(a.a, refErr);
-        CHECK(r.has_value() == refOk, "step %d: shim ok=%d ref ok=%d (%s)", step, (int)r.has_value(), (int)refOk, refErr.c_str());
+        if (stopAtUnsampledHold && orc::g_unsampledHolds != holdsBefore) break;   // the documented deviation: nothing comparable follows
+        CHECK(r.has_value() == refOk, "%s step %d: shim ok=%d ref ok=%d (%s)", label, step, (int)r.has_value(), (int)refOk, refErr.c_str());
         if (!r) {
             ++errors;
-            CHECK(r.error() == refErr, "step %d: error '%s' vs '%s'", step, r.error().c_str(), refErr.c_str());
+            CHECK(r.error() == refErr, "%s step %d: error '%s' vs '%s'", label, step, r.error().c_str(), refErr.c_str());
             continue;
         }
         if (active) {
@@ -250,29 +256,43 @@ static int runCpu(const std::string& dir) {
                     const float* ptrs[2] = {locals.data(), cur.data()};
                     const float w[2] = {req.w0, req.w1};
                     std::vector<float> out((size_t)S * 40);
-                    CHECK(orc_blend(2, ptrs, w, locals.data(), FLT_MIN, S, out.data()), "step %d: transition blend failed", step);
+                    CHECK(orc_blend(2, ptrs, w, locals.data(), FLT_MIN, S, out.data()), "%s step %d: transition blend failed", label, step);
                     locals = out;
                 }
                 orc_local_to_model(o.skel, locals.data(), models.data());
             }
             core.afterUpdate();
         }
-        CHECK(std::memcmp(models.data(), ref.models().data(), models.size() * 4) == 0, "step %d: model matrices differ from the reference animator", step);
-        CHECK(events == ref.events, "step %d: listener events differ (%zu vs %zu)", step, events.size(), ref.events.size());
+        CHECK(std::memcmp(models.data(), ref.models().data(), models.size() * 4) == 0, "%s step %d: model matrices differ from the reference animator", label, step);
+        CHECK(events == ref.events, "%s step %d: listener events differ (%zu vs %zu)", label, step, events.size(), ref.events.size());
         const auto* cs = core.getCurrentState();
         const auto* rs = ref.currentState();
-        CHECK((cs != nullptr) == (rs != nullptr), "step %d: current state presence", step);
+        CHECK((cs != nullptr) == (rs != nullptr), "%s step %d: current state presence", label, step);
         if (cs && rs) {
-            CHECK(cs->getName() == rs->getName(), "step %d: state %s vs %s", step, std::string(cs->getName()).c_str(), rs->getName().c_str());
-            CHECK(cs->getNormalizedTime() == rs->getNormalizedTime(), "step %d: normalized time %g vs %g", step, cs->getNormalizedTime(), rs->getNormalizedTime());
-            CHECK(cs->getDuration() == rs->getDuration(), "step %d: duration %g vs %g", step, cs->getDuration(), rs->getDuration());
+            CHECK(cs->getName() == rs->getName(), "%s step %d: state %s vs %s", label, step, std::string(cs->getName()).c_str(), rs->getName().c_str());
+            CHECK(cs->getNormalizedTime() == rs->getNormalizedTime(), "%s step %d: normalized time %g vs %g", label, step, cs->getNormalizedTime(), rs->getNormalizedTime());
+            CHECK(cs->getDuration() == rs->getDuration(), "%s step %d: duration %g vs %g", label, step, cs->getDuration(), rs->getDuration());
         }
-        CHECK((core.getCurrentTransition() != nullptr) == (ref.currentTransition() != nullptr), "step %d: transition presence", step);
+        CHECK((core.getCurrentTransition() != nullptr) == (ref.currentTransition() != nullptr), "%s step %d: transition presence", label, step);
         if (core.getCurrentTransition() && ref.currentTransition())
-            CHECK(core.getCurrentTransition()->getNormalizedTime() == ref.currentTransition()->getNormalizedTime(), "step %d: transition time", step);
+            CHECK(core.getCurrentTransition()->getNormalizedTime() == ref.currentTransition()->getNormalizedTime(), "%s step %d: transition time", label, step);
     }
     for (const char* n : {"locomotion", "talk", "greet", "strafe", "nope"})
         CHECK(core.getStateDuration(n) == ref.getStateDuration(n), "getStateDuration(%s): %g vs %g", n, core.getStateDuration(n), ref.getStateDuration(n));
+    ScenarioStats st;
+    st.ticks = ticks; st.poses = poses; st.transitions = transitions; st.blends = blends; st.passthroughs = passthroughs; st.errors = errors;
+    st.events = events.size();
+    return st;
+}
+
+static int runCpu(const std::string& dir) {
+    OracleAssets o = loadOracle(dir);
+    SkeletalAnimatorDefinition def;
+    orc::AnimatorDef rdef;
+    buildDefinitions(def, rdef);
+    const ScenarioStats st = runScenarioCpu(o, def, rdef, scenario(), "scenario");
+    const int ticks = st.ticks, poses = st.poses, transitions = st.transitions, blends = st.blends, passthroughs = st.passthroughs, errors = st.errors;
+    struct { size_t n; size_t size() const { return n; } } events{st.events};
     // MeshData::exportData's influence packing (src/mesh_core.cpp:336-356): known answers derived from the reference's loop
     {
         auto pack = [](std::vector<MeshDataWeight> w) {
@@ -330,6 +350,68 @@ static int runCpu(const std::string& dir) {
     std::printf("cpu: %d ticks, %d poses (%d blends, %d passthroughs, %d in transition), %d job errors, %zu events, %d failures\n", ticks, poses, blends,
                 passthroughs, transitions, errors, events.size(), g_failures);
     CHECK(transitions > 20 && blends > 50 && passthroughs > 20 && errors == 2 && events.size() > 10, "scenario lost coverage");
+    return g_failures ? 1 : 0;
+}
+
+// Random action sequences (seeded): the same equivalence as the scripted scenario, over situations nobody thought of.
+static int runFuzz(const std::string& dir, int sequences, uint64_t seed) {
+    OracleAssets o = loadOracle(dir);
+    SkeletalAnimatorDefinition def;
+    orc::AnimatorDef rdef;
+    buildDefinitions(def, rdef);
+    uint64_t state = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    auto next = [&]() {   // xorshift64*
+        state ^= state >> 12; state ^= state << 25; state ^= state >> 27;
+        return state * 0x2545F4914F6CDD1Dull;
+    };
+    auto pick = [&](int n) { return static_cast<int>((next() >> 33) % static_cast<uint64_t>(n)); };
+    auto unit = [&]() { return static_cast<float>((next() >> 40) * (1.0 / 16777216.0)); };
+    const char* states[] = {"locomotion", "talk", "greet", "strafe", "locomotion", "talk", "run", "ghost", "broken"};
+    const float dts[] = {1 / 60.f, 1 / 60.f, 1 / 30.f, 1 / 30.f, 1 / 15.f, 0.1f, 0.4f, 0.f, 1.7f, 1e-4f};
+    const float speeds[] = {1.f, 1.f, 2.f, 0.5f, 0.f, 3.f};
+    ScenarioStats total;
+    int cut = 0;   // sequences that ended early at the documented deviation (non-looping clip past its end on its first tick)
+    for (int q = 0; q < sequences; ++q) {
+        std::vector<Action> actions;
+        const int len = 60 + pick(120);
+        for (int i = 0; i < len; ++i) {
+            const int kind = pick(100);
+            if (kind < 70) {
+                actions.push_back({Action::Tick, "", dts[pick(10)], 0});
+            } else if (kind < 82) {
+                actions.push_back({Action::Play, states[pick(9)], speeds[pick(6)], 0});
+            } else if (kind < 92) {
+                // blend positions: random, on a clip's own position (early exit, C6), or the origin
+                const int how = pick(4);
+                float x = unit() * 2.4f - 1.2f, y = unit() * 2.4f - 1.2f;
+                if (how == 0) { const int c = pick(9); x = kBlendPos[c][0]; y = kBlendPos[c][1]; }
+                if (how == 1) { x = 0.f; y = 0.f; }
+                actions.push_back({Action::Blend, "", x, y});
+            } else if (kind < 96) {
+                actions.push_back({Action::Speed, "", speeds[pick(6)], 0});
+            } else if (kind < 98) {
+                actions.push_back({Action::Stop, "", 0, 0});
+            } else {
+                actions.push_back({Action::Pause, "", 0, 0});
+            }
+        }
+        char label[32];
+        std::snprintf(label, sizeof label, "fuzz %d", q);
+        const int holds = orc::g_unsampledHolds;
+        const ScenarioStats st = runScenarioCpu(o, def, rdef, actions, label, true);
+        cut += orc::g_unsampledHolds != holds;
+        total.ticks += st.ticks; total.poses += st.poses; total.transitions += st.transitions; total.blends += st.blends;
+        total.passthroughs += st.passthroughs; total.errors += st.errors; total.events += st.events;
+        if (g_failures) {
+            std::printf("fuzz: first failing sequence %d (seed %llu); its actions:\n", q, (unsigned long long)seed);
+            const char* kinds[] = {"tick", "play", "stop", "blend", "speed", "pause"};
+            for (size_t i = 0; i < actions.size(); ++i)
+                std::printf("  %zu %s %s %g %g\n", i + 1, kinds[actions[i].kind], actions[i].name.c_str(), actions[i].a, actions[i].b);
+            break;
+        }
+    }
+    std::printf("fuzz: %d sequences (%d cut at the known first-tick deviation), %d ticks, %d poses (%d blends, %d passthroughs, %d in transition), %d job errors, %zu events, %d failures\n", sequences,
+                cut, total.ticks, total.poses, total.blends, total.passthroughs, total.transitions, total.errors, total.events, g_failures);
     return g_failures ? 1 : 0;
 }
 
@@ -930,8 +1012,9 @@ static int runHostBench(const std::string& dir, int n) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { std::printf("usage: animator_test <assets_dir> cpu|gpu|hostbench [n]\n"); return 2; }
+    if (argc < 3) { std::printf("usage: animator_test <assets_dir> cpu|gpu|hostbench [n]|fuzz [sequences] [seed]\n"); return 2; }
     if (std::string(argv[2]) == "hostbench") return runHostBench(argv[1], argc > 3 ? std::atoi(argv[3]) : 100000);
+    if (std::string(argv[2]) == "fuzz") return runFuzz(argv[1], argc > 3 ? std::atoi(argv[3]) : 50, argc > 4 ? std::strtoull(argv[4], nullptr, 10) : 1);
     std::setvbuf(stdout, nullptr, _IOLBF, 0);   // keep the progress lines if a section dies
     return std::string(argv[2]) == "gpu" ? runGpu(argv[1]) : runCpu(argv[1]);
 }

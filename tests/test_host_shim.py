@@ -56,6 +56,15 @@ def test_state_machine_matches_reference_animator_on_cpu(binary, assets_dir):
     assert "3136 easing values equal to the reference's easing.hpp" in out
 
 
+def test_state_machine_fuzz_matches_reference_animator(binary, assets_dir):
+    # seeded random action sequences (play / stop / blend position / speed / pause / ticks of assorted lengths, valid and invalid
+    # states): the shim's state machine and the literal restatement of darmok's animator must agree on every observable
+    for seed in (1, 2):
+        r = subprocess.run([binary, assets_dir, "fuzz", "250", str(seed)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and " 0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-500:]
+        assert "250 sequences" in r.stdout
+
+
 def test_host_tick_benchmark_mode_runs(binary, assets_dir):
     # the CPU cost of the per-character animator tick that the device-side state machines remove
     r = subprocess.run([binary, assets_dir, "hostbench", "2000"], capture_output=True, text=True, timeout=120)
