@@ -367,8 +367,8 @@ static int runFuzz(const std::string& dir, int sequences, uint64_t seed) {
     auto pick = [&](int n) { return static_cast<int>((next() >> 33) % static_cast<uint64_t>(n)); };
     auto unit = [&]() { return static_cast<float>((next() >> 40) * (1.0 / 16777216.0)); };
     const char* states[] = {"locomotion", "talk", "greet", "strafe", "locomotion", "talk", "run", "ghost", "broken"};
-    const float dts[] = {1 / 60.f, 1 / 60.f, 1 / 30.f, 1 / 30.f, 1 / 15.f, 0.1f, 0.4f, 0.f, 1.7f, 1e-4f};
-    const float speeds[] = {1.f, 1.f, 2.f, 0.5f, 0.f, 3.f};
+    const float dts[] = {1 / 60.f, 1 / 60.f, 1 / 30.f, 1 / 30.f, 1 / 15.f, 0.1f, 0.4f, 0.f, 1.7f, 1e-4f, -1 / 60.f, -0.3f};   // C1: negative steps too
+    const float speeds[] = {1.f, 1.f, 2.f, 0.5f, 0.f, 3.f, -1.f};
     ScenarioStats total;
     int cut = 0;   // sequences that ended early at the documented deviation (non-looping clip past its end on its first tick)
     for (int q = 0; q < sequences; ++q) {
@@ -377,9 +377,9 @@ static int runFuzz(const std::string& dir, int sequences, uint64_t seed) {
         for (int i = 0; i < len; ++i) {
             const int kind = pick(100);
             if (kind < 70) {
-                actions.push_back({Action::Tick, "", dts[pick(10)], 0});
+                actions.push_back({Action::Tick, "", dts[pick(12)], 0});
             } else if (kind < 82) {
-                actions.push_back({Action::Play, states[pick(9)], speeds[pick(6)], 0});
+                actions.push_back({Action::Play, states[pick(9)], speeds[pick(7)], 0});
             } else if (kind < 92) {
                 // blend positions: random, on a clip's own position (early exit, C6), or the origin
                 const int how = pick(4);
@@ -388,7 +388,7 @@ static int runFuzz(const std::string& dir, int sequences, uint64_t seed) {
                 if (how == 1) { x = 0.f; y = 0.f; }
                 actions.push_back({Action::Blend, "", x, y});
             } else if (kind < 96) {
-                actions.push_back({Action::Speed, "", speeds[pick(6)], 0});
+                actions.push_back({Action::Speed, "", speeds[pick(7)], 0});
             } else if (kind < 98) {
                 actions.push_back({Action::Stop, "", 0, 0});
             } else {
