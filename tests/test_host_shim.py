@@ -65,6 +65,16 @@ def test_state_machine_fuzz_matches_reference_animator(binary, assets_dir):
         assert "250 sequences" in r.stdout
 
 
+def test_archive_reader_survives_damaged_archives_under_asan(assets_dir):
+    # the product's ozz reader (darmok_b200/csrc/ozz_io.cpp) built with AddressSanitizer + UBSan: every truncation and 20k seeded
+    # corruptions of a valid skeleton / animation archive are answered with true or false, never with a crash
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "ozz_io_fuzz"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "ozz_io_fuzz"), os.path.join(assets_dir, "skeleton.ozz"),
+                        os.path.join(assets_dir, "Idle01.ozz"), "20000", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and " 0 failures" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_host_tick_benchmark_mode_runs(binary, assets_dir):
     # the CPU cost of the per-character animator tick that the device-side state machines remove
     r = subprocess.run([binary, assets_dir, "hostbench", "2000"], capture_output=True, text=True, timeout=120)
