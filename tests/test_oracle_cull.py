@@ -176,3 +176,21 @@ def test_math_transform_conventions_match_reference_plane_kat():
     assert np.allclose(plane[0], [-1, 0, 0], atol=1e-6) and np.isclose(plane[1], 0, atol=1e-6)
     plane = apply((np.array([0, 0, -1], np.float32), np.float32(1)), roty)
     assert np.allclose(plane[0], [1, 0, 0], atol=1e-6) and np.isclose(plane[1], 1, atol=1e-6)
+
+
+def test_product_frustum_corners_equal_the_oracle_on_the_host():
+    # dmk_frustum_corners (Frustum::Frustum(mtx), src/shape.cpp:1141-1163) is host code of the product and needs no device:
+    # bit-identical to the oracle's restatement for the sample camera and for random view-projection matrices
+    import ctypes
+    from darmok_b200 import build, capi, synth
+    build.build()
+    rng = np.random.default_rng(5)
+    mats = [synth.sample_camera_view_proj()] + [rng.normal(size=(4, 4)).astype(np.float32) for _ in range(200)]
+    for vp in mats:
+        for nd in (0.0, -1.0):
+            v = np.ascontiguousarray(vp, np.float32)
+            out = np.zeros((8, 3), np.float32)
+            st = capi.lib().dmk_frustum_corners(v.ctypes.data_as(ctypes.c_void_p), nd, out.ctypes.data_as(ctypes.c_void_p))
+            assert st == 0
+            ref = O.frustum_corners(v, nd)
+            assert np.array_equal(out, ref, equal_nan=True)
