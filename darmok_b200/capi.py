@@ -17,7 +17,7 @@ OK, ERR_INVALID, ERR_FORMAT, ERR_CUDA, ERR_UNSUPPORTED, ERR_JOB = range(6)
 STEP_ADVANCE, STEP_POSE, STEP_CULL, STEP_SKIN, STEP_SKIN_VISIBLE_ONLY, STEP_READBACK_VISIBILITY = 1, 2, 4, 8, 16, 32
 STEP_ALL = 15
 STEP_ANIMATOR = 64
-ANIM_NONE, ANIM_STOP = -2, -1
+ANIM_CLEAR, ANIM_NONE, ANIM_STOP = -3, -2, -1
 OUT_MODELS, OUT_LOCALS, OUT_KEY_INDICES = 1, 2, 4
 OPT_FORCE_KEY_SEARCH = 1
 OPT_SKIN_RESERVED_SMS = 2

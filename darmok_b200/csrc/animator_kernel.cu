@@ -241,6 +241,8 @@ __device__ __forceinline__ void set_group(PoseProgram& prog, int k, const GroupO
 constexpr int kAnimBlock = 256;
 constexpr int kAnimKeys = 64;
 
+__device__ __forceinline__ void tick_character(const AnimatorParams& p, int64_t c);
+
 __global__ void __launch_bounds__(kAnimBlock) animator_kernel(const AnimatorParams p) {
     __shared__ int key_count[kAnimKeys];
     __shared__ uint16_t order[kAnimBlock];
@@ -269,6 +271,12 @@ __global__ void __launch_bounds__(kAnimBlock) animator_kernel(const AnimatorPara
     }
     const int64_t c = block_base + order[threadIdx.x];
     if (c >= p.n) return;
+    tick_character(p, c);
+}
+
+// One SkeletalAnimatorImpl tick: pending command, update, afterUpdate.  (A function of its own so that
+// tests/cpp/animator_kernel_host.cpp can compile this file for the CPU and run it next to the host state machine.)
+__device__ __forceinline__ void tick_character(const AnimatorParams& p, int64_t c) {
     const Slot st = slot_of(p, kSlotState, c), prev = slot_of(p, kSlotPrev, c), cur = slot_of(p, kSlotCur, c);
     Character a;
     a.state_def = st.geti(kWDef);
@@ -284,6 +292,7 @@ __global__ void __launch_bounds__(kAnimBlock) animator_kernel(const AnimatorPara
     if (cmd != -2) {
         if (cmd >= 0) play(p, c, a, cmd, p.cmd_speed[c], ev.cmd_started, ev.cmd_transition_started);
         else if (cmd == -1) { a.state_def = -1; st.seti(kWDef, -1); }   // stop(): clears _state only; a running transition keeps going (C10)
+        else if (cmd == -3) { a.state_def = -1; st.seti(kWDef, -1); a.transition_def = -1; }   // play() of a state that cannot be created (:793-845)
         p.cmd_state[c] = -2;
     }
 
@@ -362,9 +371,13 @@ __global__ void __launch_bounds__(kAnimBlock) animator_kernel(const AnimatorPara
     p.status[c] = status;
 }
 
+__device__ __forceinline__ void query_character(const AnimatorParams& p, int64_t c, AnimStateInfo* out);
 __global__ void animator_query_kernel(const AnimatorParams p, AnimStateInfo* out) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.n) return;
+    query_character(p, c, out);
+}
+__device__ __forceinline__ void query_character(const AnimatorParams& p, int64_t c, AnimStateInfo* out) {
     const int t = p.transition_def[c];
     const Slot s = slot_of(p, t >= 0 ? kSlotCur : kSlotState, c);   // getCurrentState (src/skeleton_ozz.cpp:867-878)
     const Slot pv = slot_of(p, kSlotPrev, c);
@@ -380,9 +393,13 @@ __global__ void animator_query_kernel(const AnimatorParams p, AnimStateInfo* out
     out[c] = o;
 }
 
+__device__ __forceinline__ void init_character(const AnimatorParams& p, int64_t c, float* cmd_speed, float* in_blend, float* in_speed);
 __global__ void animator_init_kernel(const AnimatorParams p, float* cmd_speed, float* in_blend, float* in_speed) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.n) return;
+    init_character(p, c, cmd_speed, in_blend, in_speed);
+}
+__device__ __forceinline__ void init_character(const AnimatorParams& p, int64_t c, float* cmd_speed, float* in_blend, float* in_speed) {
     for (int s = 0; s < kNumSlots; ++s) slot_of(p, s, c).seti(kWDef, -1);
     p.transition_def[c] = -1;
     p.transition_time[c] = 0.f;
@@ -394,6 +411,7 @@ __global__ void animator_init_kernel(const AnimatorParams p, float* cmd_speed, f
 
 }  // namespace
 
+#ifndef DMK_ANIMATOR_HOST_TEST   // the CPU build of the test harness has no launches
 cudaError_t launch_animator_init(const AnimatorParams& p, float* cmd_speed, float* in_blend, float* in_speed, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     animator_init_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(p, cmd_speed, in_blend, in_speed);
@@ -411,5 +429,6 @@ cudaError_t launch_animator(const AnimatorParams& p, cudaStream_t stream) {
     animator_kernel<<<(unsigned)((p.n + kAnimBlock - 1) / kAnimBlock), kAnimBlock, 0, stream>>>(p);
     return cudaGetLastError();
 }
+#endif
 
 }  // namespace dmk

@@ -439,8 +439,17 @@ bool SkeletalAnimator::play(std::string_view name, float speedFactor) noexcept {
     if (!onDevice()) return _core->play(name, speedFactor);
     auto& im = *_batch->_impl;
     const int state = im.stateIndex(name);
-    if (state < 0) return false;   // unknown state (C16), or one without a known animation
     const size_t i = static_cast<size_t>(_batchIndex);
+    if (state < 0) {
+        // an unknown name does nothing (C16); a state that IS defined but has no known animation cannot be created, and the
+        // reference has dropped _state and _transition by the time it finds out (src/skeleton_ozz.cpp:793-845)
+        const auto& states = im.def.states;
+        if (std::any_of(states.begin(), states.end(), [&](const auto& s) { return s.name == name; })) {
+            im.cmd[i] = DMK_ANIM_CLEAR;
+            im.cmdDirty = true;
+        }
+        return false;
+    }
     int current = im.cmd[i] >= 0 ? im.cmd[i] : -1;   // a command queued this frame counts as the state being played
     if (current < 0)
         if (const dmk_anim_state* st = im.stateOf(_batchIndex)) current = (im.cmd[i] == DMK_ANIM_STOP && st->transition < 0) ? -1 : st->state;

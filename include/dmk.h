@@ -244,8 +244,11 @@ DMK_API dmk_status dmk_crowd_set_animator(dmk_crowd_t crowd, const dmk_anim_stat
                                           const dmk_anim_clip_def* clips, int num_clips,
                                           const dmk_anim_transition_def* transitions, int num_transitions);
 /* Commands executed at the start of the next DMK_STEP_ANIMATOR, per character: state >= 0 = play(state, speed),
- * DMK_ANIM_STOP = stop(), DMK_ANIM_NONE = nothing.  speed NULL = 1 (play()'s default stateSpeed). */
-enum { DMK_ANIM_NONE = -2, DMK_ANIM_STOP = -1 };
+ * DMK_ANIM_STOP = stop() (clears _state only: a running transition keeps going), DMK_ANIM_NONE = nothing,
+ * DMK_ANIM_CLEAR = what play() of a state that is defined but cannot be created (none of its animations is known) leaves
+ * behind: _state and _transition are both gone before State::create fails, no listener is called and play returns false
+ * (src/skeleton_ozz.cpp:793-845).  speed NULL = 1 (play()'s default stateSpeed). */
+enum { DMK_ANIM_CLEAR = -3, DMK_ANIM_NONE = -2, DMK_ANIM_STOP = -1 };
 DMK_API dmk_status dmk_crowd_animator_commands(dmk_crowd_t crowd, const int32_t* state, const float* speed);
 /* setBlendPosition / setPlaybackSpeed for every character: blend_xy [N][2] and/or speed [N] (NULL = unchanged) */
 DMK_API dmk_status dmk_crowd_animator_set_inputs(dmk_crowd_t crowd, const float* blend_xy, const float* speed);

@@ -10,6 +10,7 @@
 #include "darmok_b200/animator_core.hpp"
 #include "darmok_b200/skeleton.hpp"
 
+#include "animator_kernel_host.hpp"
 #include "animator_ref.hpp"
 #include "dmk_oracle.h"
 #include "dmk.h"
@@ -425,6 +426,248 @@ static bool close(float a, float e) {
 // through the C ABI.  Every character is driven by its own script; each tick is compared with the oracle's RefAnimator
 // (events, error status, current state / transition and their clocks, model matrices) and with the host shim's
 // AnimatorCore (the resolved layers and pose program, bit for bit where no libm function is involved).
+struct FlatDefinition {
+    std::vector<dmk_anim_state_def> states;
+    std::vector<dmk_anim_clip_def> clips;
+    std::vector<dmk_anim_transition_def> transitions;
+    std::vector<std::string> stateNames;
+    int stateIndex(const std::string& name) const {
+        for (size_t i = 0; i < stateNames.size(); ++i) if (stateNames[i] == name) return (int)i;
+        return -1;
+    }
+    // the command play(name) turns into: the state's index; nothing for an unknown name (C16); DMK_ANIM_CLEAR for a state that is
+    // defined but cannot be created -- the reference has dropped _state and _transition by then (src/skeleton_ozz.cpp:793-845)
+    int command(const SkeletalAnimatorDefinition& def, const std::string& name) const {
+        if (const int s = stateIndex(name); s >= 0) return s;
+        for (const auto& s : def.states) if (s.name == name) return DMK_ANIM_CLEAR;
+        return DMK_ANIM_NONE;
+    }
+};
+// names -> indices; a state without any known animation cannot be created (src/skeleton_ozz.cpp:469-485) and is left out, so
+// play() of it is "no command"
+static FlatDefinition flattenDefinition(const SkeletalAnimatorDefinition& def, const OracleAssets& o) {
+    FlatDefinition f;
+    auto clipIndex = [&](const std::string& name) {
+        for (size_t i = 0; i < o.named.size(); ++i) if (o.named[i].name == name) return (int)i;
+        return -1;
+    };
+    for (const auto& s : def.states) {
+        bool any = false;
+        for (const auto& a : s.animations) any = any || clipIndex(a.name) >= 0;
+        if (any) f.stateNames.push_back(s.name);
+    }
+    for (const auto& s : def.states) {
+        if (f.stateIndex(s.name) < 0) continue;
+        dmk_anim_state_def d{};
+        d.first_clip = (int)f.clips.size();
+        for (const auto& a : s.animations) {
+            const int ci = clipIndex(a.name);
+            if (ci < 0) continue;
+            f.clips.push_back({ci, a.blend_position.x, a.blend_position.y, a.speed, a.loop ? 1 : 0});
+        }
+        d.num_clips = (int)f.clips.size() - d.first_clip;
+        d.blend_type = (int)s.blend;
+        d.threshold = s.threshold;
+        d.tween_easing = (int)s.tween.easing;
+        d.tween_duration = s.tween.duration;
+        d.next_state = s.next_state.empty() ? -1 : f.stateIndex(s.next_state);
+        d.speed = s.speed;
+        f.states.push_back(d);
+    }
+    for (const auto& t : def.transitions)
+        f.transitions.push_back({t.src_state.empty() ? -1 : f.stateIndex(t.src_state), t.dst_state.empty() ? -1 : f.stateIndex(t.dst_state), (int)t.tween.easing,
+                                 t.tween.duration, t.offset});
+    return f;
+}
+
+struct AnimatorCounters { long exactWeights = 0, closeWeights = 0, transitions = 0, errors = 0, blends = 0, keptByDevice = 0; };
+// One character, one tick: what the device (or its CPU build) reports against the reference animator (events, error status,
+// current state / transition and clocks) and against the host shim's resolved pose request (layers and program).
+static void compareAnimatorTick(int frame, int64_t i, int64_t n, float dt, orc::RefAnimator& ref, detail::AnimatorCore& core, std::vector<std::string>& log,
+                                const dmk_anim_events& e, int status, const dmk_anim_state& di, const dmk_pose_program& g, const std::vector<int32_t>& lclip,
+                                const std::vector<float>& lratio, const std::vector<float>& lweight, const std::vector<std::string>& stateNames,
+                                const std::vector<dmk_anim_state_def>& dstates, AnimatorCounters& counters, bool* deviated = nullptr) {
+    std::string err;
+    const int holds = orc::g_unsampledHolds;
+    const bool refOk = ref.update(dt, err);
+    if (deviated && orc::g_unsampledHolds != holds) {   // the documented first-tick deviation: nothing comparable follows for this character
+        *deviated = true;
+        return;
+    }
+    const bool active = core.hasActiveStateOrTransition();
+    detail::PoseRequest req;
+    const auto r = core.update(dt, req);
+    if (r && active) core.afterUpdate();
+    CHECK(refOk == (status == 0), "frame %d animator %ld: status %d, reference ok=%d (%s)", frame, (long)i, status, (int)refOk, err.c_str());
+    counters.errors += !refOk;
+    // listener events in the reference's order
+                            if (e.cmd_started >= 0) log.push_back("started:" + stateNames[(size_t)e.cmd_started]);
+    if (e.cmd_transition_started) log.push_back("transition_started");
+    if (e.transition_finished) { log.push_back("transition_finished"); log.push_back("finished:" + stateNames[(size_t)e.prev_finished]); }
+    if (e.looped >= 0) log.push_back("looped:" + stateNames[(size_t)e.looped]);
+    if (e.finished >= 0) log.push_back("finished:" + stateNames[(size_t)e.finished]);
+    if (e.auto_started >= 0) log.push_back("started:" + stateNames[(size_t)e.auto_started]);
+    if (e.auto_transition_started) log.push_back("transition_started");
+    CHECK(log == ref.events, "frame %d animator %ld: listener events differ (%zu vs %zu)", frame, (long)i, log.size(), ref.events.size());
+    // current state / transition and their clocks (exact: only +, *, /, fmod)
+    const auto* rs = ref.currentState();
+                CHECK((rs != nullptr) == (di.state >= 0), "frame %d animator %ld: current state presence", frame, (long)i);
+    if (rs && di.state >= 0) {
+        CHECK(stateNames[(size_t)di.state] == rs->getName(), "frame %d animator %ld: state %s vs %s", frame, (long)i, stateNames[(size_t)di.state].c_str(), rs->getName().c_str());
+        CHECK(di.state_time == rs->getNormalizedTime(), "frame %d animator %ld: state clock %.9g vs %.9g", frame, (long)i, di.state_time, rs->getNormalizedTime());
+        const float duration = core.getStateDuration(std::string(rs->getName())) / dstates[(size_t)di.state].speed * di.state_speed;
+        CHECK(std::fabs(duration - rs->getDuration()) <= 1e-6f * std::fabs(rs->getDuration()), "frame %d animator %ld: state duration %g vs %g", frame, (long)i, duration, rs->getDuration());
+    }
+    auto* rt = const_cast<orc::RefTransition*>(ref.currentTransition());
+    CHECK((rt != nullptr) == (di.transition >= 0), "frame %d animator %ld: transition presence", frame, (long)i);
+    if (rt && di.transition >= 0) {
+        CHECK(di.transition_time == rt->getNormalizedTime(), "frame %d animator %ld: transition clock", frame, (long)i);
+        CHECK(di.previous_state >= 0 && stateNames[(size_t)di.previous_state] == rt->previous().getName() && di.previous_time == rt->previous().getNormalizedTime(),
+              "frame %d animator %ld: previous state of the transition", frame, (long)i);
+    }
+    // resolved program against the host shim's PoseRequest
+    // Known difference of the device-side animators: a transition whose current state fails before the
+    // transition has ever blended shows, in darmok and in the host state machine, the previous state's locals as they were when
+    // the transition was created; the kernel keeps the matrices (SKIP).  Only reachable through a state whose BlendingJob is
+    // invalid (threshold <= 0).
+    const bool keptByDevice = r && active && req.top == detail::PoseRequest::Group0 && g.top == DMK_TOP_SKIP && di.transition >= 0 && di.transition_time == 0.f;
+    counters.keptByDevice += keptByDevice;
+    if (keptByDevice) {
+    } else if (!r || !active || req.top == detail::PoseRequest::Skip) {
+        CHECK(g.top == DMK_TOP_SKIP, "frame %d animator %ld: program top %d, expected SKIP", frame, (long)i, g.top);
+    } else {
+        const bool tr = req.top == detail::PoseRequest::Transition;
+        counters.transitions += tr;
+        CHECK(g.top == (tr ? DMK_TOP_TRANSITION : DMK_TOP_GROUP0), "frame %d animator %ld: program top %d (state %d, transition %d, previous %d)", frame, (long)i, g.top,
+              di.state, di.transition, di.previous_state);
+        int row = 0;
+        for (int k = 0; k < (tr ? 2 : 1); ++k) {
+            const detail::GroupRequest& gr = k ? req.group1 : req.group0;
+            const int cnt = k ? g.num_layers1 : g.num_layers0, rest = k ? g.rest1 : g.rest0, mode = k ? g.mode1 : g.mode0;
+            const float th = k ? g.threshold1 : g.threshold0;
+            CHECK(cnt == (int)gr.layers.size() && rest == gr.rest && mode == (gr.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND) && th == gr.threshold,
+                  "frame %d animator %ld group %d: count %d/%zu rest %d/%d mode %d", frame, (long)i, k, cnt, gr.layers.size(), rest, gr.rest, mode);
+            counters.blends += !gr.passthrough;
+            for (size_t l = 0; l < gr.layers.size() && (int)l < cnt; ++l, ++row) {
+                const size_t at = (size_t)row * n + i;
+                CHECK(lclip[at] == gr.layers[l].clip, "frame %d animator %ld row %d: clip %d vs %d", frame, (long)i, row, lclip[at], gr.layers[l].clip);
+                CHECK(lratio[at] == gr.layers[l].ratio, "frame %d animator %ld row %d: ratio %.9g vs %.9g", frame, (long)i, row, lratio[at], gr.layers[l].ratio);
+                if (gr.passthrough) continue;
+                if (lweight[at] == gr.layers[l].weight) ++counters.exactWeights;
+                else {
+                    ++counters.closeWeights;
+                    CHECK(std::fabs(lweight[at] - gr.layers[l].weight) <= 2e-6f * std::fmax(1.f, std::fabs(gr.layers[l].weight)),
+                          "frame %d animator %ld row %d: weight %.9g vs %.9g", frame, (long)i, row, lweight[at], gr.layers[l].weight);
+                }
+            }
+        }
+        if (tr) CHECK(std::fabs(g.weight0 - req.w0) <= 1e-6f && std::fabs(g.weight1 - req.w1) <= 1e-6f, "frame %d animator %ld: transition weights %.9g/%.9g vs %.9g/%.9g",
+                      frame, (long)i, g.weight0, g.weight1, req.w0, req.w1);
+    }
+}
+
+// ---- the same comparison without a GPU: the animator kernel's per-character code compiled for the CPU (animator_kernel_host.cpp),
+// thousands of characters, each with its own seeded random script
+static int runDeviceSim(const std::string& dir, int64_t n, int frames, uint64_t seed) {
+    OracleAssets o = loadOracle(dir);
+    SkeletalAnimatorDefinition def;
+    orc::AnimatorDef rdef;
+    buildDefinitions(def, rdef);
+    const FlatDefinition flat = flattenDefinition(def, o);
+    std::vector<float> durations;
+    std::vector<detail::ClipInfo> clipInfo;
+    for (const auto& a : o.named) { durations.push_back(a.anim->duration); clipInfo.push_back({a.name, a.anim->duration}); }
+    devsim::Sim sim(flat.states.data(), (int)flat.states.size(), flat.clips.data(), (int)flat.clips.size(), flat.transitions.data(), (int)flat.transitions.size(),
+                    durations, n);
+    const int L = sim.layers();
+    std::vector<std::unique_ptr<orc::RefAnimator>> refs;
+    std::vector<std::unique_ptr<detail::AnimatorCore>> cores;
+    for (int64_t i = 0; i < n; ++i) {
+        refs.push_back(std::make_unique<orc::RefAnimator>(o.skel, o.named, rdef));
+        cores.push_back(std::make_unique<detail::AnimatorCore>(clipInfo, def));
+    }
+    std::vector<std::vector<std::string>> devEvents((size_t)n);
+    std::vector<char> deviated((size_t)n, 0);
+    uint64_t state = seed * 0x9E3779B97F4A7C15ull + 0x777ull;
+    auto next = [&]() { state ^= state >> 12; state ^= state << 25; state ^= state >> 27; return state * 0x2545F4914F6CDD1Dull; };
+    auto pick = [&](int m) { return static_cast<int>((next() >> 33) % static_cast<uint64_t>(m)); };
+    auto unit = [&]() { return static_cast<float>((next() >> 40) * (1.0 / 16777216.0)); };
+    const char* states[] = {"locomotion", "talk", "greet", "strafe", "locomotion", "talk", "run", "ghost", "broken"};
+    const float dts[] = {1 / 60.f, 1 / 60.f, 1 / 30.f, 1 / 30.f, 1 / 15.f, 0.1f, 0.4f, 0.f, 1.7f, 1e-4f, -1 / 60.f, -0.3f};
+    const float speeds[] = {1.f, 1.f, 2.f, 0.5f, 0.f, 3.f, -1.f};
+    std::vector<int32_t> cmd((size_t)n), status((size_t)n);
+    std::vector<dmk_anim_state> info((size_t)n);
+    std::vector<float> cmdSpeed((size_t)n), blend((size_t)n * 2, 0.f), speed((size_t)n, 1.f);
+    std::vector<dmk_anim_events> ev((size_t)n);
+    std::vector<int32_t> lclip((size_t)L * n);
+    std::vector<float> lratio((size_t)L * n), lweight((size_t)L * n);
+    std::vector<dmk_pose_program> prog((size_t)n);
+    AnimatorCounters cnt;
+    long ticksCompared = 0;
+    for (int frame = 0; frame < frames && g_failures == 0; ++frame) {
+        const float dt = dts[pick(12)];
+        for (int64_t i = 0; i < n; ++i) {
+            cmd[i] = DMK_ANIM_NONE;
+            cmdSpeed[i] = 1.f;
+            if (deviated[(size_t)i]) continue;
+            const int kind = pick(100);
+            if (kind < 5) {   // one command per animator and frame
+                const std::string name = states[pick(9)];
+                const float sp = speeds[pick(7)];
+                cmd[i] = flat.command(def, name);
+                cmdSpeed[i] = sp;
+                refs[i]->play(name, sp);
+                cores[i]->play(name, sp);
+            } else if (kind < 6) {
+                cmd[i] = DMK_ANIM_STOP;
+                refs[i]->stop();
+                cores[i]->stop();
+            }
+            const int what = pick(100);
+            if (what < 8) {
+                const int how = pick(4);
+                float x = unit() * 2.4f - 1.2f, y = unit() * 2.4f - 1.2f;
+                if (how == 0) { const int c = pick(9); x = kBlendPos[c][0]; y = kBlendPos[c][1]; }
+                if (how == 1) { x = 0.f; y = 0.f; }
+                blend[2 * i] = x;
+                blend[2 * i + 1] = y;
+                refs[i]->setBlendPosition({x, y});
+                cores[i]->setBlendPosition(glm::vec2(x, y));
+            } else if (what < 10) {
+                speed[i] = speeds[pick(7)];
+                refs[i]->setPlaybackSpeed(speed[i]);
+                cores[i]->setPlaybackSpeed(speed[i]);
+            }
+        }
+        if (const char* tc = std::getenv("DMK_TRACE_CHAR")) {   // debugging aid: the script of one character
+            const int64_t t = std::atoll(tc);
+            if (t >= 0 && t < n) std::printf("  trace %ld frame %d: dt %g cmd %d speed %g blend (%g, %g) playback %g\n", (long)t, frame, dt, cmd[t], cmdSpeed[t], blend[2 * t], blend[2 * t + 1], speed[t]);
+        }
+        sim.commands(cmd.data(), cmdSpeed.data());
+        sim.setInputs(blend.data(), speed.data());
+        sim.step(dt);
+        sim.getEvents(ev.data(), status.data());
+        sim.getState(info.data());
+        sim.getPrograms(L, lclip.data(), lratio.data(), lweight.data(), prog.data());
+        for (int64_t i = 0; i < n; ++i) {
+            if (deviated[(size_t)i]) continue;
+            bool dev = false;
+            compareAnimatorTick(frame, i, n, dt, *refs[i], *cores[i], devEvents[(size_t)i], ev[(size_t)i], status[i], info[(size_t)i], prog[(size_t)i], lclip, lratio,
+                                lweight, flat.stateNames, flat.states, cnt, &dev);
+            deviated[(size_t)i] = dev;
+            ticksCompared += !dev;
+        }
+    }
+    long cut = 0, eventsSeen = 0;
+    for (char d : deviated) cut += d;
+    for (const auto& l : devEvents) eventsSeen += (long)l.size();
+    std::printf("devsim: kernel code on the CPU, %ld characters x %d frames (%ld cut at the known first-tick deviation): %ld ticks compared, %ld transitions, "
+                "%ld blends, %ld job errors, %ld events; blend weights %ld exact, %ld within 2e-6; %ld ticks where the device keeps the matrices of a never-blended "
+                "transition; %d failures\n",
+                (long)n, frames, cut, ticksCompared, cnt.transitions, cnt.blends, cnt.errors, eventsSeen, cnt.exactWeights, cnt.closeWeights, cnt.keptByDevice, g_failures);
+    return g_failures ? 1 : 0;
+}
+
 #define DMK_OK_OR_FAIL(expr)                                                                              \
     do {                                                                                                  \
         if ((expr) != DMK_OK) { CHECK(false, "%s: %s", #expr, dmk_last_error(ctx)); return; }             \
@@ -448,47 +691,11 @@ static void runDeviceAnimators(const std::string& dir, const OracleAssets& o, co
     dmk_clipset_t clipset = nullptr;
     DMK_OK_OR_FAIL(dmk_clipset_create(ctx, skel, clips.data(), (int)clips.size(), &clipset));
 
-    // flatten the definition: names -> indices; a state without any known animation cannot be created (src/skeleton_ozz.cpp:469-485)
-    // and is left out, so play() of it is "no command"
-    std::vector<dmk_anim_state_def> dstates;
-    std::vector<dmk_anim_clip_def> dclips;
-    std::vector<dmk_anim_transition_def> dtrans;
-    std::vector<std::string> stateNames;
-    auto clipIndex = [&](const std::string& name) {
-        for (size_t i = 0; i < o.named.size(); ++i) if (o.named[i].name == name) return (int)i;
-        return -1;
-    };
-    for (const auto& s : def.states) {
-        bool any = false;
-        for (const auto& a : s.animations) any = any || clipIndex(a.name) >= 0;
-        if (any) stateNames.push_back(s.name);
-    }
-    auto stateIndex = [&](const std::string& name) {
-        for (size_t i = 0; i < stateNames.size(); ++i) if (stateNames[i] == name) return (int)i;
-        return -1;
-    };
-    for (const auto& s : def.states) {
-        if (stateIndex(s.name) < 0) continue;
-        dmk_anim_state_def d{};
-        d.first_clip = (int)dclips.size();
-        for (const auto& a : s.animations) {
-            const int ci = clipIndex(a.name);
-            if (ci < 0) continue;
-            dclips.push_back({ci, a.blend_position.x, a.blend_position.y, a.speed, a.loop ? 1 : 0});
-        }
-        d.num_clips = (int)dclips.size() - d.first_clip;
-        d.blend_type = (int)s.blend;
-        d.threshold = s.threshold;
-        d.tween_easing = (int)s.tween.easing;
-        d.tween_duration = s.tween.duration;
-        d.next_state = s.next_state.empty() ? -1 : stateIndex(s.next_state);
-        d.speed = s.speed;
-        dstates.push_back(d);
-    }
-    for (const auto& t : def.transitions)
-        dtrans.push_back({t.src_state.empty() ? -1 : stateIndex(t.src_state), t.dst_state.empty() ? -1 : stateIndex(t.dst_state), (int)t.tween.easing,
-                          t.tween.duration, t.offset});
-
+    const FlatDefinition flat = flattenDefinition(def, o);
+    const std::vector<dmk_anim_state_def>& dstates = flat.states;
+    const std::vector<dmk_anim_clip_def>& dclips = flat.clips;
+    const std::vector<dmk_anim_transition_def>& dtrans = flat.transitions;
+    const std::vector<std::string>& stateNames = flat.stateNames;
     const int64_t n = 330;
     const int J = o.skel->num_joints, L = 18;
     dmk_crowd_t crowd = nullptr;
@@ -520,7 +727,8 @@ static void runDeviceAnimators(const std::string& dir, const OracleAssets& o, co
     std::vector<int32_t> lclip((size_t)L * n);
     std::vector<float> lratio((size_t)L * n), lweight((size_t)L * n), models((size_t)n * J * 16);
     std::vector<dmk_pose_program> prog((size_t)n);
-    long exactWeights = 0, closeWeights = 0, transitionsSeen = 0, errorsSeen = 0, blendsSeen = 0, matricesChecked = 0, eventsSeen = 0;
+    AnimatorCounters cnt;
+    long matricesChecked = 0, eventsSeen = 0;
     const float dt = 1 / 30.f;
     for (int frame = 0; frame < 64; ++frame) {
         bool anyCmd = false, inputs = false;
@@ -528,7 +736,7 @@ static void runDeviceAnimators(const std::string& dir, const OracleAssets& o, co
             cmd[i] = DMK_ANIM_NONE;
             cmdSpeed[i] = 1.f;
             auto play = [&](const std::string& name, float sp) {
-                cmd[i] = stateIndex(name) >= 0 ? stateIndex(name) : DMK_ANIM_NONE;
+                cmd[i] = flat.command(def, name);
                 cmdSpeed[i] = sp;
                 refs[i]->play(name, sp);
                 cores[i]->play(name, sp);
@@ -565,74 +773,8 @@ static void runDeviceAnimators(const std::string& dir, const OracleAssets& o, co
         const bool readMatrices = frame % 6 == 5 || frame == 63;
         if (readMatrices) DMK_OK_OR_FAIL(dmk_crowd_get_models(crowd, 0, n, models.data()));
         for (int64_t i = 0; i < n; ++i) {
-            std::string err;
-            const bool refOk = refs[i]->update(dt, err);
-            const bool active = cores[i]->hasActiveStateOrTransition();
-            detail::PoseRequest req;
-            const auto r = cores[i]->update(dt, req);
-            if (r && active) cores[i]->afterUpdate();
-            CHECK(refOk == (status[i] == 0), "frame %d animator %ld: status %d, reference ok=%d (%s)", frame, (long)i, status[i], (int)refOk, err.c_str());
-            errorsSeen += !refOk;
-            // listener events in the reference's order
-            auto& log = devEvents[(size_t)i];
-            const dmk_anim_events& e = ev[(size_t)i];
-            if (e.cmd_started >= 0) log.push_back("started:" + stateNames[(size_t)e.cmd_started]);
-            if (e.cmd_transition_started) log.push_back("transition_started");
-            if (e.transition_finished) { log.push_back("transition_finished"); log.push_back("finished:" + stateNames[(size_t)e.prev_finished]); }
-            if (e.looped >= 0) log.push_back("looped:" + stateNames[(size_t)e.looped]);
-            if (e.finished >= 0) log.push_back("finished:" + stateNames[(size_t)e.finished]);
-            if (e.auto_started >= 0) log.push_back("started:" + stateNames[(size_t)e.auto_started]);
-            if (e.auto_transition_started) log.push_back("transition_started");
-            CHECK(log == refs[i]->events, "frame %d animator %ld: listener events differ (%zu vs %zu)", frame, (long)i, log.size(), refs[i]->events.size());
-            // current state / transition and their clocks (exact: only +, *, /, fmod)
-            const auto* rs = refs[i]->currentState();
-            const dmk_anim_state& di = info[(size_t)i];
-            CHECK((rs != nullptr) == (di.state >= 0), "frame %d animator %ld: current state presence", frame, (long)i);
-            if (rs && di.state >= 0) {
-                CHECK(stateNames[(size_t)di.state] == rs->getName(), "frame %d animator %ld: state %s vs %s", frame, (long)i, stateNames[(size_t)di.state].c_str(), rs->getName().c_str());
-                CHECK(di.state_time == rs->getNormalizedTime(), "frame %d animator %ld: state clock %.9g vs %.9g", frame, (long)i, di.state_time, rs->getNormalizedTime());
-                const float duration = cores[i]->getStateDuration(std::string(rs->getName())) / dstates[(size_t)di.state].speed * di.state_speed;
-                CHECK(std::fabs(duration - rs->getDuration()) <= 1e-6f * rs->getDuration(), "frame %d animator %ld: state duration %g vs %g", frame, (long)i, duration, rs->getDuration());
-            }
-            auto* rt = const_cast<orc::RefTransition*>(refs[i]->currentTransition());
-            CHECK((rt != nullptr) == (di.transition >= 0), "frame %d animator %ld: transition presence", frame, (long)i);
-            if (rt && di.transition >= 0) {
-                CHECK(di.transition_time == rt->getNormalizedTime(), "frame %d animator %ld: transition clock", frame, (long)i);
-                CHECK(di.previous_state >= 0 && stateNames[(size_t)di.previous_state] == rt->previous().getName() && di.previous_time == rt->previous().getNormalizedTime(),
-                      "frame %d animator %ld: previous state of the transition", frame, (long)i);
-            }
-            // resolved program against the host shim's PoseRequest
-            const dmk_pose_program& g = prog[(size_t)i];
-            if (!r || !active || req.top == detail::PoseRequest::Skip) {
-                CHECK(g.top == DMK_TOP_SKIP, "frame %d animator %ld: program top %d, expected SKIP", frame, (long)i, g.top);
-            } else {
-                const bool tr = req.top == detail::PoseRequest::Transition;
-                transitionsSeen += tr;
-                CHECK(g.top == (tr ? DMK_TOP_TRANSITION : DMK_TOP_GROUP0), "frame %d animator %ld: program top %d", frame, (long)i, g.top);
-                int row = 0;
-                for (int k = 0; k < (tr ? 2 : 1); ++k) {
-                    const detail::GroupRequest& gr = k ? req.group1 : req.group0;
-                    const int cnt = k ? g.num_layers1 : g.num_layers0, rest = k ? g.rest1 : g.rest0, mode = k ? g.mode1 : g.mode0;
-                    const float th = k ? g.threshold1 : g.threshold0;
-                    CHECK(cnt == (int)gr.layers.size() && rest == gr.rest && mode == (gr.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND) && th == gr.threshold,
-                          "frame %d animator %ld group %d: count %d/%zu rest %d/%d mode %d", frame, (long)i, k, cnt, gr.layers.size(), rest, gr.rest, mode);
-                    blendsSeen += !gr.passthrough;
-                    for (size_t l = 0; l < gr.layers.size() && (int)l < cnt; ++l, ++row) {
-                        const size_t at = (size_t)row * n + i;
-                        CHECK(lclip[at] == gr.layers[l].clip, "frame %d animator %ld row %d: clip %d vs %d", frame, (long)i, row, lclip[at], gr.layers[l].clip);
-                        CHECK(lratio[at] == gr.layers[l].ratio, "frame %d animator %ld row %d: ratio %.9g vs %.9g", frame, (long)i, row, lratio[at], gr.layers[l].ratio);
-                        if (gr.passthrough) continue;
-                        if (lweight[at] == gr.layers[l].weight) ++exactWeights;
-                        else {
-                            ++closeWeights;
-                            CHECK(std::fabs(lweight[at] - gr.layers[l].weight) <= 2e-6f * std::fmax(1.f, std::fabs(gr.layers[l].weight)),
-                                  "frame %d animator %ld row %d: weight %.9g vs %.9g", frame, (long)i, row, lweight[at], gr.layers[l].weight);
-                        }
-                    }
-                }
-                if (tr) CHECK(std::fabs(g.weight0 - req.w0) <= 1e-6f && std::fabs(g.weight1 - req.w1) <= 1e-6f, "frame %d animator %ld: transition weights %.9g/%.9g vs %.9g/%.9g",
-                              frame, (long)i, g.weight0, g.weight1, req.w0, req.w1);
-            }
+            compareAnimatorTick(frame, i, n, dt, *refs[i], *cores[i], devEvents[(size_t)i], ev[(size_t)i], status[i], info[(size_t)i], prog[(size_t)i], lclip, lratio,
+                                lweight, stateNames, dstates, cnt);
             // model matrices against the reference animator
             if (readMatrices && i % 3 == 0) {
                 const float* m = &models[(size_t)i * J * 16];
@@ -651,8 +793,8 @@ static void runDeviceAnimators(const std::string& dir, const OracleAssets& o, co
     }
     for (const auto& l : devEvents) eventsSeen += (long)l.size();
     std::printf("gpu: device animators, %ld characters x 64 frames: %ld transitions, %ld blends, %ld job errors, %ld events, %ld characters' matrices; "
-                "blend weights %ld exact, %ld within 2e-6\n", (long)n, transitionsSeen, blendsSeen, errorsSeen, eventsSeen, matricesChecked, exactWeights, closeWeights);
-    CHECK(transitionsSeen > 1000 && blendsSeen > 3000 && errorsSeen > 100 && eventsSeen > 1500 && matricesChecked > 500, "device animator scenario lost coverage");
+                "blend weights %ld exact, %ld within 2e-6\n", (long)n, cnt.transitions, cnt.blends, cnt.errors, eventsSeen, matricesChecked, cnt.exactWeights, cnt.closeWeights);
+    CHECK(cnt.transitions > 1000 && cnt.blends > 3000 && cnt.errors > 100 && eventsSeen > 1500 && matricesChecked > 500, "device animator scenario lost coverage");
     dmk_crowd_destroy(crowd);
     dmk_clipset_destroy(clipset);
     for (auto c : clips) dmk_clip_destroy(c);
@@ -1012,8 +1154,10 @@ static int runHostBench(const std::string& dir, int n) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { std::printf("usage: animator_test <assets_dir> cpu|gpu|hostbench [n]|fuzz [sequences] [seed]\n"); return 2; }
+    if (argc < 3) { std::printf("usage: animator_test <assets_dir> cpu|gpu|hostbench [n]|fuzz [sequences] [seed]|devsim [characters] [frames] [seed]\n"); return 2; }
     if (std::string(argv[2]) == "hostbench") return runHostBench(argv[1], argc > 3 ? std::atoi(argv[3]) : 100000);
+    if (std::string(argv[2]) == "devsim")
+        return runDeviceSim(argv[1], argc > 3 ? std::atoll(argv[3]) : 1000, argc > 4 ? std::atoi(argv[4]) : 150, argc > 5 ? std::strtoull(argv[5], nullptr, 10) : 1);
     if (std::string(argv[2]) == "fuzz") return runFuzz(argv[1], argc > 3 ? std::atoi(argv[3]) : 50, argc > 4 ? std::strtoull(argv[4], nullptr, 10) : 1);
     std::setvbuf(stdout, nullptr, _IOLBF, 0);   // keep the progress lines if a section dies
     return std::string(argv[2]) == "gpu" ? runGpu(argv[1]) : runCpu(argv[1]);

@@ -65,6 +65,15 @@ def test_state_machine_fuzz_matches_reference_animator(binary, assets_dir):
         assert "250 sequences" in r.stdout
 
 
+def test_device_animator_code_on_the_cpu_matches_reference_animator(binary, assets_dir):
+    # the animator kernel's per-character code (darmok_b200/csrc/animator_kernel.cu) compiled for the CPU by
+    # tests/cpp/animator_kernel_host.cpp: 1500 characters with seeded random scripts for 200 frames against the reference
+    # animator (events, status, states, clocks) and the host state machine (layers, weights, programs)
+    r = subprocess.run([binary, assets_dir, "devsim", "1500", "200", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and " 0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-500:]
+    assert "1500 characters x 200 frames" in r.stdout
+
+
 def test_archive_reader_survives_damaged_archives_under_asan(assets_dir):
     # the product's ozz reader (darmok_b200/csrc/ozz_io.cpp) built with AddressSanitizer + UBSan: every truncation and 20k seeded
     # corruptions of a valid skeleton / animation archive are answered with true or false, never with a crash
