@@ -20,6 +20,10 @@ RAW_KEYS = [
     "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    # global stores: what the output layouts of the skinning kernel differ in (wavefronts, requests, sectors per request)
+    "l1tex__data_pipe_lsu_wavefronts_mem_lg.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_st.ratio",
+    "lts__t_sectors_srcunit_tex_op_write.sum",
     "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -67,6 +71,9 @@ def main():
             reasons = {k: int(r[ix[k]] or 0) for k in h2 if k.startswith("stall_") and "(Not Issued)" not in k}
             top = max(reasons, key=reasons.get)
             print(f"    {100 * int(r[ix['# Samples']] or 0) / total:5.1f}%  {r[ix['Source']][:60]:60s} {top}")
+        for col in ("L2 Theoretical Sectors Global", "L2 Theoretical Sectors Global Excessive"):
+            if col in ix:
+                print(f"  {col}: {sum(int(r[ix[col]] or 0) for r in data)}")
         if "L1 Wavefronts Shared" in ix:
             wf = sum(int(r[ix["L1 Wavefronts Shared"]] or 0) for r in data)
             ex = sum(int(r[ix["L1 Wavefronts Shared Excessive"]] or 0) for r in data)
