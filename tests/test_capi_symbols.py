@@ -69,3 +69,22 @@ def test_header_is_plain_c99(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_every_declared_function_links_from_c(tmp_path):
+    # a C program that takes the address of every function include/dmk.h declares must link against libdarmok_b200.so:
+    # header and library agree at the linker's level, from the language a binding would be written in
+    import subprocess
+    build.build()
+    names = declared_symbols()
+    src = tmp_path / "link_all.c"
+    src.write_text('#include "dmk.h"\n#include <stdio.h>\nint main(void) {\n    const void* f[] = {\n'
+                   + "".join(f"        (const void*)&{n},\n" for n in names)
+                   + '    };\n    printf("%d\\n", (int)(sizeof f / sizeof f[0]));\n    return 0;\n}\n')
+    exe = tmp_path / "link_all"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-ldarmok_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and int(r.stdout) == len(names)
