@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <new>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -1591,7 +1592,12 @@ static dmk_status read_skinned(dmk_crowd_t c, dmk_mesh_t mesh, const float* d_sk
         return finish_and_check(c);
     }
     // on the device: nine component planes [9][vpad] (1, 2) or three float3 streams [3][vpad][3] (3) per character
-    std::vector<float> planes(static_cast<size_t>(count) * pitch);
+    std::vector<float> planes;
+    try {
+        planes.resize(static_cast<size_t>(count) * pitch);
+    } catch (const std::bad_alloc&) {   // no exception crosses the C ABI
+        return fail(c->ctx, DMK_ERR_INVALID, "not enough host memory to re-interleave that many characters: read a smaller range");
+    }
     DMK_CUDA(c->ctx, cudaMemcpyAsync(planes.data(), d_skinned + first * pitch, planes.size() * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
     if (dmk_status st = finish_and_check(c)) return st;
     for (size_t i = 0; i < static_cast<size_t>(count); ++i) {
