@@ -74,6 +74,19 @@ def test_device_animator_code_on_the_cpu_matches_reference_animator(binary, asse
     assert "1500 characters x 200 frames" in r.stdout
 
 
+def test_host_code_is_clean_under_address_and_ub_sanitizers(binary, assets_dir):
+    # the shim, the state machine and the CPU build of the animator kernel's code, rebuilt with -fsanitize=address,undefined:
+    # the scripted scenario, 60 fuzz sequences and 300 scripted characters x 100 frames must finish without a report
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "animator_test_asan"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exe = os.path.join(ROOT, "tests", "cpp", "animator_test_asan")
+    env = dict(os.environ, DMK_GOLDEN_DIR=os.path.join(ROOT, "tests", "golden"), ASAN_OPTIONS="detect_leaks=0")
+    for args in (["cpu"], ["fuzz", "60", "11"], ["devsim", "300", "100", "11"]):
+        r = subprocess.run([exe, assets_dir, *args], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0 and " 0 failures" in r.stdout and "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, \
+            r.stdout[-1500:] + r.stderr[-3000:]
+
+
 def test_archive_reader_survives_damaged_archives_under_asan(assets_dir):
     # the product's ozz reader (darmok_b200/csrc/ozz_io.cpp) built with AddressSanitizer + UBSan: every truncation and 20k seeded
     # corruptions of a valid skeleton / animation archive are answered with true or false, never with a crash
