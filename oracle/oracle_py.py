@@ -28,7 +28,8 @@ def build(force: bool = False) -> str:
 def lib():
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        # DMK_ORACLE_LIBRARY: another build of the same sources (`make -C oracle asan`, run under LD_PRELOAD=libasan)
+        L = C.CDLL(os.environ.get("DMK_ORACLE_LIBRARY") or build())
         L.orc_skeleton_load.restype = C.c_void_p
         L.orc_skeleton_load.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         L.orc_skeleton_free.argtypes = [C.c_void_p]
