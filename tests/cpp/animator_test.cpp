@@ -501,7 +501,7 @@ static void compareAnimatorTick(int frame, int64_t i, int64_t n, float dt, orc::
     CHECK(refOk == (status == 0), "frame %d animator %ld: status %d, reference ok=%d (%s)", frame, (long)i, status, (int)refOk, err.c_str());
     counters.errors += !refOk;
     // listener events in the reference's order
-                            if (e.cmd_started >= 0) log.push_back("started:" + stateNames[(size_t)e.cmd_started]);
+    if (e.cmd_started >= 0) log.push_back("started:" + stateNames[(size_t)e.cmd_started]);
     if (e.cmd_transition_started) log.push_back("transition_started");
     if (e.transition_finished) { log.push_back("transition_finished"); log.push_back("finished:" + stateNames[(size_t)e.prev_finished]); }
     if (e.looped >= 0) log.push_back("looped:" + stateNames[(size_t)e.looped]);
