@@ -23,7 +23,7 @@ OPT_FORCE_KEY_SEARCH = 1
 OPT_SKIN_RESERVED_SMS = 2
 OPT_KEEP_WORLD_INVERSE = 3
 OPT_SKIN_PLANAR_OUTPUT = 4
-GROUP_BLEND, GROUP_PASSTHROUGH = 0, 1
+GROUP_BLEND, GROUP_PASSTHROUGH, GROUP_ZERO = 0, 1, 2
 TOP_GROUP0, TOP_TRANSITION, TOP_REST_POSE, TOP_SKIP = 0, 1, 2, 3
 PROGRAM_DTYPE = np.dtype([("n0", "u1"), ("n1", "u1"), ("rest0", "u1"), ("rest1", "u1"), ("mode0", "u1"), ("mode1", "u1"),
                           ("top", "u1"), ("reserved", "u1"), ("threshold0", "f4"), ("threshold1", "f4"), ("w0", "f4"), ("w1", "f4")])

@@ -103,6 +103,7 @@ __device__ float blend_weight(const AnimStateDef& d, const AnimClipDef* clips, c
 
 struct GroupOut {
     int count, rest, passthrough;
+    int zero;   // passthrough of a clip that has never been sampled: darmok's zero-initialised locals (kGroupZero)
     float threshold;
 };
 
@@ -127,6 +128,7 @@ __device__ bool state_update(const AnimatorParams& p, int64_t c, const Slot& s, 
             if (!(now_looped && !cd.loop)) {
                 t = fmodf(norm_time, 1.f);
                 if (commit) s.setf(kWClipTime + k, t);
+                if (commit) clip_looped |= 0x10000u << k;   // SamplingJob has run for this clip at least once (bits 16.. of the word)
             }
         }
         const int64_t at = (int64_t)(first + k) * p.n + c;
@@ -145,6 +147,7 @@ __device__ bool state_update(const AnimatorParams& p, int64_t c, const Slot& s, 
     g.threshold = d.threshold;
     g.rest = 0;
     g.passthrough = 1;
+    g.zero = ((clip_looped >> 16) & 1u) ? 0 : 1;
     if (d.num_clips <= 1) return true;
     const EasingType easing = static_cast<EasingType>(d.tween_easing);
     float blend_x = s.getf(kWBlendX), blend_y = s.getf(kWBlendY), old_x = s.getf(kWOldBlendX), old_y = s.getf(kWOldBlendY);
@@ -171,11 +174,13 @@ __device__ bool state_update(const AnimatorParams& p, int64_t c, const Slot& s, 
         const AnimClipDef& cd = p.clips[d.first_clip + k];
         if (cd.blend_x == px && cd.blend_y == py) {   // early exit: a clip sits exactly at the blend position
             g.rest = k;
+            g.zero = ((clip_looped >> (16 + k)) & 1u) ? 0 : 1;
             return true;
         }
         p.weight[(int64_t)(first + k) * p.n + c] = blend_weight(d, p.clips, p.tables, px, py, len, k);
     }
     g.passthrough = 0;
+    g.zero = 0;
     g.rest = d.rest_clip;
     return d.threshold > 0.f;   // BlendingJob::Validate
 }
@@ -229,7 +234,7 @@ __device__ void play(const AnimatorParams& p, int64_t c, Character& a, int state
 }
 
 __device__ __forceinline__ void set_group(PoseProgram& prog, int k, const GroupOut& g) {
-    const uint8_t mode = g.passthrough ? kGroupPassthrough : kGroupBlend;
+    const uint8_t mode = g.zero ? kGroupZero : g.passthrough ? kGroupPassthrough : kGroupBlend;
     if (k == 0) { prog.n0 = (uint8_t)g.count; prog.rest0 = (uint8_t)g.rest; prog.mode0 = mode; prog.threshold0 = g.threshold; }
     else { prog.n1 = (uint8_t)g.count; prog.rest1 = (uint8_t)g.rest; prog.mode1 = mode; prog.threshold1 = g.threshold; }
 }

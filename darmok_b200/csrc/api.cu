@@ -960,7 +960,7 @@ dmk_status dmk_crowd_set_programs(dmk_crowd_t c, int num_layers, const int32_t* 
     const size_t n = static_cast<size_t>(c->n);
     for (size_t i = 0; i < n; ++i) {
         const dmk_pose_program& g = programs[i];
-        if (g.top > DMK_TOP_SKIP || g.mode0 > DMK_GROUP_PASSTHROUGH || g.mode1 > DMK_GROUP_PASSTHROUGH || g.num_layers0 + g.num_layers1 > num_layers)
+        if (g.top > DMK_TOP_SKIP || g.mode0 > DMK_GROUP_ZERO || g.mode1 > DMK_GROUP_ZERO || g.num_layers0 + g.num_layers1 > num_layers)
             return fail(ctx, DMK_ERR_INVALID, "malformed pose program for character " + std::to_string(i));
         if (g.top == DMK_TOP_SKIP || g.top == DMK_TOP_REST_POSE) continue;
         const int groups = g.top == DMK_TOP_TRANSITION ? 2 : 1;

@@ -38,13 +38,13 @@ struct ClipSetDev {
 struct PoseProgram {
     uint8_t n0, n1;        // layers of group 0 = [0, n0), of group 1 = [n0, n0 + n1)
     uint8_t rest0, rest1;  // blend: index (within the group) of the rest-pose layer; pass-through: the layer to copy
-    uint8_t mode0, mode1;  // kGroupBlend / kGroupPassthrough
+    uint8_t mode0, mode1;  // kGroupBlend / kGroupPassthrough / kGroupZero
     uint8_t top;           // kTopGroup0 / kTopTransition / kTopRestPose / kTopSkip
     uint8_t reserved;
     float threshold0, threshold1;  // BlendingJob::threshold of each group
     float w0, w1;          // transition layer weights (1 - v, v); threshold is bx::kFloatSmallest
 };
-constexpr uint8_t kGroupBlend = 0, kGroupPassthrough = 1;
+constexpr uint8_t kGroupBlend = 0, kGroupPassthrough = 1, kGroupZero = 2;
 constexpr uint8_t kTopGroup0 = 0, kTopTransition = 1, kTopRestPose = 2, kTopSkip = 3;
 
 struct SkeletonDev {

@@ -209,6 +209,15 @@ template <int F, typename LayerFn>
 __device__ __forceinline__ Xform eval_group(const ClipSetDev& cs, const LayerFn& layer, int begin, int count, int mode, int rest_idx,
                                             float threshold, int jt, int32_t* key_base, int P) {
     Xform acc;
+    if (mode == kGroupZero) {   // the never-sampled clip of a state: darmok's zero-initialised locals are the pose
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc.t[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc.r[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc.s[k] = 0.f;
+        return acc;
+    }
     if (mode == kGroupPassthrough) {
         // every clip of a state is sampled each tick (:538-545); only one of them is the pose
         for (int l = begin; l < begin + count; ++l) {

@@ -24,6 +24,7 @@ struct LayerRequest {
 struct GroupRequest {
     std::vector<LayerRequest> layers;
     bool passthrough = false;   // single-clip state, or a clip sitting exactly at the blend position
+    bool zero = false;          // passthrough of a clip that has never been sampled: darmok's zero-initialised locals are the pose
     int rest = 0;               // blend: rest-pose layer; passthrough: the layer that is the pose
     float threshold = 0.f;
 };
@@ -48,12 +49,16 @@ public:
     float getNormalizedTime() const noexcept { return _normalizedTime; }
     const glm::vec2& getBlendPosition() const noexcept { return _def.blend_position; }
     int clip() const noexcept { return _clip; }
+    // false while the clip has never been sampled: darmok's AnimationState then still holds its zero-initialised locals
+    // (a non-looping clip that runs past its end on its very first tick is never sampled at all, src/skeleton_ozz.cpp:411-428)
+    bool sampledOnce() const noexcept { return _sampledOnce; }
 private:
     SkeletalAnimatorAnimationDefinition _def;
     int _clip;
     float _clipDuration;
     float _normalizedTime = 0.f;
     bool _looped = false;
+    bool _sampledOnce = false;
 };
 
 class StateMachineState final : public ISkeletalAnimatorState {

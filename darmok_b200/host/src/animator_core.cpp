@@ -28,6 +28,7 @@ void ClipState::update(float deltaTime) noexcept {
     _looped = normTime > 1.f;
     if (hasFinished()) return;
     _normalizedTime = std::fmod(normTime, 1.f);   // setNormalizedTime (:392-396)
+    _sampledOnce = true;                          // SamplingJob runs from here on (:429-437)
 }
 
 // ---- StateMachineState: OzzSkeletalAnimatorState --------------------------------------------------------------------
@@ -135,6 +136,7 @@ expected<void, std::string> StateMachineState::updateImpl(float deltaTime, const
     if (_clips.size() <= 1) {   // getLocals() returns the single clip's buffer (:617-624)
         out.passthrough = true;
         out.rest = 0;
+        out.zero = !_clips[0].sampledOnce();
         return {};
     }
     if (_blendPos != blendPosition) {
@@ -156,6 +158,7 @@ expected<void, std::string> StateMachineState::updateImpl(float deltaTime, const
         if (clip.getBlendPosition() == pos) {   // early exit: one clip sits exactly at the blend position
             out.passthrough = true;
             out.rest = static_cast<int>(i);
+            out.zero = !clip.sampledOnce();   // the copy of a buffer that was never written
             return {};
         }
         if (i < weights.size()) out.layers[i].weight = weights[i];

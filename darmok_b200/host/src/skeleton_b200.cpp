@@ -36,13 +36,13 @@ void writeRequest(const detail::PoseRequest& req, int64_t index, int64_t n, int3
     prog.top = req.top == detail::PoseRequest::Transition ? DMK_TOP_TRANSITION : DMK_TOP_GROUP0;
     prog.num_layers0 = static_cast<uint8_t>(req.group0.layers.size());
     prog.rest0 = static_cast<uint8_t>(req.group0.rest);
-    prog.mode0 = req.group0.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND;
+    prog.mode0 = req.group0.zero ? DMK_GROUP_ZERO : req.group0.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND;
     prog.threshold0 = req.group0.threshold;
     writeGroup(req.group0, 0);
     if (req.top == detail::PoseRequest::Transition) {
         prog.num_layers1 = static_cast<uint8_t>(req.group1.layers.size());
         prog.rest1 = static_cast<uint8_t>(req.group1.rest);
-        prog.mode1 = req.group1.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND;
+        prog.mode1 = req.group1.zero ? DMK_GROUP_ZERO : req.group1.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND;
         prog.threshold1 = req.group1.threshold;
         prog.weight0 = req.w0;
         prog.weight1 = req.w1;

@@ -192,7 +192,11 @@ typedef struct dmk_pose_program {
     float threshold0, threshold1;
     float weight0, weight1;
 } dmk_pose_program;
-enum { DMK_GROUP_BLEND = 0, DMK_GROUP_PASSTHROUGH = 1 };
+/* DMK_GROUP_ZERO: the group's pose is darmok's zero-initialised locals (translation, rotation and scale all 0) -- what a state
+ * shows whose single clip (or the clip sitting exactly at the blend position) has never been sampled, because a non-looping
+ * clip that runs past its end on its very first tick is never sampled at all (src/skeleton_ozz.cpp:411-428).  The group's
+ * layer rows are ignored. */
+enum { DMK_GROUP_BLEND = 0, DMK_GROUP_PASSTHROUGH = 1, DMK_GROUP_ZERO = 2 };
 enum { DMK_TOP_GROUP0 = 0, DMK_TOP_TRANSITION = 1, DMK_TOP_REST_POSE = 2, DMK_TOP_SKIP = 3 };
 DMK_API dmk_status dmk_crowd_set_programs(dmk_crowd_t crowd, int num_layers, const int32_t* clip, const float* ratio,
                                           const float* weight, const dmk_pose_program* programs);

@@ -143,7 +143,7 @@ RefAnimationState::RefAnimationState(const orc_skeleton* skel, const AnimationDe
     : _def(def), _animation(anim), _sampling(orc_sampling_context_create(skel->num_joints)),
       _locals((size_t)skel->num_soa * ORC_SOA_FLOATS, 0.f) {}
 RefAnimationState::RefAnimationState(RefAnimationState&& o) noexcept
-    : _def(std::move(o._def)), _normalizedTime(o._normalizedTime), _looped(o._looped), _sampledOnce(o._sampledOnce), _animation(o._animation), _sampling(o._sampling),
+    : _def(std::move(o._def)), _normalizedTime(o._normalizedTime), _looped(o._looped), _animation(o._animation), _sampling(o._sampling),
       _locals(std::move(o._locals)) {
     o._sampling = nullptr;
 }
@@ -153,7 +153,6 @@ RefAnimationState& RefAnimationState::operator=(RefAnimationState&& o) noexcept 
         _def = std::move(o._def);
         _normalizedTime = o._normalizedTime;
         _looped = o._looped;
-        _sampledOnce = o._sampledOnce;
         _animation = o._animation;
         _sampling = o._sampling;
         _locals = std::move(o._locals);
@@ -174,12 +173,8 @@ bool RefAnimationState::update(float dt, std::string& err) {
     const float normDeltaTime = dt / getDuration();
     const float normTime = _normalizedTime + normDeltaTime;
     _looped = normTime > 1.f;
-    if (hasFinished()) {
-        if (!_sampledOnce) ++g_unsampledHolds;
-        return true;
-    }
+    if (hasFinished()) return true;   // (never sampled at all when this happens on the first tick: the locals stay zero)
     _normalizedTime = std::fmod(normTime, 1.f);
-    _sampledOnce = true;
     if (!orc_sample(_animation, _sampling, _normalizedTime, _locals.data(), (int)(_locals.size() / ORC_SOA_FLOATS), nullptr)) {
         err = "error in the sampling job";
         return false;

@@ -54,9 +54,10 @@ struct AnimatorDef {
 };
 
 float ease(int type, float position, float start, float end);
-// Number of times a non-looping clip ran past its end on its very FIRST tick: darmok then never samples it and the state
-// keeps the zero-initialised locals (src/skeleton_ozz.cpp:411-428).  The product shows the clip's ratio-0 pose instead
-// (documented deviation); tests that generate random inputs stop a sequence when this counter moves.
+// Number of times darmok's zero-initialised locals of a state that was NEVER updated became the pose: a transition copies its
+// previous state's locals when it is created (src/skeleton_ozz.cpp:658-665) and keeps showing them while its current state
+// fails.  The product cannot express that pose (documented deviation); tests that generate random inputs
+// stop a sequence when this counter moves.
 extern int g_unsampledHolds;
 
 struct NamedAnimation {
@@ -79,7 +80,6 @@ private:
     AnimationDef _def;
     float _normalizedTime = 0.f;
     bool _looped = false;
-    bool _sampledOnce = false;    // test bookkeeping only (see g_unsampledHolds)
     const orc_animation* _animation;
     orc_sampling_context* _sampling;
     std::vector<float> _locals;   // SoaTransform[num_soa]

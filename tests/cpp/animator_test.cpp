@@ -176,6 +176,7 @@ static OracleAssets loadOracle(const std::string& dir) {
 // evaluates one group of a PoseRequest with the oracle's jobs (what the device does)
 static std::vector<float> evalGroup(const OracleAssets& o, const detail::GroupRequest& g) {
     const int S = o.skel->num_soa;
+    if (g.zero) return std::vector<float>((size_t)S * 40, 0.f);   // a clip that was never sampled: darmok's zero-initialised locals
     std::vector<std::vector<float>> samples;
     for (const auto& l : g.layers) {
         samples.emplace_back((size_t)S * 40);
@@ -239,7 +240,7 @@ static ScenarioStats runScenarioCpu(const OracleAssets& o, const SkeletalAnimato
         std::string refErr;
         const int holdsBefore = orc::g_unsampledHolds;
         const bool refOk = ref.update(a.a, refErr);
-        if (stopAtUnsampledHold && orc::g_unsampledHolds != holdsBefore) break;   // the documented deviation: nothing comparable follows
+        if (stopAtUnsampledHold && orc::g_unsampledHolds != holdsBefore) break;   // the documented deviation (zero locals of a never-updated state): nothing comparable follows
         CHECK(r.has_value() == refOk, "%s step %d: shim ok=%d ref ok=%d (%s)", label, step, (int)r.has_value(), (int)refOk, refErr.c_str());
         if (!r) {
             ++errors;
@@ -371,7 +372,7 @@ static int runFuzz(const std::string& dir, int sequences, uint64_t seed) {
     const float dts[] = {1 / 60.f, 1 / 60.f, 1 / 30.f, 1 / 30.f, 1 / 15.f, 0.1f, 0.4f, 0.f, 1.7f, 1e-4f, -1 / 60.f, -0.3f};   // C1: negative steps too
     const float speeds[] = {1.f, 1.f, 2.f, 0.5f, 0.f, 3.f, -1.f};
     ScenarioStats total;
-    int cut = 0;   // sequences that ended early at the documented deviation (non-looping clip past its end on its first tick)
+    int cut = 0;   // sequences that ended early at the documented deviation (darmok showing the zero locals of a never-updated state)
     for (int q = 0; q < sequences; ++q) {
         std::vector<Action> actions;
         const int len = 60 + pick(120);
@@ -411,7 +412,7 @@ static int runFuzz(const std::string& dir, int sequences, uint64_t seed) {
             break;
         }
     }
-    std::printf("fuzz: %d sequences (%d cut at the known first-tick deviation), %d ticks, %d poses (%d blends, %d passthroughs, %d in transition), %d job errors, %zu events, %d failures\n", sequences,
+    std::printf("fuzz: %d sequences (%d cut where darmok shows the zero locals of a never-updated state), %d ticks, %d poses (%d blends, %d passthroughs, %d in transition), %d job errors, %zu events, %d failures\n", sequences,
                 cut, total.ticks, total.poses, total.blends, total.passthroughs, total.transitions, total.errors, total.events, g_failures);
     return g_failures ? 1 : 0;
 }
@@ -490,7 +491,7 @@ static void compareAnimatorTick(int frame, int64_t i, int64_t n, float dt, orc::
     std::string err;
     const int holds = orc::g_unsampledHolds;
     const bool refOk = ref.update(dt, err);
-    if (deviated && orc::g_unsampledHolds != holds) {   // the documented first-tick deviation: nothing comparable follows for this character
+    if (deviated && orc::g_unsampledHolds != holds) {   // the documented deviation (zero locals of a never-updated state): nothing comparable follows for this character
         *deviated = true;
         return;
     }
@@ -545,7 +546,7 @@ static void compareAnimatorTick(int frame, int64_t i, int64_t n, float dt, orc::
             const detail::GroupRequest& gr = k ? req.group1 : req.group0;
             const int cnt = k ? g.num_layers1 : g.num_layers0, rest = k ? g.rest1 : g.rest0, mode = k ? g.mode1 : g.mode0;
             const float th = k ? g.threshold1 : g.threshold0;
-            CHECK(cnt == (int)gr.layers.size() && rest == gr.rest && mode == (gr.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND) && th == gr.threshold,
+            CHECK(cnt == (int)gr.layers.size() && rest == gr.rest && mode == (gr.zero ? DMK_GROUP_ZERO : gr.passthrough ? DMK_GROUP_PASSTHROUGH : DMK_GROUP_BLEND) && th == gr.threshold,
                   "frame %d animator %ld group %d: count %d/%zu rest %d/%d mode %d", frame, (long)i, k, cnt, gr.layers.size(), rest, gr.rest, mode);
             counters.blends += !gr.passthrough;
             for (size_t l = 0; l < gr.layers.size() && (int)l < cnt; ++l, ++row) {
@@ -661,7 +662,7 @@ static int runDeviceSim(const std::string& dir, int64_t n, int frames, uint64_t 
     long cut = 0, eventsSeen = 0;
     for (char d : deviated) cut += d;
     for (const auto& l : devEvents) eventsSeen += (long)l.size();
-    std::printf("devsim: kernel code on the CPU, %ld characters x %d frames (%ld cut at the known first-tick deviation): %ld ticks compared, %ld transitions, "
+    std::printf("devsim: kernel code on the CPU, %ld characters x %d frames (%ld cut where darmok shows the zero locals of a never-updated state): %ld ticks compared, %ld transitions, "
                 "%ld blends, %ld job errors, %ld events; blend weights %ld exact, %ld within 2e-6; %ld ticks where the device keeps the matrices of a never-blended "
                 "transition; %d failures\n",
                 (long)n, frames, cut, ticksCompared, cnt.transitions, cnt.blends, cnt.errors, eventsSeen, cnt.exactWeights, cnt.closeWeights, cnt.keptByDevice, g_failures);
