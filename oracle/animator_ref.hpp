@@ -140,6 +140,8 @@ public:
     RefAnimator(const orc_skeleton* skel, std::vector<NamedAnimation> anims, AnimatorDef def);
     bool play(const std::string& name, float stateSpeed = 1.f);
     void stop() { _state.reset(); }
+    void pause() { _paused = !_paused; }                            // src/skeleton_ozz.cpp:875-878: a toggle nothing else reads
+    int getPlaybackState() const { return !_state ? 0 : _paused ? 2 : 1; }   // Stopped, Playing, Paused (:880-891)
     void setPlaybackSpeed(float s) { _speed = s; }
     void setBlendPosition(Vec2 p) { _blendPosition = p; }
     bool update(float dt, std::string& err);
@@ -156,6 +158,7 @@ private:
     std::vector<NamedAnimation> _anims;
     AnimatorDef _def;
     float _speed = 1.f;
+    bool _paused = false;
     Vec2 _blendPosition;
     std::optional<RefTransition> _transition;
     std::optional<RefState> _state;

@@ -201,7 +201,7 @@ static void applyAction(const Action& a, auto& shim, orc::RefAnimator& ref, int 
     case Action::Stop: shim.stop(); ref.stop(); break;
     case Action::Blend: shim.setBlendPosition(glm::vec2(a.a, a.b)); ref.setBlendPosition({a.a, a.b}); break;
     case Action::Speed: shim.setPlaybackSpeed(a.a); ref.setPlaybackSpeed(a.a); break;
-    case Action::Pause: shim.pause(); break;   // only changes getPlaybackState (C10)
+    case Action::Pause: shim.pause(); ref.pause(); break;   // only changes getPlaybackState (C10)
     default: break;
     }
 }
@@ -275,6 +275,11 @@ static ScenarioStats runScenarioCpu(const OracleAssets& o, const SkeletalAnimato
             CHECK(cs->getNormalizedTime() == rs->getNormalizedTime(), "%s step %d: normalized time %g vs %g", label, step, cs->getNormalizedTime(), rs->getNormalizedTime());
             CHECK(cs->getDuration() == rs->getDuration(), "%s step %d: duration %g vs %g", label, step, cs->getDuration(), rs->getDuration());
         }
+        // Stopped without _state (also while a transition runs), else Paused / Playing by the toggle (src/skeleton_ozz.cpp:880-891)
+        CHECK(static_cast<int>(core.getPlaybackState()) == (ref.getPlaybackState() == 0 ? (int)SkeletalAnimatorPlaybackState::Stopped
+                                                            : ref.getPlaybackState() == 1 ? (int)SkeletalAnimatorPlaybackState::Playing
+                                                                                          : (int)SkeletalAnimatorPlaybackState::Paused),
+              "%s step %d: playback state %d, reference %d", label, step, (int)core.getPlaybackState(), ref.getPlaybackState());
         CHECK((core.getCurrentTransition() != nullptr) == (ref.currentTransition() != nullptr), "%s step %d: transition presence", label, step);
         if (core.getCurrentTransition() && ref.currentTransition())
             CHECK(core.getCurrentTransition()->getNormalizedTime() == ref.currentTransition()->getNormalizedTime(), "%s step %d: transition time", label, step);
