@@ -147,6 +147,12 @@ private:
     DataLoader _dataLoader;
 };
 
+// ConstSkeletalAnimatorDefinitionWrapper::loadAnimations (src/skeleton.cpp:535-562): the path of an animation is the
+// definition's animation_pattern with every "*" replaced by the animation's name (the name itself without a pattern);
+// animations that fail to load are left out of the map (a state without any known animation cannot be created).
+std::filesystem::path animationPath(const SkeletalAnimatorDefinition& def, std::string_view name) noexcept;
+SkeletalAnimationMap loadAnimations(const SkeletalAnimatorDefinition& def, B200SkeletalAnimationLoader& loader) noexcept;
+
 struct ArmatureJoint final {
     std::string name;
     glm::mat4 inverseBindPose{1.f};
@@ -284,6 +290,11 @@ public:
 
     // stand-alone use: ticks the state machine and runs a one-character device step
     expected<void, std::string> update(float deltaTime) noexcept;
+    // SkeletalAnimator::load(def, ctxt) (src/skeleton_ozz.cpp:901-933) with the two loaders darmok's load context hands out:
+    // skeleton from def.skeleton_path (its error is returned), animations through loadAnimations, then the animator is reset
+    // (no state, no transition, speed 1, not paused, blend position (0, 0)) and shows the new skeleton's rest pose.  The
+    // skinning targets stay; not for animators owned by a SkeletalAnimationSceneComponent.
+    expected<void, std::string> load(const Definition& def, B200SkeletonLoader& skeletons, B200SkeletalAnimationLoader& animations) noexcept;
 
 private:
     friend class SkeletalAnimationSceneComponent;

@@ -351,6 +351,43 @@ SkeletalAnimator::SkeletalAnimator(std::shared_ptr<Skeleton> skel, AnimationMap 
     _core = std::make_unique<detail::AnimatorCore>(std::move(clips), std::move(def));
 }
 
+std::filesystem::path animationPath(const SkeletalAnimatorDefinition& def, std::string_view name) noexcept {
+    if (def.animation_pattern.empty()) return std::string{name};
+    std::string v = def.animation_pattern;   // StringUtils::replace(v, "*", name) (src/string.cpp:134-149): every occurrence
+    size_t at = 0;
+    while ((at = v.find('*', at)) != std::string::npos) {
+        v.replace(at, 1, name);
+        at += name.size();
+    }
+    return v;
+}
+
+SkeletalAnimationMap loadAnimations(const SkeletalAnimatorDefinition& def, B200SkeletalAnimationLoader& loader) noexcept {
+    SkeletalAnimationMap anims;
+    for (const auto& state : def.states)
+        for (const auto& anim : state.animations)
+            if (auto result = loader(animationPath(def, anim.name))) anims.emplace(anim.name, *result);
+    return anims;
+}
+
+expected<void, std::string> SkeletalAnimator::load(const Definition& def, B200SkeletonLoader& skeletons, B200SkeletalAnimationLoader& animations) noexcept {
+    if (_batch) return unexpected<std::string>{"this animator is owned by its SkeletalAnimationSceneComponent"};
+    auto skel = skeletons(def.skeleton_path);
+    if (!skel) return unexpected<std::string>{skel.error()};
+    // load(skeleton, animations, def) (:901-917): reset() drops state, transition, speed, pause and blend position -- a new
+    // state machine -- and the rest-pose LocalToModelJob is what a freshly created device crowd shows
+    _skeleton = std::move(*skel);
+    _animations = loadAnimations(def, animations);
+    std::vector<detail::ClipInfo> clips;
+    for (const auto& [name, anim] : sortedClips(_animations)) clips.push_back({name, anim->getDuration()});
+    _core = std::make_unique<detail::AnimatorCore>(std::move(clips), def);
+    bindEvents(*this, *_core);
+    _device.reset();
+    _views.reset();
+    _modelsValid = false;
+    return {};
+}
+
 SkeletalAnimator::~SkeletalAnimator() noexcept {
     auto itr = listenerRegistry().find(this);
     if (itr != listenerRegistry().end()) {

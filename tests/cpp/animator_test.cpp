@@ -321,6 +321,17 @@ static int runCpu(const std::string& dir) {
         CHECK(md.numVertices() == 2 && md.position[1] == 2.f && md.normal[1] == 1.f && md.normal[4] == 1.f && md.tangent[5] == 1.f, "mesh data streams");
         CHECK(md.indices[0] == 6.f && md.indices[1] == -1.f && md.weights[0] == 1.f && md.indices[4] == -1.f && md.weights[4] == 1.f, "mesh data influences");
     }
+    // ConstSkeletalAnimatorDefinitionWrapper::loadAnimations' path rule (src/skeleton.cpp:538-548, src/string.cpp:134-149)
+    {
+        SkeletalAnimatorDefinition d;
+        CHECK(animationPath(d, "Idle01") == std::filesystem::path("Idle01"), "no pattern: the name is the path");
+        d.animation_pattern = "*.ozz";   // samples/ozz/assets/animator.json: "animationNamePattern": "*.ozz"
+        CHECK(animationPath(d, "Idle01") == std::filesystem::path("Idle01.ozz"), "the sample's pattern");
+        d.animation_pattern = "anims/*/*_v2.bin";
+        CHECK(animationPath(d, "Run") == std::filesystem::path("anims/Run/Run_v2.bin"), "every * is replaced");
+        d.animation_pattern = "fixed.ozz";
+        CHECK(animationPath(d, "Run") == std::filesystem::path("fixed.ozz"), "a pattern without * is used as it is");
+    }
     // every easing curve, specialised (shim) against general (oracle) form
     for (int type = 0; type < 32; ++type)
         for (int i = -4; i <= 44; ++i) {
@@ -931,6 +942,33 @@ static int runGpu(const std::string& dir) {
             CHECK(map.size() == expected && expected > 10, "bone map size %zu vs %zu", map.size(), expected);
         }
         CHECK(animator.getPlaybackState() == SkeletalAnimatorPlaybackState::Paused, "pause toggled once and a state is playing");
+        {   // SkeletalAnimator::load(def, ctxt) (src/skeleton_ozz.cpp:901-933): skeleton + animations through the loaders, reset, rest pose
+            SkeletalAnimatorDefinition fromFiles = def;
+            fromFiles.skeleton_path = dir + "/no_such_skeleton.ozz";
+            fromFiles.animation_pattern = dir + "/*.ozz";
+            CHECK(!animator.load(fromFiles, skelLoader, animLoader).has_value(), "a missing skeleton is the loader's error");
+            CHECK(animator.getCurrentState() != nullptr, "a failed load leaves the animator as it was");
+            fromFiles.skeleton_path = dir + "/skeleton.ozz";
+            const auto loaded = animator.load(fromFiles, skelLoader, animLoader);
+            CHECK(loaded.has_value(), "load: %s", loaded ? "" : loaded.error().c_str());
+            CHECK(animator.getCurrentState() == nullptr && animator.getCurrentTransition() == nullptr && animator.getPlaybackSpeed() == 1.f &&
+                      animator.getPlaybackState() == SkeletalAnimatorPlaybackState::Stopped && animator.getBlendPosition() == glm::vec2(0.f, 0.f),
+                  "load resets the animator");
+            orc::RefAnimator fresh(o.skel, o.named, rdef);   // its load-time LocalToModelJob over the rest pose (:909-916)
+            for (int j = 0; j < J; ++j) {
+                const glm::mat4 m = animator.getJointModelMatrix(o.skel->names[j]);
+                orc_flip_handedness(fresh.models().data() + (size_t)j * 16, flipped.data());
+                for (int e = 0; e < 16; ++e) CHECK(close(glm::value_ptr(m)[e], flipped[e]), "rest pose after load: joint %d elem %d", j, e);
+            }
+            CHECK(animator.play("locomotion") && fresh.play("locomotion"), "the loaded definition plays");   // every clip of the sample was found
+            std::string err;
+            CHECK(animator.update(1 / 30.f).has_value() && fresh.update(1 / 30.f, err), "first tick after load");
+            for (int j = 0; j < J; j += 7) {
+                const glm::mat4 m = animator.getJointModelMatrix(o.skel->names[j]);
+                orc_flip_handedness(fresh.models().data() + (size_t)j * 16, flipped.data());
+                for (int e = 0; e < 16; ++e) CHECK(close(glm::value_ptr(m)[e], flipped[e]), "pose after load: joint %d elem %d", j, e);
+            }
+        }
         std::printf("gpu: stand-alone animator, %d ticks compared with matrices/palette/skin, %zu events\n", checked, log.events.size());
     }
 
