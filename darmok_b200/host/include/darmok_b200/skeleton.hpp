@@ -238,6 +238,12 @@ public:
     virtual void onAnimatorTransitionStarted(SkeletalAnimator&) {}
 };
 
+class ISkeletalAnimatorListenerFilter {   // include/darmok/skeleton.hpp:123-128
+public:
+    virtual ~ISkeletalAnimatorListenerFilter() = default;
+    virtual bool operator()(const ISkeletalAnimatorListener& listener) const = 0;
+};
+
 enum class SkeletalAnimatorPlaybackState { Stopped, Playing, Paused };
 
 namespace detail {
@@ -252,6 +258,7 @@ public:
     using AnimationMap = SkeletalAnimationMap;
     using PlaybackState = SkeletalAnimatorPlaybackState;
 
+    SkeletalAnimator() noexcept;   // no skeleton, no animations, empty definition: to be filled by load()
     SkeletalAnimator(std::shared_ptr<Skeleton> skel, AnimationMap anims, Definition def) noexcept;
     ~SkeletalAnimator() noexcept;
     SkeletalAnimator(const SkeletalAnimator&) = delete;
@@ -260,6 +267,7 @@ public:
     SkeletalAnimator& addListener(std::unique_ptr<ISkeletalAnimatorListener> listener) noexcept;
     SkeletalAnimator& addListener(ISkeletalAnimatorListener& listener) noexcept;
     bool removeListener(const ISkeletalAnimatorListener& listener) noexcept;
+    size_t removeListeners(const ISkeletalAnimatorListenerFilter& filter) noexcept;   // number removed (src/skeleton_ozz.cpp:259-262)
 
     SkeletalAnimator& setPlaybackSpeed(float speed) noexcept;
     float getPlaybackSpeed() const noexcept;
@@ -295,6 +303,7 @@ public:
     // (no state, no transition, speed 1, not paused, blend position (0, 0)) and shows the new skeleton's rest pose.  The
     // skinning targets stay; not for animators owned by a SkeletalAnimationSceneComponent.
     expected<void, std::string> load(const Definition& def, B200SkeletonLoader& skeletons, B200SkeletalAnimationLoader& animations) noexcept;
+    static Definition createDefinition() noexcept { return {}; }   // src/skeleton_ozz.cpp:956-959
 
 private:
     friend class SkeletalAnimationSceneComponent;

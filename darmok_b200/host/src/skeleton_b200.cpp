@@ -344,6 +344,8 @@ void bindEvents(SkeletalAnimator& animator, detail::AnimatorCore& core) {
 }
 }  // namespace
 
+SkeletalAnimator::SkeletalAnimator() noexcept : SkeletalAnimator(nullptr, AnimationMap{}, Definition{}) {}
+
 SkeletalAnimator::SkeletalAnimator(std::shared_ptr<Skeleton> skel, AnimationMap anims, Definition def) noexcept
     : _skeleton{std::move(skel)}, _animations{std::move(anims)} {
     std::vector<detail::ClipInfo> clips;
@@ -418,6 +420,19 @@ bool SkeletalAnimator::removeListener(const ISkeletalAnimatorListener& listener)
     auto& owned = itr->second.owned;
     owned.erase(std::remove_if(owned.begin(), owned.end(), [&](const auto& p) { return p.get() == &listener; }), owned.end());
     return all.size() != before;
+}
+
+size_t SkeletalAnimator::removeListeners(const ISkeletalAnimatorListenerFilter& filter) noexcept {
+    auto itr = listenerRegistry().find(this);
+    if (itr == listenerRegistry().end()) return 0;
+    auto& all = itr->second.all;
+    std::vector<ISkeletalAnimatorListener*> gone;
+    for (auto* l : all)
+        if (filter(*l)) gone.push_back(l);
+    all.erase(std::remove_if(all.begin(), all.end(), [&](auto* l) { return std::find(gone.begin(), gone.end(), l) != gone.end(); }), all.end());
+    auto& owned = itr->second.owned;   // after the filter has looked at them
+    owned.erase(std::remove_if(owned.begin(), owned.end(), [&](const auto& p) { return std::find(gone.begin(), gone.end(), p.get()) != gone.end(); }), owned.end());
+    return gone.size();
 }
 
 bool SkeletalAnimator::onDevice() const noexcept { return _batch && _batch->_impl->deviceAnimators; }
@@ -527,6 +542,7 @@ expected<int, std::string> SkeletalAnimator::addSkinning(const std::shared_ptr<A
 
 expected<void, std::string> SkeletalAnimator::ensureDevice() noexcept {
     if (_device || _batch) return {};
+    if (!_skeleton) return unexpected<std::string>{"the animator has no skeleton (default constructed and not loaded)"};
     auto dev = Device::create(_skeleton, _animations, _skins, 1);
     if (!dev) return unexpected<std::string>{dev.error()};
     _device = std::move(*dev);

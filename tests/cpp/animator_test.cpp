@@ -321,6 +321,20 @@ static int runCpu(const std::string& dir) {
         CHECK(md.numVertices() == 2 && md.position[1] == 2.f && md.normal[1] == 1.f && md.normal[4] == 1.f && md.tangent[5] == 1.f, "mesh data streams");
         CHECK(md.indices[0] == 6.f && md.indices[1] == -1.f && md.weights[0] == 1.f && md.indices[4] == -1.f && md.weights[4] == 1.f, "mesh data influences");
     }
+    {   // the rest of the public surface that needs no device (include/darmok/skeleton.hpp:259-301)
+        SkeletalAnimator empty;   // default constructed: nothing to play, identity matrices, refuses to tick without a skeleton
+        CHECK(!empty.play("locomotion") && empty.getCurrentState() == nullptr && empty.getJointModelMatrix("root") == glm::mat4(1.f), "empty animator");
+        CHECK(!empty.update(0.1f).has_value(), "an animator without a skeleton cannot tick");
+        CHECK(SkeletalAnimator::createDefinition().states.empty(), "createDefinition");
+        struct Tagged : ISkeletalAnimatorListener { int tag; explicit Tagged(int t) : tag(t) {} };
+        struct OddOnes : ISkeletalAnimatorListenerFilter {
+            bool operator()(const ISkeletalAnimatorListener& l) const override { return static_cast<const Tagged&>(l).tag % 2 == 1; }
+        };
+        Tagged borrowed(3);
+        empty.addListener(std::make_unique<Tagged>(1)).addListener(std::make_unique<Tagged>(2)).addListener(borrowed);
+        CHECK(empty.removeListeners(OddOnes{}) == 2, "removeListeners returns how many went");
+        CHECK(!empty.removeListener(borrowed) && empty.removeListeners(OddOnes{}) == 0, "they are gone");
+    }
     // ConstSkeletalAnimatorDefinitionWrapper::loadAnimations' path rule (src/skeleton.cpp:538-548, src/string.cpp:134-149)
     {
         SkeletalAnimatorDefinition d;
