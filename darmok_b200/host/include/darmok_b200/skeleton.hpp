@@ -157,8 +157,30 @@ struct ArmatureJoint final {
     std::string name;
     glm::mat4 inverseBindPose{1.f};
 };
+// protobuf::Armature as a plain struct (assets/protobuf/skeleton.proto:8-16): a joint's inverse_bind_pose is a Mat4 message of
+// four column vectors col1..col4 (assets/protobuf/math.proto:41-46), i.e. glm's column-major mat4
+struct ArmatureJointDefinition final {
+    std::string name;
+    float inverse_bind_pose[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};   // [column][row]
+};
+struct ArmatureDefinition final {
+    std::string name;
+    std::vector<ArmatureJointDefinition> joints;
+};
 class Armature final {
 public:
+    using Definition = ArmatureDefinition;
+    explicit Armature(const Definition& def) noexcept {   // src/skeleton.cpp:662-669
+        _joints.reserve(def.joints.size());
+        for (const auto& joint : def.joints) {
+            ArmatureJoint j;
+            j.name = joint.name;
+            for (int c = 0; c < 4; ++c)
+                for (int r = 0; r < 4; ++r) j.inverseBindPose[c][r] = joint.inverse_bind_pose[c][r];
+            _joints.push_back(std::move(j));
+        }
+    }
+    static Definition createDefinition() noexcept { return {}; }
     explicit Armature(std::vector<ArmatureJoint> joints) noexcept : _joints{std::move(joints)} {}
     const std::vector<ArmatureJoint>& getJoints() const noexcept { return _joints; }
 private:

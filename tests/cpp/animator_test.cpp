@@ -330,6 +330,15 @@ static int runCpu(const std::string& dir) {
         struct OddOnes : ISkeletalAnimatorListenerFilter {
             bool operator()(const ISkeletalAnimatorListener& l) const override { return static_cast<const Tagged&>(l).tag % 2 == 1; }
         };
+        ArmatureDefinition ad = Armature::createDefinition();
+        ad.joints.resize(2);
+        ad.joints[0].name = "hip";
+        ad.joints[1].name = "knee";
+        ad.joints[1].inverse_bind_pose[3][1] = -0.5f;   // col4.y: a translation
+        const Armature fromDef(ad);
+        CHECK(fromDef.getJoints().size() == 2 && fromDef.getJoints()[0].inverseBindPose == glm::mat4(1.f) && fromDef.getJoints()[1].name == "knee" &&
+                  fromDef.getJoints()[1].inverseBindPose[3][1] == -0.5f && fromDef.getJoints()[1].inverseBindPose[1][3] == 0.f,
+              "Armature(Definition): columns stay columns");
         Tagged borrowed(3);
         empty.addListener(std::make_unique<Tagged>(1)).addListener(std::make_unique<Tagged>(2)).addListener(borrowed);
         CHECK(empty.removeListeners(OddOnes{}) == 2, "removeListeners returns how many went");
