@@ -4,9 +4,11 @@
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
+PORT=29517
 run() {  # name, extra bench args
   local name=$1; shift
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N \
+  PORT=$((PORT + 1))   # a fresh rendezvous port per run
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus $N \
       --steps 20 --warmup 5 "$@" > gpurun_out/r02_b${N}_${name}.json 2> gpurun_out/r02_b${N}_${name}.err
   echo "$name exit $?: $(cut -c1-200 gpurun_out/r02_b${N}_${name}.json)"
 }
