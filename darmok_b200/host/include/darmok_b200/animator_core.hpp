@@ -75,6 +75,7 @@ public:
     void afterFinished() noexcept { _speed = _def.speed; }
     // blend weights of the state's clips for a blend position (calcBlendWeights, src/skeleton.cpp:346-364)
     std::vector<float> calcBlendWeights(const glm::vec2& pos) const noexcept;
+    void calcBlendWeights(const glm::vec2& pos, std::vector<float>& weights) const noexcept;   // same, into a reused buffer
     // what getLocals() holds (src/skeleton_ozz.cpp:617-624): the group of the last update that succeeded; null before the first
     const GroupRequest* lastGood() const noexcept { return _hasLastGood ? &_lastGood : nullptr; }
 private:
@@ -82,6 +83,8 @@ private:
     expected<void, std::string> updateImpl(float deltaTime, const glm::vec2& blendPosition, GroupRequest& out) noexcept;
     GroupRequest _lastGood;
     bool _hasLastGood = false;
+    std::vector<float> _animLengths, _animAngles;   // Directional: per-definition terms of calcBlendWeight (built once)
+    std::vector<float> _weights;                    // scratch of update()
     float calcDuration() const noexcept;
     float calcBlendWeight(const glm::vec2& pos, const glm::vec2& animPos) const noexcept;
     SkeletalAnimatorStateDefinition _def;

@@ -35,6 +35,16 @@ void ClipState::update(float deltaTime) noexcept {
 StateMachineState::StateMachineState(const SkeletalAnimatorStateDefinition& def, std::vector<ClipState> clips) noexcept
     : _def{def}, _clips{std::move(clips)}, _speed{def.speed} {
     _duration = calcDuration();
+    if (_def.blend == SkeletalAnimatorStateDefinition::Directional) {
+        // the terms of calcBlendWeight that only depend on the definition: |blend_position| and the angle between two of them
+        const size_t m = _def.animations.size();
+        _animLengths.resize(m);
+        _animAngles.resize(m * m);
+        for (size_t i = 0; i < m; ++i) {
+            _animLengths[i] = glm::length(_def.animations[i].blend_position);
+            for (size_t j = 0; j < m; ++j) _animAngles[i * m + j] = glm::angle(_def.animations[j].blend_position, _def.animations[i].blend_position);
+        }
+    }
 }
 
 std::optional<StateMachineState> StateMachineState::create(const SkeletalAnimatorStateDefinition& def,
@@ -78,9 +88,10 @@ bool StateMachineState::hasFinished() const noexcept {
 }
 
 float StateMachineState::calcBlendWeight(const glm::vec2& pos, const glm::vec2& animPos) const noexcept {
-    // src/skeleton.cpp:306-344 (gradient bands; the j == i term is 0/0 = NaN and drops out because NaN < w is false)
-    std::vector<std::pair<glm::vec2, glm::vec2>> parts;
-    parts.reserve(_def.animations.size());
+    // src/skeleton.cpp:306-344 (gradient bands; the j == i term is 0/0 = NaN and drops out because NaN < w is false).
+    // Stated as the reference states it; update() goes through calcBlendWeights, which evaluates the same expressions with
+    // the per-definition terms (|blend_position|, angle between two blend positions) taken from tables built once.
+    float w = FLT_MAX;   // bx::kFloatLargest
     if (_def.blend == SkeletalAnimatorStateDefinition::Directional) {
         const float lenAnim = glm::length(animPos);
         const float len = glm::length(pos);
@@ -90,24 +101,49 @@ float StateMachineState::calcBlendWeight(const glm::vec2& pos, const glm::vec2& 
             const float p = lenAnim + lenAnim2;
             const glm::vec2 a{(len - lenAnim) * p, glm::angle(pos, animPos)};
             const glm::vec2 b{(lenAnim2 - lenAnim) * p, glm::angle(blendPos, animPos)};
-            parts.emplace_back(a, b);
+            const float f = 1.F - (glm::dot(a, b) / glm::length2(b));
+            if (f < w) w = f;
         }
     } else {
         const glm::vec2 a = pos - animPos;
-        for (const auto& anim : _def.animations) parts.emplace_back(a, anim.blend_position - animPos);
-    }
-    float w = FLT_MAX;   // bx::kFloatLargest
-    for (const auto& [a, b] : parts) {
-        const float f = 1.F - (glm::dot(a, b) / glm::length2(b));
-        if (f < w) w = f;
+        for (const auto& anim : _def.animations) {
+            const glm::vec2 b = anim.blend_position - animPos;
+            const float f = 1.F - (glm::dot(a, b) / glm::length2(b));
+            if (f < w) w = f;
+        }
     }
     return w;
 }
 
+void StateMachineState::calcBlendWeights(const glm::vec2& pos, std::vector<float>& weights) const noexcept {
+    // calcBlendWeights (src/skeleton.cpp:346-364) over ALL animations of the definition, known to the provider or not
+    const size_t m = _def.animations.size();
+    weights.resize(m);
+    if (_def.blend == SkeletalAnimatorStateDefinition::Directional) {
+        const float len = glm::length(pos);
+        for (size_t i = 0; i < m; ++i) {
+            const float lenAnim = _animLengths[i];
+            const float angle = glm::angle(pos, _def.animations[i].blend_position);   // the one term that depends on the tick
+            const float* angles = &_animAngles[i * m];
+            float w = FLT_MAX;
+            for (size_t j = 0; j < m; ++j) {
+                const float lenAnim2 = _animLengths[j];
+                const float p = lenAnim + lenAnim2;
+                const glm::vec2 a{(len - lenAnim) * p, angle};
+                const glm::vec2 b{(lenAnim2 - lenAnim) * p, angles[j]};
+                const float f = 1.F - (glm::dot(a, b) / glm::length2(b));
+                if (f < w) w = f;
+            }
+            weights[i] = w;
+        }
+        return;
+    }
+    for (size_t i = 0; i < m; ++i) weights[i] = calcBlendWeight(pos, _def.animations[i].blend_position);
+}
+
 std::vector<float> StateMachineState::calcBlendWeights(const glm::vec2& pos) const noexcept {
     std::vector<float> weights;
-    weights.reserve(_def.animations.size());
-    for (const auto& anim : _def.animations) weights.push_back(calcBlendWeight(pos, anim.blend_position));
+    calcBlendWeights(pos, weights);
     return weights;
 }
 
@@ -130,7 +166,10 @@ expected<void, std::string> StateMachineState::updateImpl(float deltaTime, const
     _looped = _normalizedTime > 1.f;
     _normalizedTime = std::fmod(_normalizedTime, 1.f);
 
-    out = GroupRequest{};
+    out.layers.clear();   // keeps the caller's capacity: no allocation per tick once a request has been used
+    out.passthrough = false;
+    out.zero = false;
+    out.rest = 0;
     out.threshold = _def.threshold;
     for (const auto& clip : _clips) out.layers.push_back({clip.clip(), clip.getNormalizedTime(), 0.f});
     if (_clips.size() <= 1) {   // getLocals() returns the single clip's buffer (:617-624)
@@ -150,7 +189,8 @@ expected<void, std::string> StateMachineState::updateImpl(float deltaTime, const
     const float blendFactor = ease01(_def.tween.easing, _normalizedTweenTime);
     const glm::vec2 pos = _oldBlendPos + blendFactor * (_blendPos - _oldBlendPos);
 
-    const std::vector<float> weights = calcBlendWeights(pos);
+    calcBlendWeights(pos, _weights);
+    const std::vector<float>& weights = _weights;
     int rest = -1;
     size_t i = 0;
     for (const auto& clip : _clips) {
@@ -304,7 +344,15 @@ bool AnimatorCore::play(std::string_view name, float stateSpeed) noexcept {
 expected<void, std::string> AnimatorCore::update(float deltaTime, PoseRequest& out) noexcept {
     // src/skeleton_ozz.cpp:1006-1042
     deltaTime *= _speed;
-    out = PoseRequest{};
+    out.top = PoseRequest::Skip;   // reset in place (the groups' layer vectors keep their capacity)
+    out.group0.layers.clear();
+    out.group1.layers.clear();
+    out.group0.passthrough = out.group1.passthrough = false;
+    out.group0.zero = out.group1.zero = false;
+    out.group0.rest = out.group1.rest = 0;
+    out.group0.threshold = out.group1.threshold = 0.f;
+    out.w0 = 1.f;
+    out.w1 = 0.f;
     if (_transition) return _transition->update(deltaTime, _blendPosition, out);
     if (_state) {
         out.top = PoseRequest::Group0;
