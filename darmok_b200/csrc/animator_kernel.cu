@@ -14,6 +14,7 @@
 // Compiled with -fmad=false: clocks, tweens and Cartesian weights are bit-identical to the host; the Directional
 // weights' per-definition angles come precomputed from the host, the per-tick angle(position, clip) uses CUDA's acosf
 // and the transcendental easing curves CUDA's sinf/cosf/powf (last-ulp differences from glibc are possible).
+#include "device_intrinsics.cuh"
 #include "device_types.cuh"
 #include "kernels.cuh"
 
@@ -416,24 +417,22 @@ __device__ __forceinline__ void init_character(const AnimatorParams& p, int64_t 
 
 }  // namespace
 
-#ifndef DMK_ANIMATOR_HOST_TEST   // the CPU build of the test harness has no launches
 cudaError_t launch_animator_init(const AnimatorParams& p, float* cmd_speed, float* in_blend, float* in_speed, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    animator_init_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(p, cmd_speed, in_blend, in_speed);
+    DMK_LAUNCH(animator_init_kernel, (unsigned)((p.n + 255) / 256), 256, 0, stream)(p, cmd_speed, in_blend, in_speed);
     return cudaGetLastError();
 }
 
 cudaError_t launch_animator_query(const AnimatorParams& p, AnimStateInfo* out, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    animator_query_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(p, out);
+    DMK_LAUNCH(animator_query_kernel, (unsigned)((p.n + 255) / 256), 256, 0, stream)(p, out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_animator(const AnimatorParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    animator_kernel<<<(unsigned)((p.n + kAnimBlock - 1) / kAnimBlock), kAnimBlock, 0, stream>>>(p);
+    DMK_LAUNCH(animator_kernel, (unsigned)((p.n + kAnimBlock - 1) / kAnimBlock), kAnimBlock, 0, stream)(p);
     return cudaGetLastError();
 }
-#endif
 
 }  // namespace dmk

@@ -13,6 +13,7 @@
 // have signed distance > 0" is evaluated on the corner that minimises every rounded product -- IEEE rounding is
 // monotonic, so fl(fl(px+py)+pz)-d of that corner is the minimum over the 8 corners (NaN corners never fail the
 // reference's `<= 0` test, and fminf drops them the same way).
+#include "device_intrinsics.cuh"
 #include "device_types.cuh"
 #include "kernels.cuh"
 
@@ -308,8 +309,8 @@ __global__ void pack_palettes_kernel(const float4* __restrict__ palette, int pal
 cudaError_t launch_cull(const CullParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     const int64_t blocks = (p.n + 255) / 256;
-    if (p.position) cull_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p);
-    else cull_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    if (p.position) DMK_LAUNCH(cull_kernel<true>, (unsigned)blocks, 256, 0, stream)(p);
+    else DMK_LAUNCH(cull_kernel<false>, (unsigned)blocks, 256, 0, stream)(p);
     return cudaGetLastError();
 }
 
@@ -365,7 +366,7 @@ cudaError_t launch_bone_matrices(const float* models, const int16_t* first_child
                                  float half_turn_cos, float* out, cudaStream_t stream) {
     const int64_t threads = count * num_joints;
     if (threads <= 0) return cudaSuccess;
-    bone_matrices_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(models, first_child, num_joints, count, dir[0], dir[1], dir[2],
+    DMK_LAUNCH(bone_matrices_kernel, (unsigned)((threads + 127) / 128), 128, 0, stream)(models, first_child, num_joints, count, dir[0], dir[1], dir[2],
                                                                                 half_turn_sin, half_turn_cos, out);
     return cudaGetLastError();
 }
@@ -373,7 +374,7 @@ cudaError_t launch_bone_matrices(const float* models, const int16_t* first_child
 cudaError_t launch_transform_nodes(const float* pos, const float* rot, const float* scl, const int32_t* parent, int num_nodes, float* world,
                                    float* world_inverse, cudaStream_t stream) {
     if (num_nodes <= 0) return cudaSuccess;
-    transform_nodes_kernel<<<(num_nodes + 127) / 128, 128, 0, stream>>>(pos, rot, scl, parent, num_nodes, world, world_inverse);
+    DMK_LAUNCH(transform_nodes_kernel, (num_nodes + 127) / 128, 128, 0, stream)(pos, rot, scl, parent, num_nodes, world, world_inverse);
     return cudaGetLastError();
 }
 
@@ -387,16 +388,16 @@ cudaError_t launch_compact(const uint32_t* vis_bits, int64_t n, int32_t* ids_out
     if (n <= 0) return cudaMemsetAsync(count_out, 0, sizeof(int32_t), stream);
     const int64_t words = (n + 31) / 32;
     const int blocks = (int)((words + kScanBlock - 1) / kScanBlock);
-    compact_count_kernel<<<blocks, kScanBlock, 0, stream>>>(vis_bits, words, scratch);
-    compact_scan_kernel<<<1, 1024, 0, stream>>>(scratch, blocks, count_out);
-    compact_scatter_kernel<<<blocks, kScanBlock, 0, stream>>>(vis_bits, words, scratch, ids_out);
+    DMK_LAUNCH(compact_count_kernel, blocks, kScanBlock, 0, stream)(vis_bits, words, scratch);
+    DMK_LAUNCH(compact_scan_kernel, 1, 1024, 0, stream)(scratch, blocks, count_out);
+    DMK_LAUNCH(compact_scatter_kernel, blocks, kScanBlock, 0, stream)(vis_bits, words, scratch, ids_out);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }
 
 cudaError_t launch_pack_palettes(const float* palette, int palette_floats, const int32_t* ids, const int32_t* count,
                                  int64_t capacity, float* out, int num_sms, cudaStream_t stream) {
-    pack_palettes_kernel<<<num_sms * 4, 256, 0, stream>>>(reinterpret_cast<const float4*>(palette), palette_floats / 4, ids,
+    DMK_LAUNCH(pack_palettes_kernel, num_sms * 4, 256, 0, stream)(reinterpret_cast<const float4*>(palette), palette_floats / 4, ids,
                                                           count, capacity, reinterpret_cast<float4*>(out));
     return cudaGetLastError();
 }

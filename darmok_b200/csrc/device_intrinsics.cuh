@@ -1,0 +1,127 @@
+// device_intrinsics.cuh -- everything in the kernels that is not C++: the PTX wrappers (mbarrier, TMA bulk copy,
+// 128/256-bit shared and global accesses, system-scope acquire/release, %globaltimer), the dynamic shared-memory
+// declaration and the <<< >>> launch syntax.  The kernels only use these through the names below.
+//
+// tests/devsim/ builds the same kernel sources with g++ and runs them on the CPU in lockstep (one fiber per CUDA thread)
+// to check the kernels' indexing and hand-off protocols without a GPU; it defines DMK_DEVSIM and supplies these names
+// itself.  That build is test infrastructure under tests/: the product library is always the nvcc build of this branch.
+#pragma once
+
+#ifdef DMK_DEVSIM
+#include <dmk_devsim_intrinsics.hpp>
+#else
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+// kernel<<<grid, block, dynamic shared bytes, stream>>>(arguments...)  ==  DMK_LAUNCH(kernel, grid, block, bytes, stream)(arguments...)
+#define DMK_LAUNCH(kernel, grid, block, smem_bytes, stream) kernel<<<(grid), (block), (smem_bytes), (stream)>>>
+// the block's dynamic shared memory as `unsigned char name[]`
+#define DMK_DYNAMIC_SMEM(name, alignment) extern __shared__ __align__(alignment) unsigned char name[]
+
+namespace dmk {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait suspends the thread in hardware until the phase completes or a time limit passes; the spin bound
+    // turns a protocol bug into a trap instead of a hung GPU
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 22)) __trap();
+    } while (!done);
+}
+// mbarrier arrive (release at CTA scope): one arrival per warp after its lanes' shared-memory writes
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- wide global / shared accesses --------------------------------------------------------------------------------
+__device__ __forceinline__ void st_v8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void st_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_v8(const float* p, float* v) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void st_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// Predicated gather: an influence with zero weight contributes w * P = 0, so its rows are not fetched.  A quarter-warp
+// whose 8 lanes all skip costs no shared-memory wavefront (meshes whose vertices are grouped by influence count --
+// DMK_MESH_SORT_BY_INFLUENCES, or any mesh with spatially coherent skinning -- gather proportionally fewer bytes).
+__device__ __forceinline__ float4 lds128_if(uint32_t addr, uint32_t take) {
+    float4 v;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "setp.ne.u32 P1, %5, 0;\n"
+        "mov.f32 %0, 0f00000000;\n"
+        "mov.f32 %1, 0f00000000;\n"
+        "mov.f32 %2, 0f00000000;\n"
+        "mov.f32 %3, 0f00000000;\n"
+        "@P1 ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+        "}\n"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "r"(addr), "r"(take));
+    return v;
+}
+
+// ---- system scope (peer memory over NVLink) -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+}  // namespace
+}  // namespace dmk
+
+#endif  // DMK_DEVSIM

@@ -17,24 +17,12 @@
 // by frame f - 2); the owner reads frame f once published[r] >= f for every r.  Dependencies only point to earlier
 // frames, so the waits cannot form a cycle.  Every wait is bounded (globaltimer): on expiry the kernel raises the
 // error word and gives up instead of hanging the GPU.
+#include "device_intrinsics.cuh"
 #include "kernels.cuh"
 
 namespace dmk {
 namespace {
 
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t global_timer_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 // waits until *word has reached `need` (wrap-safe); false when `timeout_ns` passed first
 __device__ bool wait_reached(const uint32_t* word, uint32_t need, uint64_t timeout_ns) {
     if (static_cast<int32_t>(ld_acquire_sys(word) - need) >= 0) return true;
@@ -107,16 +95,16 @@ __global__ void release_frame_kernel(ExchangeHeader* hdr, uint32_t frame) {
 cudaError_t launch_push_palettes(const float* palette, int palette_floats, const int32_t* ids, const int32_t* count, int64_t capacity, float* slab,
                                  ExchangeHeader* hdr, int rank, uint32_t frame, uint32_t* done, uint32_t* local_error, uint64_t timeout_ns, int num_ctas,
                                  cudaStream_t stream) {
-    push_palettes_kernel<<<num_ctas, 256, 0, stream>>>(reinterpret_cast<const float4*>(palette), palette_floats / 4, ids, count, capacity,
+    DMK_LAUNCH(push_palettes_kernel, num_ctas, 256, 0, stream)(reinterpret_cast<const float4*>(palette), palette_floats / 4, ids, count, capacity,
                                                        reinterpret_cast<float4*>(slab), hdr, rank, frame, done, local_error, timeout_ns);
     return cudaGetLastError();
 }
 cudaError_t launch_wait_published(ExchangeHeader* hdr, int world, uint32_t frame, int32_t* counts_out, uint64_t timeout_ns, cudaStream_t stream) {
-    wait_published_kernel<<<1, kExchangeMaxRanks, 0, stream>>>(hdr, world, frame, counts_out, timeout_ns);
+    DMK_LAUNCH(wait_published_kernel, 1, kExchangeMaxRanks, 0, stream)(hdr, world, frame, counts_out, timeout_ns);
     return cudaGetLastError();
 }
 cudaError_t launch_release_frame(ExchangeHeader* hdr, uint32_t frame, cudaStream_t stream) {
-    release_frame_kernel<<<1, 1, 0, stream>>>(hdr, frame);
+    DMK_LAUNCH(release_frame_kernel, 1, 1, 0, stream)(hdr, frame);
     return cudaGetLastError();
 }
 

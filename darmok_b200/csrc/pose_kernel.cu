@@ -13,6 +13,7 @@
 // Data layout: key tracks are SoA per (clip, component, track) and shared by all characters (L1/L2 resident);
 // the per-skeleton tables (parents, level-order schedule, remap, inverse binds) are staged in shared memory once
 // per persistent block; hierarchy concatenation runs level by level, one (joint, column) task per lane.
+#include "device_intrinsics.cuh"
 #include "device_types.cuh"
 #include "kernels.cuh"
 
@@ -24,11 +25,6 @@ namespace {
 
 constexpr int kWarpsPerBlock = 4;   // maximum; skeletons with many joints run fewer warps per block (shared memory)
 constexpr int kMS = 13;  // shared-memory stride of a 3x4 matrix in floats: odd, so lanes on consecutive joints hit distinct banks
-
-__device__ __forceinline__ void st_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h)
-                 : "memory");
-}
 
 // 1/x and 1/sqrt(x) of the scalar reference (simd_ref RcpEst / RSqrtEst): correctly rounded reciprocal == 1.f / x
 __device__ __forceinline__ float rcp_exact(float x) { return __frcp_rn(x); }
@@ -413,15 +409,9 @@ __global__ void __launch_bounds__(DMK_SAMPLE_BLOCK, DMK_SAMPLE_MIN_BLOCKS) sampl
     st_v8(out + 8, m[8], m[9], m[10], m[11], 0.f, 0.f, 0.f, 0.f);
 }
 
-__device__ __forceinline__ void ld_v8(const float* p, float* v) {
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
-}
-
 // ---- K2 + K3: local-to-model and skin palette, one warp per character ------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) model_kernel(const PoseParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DMK_DYNAMIC_SMEM(smem_raw, 16);
     const int J = p.skel.num_joints, P = p.skel.padded_joints, K = p.arm.num_joints, PS = K + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -559,7 +549,7 @@ cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream, i
     if (p.n <= 0) return cudaSuccess;
     if (p.advance) {
         const int64_t total = p.n * p.num_layers;
-        advance_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+        DMK_LAUNCH(advance_kernel, (unsigned)((total + 255) / 256), 256, 0, stream)(p);
         if (launches) ++*launches;
     }
     {
@@ -568,10 +558,10 @@ cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream, i
         const unsigned grid = (unsigned)((total + kBlock - 1) / kBlock);
         const int shape = (p.clips.bucket_dir ? kBuckets : 0) | (p.key_indices ? kKeys : 0);
         switch (shape) {
-        case 0: sample_kernel<0><<<grid, kBlock, 0, stream>>>(p); break;
-        case kBuckets: sample_kernel<kBuckets><<<grid, kBlock, 0, stream>>>(p); break;
-        case kKeys: sample_kernel<kKeys><<<grid, kBlock, 0, stream>>>(p); break;
-        default: sample_kernel<kBuckets | kKeys><<<grid, kBlock, 0, stream>>>(p); break;
+        case 0: DMK_LAUNCH(sample_kernel<0>, grid, kBlock, 0, stream)(p); break;
+        case kBuckets: DMK_LAUNCH(sample_kernel<kBuckets>, grid, kBlock, 0, stream)(p); break;
+        case kKeys: DMK_LAUNCH(sample_kernel<kKeys>, grid, kBlock, 0, stream)(p); break;
+        default: DMK_LAUNCH(sample_kernel<kBuckets | kKeys>, grid, kBlock, 0, stream)(p); break;
         }
         if (launches) ++*launches;
     }
@@ -594,7 +584,7 @@ cudaError_t launch_model(const PoseParams& p, int num_sms, cudaStream_t stream, 
     int64_t blocks = (p.n + warps - 1) / warps;
     const int64_t cap = (int64_t)num_sms * per_sm;
     if (blocks > cap) blocks = cap;
-    model_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(p);
+    DMK_LAUNCH(model_kernel, (unsigned)blocks, warps * 32, smem, stream)(p);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -20,6 +20,7 @@
 //     whatever the bone indices are.
 //   * 8 vertices x 36 B = 288 B = 9 full 32-byte sectors per thread: results leave as 256-bit stores
 //     (st.global.v8.f32 -> STG.E.256), every store writing whole sectors.
+#include "device_intrinsics.cuh"
 #include "device_types.cuh"
 #include "kernels.cuh"
 
@@ -31,82 +32,6 @@ constexpr int kVPT = 8;           // vertices per thread: lcm(36 B, 32 B) / 36 B
 constexpr int kMaxThreads = 256;  // 8 warps = 2 per SM sub-partition (16K registers each): up to 255 registers per thread;
                                   // a 3rd warp per sub-partition (any block of 9..12 warps) would cap the kernel at 168
 constexpr int kRepl = 8;          // palette replicas = bank groups of a 16-byte access
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    // try_wait suspends the thread in hardware until the phase completes or a time limit passes; the spin bound
-    // turns a protocol bug into a trap instead of a hung GPU
-    uint32_t done = 0;
-    uint32_t spins = 0;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, P1;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (!done && ++spins > (1u << 22)) __trap();
-    } while (!done);
-}
-// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void st_v8(float* p, const float* v) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
-}
-
-__device__ __forceinline__ void st_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
-// Predicated gather: an influence with zero weight contributes w * P = 0, so its rows are not fetched.  A quarter-warp
-// whose 8 lanes all skip costs no shared-memory wavefront (meshes whose vertices are grouped by influence count --
-// DMK_MESH_SORT_BY_INFLUENCES, or any mesh with spatially coherent skinning -- gather proportionally fewer bytes).
-__device__ __forceinline__ float4 lds128_if(uint32_t addr, uint32_t take) {
-    float4 v;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "setp.ne.u32 P1, %5, 0;\n"
-        "mov.f32 %0, 0f00000000;\n"
-        "mov.f32 %1, 0f00000000;\n"
-        "mov.f32 %2, 0f00000000;\n"
-        "mov.f32 %3, 0f00000000;\n"
-        "@P1 ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
-        "}\n"
-        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-        : "r"(addr), "r"(take));
-    return v;
-}
-
-// mbarrier arrive (release at CTA scope): one arrival per warp after its lanes' shared-memory writes
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 constexpr int kNumRepl = 3;   // replica ring: fill(i+1) may overlap compute(i) and the slowest warp's compute(i-1)
 constexpr int kNumStage = 2;  // bulk-copy staging ring
@@ -153,7 +78,7 @@ __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
     static_assert(PLANAR ? VPT == 4 : VPT == 8, "interleaved output needs 8 vertices per thread (9 whole sectors); planar uses 4 (st.v4 per plane)");
     static_assert(!(PLANAR && STREAMS), "one output layout at a time");
     constexpr int kVPT = VPT;   // shadows the file-level constant inside this kernel
-    extern __shared__ __align__(128) unsigned char smem[];
+    DMK_DYNAMIC_SMEM(smem, 128);
     const int PS = p.palette_size;
     const uint32_t pal_bytes = (uint32_t)PS * 64u;             // staged palette: 3 rows of 4 floats + 1 pad row per slot
     const uint32_t repl_bytes = (uint32_t)PS * 48u * REPL;     // replicated: the 3 rows only
@@ -177,7 +102,7 @@ __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
     if (tid == 0) {
         for (int k = 0; k < kNumStage; ++k) mbar_init(&s_tma_bar[k], 1);
         for (int k = 0; k < kNumRepl; ++k) mbar_init(&s_full_bar[k], nwarps);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
 
@@ -380,7 +305,7 @@ cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t 
     return with_kernel(plan.replicas, p.skip_zero_weights != 0, plan.variant, [&](auto kernel) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (e != cudaSuccess) return e;
-        kernel<<<plan.grid, plan.threads, plan.smem, stream>>>(p);
+        DMK_LAUNCH(kernel, plan.grid, plan.threads, plan.smem, stream)(p);
         return cudaGetLastError();
     });
 }

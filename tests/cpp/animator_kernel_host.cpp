@@ -1,30 +1,11 @@
-// animator_kernel_host.cpp -- see animator_kernel_host.hpp.  The kernel source is included as it is; the CUDA qualifiers are
-// no-ops for a host compiler (cuda_runtime.h) and the handful of device intrinsics it uses get their IEEE meaning.
-#define DMK_ANIMATOR_HOST_TEST 1
-#include <cuda_runtime.h>
+// animator_kernel_host.cpp -- see animator_kernel_host.hpp.  The kernel source is compiled as it is for the CPU lockstep
+// simulator of tests/devsim (DMK_DEVSIM: one fiber per CUDA thread, blocks one after the other) and its three kernels are
+// LAUNCHED through it -- the block-level regrouping of animator_kernel (shared counters, barriers) runs as well as the
+// per-character tick.  Built with -ffp-contract=off, the device intrinsics have their IEEE meaning.
+#define DMK_DEVSIM 1
+#include <dmk_devsim_intrinsics.hpp>
 
-#include <algorithm>
-#include <cmath>
-#include <cstdint>
-#include <cstring>
 #include <stdexcept>
-
-namespace {
-inline float __fdiv_rn(float a, float b) { return a / b; }          // built with -ffp-contract=off: correctly rounded, like the intrinsic
-inline float __fsqrt_rn(float x) { return std::sqrt(x); }
-inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
-inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
-// only the block-level regrouping of animator_kernel (never run here) uses these
-struct Dim3 { unsigned x = 0, y = 0, z = 0; };
-Dim3 threadIdx, blockIdx, blockDim;
-inline int atomicAdd(int* p, int v) { const int o = *p; *p += v; return o; }
-inline void __syncthreads() {}
-using std::min;
-}  // namespace
-#undef __shared__
-#undef __launch_bounds__
-#define __shared__ static
-#define __launch_bounds__(...)
 
 #include "../../darmok_b200/csrc/animator_flatten.hpp"
 #include "../../darmok_b200/csrc/animator_kernel.cu"
@@ -90,8 +71,7 @@ Sim::Sim(const dmk_anim_state_def* states, int numStates, const dmk_anim_clip_de
     s.events.resize(N);
     std::memset(s.events.data(), 0xff, N * sizeof(dmk::AnimEvents));
     s.program.assign(N, dmk::PoseProgram{});
-    const dmk::AnimatorParams p = s.params(0.f);
-    for (int64_t c = 0; c < n; ++c) dmk::init_character(p, c, s.cmdSpeed.data(), s.blend.data(), s.speed.data());
+    dmk::launch_animator_init(s.params(0.f), s.cmdSpeed.data(), s.blend.data(), s.speed.data(), nullptr);
 }
 Sim::~Sim() = default;
 
@@ -107,8 +87,7 @@ void Sim::setInputs(const float* blendXY, const float* speed) {
     if (speed) std::copy(speed, speed + N, _impl->speed.begin());
 }
 void Sim::step(float dt) {
-    const dmk::AnimatorParams p = _impl->params(dt);
-    for (int64_t c = 0; c < _impl->n; ++c) dmk::tick_character(p, c);
+    dmk::launch_animator(_impl->params(dt), nullptr);
 }
 int Sim::layers() const { return _impl->layers; }
 void Sim::getEvents(dmk_anim_events* events, int32_t* status) const {
@@ -117,8 +96,7 @@ void Sim::getEvents(dmk_anim_events* events, int32_t* status) const {
     if (status) std::copy(_impl->status.begin(), _impl->status.end(), status);
 }
 void Sim::getState(dmk_anim_state* out) const {
-    const dmk::AnimatorParams p = _impl->params(0.f);
-    for (int64_t c = 0; c < _impl->n; ++c) dmk::query_character(p, c, reinterpret_cast<dmk::AnimStateInfo*>(out));
+    dmk::launch_animator_query(_impl->params(0.f), reinterpret_cast<dmk::AnimStateInfo*>(out), nullptr);
 }
 void Sim::getPrograms(int numLayers, int32_t* clip, float* ratio, float* weight, dmk_pose_program* programs) const {
     const size_t N = static_cast<size_t>(_impl->n), rows = static_cast<size_t>(std::min(numLayers, _impl->layers));

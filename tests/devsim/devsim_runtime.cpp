@@ -1,0 +1,394 @@
+// devsim_runtime.cpp -- TEST INFRASTRUCTURE (see dmk_devsim_intrinsics.hpp): the lockstep executor behind DMK_LAUNCH and a
+// stand-in for the few CUDA runtime calls darmok_b200/csrc/api.cu makes, with "device" memory on the host heap (so that
+// AddressSanitizer sees every kernel access).  Kernels run synchronously inside the launch call, blocks one after the
+// other, the threads of a block as fibers switched at blocking calls only.
+//
+// The library built from this refuses to create a context unless DMK_DEVSIM=1 is set in the environment: it can never be
+// mistaken for, or silently stand in for, the CUDA build.
+#include "dmk_devsim_intrinsics.hpp"
+
+#include <sys/mman.h>
+#include <ucontext.h>
+
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define DEVSIM_ASAN 1
+#else
+#define DEVSIM_ASAN 0
+#endif
+
+namespace devsim {
+
+uint3 g_thread_idx, g_block_idx;
+dim3 g_block_dim, g_grid_dim;
+
+namespace {
+
+constexpr size_t kStackBytes = 256 * 1024;
+constexpr int kMaxThreads = 1024;
+
+struct Fiber {
+    ucontext_t ctx;
+    uint3 tid;
+    int linear = 0;
+    bool done = false;
+    bool blocked = false;   // last yield was a wait only another fiber can end
+};
+
+struct Warp {
+    int live = 0, arrived = 0;
+    unsigned generation = 0;
+    uint32_t slot[32];
+    bool alive[32];
+};
+
+struct Block {
+    std::vector<Fiber> fibers;
+    std::vector<Warp> warps;
+    int live = 0, arrived = 0;
+    unsigned generation = 0;
+    unsigned char* smem = nullptr;
+    size_t smem_bytes = 0;
+    uint64_t progress = 0;
+};
+
+ucontext_t g_scheduler;
+Fiber* g_cur = nullptr;
+Block* g_block = nullptr;
+const std::function<void()>* g_body = nullptr;
+unsigned char* g_stacks = nullptr;
+std::string g_kernel_note;
+
+void switch_to_scheduler() {
+#if DEVSIM_ASAN
+    void* fake = nullptr;
+    __sanitizer_start_switch_fiber(&fake, nullptr, 0);   // scheduler runs on the thread's own stack
+    swapcontext(&g_cur->ctx, &g_scheduler);
+    __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#else
+    swapcontext(&g_cur->ctx, &g_scheduler);
+#endif
+}
+
+void release_block_barrier_if_complete(Block& b) {
+    if (b.live > 0 && b.arrived == b.live) {
+        b.arrived = 0;
+        ++b.generation;
+        ++b.progress;
+    }
+}
+void release_warp_barrier_if_complete(Block& b, Warp& w) {
+    if (w.live > 0 && w.arrived == w.live) {
+        w.arrived = 0;
+        ++w.generation;
+        ++b.progress;
+    }
+}
+
+void fiber_entry() {
+#if DEVSIM_ASAN
+    __sanitizer_finish_switch_fiber(nullptr, nullptr, nullptr);
+#endif
+    (*g_body)();
+    Fiber* f = g_cur;
+    Block& b = *g_block;
+    f->done = true;
+    Warp& w = b.warps[static_cast<size_t>(f->linear >> 5)];
+    w.alive[f->linear & 31] = false;
+    --w.live;
+    --b.live;
+    ++b.progress;
+    // a thread that has exited no longer takes part in barriers
+    release_warp_barrier_if_complete(b, w);
+    release_block_barrier_if_complete(b);
+#if DEVSIM_ASAN
+    void* fake = nullptr;
+    __sanitizer_start_switch_fiber(nullptr, nullptr, 0);   // this fiber never resumes
+    (void)fake;
+#endif
+    swapcontext(&f->ctx, &g_scheduler);
+    std::abort();
+}
+
+}  // namespace
+
+[[noreturn]] void trap(const char* why) {
+    std::fprintf(stderr, "devsim: %s (block %u,%u thread %u of %u)\n", why, g_block_idx.x, g_block_idx.y, g_thread_idx.x, g_block_dim.x);
+    std::fflush(stderr);
+    std::abort();
+}
+
+uint64_t now_ns() {
+    return static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count());
+}
+
+void note_progress() {
+    if (g_block) ++g_block->progress;
+}
+void yield_blocked() {
+    if (!g_cur) trap("blocking call outside a kernel");
+    g_cur->blocked = true;
+    switch_to_scheduler();
+}
+void yield_sleep() {
+    if (!g_cur) trap("blocking call outside a kernel");
+    g_cur->blocked = false;
+    ++g_block->progress;
+    switch_to_scheduler();
+}
+
+void sync_threads() {
+    Block& b = *g_block;
+    const unsigned gen = b.generation;
+    ++b.arrived;
+    release_block_barrier_if_complete(b);
+    while (b.generation == gen) yield_blocked();
+}
+void sync_warp() {
+    Block& b = *g_block;
+    Warp& w = b.warps[static_cast<size_t>(g_cur->linear >> 5)];
+    const unsigned gen = w.generation;
+    ++w.arrived;
+    release_warp_barrier_if_complete(b, w);
+    while (w.generation == gen) yield_blocked();
+}
+uint32_t warp_exchange(uint32_t mine, int src_lane) {
+    Warp& w = g_block->warps[static_cast<size_t>(g_cur->linear >> 5)];
+    const int lane = g_cur->linear & 31;
+    w.slot[lane] = mine;
+    sync_warp();
+    const uint32_t got = (src_lane >= 0 && src_lane < 32 && w.alive[src_lane]) ? w.slot[src_lane] : mine;
+    sync_warp();   // nobody overwrites a slot before everybody has read
+    return got;
+}
+uint32_t warp_ballot(bool pred) {
+    Warp& w = g_block->warps[static_cast<size_t>(g_cur->linear >> 5)];
+    const int lane = g_cur->linear & 31;
+    w.slot[lane] = pred ? 1u : 0u;
+    sync_warp();
+    uint32_t bits = 0;
+    for (int l = 0; l < 32; ++l)
+        if (w.alive[l] && w.slot[l]) bits |= 1u << l;
+    sync_warp();
+    return bits;
+}
+
+unsigned char* dynamic_smem() { return g_block ? g_block->smem : nullptr; }
+size_t dynamic_smem_bytes() { return g_block ? g_block->smem_bytes : 0; }
+
+void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& thread_body) {
+    if (g_block) trap("nested kernel launch");
+    const size_t nthreads = static_cast<size_t>(block.x) * block.y * block.z;
+    if (nthreads == 0 || nthreads > kMaxThreads) trap("launch: block size outside [1, 1024]");
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0) trap("launch: empty grid");
+    if (smem_bytes > 227 * 1024) trap("launch: more than 227 KB of dynamic shared memory");
+    if (!g_stacks) {
+        g_stacks = static_cast<unsigned char*>(mmap(nullptr, kStackBytes * kMaxThreads, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0));
+        if (g_stacks == MAP_FAILED) trap("cannot map fiber stacks");
+    }
+    g_body = &thread_body;
+    g_grid_dim = grid;
+    g_block_dim = block;
+    Block b;
+    g_block = &b;
+    b.fibers.resize(nthreads);
+    b.warps.resize((nthreads + 31) / 32);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                g_block_idx = uint3{bx, by, bz};
+                // a fresh heap block per CTA: AddressSanitizer sees accesses past the dynamic shared memory the launch asked for
+                b.smem_bytes = smem_bytes;
+                b.smem = nullptr;
+                if (smem_bytes) {
+                    void* m = nullptr;
+                    if (posix_memalign(&m, 1024, smem_bytes) != 0) trap("out of memory for a block's shared memory");
+                    b.smem = static_cast<unsigned char*>(m);
+                    std::memset(b.smem, 0xcd, smem_bytes);
+                }
+                b.live = static_cast<int>(nthreads);
+                b.arrived = 0;
+                for (auto& w : b.warps) {
+                    w.live = 0;
+                    w.arrived = 0;
+                    for (int l = 0; l < 32; ++l) { w.alive[l] = false; w.slot[l] = 0; }
+                }
+                for (size_t t = 0; t < nthreads; ++t) {
+                    Fiber& f = b.fibers[t];
+                    f.linear = static_cast<int>(t);
+                    f.tid = uint3{static_cast<unsigned>(t % block.x), static_cast<unsigned>((t / block.x) % block.y),
+                                  static_cast<unsigned>(t / (static_cast<size_t>(block.x) * block.y))};
+                    f.done = false;
+                    f.blocked = false;
+                    getcontext(&f.ctx);
+                    f.ctx.uc_stack.ss_sp = g_stacks + t * kStackBytes;
+                    f.ctx.uc_stack.ss_size = kStackBytes;
+                    f.ctx.uc_link = nullptr;
+                    makecontext(&f.ctx, fiber_entry, 0);
+                    Warp& w = b.warps[t >> 5];
+                    w.alive[t & 31] = true;
+                    ++w.live;
+                }
+                int idle_rounds = 0;
+                while (b.live > 0) {
+                    const uint64_t before = b.progress;
+                    bool all_blocked = true;
+                    for (size_t t = 0; t < nthreads; ++t) {
+                        Fiber& f = b.fibers[t];
+                        if (f.done) continue;
+                        g_cur = &f;
+                        g_thread_idx = f.tid;
+                        f.blocked = false;
+#if DEVSIM_ASAN
+                        void* fake = nullptr;
+                        __sanitizer_start_switch_fiber(&fake, f.ctx.uc_stack.ss_sp, f.ctx.uc_stack.ss_size);
+                        swapcontext(&g_scheduler, &f.ctx);
+                        __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#else
+                        swapcontext(&g_scheduler, &f.ctx);
+#endif
+                        if (!f.done && !f.blocked) all_blocked = false;
+                    }
+                    g_cur = nullptr;
+                    if (b.live > 0 && all_blocked && b.progress == before) {
+                        if (++idle_rounds > 4) trap("deadlock: every live thread of the block waits and nothing changes");
+                    } else {
+                        idle_rounds = 0;
+                    }
+                }
+                std::free(b.smem);
+                b.smem = nullptr;
+            }
+    g_block = nullptr;
+    g_body = nullptr;
+}
+
+}  // namespace devsim
+
+// ======================================================================================================================
+// CUDA runtime stand-in: exactly the calls api.cu makes.  One device ("B200", 148 SMs, sm_100), memory on the heap,
+// streams and events are tokens (everything is synchronous).
+// ======================================================================================================================
+namespace {
+bool devsim_enabled() {
+    const char* e = std::getenv("DMK_DEVSIM");
+    return e && e[0] == '1';
+}
+struct EventImpl { uint64_t t_ns = 0; };
+int g_stream_token;
+}  // namespace
+
+extern "C" {
+
+cudaError_t cudaGetDeviceCount(int* count) {
+    *count = devsim_enabled() ? 1 : 0;   // without the switch this library has no device: dmk_context_create fails
+    return cudaSuccess;
+}
+cudaError_t cudaSetDevice(int device) { return device == 0 && devsim_enabled() ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* prop, int device) {
+    if (device != 0) return cudaErrorInvalidDevice;
+    std::memset(prop, 0, sizeof *prop);
+    std::snprintf(prop->name, sizeof prop->name, "devsim (CPU lockstep simulator, not a GPU)");
+    prop->major = 10;
+    prop->minor = 0;
+    prop->multiProcessorCount = 148;
+    prop->sharedMemPerBlockOptin = 227 * 1024;
+    prop->warpSize = 32;
+    return cudaSuccess;
+}
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "devsim runtime error"; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+
+cudaError_t cudaMalloc(void** p, size_t bytes) {
+    // cudaMalloc's 256-byte alignment, but the exact size: ASan flags any access past the end
+    if (posix_memalign(p, 256, bytes ? bytes : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    std::memset(*p, 0xcd, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) {
+    std::free(p);
+    return cudaSuccess;
+}
+cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned int) {
+    *p = std::malloc(bytes ? bytes : 1);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFreeHost(void* p) {
+    std::free(p);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) {
+    if (bytes) std::memmove(dst, src, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < height; ++r) std::memmove(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
+    return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t) {
+    if (bytes) std::memset(p, value, bytes);
+    return cudaSuccess;
+}
+
+cudaError_t cudaStreamCreate(cudaStream_t* s) {
+    *s = reinterpret_cast<cudaStream_t>(&g_stream_token);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned int) { return cudaStreamCreate(s); }
+cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+
+cudaError_t cudaEventCreate(cudaEvent_t* e) {
+    *e = reinterpret_cast<cudaEvent_t>(new EventImpl());
+    return cudaSuccess;
+}
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned int) { return cudaEventCreate(e); }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+    reinterpret_cast<EventImpl*>(e)->t_ns = devsim::now_ns();
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = static_cast<float>(static_cast<double>(reinterpret_cast<EventImpl*>(b)->t_ns - reinterpret_cast<EventImpl*>(a)->t_ns) * 1e-6);
+    return cudaSuccess;
+}
+cudaError_t cudaEventDestroy(cudaEvent_t e) {
+    delete reinterpret_cast<EventImpl*>(e);
+    return cudaSuccess;
+}
+
+cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* blocks, const void*, int, size_t) {
+    *blocks = 1;
+    return cudaSuccess;
+}
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* blocks, const void*, int, size_t, unsigned int) {
+    *blocks = 1;
+    return cudaSuccess;
+}
+
+// "IPC" within the one process: the handle carries the pointer
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* handle, void* p) {
+    std::memset(handle, 0, sizeof *handle);
+    std::memcpy(handle, &p, sizeof p);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t handle, unsigned int) {
+    std::memcpy(p, &handle, sizeof *p);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) {
+    *can = 1;
+    return cudaSuccess;
+}
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned int) { return cudaSuccess; }
+
+}  // extern "C"
