@@ -8,7 +8,9 @@
 #include "dmk_devsim_intrinsics.hpp"
 
 #include <sys/mman.h>
+#if !defined(__x86_64__)
 #include <ucontext.h>
+#endif
 
 #include <chrono>
 #include <map>
@@ -33,8 +35,71 @@ namespace {
 constexpr size_t kStackBytes = 256 * 1024;
 constexpr int kMaxThreads = 1024;
 
+// Fiber switch.  x86-64: six callee-saved registers + the floating-point control words and the stack pointer, no system call
+// (swapcontext saves the signal mask with one per switch, which dominated the run time); elsewhere: ucontext.
+#if defined(__x86_64__)
+struct Context {
+    void* sp = nullptr;
+};
+extern "C" void devsim_switch_context(void** save_sp, void* load_sp);
+asm(R"(
+    .text
+    .globl devsim_switch_context
+    .hidden devsim_switch_context
+    .type devsim_switch_context,@function
+devsim_switch_context:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    subq $8, %rsp
+    stmxcsr (%rsp)
+    fnstcw 4(%rsp)
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    ldmxcsr (%rsp)
+    fldcw 4(%rsp)
+    addq $8, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size devsim_switch_context,.-devsim_switch_context
+)");
+void prepare_context(Context& c, unsigned char* stack, size_t bytes, void (*entry)()) {
+    // stack as devsim_switch_context leaves it: {mxcsr, x87 cw}, r15, r14, r13, r12, rbx, rbp, return address (= entry), and
+    // above it the slot a caller's return address would occupy: entry starts with rsp % 16 == 8 as the ABI has it after a call
+    uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + bytes) & ~uintptr_t(15);
+    uint64_t* sp = reinterpret_cast<uint64_t*>(top);
+    *--sp = 0;                                        // return address of entry: never used, entry does not return
+    *--sp = reinterpret_cast<uint64_t>(entry);        // popped by ret
+    for (int k = 0; k < 6; ++k) *--sp = 0;            // rbp, rbx, r12..r15
+    *--sp = 0x0000037f00001f80ull;                    // mxcsr = 0x1f80 (low word), x87 control word = 0x037f
+    c.sp = sp;
+}
+inline void switch_context(Context& from, Context& to) { devsim_switch_context(&from.sp, to.sp); }
+#else
+struct Context {
+    ucontext_t uc;
+};
+void prepare_context(Context& c, unsigned char* stack, size_t bytes, void (*entry)()) {
+    getcontext(&c.uc);
+    c.uc.uc_stack.ss_sp = stack;
+    c.uc.uc_stack.ss_size = bytes;
+    c.uc.uc_link = nullptr;
+    makecontext(&c.uc, entry, 0);
+}
+inline void switch_context(Context& from, Context& to) { swapcontext(&from.uc, &to.uc); }
+#endif
+
 struct Fiber {
-    ucontext_t ctx;
+    Context ctx;
+    unsigned char* stack = nullptr;
     uint3 tid;
     int linear = 0;
     bool done = false;
@@ -58,7 +123,11 @@ struct Block {
     uint64_t progress = 0;
 };
 
-ucontext_t g_scheduler;
+Context g_scheduler;
+#if DEVSIM_ASAN
+const void* g_main_stack_bottom = nullptr;
+size_t g_main_stack_size = 0;
+#endif
 Fiber* g_cur = nullptr;
 Block* g_block = nullptr;
 const std::function<void()>* g_body = nullptr;
@@ -68,11 +137,11 @@ std::string g_kernel_note;
 void switch_to_scheduler() {
 #if DEVSIM_ASAN
     void* fake = nullptr;
-    __sanitizer_start_switch_fiber(&fake, nullptr, 0);   // scheduler runs on the thread's own stack
-    swapcontext(&g_cur->ctx, &g_scheduler);
+    __sanitizer_start_switch_fiber(&fake, g_main_stack_bottom, g_main_stack_size);   // the scheduler runs on the thread's own stack
+    switch_context(g_cur->ctx, g_scheduler);
     __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
 #else
-    swapcontext(&g_cur->ctx, &g_scheduler);
+    switch_context(g_cur->ctx, g_scheduler);
 #endif
 }
 
@@ -93,7 +162,7 @@ void release_warp_barrier_if_complete(Block& b, Warp& w) {
 
 void fiber_entry() {
 #if DEVSIM_ASAN
-    __sanitizer_finish_switch_fiber(nullptr, nullptr, nullptr);
+    __sanitizer_finish_switch_fiber(nullptr, &g_main_stack_bottom, &g_main_stack_size);
 #endif
     (*g_body)();
     Fiber* f = g_cur;
@@ -108,11 +177,9 @@ void fiber_entry() {
     release_warp_barrier_if_complete(b, w);
     release_block_barrier_if_complete(b);
 #if DEVSIM_ASAN
-    void* fake = nullptr;
-    __sanitizer_start_switch_fiber(nullptr, nullptr, 0);   // this fiber never resumes
-    (void)fake;
+    __sanitizer_start_switch_fiber(nullptr, g_main_stack_bottom, g_main_stack_size);   // null save slot: this fiber never resumes
 #endif
-    swapcontext(&f->ctx, &g_scheduler);
+    switch_context(f->ctx, g_scheduler);
     std::abort();
 }
 
@@ -226,11 +293,8 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void
                                   static_cast<unsigned>(t / (static_cast<size_t>(block.x) * block.y))};
                     f.done = false;
                     f.blocked = false;
-                    getcontext(&f.ctx);
-                    f.ctx.uc_stack.ss_sp = g_stacks + t * kStackBytes;
-                    f.ctx.uc_stack.ss_size = kStackBytes;
-                    f.ctx.uc_link = nullptr;
-                    makecontext(&f.ctx, fiber_entry, 0);
+                    f.stack = g_stacks + t * kStackBytes;
+                    prepare_context(f.ctx, f.stack, kStackBytes, fiber_entry);
                     Warp& w = b.warps[t >> 5];
                     w.alive[t & 31] = true;
                     ++w.live;
@@ -247,11 +311,11 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void
                         f.blocked = false;
 #if DEVSIM_ASAN
                         void* fake = nullptr;
-                        __sanitizer_start_switch_fiber(&fake, f.ctx.uc_stack.ss_sp, f.ctx.uc_stack.ss_size);
-                        swapcontext(&g_scheduler, &f.ctx);
+                        __sanitizer_start_switch_fiber(&fake, f.stack, kStackBytes);
+                        switch_context(g_scheduler, f.ctx);
                         __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
 #else
-                        swapcontext(&g_scheduler, &f.ctx);
+                        switch_context(g_scheduler, f.ctx);
 #endif
                         if (!f.done && !f.blocked) all_blocked = false;
                     }

@@ -18,18 +18,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from darmok_b200 import capi, synth  # noqa: E402
-
-
-class _Dev:
-    """__cuda_array_interface__ view of library-owned device memory"""
-
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+from tests import devmem  # noqa: E402
 
 
 def main():
-    import torch
-    dev = torch.device("cuda", 0)
     tiny = float(np.finfo(np.float32).tiny)
     skel_s = synth.make_skeleton(67)
     clips_s = [synth.make_clip(skel_s, f"clip{i}", seed=i) for i in range(3)]
@@ -70,8 +62,8 @@ def main():
         owner.wait(frame)
         slab_ptr, counts_ptr = owner.frame_dev(frame)
         ctx.sync()
-        slab = torch.as_tensor(_Dev(slab_ptr, (world, capacity, ps, 16), "<f4"), device=dev).cpu().numpy()
-        counts = torch.as_tensor(_Dev(counts_ptr, (world,), "<i4"), device=dev).cpu().numpy()
+        slab = devmem.read(slab_ptr, (world, capacity, ps, 16))
+        counts = devmem.read(counts_ptr, (world,), np.int32)
         for r in range(world):
             assert counts[r] == len(expect[r]), f"frame {frame} rank {r}: count {counts[r]} != {len(expect[r])}"
             assert np.array_equal(slab[r, :counts[r]], expect[r]), f"frame {frame} rank {r}: palettes differ"

@@ -18,19 +18,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from darmok_b200 import capi, synth  # noqa: E402
-from tests import common  # noqa: E402
+from tests import common, devmem  # noqa: E402
 from tests.common import FLT_MIN, assert_close  # noqa: E402
 
 
-class _Dev:
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
 def main():
-    import torch
     from oracle import oracle_py as O
-    dev = torch.device("cuda", 0)
     base = common.default_assets()
     oskel = O.Skeleton(base.skel.archive)
     oclips = [O.Animation(c.archive) for c in base.clips]
@@ -60,21 +53,19 @@ def main():
         vpad = (num_vertices + 7) // 8 * 8
         for variant in (1, 2, 3):
             crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
-            torch.as_tensor(_Dev(crowd.skinned_dev(), (n * vpad * 9,), "<f4"), device=dev).fill_(float("nan"))
-            torch.cuda.synchronize()   # torch's stream is not the context's: the fill must have landed before the step
+            devmem.fill_f32(crowd.skinned_dev(), n * vpad * 9, float("nan"))
             crowd.step(0.0, capi.STEP_SKIN)
             got = crowd.get_skinned()
             assert np.array_equal(got, reference), f"variant {variant} V={num_vertices}: differs from the default kernel"
             if variant == 3:   # three float3 streams
-                streams = torch.as_tensor(_Dev(crowd.skinned_dev(), (n, 3, vpad, 3), "<f4"), device=dev).cpu().numpy()
+                streams = devmem.read(crowd.skinned_dev(), (n, 3, vpad, 3))
                 assert np.array_equal(streams[:, :, :num_vertices].transpose(0, 2, 1, 3).reshape(n, num_vertices, 9), reference), \
                     "variant 3: device layout is not [N][3][pitch][3]"
             else:
-                planes = torch.as_tensor(_Dev(crowd.skinned_dev(), (n, 9, vpad), "<f4"), device=dev).cpu().numpy()
+                planes = devmem.read(crowd.skinned_dev(), (n, 9, vpad))
                 assert np.array_equal(planes[:, :, :num_vertices].transpose(0, 2, 1), reference), f"variant {variant}: device layout is not [N][9][pitch]"
             # only the visible characters
-            torch.as_tensor(_Dev(crowd.skinned_dev(), (n * vpad * 9,), "<f4"), device=dev).fill_(float("nan"))
-            torch.cuda.synchronize()   # torch's stream is not the context's: the fill must have landed before the step
+            devmem.fill_f32(crowd.skinned_dev(), n * vpad * 9, float("nan"))
             crowd.step(0.0, capi.STEP_SKIN | capi.STEP_SKIN_VISIBLE_ONLY)
             got = crowd.get_skinned()
             assert np.array_equal(got[visible], reference[visible]) and np.isnan(got[~visible]).all(), f"variant {variant}: visible-only"

@@ -1,0 +1,107 @@
+"""The kernels' own source on the CPU (tests/devsim): darmok_b200/csrc/*.cu built with g++ for a lockstep simulator -- one
+fiber per CUDA thread, emulated mbarrier / bulk copy / warp collectives, "device" and shared memory as exact-size heap blocks --
+behind the unchanged host side of the C ABI (api.cu).  The GPU parity tests then run against that build without a GPU.
+
+What it is for: the index arithmetic and the hand-off protocols of the kernels (a wrong tile bound, a replica ring reused too
+early, a barrier some thread never reaches) show up here as a wrong result, an AddressSanitizer report naming the kernel source
+line, or a "deadlock" abort -- before GPU time is spent, and on a pool whose compute-sanitizer is closed.  What it is not: a
+fallback (the library refuses to make a context without DMK_DEVSIM=1 and lives under tests/), a performance model, or a memory
+model check (fibers only interleave at blocking calls).  The `-m gpu` tests on the B200 remain the parity evidence.
+"""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from tests.test_host_shim import assets_dir  # noqa: F401  (fixture: the shim scenario's assets)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEVSIM = os.path.join(ROOT, "tests", "devsim")
+LIB = os.path.join(DEVSIM, "_build", "libdarmok_b200_devsim.so")
+LIB_ASAN = os.path.join(DEVSIM, "_build", "libdarmok_b200_devsim_asan.so")
+
+# not on the simulator: the full-size crowds (hours of fibers), the tests whose C++ binary links the CUDA build (their
+# simulator twin is test_host_shim_device_scenarios_on_the_simulator below) and the two-process CUDA IPC check
+DESELECT = ["tests/test_gpu_fullsize.py", "tests/test_host_shim.py", "tests/test_shim_extras_gpu.py",
+            "tests/test_gpu_zz_peer_exchange.py::test_peer_exchange_two_processes_over_cuda_ipc"]
+
+
+@pytest.fixture(scope="module")
+def libs():
+    from oracle import oracle_py
+    oracle_py.build()
+    r = subprocess.run(["make", "-C", DEVSIM, "-j8", "all", "asan"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return LIB, LIB_ASAN
+
+
+def _env(lib, asan=False):
+    env = dict(os.environ, DMK_DEVSIM="1", DMK_LIBRARY=lib, DMK_GOLDEN_DIR=os.path.join(ROOT, "tests", "golden"))
+    if asan:
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        pre = [subprocess.run([cc, f"-print-file-name={n}"], capture_output=True, text=True).stdout.strip() for n in ("libasan.so", "libubsan.so")]
+        env.update(LD_PRELOAD=":".join(pre), ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    return env
+
+
+def _clean(r):
+    return "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr and "devsim:" not in r.stderr
+
+
+def _pytest(env, *args):
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", *args]
+    for d in DESELECT:
+        cmd += ["--deselect", d]
+    return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+
+
+def test_library_has_no_device_without_the_switch(libs):
+    # the simulator build can not stand in for the CUDA build by accident
+    env = _env(libs[0])
+    del env["DMK_DEVSIM"]
+    r = subprocess.run([sys.executable, "-c", "from darmok_b200 import capi; capi.Context(0)"], cwd=ROOT, env=env, capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr, r.stderr[-1500:]
+
+
+def test_smoke_on_the_simulator(libs):
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=_env(libs[0]), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "smoke ok" in r.stdout and _clean(r), r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_gpu_parity_suite_on_the_simulator(libs):
+    # every `-m gpu` test that fits: pose (key indices, clocks, locals, models, palette), skinning, cull + compaction, transform
+    # hierarchy, device animators, several skins per character, zero groups, the planar / three-stream skinning shapes and the
+    # peer-memory exchange with three logical ranks
+    r = _pytest(_env(libs[0]), "tests")
+    tail = r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and _clean(r), tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 50, tail
+    assert "failed" not in r.stdout.splitlines()[-1], tail
+
+
+def test_host_shim_device_scenarios_on_the_simulator(libs, assets_dir):  # noqa: F811
+    # tests/cpp/animator_test.cpp linked against the simulator build: SkeletalAnimator / scene component / device animators
+    # against the reference animator (mode gpu) and the second skin + load / reload (mode gpuextras)
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "animator_test_devsim"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    exe = os.path.join(ROOT, "tests", "cpp", "animator_test_devsim")
+    for mode, expect in (("gpu", "gpu: 0 failures"), ("gpuextras", " 0 failures")):
+        r = subprocess.run([exe, assets_dir, mode], env=_env(libs[0]), capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and expect in r.stdout and _clean(r), r.stdout[-2500:] + r.stderr[-2000:]
+
+
+def test_kernels_are_clean_under_address_and_ub_sanitizers(libs):
+    # every load and store of the kernels against exact-size heap blocks (device buffers, one block per CTA for the dynamic shared
+    # memory): the frame of smoke(), all skinning shapes at ragged vertex counts, the exchange, several skins, zero groups
+    env = _env(libs[1], asan=True)
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "smoke ok" in r.stdout and _clean(r), r.stdout[-1500:] + r.stderr[-4000:]
+    for script, expect in (("skin_planar_check.py", "bit-identical to the default kernel"), ("peer_exchange_check.py", "gives up on a rank that never publishes")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script)], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0 and expect in r.stdout and _clean(r), r.stdout[-1500:] + r.stderr[-4000:]
+    r = _pytest(env, "tests/test_multi_skin_gpu.py", "tests/test_pose_zero_gpu.py", "tests/test_gpu_skin.py", "tests/test_gpu_pose.py")
+    assert r.returncode == 0 and _clean(r), r.stdout[-3000:] + r.stderr[-4000:]

@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from tests.common import GpuRig
+from tests.devmem import DeviceArray
 from darmok_b200 import capi, synth
 from oracle import oracle_py as O
 
@@ -84,13 +85,12 @@ def test_crowd_cull_and_visible_id_compaction(assets):
         assert np.array_equal(bits, ref)
         vis = capi.bits_to_bool(bits, n)
         assert count == vis.sum() and 0 < count < n
-        # the compacted ids + packed palettes (payload of the multi-GPU gather) through torch device memory
-        import torch
-        out = torch.zeros((count, 68, 16), dtype=torch.float32, device="cuda")
-        crowd.pack_visible_palettes(out.data_ptr(), count)
+        # the compacted ids + packed palettes (payload of the multi-GPU gather) into caller-owned device memory
+        out = DeviceArray.zeros((count, 68, 16), np.float32)
+        crowd.pack_visible_palettes(out.ptr, count)
         g.ctx.sync()
         pal = crowd.get_palette()
-        assert np.array_equal(out.cpu().numpy(), pal[np.nonzero(vis)[0]])
+        assert np.array_equal(out.numpy(), pal[np.nonzero(vis)[0]])
     finally:
         g.close()
 
@@ -98,7 +98,6 @@ def test_crowd_cull_and_visible_id_compaction(assets):
 def test_transform_update_on_device_world_inverse_and_visibility():
     # Transform::update (src/transform.cpp:286-309) fused into the cull: world inverse from
     # position / rotation / scale in glm order, visibility bit-exact, matrices identical to the oracle's
-    import torch
     n = 200_003
     tr = synth.make_transforms(n, seed=9, extent=150.0)
     vp = synth.sample_camera_view_proj()
@@ -106,14 +105,13 @@ def test_transform_update_on_device_world_inverse_and_visibility():
     ref_bits, ref_wi = O.cull_batch_trs(corners, tr.position, tr.rotation, tr.scale, tr.bbox, want_world_inverse=True)
     c = capi.Context(0)
     try:
-        dev = [torch.from_numpy(a).cuda() for a in (tr.position, tr.rotation, tr.scale, tr.bbox)]
-        bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
-        wi = torch.zeros((n, 16), dtype=torch.float32, device="cuda")
-        torch.cuda.synchronize()
-        c.cull_trs_dev(corners, *[d.data_ptr() for d in dev], n, bits.data_ptr(), wi.data_ptr())
+        dev = [DeviceArray(a) for a in (tr.position, tr.rotation, tr.scale, tr.bbox)]
+        bits = DeviceArray.zeros((n + 31) // 32, np.int32)
+        wi = DeviceArray.zeros((n, 16), np.float32)
+        c.cull_trs_dev(corners, *[d.ptr for d in dev], n, bits.ptr, wi.ptr)
         c.sync()
-        assert np.array_equal(bits.cpu().numpy().view(np.uint32), ref_bits)
-        assert np.array_equal(wi.cpu().numpy(), ref_wi)       # same operation order, no contraction: identical matrices
+        assert np.array_equal(bits.numpy().view(np.uint32), ref_bits)
+        assert np.array_equal(wi.numpy(), ref_wi)             # same operation order, no contraction: identical matrices
         vis = capi.bits_to_bool(ref_bits, n)
         assert 0 < vis.sum() < n
     finally:
