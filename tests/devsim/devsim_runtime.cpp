@@ -113,7 +113,16 @@ struct Warp {
     bool alive[32];
 };
 
+struct PendingCopy {   // a bulk copy in flight (DMK_DEVSIM_SEED: it lands some scheduler rounds after its issue)
+    void* dst;
+    const void* src;
+    uint32_t bytes;
+    MBar* bar;
+    int rounds_left;
+};
+
 struct Block {
+    std::vector<PendingCopy> copies;
     std::vector<Fiber> fibers;
     std::vector<Warp> warps;
     int live = 0, arrived = 0;
@@ -132,7 +141,31 @@ Fiber* g_cur = nullptr;
 Block* g_block = nullptr;
 const std::function<void()>* g_body = nullptr;
 unsigned char* g_stacks = nullptr;
-std::string g_kernel_note;
+
+// DMK_DEVSIM_SEED=<n>, n != 0: instead of the fixed round-robin, every scheduler round runs the warps in a random order and leaves
+// each one out with probability 1/2 (warps drift apart by many rounds), and bulk copies land 0..3 rounds after their issue
+uint64_t g_rng = 0;
+bool g_random_schedule = false, g_skip_warp = false;
+uint32_t next_random() {   // xorshift64*
+    g_rng ^= g_rng >> 12;
+    g_rng ^= g_rng << 25;
+    g_rng ^= g_rng >> 27;
+    return static_cast<uint32_t>((g_rng * 0x2545F4914F6CDD1Dull) >> 32);
+}
+void read_schedule_options() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char* e = std::getenv("DMK_DEVSIM_SEED");
+    const uint64_t seed = e ? std::strtoull(e, nullptr, 10) : 0;
+    g_random_schedule = seed != 0;
+    g_rng = seed * 0x9E3779B97F4A7C15ull + 1;
+}
+void land(const PendingCopy& c) {
+    std::memcpy(c.dst, c.src, c.bytes);
+    c.bar->tx -= static_cast<int32_t>(c.bytes);
+    mbar_check_complete(c.bar);
+}
 
 void switch_to_scheduler() {
 #if DEVSIM_ASAN
@@ -246,11 +279,18 @@ uint32_t warp_ballot(bool pred) {
     return bits;
 }
 
+void bulk_copy(void* dst, const void* src, uint32_t bytes, MBar* bar) {
+    PendingCopy c{dst, src, bytes, bar, g_random_schedule ? static_cast<int>(next_random() % 4) : 0};
+    if (c.rounds_left == 0) land(c);   // at once: the earliest possible overwrite of the destination
+    else g_block->copies.push_back(c);
+}
+
 unsigned char* dynamic_smem() { return g_block ? g_block->smem : nullptr; }
 size_t dynamic_smem_bytes() { return g_block ? g_block->smem_bytes : 0; }
 
 void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& thread_body) {
     if (g_block) trap("nested kernel launch");
+    read_schedule_options();
     const size_t nthreads = static_cast<size_t>(block.x) * block.y * block.z;
     if (nthreads == 0 || nthreads > kMaxThreads) trap("launch: block size outside [1, 1024]");
     if (grid.x == 0 || grid.y == 0 || grid.z == 0) trap("launch: empty grid");
@@ -300,12 +340,31 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void
                     ++w.live;
                 }
                 int idle_rounds = 0;
+                b.copies.clear();
+                std::vector<int> warp_order(b.warps.size());
+                for (size_t w = 0; w < warp_order.size(); ++w) warp_order[w] = static_cast<int>(w);
                 while (b.live > 0) {
                     const uint64_t before = b.progress;
                     bool all_blocked = true;
-                    for (size_t t = 0; t < nthreads; ++t) {
+                    for (size_t k = 0; k < b.copies.size();) {   // bulk copies in flight
+                        if (--b.copies[k].rounds_left <= 0) {
+                            land(b.copies[k]);
+                            b.copies[k] = b.copies.back();
+                            b.copies.pop_back();
+                        } else {
+                            ++k;
+                        }
+                    }
+                    if (!b.copies.empty()) all_blocked = false;
+                    if (g_random_schedule)
+                        for (size_t w = warp_order.size(); w > 1; --w) std::swap(warp_order[w - 1], warp_order[next_random() % w]);
+                    for (size_t slot = 0; slot < nthreads; ++slot) {
+                        const size_t t = static_cast<size_t>(warp_order[slot >> 5]) * 32 + (slot & 31);
+                        if ((slot & 31) == 0) g_skip_warp = g_random_schedule && (next_random() & 1u) != 0;
+                        if (t >= nthreads) continue;
                         Fiber& f = b.fibers[t];
                         if (f.done) continue;
+                        if (g_skip_warp) { all_blocked = false; continue; }
                         g_cur = &f;
                         g_thread_idx = f.tid;
                         f.blocked = false;

@@ -43,6 +43,8 @@ unsigned char* dynamic_smem();        // this block's dynamic shared memory
 size_t dynamic_smem_bytes();
 void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& thread_body);
 uint64_t now_ns();
+struct MBar;
+void bulk_copy(void* dst, const void* src, uint32_t bytes, MBar* bar);   // lands at once, or some rounds later (DMK_DEVSIM_SEED)
 
 template <class... P>
 struct Launcher {
@@ -194,14 +196,10 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {   // waits for the compl
         ::devsim::yield_blocked();
     }
 }
-// the bulk copy lands at once (one legal schedule; the earliest possible overwrite of its destination)
 inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     if (bytes % 16 || reinterpret_cast<uintptr_t>(src_gmem) % 16 || reinterpret_cast<uintptr_t>(dst_smem) % 16)
         ::devsim::trap("cp.async.bulk: size and both addresses must be multiples of 16");
-    std::memcpy(::devsim::smem_pointer(::devsim::smem_offset(dst_smem), bytes), src_gmem, bytes);
-    auto* b = reinterpret_cast<::devsim::MBar*>(bar);
-    b->tx -= static_cast<int32_t>(bytes);
-    ::devsim::mbar_check_complete(b);
+    ::devsim::bulk_copy(::devsim::smem_pointer(::devsim::smem_offset(dst_smem), bytes), src_gmem, bytes, reinterpret_cast<::devsim::MBar*>(bar));
 }
 
 inline void check_aligned(const void* p, size_t a, const char* what) {
