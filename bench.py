@@ -233,11 +233,34 @@ class NvmlClockSampler:
                 "source": "nvml, 5 ms period"}
 
 
+class CombinedClockSampler:
+    """NVML every 5 ms with `nvidia-smi -lms 100` running beside it: the line always carries clocks, even when NVML starts but then
+    delivers nothing inside the timed region (the nvidia-smi path is the one round 1's numbers were taken with)."""
+
+    def __init__(self, device_index, pci_bus_id=None):
+        self.nvml = NvmlClockSampler(device_index, pci_bus_id)
+        self.smi = ClockSampler(device_index)
+        self.nvml_ok = False
+
+    def start(self):
+        self.nvml_ok = self.nvml.start()
+        self.smi.start()
+
+    def stop(self, t_begin, t_end):
+        smi = self.smi.stop(t_begin, t_end)
+        if self.nvml_ok:
+            nv = self.nvml.stop(t_begin, t_end)
+            if nv.get("sm_mhz") is not None and nv.get("samples", 0) > 0:
+                if smi.get("sm_mhz") is not None:   # the two sources side by side
+                    nv["nvidia_smi"] = {"sm_mhz": smi["sm_mhz"], "samples": smi.get("samples"), "reasons": smi.get("reasons")}
+                    nv["reasons"] = sorted(set(nv["reasons"]) | set(smi.get("reasons") or []))
+                return nv
+        smi.setdefault("source", "nvidia-smi -lms 100")
+        return smi
+
+
 def make_clock_sampler(device_index, pci_bus_id=None):
-    s = NvmlClockSampler(device_index, pci_bus_id)
-    if s.start():
-        return s
-    s = ClockSampler(device_index)
+    s = CombinedClockSampler(device_index, pci_bus_id)
     s.start()
     return s
 
