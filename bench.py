@@ -179,8 +179,8 @@ class ClockSampler:
 
 
 class NvmlClockSampler:
-    """Same contract as ClockSampler, through NVML directly (pynvml): a sample every 5 ms, so that a timed region of a
-    few hundred milliseconds holds dozens of samples instead of the one or two `nvidia-smi -lms 100` delivers.  start()
+    """Same contract as ClockSampler, through NVML directly (pynvml): a sample every 10 ms, so that a timed region of a
+    hundred milliseconds holds about ten samples instead of the one or two `nvidia-smi -lms 100` delivers.  start()
     returns False when NVML is not usable; the caller then falls back to nvidia-smi."""
     REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
                ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
@@ -220,7 +220,7 @@ class NvmlClockSampler:
                 self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(self.get_reasons(h))))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.010)
 
     def stop(self, t_begin, t_end):
         self.stop_flag.set()
@@ -230,11 +230,11 @@ class NvmlClockSampler:
         sm = [r[1] for r in rows]
         reasons = sorted({name for _, _, bits in rows for name, mask in self.masks if bits & mask})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
-                "source": "nvml, 5 ms period"}
+                "source": "nvml, 10 ms period"}
 
 
 class CombinedClockSampler:
-    """NVML every 5 ms with `nvidia-smi -lms 100` running beside it: the line always carries clocks, even when NVML starts but then
+    """NVML every 10 ms with `nvidia-smi -lms 100` running beside it: the line always carries clocks, even when NVML starts but then
     delivers nothing inside the timed region (the nvidia-smi path is the one round 1's numbers were taken with)."""
 
     def __init__(self, device_index, pci_bus_id=None):
