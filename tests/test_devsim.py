@@ -24,7 +24,8 @@ LIB_ASAN = os.path.join(DEVSIM, "_build", "libdarmok_b200_devsim_asan.so")
 
 # not on the simulator: the full-size crowds (hours of fibers), the tests whose C++ binary links the CUDA build (their
 # simulator twin is test_host_shim_device_scenarios_on_the_simulator below) and the two-process CUDA IPC check
-DESELECT = ["tests/test_gpu_fullsize.py", "tests/test_host_shim.py", "tests/test_shim_extras_gpu.py",
+DESELECT = ["tests/test_gpu_fullsize.py", "tests/test_host_shim.py", "tests/test_shim_extras_gpu.py", "tests/test_gpu_zz_crowd_fuzz.py",
+            "tests/test_gpu_zz_skin_ring.py",   # (these two scripts have their own tests below)
             "tests/test_gpu_zz_peer_exchange.py::test_peer_exchange_two_processes_over_cuda_ipc"]
 
 
@@ -92,6 +93,19 @@ def test_skinning_character_loop_under_random_warp_schedules(libs):
         env = dict(_env(libs[0]), DMK_DEVSIM_SEED=seed)
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "skin_ring_check.py")], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
         assert r.returncode == 0 and "cases match the oracle" in r.stdout and _clean(r), r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_random_configurations_on_the_simulator(libs):
+    # tests/crowd_fuzz_check.py: skeleton / armature / palette sizes (1 .. 300 joints, palettes beyond 181 slots), 1 .. 4 layers,
+    # thresholds that pull the rest pose in, vertex counts / orders / layouts, crowd sizes -- 40 seeds, and 12 more under ASan + UBSan
+    # with a random warp schedule (several hundred seeds were run when this was written; all agree with the oracle)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "crowd_fuzz_check.py"), "1", "40"], cwd=ROOT, env=_env(libs[0]), capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "40 configurations match the oracle" in r.stdout and _clean(r), r.stdout[-2500:] + r.stderr[-3000:]
+    env = dict(_env(libs[1], asan=True), DMK_DEVSIM_SEED="7")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "crowd_fuzz_check.py"), "900", "12"], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "12 configurations match the oracle" in r.stdout and _clean(r), r.stdout[-2500:] + r.stderr[-3000:]
 
 
 def test_host_shim_device_scenarios_on_the_simulator(libs, assets_dir):  # noqa: F811
