@@ -9,6 +9,8 @@ timeout 900 python -m pytest tests -q -m gpu -rxX > gpurun_out/r02_pytest_gpu.lo
 timeout 200 python tests/peer_exchange_check.py > gpurun_out/r02_peer_exchange_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_peer_exchange_check.log
 timeout 300 python tests/peer_exchange_ipc_check.py > gpurun_out/r02_peer_exchange_ipc_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_peer_exchange_ipc_check.log
 timeout 300 python tests/skin_planar_check.py > gpurun_out/r02_skin_planar_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_skin_planar_check.log
+timeout 300 python tests/skin_ring_check.py > gpurun_out/r02_skin_ring_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_skin_ring_check.log
+timeout 300 python tests/crowd_fuzz_check.py 1 200 > gpurun_out/r02_crowd_fuzz_check.log 2>&1; echo "exit $?" >> gpurun_out/r02_crowd_fuzz_check.log
 timeout 300 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
 for layout in 1 2 3; do timeout 200 python bench.py --skin-layout $layout --no-cpu-baseline > gpurun_out/r02_bench_layout$layout.json 2> gpurun_out/r02_bench_layout$layout.err; done
 timeout 300 python tools/bench_configs.py 3s > gpurun_out/r02_skin_variants.jsonl 2> gpurun_out/r02_skin_variants.err
@@ -19,4 +21,4 @@ for shape in "" planar1 planar2 planar3; do
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:skin_kernel -s 2 -c 1 -f -o gpurun_out/r02_skin_${shape:-default} \
       python tools/skin_only.py $shape > gpurun_out/r02_ncu_skin_${shape:-default}.log 2>&1
 done
-tail -3 gpurun_out/r02_pytest_gpu.log gpurun_out/r02_peer_exchange_check.log gpurun_out/r02_peer_exchange_ipc_check.log gpurun_out/r02_skin_planar_check.log gpurun_out/r02_skin_variants.jsonl
+tail -3 gpurun_out/r02_pytest_gpu.log gpurun_out/r02_peer_exchange_check.log gpurun_out/r02_peer_exchange_ipc_check.log gpurun_out/r02_skin_planar_check.log gpurun_out/r02_skin_ring_check.log gpurun_out/r02_crowd_fuzz_check.log gpurun_out/r02_skin_variants.jsonl
