@@ -13,9 +13,6 @@
 #endif
 
 #include <chrono>
-#include <map>
-#include <mutex>
-#include <string>
 #include <vector>
 
 #if defined(__SANITIZE_ADDRESS__)
