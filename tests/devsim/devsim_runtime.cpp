@@ -402,6 +402,11 @@ bool devsim_enabled() {
 }
 struct EventImpl { uint64_t t_ns = 0; };
 int g_stream_token;
+long g_live_allocations = 0, g_allocation_count = 0, g_fail_countdown = 0;
+bool allocation_fails() {
+    ++g_allocation_count;
+    return g_fail_countdown > 0 && --g_fail_countdown == 0;
+}
 }  // namespace
 
 extern "C" {
@@ -423,24 +428,40 @@ cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* prop, int device) {
     return cudaSuccess;
 }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "devsim runtime error"; }
+const char* cudaGetErrorString(cudaError_t e) {
+    return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "devsim runtime error";
+}
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 
+// Allocation bookkeeping for the tests: live device / pinned blocks, and an injected failure -- devsim_fail_allocation_after(k)
+// makes the k-th allocation from now (device or pinned, counted together) fail once with cudaErrorMemoryAllocation.
+__attribute__((visibility("default"))) long devsim_live_allocations(void) { return g_live_allocations; }
+__attribute__((visibility("default"))) long devsim_allocation_count(void) { return g_allocation_count; }
+__attribute__((visibility("default"))) void devsim_fail_allocation_after(long k) { g_fail_countdown = k; }
+
 cudaError_t cudaMalloc(void** p, size_t bytes) {
+    *p = nullptr;
+    if (allocation_fails()) return cudaErrorMemoryAllocation;
     // cudaMalloc's 256-byte alignment, but the exact size: ASan flags any access past the end
     if (posix_memalign(p, 256, bytes ? bytes : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
     std::memset(*p, 0xcd, bytes);
+    ++g_live_allocations;
     return cudaSuccess;
 }
 cudaError_t cudaFree(void* p) {
+    if (p) --g_live_allocations;
     std::free(p);
     return cudaSuccess;
 }
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned int) {
+    *p = nullptr;
+    if (allocation_fails()) return cudaErrorMemoryAllocation;
     *p = std::malloc(bytes ? bytes : 1);
+    if (*p) ++g_live_allocations;
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 cudaError_t cudaFreeHost(void* p) {
+    if (p) --g_live_allocations;
     std::free(p);
     return cudaSuccess;
 }

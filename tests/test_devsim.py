@@ -108,6 +108,15 @@ def test_random_configurations_on_the_simulator(libs):
     assert r.returncode == 0 and "12 configurations match the oracle" in r.stdout and _clean(r), r.stdout[-2500:] + r.stderr[-3000:]
 
 
+def test_every_allocation_of_a_frame_may_fail(libs):
+    # tests/devsim/alloc_failure_check.py under ASan: each of the ~90 device / pinned allocations of a full set-up + frame (create calls,
+    # lazy buffers of setters and getters, second skin, device animators, exchange) fails once: an error status with a message, no
+    # crash, and the live allocation count returns to where it started (nothing leaks from a create call that fails part-way)
+    r = subprocess.run([sys.executable, os.path.join(DEVSIM, "alloc_failure_check.py")], cwd=ROOT, env=_env(libs[1], asan=True), capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "no crash, nothing left allocated" in r.stdout and _clean(r), r.stdout[-2500:] + r.stderr[-3000:]
+
+
 def test_host_shim_device_scenarios_on_the_simulator(libs, assets_dir):  # noqa: F811
     # tests/cpp/animator_test.cpp linked against the simulator build: SkeletalAnimator / scene component / device animators
     # against the reference animator (mode gpu) and the second skin + load / reload (mode gpuextras)
