@@ -117,6 +117,14 @@ def test_every_allocation_of_a_frame_may_fail(libs):
     assert r.returncode == 0 and "no crash, nothing left allocated" in r.stdout and _clean(r), r.stdout[-2500:] + r.stderr[-3000:]
 
 
+def test_null_and_out_of_range_arguments_never_crash(libs):
+    # tests/devsim/null_sweep_check.py under ASan + UBSan: every function of include/dmk.h with all-NULL arguments, then with real
+    # handles and every other pointer NULL and every number 0 / -1 / INT_MAX: statuses, never a crash, and the objects still work
+    r = subprocess.run([sys.executable, os.path.join(DEVSIM, "null_sweep_check.py")], cwd=ROOT, env=_env(libs[1], asan=True), capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "no crash" in r.stdout and _clean(r), r.stdout[-1500:] + r.stderr[-4000:]
+
+
 def test_host_shim_device_scenarios_on_the_simulator(libs, assets_dir):  # noqa: F811
     # tests/cpp/animator_test.cpp linked against the simulator build: SkeletalAnimator / scene component / device animators
     # against the reference animator (mode gpu) and the second skin + load / reload (mode gpuextras)
