@@ -140,9 +140,11 @@ const std::function<void()>* g_body = nullptr;
 unsigned char* g_stacks = nullptr;
 
 // DMK_DEVSIM_SEED=<n>, n != 0: instead of the fixed round-robin, every scheduler round runs the warps in a random order and leaves
-// each one out with probability 1/2 (warps drift apart by many rounds), and bulk copies land 0..3 rounds after their issue
+// each one out with probability 1/2 (warps drift apart by many rounds), runs the lanes of a warp in a permuted order (lane ^ r), and
+// lets bulk copies land 0..3 rounds after their issue
 uint64_t g_rng = 0;
 bool g_random_schedule = false, g_skip_warp = false;
+unsigned g_lane_xor = 0;
 uint32_t next_random() {   // xorshift64*
     g_rng ^= g_rng >> 12;
     g_rng ^= g_rng << 25;
@@ -355,9 +357,14 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void
                     if (!b.copies.empty()) all_blocked = false;
                     if (g_random_schedule)
                         for (size_t w = warp_order.size(); w > 1; --w) std::swap(warp_order[w - 1], warp_order[next_random() % w]);
-                    for (size_t slot = 0; slot < nthreads; ++slot) {
-                        const size_t t = static_cast<size_t>(warp_order[slot >> 5]) * 32 + (slot & 31);
-                        if ((slot & 31) == 0) g_skip_warp = g_random_schedule && (next_random() & 1u) != 0;
+                    for (size_t slot = 0; slot < b.warps.size() * 32; ++slot) {   // whole warps: the lane permutation maps into them
+                        // random mode also runs the lanes of a warp in a rotated, possibly reversed order: code that leans on lanes
+                        // running in step without a __syncwarp() sees its neighbours' data too early or too late
+                        if ((slot & 31) == 0) {
+                            g_skip_warp = g_random_schedule && (next_random() & 1u) != 0;
+                            g_lane_xor = g_random_schedule ? next_random() & 31u : 0u;
+                        }
+                        const size_t t = static_cast<size_t>(warp_order[slot >> 5]) * 32 + ((slot & 31) ^ g_lane_xor);
                         if (t >= nthreads) continue;
                         Fiber& f = b.fibers[t];
                         if (f.done) continue;

@@ -76,7 +76,9 @@ def test_gpu_parity_suite_on_the_simulator(libs):
     # every `-m gpu` test that fits: pose (key indices, clocks, locals, models, palette), skinning, cull + compaction, transform
     # hierarchy, device animators, several skins per character, zero groups, the planar / three-stream skinning shapes and the
     # peer-memory exchange with three logical ranks
-    r = _pytest(_env(libs[0]), "tests")
+    # (DMK_DEVSIM_SEED: random warp order, half of the warps left out of every scheduler round, lanes of a warp in a permuted order --
+    # a missing __syncwarp() / __syncthreads() shows; the fixed round-robin order is what smoke() and the sanitizer run use)
+    r = _pytest(dict(_env(libs[0]), DMK_DEVSIM_SEED="5"), "tests")
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0 and _clean(r), tail
     m = re.search(r"(\d+) passed", r.stdout)
@@ -132,7 +134,7 @@ def test_host_shim_device_scenarios_on_the_simulator(libs, assets_dir):  # noqa:
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     exe = os.path.join(ROOT, "tests", "cpp", "animator_test_devsim")
     for mode, expect in (("gpu", "gpu: 0 failures"), ("gpuextras", " 0 failures")):
-        r = subprocess.run([exe, assets_dir, mode], env=_env(libs[0]), capture_output=True, text=True, timeout=900)
+        r = subprocess.run([exe, assets_dir, mode], env=dict(_env(libs[0]), DMK_DEVSIM_SEED="6"), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0 and expect in r.stdout and _clean(r), r.stdout[-2500:] + r.stderr[-2000:]
 
 
