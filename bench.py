@@ -389,10 +389,13 @@ def run_gpu(args):
         time.sleep(0.25)
         launches0 = ctx.launches
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # one more event behind every step: the per-frame distribution (median, p10, p90) next to the mean the metric is made of
+        frame_events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         t_begin = time.perf_counter()
         ev0.record(stream)
-        for _ in range(args.steps):
+        for k in range(args.steps):
             step()
+            frame_events[k].record(stream)
         ev1.record(stream)
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -401,6 +404,14 @@ def run_gpu(args):
         clocks = sampler.stop(t_begin, t_end)
         elapsed_ms = ev0.elapsed_time(ev1)
         launches = ctx.launches - launches0
+        frame_ms = None
+        try:
+            marks = [ev0] + frame_events
+            per = sorted(marks[k].elapsed_time(marks[k + 1]) for k in range(args.steps))
+            frame_ms = {"median": statistics.median(per), "p10": per[int(0.1 * (len(per) - 1))], "p90": per[int(round(0.9 * (len(per) - 1)))],
+                        "min": per[0], "max": per[-1], "frames": len(per)}
+        except Exception as exc:   # the distribution is an extra: it never costs the line
+            frame_ms = {"error": str(exc)[:200]}
         if world > 1:
             t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -519,6 +530,7 @@ def run_gpu(args):
         "kernel_ms_per_step": {"pose": pose_ms / max(1, pose_n), "cull+compact": cull_ms / max(1, cull_n),
                                "skin": skin_avg_ms, "pack_visible_palettes": pack_ms / max(1, pack_n)},
         "visible_characters_rank0": int(vis0),
+        "frame_ms_rank0": frame_ms,
     }
     emit(line)
     if world > 1:

@@ -127,6 +127,26 @@ def test_null_and_out_of_range_arguments_never_crash(libs):
     assert r.returncode == 0 and "no crash" in r.stdout and _clean(r), r.stdout[-1500:] + r.stderr[-4000:]
 
 
+def test_bench_single_gpu_arm_runs_on_the_simulator(libs):
+    # bench.py as it is, with torch's streams / events / device tensors swapped for host stand-ins (tests/devsim/bench_on_simulator.py):
+    # its step, e2e, roofline, clocks and cpu_baseline sections all execute and the one JSON line carries every key of the contract.
+    # The numbers in it are fibers on a CPU and mean nothing; this guards bench.py's own code between GPU runs.
+    import json
+    for extra in ([], ["--skin-layout", "2", "--no-cpu-baseline"]):
+        r = subprocess.run([sys.executable, os.path.join(DEVSIM, "bench_on_simulator.py"), "--chars", "300", "--verts", "40", "--clips", "2", "--steps", "3",
+                            "--warmup", "3", *extra], cwd=ROOT, env=_env(libs[0]), capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and _clean(r), r.stdout[-1500:] + r.stderr[-3000:]
+        lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+        assert len(lines) == 1, r.stdout[-1500:]
+        line = json.loads(lines[0])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                    "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+            assert key in line, key
+        assert line["gpu_launches"] > 0 and line["steps"] == 3 and line["n_gpus"] == 1 and line["e2e"]["h2d_bytes_per_step"] > 0
+        assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["frame_ms_rank0"]["frames"] == 3
+        assert (line["cpu_baseline"] is None) == bool(extra)
+
+
 def test_host_shim_device_scenarios_on_the_simulator(libs, assets_dir):  # noqa: F811
     # tests/cpp/animator_test.cpp linked against the simulator build: SkeletalAnimator / scene component / device animators
     # against the reference animator (mode gpu) and the second skin + load / reload (mode gpuextras)
