@@ -62,6 +62,15 @@ def install_host_stand_ins():
     def no_properties(device=None):
         raise RuntimeError("no device properties on the simulator")
 
+    # N > 1 (under torchrun): the process group the bench asks NCCL for is a gloo group here, and the visible-palette gather moves
+    # host tensors; what runs is bench.py's own multi-rank logic (shard seeds, agreed slab capacity, gather calls, max over ranks)
+    import torch.distributed as dist
+    real_init = dist.init_process_group
+
+    def init_process_group(backend=None, device_id=None, **kwargs):
+        return real_init("gloo", **kwargs)
+
+    dist.init_process_group = init_process_group
     torch.cuda.Stream = lambda device=None: Stream()
     torch.cuda.stream = lambda stream: contextlib.nullcontext()
     torch.cuda.Event = Event

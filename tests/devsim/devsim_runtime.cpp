@@ -418,13 +418,19 @@ bool allocation_fails() {
 
 extern "C" {
 
+static int device_count() {   // DMK_DEVSIM_DEVICES: how many (identical, independent) devices to announce; one process per device in the tests
+    if (!devsim_enabled()) return 0;   // without the switch this library has no device: dmk_context_create fails
+    const char* e = std::getenv("DMK_DEVSIM_DEVICES");
+    const int n = e ? std::atoi(e) : 1;
+    return n < 1 ? 1 : n;
+}
 cudaError_t cudaGetDeviceCount(int* count) {
-    *count = devsim_enabled() ? 1 : 0;   // without the switch this library has no device: dmk_context_create fails
+    *count = device_count();
     return cudaSuccess;
 }
-cudaError_t cudaSetDevice(int device) { return device == 0 && devsim_enabled() ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaSetDevice(int device) { return device >= 0 && device < device_count() ? cudaSuccess : cudaErrorInvalidDevice; }
 cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* prop, int device) {
-    if (device != 0) return cudaErrorInvalidDevice;
+    if (device < 0 || device >= device_count()) return cudaErrorInvalidDevice;
     std::memset(prop, 0, sizeof *prop);
     std::snprintf(prop->name, sizeof prop->name, "devsim (CPU lockstep simulator, not a GPU)");
     prop->major = 10;

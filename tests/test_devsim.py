@@ -147,6 +147,26 @@ def test_bench_single_gpu_arm_runs_on_the_simulator(libs):
         assert (line["cpu_baseline"] is None) == bool(extra)
 
 
+def test_bench_two_rank_arm_runs_on_the_simulator(libs):
+    # the same under torchrun with two ranks: the process group the bench asks NCCL for is a gloo group here (bench_on_simulator.py) and
+    # every rank drives its own simulated device.  bench.py's multi-rank code runs as it is: per-rank seeds, the slab capacity all ranks
+    # agree on, the reserved-SM option, the visible-palette gather on the side "stream" every frame, max-over-ranks timing, rank 0's line
+    import json
+    import socket
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    env = dict(_env(libs[0]), DMK_DEVSIM_DEVICES="2", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        str(port), os.path.join(DEVSIM, "bench_on_simulator.py"), "--gpus", "2", "--chars", "300", "--verts", "40", "--clips", "2", "--steps", "3",
+                        "--warmup", "3"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "devsim:" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stdout[-1500:] + r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-1500:]
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["gpu_launches"] > 0 and line["cpu_baseline"] is None and "NCCL" in line["config"]["gather"]
+
+
 def test_host_shim_device_scenarios_on_the_simulator(libs, assets_dir):  # noqa: F811
     # tests/cpp/animator_test.cpp linked against the simulator build: SkeletalAnimator / scene component / device animators
     # against the reference animator (mode gpu) and the second skin + load / reload (mode gpuextras)
