@@ -8,6 +8,7 @@ bench.py's own code -- argument handling, the step / e2e / cpu_baseline sections
 its keys; every number in that line is meaningless (fibers on a CPU) and nothing here is ever reported.
 
     DMK_DEVSIM=1 DMK_LIBRARY=tests/devsim/_build/libdarmok_b200_devsim.so python tests/devsim/bench_on_simulator.py [bench args]
+    ... python tests/devsim/bench_on_simulator.py --script tools/bench_configs.py 3s      (another script, same stand-ins)
 """
 import contextlib
 import ctypes
@@ -71,6 +72,7 @@ def install_host_stand_ins():
         return real_init("gloo", **kwargs)
 
     dist.init_process_group = init_process_group
+    torch.cuda.current_stream = lambda device=None: Stream()
     torch.cuda.Stream = lambda device=None: Stream()
     torch.cuda.stream = lambda stream: contextlib.nullcontext()
     torch.cuda.Event = Event
@@ -87,6 +89,12 @@ def main():
     if os.environ.get("DMK_DEVSIM") != "1":
         sys.exit("simulator only: set DMK_DEVSIM=1 and DMK_LIBRARY to the devsim build")
     install_host_stand_ins()
+    if len(sys.argv) > 2 and sys.argv[1] == "--script":   # another measurement script of the repository, as it is
+        import runpy
+        script = os.path.join(ROOT, sys.argv[2])
+        sys.argv = [script] + sys.argv[3:]
+        runpy.run_path(script, run_name="__main__")
+        return 0
     import bench
     sys.argv = ["bench.py"] + (sys.argv[1:] or ["--chars", "400", "--verts", "72", "--clips", "3", "--steps", "3", "--warmup", "3"])
     return bench.main()

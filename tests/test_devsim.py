@@ -167,6 +167,17 @@ def test_bench_two_rank_arm_runs_on_the_simulator(libs):
     assert line["n_gpus"] == 2 and line["gpu_launches"] > 0 and line["cpu_baseline"] is None and "NCCL" in line["config"]["gather"]
 
 
+def test_round_two_measurement_scripts_dry_run_on_the_simulator(libs):
+    # the scripts the next GPU call runs (tools/round2_first_call.sh), with a crowd of 200 characters x 72 vertices: they must get to
+    # their last line without a Python error, so that GPU minutes are not spent finding a typo
+    env = dict(_env(libs[0]), DMK_TOOL_CHARS="200", DMK_TOOL_VERTS="72")
+    for script, args, expect in (("tools/bench_configs.py", ["3s"], "three_float3_streams"), ("tools/bench_pipelined.py", ["2"], "4_crowds"),
+                                 ("tools/skin_only.py", ["sorted", "planar1"], "done")):
+        r = subprocess.run([sys.executable, os.path.join(DEVSIM, "bench_on_simulator.py"), "--script", script, *args], cwd=ROOT, env=env, capture_output=True,
+                           text=True, timeout=900)
+        assert r.returncode == 0 and expect in r.stdout and _clean(r), script + "\n" + r.stdout[-1500:] + r.stderr[-3000:]
+
+
 def test_host_shim_device_scenarios_on_the_simulator(libs, assets_dir):  # noqa: F811
     # tests/cpp/animator_test.cpp linked against the simulator build: SkeletalAnimator / scene component / device animators
     # against the reference animator (mode gpu) and the second skin + load / reload (mode gpuextras)

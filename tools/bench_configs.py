@@ -138,7 +138,8 @@ def config3_sorted():
     palette gathers.  Reported next to bench.py's number, which keeps the caller's vertex order."""
     import torch
     from darmok_b200 import capi, synth
-    n, verts = 100_000, 5000
+    # (DMK_TOOL_CHARS / DMK_TOOL_VERTS: a small crowd for the dry run on the CPU simulator, tests/test_devsim.py)
+    n, verts = int(os.environ.get("DMK_TOOL_CHARS", 100_000)), int(os.environ.get("DMK_TOOL_VERTS", 5000))
     skel_s = synth.make_skeleton(67)
     clips_s = [synth.make_clip(skel_s, f"clip{i}", seed=i, duration=1.5) for i in range(8)]
     arm_s = synth.make_armature(skel_s)

@@ -22,7 +22,8 @@ def main():
     import torch
     from darmok_b200 import capi, synth
     frames = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    n_total, verts = 100_000, 5000
+    # (DMK_TOOL_CHARS / DMK_TOOL_VERTS: a small crowd for the dry run on the CPU simulator, tests/test_devsim.py)
+    n_total, verts = int(os.environ.get("DMK_TOOL_CHARS", 100_000)), int(os.environ.get("DMK_TOOL_VERTS", 5000))
     tiny = float(np.finfo(np.float32).tiny)
     skel_s = synth.make_skeleton(67)
     clips_s = [synth.make_clip(skel_s, f"clip{i}", seed=i, duration=1.5) for i in range(8)]

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 from darmok_b200 import capi, synth
 flags = capi.MESH_SORT_BY_INFLUENCES if "sorted" in sys.argv else 0
-n, verts = 100_000, 5000
+n, verts = int(os.environ.get("DMK_TOOL_CHARS", 100_000)), int(os.environ.get("DMK_TOOL_VERTS", 5000))   # (small for the dry run on the CPU simulator)
 skel_s = synth.make_skeleton(67)
 clips_s = [synth.make_clip(skel_s, f"clip{i}", seed=i, duration=1.5) for i in range(8)]
 arm_s = synth.make_armature(skel_s)
