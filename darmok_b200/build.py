@@ -2,7 +2,7 @@
 
     python -m darmok_b200.build [--force] [--verbose]
 
-The pose, cull and API translation units are compiled with -fmad=false: their arithmetic must follow the
+The pose, cull and API (api_*.cu) translation units are compiled with -fmad=false: their arithmetic must follow the
 reference's un-contracted IEEE operation order (keyframe indices and visibility are bit-exact contracts).
 The skinning kernel keeps FMA contraction (its contract is a 1e-5 relative tolerance and it is the kernel
 whose instruction count matters).
@@ -25,7 +25,11 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-cudart", "static", "-Xcompiler", "
           "-I", INCLUDE, "-I", CSRC]
 # (source, extra flags)
 UNITS = [
-    ("api.cu", ["-fmad=false"]),
+    ("api_context.cu", ["-fmad=false"]),
+    ("api_assets.cu", ["-fmad=false"]),
+    ("api_crowd.cu", ["-fmad=false"]),
+    ("api_results.cu", ["-fmad=false"]),
+    ("api_exchange.cu", ["-fmad=false"]),
     ("ozz_io.cpp", []),
     ("pose_kernel.cu", ["-fmad=false"]),
     ("cull_kernel.cu", ["-fmad=false"]),

@@ -1,6 +1,6 @@
 // animator_flatten.hpp -- host-only: a flattened SkeletalAnimatorDefinition (dmk.h dmk_anim_*_def) turned into the tables the
 // animator kernel reads (device_types.cuh): clip durations resolved, OzzSkeletalAnimatorState::calcDuration per state, the rest
-// clip and, for Directional states, the clip-pair constants of calcBlendWeight.  Used by dmk_crowd_set_animator (api.cu) and
+// clip and, for Directional states, the clip-pair constants of calcBlendWeight.  Used by dmk_crowd_set_animator (api_crowd.cu) and
 // by tests/cpp/animator_kernel_host.cpp, which runs the kernel's per-character code on the CPU.
 #pragma once
 

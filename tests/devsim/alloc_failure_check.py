@@ -6,7 +6,7 @@ and nodes, a second skin, the device animators, the peer-memory exchange, one fr
 count its device / pinned allocations (A), then A more times with the k-th allocation failing.  Each time the call that hits the
 failure must come back as an error status with a message (never a crash; the build runs under AddressSanitizer), everything that had
 been created must still close, and the library's live allocation count must return to where it started: a create call that fails
-part-way gives back what it had taken (api.cu `Building<>`), and so do the lazy allocations of the setters and getters.
+part-way gives back what it had taken (api_internal.hpp `Building<>`), and so do the lazy allocations of the setters and getters.
 
     DMK_DEVSIM=1 DMK_LIBRARY=tests/devsim/_build/libdarmok_b200_devsim.so python tests/devsim/alloc_failure_check.py
 """

@@ -1,5 +1,5 @@
 // devsim_runtime.cpp -- TEST INFRASTRUCTURE (see dmk_devsim_intrinsics.hpp): the lockstep executor behind DMK_LAUNCH and a
-// stand-in for the few CUDA runtime calls darmok_b200/csrc/api.cu makes, with "device" memory on the host heap (so that
+// stand-in for the few CUDA runtime calls darmok_b200/csrc/api_*.cu make, with "device" memory on the host heap (so that
 // AddressSanitizer sees every kernel access).  Kernels run synchronously inside the launch call, blocks one after the
 // other, the threads of a block as fibers switched at blocking calls only.
 //
@@ -399,7 +399,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void
 }  // namespace devsim
 
 // ======================================================================================================================
-// CUDA runtime stand-in: exactly the calls api.cu makes.  One device ("B200", 148 SMs, sm_100), memory on the heap,
+// CUDA runtime stand-in: exactly the calls api_*.cu make.  One device ("B200", 148 SMs, sm_100), memory on the heap,
 // streams and events are tokens (everything is synchronous).
 // ======================================================================================================================
 namespace {

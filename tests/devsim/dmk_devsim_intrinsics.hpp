@@ -4,7 +4,7 @@
 // blocking calls (__syncthreads, __syncwarp, warp collectives, mbarrier waits, __nanosleep) switch fibers
 // (tests/devsim/devsim_runtime.cpp).  What this checks: index arithmetic (device buffers and dynamic shared memory are
 // bounds-checked / ASan-visible heap blocks), hand-off protocols (a deadlock or a spin bound aborts with a message) and the
-// host-side launch logic of api.cu -- not performance and not the memory model (fibers interleave only at blocking calls).
+// host-side launch logic of api_*.cu -- not performance and not the memory model (fibers interleave only at blocking calls).
 // Nothing under darmok_b200/ or include/ uses this; the product library is the nvcc build.
 #pragma once
 

@@ -1,6 +1,6 @@
 """The kernels' own source on the CPU (tests/devsim): darmok_b200/csrc/*.cu built with g++ for a lockstep simulator -- one
 fiber per CUDA thread, emulated mbarrier / bulk copy / warp collectives, "device" and shared memory as exact-size heap blocks --
-behind the unchanged host side of the C ABI (api.cu).  The GPU parity tests then run against that build without a GPU.
+behind the unchanged host side of the C ABI (api_*.cu).  The GPU parity tests then run against that build without a GPU.
 
 What it is for: the index arithmetic and the hand-off protocols of the kernels (a wrong tile bound, a replica ring reused too
 early, a barrier some thread never reaches) show up here as a wrong result, an AddressSanitizer report naming the kernel source
