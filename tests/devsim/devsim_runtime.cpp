@@ -7,12 +7,15 @@
 // mistaken for, or silently stand in for, the CUDA build.
 #include "dmk_devsim_intrinsics.hpp"
 
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <unistd.h>
 #if !defined(__x86_64__)
 #include <ucontext.h>
 #endif
 
 #include <chrono>
+#include <map>
 #include <vector>
 
 #if defined(__SANITIZE_ADDRESS__)
@@ -410,6 +413,14 @@ bool devsim_enabled() {
 struct EventImpl { uint64_t t_ns = 0; };
 int g_stream_token;
 long g_live_allocations = 0, g_allocation_count = 0, g_fail_countdown = 0;
+struct SharedBlock { int fd; size_t size; };
+std::map<void*, SharedBlock> g_shared;   // memfd-backed "device" blocks of this process
+std::map<void*, size_t> g_opened;        // blocks of other processes mapped here
+struct IpcHandle { void* pointer; int64_t pid; int32_t fd; uint64_t size; };
+size_t shared_min_bytes() {
+    const char* e = std::getenv("DMK_DEVSIM_SHARED");
+    return e && e[0] == '1' ? size_t(65536) : ~size_t(0);
+}
 bool allocation_fails() {
     ++g_allocation_count;
     return g_fail_countdown > 0 && --g_fail_countdown == 0;
@@ -455,6 +466,20 @@ __attribute__((visibility("default"))) void devsim_fail_allocation_after(long k)
 cudaError_t cudaMalloc(void** p, size_t bytes) {
     *p = nullptr;
     if (allocation_fails()) return cudaErrorMemoryAllocation;
+    if (bytes >= shared_min_bytes()) {
+        // DMK_DEVSIM_SHARED=1: large blocks are memfd mappings, so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle can map them into
+        // another PROCESS (the two-process check of the peer-memory exchange); ASan does not see past their end
+        const size_t size = (bytes + 4095) & ~size_t(4095);
+        const int fd = memfd_create("devsim", 0);
+        if (fd < 0 || ftruncate(fd, static_cast<off_t>(size)) != 0) return cudaErrorMemoryAllocation;
+        void* m = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (m == MAP_FAILED) { close(fd); return cudaErrorMemoryAllocation; }
+        std::memset(m, 0xcd, bytes);
+        g_shared[m] = SharedBlock{fd, size};
+        *p = m;
+        ++g_live_allocations;
+        return cudaSuccess;
+    }
     // cudaMalloc's 256-byte alignment, but the exact size: ASan flags any access past the end
     if (posix_memalign(p, 256, bytes ? bytes : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
     std::memset(*p, 0xcd, bytes);
@@ -463,6 +488,13 @@ cudaError_t cudaMalloc(void** p, size_t bytes) {
 }
 cudaError_t cudaFree(void* p) {
     if (p) --g_live_allocations;
+    auto it = g_shared.find(p);
+    if (it != g_shared.end()) {
+        munmap(p, it->second.size);
+        close(it->second.fd);
+        g_shared.erase(it);
+        return cudaSuccess;
+    }
     std::free(p);
     return cudaSuccess;
 }
@@ -528,17 +560,52 @@ cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* blocks, 
     return cudaSuccess;
 }
 
-// "IPC" within the one process: the handle carries the pointer
+// IPC: the handle carries the pointer (same process) or {pid, fd, size} of a memfd block (DMK_DEVSIM_SHARED=1), which another
+// process maps through /proc/<pid>/fd/<fd>
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* handle, void* p) {
+    IpcHandle h{};
+    h.pointer = p;
+    h.pid = static_cast<int64_t>(getpid());
+    auto it = g_shared.find(p);
+    if (it != g_shared.end()) {
+        h.fd = it->second.fd;
+        h.size = static_cast<uint64_t>(it->second.size);
+    } else {
+        h.fd = -1;
+    }
+    static_assert(sizeof(IpcHandle) <= sizeof(cudaIpcMemHandle_t), "handle payload");
     std::memset(handle, 0, sizeof *handle);
-    std::memcpy(handle, &p, sizeof p);
+    std::memcpy(handle, &h, sizeof h);
     return cudaSuccess;
 }
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t handle, unsigned int) {
-    std::memcpy(p, &handle, sizeof *p);
+    IpcHandle h{};
+    std::memcpy(&h, &handle, sizeof h);
+    *p = nullptr;
+    if (h.pid == static_cast<int64_t>(getpid())) {
+        *p = h.pointer;
+        return cudaSuccess;
+    }
+    if (h.fd < 0) return cudaErrorInvalidValue;   // a heap block of another process: run both sides with DMK_DEVSIM_SHARED=1
+    char path[64];
+    std::snprintf(path, sizeof path, "/proc/%lld/fd/%d", static_cast<long long>(h.pid), h.fd);
+    const int fd = open(path, O_RDWR);
+    if (fd < 0) return cudaErrorInvalidValue;
+    void* m = mmap(nullptr, h.size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
+    g_opened[m] = static_cast<size_t>(h.size);
+    *p = m;
     return cudaSuccess;
 }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+    auto it = g_opened.find(p);
+    if (it != g_opened.end()) {
+        munmap(p, it->second);
+        g_opened.erase(it);
+    }
+    return cudaSuccess;
+}
 cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) {
     *can = 1;
     return cudaSuccess;

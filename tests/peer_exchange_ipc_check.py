@@ -22,20 +22,14 @@ FRAMES = 6
 OWNER = 1
 
 
-class _Dev:
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
 def worker(rank, world, port, out_dir):
-    import torch
     import torch.distributed as dist
+    from tests import devmem
     from darmok_b200 import capi, synth
     from darmok_b200.parallel import PeerPaletteExchange
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        dev = torch.device("cuda", 0)
         tiny = float(np.finfo(np.float32).tiny)
         skel_s = synth.make_skeleton(67)
         clips_s = [synth.make_clip(skel_s, f"clip{i}", seed=i) for i in range(3)]
@@ -66,8 +60,8 @@ def worker(rank, world, port, out_dir):
             if x.is_owner:
                 slab_ptr, counts_ptr = x.wait(f)
                 ctx.sync()
-                slab = torch.as_tensor(_Dev(slab_ptr, (world, x.capacity, ps, 16), "<f4"), device=dev).cpu().numpy()
-                counts = torch.as_tensor(_Dev(counts_ptr, (world,), "<i4"), device=dev).cpu().numpy()
+                slab = devmem.read(slab_ptr, (world, x.capacity, ps, 16))
+                counts = devmem.read(counts_ptr, (world,), np.int32)
                 for r in range(world):
                     sent = np.load(os.path.join(out_dir, f"sent_r{r}_f{f}.npy"))
                     assert counts[r] == len(sent), f"frame {f} rank {r}: count {counts[r]} != {len(sent)}"

@@ -67,9 +67,12 @@ def jobs(assets_dir):  # noqa: F811
     r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "animator_test_devsim"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     exe = os.path.join(ROOT, "tests", "cpp", "animator_test_devsim")
-    with socket.socket() as sock:
-        sock.bind(("127.0.0.1", 0))
-        port = sock.getsockname()[1]
+    ports = []
+    for _ in range(2):
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            ports.append(sock.getsockname()[1])
+    port = ports[0]
     plain, asan = _env(LIB), _env(LIB_ASAN, asan=True)
     smoke = [PY, "-c", "import __graft_entry__ as g; g.smoke()"]
     script = lambda *p: [PY, os.path.join(ROOT, *p)]   # noqa: E731
@@ -93,6 +96,12 @@ def jobs(assets_dir):  # noqa: F811
         "bench_1_layout": (sim(*small, "--skin-layout", "2", "--no-cpu-baseline"), plain),
         "bench_2": ([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
                      os.path.join(DEVSIM, "bench_on_simulator.py"), "--gpus", "2", *small], _env(LIB, DMK_DEVSIM_DEVICES="2", OMP_NUM_THREADS="2")),
+        # DMK_DEVSIM_SHARED: large "device" blocks are memfd mappings that another process can open through the IPC handle, so the
+        # peer-memory exchange runs between two real processes (concurrently: the flow control works in real time)
+        "bench_2_peer": ([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(ports[1]),
+                          os.path.join(DEVSIM, "bench_on_simulator.py"), "--gpus", "2", *small, "--gather", "peer"],
+                         _env(LIB, DMK_DEVSIM_DEVICES="2", DMK_DEVSIM_SHARED="1", OMP_NUM_THREADS="2")),
+        "ipc_check": (script("tests", "peer_exchange_ipc_check.py"), _env(LIB, DMK_DEVSIM_SHARED="1")),
         "tool_3s": (sim("--script", "tools/bench_configs.py", "3s"), tool_env),
         "tool_pipelined": (sim("--script", "tools/bench_pipelined.py", "2"), tool_env),
         "tool_skin_only": (sim("--script", "tools/skin_only.py", "sorted", "planar1"), tool_env),
@@ -206,6 +215,20 @@ def test_bench_two_rank_arm_runs_on_the_simulator(jobs):
     assert len(lines) == 1, j.tail
     line = json.loads(lines[0])
     assert line["n_gpus"] == 2 and line["gpu_launches"] > 0 and line["cpu_baseline"] is None and "NCCL" in line["config"]["gather"]
+
+
+def test_peer_memory_exchange_between_two_processes_on_the_simulator(jobs):
+    # tests/peer_exchange_ipc_check.py: two processes, the render rank is rank 1, darmok_b200.parallel.PeerPaletteExchange start-up (handle
+    # over gloo, open, barrier) and six frames of push / wait / release with the slab in memory both processes map; and bench.py
+    # --gather peer with two ranks (pack+transfer kernel on the side "stream", double-buffered slab, status check at the end)
+    j = jobs["ipc_check"]
+    assert j.returncode == 0 and "identical to what the ranks sent" in j.stdout and j.clean, j.tail
+    j = jobs["bench_2_peer"]
+    assert j.returncode == 0 and "devsim:" not in j.stderr, j.tail
+    lines = [ln for ln in j.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, j.tail
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and "pack+transfer kernel" in line["config"]["gather"]
 
 
 def test_round_two_measurement_scripts_dry_run_on_the_simulator(jobs):
