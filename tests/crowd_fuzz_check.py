@@ -2,7 +2,7 @@
 """Seeded random configurations through the C ABI against the oracle: skeleton size (1 .. 300 joints, so every warps-per-block
 choice of the model kernel), armature size and order (partial, with unknown names; palettes beyond 181 slots use fewer shared
 replicas in the skinning kernel), layers (1 .. 4, weights with zeros, thresholds that pull the rest pose in), vertex counts,
-vertex order, skinned layout, crowd size, cull on / off, visible-only skinning.  Palette within the north-star tolerance, key
+vertex order, skinned layout, SMs reserved from the skinning grid, crowd size, visible-only skinning.  Palette within the north-star tolerance, key
 indices and visibility bit-exact, skinned vertices within tolerance.
 
 Runs on a GPU or on the CPU lockstep simulator (tests/test_devsim.py runs a few seeds, also under AddressSanitizer).
@@ -64,6 +64,9 @@ def one(seed):
         except capi.DmkError:
             assert arm.palette_size > 181, what + ": layout refused for a palette that fits 8 replicas"
             layout = 0
+    reserved = int(rng.choice([0, 0, 8, 100, 147]))                   # SMs left out of the persistent skinning grid (more characters per block)
+    if reserved:
+        crowd.set_option(capi.OPT_SKIN_RESERVED_SMS, reserved)
     crowd.set_layers(cr.clip, cr.ratio, weight, cr.speed, threshold=threshold)
     crowd.set_instances(inst.world_inverse, inst.bbox)
     crowd.set_camera(vp, 0.0)
