@@ -115,9 +115,12 @@ expected<std::shared_ptr<Skeleton>, std::string> B200SkeletonLoader::operator()(
 B200SkeletalAnimationLoader::B200SkeletalAnimationLoader(std::shared_ptr<DeviceContext> ctx, DataLoader dataLoader) noexcept
     : _ctx{std::move(ctx)}, _dataLoader{std::move(dataLoader)} {}
 expected<std::shared_ptr<SkeletalAnimation>, std::string> B200SkeletalAnimationLoader::operator()(const std::filesystem::path& path) noexcept {
-    auto data = _dataLoader(path);
-    if (!data) return unexpected<std::string>{data.error()};
-    return SkeletalAnimation::load(_ctx, data->data(), data->size());
+    // OzzSkeletalAnimationLoader (src/skeleton_ozz.cpp:207-216): whatever went wrong -- the data loader, the tag, the archive -- the caller
+    // gets this one text (unlike the skeleton loader, which passes loadFromData's own message on); the library's detail stays in
+    // DeviceContext::lastError()
+    if (auto data = _dataLoader(path))
+        if (auto anim = SkeletalAnimation::load(_ctx, data->data(), data->size())) return anim;
+    return unexpected<std::string>{"archive doesn't contain an animation"};
 }
 
 // ---- MeshData::exportData's influence packing (src/mesh_core.cpp:336-356) ---------------------------------------------------

@@ -859,6 +859,13 @@ static int runGpuExtras(const std::string& dir) {
     CHECK((*skel)->toString() == "Skeleton " + std::to_string(o.skel->num_joints) + " joints", "toString: %s", (*skel)->toString().c_str());
     auto bad = skelLoader(dir + "/Idle01.ozz");
     CHECK(!bad && bad.error() == "archive does not contain the type", "wrong archive type must keep darmok's message");
+    // OzzSkeletalAnimationLoader answers every failure with one text (src/skeleton_ozz.cpp:207-216): wrong archive type, missing file
+    auto notAnim = animLoader(dir + "/skeleton.ozz");
+    CHECK(!notAnim && notAnim.error() == "archive doesn't contain an animation", "a skeleton archive is not an animation: %s", notAnim ? "" : notAnim.error().c_str());
+    auto missing = animLoader(dir + "/no_such_clip.ozz");
+    CHECK(!missing && missing.error() == "archive doesn't contain an animation", "missing animation file: %s", missing ? "" : missing.error().c_str());
+    auto missingSkel = skelLoader(dir + "/no_such_skeleton.ozz");
+    CHECK(!missingSkel && !missingSkel.error().empty() && missingSkel.error() != "archive does not contain the type", "missing skeleton file passes the data loader's message on");
     SkeletalAnimationMap anims;
     for (const char* n : kClipNames) {
         auto a = animLoader(dir + "/" + std::string(n) + ".ozz");
