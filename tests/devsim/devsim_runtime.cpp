@@ -371,7 +371,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void
                         if (t >= nthreads) continue;
                         Fiber& f = b.fibers[t];
                         if (f.done) continue;
-                        if (g_skip_warp) { all_blocked = false; continue; }
+                        if (g_skip_warp) continue;   // (its fibers keep the blocked / not blocked state of their last run)
                         g_cur = &f;
                         g_thread_idx = f.tid;
                         f.blocked = false;
@@ -383,11 +383,14 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void
 #else
                         switch_context(g_scheduler, f.ctx);
 #endif
-                        if (!f.done && !f.blocked) all_blocked = false;
                     }
                     g_cur = nullptr;
+                    // deadlock: every live fiber sits in a wait that only another fiber can end, and round after round nothing changes
+                    // (64 rounds: under the random schedule a fiber only runs in about every other one)
+                    for (size_t t = 0; t < nthreads && all_blocked; ++t)
+                        if (!b.fibers[t].done && !b.fibers[t].blocked) all_blocked = false;
                     if (b.live > 0 && all_blocked && b.progress == before) {
-                        if (++idle_rounds > 4) trap("deadlock: every live thread of the block waits and nothing changes");
+                        if (++idle_rounds > 64) trap("deadlock: every live thread of the block waits and nothing changes");
                     } else {
                         idle_rounds = 0;
                     }
