@@ -14,6 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.gpu
 @pytest.mark.xfail(reason="draws skinning shapes not yet verified on hardware (round 1 GPU budget spent)", strict=False)
 def test_random_configurations_match_the_oracle():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "crowd_fuzz_check.py"), "1", "60"], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "crowd_fuzz_check.py"), "1", "60"], capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0 and "60 configurations match the oracle" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -14,6 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.gpu
 @pytest.mark.xfail(reason="planar / three-stream skinning shapes not yet verified on hardware (round 1 GPU budget spent)", strict=False)
 def test_character_loop_of_every_skinning_shape_matches_the_oracle():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "skin_ring_check.py")], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "skin_ring_check.py")], capture_output=True, text=True, timeout=300)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "cases match the oracle" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
