@@ -30,8 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SKIN_KERNEL_NAMES = {0: "skin_kernel<8> (K5 LBS)", 1: "skin_kernel<8, planar, 4 vertices/thread, <= 320 threads> (K5 LBS)",
-                     2: "skin_kernel<8, planar, 4 vertices/thread, <= 448 threads> (K5 LBS)", 3: "skin_kernel<8, three float3 streams> (K5 LBS)"}
-SKIN_LAYOUTS = {0: "interleaved [V][9]", 1: "nine component planes [9][V]", 2: "nine component planes [9][V]", 3: "three float3 streams [3][V][3]"}
+                     2: "skin_kernel<8, planar, 4 vertices/thread, <= 448 threads> (K5 LBS)", 3: "skin_kernel<8, three float3 streams> (K5 LBS)",
+                     4: "skin_kernel<8, planar, 8 vertices/thread> (K5 LBS)"}
+SKIN_LAYOUTS = {0: "interleaved [V][9]", 1: "nine component planes [9][V]", 2: "nine component planes [9][V]", 3: "three float3 streams [3][V][3]", 4: "nine component planes [9][V]"}
 METRIC = "skinned_characters_per_sec"
 UNIT = "characters/s"
 FLT_MIN = float(np.finfo(np.float32).tiny)
@@ -569,9 +570,9 @@ def main():
     ap.add_argument("--clips", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs left to the gather so that it overlaps the skinning")
-    ap.add_argument("--skin-layout", type=int, default=0, choices=[0, 1, 2, 3],
+    ap.add_argument("--skin-layout", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="DMK_OPT_SKIN_PLANAR_OUTPUT: 0 interleaved [V][9] (default), 1 / 2 nine component planes (10 / 14 warps), 3 three float3 "
-                         "streams; not yet measured on hardware, see DESIGN.md section 9")
+                         "streams, 4 nine planes from the default thread shape; not yet measured on hardware, see DESIGN.md section 9")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
                     help="N > 1: visible-palette transport: pack kernel + NCCL send/recv, or the pack+transfer kernel storing into rank 0's "
                          "memory over NVLink (dmk_exchange_*; not yet measured on hardware, see DESIGN.md section 5)")

@@ -100,7 +100,7 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
         return DMK_OK;
     }
     if (option == DMK_OPT_SKIN_PLANAR_OUTPUT) {
-        if (value < 0 || value > 3) return fail(c->ctx, DMK_ERR_INVALID, "DMK_OPT_SKIN_PLANAR_OUTPUT takes 0, 1, 2 or 3");
+        if (value < 0 || value > 4) return fail(c->ctx, DMK_ERR_INVALID, "DMK_OPT_SKIN_PLANAR_OUTPUT takes 0, 1, 2, 3 or 4");
         if (value) {
             auto supported = [&](dmk_mesh_t m) { return !m || plan_skin(m->vpad, m->palette_size, c->ctx->num_sms, value).replicas == 8; };
             bool ok = supported(c->mesh);
@@ -123,7 +123,7 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
 }
 
 dmk_status dmk_skin_plan(int vertex_pitch, int palette_size, int num_sms, int layout, int64_t* out7) {
-    if (!out7 || vertex_pitch < 8 || vertex_pitch % 8 || palette_size < 1 || palette_size > kMaxPalette || num_sms < 1 || layout < 0 || layout > 3)
+    if (!out7 || vertex_pitch < 8 || vertex_pitch % 8 || palette_size < 1 || palette_size > kMaxPalette || num_sms < 1 || layout < 0 || layout > 4)
         return fail(nullptr, DMK_ERR_INVALID, "dmk_skin_plan: argument out of range");
     const SkinPlan plan = plan_skin(vertex_pitch, palette_size, num_sms, layout);
     cudaGetLastError();   // without a device the occupancy query fails and the plan assumes one block per SM

@@ -33,7 +33,7 @@ struct SkinPlan {
     int replicas;       // palette replicas in shared memory (bank-conflict-free gathers)
     size_t smem;
     int variant;        // 0: interleaved [V][9] output, 8 vertices per thread; 1 / 2: planar [9][V] output, 4 per thread, <= 320 / 448 threads;
-                        // 3: three float3 streams [3][V][3], 8 per thread
+                        // 3: three float3 streams [3][V][3], 8 per thread; 4: planar [9][V], 8 per thread
 };
 SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant = 0);
 cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t stream);

@@ -70,12 +70,14 @@ __device__ __forceinline__ float4 blend_row(const Rows4& x, float w0, float w1, 
 //     4 consecutive vertices are 16 contiguous bytes of every plane, so each warp store covers 512 contiguous bytes --
 //     whole 128-byte lines instead of 32 scattered sectors -- and half the vertices per thread leave room for 10 (MAXT =
 //     320, up to 204 registers) or 14 warps (MAXT = 448, up to 144 registers) per SM instead of 7.
+//   VPT = 8, PLANAR = true: the same nine planes from the default thread shape -- a thread's 8 vertices are 32 contiguous bytes of
+//     every plane (one st.v8 per plane, held back until the 8th vertex is done): the store layout alone, occupancy as the default.
 //   VPT = 8, STREAMS = true: three float3 streams per character, [N][3][V][3] (positions, normals, tangents: the usual
 //     non-interleaved vertex-buffer layout); a thread's 8 vertices are 96 contiguous bytes = 3 whole sectors of each stream,
 //     flushed as they complete like the interleaved sectors; a warp store then touches 24 lines instead of 32.
 template <int REPL, bool SKIP, int VPT = 8, bool PLANAR = false, int MAXT = kMaxThreads, bool STREAMS = false>
 __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
-    static_assert(PLANAR ? VPT == 4 : VPT == 8, "interleaved output needs 8 vertices per thread (9 whole sectors); planar uses 4 (st.v4 per plane)");
+    static_assert(VPT == 8 || (PLANAR && VPT == 4), "interleaved / stream output needs 8 vertices per thread (whole sectors); planar takes 4 (st.v4 per plane) or 8 (st.v8)");
     static_assert(!(PLANAR && STREAMS), "one output layout at a time");
     constexpr int kVPT = VPT;   // shadows the file-level constant inside this kernel
     DMK_DYNAMIC_SMEM(smem, 128);
@@ -241,7 +243,14 @@ __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
                     // the character; this thread's 4 vertices are 16 contiguous bytes of each
                     float* plane = p.out + (size_t)cid * 9 * p.vpad + v0;
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) st_v4(plane + (size_t)c * p.vpad, res[c], res[9 + c], res[18 + c], res[27 + c]);
+                    for (int c = 0; c < 9; ++c) {
+                        if (VPT == 4) {
+                            st_v4(plane + (size_t)c * p.vpad, res[c], res[9 + c], res[18 + c], res[27 + c]);
+                        } else {   // 8 vertices: 32 contiguous bytes of the plane, one whole sector per lane
+                            const float v8[8] = {res[c], res[9 + c], res[18 + c], res[27 + c], res[36 + c], res[45 + c], res[54 + c], res[63 + c]};
+                            st_v8(plane + (size_t)c * p.vpad, v8);
+                        }
+                    }
                 }
             }
             ++q_comp;
@@ -259,6 +268,7 @@ size_t skin_smem_bytes(int palette_size, int repl) {
 }
 template <typename F>
 auto with_kernel(int repl, bool skip, int variant, F&& f) {
+    if (variant == 4) return skip ? f(skin_kernel<8, true, 8, true>) : f(skin_kernel<8, false, 8, true>);   // planar output, the default kernel's thread shape
     if (variant == 3) return skip ? f(skin_kernel<8, true, 8, false, kMaxThreads, true>) : f(skin_kernel<8, false, 8, false, kMaxThreads, true>);   // three float3 streams
     if (variant == 1) return skip ? f(skin_kernel<8, true, 4, true, 320>) : f(skin_kernel<8, false, 4, true, 320>);   // planar output, up to 10 warps
     if (variant == 2) return skip ? f(skin_kernel<8, true, 4, true, 448>) : f(skin_kernel<8, false, 4, true, 448>);   // planar output, up to 14 warps

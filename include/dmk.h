@@ -148,7 +148,9 @@ enum {
      * character, [N][9][vertex_pitch] (plane 0..2 position.xyz, 3..5 normal.xyz, 6..8 tangent.xyz), for consumers that
      * pull vertices from buffers; the skinning kernel then keeps 4 vertices per thread and writes whole 128-byte lines
      * (1: up to 10 warps per SM, 2: up to 14).  3: three float3 streams per character, [N][3][vertex_pitch][3] (positions,
-     * normals, tangents: the usual non-interleaved vertex-buffer layout), same thread shape as the default.  The host getters (dmk_crowd_get_skinned, dmk_crowd_get_skin_skinned)
+     * normals, tangents: the usual non-interleaved vertex-buffer layout), same thread shape as the default.  4: the nine planes of 1 / 2
+     * written by the default kernel's thread shape (8 vertices per thread, one whole sector of every plane per lane): the store
+     * layout alone, without the change of occupancy.  The host getters (dmk_crowd_get_skinned, dmk_crowd_get_skin_skinned)
      * return [count][V][9] whatever the device layout is.  DMK_ERR_UNSUPPORTED for palettes above 181 slots.  EXPERIMENTAL: compiled and tested against the reference layout, not yet timed. */
     DMK_OPT_SKIN_PLANAR_OUTPUT = 4
 };

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Stand-alone check of the non-interleaved skinning kernels (DMK_OPT_SKIN_PLANAR_OUTPUT = 1, 2, 3), run by
+"""Stand-alone check of the non-interleaved skinning kernels (DMK_OPT_SKIN_PLANAR_OUTPUT = 1, 2, 3, 4), run by
 tests/test_gpu_zz_skin_planar.py in a child process (a device fault here must not poison the parity suite's CUDA context).
 
 For every variant and a set of vertex counts around the tile boundaries of both shapes: the skinned vertices returned by
@@ -51,7 +51,7 @@ def main():
         bits, count = crowd.get_visibility()
         visible = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
         vpad = (num_vertices + 7) // 8 * 8
-        for variant in (1, 2, 3):
+        for variant in (1, 2, 3, 4):
             crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
             devmem.fill_f32(crowd.skinned_dev(), n * vpad * 9, float("nan"))
             crowd.step(0.0, capi.STEP_SKIN)
@@ -86,7 +86,7 @@ def main():
         assert sorted(order.tolist()) == list(range(2000))
         crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
         crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
-        for variant in (0, 1, 2, 3):
+        for variant in (0, 1, 2, 3, 4):
             crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
             crowd.step(0.0, capi.STEP_POSE | capi.STEP_SKIN)
             assert_close(crowd.get_skinned(), ref["skinned"][:, order], f"sorted mesh (flags {flags}), variant {variant}")

@@ -53,7 +53,7 @@ def main():
             bits, count = crowd.get_visibility()
             visible = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
             assert 148 < count < n, "the visible set must keep every block busy for several characters"
-            for variant in (0, 1, 2, 3):
+            for variant in (0, 1, 2, 3, 4):
                 crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
                 devmem.fill_f32(crowd.skinned_dev(), n * vpad * 9, float("nan"))
                 crowd.step(0.0, capi.STEP_SKIN)

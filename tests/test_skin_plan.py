@@ -6,7 +6,7 @@ import pytest
 
 from darmok_b200 import build, capi
 
-MAX_THREADS = {0: 256, 1: 320, 2: 448, 3: 256}
+MAX_THREADS = {0: 256, 1: 320, 2: 448, 3: 256, 4: 256}
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -14,7 +14,7 @@ def _built():
     build.build()
 
 
-@pytest.mark.parametrize("layout", [0, 1, 2, 3])
+@pytest.mark.parametrize("layout", [0, 1, 2, 3, 4])
 def test_every_vertex_is_owned_by_exactly_one_thread(layout):
     for num_vertices in [1, 7, 8, 9, 255, 1249, 1256, 1281, 1792, 1793, 2048, 2049, 2560, 2561, 5000, 6007, 20000, 65536]:
         vpad = (num_vertices + 7) // 8 * 8

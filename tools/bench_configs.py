@@ -146,7 +146,7 @@ def config3_sorted():
     mesh_s = synth.make_mesh(verts, 67)
     out = {}
     for name, flags, variant in (("caller_order", 0, 0), ("sorted_by_influences", capi.MESH_SORT_BY_INFLUENCES, 0),
-                                 ("planar_output_10_warps", 0, 1), ("planar_output_14_warps", 0, 2), ("three_float3_streams", 0, 3),
+                                 ("planar_output_10_warps", 0, 1), ("planar_output_14_warps", 0, 2), ("three_float3_streams", 0, 3), ("planar_output_default_thread_shape", 0, 4),
                                  ("planar_10_warps_sorted_by_influences", capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4, 1),
                                  ("planar_14_warps_sorted_by_influences", capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4, 2)):
         stream = torch.cuda.Stream()

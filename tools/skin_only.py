@@ -1,4 +1,4 @@
-"""Runs only the skinning kernel of config 3 (for ncu): python tools/skin_only.py [sorted] [planar1|planar2|planar3]"""
+"""Runs only the skinning kernel of config 3 (for ncu): python tools/skin_only.py [sorted] [planar1|planar2|planar3|planar4]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -19,7 +19,7 @@ mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s
 crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
 cr = synth.make_crowd(n, 2, 8, seed=42)
 crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=float(np.finfo(np.float32).tiny))
-for variant in (1, 2, 3):
+for variant in (1, 2, 3, 4):
     if f"planar{variant}" in sys.argv:
         crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
 crowd.step(1 / 60, capi.STEP_POSE)
