@@ -49,5 +49,5 @@ def test_large_palettes_fall_back_to_fewer_replicas_and_fit_shared_memory():
 def test_plan_rejects_bad_arguments():
     out = (capi.C.c_int64 * 7)()
     assert capi.lib().dmk_skin_plan(5001, 68, 148, 0, out) == capi.ERR_INVALID     # pitch not a multiple of 8
-    assert capi.lib().dmk_skin_plan(5000, 68, 148, 4, out) == capi.ERR_INVALID     # unknown layout
+    assert capi.lib().dmk_skin_plan(5000, 68, 148, 5, out) == capi.ERR_INVALID     # unknown layout
     assert capi.lib().dmk_skin_plan(5000, 300, 148, 0, out) == capi.ERR_INVALID
