@@ -31,6 +31,7 @@ UNITS = [
     ("api_results.cu", ["-fmad=false"]),
     ("api_exchange.cu", ["-fmad=false"]),
     ("ozz_io.cpp", []),
+    ("mesh_cluster.cpp", []),
     ("pose_kernel.cu", ["-fmad=false"]),
     ("cull_kernel.cu", ["-fmad=false"]),
     ("animator_kernel.cu", ["-fmad=false"]),

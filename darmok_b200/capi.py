@@ -23,6 +23,7 @@ OPT_FORCE_KEY_SEARCH = 1
 OPT_SKIN_RESERVED_SMS = 2
 OPT_KEEP_WORLD_INVERSE = 3
 OPT_SKIN_PLANAR_OUTPUT = 4
+OPT_SKIN_ROUND1_KERNEL = 5
 GROUP_BLEND, GROUP_PASSTHROUGH, GROUP_ZERO = 0, 1, 2
 TOP_GROUP0, TOP_TRANSITION, TOP_REST_POSE, TOP_SKIP = 0, 1, 2, 3
 PROGRAM_DTYPE = np.dtype([("n0", "u1"), ("n1", "u1"), ("rest0", "u1"), ("rest1", "u1"), ("mode0", "u1"), ("mode1", "u1"),
@@ -69,6 +70,7 @@ SIGNATURES = [
     ("dmk_mesh_create", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
     ("dmk_mesh_create_ex", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u32, C.POINTER(_vp)]),
     ("dmk_mesh_vertex_order", _i, [_vp, _vp]),
+    ("dmk_mesh_cluster_stats", _i, [_vp, _vp, _i, _i, _vp, C.POINTER(_i64)]),
     ("dmk_mesh_destroy", None, [_vp]),
     ("dmk_mesh_num_vertices", _i, [_vp]),
     ("dmk_mesh_vertex_pitch", _i, [_vp]),
@@ -299,6 +301,7 @@ class Armature:
 
 MESH_SORT_BY_INFLUENCES = 1
 MESH_SORT_BLOCKS_OF_4 = 2
+MESH_CLUSTER_BONES = 4
 
 
 class Mesh:
@@ -594,6 +597,18 @@ class Exchange:
         if self.h:
             lib().dmk_exchange_destroy(self.h)
             self.h = None
+
+
+def mesh_cluster_stats(indices, weights, palette_size):
+    """dmk_mesh_cluster_stats (works without a device): the stored order DMK_MESH_CLUSTER_BONES would choose and what it buys"""
+    indices, weights = _f32(indices), _f32(weights)
+    order = np.zeros(indices.shape[0], np.int32)
+    out = (C.c_int64 * 4)()
+    st = lib().dmk_mesh_cluster_stats(_ptr(indices), _ptr(weights), indices.shape[0], palette_size, _ptr(order), out)
+    if st:
+        raise DmkError(st, lib().dmk_last_error(None).decode())
+    keys = ("gather_wavefronts", "gather_wavefronts_caller_order", "shared_blocks", "total_blocks")
+    return order, dict(zip(keys, [int(x) for x in out]))
 
 
 def skin_plan(vertex_pitch, palette_size=68, num_sms=148, layout=0):

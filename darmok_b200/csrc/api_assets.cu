@@ -301,6 +301,53 @@ dmk_status dmk_mesh_vertex_order(dmk_mesh_t mesh, int32_t* out_order) {
     return DMK_OK;
 }
 
+// (slot, weight) pairs per caller vertex: getSkinningMatrixPart reads u_skinning[int(index + 1)]
+// (assets/shaders/core/darmok_skinning.inc.slang:5-14); applySkinning passes vertices with indices.x < 0 through
+// (= 1 * identity, slot 0).
+static bool vertex_influences(const float* indices, const float* weights, int num_vertices, int palette_size, std::vector<ClusterInfluence>& infl,
+                              std::string& err) {
+    infl.resize(static_cast<size_t>(num_vertices));
+    for (int v = 0; v < num_vertices; ++v) {
+        ClusterInfluence& x = infl[static_cast<size_t>(v)];
+        x = ClusterInfluence{{0, 0, 0, 0}, {1.f, 0.f, 0.f, 0.f}};
+        const float* idx = indices + static_cast<size_t>(v) * 4;
+        if (!(idx[0] >= 0.f)) continue;
+        for (int c = 0; c < 4; ++c) {
+            const int slot = static_cast<int>(idx[c] + 1.f);
+            if (!(idx[c] >= -1.f) || slot < 0 || slot >= palette_size) {
+                err = "vertex " + std::to_string(v) + " references bone " + std::to_string(idx[c]) + " outside the palette (size " +
+                      std::to_string(palette_size) + ")";
+                return false;
+            }
+            x.slot[c] = static_cast<uint8_t>(slot);
+            x.weight[c] = weights[static_cast<size_t>(v) * 4 + c];
+        }
+    }
+    return true;
+}
+
+dmk_status dmk_mesh_cluster_stats(const float* indices, const float* weights, int num_vertices, int palette_size, int32_t* out_order,
+                                  int64_t* out_stats4) {
+    if (num_vertices < 0 || (num_vertices > 0 && (!indices || !weights)) || !out_stats4 || palette_size < 1 || palette_size > kMaxPalette)
+        return fail(nullptr, DMK_ERR_INVALID, "dmk_mesh_cluster_stats: argument out of range");
+    std::vector<ClusterInfluence> infl;
+    std::string err;
+    if (!vertex_influences(indices, weights, num_vertices, palette_size, infl, err)) return fail(nullptr, DMK_ERR_INVALID, err);
+    const int vpad = (num_vertices + 7) / 8 * 8;
+    SkinPlan plan{};
+    if (vpad > 0) {
+        plan = plan_skin(vpad, palette_size, 148, 0);
+        cudaGetLastError();   // without a device the occupancy query fails; the tile shape does not depend on it
+    }
+    const ClusterResult cl = cluster_mesh(infl, plan.num_tiles, plan.tile_vertices);
+    if (out_order) std::copy(cl.order.begin(), cl.order.begin() + num_vertices, out_order);
+    out_stats4[0] = cl.gather_wavefronts;
+    out_stats4[1] = cl.gather_wavefronts_unclustered;
+    out_stats4[2] = cl.shared_blocks;
+    out_stats4[3] = cl.total_blocks;
+    return DMK_OK;
+}
+
 dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const float* normal, const float* tangent, const float* indices,
                               const float* weights, int num_vertices, int palette_size, uint32_t flags, dmk_mesh_t* out) {
     if (!ctx || !out || num_vertices < 0 || (num_vertices > 0 && (!position || !normal || !tangent || !indices || !weights)))
@@ -347,9 +394,26 @@ dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const fl
         mesh->sorted = true;
         mesh->sort_block = static_cast<int>(per);
     }
+    std::vector<ClusterInfluence> infl;
+    {
+        std::string err;
+        if (!vertex_influences(indices, weights, num_vertices, palette_size, infl, err)) return fail(ctx, DMK_ERR_INVALID, err);
+    }
+    std::vector<ClusterInfluence> stored;
+    if (flags & DMK_MESH_CLUSTER_BONES) {
+        const SkinPlan plan = plan_skin(vpad, palette_size, ctx->num_sms, 0);
+        ClusterResult cl = cluster_mesh(infl, plan.num_tiles, plan.tile_vertices);
+        mesh->order.assign(cl.order.begin(), cl.order.begin() + num_vertices);   // padding sits behind the last real vertex
+        stored = std::move(cl.stored);
+        mesh->clustered = true;
+        mesh->sorted = true;   // absent influences carry weight 0 behind the present ones: the gathers are predicated
+        mesh->sort_block = 8;
+        mesh->cluster_gather_wavefronts = cl.gather_wavefronts;
+        mesh->cluster_shared_blocks = cl.shared_blocks;
+    }
     for (int s = 0; s < vpad; ++s) {
         float* wv = &w[static_cast<size_t>(s) * 4];
-        wv[0] = 1.f;  // padding and unskinned vertices: 1 * identity
+        wv[0] = 1.f;  // padding: 1 * identity
         if (s >= num_vertices) continue;
         const int v = mesh->order[static_cast<size_t>(s)];
         for (int k = 0; k < 3; ++k) {
@@ -357,16 +421,11 @@ dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const fl
             nrm[static_cast<size_t>(s) * 3 + k] = normal[static_cast<size_t>(v) * 3 + k];
             tan[static_cast<size_t>(s) * 3 + k] = tangent[static_cast<size_t>(v) * 3 + k];
         }
-        const float* idx = indices + static_cast<size_t>(v) * 4;
-        if (!(idx[0] >= 0.f)) continue;  // applySkinning: `if (indices.x >= 0)` else the vertex passes through
+        const ClusterInfluence& x = mesh->clustered ? stored[static_cast<size_t>(s)] : infl[static_cast<size_t>(v)];
         uint32_t packed = 0;
         for (int c = 0; c < 4; ++c) {
-            const int slot = static_cast<int>(idx[c] + 1.f);  // getSkinningMatrixPart: u_skinning[int(v + 1)]
-            if (!(idx[c] >= -1.f) || slot < 0 || slot >= palette_size)
-                return fail(ctx, DMK_ERR_INVALID, "vertex " + std::to_string(v) + " references bone " + std::to_string(idx[c]) +
-                                                      " outside the palette (size " + std::to_string(palette_size) + ")");
-            packed |= static_cast<uint32_t>(slot) << (8 * c);
-            wv[c] = weights[static_cast<size_t>(v) * 4 + c];
+            packed |= static_cast<uint32_t>(x.slot[c]) << (8 * c);
+            wv[c] = x.weight[c];
         }
         slots[s] = packed;
     }

@@ -94,23 +94,30 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
     if (option == DMK_OPT_SKIN_RESERVED_SMS) {
         if (value < 0 || value >= c->ctx->num_sms) return fail(c->ctx, DMK_ERR_INVALID, "reserved SM count out of range");
         c->reserved_sms = value;
-        if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - value, c->skin_variant);
+        if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - value, c->skin_variant, c->skin_legacy);
         for (auto& x : c->extra_skins)
-            if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - value, c->skin_variant);
+            if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - value, c->skin_variant, c->skin_legacy);
         return DMK_OK;
     }
     if (option == DMK_OPT_SKIN_PLANAR_OUTPUT) {
         if (value < 0 || value > 4) return fail(c->ctx, DMK_ERR_INVALID, "DMK_OPT_SKIN_PLANAR_OUTPUT takes 0, 1, 2, 3 or 4");
         if (value) {
-            auto supported = [&](dmk_mesh_t m) { return !m || plan_skin(m->vpad, m->palette_size, c->ctx->num_sms, value).replicas == 8; };
+            auto supported = [&](dmk_mesh_t m) { return !m || plan_skin(m->vpad, m->palette_size, c->ctx->num_sms, value, c->skin_legacy).replicas == 8; };
             bool ok = supported(c->mesh);
             for (auto& x : c->extra_skins) ok = ok && supported(x.mesh);
             if (!ok) return fail(c->ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots");
         }
         c->skin_variant = value;
-        if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - c->reserved_sms, value);
+        if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - c->reserved_sms, value, c->skin_legacy);
         for (auto& x : c->extra_skins)
-            if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - c->reserved_sms, value);
+            if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - c->reserved_sms, value, c->skin_legacy);
+        return DMK_OK;
+    }
+    if (option == DMK_OPT_SKIN_ROUND1_KERNEL) {
+        c->skin_legacy = value != 0;
+        if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - c->reserved_sms, c->skin_variant, c->skin_legacy);
+        for (auto& x : c->extra_skins)
+            if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - c->reserved_sms, c->skin_variant, c->skin_legacy);
         return DMK_OK;
     }
     if (option == DMK_OPT_KEEP_WORLD_INVERSE) {
@@ -720,7 +727,7 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
             p.palette_size = c->mesh->palette_size;
             p.num_tiles = c->plan.num_tiles;
             p.tile_vertices = c->plan.tile_vertices;
-            p.skip_zero_weights = c->mesh->sorted ? 1 : 0;
+            p.vertex_order_mode = c->mesh->clustered ? 2 : c->mesh->sorted ? 1 : 0;
             {
                 KernelTimer timer(ctx, DMK_KERNEL_SKIN);
                 DMK_CUDA(ctx, launch_skin(p, c->plan, s));
@@ -741,7 +748,7 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
             q.palette_size = x.mesh->palette_size;
             q.num_tiles = x.plan.num_tiles;
             q.tile_vertices = x.plan.tile_vertices;
-            q.skip_zero_weights = x.mesh->sorted ? 1 : 0;
+            q.vertex_order_mode = x.mesh->clustered ? 2 : x.mesh->sorted ? 1 : 0;
             {
                 KernelTimer timer(ctx, DMK_KERNEL_SKIN);
                 DMK_CUDA(ctx, launch_skin(q, x.plan, s));

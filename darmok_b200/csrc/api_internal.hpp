@@ -11,6 +11,7 @@
 #include "device_types.cuh"
 #include "host_math.hpp"
 #include "kernels.cuh"
+#include "mesh_cluster.hpp"
 #include "ozz_io.hpp"
 
 #include <algorithm>
@@ -98,6 +99,9 @@ struct dmk_mesh_s {
     std::vector<int32_t> order;  // order[i] = caller's index of the vertex stored at position i
     bool sorted = false;
     int sort_block = 0;          // vertices per thread the influence grouping was dealt for (8 or 4)
+    bool clustered = false;      // DMK_MESH_CLUSTER_BONES: every 8-vertex block names its common bone in entry 0 of its first vertex
+    int64_t cluster_gather_wavefronts = 0;
+    int cluster_shared_blocks = 0;
 };
 
 struct dmk_crowd_s {
@@ -159,6 +163,7 @@ struct dmk_crowd_s {
     std::vector<ExtraSkin> extra_skins;
     int reserved_sms = 0;
     int skin_variant = 0;   // DMK_OPT_SKIN_PLANAR_OUTPUT
+    bool skin_legacy = false;   // DMK_OPT_SKIN_ROUND1_KERNEL
     // device-side animators (dmk_crowd_set_animator)
     AnimStateDef* d_anim_states = nullptr;
     AnimClipDef* d_anim_clips = nullptr;

@@ -150,13 +150,13 @@ dmk_status dmk_crowd_add_skin(dmk_crowd_t c, dmk_armature_t arm, dmk_mesh_t mesh
         dev_free(x.d_skinned);
         return cuda_fail(ctx, e, "dmk_crowd_add_skin allocation");
     }
-    if (mesh && c->skin_variant && plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms, c->skin_variant).replicas != 8) {
+    if (mesh && c->skin_variant && plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms, c->skin_variant, c->skin_legacy).replicas != 8) {
         dev_free(x.d_palette);
         dev_free(x.d_palette34);
         dev_free(x.d_skinned);
         return fail(ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots");
     }
-    if (mesh) x.plan = plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms - c->reserved_sms, c->skin_variant);
+    if (mesh) x.plan = plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms - c->reserved_sms, c->skin_variant, c->skin_legacy);
     c->extra_skins.push_back(x);
     if (out_skin) *out_skin = static_cast<int>(c->extra_skins.size());
     return DMK_OK;

@@ -106,6 +106,37 @@ __device__ __forceinline__ float4 lds128_if(uint32_t addr, uint32_t take) {
     return v;
 }
 
+// Gather unless the row is already in registers: `fallback` (the block's bone, read once per character) where `take` is 0.
+__device__ __forceinline__ float4 lds128_or(uint32_t addr, uint32_t take, const float4& fallback) {
+    float4 v;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "setp.ne.u32 P1, %5, 0;\n"
+        "mov.f32 %0, %6;\n"
+        "mov.f32 %1, %7;\n"
+        "mov.f32 %2, %8;\n"
+        "mov.f32 %3, %9;\n"
+        "@P1 ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+        "}\n"
+        : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
+        : "r"(addr), "r"(take), "f"(fallback.x), "f"(fallback.y), "f"(fallback.z), "f"(fallback.w));
+    return v;
+}
+
+// Predicated gather that leaves the registers as they are where `take` is 0 (no zero fill): the caller multiplies by a
+// zero weight then, so the registers must hold something finite -- zero, or a row fetched earlier.
+__device__ __forceinline__ void lds128_keep(float4& v, uint32_t addr, uint32_t take) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "setp.ne.u32 P1, %5, 0;\n"
+        "@P1 ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+        "}\n"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+        : "r"(addr), "r"(take));
+}
+
 // ---- system scope (peer memory over NVLink) -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;

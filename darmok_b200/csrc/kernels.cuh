@@ -32,10 +32,12 @@ struct SkinPlan {
     int grid;           // persistent blocks
     int replicas;       // palette replicas in shared memory (bank-conflict-free gathers)
     size_t smem;
+    int stages;         // bulk-copy staging depth
+    bool legacy;        // the round-1 kernel shape (every warp replicates and skins) instead of producer warp + compute warps
     int variant;        // 0: interleaved [V][9] output, 8 vertices per thread; 1 / 2: planar [9][V] output, 4 per thread, <= 320 / 448 threads;
                         // 3: three float3 streams [3][V][3], 8 per thread; 4: planar [9][V], 8 per thread
 };
-SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant = 0);
+SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant = 0, bool legacy = false);
 cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t stream);
 
 // K6 payload: gather palettes of the listed characters into a dense buffer

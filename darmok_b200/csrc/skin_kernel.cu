@@ -259,15 +259,285 @@ __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Warp-specialised shape of the same kernel (round 2).  What the round-1 captures said about the kernel above
+// (profiles/r02_skin_kernel_layout_default.txt): the L1 data pipe is 91 % busy -- 828 M gather wavefronts, 64 M replica
+// stores, 235 M global-store wavefronts (stores cost 64 B per cycle whatever their layout) -- and 18 % of the stall samples
+// are warps parked on an mbarrier: every warp replicates a slice of the next palette BEFORE it skins the current one, so a
+// bulk copy that arrives late (issued only one character ahead, behind 4 TB/s of writes) stops all 7 warps.  Here
+//   * one PRODUCER warp owns the palette path: bulk copies kStages characters ahead, replication into the 3-deep replica
+//     ring, "full" / "empty" mbarriers towards the compute warps.  It needs ~60 LSU instructions per character;
+//   * the COMPUTE warps (up to 7) do nothing but wait for a full replica buffer, skin their 8 vertices and hand the buffer
+//     back.  No warp ever waits for another compute warp;
+//   * SHARE (meshes stored with DMK_MESH_CLUSTER_BONES): entry 0 of the thread's first vertex names the block's bone; its 3
+//     rows are read once per character into registers and every vertex whose entry 0 is that bone skips its gather.  With
+//     SKIP (absent influences are predicated off, whole quarter-warps at a time) the gathers drop from 96 to ~51 LDS.128
+//     per thread and character (dmk_mesh_cluster_stats), which takes the kernel off the L1 data pipe and onto HBM.
+// LAYOUT: 0 interleaved [V][9], 3 three float3 streams [3][V][3], 4 nine planes [9][V]  (DMK_OPT_SKIN_PLANAR_OUTPUT values).
+constexpr int kMaxStages = 4;   // bulk-copy staging ring of the producer warp (SkinParams::num_stages: 4, or 2 where shared memory is short)
+
+template <int REPL, bool SKIP, bool SHARE, int LAYOUT>
+__global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParams p) {
+    static_assert(LAYOUT == 0 || LAYOUT == 3 || LAYOUT == 4, "8 vertices per thread: interleaved, three streams or nine planes");
+    constexpr int kVPT = 8;
+    constexpr bool STREAMS = LAYOUT == 3, PLANAR = LAYOUT == 4;
+    DMK_DYNAMIC_SMEM(smem, 128);
+    const int PS = p.palette_size;
+    const uint32_t pal_bytes = (uint32_t)PS * 64u;             // staged palette: 3 rows of 4 floats + 1 pad row per slot
+    const uint32_t repl_bytes = (uint32_t)PS * 48u * REPL;     // replicated: the 3 rows only
+    unsigned char* s_repl = smem;                                        // [kNumRepl][PS*3][REPL] float4
+    const int kStages = p.num_stages;
+    unsigned char* s_stage = smem + kNumRepl * (size_t)repl_bytes;       // [kStages][PS*4] float4 (bulk copy dst)
+    uint64_t* s_tma_bar = reinterpret_cast<uint64_t*>(s_stage + kStages * (size_t)pal_bytes);  // [kStages]
+    uint64_t* s_full_bar = s_tma_bar + kMaxStages;                       // [kNumRepl] producer -> compute warps
+    uint64_t* s_empty_bar = s_full_bar + kNumRepl;                       // [kNumRepl] compute warps -> producer
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncompute = (blockDim.x >> 5) - 1;                          // the last warp is the producer
+    const int tiles_per_pass = min(p.num_tiles, (int)gridDim.x);
+    const int ngroups = gridDim.x / tiles_per_pass;
+    const int tslot = blockIdx.x % tiles_per_pass, group = blockIdx.x / tiles_per_pass;
+    if (group >= ngroups) return;
+
+    int64_t nchars = p.n;
+    if (p.char_ids) nchars = p.char_count[0];
+    const int64_t my_count = nchars > group ? (nchars - group + ngroups - 1) / ngroups : 0;
+    if (my_count == 0) return;
+
+    if (tid == 0) {
+        for (int k = 0; k < kStages; ++k) mbar_init(&s_tma_bar[k], 1);
+        for (int k = 0; k < kNumRepl; ++k) {
+            mbar_init(&s_full_bar[k], 1);
+            mbar_init(&s_empty_bar[k], ncompute);
+        }
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    auto char_of = [&](int64_t i) -> int64_t {
+        const int64_t k = group + i * ngroups;
+        return p.char_ids ? (int64_t)__ldg(p.char_ids + k) : k;
+    };
+    const int passes = (p.num_tiles - tslot + tiles_per_pass - 1) / tiles_per_pass;   // tiles this block walks (1 unless the mesh has more tiles than the grid)
+
+    if (warp == ncompute) {
+        // ---------------- producer warp: items = (tile pass, character), numbered through the whole launch ----------------
+        const int64_t total = (int64_t)passes * my_count;
+        auto issue = [&](int64_t q) {   // lane 0: bulk copy of item q's palette into staging slot q % kStages
+            const uint32_t b = (uint32_t)(q % kStages);   // (lane 0 only, once per character)
+            mbar_expect_tx(&s_tma_bar[b], pal_bytes);
+            bulk_g2s(s_stage + (size_t)b * pal_bytes, p.palette34 + (size_t)char_of(q % my_count) * PS * 16, pal_bytes, &s_tma_bar[b]);
+        };
+        if (lane == 0)
+            for (int64_t q = 0; q < kStages && q < total; ++q) issue(q);
+        uint32_t sb = 0, sphase = 0, rb = 0, rphase = 0;   // staging slot / replica buffer of the current item and their phase parities
+        for (int64_t q = 0; q < total; ++q) {
+            if (q >= kNumRepl) mbar_wait(&s_empty_bar[rb], rphase ^ 1u);   // every compute warp is done with item q - kNumRepl
+            mbar_wait(&s_tma_bar[sb], sphase);
+            // staging -> REPL bank-group-private replicas; lane L writes replica (L + k) & 7 at step k: conflict free
+            const float4* src = reinterpret_cast<const float4*>(s_stage + (size_t)sb * pal_bytes);
+            float4* dst = reinterpret_cast<float4*>(s_repl + (size_t)rb * repl_bytes);
+            for (int t = lane; t < PS * 3; t += 32) {
+                const float4 val = src[(t / 3) * 4 + t % 3];
+#pragma unroll
+                for (int k = 0; k < REPL; ++k) dst[t * REPL + ((lane + k) & (REPL - 1))] = val;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&s_full_bar[rb]);
+                if (q + kStages < total) issue(q + kStages);   // the slot has been read by every lane (the __syncwarp above)
+            }
+            if (++sb == kStages) { sb = 0; sphase ^= 1u; }
+            if (++rb == kNumRepl) { rb = 0; rphase ^= 1u; }
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    const uint32_t lane_off = (uint32_t)(lane & (REPL - 1)) * 16u;
+    const uint32_t repl_base = smem_u32(s_repl) + lane_off;
+    uint32_t rb = 0, rphase = 0;
+    for (int tile = tslot; tile < p.num_tiles; tile += tiles_per_pass) {
+        // ---- this thread's 8 vertices: loaded once, kept in registers for every character ----
+        const int v0 = tile * p.tile_vertices + tid * kVPT;
+        const bool active = tid * kVPT < p.tile_vertices && v0 < p.vpad;
+        float px[kVPT], py[kVPT], pz[kVPT], nx[kVPT], ny[kVPT], nz[kVPT], tx[kVPT], ty[kVPT], tz[kVPT];
+        float w0[kVPT], w1[kVPT], w2[kVPT], w3[kVPT];
+        uint32_t slots[kVPT];
+#pragma unroll
+        for (int v = 0; v < kVPT; ++v) {
+            const int vi = active ? v0 + v : 0;
+            px[v] = __ldg(p.pos + (size_t)vi * 3 + 0); py[v] = __ldg(p.pos + (size_t)vi * 3 + 1); pz[v] = __ldg(p.pos + (size_t)vi * 3 + 2);
+            nx[v] = __ldg(p.nrm + (size_t)vi * 3 + 0); ny[v] = __ldg(p.nrm + (size_t)vi * 3 + 1); nz[v] = __ldg(p.nrm + (size_t)vi * 3 + 2);
+            tx[v] = __ldg(p.tan + (size_t)vi * 3 + 0); ty[v] = __ldg(p.tan + (size_t)vi * 3 + 1); tz[v] = __ldg(p.tan + (size_t)vi * 3 + 2);
+            const float4 w = __ldg(reinterpret_cast<const float4*>(p.weights) + vi);
+            w0[v] = w.x; w1[v] = w.y; w2[v] = w.z; w3[v] = w.w;
+            slots[v] = __ldg(p.slots + vi);
+        }
+        // bit 4 v + k: influence k of vertex v is fetched from shared memory (k = 0: unless it is the block's bone)
+        uint32_t used = 0;
+        const uint32_t block_slot = slots[0] & 0xffu;
+#pragma unroll
+        for (int v = 0; v < kVPT; ++v) {
+            uint32_t u = (SHARE && (slots[v] & 0xffu) == block_slot) ? 0u : 1u;
+            if (SKIP) u |= (w1[v] != 0.f ? 2u : 0u) | (w2[v] != 0.f ? 4u : 0u) | (w3[v] != 0.f ? 8u : 0u);
+            else u |= 14u;
+            used |= u << (4 * v);
+        }
+        const uint32_t block_off = block_slot * (48u * REPL);
+        // bit v: some lane of this warp still gathers entry 0 of its vertex v (mixed blocks only)
+        uint32_t rare = 0;
+        if (SHARE) {
+#pragma unroll
+            for (int v = 0; v < kVPT; ++v) rare |= __ballot_sync(0xffffffffu, (used >> (4 * v) & 1u) != 0u) != 0u ? 1u << v : 0u;
+        }
+
+        for (int64_t i = 0; i < my_count; ++i) {
+            const int64_t cid = char_of(i);
+            mbar_wait(&s_full_bar[rb], rphase);
+            if (active) {
+                const uint32_t base = repl_base + rb * repl_bytes;
+                float4 b0, b1, b2;   // the block's bone, once per character
+                if (SHARE) {
+                    b0 = lds128(base + block_off);
+                    b1 = lds128(base + block_off + 16u * REPL);
+                    b2 = lds128(base + block_off + 32u * REPL);
+                }
+                float res[kVPT * 9];
+                uint32_t a0, a1, a2, a3;
+                auto addr = [&](uint32_t s) {
+                    asm volatile("" : "+r"(s));   // keeps the 32 (vertex, slot) offsets from being hoisted into 24 more registers
+                    a0 = base + (s & 0xffu) * (48u * REPL);
+                    a1 = base + ((s >> 8) & 0xffu) * (48u * REPL);
+                    a2 = base + ((s >> 16) & 0xffu) * (48u * REPL);
+                    a3 = base + (s >> 24) * (48u * REPL);
+                };
+                auto load = [&](int v, int r) {
+                    const uint32_t u = used >> (4 * v);
+                    Rows4 x;
+                    x.q0 = lds128(a0 + r * 16u * REPL);
+                    if (SKIP) {
+                        x.q1 = lds128_if(a1 + r * 16u * REPL, u & 2u);
+                        x.q2 = lds128_if(a2 + r * 16u * REPL, u & 4u);
+                        x.q3 = lds128_if(a3 + r * 16u * REPL, u & 8u);
+                    } else {
+                        x.q1 = lds128(a1 + r * 16u * REPL);
+                        x.q2 = lds128(a2 + r * 16u * REPL);
+                        x.q3 = lds128(a3 + r * 16u * REPL);
+                    }
+                    return x;
+                };
+                // SHARE: rows of influences 1..3; a skipped gather keeps what is there and meets a zero weight, so they start at
+                // zero and only ever hold rows of this character's palette
+                float4 T[3][3];
+                if (SHARE) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) T[k][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                Rows4 cur;
+                if (!SHARE) {
+                    addr(slots[0]);
+                    cur = load(0, 0);
+                }
+#pragma unroll
+                for (int v = 0; v < kVPT; ++v) {
+                    float4 m[3];
+                    if (SHARE) {
+                        // entry 0 is the block's bone (already in registers) for every lane of the warp, except in the few
+                        // mixed blocks: a warp-uniform branch, so the common path carries neither the gather nor a select
+                        addr(slots[v]);
+                        float4 e0 = b0, e1 = b1, e2 = b2;
+                        if (rare >> v & 1u) {
+                            const uint32_t take = used >> (4 * v) & 1u;
+                            e0 = lds128_or(a0, take, b0);
+                            e1 = lds128_or(a0 + 16u * REPL, take, b1);
+                            e2 = lds128_or(a0 + 32u * REPL, take, b2);
+                        }
+                        m[0] = make_float4(w0[v] * e0.x, w0[v] * e0.y, w0[v] * e0.z, w0[v] * e0.w);
+                        m[1] = make_float4(w0[v] * e1.x, w0[v] * e1.y, w0[v] * e1.z, w0[v] * e1.w);
+                        m[2] = make_float4(w0[v] * e2.x, w0[v] * e2.y, w0[v] * e2.z, w0[v] * e2.w);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            lds128_keep(T[0][r], a1 + r * 16u * REPL, w1[v] != 0.f);
+                            lds128_keep(T[1][r], a2 + r * 16u * REPL, w2[v] != 0.f);
+                            lds128_keep(T[2][r], a3 + r * 16u * REPL, w3[v] != 0.f);
+                        }
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            m[r].x = fmaf(w3[v], T[2][r].x, fmaf(w2[v], T[1][r].x, fmaf(w1[v], T[0][r].x, m[r].x)));
+                            m[r].y = fmaf(w3[v], T[2][r].y, fmaf(w2[v], T[1][r].y, fmaf(w1[v], T[0][r].y, m[r].y)));
+                            m[r].z = fmaf(w3[v], T[2][r].z, fmaf(w2[v], T[1][r].z, fmaf(w1[v], T[0][r].z, m[r].z)));
+                            m[r].w = fmaf(w3[v], T[2][r].w, fmaf(w2[v], T[1][r].w, fmaf(w1[v], T[0][r].w, m[r].w)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            Rows4 nxt;  // next row (or row 0 of the next vertex) is requested before this one is consumed
+                            if (r < 2) {
+                                nxt = load(v, r + 1);
+                            } else if (v + 1 < kVPT) {
+                                addr(slots[v + 1]);
+                                nxt = load(v + 1, 0);
+                            }
+                            m[r] = blend_row(cur, w0[v], w1[v], w2[v], w3[v]);
+                            cur = nxt;
+                        }
+                    }
+                    const float m0[3] = {m[0].x, m[1].x, m[2].x}, m1[3] = {m[0].y, m[1].y, m[2].y};
+                    const float m2[3] = {m[0].z, m[1].z, m[2].z}, m3[3] = {m[0].w, m[1].w, m[2].w};
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        // interleaved / planar: vertex-major (v * 9 + attribute * 3 + r); streams: attribute-major (a * 24 + v * 3 + r)
+                        res[STREAMS ? v * 3 + r : v * 9 + r] = fmaf(m2[r], pz[v], fmaf(m1[r], py[v], fmaf(m0[r], px[v], m3[r])));
+                        res[STREAMS ? kVPT * 3 + v * 3 + r : v * 9 + 3 + r] = fmaf(m2[r], nz[v], fmaf(m1[r], ny[v], m0[r] * nx[v]));
+                        res[STREAMS ? kVPT * 6 + v * 3 + r : v * 9 + 6 + r] = fmaf(m2[r], tz[v], fmaf(m1[r], ty[v], m0[r] * tx[v]));
+                    }
+                    if (LAYOUT == 0) {   // flush every 32-byte sector that just became complete
+                        float* out = p.out + ((size_t)cid * p.vpad + v0) * 9;
+#pragma unroll
+                        for (int sct = (v * 9) / 8; sct < ((v + 1) * 9) / 8; ++sct) st_v8(out + sct * 8, res + sct * 8);
+                    }
+                    if (STREAMS) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            float* stream = p.out + (((size_t)cid * 3 + a) * p.vpad + v0) * 3;
+#pragma unroll
+                            for (int sct = (v * 3) / 8; sct < ((v + 1) * 3) / 8; ++sct) st_v8(stream + sct * 8, res + a * kVPT * 3 + sct * 8);
+                        }
+                    }
+                }
+                if (PLANAR) {   // one whole sector of every component plane
+                    float* plane = p.out + (size_t)cid * 9 * p.vpad + v0;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        const float v8[8] = {res[c], res[9 + c], res[18 + c], res[27 + c], res[36 + c], res[45 + c], res[54 + c], res[63 + c]};
+                        st_v8(plane + (size_t)c * p.vpad, v8);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty_bar[rb]);
+            if (++rb == kNumRepl) { rb = 0; rphase ^= 1u; }
+        }
+    }
+}
+
 }  // namespace
 
 namespace {
 constexpr size_t kMaxSmem = 227 * 1024;   // per-CTA shared memory limit on sm_100
-size_t skin_smem_bytes(int palette_size, int repl) {
-    return (size_t)palette_size * (48 * kNumRepl * repl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
+constexpr int kComputeThreads = kMaxThreads - 32;   // warp-specialised shape: the 8th warp is the producer
+// legacy: the round-1 kernel (every warp replicates and skins); the VPT = 4 layouts (1, 2) only exist in that shape
+bool is_legacy(int variant, bool legacy) { return legacy || variant == 1 || variant == 2; }
+size_t skin_smem_bytes(int palette_size, int repl, bool legacy, int stages = kMaxStages) {
+    if (legacy) return (size_t)palette_size * (48 * kNumRepl * repl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
+    return (size_t)palette_size * (48 * kNumRepl * repl + 64 * stages) + 8 * (kMaxStages + 2 * kNumRepl) + 16;
 }
 template <typename F>
-auto with_kernel(int repl, bool skip, int variant, F&& f) {
+auto with_legacy_kernel(int repl, bool skip, int variant, F&& f) {
     if (variant == 4) return skip ? f(skin_kernel<8, true, 8, true>) : f(skin_kernel<8, false, 8, true>);   // planar output, the default kernel's thread shape
     if (variant == 3) return skip ? f(skin_kernel<8, true, 8, false, kMaxThreads, true>) : f(skin_kernel<8, false, 8, false, kMaxThreads, true>);   // three float3 streams
     if (variant == 1) return skip ? f(skin_kernel<8, true, 4, true, 320>) : f(skin_kernel<8, false, 4, true, 320>);   // planar output, up to 10 warps
@@ -280,25 +550,54 @@ auto with_kernel(int repl, bool skip, int variant, F&& f) {
     default: return f(skin_kernel<1, false>);
     }
 }
+// mode: 0 caller's vertex order, 1 influence-sorted (predicated gathers), 2 clustered by bone (block bone in registers + predicated gathers)
+template <int LAYOUT, typename F>
+auto with_ws_layout(int repl, int mode, F&& f) {
+    if (repl == 8) {
+        if (mode == 2) return f(skin_ws_kernel<8, true, true, LAYOUT>);
+        if (mode == 1) return f(skin_ws_kernel<8, true, false, LAYOUT>);
+        return f(skin_ws_kernel<8, false, false, LAYOUT>);
+    }
+    if (LAYOUT != 0) return f(skin_ws_kernel<8, false, false, LAYOUT>);   // (refused earlier: these layouts need 8 replicas)
+    // palettes too large for 8 replicas: fewer, with bank conflicts; sorted meshes take the clustered kernel's predicates
+    // (SHARE only ever compares entry 0 with the block's first vertex, so it is correct on any order)
+    switch (repl) {
+    case 4: return mode ? f(skin_ws_kernel<4, true, true, 0>) : f(skin_ws_kernel<4, false, false, 0>);
+    case 2: return mode ? f(skin_ws_kernel<2, true, true, 0>) : f(skin_ws_kernel<2, false, false, 0>);
+    default: return mode ? f(skin_ws_kernel<1, true, true, 0>) : f(skin_ws_kernel<1, false, false, 0>);
+    }
+}
+template <typename F>
+auto with_kernel(int repl, int mode, int variant, bool legacy, F&& f) {
+    if (is_legacy(variant, legacy)) return with_legacy_kernel(repl, mode != 0, variant, f);
+    if (variant == 3) return with_ws_layout<3>(repl, mode, f);
+    if (variant == 4) return with_ws_layout<4>(repl, mode, f);
+    return with_ws_layout<0>(repl, mode, f);
+}
 }  // namespace
 
-SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant) {
+SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant, bool legacy) {
     SkinPlan plan{};
     plan.variant = variant;
+    plan.legacy = is_legacy(variant, legacy);
     const int vpt = (variant == 1 || variant == 2) ? 4 : kVPT;
-    const int max_threads = variant == 1 ? 320 : variant == 2 ? 448 : kMaxThreads;
+    const int max_threads = variant == 1 ? 320 : variant == 2 ? 448 : plan.legacy ? kMaxThreads : kComputeThreads;
     const int max_tile = max_threads * vpt;
     plan.num_tiles = (vpad + max_tile - 1) / max_tile;
     int tv = (vpad + plan.num_tiles - 1) / plan.num_tiles;
     tv = (tv + kVPT - 1) / kVPT * kVPT;      // multiple of 8 for either shape
     plan.tile_vertices = tv;
-    plan.threads = ((tv / vpt) + 31) / 32 * 32;
+    plan.threads = ((tv / vpt) + 31) / 32 * 32 + (plan.legacy ? 0 : 32);   // + the producer warp
     // 8 replicas make the gathers conflict free; palettes too large for that (> 181 slots) fall back to fewer replicas
+    // (and give up half of the staging depth before giving up replicas)
     plan.replicas = kRepl;
-    while (plan.replicas > 1 && skin_smem_bytes(palette_size, plan.replicas) > kMaxSmem) plan.replicas /= 2;
-    plan.smem = skin_smem_bytes(palette_size, plan.replicas);
+    plan.stages = plan.legacy ? kNumStage : kMaxStages;
+    auto fits = [&] { return skin_smem_bytes(palette_size, plan.replicas, plan.legacy, plan.stages) <= kMaxSmem; };
+    if (!fits() && !plan.legacy) plan.stages = 2;
+    while (plan.replicas > 1 && !fits()) plan.replicas /= 2;
+    plan.smem = skin_smem_bytes(palette_size, plan.replicas, plan.legacy, plan.stages);
     int occ = 1;
-    with_kernel(plan.replicas, false, variant, [&](auto kernel) {
+    with_kernel(plan.replicas, 0, variant, legacy, [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, plan.threads, plan.smem) != cudaSuccess || occ < 1) occ = 1;
         return 0;
@@ -312,7 +611,9 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant) {
 
 cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t stream) {
     if (p.n <= 0 || p.vpad <= 0) return cudaSuccess;
-    return with_kernel(plan.replicas, p.skip_zero_weights != 0, plan.variant, [&](auto kernel) {
+    SkinParams q = p;
+    q.num_stages = plan.stages;
+    return with_kernel(plan.replicas, p.vertex_order_mode, plan.variant, plan.legacy, [&, p = q](auto kernel) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (e != cudaSuccess) return e;
         DMK_LAUNCH(kernel, plan.grid, plan.threads, plan.smem, stream)(p);

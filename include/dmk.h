@@ -117,12 +117,28 @@ enum {
     /* with DMK_MESH_SORT_BY_INFLUENCES: group for the 4-vertices-per-thread skinning shapes of
      * DMK_OPT_SKIN_PLANAR_OUTPUT instead of the default 8-vertices-per-thread kernel (either kernel is correct on either
      * grouping; the matching one skips more gathers) */
-    DMK_MESH_SORT_BLOCKS_OF_4 = 2
+    DMK_MESH_SORT_BLOCKS_OF_4 = 2,
+    /* Store the vertices clustered by bone (supersedes the two flags above).  The skinning kernel's threads own 8 consecutive
+     * stored vertices; with this flag (almost) every such block shares one bone, which the thread then reads once per character
+     * instead of once per vertex, absent influences are skipped by whole quarter-warps, and heavy and light blocks are dealt
+     * evenly over the kernel's tiles and warps.  On a mesh with 1..4 random influences per vertex this halves the kernel's
+     * shared-memory traffic (its limiter); on a real mesh, whose neighbouring vertices share bones anyway, it does at least as
+     * well.  As with DMK_MESH_SORT_BY_INFLUENCES the skinned buffer is in the order dmk_mesh_vertex_order reports, and the 4
+     * (bone, weight) pairs of a vertex may be summed in another order than the caller listed them (same result within 1 ulp of
+     * the 4-term sum).  The reference has no counterpart: its vertex order is whatever the asset importer wrote
+     * (src/mesh_core.cpp:323-365) and the GPU's vertex fetch does not care. */
+    DMK_MESH_CLUSTER_BONES = 4
 };
 DMK_API dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const float* normal, const float* tangent,
                                       const float* indices, const float* weights, int num_vertices, int palette_size,
                                       uint32_t flags, dmk_mesh_t* out);
 DMK_API dmk_status dmk_mesh_vertex_order(dmk_mesh_t mesh, int32_t* out_order);
+/* What DMK_MESH_CLUSTER_BONES would do to a mesh, without a device: the stored order (out_order[num_vertices], may be NULL)
+ * and out_stats[0] = 128-bit shared-memory load wavefronts per character the clustered order needs, [1] = the same for the
+ * caller's order (4 influences x 3 rows per vertex), [2] = 8-vertex blocks that share a bone, [3] = blocks in total.
+ * `indices` / `weights` as for dmk_mesh_create. */
+DMK_API dmk_status dmk_mesh_cluster_stats(const float* indices, const float* weights, int num_vertices, int palette_size,
+                                          int32_t* out_order, int64_t* out_stats4);
 DMK_API void dmk_mesh_destroy(dmk_mesh_t mesh);
 DMK_API int dmk_mesh_num_vertices(dmk_mesh_t mesh);
 DMK_API int dmk_mesh_vertex_pitch(dmk_mesh_t mesh); /* vertices per character in the skinned buffer (V rounded up to 8) */
@@ -152,7 +168,11 @@ enum {
      * written by the default kernel's thread shape (8 vertices per thread, one whole sector of every plane per lane): the store
      * layout alone, without the change of occupancy.  The host getters (dmk_crowd_get_skinned, dmk_crowd_get_skin_skinned)
      * return [count][V][9] whatever the device layout is.  DMK_ERR_UNSUPPORTED for palettes above 181 slots.  EXPERIMENTAL: compiled and tested against the reference layout, not yet timed. */
-    DMK_OPT_SKIN_PLANAR_OUTPUT = 4
+    DMK_OPT_SKIN_PLANAR_OUTPUT = 4,
+    /* Diagnostic: 1 = skin with the round-1 kernel shape (every warp replicates the palette and skins) instead of the
+     * producer-warp / compute-warps shape, for A/B timing of the two on the same crowd.  Layouts 1 and 2 only exist in the
+     * round-1 shape.  Results are identical either way. */
+    DMK_OPT_SKIN_ROUND1_KERNEL = 5
 };
 DMK_API dmk_status dmk_crowd_set_option(dmk_crowd_t crowd, int option, int value);
 /* Launch shape the skinning kernel would use for a mesh of `vertex_pitch` vertices (multiple of 8), a palette of

@@ -40,7 +40,7 @@ def one(seed):
     verts = int(rng.choice([1, 8, 40, 257, 1000, 2100]))
     with_mesh = rng.random() < 0.8
     mesh_s = synth.make_mesh(verts, k, seed=seed, unskinned_fraction=float(rng.choice([0.0, 0.05]))) if with_mesh else None
-    mesh_flags = int(rng.choice([0, capi.MESH_SORT_BY_INFLUENCES, capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4]))
+    mesh_flags = int(rng.choice([0, capi.MESH_SORT_BY_INFLUENCES, capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4, capi.MESH_CLUSTER_BONES]))
     layout = int(rng.integers(0, 5))
     cr = synth.make_crowd(n, layers, num_clips, seed=seed)
     weight = cr.weight.copy()

@@ -229,6 +229,10 @@ inline float4 lds128(uint32_t addr) {
     return v;
 }
 inline float4 lds128_if(uint32_t addr, uint32_t take) { return take ? lds128(addr) : make_float4(0.f, 0.f, 0.f, 0.f); }
+inline void lds128_keep(float4& v, uint32_t addr, uint32_t take) {
+    if (take) v = lds128(addr);
+}
+inline float4 lds128_or(uint32_t addr, uint32_t take, const float4& fallback) { return take ? lds128(addr) : fallback; }
 
 inline uint32_t ld_acquire_sys(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 inline void st_release_sys(uint32_t* p, uint32_t v) {

@@ -80,7 +80,7 @@ def main():
     n = 11
     cr = synth.make_crowd(n, 2, len(base.clips), seed=77)
     ref = O.Crowd(oskel, oclips, remap, base.arm.inv_bind, n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, mesh=mesh_s, want=("skinned",))
-    for flags in (capi.MESH_SORT_BY_INFLUENCES, capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4):
+    for flags in (capi.MESH_SORT_BY_INFLUENCES, capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4, capi.MESH_CLUSTER_BONES):
         mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size, flags=flags)
         order = mesh.order
         assert sorted(order.tolist()) == list(range(2000))

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""The character loop of the skinning kernel: every persistent block walks MANY characters, so the 2-deep bulk-copy staging
+"""The character loop of the skinning kernel: every persistent block walks MANY characters, so the bulk-copy staging
 ring, the 3-deep replica ring and their mbarrier hand-offs wrap around several times (the small crowds of the other parity
-tests give a block one character at most).  Every output shape, caller's vertex order and influence-sorted (predicated
-gathers), several vertex counts (1 tile / 2 tiles, full and ragged last warp), visible-only; against the oracle.
+tests give a block one character at most).  Every output shape, caller's vertex order, influence-sorted (predicated
+gathers) and clustered by bone (block bone in registers), several vertex counts (1 tile / 2 tiles, full and ragged last warp), visible-only; against the oracle.
 
 Runs on a GPU or on the CPU lockstep simulator (DMK_DEVSIM=1; DMK_DEVSIM_SEED picks a random warp schedule with delayed
 bulk copies -- tests/test_devsim.py runs a few).
@@ -42,7 +42,7 @@ def main():
         inst = synth.make_instances(n, seed=3, extent=60.0)
         ref = O.Crowd(oskel, oclips, remap, base.arm.inv_bind, n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, mesh=mesh_s, want=("skinned",))["skinned"]
         vpad = (num_vertices + 7) // 8 * 8
-        for flags in (0, capi.MESH_SORT_BY_INFLUENCES, capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4):
+        for flags in (0, capi.MESH_SORT_BY_INFLUENCES, capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4, capi.MESH_CLUSTER_BONES):
             mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size, flags=flags)
             want = ref[:, mesh.order] if flags else ref
             crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
@@ -53,15 +53,17 @@ def main():
             bits, count = crowd.get_visibility()
             visible = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
             assert 148 < count < n, "the visible set must keep every block busy for several characters"
-            for variant in (0, 1, 2, 3, 4):
+            # (layout, round-1 kernel shape): layouts 0 / 3 / 4 exist as producer-warp + compute-warps kernel and in the round-1 shape
+            for variant, round1 in ((0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (0, 1), (3, 1), (4, 1)):
+                crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, round1)
                 crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
                 devmem.fill_f32(crowd.skinned_dev(), n * vpad * 9, float("nan"))
                 crowd.step(0.0, capi.STEP_SKIN)
-                assert_close(crowd.get_skinned(), want, f"V={num_vertices} mesh flags {flags} layout {variant}")
+                assert_close(crowd.get_skinned(), want, f"V={num_vertices} mesh flags {flags} layout {variant} round1 {round1}")
                 devmem.fill_f32(crowd.skinned_dev(), n * vpad * 9, float("nan"))
                 crowd.step(0.0, capi.STEP_SKIN | capi.STEP_SKIN_VISIBLE_ONLY)
                 got = crowd.get_skinned()
-                assert_close(got[visible], want[visible], f"visible-only V={num_vertices} mesh flags {flags} layout {variant}")
+                assert_close(got[visible], want[visible], f"visible-only V={num_vertices} mesh flags {flags} layout {variant} round1 {round1}")
                 assert np.isnan(got[~visible]).all(), "visible-only touched a culled character"
                 checked += 1
             crowd.close()

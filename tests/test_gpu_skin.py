@@ -139,3 +139,32 @@ def test_sorted_mesh_option_permutes_output(assets):
         assert_close(crowd.get_skinned(), ref[:, order], "skinned (sorted order)")
     finally:
         g.close()
+
+
+def test_clustered_mesh_shares_a_bone_per_block_and_matches_the_oracle(assets):
+    # DMK_MESH_CLUSTER_BONES: every 8-vertex block of the stored order carries a common bone (read once per thread and
+    # character), absent influences are skipped; same results, in the order dmk_mesh_vertex_order reports.  Both kernel
+    # shapes and the three 8-vertices-per-thread layouts.
+    from darmok_b200 import capi
+    g, o = GpuRig(assets, with_mesh=False), OracleRig(assets)
+    try:
+        m = assets.mesh
+        g.mesh = capi.Mesh(g.ctx, m.pos, m.nrm, m.tan, m.indices, m.weights, g.arm.palette_size, flags=capi.MESH_CLUSTER_BONES)
+        order = g.mesh.order
+        assert sorted(order.tolist()) == list(range(m.pos.shape[0]))
+        order2, stats = capi.mesh_cluster_stats(m.indices, m.weights, g.arm.palette_size)
+        assert np.array_equal(order, order2)
+        assert stats["gather_wavefronts"] < 0.62 * stats["gather_wavefronts_caller_order"]
+        n = 333
+        cr = synth.make_crowd(n, 2, len(assets.clips), seed=13)
+        crowd = g.crowd(n, 2)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+        ref = o.crowd(n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, mesh=m, want=("skinned",))["skinned"]
+        for round1 in (0, 1):
+            crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, round1)
+            for layout in (0, 3, 4):
+                crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, layout)
+                crowd.step(0.0, capi.STEP_POSE | capi.STEP_SKIN)
+                assert_close(crowd.get_skinned(), ref[:, order], f"skinned (clustered order, layout {layout}, round-1 shape {round1})")
+    finally:
+        g.close()

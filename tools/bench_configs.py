@@ -145,10 +145,19 @@ def config3_sorted():
     arm_s = synth.make_armature(skel_s)
     mesh_s = synth.make_mesh(verts, 67)
     out = {}
-    for name, flags, variant in (("caller_order", 0, 0), ("sorted_by_influences", capi.MESH_SORT_BY_INFLUENCES, 0),
-                                 ("planar_output_10_warps", 0, 1), ("planar_output_14_warps", 0, 2), ("three_float3_streams", 0, 3), ("planar_output_default_thread_shape", 0, 4),
-                                 ("planar_10_warps_sorted_by_influences", capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4, 1),
-                                 ("planar_14_warps_sorted_by_influences", capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4, 2)):
+    S, S4, CL = capi.MESH_SORT_BY_INFLUENCES, capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4, capi.MESH_CLUSTER_BONES
+    # (name, mesh flags, output layout, round-1 kernel shape)
+    cases = [("ws_caller_order", 0, 0, 0), ("ws_caller_order_streams", 0, 3, 0), ("ws_caller_order_planes", 0, 4, 0),
+             ("ws_sorted_by_influences", S, 0, 0),
+             ("ws_clustered", CL, 0, 0), ("ws_clustered_streams", CL, 3, 0), ("ws_clustered_planes", CL, 4, 0),
+             ("round1_caller_order", 0, 0, 1), ("round1_sorted_by_influences", S, 0, 1), ("round1_clustered", CL, 0, 1),
+             ("round1_three_float3_streams", 0, 3, 1), ("round1_planes_8_per_thread", 0, 4, 1),
+             ("round1_planes_10_warps", 0, 1, 1), ("round1_planes_14_warps", 0, 2, 1),
+             ("round1_planes_14_warps_sorted", S4, 2, 1)]
+    only = os.environ.get("DMK_TOOL_CASES")
+    if only:
+        cases = [c for c in cases if c[0] in only.split(",")]
+    for name, flags, variant, round1 in cases:
         stream = torch.cuda.Stream()
         with torch.cuda.stream(stream):
             ctx = capi.Context(0, stream.cuda_stream)
@@ -160,8 +169,9 @@ def config3_sorted():
             crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
             cr = synth.make_crowd(n, 2, 8, seed=42)
             crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+            crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, round1)
             if variant:
-                crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)   # nine component planes, 4 vertices per thread
+                crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
             crowd.step(1 / 60, capi.STEP_POSE)
             for _ in range(3):
                 crowd.step(1 / 60, capi.STEP_SKIN)

@@ -1,10 +1,10 @@
-"""Runs only the skinning kernel of config 3 (for ncu): python tools/skin_only.py [sorted] [planar1|planar2|planar3|planar4]"""
+"""Runs only the skinning kernel of config 3 (for ncu): python tools/skin_only.py [sorted|clustered] [planar1|planar2|planar3|planar4] [round1]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 from darmok_b200 import capi, synth
-flags = capi.MESH_SORT_BY_INFLUENCES if "sorted" in sys.argv else 0
+flags = capi.MESH_CLUSTER_BONES if "clustered" in sys.argv else capi.MESH_SORT_BY_INFLUENCES if "sorted" in sys.argv else 0
 n, verts = int(os.environ.get("DMK_TOOL_CHARS", 100_000)), int(os.environ.get("DMK_TOOL_VERTS", 5000))   # (small for the dry run on the CPU simulator)
 skel_s = synth.make_skeleton(67)
 clips_s = [synth.make_clip(skel_s, f"clip{i}", seed=i, duration=1.5) for i in range(8)]
@@ -19,6 +19,7 @@ mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s
 crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
 cr = synth.make_crowd(n, 2, 8, seed=42)
 crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=float(np.finfo(np.float32).tiny))
+crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, int("round1" in sys.argv))
 for variant in (1, 2, 3, 4):
     if f"planar{variant}" in sys.argv:
         crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
