@@ -105,7 +105,7 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
             auto supported = [&](dmk_mesh_t m) { return !m || plan_skin(m->vpad, m->palette_size, c->ctx->num_sms, value, c->skin_legacy).replicas == 8; };
             bool ok = supported(c->mesh);
             for (auto& x : c->extra_skins) ok = ok && supported(x.mesh);
-            if (!ok) return fail(c->ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots");
+            if (!ok) return fail(c->ctx, DMK_ERR_UNSUPPORTED, "this skinned-output layout needs a palette of at most 226 slots (181 for layouts 1 and 2)");
         }
         c->skin_variant = value;
         if (c->mesh) c->plan = plan_skin(c->mesh->vpad, c->mesh->palette_size, c->ctx->num_sms - c->reserved_sms, value, c->skin_legacy);

@@ -154,7 +154,7 @@ dmk_status dmk_crowd_add_skin(dmk_crowd_t c, dmk_armature_t arm, dmk_mesh_t mesh
         dev_free(x.d_palette);
         dev_free(x.d_palette34);
         dev_free(x.d_skinned);
-        return fail(ctx, DMK_ERR_UNSUPPORTED, "planar skinned output needs a palette of at most 181 slots");
+        return fail(ctx, DMK_ERR_UNSUPPORTED, "this skinned-output layout needs a palette of at most 226 slots (181 for layouts 1 and 2)");
     }
     if (mesh) x.plan = plan_skin(mesh->vpad, mesh->palette_size, ctx->num_sms - c->reserved_sms, c->skin_variant, c->skin_legacy);
     c->extra_skins.push_back(x);

@@ -261,21 +261,30 @@ __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
 
 
 // ------------------------------------------------------------------------------------------------------------------------
-// Warp-specialised shape of the same kernel (round 2).  What the round-1 captures said about the kernel above
+// Warp-specialised shape of the same kernel (round 2).  What the captures said about the kernel above
 // (profiles/r02_skin_kernel_layout_default.txt): the L1 data pipe is 91 % busy -- 828 M gather wavefronts, 64 M replica
 // stores, 235 M global-store wavefronts (stores cost 64 B per cycle whatever their layout) -- and 18 % of the stall samples
 // are warps parked on an mbarrier: every warp replicates a slice of the next palette BEFORE it skins the current one, so a
 // bulk copy that arrives late (issued only one character ahead, behind 4 TB/s of writes) stops all 7 warps.  Here
-//   * one PRODUCER warp owns the palette path: bulk copies kStages characters ahead, replication into the 3-deep replica
-//     ring, "full" / "empty" mbarriers towards the compute warps.  It needs ~60 LSU instructions per character;
-//   * the COMPUTE warps (up to 7) do nothing but wait for a full replica buffer, skin their 8 vertices and hand the buffer
-//     back.  No warp ever waits for another compute warp;
+//   * the palette path runs without the LSU: ONE thread (of a producer warp) issues, per character, 8 bulk copies of the
+//     palette from global memory into a ring of up to 4 replica buffers, several characters ahead; the copies' bytes
+//     complete the buffer's "full" mbarrier; the compute warps return the buffer through its "empty" mbarrier;
+//   * the COMPUTE warps (up to 7) do nothing but wait for a full buffer, skin their 8 vertices and hand the buffer back.
+//     No warp ever waits for another compute warp;
 //   * SHARE (meshes stored with DMK_MESH_CLUSTER_BONES): entry 0 of the thread's first vertex names the block's bone; its 3
 //     rows are read once per character into registers and every vertex whose entry 0 is that bone skips its gather.  With
 //     SKIP (absent influences are predicated off, whole quarter-warps at a time) the gathers drop from 96 to ~51 LDS.128
-//     per thread and character (dmk_mesh_cluster_stats), which takes the kernel off the L1 data pipe and onto HBM.
+//     per thread and character (dmk_mesh_cluster_stats), which takes the kernel off the L1 data pipe.
 // LAYOUT: 0 interleaved [V][9], 3 three float3 streams [3][V][3], 4 nine planes [9][V]  (DMK_OPT_SKIN_PLANAR_OUTPUT values).
-constexpr int kMaxStages = 4;   // bulk-copy staging ring of the producer warp (SkinParams::num_stages: 4, or 2 where shared memory is short)
+constexpr int kMaxRing = 4;   // replica ring of the warp-specialised kernel (SkinParams::num_stages: 4, fewer where shared memory is short)
+
+// Replica layout of the warp-specialised kernel: REPL plain copies of the character's palette34 ([PS][16] floats, rows 0..2 of
+// every slot used), each written by ONE bulk copy straight from global memory -- no thread ever touches the palette on its
+// way in.  Replica r starts at r * RS with RS = 64 PS + 16 pad and pad chosen so that RS / 16 = 1 (mod 8): row `row` of slot
+// s in replica r then sits in bank group (r + 4 s + row) mod 8, and lane L reads replica (L + 4 (s & 1)) mod 8, i.e. bank
+// group (L + row) mod 8 whatever the slot -- the 8 lanes of a quarter-warp never collide, as with the interleaved replicas
+// of the round-1 kernel, for 2 more integer instructions per gather.
+__host__ __device__ inline uint32_t replica_stride(int palette_size) { return (uint32_t)palette_size * 64u + ((palette_size & 1) ? 80u : 16u); }
 
 template <int REPL, bool SKIP, bool SHARE, int LAYOUT>
 __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParams p) {
@@ -284,14 +293,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
     constexpr bool STREAMS = LAYOUT == 3, PLANAR = LAYOUT == 4;
     DMK_DYNAMIC_SMEM(smem, 128);
     const int PS = p.palette_size;
-    const uint32_t pal_bytes = (uint32_t)PS * 64u;             // staged palette: 3 rows of 4 floats + 1 pad row per slot
-    const uint32_t repl_bytes = (uint32_t)PS * 48u * REPL;     // replicated: the 3 rows only
-    unsigned char* s_repl = smem;                                        // [kNumRepl][PS*3][REPL] float4
-    const int kStages = p.num_stages;
-    unsigned char* s_stage = smem + kNumRepl * (size_t)repl_bytes;       // [kStages][PS*4] float4 (bulk copy dst)
-    uint64_t* s_tma_bar = reinterpret_cast<uint64_t*>(s_stage + kStages * (size_t)pal_bytes);  // [kStages]
-    uint64_t* s_full_bar = s_tma_bar + kMaxStages;                       // [kNumRepl] producer -> compute warps
-    uint64_t* s_empty_bar = s_full_bar + kNumRepl;                       // [kNumRepl] compute warps -> producer
+    const uint32_t pal_bytes = (uint32_t)PS * 64u;             // one palette34: 3 rows of 4 floats + 1 pad row per slot
+    const uint32_t RS = replica_stride(PS);
+    const uint32_t buf_bytes = RS * REPL;                      // one ring buffer: REPL replicas
+    const int ring = p.num_stages;
+    unsigned char* s_repl = smem;                                        // [ring][REPL] palettes, RS apart
+    uint64_t* s_full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)ring * buf_bytes);   // [kMaxRing] bulk copies -> compute warps
+    uint64_t* s_empty_bar = s_full_bar + kMaxRing;                       // [kMaxRing] compute warps -> producer
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncompute = (blockDim.x >> 5) - 1;                          // the last warp is the producer
@@ -306,8 +314,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
     if (my_count == 0) return;
 
     if (tid == 0) {
-        for (int k = 0; k < kStages; ++k) mbar_init(&s_tma_bar[k], 1);
-        for (int k = 0; k < kNumRepl; ++k) {
+        for (int k = 0; k < ring; ++k) {
             mbar_init(&s_full_bar[k], 1);
             mbar_init(&s_empty_bar[k], ncompute);
         }
@@ -322,41 +329,29 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
     const int passes = (p.num_tiles - tslot + tiles_per_pass - 1) / tiles_per_pass;   // tiles this block walks (1 unless the mesh has more tiles than the grid)
 
     if (warp == ncompute) {
-        // ---------------- producer warp: items = (tile pass, character), numbered through the whole launch ----------------
-        const int64_t total = (int64_t)passes * my_count;
-        auto issue = [&](int64_t q) {   // lane 0: bulk copy of item q's palette into staging slot q % kStages
-            const uint32_t b = (uint32_t)(q % kStages);   // (lane 0 only, once per character)
-            mbar_expect_tx(&s_tma_bar[b], pal_bytes);
-            bulk_g2s(s_stage + (size_t)b * pal_bytes, p.palette34 + (size_t)char_of(q % my_count) * PS * 16, pal_bytes, &s_tma_bar[b]);
-        };
-        if (lane == 0)
-            for (int64_t q = 0; q < kStages && q < total; ++q) issue(q);
-        uint32_t sb = 0, sphase = 0, rb = 0, rphase = 0;   // staging slot / replica buffer of the current item and their phase parities
-        for (int64_t q = 0; q < total; ++q) {
-            if (q >= kNumRepl) mbar_wait(&s_empty_bar[rb], rphase ^ 1u);   // every compute warp is done with item q - kNumRepl
-            mbar_wait(&s_tma_bar[sb], sphase);
-            // staging -> REPL bank-group-private replicas; lane L writes replica (L + k) & 7 at step k: conflict free
-            const float4* src = reinterpret_cast<const float4*>(s_stage + (size_t)sb * pal_bytes);
-            float4* dst = reinterpret_cast<float4*>(s_repl + (size_t)rb * repl_bytes);
-            for (int t = lane; t < PS * 3; t += 32) {
-                const float4 val = src[(t / 3) * 4 + t % 3];
+        // ---------------- producer: one thread.  Per (tile pass, character): wait until the ring buffer is free, then REPL bulk
+        // copies of the palette into it; their bytes complete the buffer's "full" barrier, nothing else is needed ----------------
+        if (lane != 0) return;
+        uint32_t rb = 0, rphase = 0;
+        bool wrapped = false;
+        for (int pass = 0; pass < passes; ++pass)
+            for (int64_t i = 0; i < my_count; ++i) {
+                if (wrapped) mbar_wait(&s_empty_bar[rb], rphase ^ 1u);   // every compute warp is done with the item `ring` items back
+                const float* src = p.palette34 + (size_t)char_of(i) * PS * 16;
+                unsigned char* dst = s_repl + (size_t)rb * buf_bytes;
+                mbar_expect_tx(&s_full_bar[rb], pal_bytes * REPL);
 #pragma unroll
-                for (int k = 0; k < REPL; ++k) dst[t * REPL + ((lane + k) & (REPL - 1))] = val;
+                for (int r = 0; r < REPL; ++r) bulk_g2s(dst + (size_t)r * RS, src, pal_bytes, &s_full_bar[rb]);
+                if (++rb == (uint32_t)ring) { rb = 0; rphase ^= 1u; wrapped = true; }
             }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&s_full_bar[rb]);
-                if (q + kStages < total) issue(q + kStages);   // the slot has been read by every lane (the __syncwarp above)
-            }
-            if (++sb == kStages) { sb = 0; sphase ^= 1u; }
-            if (++rb == kNumRepl) { rb = 0; rphase ^= 1u; }
-        }
         return;
     }
 
     // ---------------- compute warps ----------------
-    const uint32_t lane_off = (uint32_t)(lane & (REPL - 1)) * 16u;
-    const uint32_t repl_base = smem_u32(s_repl) + lane_off;
+    // this lane's replica for even slots, and how far away its replica for odd slots is (REPL < 8: the same one)
+    const uint32_t lane_repl = (uint32_t)lane & (REPL - 1);
+    const uint32_t repl_base = smem_u32(s_repl) + lane_repl * RS;
+    const uint32_t odd_delta = (((lane_repl ^ 4u) & (REPL - 1)) - lane_repl) * RS;   // (mod 2^32)
     uint32_t rb = 0, rphase = 0;
     for (int tile = tslot; tile < p.num_tiles; tile += tiles_per_pass) {
         // ---- this thread's 8 vertices: loaded once, kept in registers for every character ----
@@ -385,7 +380,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
             else u |= 14u;
             used |= u << (4 * v);
         }
-        const uint32_t block_off = block_slot * (48u * REPL);
+        const uint32_t block_off = block_slot * 64u + ((block_slot & 1u) ? odd_delta : 0u);
         // bit v: some lane of this warp still gathers entry 0 of its vertex v (mixed blocks only)
         uint32_t rare = 0;
         if (SHARE) {
@@ -397,34 +392,35 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
             const int64_t cid = char_of(i);
             mbar_wait(&s_full_bar[rb], rphase);
             if (active) {
-                const uint32_t base = repl_base + rb * repl_bytes;
+                const uint32_t base = repl_base + rb * buf_bytes;
                 float4 b0, b1, b2;   // the block's bone, once per character
                 if (SHARE) {
                     b0 = lds128(base + block_off);
-                    b1 = lds128(base + block_off + 16u * REPL);
-                    b2 = lds128(base + block_off + 32u * REPL);
+                    b1 = lds128(base + block_off + 16u);
+                    b2 = lds128(base + block_off + 32u);
                 }
                 float res[kVPT * 9];
                 uint32_t a0, a1, a2, a3;
+                auto slot_addr = [&](uint32_t slot) { return base + slot * 64u + ((slot & 1u) ? odd_delta : 0u); };
                 auto addr = [&](uint32_t s) {
                     asm volatile("" : "+r"(s));   // keeps the 32 (vertex, slot) offsets from being hoisted into 24 more registers
-                    a0 = base + (s & 0xffu) * (48u * REPL);
-                    a1 = base + ((s >> 8) & 0xffu) * (48u * REPL);
-                    a2 = base + ((s >> 16) & 0xffu) * (48u * REPL);
-                    a3 = base + (s >> 24) * (48u * REPL);
+                    a0 = slot_addr(s & 0xffu);
+                    a1 = slot_addr((s >> 8) & 0xffu);
+                    a2 = slot_addr((s >> 16) & 0xffu);
+                    a3 = slot_addr(s >> 24);
                 };
                 auto load = [&](int v, int r) {
                     const uint32_t u = used >> (4 * v);
                     Rows4 x;
-                    x.q0 = lds128(a0 + r * 16u * REPL);
+                    x.q0 = lds128(a0 + r * 16u);
                     if (SKIP) {
-                        x.q1 = lds128_if(a1 + r * 16u * REPL, u & 2u);
-                        x.q2 = lds128_if(a2 + r * 16u * REPL, u & 4u);
-                        x.q3 = lds128_if(a3 + r * 16u * REPL, u & 8u);
+                        x.q1 = lds128_if(a1 + r * 16u, u & 2u);
+                        x.q2 = lds128_if(a2 + r * 16u, u & 4u);
+                        x.q3 = lds128_if(a3 + r * 16u, u & 8u);
                     } else {
-                        x.q1 = lds128(a1 + r * 16u * REPL);
-                        x.q2 = lds128(a2 + r * 16u * REPL);
-                        x.q3 = lds128(a3 + r * 16u * REPL);
+                        x.q1 = lds128(a1 + r * 16u);
+                        x.q2 = lds128(a2 + r * 16u);
+                        x.q3 = lds128(a3 + r * 16u);
                     }
                     return x;
                 };
@@ -453,17 +449,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
                         if (rare >> v & 1u) {
                             const uint32_t take = used >> (4 * v) & 1u;
                             e0 = lds128_or(a0, take, b0);
-                            e1 = lds128_or(a0 + 16u * REPL, take, b1);
-                            e2 = lds128_or(a0 + 32u * REPL, take, b2);
+                            e1 = lds128_or(a0 + 16u, take, b1);
+                            e2 = lds128_or(a0 + 32u, take, b2);
                         }
                         m[0] = make_float4(w0[v] * e0.x, w0[v] * e0.y, w0[v] * e0.z, w0[v] * e0.w);
                         m[1] = make_float4(w0[v] * e1.x, w0[v] * e1.y, w0[v] * e1.z, w0[v] * e1.w);
                         m[2] = make_float4(w0[v] * e2.x, w0[v] * e2.y, w0[v] * e2.z, w0[v] * e2.w);
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
-                            lds128_keep(T[0][r], a1 + r * 16u * REPL, w1[v] != 0.f);
-                            lds128_keep(T[1][r], a2 + r * 16u * REPL, w2[v] != 0.f);
-                            lds128_keep(T[2][r], a3 + r * 16u * REPL, w3[v] != 0.f);
+                            lds128_keep(T[0][r], a1 + r * 16u, w1[v] != 0.f);
+                            lds128_keep(T[1][r], a2 + r * 16u, w2[v] != 0.f);
+                            lds128_keep(T[2][r], a3 + r * 16u, w3[v] != 0.f);
                         }
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
@@ -520,7 +516,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty_bar[rb]);
-            if (++rb == kNumRepl) { rb = 0; rphase ^= 1u; }
+            if (++rb == (uint32_t)ring) { rb = 0; rphase ^= 1u; }
         }
     }
 }
@@ -532,9 +528,9 @@ constexpr size_t kMaxSmem = 227 * 1024;   // per-CTA shared memory limit on sm_1
 constexpr int kComputeThreads = kMaxThreads - 32;   // warp-specialised shape: the 8th warp is the producer
 // legacy: the round-1 kernel (every warp replicates and skins); the VPT = 4 layouts (1, 2) only exist in that shape
 bool is_legacy(int variant, bool legacy) { return legacy || variant == 1 || variant == 2; }
-size_t skin_smem_bytes(int palette_size, int repl, bool legacy, int stages = kMaxStages) {
+size_t skin_smem_bytes(int palette_size, int repl, bool legacy, int ring = kMaxRing) {
     if (legacy) return (size_t)palette_size * (48 * kNumRepl * repl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
-    return (size_t)palette_size * (48 * kNumRepl * repl + 64 * stages) + 8 * (kMaxStages + 2 * kNumRepl) + 16;
+    return (size_t)replica_stride(palette_size) * repl * ring + 8 * 2 * kMaxRing + 16;
 }
 template <typename F>
 auto with_legacy_kernel(int repl, bool skip, int variant, F&& f) {
@@ -588,12 +584,12 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant, bool le
     tv = (tv + kVPT - 1) / kVPT * kVPT;      // multiple of 8 for either shape
     plan.tile_vertices = tv;
     plan.threads = ((tv / vpt) + 31) / 32 * 32 + (plan.legacy ? 0 : 32);   // + the producer warp
-    // 8 replicas make the gathers conflict free; palettes too large for that (> 181 slots) fall back to fewer replicas
-    // (and give up half of the staging depth before giving up replicas)
+    // 8 replicas make the gathers conflict free; palettes too large for that (> 226 slots; > 181 in the round-1 shape) fall back to fewer replicas
+    // (and give up ring depth, down to 2 buffers, before giving up replicas)
     plan.replicas = kRepl;
-    plan.stages = plan.legacy ? kNumStage : kMaxStages;
+    plan.stages = plan.legacy ? kNumStage : kMaxRing;
     auto fits = [&] { return skin_smem_bytes(palette_size, plan.replicas, plan.legacy, plan.stages) <= kMaxSmem; };
-    if (!fits() && !plan.legacy) plan.stages = 2;
+    while (!plan.legacy && plan.stages > 2 && !fits()) --plan.stages;
     while (plan.replicas > 1 && !fits()) plan.replicas /= 2;
     plan.smem = skin_smem_bytes(palette_size, plan.replicas, plan.legacy, plan.stages);
     int occ = 1;

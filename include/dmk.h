@@ -167,7 +167,7 @@ enum {
      * normals, tangents: the usual non-interleaved vertex-buffer layout), same thread shape as the default.  4: the nine planes of 1 / 2
      * written by the default kernel's thread shape (8 vertices per thread, one whole sector of every plane per lane): the store
      * layout alone, without the change of occupancy.  The host getters (dmk_crowd_get_skinned, dmk_crowd_get_skin_skinned)
-     * return [count][V][9] whatever the device layout is.  DMK_ERR_UNSUPPORTED for palettes above 181 slots.  EXPERIMENTAL: compiled and tested against the reference layout, not yet timed. */
+     * return [count][V][9] whatever the device layout is.  DMK_ERR_UNSUPPORTED for palettes above 226 slots (181 for 1 and 2).  Measured on B200: DESIGN.md K5. */
     DMK_OPT_SKIN_PLANAR_OUTPUT = 4,
     /* Diagnostic: 1 = skin with the round-1 kernel shape (every warp replicates the palette and skins) instead of the
      * producer-warp / compute-warps shape, for A/B timing of the two on the same crowd.  Layouts 1 and 2 only exist in the

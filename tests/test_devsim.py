@@ -164,7 +164,7 @@ def test_skinning_character_loop_under_random_warp_schedules(jobs):
 
 
 def test_random_configurations_on_the_simulator(jobs):
-    # tests/crowd_fuzz_check.py: skeleton / armature / palette sizes (1 .. 300 joints, palettes beyond 181 slots), 1 .. 4 layers,
+    # tests/crowd_fuzz_check.py: skeleton / armature / palette sizes (1 .. 300 joints, palettes beyond 226 slots), 1 .. 4 layers,
     # thresholds that pull the rest pose in, vertex counts / orders / layouts, crowd sizes -- 40 seeds, and 12 more under ASan + UBSan
     # with a random schedule (several hundred seeds were run when this was written; all agree with the oracle)
     assert jobs["fuzz"].returncode == 0 and "40 configurations match the oracle" in jobs["fuzz"].stdout and jobs["fuzz"].clean, jobs["fuzz"].tail

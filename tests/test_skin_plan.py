@@ -40,10 +40,10 @@ def test_every_vertex_is_owned_by_exactly_one_thread(layout):
 
 
 def test_large_palettes_fall_back_to_fewer_replicas_and_fit_shared_memory():
-    for ps in (1, 68, 181, 182, 256):
+    for ps in (1, 68, 181, 226, 227, 256):
         p = capi.skin_plan(5000, ps, 148, 0)
         assert p["smem"] <= 227 * 1024
-        assert p["replicas"] == (8 if ps <= 181 else 4)
+        assert p["replicas"] == (8 if ps <= 226 else 4)
 
 
 def test_plan_rejects_bad_arguments():
