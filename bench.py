@@ -29,9 +29,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SKIN_KERNEL_NAMES = {0: "skin_kernel<8> (K5 LBS)", 1: "skin_kernel<8, planar, 4 vertices/thread, <= 320 threads> (K5 LBS)",
-                     2: "skin_kernel<8, planar, 4 vertices/thread, <= 448 threads> (K5 LBS)", 3: "skin_kernel<8, three float3 streams> (K5 LBS)",
-                     4: "skin_kernel<8, planar, 8 vertices/thread> (K5 LBS)"}
+ROUND1_KERNEL_NAMES = {0: "skin_kernel<8> (K5 LBS)", 1: "skin_kernel<8, planar, 4 vertices/thread, <= 320 threads> (K5 LBS)",
+                       2: "skin_kernel<8, planar, 4 vertices/thread, <= 448 threads> (K5 LBS)", 3: "skin_kernel<8, three float3 streams> (K5 LBS)",
+                       4: "skin_kernel<8, planar, 8 vertices/thread> (K5 LBS)"}
+
+
+def skin_kernel_name(args):
+    """name of the instantiation that runs (also the key of profiles/skin_kernel_traffic.json)"""
+    if args.round1_kernel or args.skin_layout in (1, 2):
+        return ROUND1_KERNEL_NAMES[args.skin_layout]
+    mode = {"caller": "<8, false, false", "clustered": "<8, true, true"}[args.mesh_order]
+    return "skin_ws_kernel%s, %d> (K5 LBS)" % (mode, args.skin_layout)
 SKIN_LAYOUTS = {0: "interleaved [V][9]", 1: "nine component planes [9][V]", 2: "nine component planes [9][V]", 3: "three float3 streams [3][V][3]", 4: "nine component planes [9][V]"}
 METRIC = "skinned_characters_per_sec"
 UNIT = "characters/s"
@@ -43,8 +51,10 @@ def gather_description(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world <= 1:
         return "one GPU: visible palettes packed into a dense device buffer, no exchange"
-    how = ("pack kernel + NCCL send/recv" if getattr(args, "gather", "nccl") == "nccl"
-           else "one pack+transfer kernel storing into rank 0's HBM over NVLink (CUDA IPC peer memory, no NCCL in the frame loop)")
+    how = {"nccl": "pack kernel + NCCL send/recv of fixed-capacity slabs",
+           "peer": "one pack+transfer kernel storing into rank 0's HBM over NVLink (CUDA IPC peer memory, no NCCL in the frame loop)",
+           "peer-ce": "pack kernel into a local buffer + one DMA-engine copy into rank 0's HBM over NVLink (CUDA IPC peer memory) + "
+                      "single-thread flow-control / publish kernels; no NCCL and no SM in the transfer"}[args.gather]
     where = ("on a side stream, overlapped with the skinning kernel (reserved SMs: %d)" % args.reserve_sms if args.reserve_sms > 0
              else "in-stream between cull and skinning")
     return "visible palettes -> rank 0: %s, %s" % (how, where)
@@ -56,6 +66,8 @@ def workload_config(args):
                     "5k verts x 4 influences LBS positions+normals+tangents; + frustum cull and visible-palette gather",
         "characters_per_gpu": args.chars, "joints": 67, "layers": 2, "clips": args.clips, "vertices": args.verts,
         "influences": 4, "dt": DT, "skinned_layout": SKIN_LAYOUTS[getattr(args, "skin_layout", 0)],
+        "mesh_vertex_order": ("stored clustered by bone (dmk_mesh_create_ex DMK_MESH_CLUSTER_BONES: a permutation the library reports through "
+                              "dmk_mesh_vertex_order; same vertices, same results)" if args.mesh_order == "clustered" else "caller's order"),
         "gather": gather_description(args),
         "l2": "inputs larger than L2: each step streams %.1f GB of skinned vertices per GPU (L2 = 126 MB)"
               % (args.chars * args.verts * 36 / 1e9),
@@ -89,7 +101,9 @@ def cpu_reference_rate(args, assets, sample_chars, steps, warmup):
     oskel = O.Skeleton(skel.archive)
     oclips = [O.Animation(c.archive) for c in clips]
     remap = np.array([oskel.find_joint(n) for n in arm.names], np.int32)
-    threads = min(host_threads(), O.max_threads())
+    # every core this process may run on, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1): the oracle takes
+    # the thread count as an argument (`#pragma omp parallel num_threads(n)`)
+    threads = host_threads()
     crowd = O.Crowd(oskel, oclips, remap, arm.inv_bind, sample_chars, 2)
     cr = synth.make_crowd(sample_chars, 2, len(clips), seed=42)
     durations = np.array([c.duration for c in clips], np.float32)
@@ -112,19 +126,22 @@ def run_reference(args):
     if rank != 0:
         return 0
     assets = make_assets(args)
-    # bounded sample: calibrate on a small crowd, then size each step to ~2 s of CPU work
+    # bounded sample: calibrate on a small crowd, then the whole job (N x characters per GPU) if a step of it stays under ~3 s of
+    # CPU work, else as many characters as 3 s buy.  ms_per_step is what was measured, for `sample` characters: NOT extrapolated
+    # (value = characters/s is the rate either way)
     probe_rate, threads, _ = cpu_reference_rate(args, assets, 64 * max(1, host_threads()) // 4 + 64, 1, 1)
-    sample = int(max(256, min(args.chars, probe_rate * 2.0)))
+    total_chars = args.chars * max(1, args.gpus)
+    sample = int(max(256, min(total_chars, probe_rate * 3.0)))
     rate, threads, sec_per_step = cpu_reference_rate(args, assets, sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3 * (args.chars / sample), "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "characters_per_step": sample, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} characters of the workload per step (sample+blend+L2M+palette+LBS of "
-                                   f"{args.verts} vertices each), OpenMP over {threads} threads; ms_per_step is "
-                                   "extrapolated to the full crowd; oracle port with exact 1/x, 1/sqrt (ozz simd_ref "
-                                   "semantics), not upstream ozz SSE code"},
+                                   f"{args.verts} vertices each) out of {total_chars}, OpenMP over {threads} threads; "
+                                   "ms_per_step is the measured time of those characters (not extrapolated); oracle port with "
+                                   "exact 1/x, 1/sqrt (ozz simd_ref semantics), not upstream ozz SSE code"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -294,8 +311,11 @@ def run_gpu(args):
         clip_objs = [capi.Clip(ctx, c.archive) for c in clips_s]
         clips = capi.ClipSet(ctx, skel, clip_objs)
         arm = capi.Armature(ctx, skel, arm_s.names, arm_s.inv_bind)
-        mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size)
+        mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size,
+                         flags=capi.MESH_CLUSTER_BONES if args.mesh_order == "clustered" else 0)
         crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
+        if args.round1_kernel:
+            crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, 1)
         if args.skin_layout:
             crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, args.skin_layout)
         cr = synth.make_crowd(n, 2, len(clips_s), seed=42 + rank)       # varied clips / phases per rank
@@ -327,10 +347,13 @@ def run_gpu(args):
         comm_stream = None
         if world > 1:
             from darmok_b200.parallel import PeerPaletteExchange, VisiblePaletteGather
-            if args.gather == "peer":
-                # pack + transfer in one kernel of ours, storing into rank 0's slab over NVLink: no NCCL in the frame loop
+            if args.gather in ("peer", "peer-ce"):
+                # pack + transfer in one kernel of ours, storing into rank 0's slab over NVLink (or: local pack + one DMA copy):
+                # no NCCL in the frame loop
                 peer = PeerPaletteExchange(ctx, cap, ps, dst=0)
                 peer_ctas = 4 * args.reserve_sms if args.reserve_sms > 0 else 0
+                if args.gather == "peer-ce":
+                    peer_ctas = -max(1, args.reserve_sms)   # dmk.h: negative = copy-engine transport, pack kernel on 4 * that many blocks
                 cull_done, pushed = torch.cuda.Event(), torch.cuda.Event()
             else:
                 gatherer = VisiblePaletteGather(cap, ps, dev, dst=0)
@@ -433,7 +456,7 @@ def run_gpu(args):
             ratio = cr.ratio.copy()
             vis_bits = np.zeros((n + 31) // 32, np.uint32)
             e2e_flags = capi.STEP_POSE | capi.STEP_CULL | capi.STEP_SKIN | capi.STEP_READBACK_VISIBILITY
-            e2e_steps = max(3, min(args.steps, 10))
+            e2e_steps = max(3, min(args.steps, 40))
 
             def host_tick(r):
                 # host state machine tick (clip clocks of looping clips) -> layer state of the next frame
@@ -441,8 +464,39 @@ def run_gpu(args):
 
             def submit(r):
                 crowd.update_layers(cr.clip, r, cr.weight)              # pinned double-buffered staging + async H2D
-                crowd.step(DT, e2e_flags)
-                crowd.pack_visible_palettes(packed.data_ptr(), cap)
+                if world == 1:
+                    crowd.step(DT, e2e_flags)
+                    crowd.pack_visible_palettes(packed.data_ptr(), cap)
+                    return
+                # N > 1: the same frame as the device-timed loop, the visible-palette exchange included
+                side = comm_stream if comm_stream is not None else stream
+                crowd.step(DT, capi.STEP_POSE | capi.STEP_CULL | capi.STEP_READBACK_VISIBILITY)
+                if peer is None:
+                    crowd.pack_visible_palettes(packed.data_ptr(), cap)
+                    if comm_stream is None:
+                        gatherer.gather(packed, vis_count)
+                    else:
+                        packed_ready.record(stream)
+                elif comm_stream is not None:
+                    cull_done.record(stream)
+                crowd.step(DT, capi.STEP_SKIN)
+                if peer is None:
+                    if comm_stream is not None:
+                        comm_stream.wait_event(packed_ready)
+                        with torch.cuda.stream(comm_stream):
+                            gatherer.gather(packed, vis_count)
+                        stream.wait_stream(comm_stream)
+                else:
+                    if comm_stream is not None:
+                        comm_stream.wait_event(cull_done)
+                    frame = peer.push(crowd, peer_ctas, side.cuda_stream)
+                    if comm_stream is not None:
+                        pushed.record(comm_stream)
+                    if peer.is_owner:
+                        peer.wait(frame, side.cuda_stream)
+                        peer.release(frame, side.cuda_stream)
+                    if comm_stream is not None:
+                        stream.wait_event(pushed)
 
             # Frame loop through the C ABI with host buffers, two frames in flight: frame k + 1 (host tick, pinned H2D of
             # its layer state, pose + cull + skin) is submitted before frame k's visibility (D2H, enqueued right behind
@@ -478,8 +532,48 @@ def run_gpu(args):
             e2e = {"value": n * world * e2e_steps_done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(3 * 2 * n * 4),
                    "d2h_bytes_per_step": int(vis_bits.nbytes + 4), "steps": e2e_steps_done,
                    "note": "frame loop with two frames in flight; per step: host clip clocks (numpy) -> dmk_crowd_update_layers (pinned H2D of clip/ratio/weight) -> "
-                           "dmk_crowd_step(POSE|CULL|SKIN|READBACK_VISIBILITY) -> pack visible palettes -> dmk_crowd_collect_visibility (pinned D2H of the bitmask + count, waited per frame); "
+                           "dmk_crowd_step(POSE|CULL|SKIN|READBACK_VISIBILITY) -> pack visible palettes (N > 1: the visible-palette exchange to rank 0, as in the "
+                           "device-timed loop) -> dmk_crowd_collect_visibility (pinned D2H of the bitmask + count, waited per frame); "
                            "skinned vertices and palettes stay on the GPU, as in the reference (vertex-stage consumers)"}
+
+        # ---- N > 1: what arrived on the render GPU is what the ranks have (outside every timed region) ----
+        gather_verified = None
+        if world > 1:
+            step()                                               # one more frame, untimed; nothing is pushed after it
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            crowd.pack_visible_palettes(packed.data_ptr(), cap)  # this rank's visible palettes of that frame, packed locally
+            torch.cuda.synchronize(dev)
+            my_count = int(vis_count.item())
+            all_counts = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
+            dist.all_gather(all_counts, vis_count.clone())
+            all_counts = [int(c.item()) for c in all_counts]
+            if max(all_counts) > cap:
+                raise SystemExit(f"visible set outgrew the slab capacity ({max(all_counts)} > {cap}): characters were dropped")
+            if rank == 0:
+                if peer is not None:
+                    slab_ptr, counts_ptr = peer.exchange.frame_dev(peer.frame)
+                    slab = torch.as_tensor(_DevArray(slab_ptr, (world, cap, ps, 16), "<f4"), device=dev)
+                    got_counts = torch.as_tensor(_DevArray(counts_ptr, (world,), "<i4"), device=dev).cpu().tolist()
+                else:
+                    slab, got_counts = gatherer.slab, gatherer.counts.cpu().tolist()
+                ok = got_counts == all_counts
+                for r in range(world):
+                    if r == 0:
+                        want = packed[:my_count]
+                    else:
+                        want = torch.empty((all_counts[r], ps, 16), dtype=torch.float32, device=dev)
+                        dist.recv(want, src=r)
+                    ok = ok and bool(torch.equal(slab[r, :all_counts[r]], want))
+                gather_verified = bool(ok)
+            else:
+                dist.send(packed[:my_count].contiguous(), dst=0)
+            flag = torch.tensor([1 if (gather_verified or rank != 0) else 0], dtype=torch.int32, device=dev)
+            dist.broadcast(flag, src=0)
+            if int(flag.item()) != 1:
+                raise SystemExit("visible-palette exchange: the slab on the render GPU differs from the ranks' own visible palettes")
+            if peer is not None:
+                peer.status()
 
     if rank != 0:
         if world > 1:
@@ -502,8 +596,9 @@ def run_gpu(args):
     try:
         with open(os.path.join(ROOT, "profiles", "skin_kernel_traffic.json")) as f:
             tj = json.load(f)
-            if tj.get("characters") == n and tj.get("vertices") == args.verts:
-                traffic = tj.get("dram_bytes_per_launch")
+            entry = tj.get("kernels", {}).get(skin_kernel_name(args))   # keyed by the instantiation that ran: another kernel, no number
+            if entry and entry.get("characters") == n and entry.get("vertices") == args.verts:
+                traffic = entry.get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     ms_per_step = elapsed_ms / args.steps
@@ -523,7 +618,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": SKIN_KERNEL_NAMES[args.skin_layout], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": skin_kernel_name(args), "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": skin_avg_ms, "launches_timed": int(skin_n)},
         "cpu_baseline": cpu_baseline,
@@ -533,10 +628,20 @@ def run_gpu(args):
         "visible_characters_rank0": int(vis0),
         "frame_ms_rank0": frame_ms,
     }
+    if world > 1:
+        line["gather_verified"] = gather_verified
+        line["gather_capacity_characters"] = int(cap)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of device memory owned by the library (no copy)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 class _DevInt32:
@@ -573,15 +678,18 @@ def main():
     ap.add_argument("--skin-layout", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="DMK_OPT_SKIN_PLANAR_OUTPUT: 0 interleaved [V][9] (default), 1 / 2 nine component planes (10 / 14 warps), 3 three float3 "
                          "streams, 4 nine planes from the default thread shape; not yet measured on hardware, see DESIGN.md section 9")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
-                    help="N > 1: visible-palette transport: pack kernel + NCCL send/recv, or the pack+transfer kernel storing into rank 0's "
-                         "memory over NVLink (dmk_exchange_*; not yet measured on hardware, see DESIGN.md section 5)")
+    ap.add_argument("--gather", default="peer", choices=["nccl", "peer", "peer-ce"],
+                    help="N > 1: visible-palette transport: pack kernel + NCCL send/recv; the pack+transfer kernel storing into rank 0's "
+                         "memory over NVLink (dmk_exchange_*); or local pack + one DMA-engine copy into rank 0's memory (DESIGN.md section 5)")
+    ap.add_argument("--mesh-order", default="clustered", choices=["caller", "clustered"],
+                    help="stored vertex order: the caller's, or clustered by bone (DMK_MESH_CLUSTER_BONES; the library reports the permutation)")
+    ap.add_argument("--round1-kernel", action="store_true", help="DMK_OPT_SKIN_ROUND1_KERNEL: the round-1 skinning kernel shape, for A/B")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.reserve_sms < 0:   # auto
-        args.reserve_sms = 0 if world <= 1 else 8
-    elif world > 1 and 0 < args.reserve_sms < 8:
+    if args.reserve_sms < 0:   # auto: NCCL's send/recv CTAs need 8 SMs; our own transports run on the SM the 147-block skinning grid leaves free
+        args.reserve_sms = 0 if world <= 1 else 8 if args.gather == "nccl" else 1
+    elif world > 1 and args.gather == "nccl" and 0 < args.reserve_sms < 8:
         # measured on 4 and 8 B200: with NCCL_MAX_CTAS = 8 the gather hides behind the skinning kernel;
         # with 6 it completes but no longer overlaps
         sys.exit("--reserve-sms must be 0 or at least 8 (with fewer NCCL CTAs the visible-palette gather no longer overlaps)")

@@ -27,6 +27,7 @@ void dmk_exchange_destroy(dmk_exchange_t x) {
     }
     dev_free(x->d_local);
     dev_free(x->d_counts);
+    dev_free(x->d_stage);
     delete x;
 }
 dmk_status dmk_exchange_create(dmk_context_t ctx, int world, int rank, int64_t capacity, int palette_size, uint8_t* handle_out,
@@ -118,11 +119,29 @@ dmk_status dmk_crowd_push_visible_palettes(dmk_crowd_t c, dmk_exchange_t x, uint
     if (c->n > 0 && !c->culled_once) return fail(ctx, DMK_ERR_INVALID, "needs a cull step");
     if (c->arm->num_joints + 1 != x->palette_size) return fail(ctx, DMK_ERR_INVALID, "palette size differs from the exchange's");
     if (frame != x->last_pushed + 1) return fail(ctx, DMK_ERR_INVALID, "frames are pushed in order: expected the previous frame + 1");
-    if (num_ctas < 0) return fail(ctx, DMK_ERR_INVALID, "num_ctas is negative");
     if (bind(ctx)) return DMK_ERR_CUDA;
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    const bool copy_engine = num_ctas < 0;
     if (num_ctas == 0) num_ctas = ctx->num_sms * 4;
     float* slab = x->buffer(frame) + static_cast<size_t>(x->rank) * static_cast<size_t>(x->capacity) * static_cast<size_t>(x->palette_size) * 16;
+    if (copy_engine) {
+        // pack locally with -num_ctas blocks, one DMA copy of the whole rank slab (padding included: the host does not know the
+        // count) into the render GPU's memory, publish.  Nothing of the transfer runs on an SM.
+        const size_t floats = static_cast<size_t>(x->capacity) * static_cast<size_t>(x->palette_size) * 16;
+        if (!x->d_stage && floats) DMK_CUDA(ctx, dev_alloc(&x->d_stage, floats));
+        DMK_CUDA(ctx, launch_wait_consumed(x->header(), frame, x->d_local + 1, x->timeout_ns, s));
+        {
+            KernelTimer timer(ctx, DMK_KERNEL_PACK, s);
+            if (x->capacity > 0)
+                DMK_CUDA(ctx, launch_pack_palettes(c->d_palette, x->palette_size * 16, c->d_visible_ids, c->d_visible_count, x->capacity, x->d_stage,
+                                                   -num_ctas, s));
+        }
+        if (floats) DMK_CUDA(ctx, cudaMemcpyAsync(slab, x->d_stage, floats * sizeof(float), cudaMemcpyDefault, s));
+        DMK_CUDA(ctx, launch_publish(x->header(), x->rank, frame, c->d_visible_count, x->d_local + 1, s));
+        ctx->launches += 3;
+        x->last_pushed = frame;
+        return DMK_OK;
+    }
     {
         KernelTimer timer(ctx, DMK_KERNEL_PACK, s);
         DMK_CUDA(ctx, launch_push_palettes(c->d_palette, x->palette_size * 16, c->d_visible_ids, c->d_visible_count, x->capacity, slab, x->header(),
@@ -139,7 +158,7 @@ dmk_status dmk_exchange_wait(dmk_exchange_t x, uint32_t frame, void* cuda_stream
     if (frame != x->last_waited + 1) return fail(ctx, DMK_ERR_INVALID, "frames are waited for in order: expected the previous frame + 1");
     if (bind(ctx)) return DMK_ERR_CUDA;
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    DMK_CUDA(ctx, launch_wait_published(x->header(), x->world, frame, x->d_counts + (frame & 1u) * kExchangeMaxRanks, x->timeout_ns, s));
+    DMK_CUDA(ctx, launch_wait_published(x->header(), x->world, frame, x->d_counts + (frame & 1u) * kExchangeMaxRanks, x->capacity, x->timeout_ns, s));
     ++ctx->launches;
     x->last_waited = frame;
     return DMK_OK;
@@ -169,13 +188,18 @@ dmk_status dmk_exchange_status(dmk_exchange_t x, void* cuda_stream, int* out_err
     dmk_context_t ctx = x->ctx;
     if (bind(ctx)) return DMK_ERR_CUDA;
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    uint32_t local = 0, owner = 0;
+    uint32_t local = 0, owner = 0, overflow = 0;
     DMK_CUDA(ctx, cudaMemcpyAsync(&local, x->d_local + 1, sizeof local, cudaMemcpyDeviceToHost, s));
-    if (x->kind == dmk_exchange_s::Owner)
+    if (x->kind == dmk_exchange_s::Owner) {
         DMK_CUDA(ctx, cudaMemcpyAsync(&owner, &x->header()->error, sizeof owner, cudaMemcpyDeviceToHost, s));
+        DMK_CUDA(ctx, cudaMemcpyAsync(&overflow, &x->header()->overflow_frame, sizeof overflow, cudaMemcpyDeviceToHost, s));
+    }
     DMK_CUDA(ctx, cudaStreamSynchronize(s));
-    const int err = local ? static_cast<int>(local) : static_cast<int>(owner);
+    const int err = local ? static_cast<int>(local) : owner ? static_cast<int>(owner) : overflow ? static_cast<int>(kExchangeErrOverflow) : 0;
     if (out_error) *out_error = err;
+    if (err == static_cast<int>(kExchangeErrOverflow))
+        return fail(ctx, DMK_ERR_UNSUPPORTED, "palette exchange: a rank had more visible characters than the slab's capacity (last in frame " +
+                                                  std::to_string(overflow) + "): the characters beyond it were not transferred");
     if (err == static_cast<int>(kExchangeErrTimeoutProducer))
         return fail(ctx, DMK_ERR_CUDA, "palette exchange: this rank's push gave up waiting for the render rank to release a buffer");
     if (err) return fail(ctx, DMK_ERR_CUDA, "palette exchange: the render rank gave up waiting for a rank's frame");

@@ -217,12 +217,13 @@ struct AnimatorParams {
 // allocation (kExchangeHeaderBytes reserved), the two slab buffers [2][world][capacity][palette][16] behind it.
 constexpr int kExchangeMaxRanks = 64;
 constexpr size_t kExchangeHeaderBytes = 4096;
-constexpr uint32_t kExchangeErrTimeoutProducer = 1, kExchangeErrTimeoutOwner = 2;
+constexpr uint32_t kExchangeErrTimeoutProducer = 1, kExchangeErrTimeoutOwner = 2, kExchangeErrOverflow = 3;
 struct ExchangeHeader {
     uint32_t published[kExchangeMaxRanks];   // last frame rank r has completely stored (release, system scope)
     int32_t count[2][kExchangeMaxRanks];     // palettes stored by rank r for the frame that uses buffer b
     uint32_t consumed;                       // last frame the owner has finished reading
     uint32_t error;                          // kExchangeErr*: a bounded wait of the owner expired
+    uint32_t overflow_frame;                 // last frame in which a rank had more visible characters than the slab holds (0: never)
 };
 static_assert(sizeof(ExchangeHeader) <= kExchangeHeaderBytes, "header outgrew its reservation");
 

@@ -11,7 +11,9 @@
 //
 // Protocol (all words live in the header at the start of the render GPU's allocation; frames count 1, 2, 3, ...):
 //   published[r]   last frame whose palettes rank r has completely stored            written by rank r, read by the owner
-//   count[b][r]    number of palettes rank r stored for the frame using buffer b     written by rank r, read by the owner
+//   count[b][r]    visible characters of rank r in the frame using buffer b          written by rank r, read by the owner
+//                  (NOT clamped: a count above the capacity says that only the first `capacity` palettes were stored;
+//                  the owner's wait records the frame in overflow_frame and dmk_exchange_status reports it)
 //   consumed       last frame the owner has finished reading                         written by the owner, read by all
 // The slab is double buffered (frame & 1).  Rank r may store frame f once consumed >= f - 2 (buffer f & 1 was last used
 // by frame f - 2); the owner reads frame f once published[r] >= f for every r.  Dependencies only point to earlier
@@ -46,8 +48,8 @@ __global__ void __launch_bounds__(256) push_palettes_kernel(const float4* __rest
         if (!go) atomicExch(local_error, kExchangeErrTimeoutProducer);
     }
     __syncthreads();
-    int64_t total = count[0];
-    if (total > capacity) total = capacity;
+    const int64_t visible = count[0];
+    const int64_t total = visible > capacity ? capacity : visible;
     if (go) {
         const int warps = (gridDim.x * blockDim.x) >> 5;
         const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -66,19 +68,35 @@ __global__ void __launch_bounds__(256) push_palettes_kernel(const float4* __rest
             *done = 0;               // next launch on this stream starts from zero
             __threadfence_system();  // acquire side of the tickets + release side of the words below
             if (*reinterpret_cast<volatile uint32_t*>(local_error) == 0) {   // a block that timed out stored nothing: do not publish
-                hdr->count[frame & 1][rank] = static_cast<int32_t>(total);
+                hdr->count[frame & 1][rank] = static_cast<int32_t>(visible);   // unclamped: the owner sees an overflow
                 st_release_sys(&hdr->published[rank], frame);
             }
         }
     }
 }
 
+// Copy-engine transport (dmk_crowd_push_visible_palettes with DMK_PUSH_COPY_ENGINE): the palettes are packed into a local
+// buffer by the pack kernel, moved by ONE cudaMemcpyAsync into the render GPU's slab (a DMA engine, no SM), and these two
+// single-thread kernels do the flow control in front of the copy and the publication behind it.
+__global__ void wait_consumed_kernel(ExchangeHeader* hdr, uint32_t frame, uint32_t* local_error, uint64_t timeout_ns) {
+    if (frame > 2 && !wait_reached(&hdr->consumed, frame - 2, timeout_ns)) atomicExch(local_error, kExchangeErrTimeoutProducer);
+}
+__global__ void publish_kernel(ExchangeHeader* hdr, int rank, uint32_t frame, const int32_t* __restrict__ count, const uint32_t* local_error) {
+    if (*reinterpret_cast<const volatile uint32_t*>(local_error) != 0) return;   // the flow-control wait gave up: nothing valid was copied
+    __threadfence_system();
+    hdr->count[frame & 1][rank] = count[0];
+    st_release_sys(&hdr->published[rank], frame);
+}
+
 // Owner: one thread per rank waits for that rank's frame, then copies its count.
-__global__ void wait_published_kernel(ExchangeHeader* hdr, int world, uint32_t frame, int32_t* __restrict__ counts_out, uint64_t timeout_ns) {
+__global__ void wait_published_kernel(ExchangeHeader* hdr, int world, uint32_t frame, int32_t* __restrict__ counts_out, int64_t capacity,
+                                      uint64_t timeout_ns) {
     const int r = threadIdx.x;
     if (r >= world) return;
     if (wait_reached(&hdr->published[r], frame, timeout_ns)) {
-        counts_out[r] = *reinterpret_cast<volatile int32_t*>(&hdr->count[frame & 1][r]);
+        const int32_t visible = *reinterpret_cast<volatile int32_t*>(&hdr->count[frame & 1][r]);
+        counts_out[r] = visible;
+        if (visible > capacity) *reinterpret_cast<volatile uint32_t*>(&hdr->overflow_frame) = frame;   // (frames are waited for in order)
     } else {
         counts_out[r] = 0;
         atomicExch(&hdr->error, kExchangeErrTimeoutOwner);
@@ -99,8 +117,17 @@ cudaError_t launch_push_palettes(const float* palette, int palette_floats, const
                                                        reinterpret_cast<float4*>(slab), hdr, rank, frame, done, local_error, timeout_ns);
     return cudaGetLastError();
 }
-cudaError_t launch_wait_published(ExchangeHeader* hdr, int world, uint32_t frame, int32_t* counts_out, uint64_t timeout_ns, cudaStream_t stream) {
-    DMK_LAUNCH(wait_published_kernel, 1, kExchangeMaxRanks, 0, stream)(hdr, world, frame, counts_out, timeout_ns);
+cudaError_t launch_wait_published(ExchangeHeader* hdr, int world, uint32_t frame, int32_t* counts_out, int64_t capacity, uint64_t timeout_ns,
+                                  cudaStream_t stream) {
+    DMK_LAUNCH(wait_published_kernel, 1, kExchangeMaxRanks, 0, stream)(hdr, world, frame, counts_out, capacity, timeout_ns);
+    return cudaGetLastError();
+}
+cudaError_t launch_wait_consumed(ExchangeHeader* hdr, uint32_t frame, uint32_t* local_error, uint64_t timeout_ns, cudaStream_t stream) {
+    DMK_LAUNCH(wait_consumed_kernel, 1, 1, 0, stream)(hdr, frame, local_error, timeout_ns);
+    return cudaGetLastError();
+}
+cudaError_t launch_publish(ExchangeHeader* hdr, int rank, uint32_t frame, const int32_t* count, const uint32_t* local_error, cudaStream_t stream) {
+    DMK_LAUNCH(publish_kernel, 1, 1, 0, stream)(hdr, rank, frame, count, local_error);
     return cudaGetLastError();
 }
 cudaError_t launch_release_frame(ExchangeHeader* hdr, uint32_t frame, cudaStream_t stream) {

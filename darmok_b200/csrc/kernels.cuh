@@ -49,7 +49,11 @@ cudaError_t launch_pack_palettes(const float* palette, int palette_floats, const
 cudaError_t launch_push_palettes(const float* palette, int palette_floats, const int32_t* ids, const int32_t* count, int64_t capacity, float* slab,
                                  ExchangeHeader* hdr, int rank, uint32_t frame, uint32_t* done, uint32_t* local_error, uint64_t timeout_ns, int num_ctas,
                                  cudaStream_t stream);
-cudaError_t launch_wait_published(ExchangeHeader* hdr, int world, uint32_t frame, int32_t* counts_out, uint64_t timeout_ns, cudaStream_t stream);
+cudaError_t launch_wait_published(ExchangeHeader* hdr, int world, uint32_t frame, int32_t* counts_out, int64_t capacity, uint64_t timeout_ns,
+                                  cudaStream_t stream);
+// copy-engine transport: flow control in front of the DMA copy, publication behind it (one thread each)
+cudaError_t launch_wait_consumed(ExchangeHeader* hdr, uint32_t frame, uint32_t* local_error, uint64_t timeout_ns, cudaStream_t stream);
+cudaError_t launch_publish(ExchangeHeader* hdr, int rank, uint32_t frame, const int32_t* count, const uint32_t* local_error, cudaStream_t stream);
 cudaError_t launch_release_frame(ExchangeHeader* hdr, uint32_t frame, cudaStream_t stream);
 
 }  // namespace dmk

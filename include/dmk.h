@@ -403,7 +403,8 @@ DMK_API dmk_status dmk_crowd_collect_visibility(dmk_crowd_t crowd, uint32_t* out
 DMK_API dmk_status dmk_crowd_get_ratios(dmk_crowd_t crowd, float* out_ratio, uint8_t* out_looped);
 
 /* Gather the palettes of the visible characters (ascending id) into a caller-owned DEVICE buffer of
- * capacity_characters * palette_size * 16 floats; count is left on the device (dmk_crowd_visible_count_dev).
+ * capacity_characters * palette_size * 16 floats; count is left on the device (dmk_crowd_visible_count_dev) and is NOT
+ * clamped: a count above capacity_characters means that only the first capacity_characters palettes were packed.
  * This is the payload of the one multi-GPU exchange. */
 DMK_API dmk_status dmk_crowd_pack_visible_palettes(dmk_crowd_t crowd, float* out_dev, int64_t capacity_characters);
 
@@ -434,8 +435,15 @@ DMK_API void dmk_exchange_destroy(dmk_exchange_t exchange); /* owner last: the o
 /* bound of every device-side wait, milliseconds (default 30000) */
 DMK_API dmk_status dmk_exchange_set_timeout_ms(dmk_exchange_t exchange, int64_t milliseconds);
 /* Pack + transfer: palettes of the crowd's visible characters (ascending id, at most capacity) -> slab[frame & 1][rank]
- * on the render GPU, then publish.  frame must be the previous frame of this exchange + 1.  num_ctas: blocks of 256
- * threads (0 = 4 per SM); keep it within the SMs left to the side stream. */
+ * on the render GPU, then publish.  frame must be the previous frame of this exchange + 1.
+ * num_ctas > 0: ONE kernel of that many 256-thread blocks packs and stores over NVLink (0 = 4 per SM); keep it within the
+ *   SMs left to the side stream.
+ * num_ctas < 0: copy-engine transport -- the pack kernel (4 * -num_ctas blocks) fills a local buffer, one cudaMemcpyAsync
+ *   moves the rank's whole slab (capacity palettes, padding included: the host never learns the count) into the render
+ *   GPU's memory on a DMA engine, and two single-thread kernels do the flow control and the publication.  No SM takes part
+ *   in the transfer; size the capacity close to the expected visible set.
+ * The published count is the rank's number of visible characters, NOT clamped to the capacity: when it is larger, only the
+ * first `capacity` palettes were transferred, dmk_exchange_wait records it and dmk_exchange_status reports error 3. */
 DMK_API dmk_status dmk_crowd_push_visible_palettes(dmk_crowd_t crowd, dmk_exchange_t exchange, uint32_t frame, int num_ctas,
                                                    void* cuda_stream);
 /* render rank: enqueue the device-side wait for `frame` of every rank; afterwards (stream order) the frame's palettes
@@ -446,7 +454,9 @@ DMK_API dmk_status dmk_exchange_frame_dev(dmk_exchange_t exchange, uint32_t fram
 /* render rank: the frame has been read; its buffer may be overwritten by frame + 2 */
 DMK_API dmk_status dmk_exchange_release(dmk_exchange_t exchange, uint32_t frame, void* cuda_stream);
 /* synchronises the given stream and reports expired waits: *out_error = 0 ok, 1 this rank's push gave up waiting for a
- * release, 2 the render rank gave up waiting for a rank (DMK_ERR_CUDA is returned as well when it is not 0) */
+ * release, 2 the render rank gave up waiting for a rank (DMK_ERR_CUDA is returned as well), 3 (render rank) some rank's
+ * visible set outgrew the capacity in a frame that was waited for: its characters beyond the capacity were dropped
+ * (DMK_ERR_UNSUPPORTED; the exchange itself keeps working) */
 DMK_API dmk_status dmk_exchange_status(dmk_exchange_t exchange, void* cuda_stream, int* out_error);
 
 /* ---- stand-alone batched cull (config 5: instances without animation) ---------------------------------- */

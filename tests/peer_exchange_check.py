@@ -4,8 +4,10 @@ tests/test_gpu_zz_peer_exchange.py in a child process (a device fault here must 
 
 One GPU, three logical ranks in one process (dmk_exchange_attach): each rank owns its own crowd; every frame all ranks push
 (pack + transfer kernel), the owner waits on the device, and the slab must hold exactly the palettes of every rank's visible
-characters in ascending id order, with the published counts (clamped to the capacity).  Then the bounded waits: a
-producer three frames ahead of the last release gives up with an error instead of hanging.
+characters in ascending id order (the first `capacity` of them), with the ranks' UNCLAMPED visible counts, and the status
+must report the overflow.  Rank 2 uses the copy-engine transport (local pack + one DMA copy + publish), the others the
+pack+transfer kernel.  Then the bounded waits: a producer three frames ahead of the last release gives up with an error
+instead of hanging.
 
     python tests/peer_exchange_check.py          exit code 0 = all checks passed
 """
@@ -52,23 +54,33 @@ def main():
         expect = []
         for r, crowd in enumerate(crowds):
             crowd.step(1.0 / 60.0, capi.STEP_ADVANCE | capi.STEP_POSE | capi.STEP_CULL)
-            crowd.push_visible_palettes(ranks[r], frame, 8 if r else 0)
+            crowd.push_visible_palettes(ranks[r], frame, (0, 8, -2)[r])   # rank 2: copy-engine transport
             bits, count = crowd.get_visibility()
             ids = np.flatnonzero(np.unpackbits(bits.view(np.uint8), bitorder="little")[:sizes[r]])
             assert len(ids) == count
             pal = crowd.get_palette()
-            expect.append(pal[ids[:capacity]])
+            expect.append((pal[ids[:capacity]], len(ids)))
             clamped += len(ids) > capacity
         owner.wait(frame)
         slab_ptr, counts_ptr = owner.frame_dev(frame)
         ctx.sync()
         slab = devmem.read(slab_ptr, (world, capacity, ps, 16))
         counts = devmem.read(counts_ptr, (world,), np.int32)
+        overflowed = False
         for r in range(world):
-            assert counts[r] == len(expect[r]), f"frame {frame} rank {r}: count {counts[r]} != {len(expect[r])}"
-            assert np.array_equal(slab[r, :counts[r]], expect[r]), f"frame {frame} rank {r}: palettes differ"
+            pal, visible = expect[r]
+            assert counts[r] == visible, f"frame {frame} rank {r}: published count {counts[r]} != visible {visible} (unclamped)"
+            assert np.array_equal(slab[r, :min(visible, capacity)], pal), f"frame {frame} rank {r}: palettes differ"
+            overflowed = overflowed or visible > capacity
         owner.release(frame)
-        assert owner.status() == 0
+        if overflowed or clamped:
+            try:    # sticky, but the exchange keeps working
+                owner.status()
+                raise AssertionError("a visible set above the capacity was not reported")
+            except capi.DmkError as e:
+                assert e.status == capi.ERR_UNSUPPORTED and "capacity" in e.message, e.message
+        else:
+            assert owner.status() == 0
     assert clamped > 0, "the capacity clamp was never exercised"
     # out-of-order frames are refused on the host
     try:
