@@ -300,7 +300,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.Stream(device=dev)
+    # the frame's own stream has the higher priority: when the skinning grid and a side-stream kernel (the exchange) become
+    # runnable together, the block scheduler places the skinning blocks first and the exchange takes the SM(s) they leave free
+    stream = torch.cuda.Stream(device=dev, priority=-1)
     assets = make_assets(args)
     skel_s, clips_s, arm_s, mesh_s = assets
     n = args.chars
@@ -361,18 +363,22 @@ def run_gpu(args):
                 # the gather runs on its own stream, on SMs the persistent skinning grid leaves free, concurrently with
                 # the skinning kernel (it only depends on pose + cull + pack)
                 crowd.set_option(capi.OPT_SKIN_RESERVED_SMS, args.reserve_sms)
-                comm_stream = torch.cuda.Stream(device=dev)
+                comm_stream = torch.cuda.Stream(device=dev, priority=0)
                 packed_ready = torch.cuda.Event()
 
-        def step_peer():
-            crowd.step(DT, flags_pre)                       # clocks + pose + cull + compaction
+        def peer_frame(pre_flags):
+            """one frame with our own transport: pose + cull, [stage], skin; the exchange on the side stream behind an event"""
+            crowd.step(DT, pre_flags)                       # clocks + pose + cull + compaction
             side = comm_stream if comm_stream is not None else stream
+            staged = args.gather == "peer-ce" and comm_stream is not None
+            if staged:
+                peer.stage(crowd, stream.cuda_stream)       # pack into the local buffer with the whole GPU, before the skinning grid takes it
             if comm_stream is not None:
                 cull_done.record(stream)
             crowd.step(DT, capi.STEP_SKIN)                  # LBS of every vertex of every character
             if comm_stream is not None:
-                comm_stream.wait_event(cull_done)           # the push depends on pose + cull only; enqueued after the skin launch
-            frame = peer.push(crowd, peer_ctas, side.cuda_stream)
+                comm_stream.wait_event(cull_done)           # the exchange depends on pose + cull only; enqueued after the skin launch
+            frame = peer.send_staged(crowd, side.cuda_stream) if staged else peer.push(crowd, peer_ctas, side.cuda_stream)
             if comm_stream is not None:
                 pushed.record(comm_stream)
             if peer.is_owner:                               # the render GPU: wait for the frame of all ranks, consume, release
@@ -383,7 +389,7 @@ def run_gpu(args):
 
         def step():
             if peer is not None:
-                return step_peer()
+                return peer_frame(flags_pre)
             crowd.step(DT, flags_pre)                       # clocks + pose + cull + compaction
             crowd.pack_visible_palettes(packed.data_ptr(), cap)
             if gatherer is not None and comm_stream is None:
@@ -469,34 +475,21 @@ def run_gpu(args):
                     crowd.pack_visible_palettes(packed.data_ptr(), cap)
                     return
                 # N > 1: the same frame as the device-timed loop, the visible-palette exchange included
-                side = comm_stream if comm_stream is not None else stream
-                crowd.step(DT, capi.STEP_POSE | capi.STEP_CULL | capi.STEP_READBACK_VISIBILITY)
-                if peer is None:
-                    crowd.pack_visible_palettes(packed.data_ptr(), cap)
-                    if comm_stream is None:
-                        gatherer.gather(packed, vis_count)
-                    else:
-                        packed_ready.record(stream)
-                elif comm_stream is not None:
-                    cull_done.record(stream)
-                crowd.step(DT, capi.STEP_SKIN)
-                if peer is None:
-                    if comm_stream is not None:
-                        comm_stream.wait_event(packed_ready)
-                        with torch.cuda.stream(comm_stream):
-                            gatherer.gather(packed, vis_count)
-                        stream.wait_stream(comm_stream)
+                pre = capi.STEP_POSE | capi.STEP_CULL | capi.STEP_READBACK_VISIBILITY
+                if peer is not None:
+                    return peer_frame(pre)
+                crowd.step(DT, pre)
+                crowd.pack_visible_palettes(packed.data_ptr(), cap)
+                if comm_stream is None:
+                    gatherer.gather(packed, vis_count)
                 else:
-                    if comm_stream is not None:
-                        comm_stream.wait_event(cull_done)
-                    frame = peer.push(crowd, peer_ctas, side.cuda_stream)
-                    if comm_stream is not None:
-                        pushed.record(comm_stream)
-                    if peer.is_owner:
-                        peer.wait(frame, side.cuda_stream)
-                        peer.release(frame, side.cuda_stream)
-                    if comm_stream is not None:
-                        stream.wait_event(pushed)
+                    packed_ready.record(stream)
+                crowd.step(DT, capi.STEP_SKIN)
+                if comm_stream is not None:
+                    comm_stream.wait_event(packed_ready)
+                    with torch.cuda.stream(comm_stream):
+                        gatherer.gather(packed, vis_count)
+                    stream.wait_stream(comm_stream)
 
             # Frame loop through the C ABI with host buffers, two frames in flight: frame k + 1 (host tick, pinned H2D of
             # its layer state, pose + cull + skin) is submitted before frame k's visibility (D2H, enqueued right behind
@@ -678,7 +671,7 @@ def main():
     ap.add_argument("--skin-layout", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="DMK_OPT_SKIN_PLANAR_OUTPUT: 0 interleaved [V][9] (default), 1 / 2 nine component planes (10 / 14 warps), 3 three float3 "
                          "streams, 4 nine planes from the default thread shape; not yet measured on hardware, see DESIGN.md section 9")
-    ap.add_argument("--gather", default="peer", choices=["nccl", "peer", "peer-ce"],
+    ap.add_argument("--gather", default="peer-ce", choices=["nccl", "peer", "peer-ce"],
                     help="N > 1: visible-palette transport: pack kernel + NCCL send/recv; the pack+transfer kernel storing into rank 0's "
                          "memory over NVLink (dmk_exchange_*); or local pack + one DMA-engine copy into rank 0's memory (DESIGN.md section 5)")
     ap.add_argument("--mesh-order", default="clustered", choices=["caller", "clustered"],

@@ -125,6 +125,8 @@ SIGNATURES = [
     ("dmk_exchange_destroy", None, [_vp]),
     ("dmk_exchange_set_timeout_ms", _i, [_vp, _i64]),
     ("dmk_crowd_push_visible_palettes", _i, [_vp, _vp, _u32, _i, _vp]),
+    ("dmk_crowd_stage_visible_palettes", _i, [_vp, _vp, _vp]),
+    ("dmk_exchange_send_staged", _i, [_vp, _vp, C.c_uint32, _vp]),
     ("dmk_exchange_wait", _i, [_vp, _u32, _vp]),
     ("dmk_exchange_frame_dev", _i, [_vp, _u32, C.POINTER(_vp), C.POINTER(_vp)]),
     ("dmk_exchange_release", _i, [_vp, _u32, _vp]),
@@ -515,6 +517,12 @@ class Crowd:
 
     def pack_visible_palettes(self, out_dev_ptr, capacity):
         self.ctx.check(lib().dmk_crowd_pack_visible_palettes(self.h, out_dev_ptr, capacity))
+
+    def stage_visible_palettes(self, exchange: "Exchange", stream=None):
+        self.ctx.check(lib().dmk_crowd_stage_visible_palettes(self.h, exchange.h, stream))
+
+    def send_staged_palettes(self, exchange: "Exchange", frame: int, stream=None):
+        self.ctx.check(lib().dmk_exchange_send_staged(exchange.h, self.h, frame, stream))
 
     def push_visible_palettes(self, exchange: "Exchange", frame: int, num_ctas: int = 0, stream=None):
         self.ctx.check(lib().dmk_crowd_push_visible_palettes(self.h, exchange.h, frame, num_ctas, stream))

@@ -111,6 +111,54 @@ dmk_status dmk_exchange_set_timeout_ms(dmk_exchange_t x, int64_t ms) {
     x->timeout_ns = static_cast<uint64_t>(ms) * 1000000ull;
     return DMK_OK;
 }
+static dmk_status exchange_check_crowd(dmk_crowd_t c, dmk_exchange_t x) {
+    dmk_context_t ctx = c->ctx;
+    if (x->ctx != ctx) return fail(ctx, DMK_ERR_INVALID, "the exchange belongs to another context");
+    if (!c->arm) return fail(ctx, DMK_ERR_INVALID, "needs an armature");
+    if (c->n > 0 && !c->culled_once) return fail(ctx, DMK_ERR_INVALID, "needs a cull step");
+    if (c->arm->num_joints + 1 != x->palette_size) return fail(ctx, DMK_ERR_INVALID, "palette size differs from the exchange's");
+    return DMK_OK;
+}
+// copy-engine transport, first half: the visible palettes into this rank's local staging buffer (pack kernel on `num_sms` SMs)
+static dmk_status exchange_stage(dmk_crowd_t c, dmk_exchange_t x, int num_sms, cudaStream_t s) {
+    dmk_context_t ctx = c->ctx;
+    const size_t floats = static_cast<size_t>(x->capacity) * static_cast<size_t>(x->palette_size) * 16;
+    if (!x->d_stage && floats) DMK_CUDA(ctx, dev_alloc(&x->d_stage, floats));
+    KernelTimer timer(ctx, DMK_KERNEL_PACK, s);
+    if (x->capacity > 0)
+        DMK_CUDA(ctx, launch_pack_palettes(c->d_palette, x->palette_size * 16, c->d_visible_ids, c->d_visible_count, x->capacity, x->d_stage, num_sms, s));
+    ++ctx->launches;
+    return DMK_OK;
+}
+// second half: flow control, ONE DMA copy of the rank's slab into the render GPU's memory, publication
+static dmk_status exchange_send(dmk_crowd_t c, dmk_exchange_t x, uint32_t frame, cudaStream_t s) {
+    dmk_context_t ctx = c->ctx;
+    const size_t floats = static_cast<size_t>(x->capacity) * static_cast<size_t>(x->palette_size) * 16;
+    float* slab = x->buffer(frame) + static_cast<size_t>(x->rank) * floats;
+    DMK_CUDA(ctx, launch_wait_consumed(x->header(), frame, x->d_local + 1, x->timeout_ns, s));
+    if (floats) DMK_CUDA(ctx, cudaMemcpyAsync(slab, x->d_stage, floats * sizeof(float), cudaMemcpyDefault, s));
+    DMK_CUDA(ctx, launch_publish(x->header(), x->rank, frame, c->d_visible_count, x->d_local + 1, s));
+    ctx->launches += 2;
+    x->last_pushed = frame;
+    return DMK_OK;
+}
+dmk_status dmk_crowd_stage_visible_palettes(dmk_crowd_t c, dmk_exchange_t x, void* cuda_stream) {
+    if (!c || !x) return DMK_ERR_INVALID;
+    if (dmk_status st = exchange_check_crowd(c, x)) return st;
+    if (bind(c->ctx)) return DMK_ERR_CUDA;
+    x->staged = true;
+    return exchange_stage(c, x, c->ctx->num_sms, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->ctx->stream);
+}
+dmk_status dmk_exchange_send_staged(dmk_exchange_t x, dmk_crowd_t c, uint32_t frame, void* cuda_stream) {
+    if (!c || !x) return DMK_ERR_INVALID;
+    dmk_context_t ctx = c->ctx;
+    if (dmk_status st = exchange_check_crowd(c, x)) return st;
+    if (!x->staged) return fail(ctx, DMK_ERR_INVALID, "nothing staged: call dmk_crowd_stage_visible_palettes first");
+    if (frame != x->last_pushed + 1) return fail(ctx, DMK_ERR_INVALID, "frames are pushed in order: expected the previous frame + 1");
+    if (bind(ctx)) return DMK_ERR_CUDA;
+    x->staged = false;
+    return exchange_send(c, x, frame, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream);
+}
 dmk_status dmk_crowd_push_visible_palettes(dmk_crowd_t c, dmk_exchange_t x, uint32_t frame, int num_ctas, void* cuda_stream) {
     if (!c || !x) return DMK_ERR_INVALID;
     dmk_context_t ctx = c->ctx;
@@ -125,22 +173,10 @@ dmk_status dmk_crowd_push_visible_palettes(dmk_crowd_t c, dmk_exchange_t x, uint
     if (num_ctas == 0) num_ctas = ctx->num_sms * 4;
     float* slab = x->buffer(frame) + static_cast<size_t>(x->rank) * static_cast<size_t>(x->capacity) * static_cast<size_t>(x->palette_size) * 16;
     if (copy_engine) {
-        // pack locally with -num_ctas blocks, one DMA copy of the whole rank slab (padding included: the host does not know the
-        // count) into the render GPU's memory, publish.  Nothing of the transfer runs on an SM.
-        const size_t floats = static_cast<size_t>(x->capacity) * static_cast<size_t>(x->palette_size) * 16;
-        if (!x->d_stage && floats) DMK_CUDA(ctx, dev_alloc(&x->d_stage, floats));
-        DMK_CUDA(ctx, launch_wait_consumed(x->header(), frame, x->d_local + 1, x->timeout_ns, s));
-        {
-            KernelTimer timer(ctx, DMK_KERNEL_PACK, s);
-            if (x->capacity > 0)
-                DMK_CUDA(ctx, launch_pack_palettes(c->d_palette, x->palette_size * 16, c->d_visible_ids, c->d_visible_count, x->capacity, x->d_stage,
-                                                   -num_ctas, s));
-        }
-        if (floats) DMK_CUDA(ctx, cudaMemcpyAsync(slab, x->d_stage, floats * sizeof(float), cudaMemcpyDefault, s));
-        DMK_CUDA(ctx, launch_publish(x->header(), x->rank, frame, c->d_visible_count, x->d_local + 1, s));
-        ctx->launches += 3;
-        x->last_pushed = frame;
-        return DMK_OK;
+        // pack locally on -num_ctas SMs' worth of blocks, one DMA copy of the whole rank slab (padding included: the host does not
+        // know the count) into the render GPU's memory, publish.  Nothing of the transfer runs on an SM.
+        if (dmk_status st = exchange_stage(c, x, -num_ctas, s)) return st;
+        return exchange_send(c, x, frame, s);
     }
     {
         KernelTimer timer(ctx, DMK_KERNEL_PACK, s);

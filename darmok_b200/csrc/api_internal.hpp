@@ -190,6 +190,7 @@ struct dmk_exchange_s {
     void* base = nullptr;             // ExchangeHeader, then float[2][world][capacity][palette_size][16], in the render GPU's memory
     uint32_t* d_local = nullptr;      // this rank's own words: {tickets of the push grid, error}
     int32_t* d_counts = nullptr;      // owner: [2][kExchangeMaxRanks] counts of the waited frame, per buffer
+    bool staged = false;              // dmk_crowd_stage_visible_palettes ran, dmk_exchange_send_staged has not yet
     float* d_stage = nullptr;         // copy-engine transport: this rank's packed palettes [capacity][palette_size][16] (allocated at first use)
     uint32_t last_pushed = 0, last_waited = 0, last_released = 0;
     uint64_t timeout_ns = 30ull * 1000 * 1000 * 1000;

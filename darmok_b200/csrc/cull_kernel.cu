@@ -298,9 +298,7 @@ __global__ void pack_palettes_kernel(const float4* __restrict__ palette, int pal
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     for (int64_t i = warp; i < total; i += warps) {
-        const float4* src = palette + (size_t)ids[i] * palette_vec4;
-        float4* dst = out + (size_t)i * palette_vec4;
-        for (int k = lane; k < palette_vec4; k += 32) dst[k] = __ldg(src + k);
+        warp_copy_palette(palette + (size_t)ids[i] * palette_vec4, out + (size_t)i * palette_vec4, palette_vec4, lane);
     }
 }
 

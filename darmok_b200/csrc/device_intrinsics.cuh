@@ -137,6 +137,26 @@ __device__ __forceinline__ void lds128_keep(float4& v, uint32_t addr, uint32_t t
         : "r"(addr), "r"(take));
 }
 
+// One warp copies one palette (palette_vec4 float4): 8 loads in flight per lane before the first store, so that a handful of
+// warps keeps enough bytes on the wire -- with one load per store a whole SM moved 14 GB/s over NVLink (r02, 2 GPUs), bound by
+// the latency of its own loads.
+__device__ __forceinline__ void warp_copy_palette(const float4* __restrict__ src, float4* __restrict__ dst, int palette_vec4, int lane) {
+    constexpr int kInFlight = 8;
+    for (int base = 0; base < palette_vec4; base += 32 * kInFlight) {
+        float4 v[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const int k = base + u * 32 + lane;
+            if (k < palette_vec4) v[u] = __ldg(src + k);
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const int k = base + u * 32 + lane;
+            if (k < palette_vec4) dst[k] = v[u];
+        }
+    }
+}
+
 // ---- system scope (peer memory over NVLink) -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;

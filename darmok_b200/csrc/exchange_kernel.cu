@@ -54,9 +54,7 @@ __global__ void __launch_bounds__(256) push_palettes_kernel(const float4* __rest
         const int warps = (gridDim.x * blockDim.x) >> 5;
         const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
         for (int64_t i = warp; i < total; i += warps) {
-            const float4* src = palette + static_cast<size_t>(ids[i]) * palette_vec4;
-            float4* dst = slab + static_cast<size_t>(i) * palette_vec4;
-            for (int k = lane; k < palette_vec4; k += 32) dst[k] = __ldg(src + k);
+            warp_copy_palette(palette + static_cast<size_t>(ids[i]) * palette_vec4, slab + static_cast<size_t>(i) * palette_vec4, palette_vec4, lane);
         }
     }
     // last block out publishes: fence (release of this thread's stores at system scope), block barrier, ticket

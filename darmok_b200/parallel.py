@@ -119,6 +119,16 @@ class PeerPaletteExchange:
         crowd.push_visible_palettes(self.exchange, self.frame, num_ctas, stream)
         return self.frame
 
+    def stage(self, crowd, stream=None):
+        """copy-engine transport, first half: pack this rank's visible palettes into its local buffer (whole GPU, microseconds)."""
+        crowd.stage_visible_palettes(self.exchange, stream)
+
+    def send_staged(self, crowd, stream=None) -> int:
+        """second half: flow control + one DMA copy into the render rank's slab + publication; returns the frame number."""
+        self.frame += 1
+        crowd.send_staged_palettes(self.exchange, self.frame, stream)
+        return self.frame
+
     def wait(self, frame: int, stream=None):
         """render rank: device-side wait for `frame` of all ranks; returns (slab pointer, counts pointer) of its buffer."""
         self.exchange.wait(frame, stream)

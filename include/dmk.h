@@ -446,6 +446,12 @@ DMK_API dmk_status dmk_exchange_set_timeout_ms(dmk_exchange_t exchange, int64_t 
  * first `capacity` palettes were transferred, dmk_exchange_wait records it and dmk_exchange_status reports error 3. */
 DMK_API dmk_status dmk_crowd_push_visible_palettes(dmk_crowd_t crowd, dmk_exchange_t exchange, uint32_t frame, int num_ctas,
                                                    void* cuda_stream);
+/* The copy-engine transport in two halves, for frame loops that keep the exchange on a side stream: stage = the pack kernel
+ * into the rank's local buffer, on the whole GPU (tens of microseconds), typically on the frame's own stream right after the
+ * cull; send = flow control + the DMA copy + publication, typically on the side stream behind an event, while the
+ * skinning kernel runs.  dmk_crowd_push_visible_palettes with num_ctas < 0 is both on one stream. */
+DMK_API dmk_status dmk_crowd_stage_visible_palettes(dmk_crowd_t crowd, dmk_exchange_t exchange, void* cuda_stream);
+DMK_API dmk_status dmk_exchange_send_staged(dmk_exchange_t exchange, dmk_crowd_t crowd, uint32_t frame, void* cuda_stream);
 /* render rank: enqueue the device-side wait for `frame` of every rank; afterwards (stream order) the frame's palettes
  * and counts are readable */
 DMK_API dmk_status dmk_exchange_wait(dmk_exchange_t exchange, uint32_t frame, void* cuda_stream);

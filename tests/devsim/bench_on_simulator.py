@@ -73,7 +73,7 @@ def install_host_stand_ins():
 
     dist.init_process_group = init_process_group
     torch.cuda.current_stream = lambda device=None: Stream()
-    torch.cuda.Stream = lambda device=None: Stream()
+    torch.cuda.Stream = lambda device=None, priority=0: Stream()
     torch.cuda.stream = lambda stream: contextlib.nullcontext()
     torch.cuda.Event = Event
     torch.cuda.synchronize = lambda device=None: None

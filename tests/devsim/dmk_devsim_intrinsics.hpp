@@ -232,6 +232,9 @@ inline float4 lds128_if(uint32_t addr, uint32_t take) { return take ? lds128(add
 inline void lds128_keep(float4& v, uint32_t addr, uint32_t take) {
     if (take) v = lds128(addr);
 }
+inline void warp_copy_palette(const float4* src, float4* dst, int palette_vec4, int lane) {
+    for (int k = lane; k < palette_vec4; k += 32) dst[k] = src[k];
+}
 inline float4 lds128_or(uint32_t addr, uint32_t take, const float4& fallback) { return take ? lds128(addr) : fallback; }
 
 inline uint32_t ld_acquire_sys(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
