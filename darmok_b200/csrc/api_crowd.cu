@@ -263,6 +263,16 @@ dmk_status dmk_crowd_update_layers(dmk_crowd_t c, int num_layers, const int32_t*
     dmk_context_t ctx = c->ctx;
     if (!c->layers_set || num_layers != c->num_layers) return fail(ctx, DMK_ERR_INVALID, "call dmk_crowd_set_layers first (same num_layers)");
     if (!clip || !ratio || !weight) return fail(ctx, DMK_ERR_INVALID, "null layer array");
+    // same contract as dmk_crowd_set_layers: a clip index outside the set is refused here, on the host, not discovered by the kernel
+    const size_t entries = static_cast<size_t>(num_layers) * static_cast<size_t>(c->n);
+    const uint32_t num_clips = static_cast<uint32_t>(c->clips->num_clips);
+    uint32_t worst = 0;
+    for (size_t i = 0; i < entries; ++i) worst = std::max(worst, static_cast<uint32_t>(clip[i]));   // negative indices wrap to large values
+    if (entries && worst >= num_clips) {
+        size_t i = 0;
+        while (static_cast<uint32_t>(clip[i]) < num_clips) ++i;
+        return fail(ctx, DMK_ERR_INVALID, "character " + std::to_string(i % static_cast<size_t>(c->n)) + " references a clip outside the clip set");
+    }
     if (bind(ctx)) return DMK_ERR_CUDA;
     const size_t bytes = static_cast<size_t>(num_layers) * static_cast<size_t>(c->n) * 4;
     char* h = nullptr;
@@ -571,6 +581,9 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
     cudaStream_t s = ctx->stream;
     if ((flags & DMK_STEP_ADVANCE) && !(flags & DMK_STEP_POSE))
         return fail(ctx, DMK_ERR_UNSUPPORTED, "DMK_STEP_ADVANCE runs inside the pose kernel: combine it with DMK_STEP_POSE");
+    // refused before anything is enqueued: a third outstanding read-back has no slot to land in
+    if ((flags & DMK_STEP_CULL) && (flags & DMK_STEP_READBACK_VISIBILITY) && c->vis_pending == 2)
+        return fail(ctx, DMK_ERR_INVALID, "two visibility read-backs are already outstanding: collect one first");
     if (flags & DMK_STEP_ANIMATOR) {
         if (!c->animator_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_animator has not been called");
         if (flags & DMK_STEP_ADVANCE) return fail(ctx, DMK_ERR_UNSUPPORTED, "the device animators own the clip clocks: do not combine them with DMK_STEP_ADVANCE");
@@ -638,6 +651,8 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         p.locals = c->d_locals;
         p.key_indices = c->d_key_indices;
         p.error_flag = c->d_error;
+        // the error word describes THIS pose step: a bad clip index of an earlier frame does not outlive the layers that had it
+        DMK_CUDA(ctx, cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), s));
         p.scratch = c->d_local_matrices;
         int pose_launches = 0;
         {

@@ -33,10 +33,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    // try_wait suspends the thread in hardware until the phase completes or a time limit passes; the spin bound
-    // turns a protocol bug into a trap instead of a hung GPU
+    // try_wait suspends the thread in hardware until the phase completes or a time limit passes.  A protocol bug becomes a
+    // trap instead of a hung GPU; the bound is in TIME (%globaltimer, 10 s), not in polls, so that a slow phase -- a profiler
+    // replay, a preempted context, a side-stream kernel holding the SM -- is never mistaken for one.
     uint32_t done = 0;
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     const uint32_t addr = smem_u32(bar);
     do {
         asm volatile(
@@ -48,7 +50,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1u << 22)) __trap();
+        if (!done && (++spins & 0xfffu) == 0) {   // every 4096 polls: look at the clock
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) __trap();
+        }
     } while (!done);
 }
 // mbarrier arrive (release at CTA scope): one arrival per warp after its lanes' shared-memory writes

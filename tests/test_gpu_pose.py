@@ -370,3 +370,49 @@ def test_debug_bone_matrices(assets):
         assert np.array_equal(part, full[7:12])
     finally:
         g.close()
+
+
+def test_per_frame_layer_update_refuses_bad_clips_and_the_crowd_stays_usable(rigs):
+    # dmk_crowd_update_layers (the per-frame path) validates clip indices like dmk_crowd_set_layers; a refused update leaves the
+    # crowd as it was, and the error word of the pose kernel describes the latest pose step only
+    g, o, a = rigs
+    n = 65
+    cr = synth.make_crowd(n, 2, len(a.clips), seed=21)
+    crowd = g.crowd(n, 2, mesh=False)
+    crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+    crowd.step(0.0, g.capi.STEP_POSE)
+    good = crowd.get_palette()
+    for bad_index in (len(a.clips), -1, 2 ** 30):
+        bad = cr.clip.copy()
+        bad[1, 17] = bad_index
+        with pytest.raises(g.capi.DmkError) as e:
+            crowd.update_layers(bad, cr.ratio, cr.weight)
+        assert e.value.status == g.capi.ERR_INVALID and "character 17" in e.value.message
+    crowd.step(0.0, g.capi.STEP_POSE)
+    assert np.array_equal(crowd.get_palette(), good)
+    crowd.update_layers(cr.clip, cr.ratio, cr.weight)
+    crowd.step(0.0, g.capi.STEP_POSE)
+    assert np.array_equal(crowd.get_palette(), good)
+
+
+def test_third_outstanding_readback_is_refused_before_anything_is_enqueued(rigs):
+    g, o, a = rigs
+    n = 40
+    cr = synth.make_crowd(n, 1, len(a.clips), seed=22)
+    inst = synth.make_instances(n, seed=2, extent=40.0)
+    crowd = g.crowd(n, 1, mesh=False)
+    crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed)
+    crowd.set_instances(inst.world_inverse, inst.bbox)
+    crowd.set_camera(synth.sample_camera_view_proj(), 0.0)
+    flags = g.capi.STEP_POSE | g.capi.STEP_CULL | g.capi.STEP_READBACK_VISIBILITY
+    crowd.step(0.0, flags)
+    crowd.step(0.0, flags)
+    launches = g.ctx.launches
+    with pytest.raises(g.capi.DmkError) as e:
+        crowd.step(0.0, flags)
+    assert e.value.status == g.capi.ERR_INVALID and g.ctx.launches == launches   # no pose, no cull: nothing ran
+    bits = np.zeros((n + 31) // 32, np.uint32)
+    crowd.collect_visibility(bits)
+    crowd.step(0.0, flags)          # a slot is free again
+    crowd.collect_visibility(bits)
+    crowd.collect_visibility(bits)

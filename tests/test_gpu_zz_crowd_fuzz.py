@@ -1,7 +1,7 @@
 """Seeded random configurations through the C ABI against the oracle (tests/crowd_fuzz_check.py, in a child process): skeleton /
-armature / palette sizes, layers and thresholds, vertex counts and orders, skinned layouts, crowd sizes.  The script draws the
-non-interleaved skinning shapes too, which had not run on hardware when this was written -- hence the non-strict xfail; all
-of it passes on the CPU lockstep simulator (tests/test_devsim.py)."""
+armature / palette sizes, layers and thresholds, vertex counts and orders, skinned layouts, crowd sizes.  The script draws every
+skinning shape, vertex order and kernel shape (verified on a B200 in round 2: profiles/r02_*; the same script runs on the CPU
+lockstep simulator in tests/test_devsim.py)."""
 import os
 import subprocess
 import sys
@@ -12,7 +12,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="draws skinning shapes not yet verified on hardware (round 1 GPU budget spent)", strict=False)
 def test_random_configurations_match_the_oracle():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "crowd_fuzz_check.py"), "1", "60"], capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:], r.stderr[-2000:])

@@ -1,9 +1,8 @@
 """Peer-memory palette exchange (dmk_exchange_*: the pack+transfer kernel that replaces NCCL in the frame loop) on one GPU
 with three logical ranks.  The check itself is tests/peer_exchange_check.py, run in a child process with a time limit.
 
-The kernels were written after round 1's GPU budget was spent: they compile for sm_100a (tests/test_capi_symbols.py) but had
-not run on hardware when this test was committed, hence the non-strict xfail -- an XPASS in the report is the first
-hardware evidence, an xfail leaves the parity suite green.  The file sorts last so it cannot disturb the other GPU tests."""
+Verified on hardware in round 2 (one GPU with three logical ranks, two processes over CUDA IPC, and 2 / 8 GPUs over NVLink through
+bench.py's own content check: profiles/r02_b2_*, r02_b8_*).  The file sorts last so it cannot disturb the other GPU tests."""
 import os
 import subprocess
 import sys
@@ -14,7 +13,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="peer-memory exchange not yet verified on hardware (round 1 GPU budget spent)", strict=False)
 def test_peer_exchange_three_logical_ranks_on_one_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "peer_exchange_check.py")], capture_output=True, text=True, timeout=300)
     print(r.stdout[-2000:], r.stderr[-2000:])
@@ -24,7 +22,6 @@ def test_peer_exchange_three_logical_ranks_on_one_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="peer-memory exchange not yet verified on hardware (round 1 GPU budget spent)", strict=False)
 def test_peer_exchange_two_processes_over_cuda_ipc():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "peer_exchange_ipc_check.py")], capture_output=True, text=True, timeout=400)
     print(r.stdout[-2000:], r.stderr[-2000:])
