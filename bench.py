@@ -69,6 +69,8 @@ def workload_config(args):
         "mesh_vertex_order": ("stored clustered by bone (dmk_mesh_create_ex DMK_MESH_CLUSTER_BONES: a permutation the library reports through "
                               "dmk_mesh_vertex_order; same vertices, same results)" if args.mesh_order == "clustered" else "caller's order"),
         "gather": gather_description(args),
+        "palette": ("3x4 row-major per character (what the skinning kernel reads); the column-major mat4 of u_skinning is produced for the "
+                    "visible characters by the pack / exchange (DMK_OPT_PALETTE_3X4_ONLY)" if not args.palette44 else "mat4 + 3x4 per character"),
         "l2": "inputs larger than L2: each step streams %.1f GB of skinned vertices per GPU (L2 = 126 MB)"
               % (args.chars * args.verts * 36 / 1e9),
     }
@@ -318,6 +320,12 @@ def run_gpu(args):
         crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
         if args.round1_kernel:
             crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, 1)
+        if args.pose_fused:
+            crowd.set_option(capi.OPT_POSE_FUSED, 1)
+        if not args.palette44:
+            # the mat4 palette is delivered where it is consumed (the packed / exchanged visible palettes); the per-frame
+            # [N][K+1][16] copy for all characters is not written (DMK_OPT_PALETTE_3X4_ONLY)
+            crowd.set_option(capi.OPT_PALETTE_3X4_ONLY, 1)
         if args.skin_layout:
             crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, args.skin_layout)
         cr = synth.make_crowd(n, 2, len(clips_s), seed=42 + rank)       # varied clips / phases per rank
@@ -677,6 +685,8 @@ def main():
     ap.add_argument("--mesh-order", default="clustered", choices=["caller", "clustered"],
                     help="stored vertex order: the caller's, or clustered by bone (DMK_MESH_CLUSTER_BONES; the library reports the permutation)")
     ap.add_argument("--round1-kernel", action="store_true", help="DMK_OPT_SKIN_ROUND1_KERNEL: the round-1 skinning kernel shape, for A/B")
+    ap.add_argument("--pose-fused", action="store_true", help="DMK_OPT_POSE_FUSED: sampling + local-to-model + palette in one kernel (less DRAM traffic, slower: see dmk.h), for A/B")
+    ap.add_argument("--palette44", action="store_true", help="also write the mat4 palette of every character each frame (default: 3x4 only, mat4 where consumed)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

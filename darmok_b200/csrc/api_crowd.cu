@@ -120,6 +120,15 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
             if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - c->reserved_sms, c->skin_variant, c->skin_legacy);
         return DMK_OK;
     }
+    if (option == DMK_OPT_POSE_FUSED) {
+        c->pose_fused = value != 0;
+        return DMK_OK;
+    }
+    if (option == DMK_OPT_PALETTE_3X4_ONLY) {
+        if (!c->mesh && !c->d_palette34) return fail(c->ctx, DMK_ERR_INVALID, "the crowd has no armature");
+        c->palette_3x4_only = value != 0;
+        return DMK_OK;
+    }
     if (option == DMK_OPT_KEEP_WORLD_INVERSE) {
         if (bind(c->ctx)) return DMK_ERR_CUDA;
         if (value && !c->d_world_inverse) DMK_CUDA(c->ctx, dev_alloc(&c->d_world_inverse, static_cast<size_t>(c->n) * 16));
@@ -645,8 +654,9 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         p.program = c->use_program ? c->d_program : nullptr;
         p.dt = dt;
         p.advance = (flags & DMK_STEP_ADVANCE) ? 1 : 0;
-        p.palette = c->d_palette;
+        p.palette = c->palette_3x4_only ? nullptr : c->d_palette;
         p.palette34 = c->d_palette34;
+        p.fused = (c->pose_fused && c->extra_skins.empty()) ? 1 : 0;
         p.models = c->d_models;
         p.locals = c->d_locals;
         p.key_indices = c->d_key_indices;

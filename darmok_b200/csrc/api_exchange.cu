@@ -126,7 +126,8 @@ static dmk_status exchange_stage(dmk_crowd_t c, dmk_exchange_t x, int num_sms, c
     if (!x->d_stage && floats) DMK_CUDA(ctx, dev_alloc(&x->d_stage, floats));
     KernelTimer timer(ctx, DMK_KERNEL_PACK, s);
     if (x->capacity > 0)
-        DMK_CUDA(ctx, launch_pack_palettes(c->d_palette, x->palette_size * 16, c->d_visible_ids, c->d_visible_count, x->capacity, x->d_stage, num_sms, s));
+        DMK_CUDA(ctx, launch_pack_palettes(c->palette_3x4_only ? c->d_palette34 : c->d_palette, x->palette_size * 16, c->d_visible_ids, c->d_visible_count,
+                                           x->capacity, x->d_stage, num_sms, s, c->palette_3x4_only));
     ++ctx->launches;
     return DMK_OK;
 }
@@ -180,8 +181,9 @@ dmk_status dmk_crowd_push_visible_palettes(dmk_crowd_t c, dmk_exchange_t x, uint
     }
     {
         KernelTimer timer(ctx, DMK_KERNEL_PACK, s);
-        DMK_CUDA(ctx, launch_push_palettes(c->d_palette, x->palette_size * 16, c->d_visible_ids, c->d_visible_count, x->capacity, slab, x->header(),
-                                           x->rank, frame, x->d_local, x->d_local + 1, x->timeout_ns, num_ctas, s));
+        DMK_CUDA(ctx, launch_push_palettes(c->palette_3x4_only ? c->d_palette34 : c->d_palette, x->palette_size * 16, c->d_visible_ids, c->d_visible_count,
+                                           x->capacity, slab, x->header(), x->rank, frame, x->d_local, x->d_local + 1, x->timeout_ns, num_ctas, s,
+                                           c->palette_3x4_only));
     }
     ++ctx->launches;
     x->last_pushed = frame;

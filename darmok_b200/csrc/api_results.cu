@@ -4,7 +4,7 @@
 extern "C" {
 
 // ---- results -----------------------------------------------------------------------------------------------
-const float* dmk_crowd_palette_dev(dmk_crowd_t c) { return c ? c->d_palette : nullptr; }
+const float* dmk_crowd_palette_dev(dmk_crowd_t c) { return c && !c->palette_3x4_only ? c->d_palette : nullptr; }
 const float* dmk_crowd_skinned_dev(dmk_crowd_t c) { return c ? c->d_skinned : nullptr; }
 const uint32_t* dmk_crowd_visibility_dev(dmk_crowd_t c) { return c ? c->d_vis_bits : nullptr; }
 const int32_t* dmk_crowd_visible_ids_dev(dmk_crowd_t c) { return c ? c->d_visible_ids : nullptr; }
@@ -29,6 +29,19 @@ dmk_status dmk_crowd_get_palette(dmk_crowd_t c, int64_t first, int64_t count, fl
     if (!c->arm) return fail(c->ctx, DMK_ERR_INVALID, "crowd has no armature");
     if (count == 0) return DMK_OK;
     const size_t per = static_cast<size_t>(c->arm->num_joints + 1) * 16;
+    if (c->palette_3x4_only) {   // DMK_OPT_PALETTE_3X4_ONLY: expand the row-major 3x4 palette on the host
+        DMK_CUDA(c->ctx, cudaMemcpyAsync(out, c->d_palette34 + first * per, count * per * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
+        if (dmk_status st = finish_and_check(c)) return st;
+        for (size_t s = 0; s < static_cast<size_t>(count) * per; s += 16) {
+            float m[16];
+            for (int col = 0; col < 4; ++col) {
+                for (int r = 0; r < 3; ++r) m[col * 4 + r] = out[s + r * 4 + col];
+                m[col * 4 + 3] = col == 3 ? 1.f : 0.f;
+            }
+            std::memcpy(out + s, m, sizeof m);
+        }
+        return DMK_OK;
+    }
     DMK_CUDA(c->ctx, cudaMemcpyAsync(out, c->d_palette + first * per, count * per * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
     return finish_and_check(c);
 }
@@ -248,8 +261,8 @@ dmk_status dmk_crowd_pack_visible_palettes(dmk_crowd_t c, float* out_dev, int64_
     if (bind(c->ctx)) return DMK_ERR_CUDA;
     {
         KernelTimer timer(c->ctx, DMK_KERNEL_PACK);
-        DMK_CUDA(c->ctx, launch_pack_palettes(c->d_palette, (c->arm->num_joints + 1) * 16, c->d_visible_ids, c->d_visible_count, capacity,
-                                              out_dev, c->ctx->num_sms, c->ctx->stream));
+        DMK_CUDA(c->ctx, launch_pack_palettes(c->palette_3x4_only ? c->d_palette34 : c->d_palette, (c->arm->num_joints + 1) * 16, c->d_visible_ids,
+                                              c->d_visible_count, capacity, out_dev, c->ctx->num_sms, c->ctx->stream, c->palette_3x4_only));
     }
     ++c->ctx->launches;
     return DMK_OK;

@@ -291,14 +291,16 @@ __global__ void __launch_bounds__(kScanBlock) compact_scatter_kernel(const uint3
     }
 }
 
+// `from34`: `palette` is the 3x4 row-major palette (same 16 floats per slot); the output is column-major mat4 either way
 __global__ void pack_palettes_kernel(const float4* __restrict__ palette, int palette_vec4, const int32_t* __restrict__ ids,
-                                     const int32_t* __restrict__ count, int64_t capacity, float4* __restrict__ out) {
+                                     const int32_t* __restrict__ count, int64_t capacity, float4* __restrict__ out, int from34) {
     int64_t total = count[0];
     if (total > capacity) total = capacity;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     for (int64_t i = warp; i < total; i += warps) {
-        warp_copy_palette(palette + (size_t)ids[i] * palette_vec4, out + (size_t)i * palette_vec4, palette_vec4, lane);
+        if (from34) warp_copy_palette34_as_mat4(reinterpret_cast<const float*>(palette + (size_t)ids[i] * palette_vec4), out + (size_t)i * palette_vec4, palette_vec4, lane);
+        else warp_copy_palette(palette + (size_t)ids[i] * palette_vec4, out + (size_t)i * palette_vec4, palette_vec4, lane);
     }
 }
 
@@ -394,9 +396,9 @@ cudaError_t launch_compact(const uint32_t* vis_bits, int64_t n, int32_t* ids_out
 }
 
 cudaError_t launch_pack_palettes(const float* palette, int palette_floats, const int32_t* ids, const int32_t* count,
-                                 int64_t capacity, float* out, int num_sms, cudaStream_t stream) {
+                                 int64_t capacity, float* out, int num_sms, cudaStream_t stream, bool from34) {
     DMK_LAUNCH(pack_palettes_kernel, num_sms * 4, 256, 0, stream)(reinterpret_cast<const float4*>(palette), palette_floats / 4, ids,
-                                                          count, capacity, reinterpret_cast<float4*>(out));
+                                                          count, capacity, reinterpret_cast<float4*>(out), from34 ? 1 : 0);
     return cudaGetLastError();
 }
 

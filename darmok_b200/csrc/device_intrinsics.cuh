@@ -164,6 +164,28 @@ __device__ __forceinline__ void warp_copy_palette(const float4* __restrict__ src
     }
 }
 
+// The same from the 3x4 row-major palette the skinning kernel reads ([slot][3 rows + 1 unused row][4]) into column-major mat4:
+// float4 k of the destination is column k % 4 of slot k / 4, bottom row (0, 0, 0, 1).
+__device__ __forceinline__ void warp_copy_palette34_as_mat4(const float* __restrict__ src34, float4* __restrict__ dst, int palette_vec4, int lane) {
+    constexpr int kInFlight = 8;
+    for (int base = 0; base < palette_vec4; base += 32 * kInFlight) {
+        float4 v[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const int k = base + u * 32 + lane;
+            if (k < palette_vec4) {
+                const float* s = src34 + (size_t)(k >> 2) * 16 + (k & 3);
+                v[u] = make_float4(__ldg(s), __ldg(s + 4), __ldg(s + 8), (k & 3) == 3 ? 1.f : 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const int k = base + u * 32 + lane;
+            if (k < palette_vec4) dst[k] = v[u];
+        }
+    }
+}
+
 // ---- system scope (peer memory over NVLink) -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;

@@ -88,6 +88,7 @@ struct PoseParams {
     int32_t* key_indices;     // [N][L][3][P][2]
     int32_t* error_flag;      // set to character index + 1 when a job would fail
     float* scratch;           // [N][P][16] local 3x4 matrices (sampling kernel -> model kernel)
+    int fused;                // one kernel for sampling + local-to-model + palette (no scratch round trip)
 };
 
 struct SkinParams {

@@ -40,7 +40,7 @@ __device__ bool wait_reached(const uint32_t* word, uint32_t need, uint64_t timeo
 __global__ void __launch_bounds__(256) push_palettes_kernel(const float4* __restrict__ palette, int palette_vec4, const int32_t* __restrict__ ids,
                                                             const int32_t* __restrict__ count, int64_t capacity, float4* __restrict__ slab,
                                                             ExchangeHeader* hdr, int rank, uint32_t frame, uint32_t* done, uint32_t* local_error,
-                                                            uint64_t timeout_ns) {
+                                                            uint64_t timeout_ns, int from34) {
     __shared__ int go;
     if (threadIdx.x == 0) {
         // flow control: the buffer of this frame was last read for frame - 2
@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(256) push_palettes_kernel(const float4* __rest
         const int warps = (gridDim.x * blockDim.x) >> 5;
         const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
         for (int64_t i = warp; i < total; i += warps) {
-            warp_copy_palette(palette + static_cast<size_t>(ids[i]) * palette_vec4, slab + static_cast<size_t>(i) * palette_vec4, palette_vec4, lane);
+            if (from34) warp_copy_palette34_as_mat4(reinterpret_cast<const float*>(palette + static_cast<size_t>(ids[i]) * palette_vec4), slab + static_cast<size_t>(i) * palette_vec4, palette_vec4, lane);
+            else warp_copy_palette(palette + static_cast<size_t>(ids[i]) * palette_vec4, slab + static_cast<size_t>(i) * palette_vec4, palette_vec4, lane);
         }
     }
     // last block out publishes: fence (release of this thread's stores at system scope), block barrier, ticket
@@ -110,9 +111,9 @@ __global__ void release_frame_kernel(ExchangeHeader* hdr, uint32_t frame) {
 
 cudaError_t launch_push_palettes(const float* palette, int palette_floats, const int32_t* ids, const int32_t* count, int64_t capacity, float* slab,
                                  ExchangeHeader* hdr, int rank, uint32_t frame, uint32_t* done, uint32_t* local_error, uint64_t timeout_ns, int num_ctas,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, bool from34) {
     DMK_LAUNCH(push_palettes_kernel, num_ctas, 256, 0, stream)(reinterpret_cast<const float4*>(palette), palette_floats / 4, ids, count, capacity,
-                                                       reinterpret_cast<float4*>(slab), hdr, rank, frame, done, local_error, timeout_ns);
+                                                       reinterpret_cast<float4*>(slab), hdr, rank, frame, done, local_error, timeout_ns, from34 ? 1 : 0);
     return cudaGetLastError();
 }
 cudaError_t launch_wait_published(ExchangeHeader* hdr, int world, uint32_t frame, int32_t* counts_out, int64_t capacity, uint64_t timeout_ns,

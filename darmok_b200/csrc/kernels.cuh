@@ -42,13 +42,13 @@ cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t 
 
 // K6 payload: gather palettes of the listed characters into a dense buffer
 cudaError_t launch_pack_palettes(const float* palette, int palette_floats, const int32_t* ids, const int32_t* count,
-                                 int64_t capacity, float* out, int num_sms, cudaStream_t stream);
+                                 int64_t capacity, float* out, int num_sms, cudaStream_t stream, bool from34 = false);
 
 // K6' (exchange_kernel.cu): pack + transfer of the visible palettes into the render GPU's slab over peer memory; the
 // owner-side wait for a frame of every rank and the release of its buffer
 cudaError_t launch_push_palettes(const float* palette, int palette_floats, const int32_t* ids, const int32_t* count, int64_t capacity, float* slab,
                                  ExchangeHeader* hdr, int rank, uint32_t frame, uint32_t* done, uint32_t* local_error, uint64_t timeout_ns, int num_ctas,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, bool from34 = false);
 cudaError_t launch_wait_published(ExchangeHeader* hdr, int world, uint32_t frame, int32_t* counts_out, int64_t capacity, uint64_t timeout_ns,
                                   cudaStream_t stream);
 // copy-engine transport: flow control in front of the DMA copy, publication behind it (one thread each)

@@ -357,15 +357,13 @@ __global__ void __launch_bounds__(256) advance_kernel(const PoseParams p) {
 #ifndef DMK_SAMPLE_BLOCK
 #define DMK_SAMPLE_BLOCK 128
 #endif
+// One (character, joint): the layers of the character's pose program sampled and blended, FromAffine -> m[12].  Returns false for
+// a character without a state (kTopSkip: the animator keeps its previous matrices, src/skeleton_ozz.cpp:1029-1032).
 template <int F>
-__global__ void __launch_bounds__(DMK_SAMPLE_BLOCK, DMK_SAMPLE_MIN_BLOCKS) sample_kernel(const PoseParams p) {
+__device__ __forceinline__ bool sample_local_matrix(const PoseParams& p, int64_t c, int j, float m[12]) {
     const int P = p.skel.padded_joints;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= p.n * P) return;
-    const int64_t c = tid / P;
-    const int j = (int)(tid - c * P);
     const PoseProgram prog = load_program(p, c);
-    if (prog.top == kTopSkip) return;  // no state: the animator keeps its previous matrices (:1029-1032)
+    if (prog.top == kTopSkip) return false;
     const int64_t n = p.n;
     const int L = p.num_layers;
     bool bad = false;
@@ -402,11 +400,78 @@ __global__ void __launch_bounds__(DMK_SAMPLE_BLOCK, DMK_SAMPLE_MIN_BLOCKS) sampl
         o[12] = acc.r[0]; o[16] = acc.r[1]; o[20] = acc.r[2]; o[24] = acc.r[3];
         o[28] = acc.s[0]; o[32] = acc.s[1]; o[36] = acc.s[2];
     }
-    float m[12];
     from_affine(acc, m);
+    return true;
+}
+
+template <int F>
+__global__ void __launch_bounds__(DMK_SAMPLE_BLOCK, DMK_SAMPLE_MIN_BLOCKS) sample_kernel(const PoseParams p) {
+    const int P = p.skel.padded_joints;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= p.n * P) return;
+    const int64_t c = tid / P;
+    const int j = (int)(tid - c * P);
+    float m[12];
+    if (!sample_local_matrix<F>(p, c, j, m)) return;
     float* out = p.scratch + (size_t)tid * 16;
     st_v8(out, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
     st_v8(out + 8, m[8], m[9], m[10], m[11], 0.f, 0.f, 0.f, 0.f);
+}
+
+// LocalToModelJob for one character by one warp: level order, one (joint, column) task per lane per round; s_loc / s_mod are the
+// character's local and model matrices in shared memory ([P][kMS] each).
+__device__ __forceinline__ void local_to_model_rounds(int rounds, const uint16_t* s_sched, const int16_t* s_parents, const float* s_identity,
+                                                      const float* s_loc, float* s_mod, int lane) {
+    for (int rd = 0; rd < rounds; ++rd) {
+        const unsigned task = s_sched[rd * 32 + lane];
+        if (task != kIdleTask) {
+            const int j = task & 0xfff, col = task >> 12;
+            const int parent = s_parents[j];
+            const float* pm = parent < 0 ? s_identity : s_mod + (size_t)parent * kMS;
+            const float* lc = s_loc + (size_t)j * kMS + col * 3;
+            const float l0 = lc[0], l1 = lc[1], l2 = lc[2], l3 = col == 3 ? 1.f : 0.f;
+            float* o = s_mod + (size_t)j * kMS + col * 3;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)  // ozz Float4x4 product: (a0*x + a1*y) + (a2*z + a3*w)
+                o[r] = (pm[r] * l0 + pm[3 + r] * l1) + (pm[6 + r] * l2 + pm[9 + r] * l3);
+        }
+        __syncwarp();
+    }
+}
+
+// Palette slot k + 1 of one character: flipHandedness(model[jm]) * inverse bind (src/skeleton_ozz.cpp:962-977, src/skeleton.cpp:236-249),
+// written as the column-major mat4 (pal) and / or the row-major 3x4 the skinning kernel reads (p34): 256-bit full-sector stores.
+__device__ __forceinline__ void palette_slot(int jm, const float* s_mod, const float* b, float* pal, float* p34, int k) {
+    float m[12];
+    if (jm >= 0) {
+        const float* src = s_mod + (size_t)jm * kMS;  // Math::flipHandedness: Z * M * Z
+        m[0] = src[0]; m[1] = src[1]; m[2] = -src[2];
+        m[3] = src[3]; m[4] = src[4]; m[5] = -src[5];
+        m[6] = -src[6]; m[7] = -src[7]; m[8] = src[8];
+        m[9] = src[9]; m[10] = src[10]; m[11] = -src[11];
+    } else {  // unknown joint name: getJointModelMatrix returns mat4(1)
+#pragma unroll
+        for (int e = 0; e < 12; ++e) m[e] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
+    }
+    float v[4][3];  // [column][row]
+#pragma unroll
+    for (int col = 0; col < 4; ++col) {
+        const float b0 = b[col * 3 + 0], b1 = b[col * 3 + 1], b2 = b[col * 3 + 2];
+        const float b3 = col == 3 ? 1.f : 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)  // glm mat4 * mat4: ((A0*b0 + A1*b1) + A2*b2) + A3*b3
+            v[col][r] = ((m[r] * b0 + m[3 + r] * b1) + m[6 + r] * b2) + m[9 + r] * b3;
+    }
+    if (pal) {
+        float* o = pal + (size_t)(k + 1) * 16;
+        st_v8(o, v[0][0], v[0][1], v[0][2], 0.f, v[1][0], v[1][1], v[1][2], 0.f);
+        st_v8(o + 8, v[2][0], v[2][1], v[2][2], 0.f, v[3][0], v[3][1], v[3][2], 1.f);
+    }
+    if (p34) {
+        float* o = p34 + (size_t)(k + 1) * 16;
+        st_v8(o, v[0][0], v[1][0], v[2][0], v[3][0], v[0][1], v[1][1], v[2][1], v[3][1]);
+        st_v8(o + 8, v[0][2], v[1][2], v[2][2], v[3][2], 0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // ---- K2 + K3: local-to-model and skin palette, one warp per character ------------------------------------------------
@@ -454,21 +519,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) model_kernel(const PosePa
         __syncwarp();
 
         // ---- K2: local-to-model, level order; one (joint, column) per lane per round ----
-        for (int rd = 0; rd < p.skel.rounds; ++rd) {
-            const unsigned task = s_sched[rd * 32 + lane];
-            if (task != kIdleTask) {
-                const int j = task & 0xfff, col = task >> 12;
-                const int parent = s_parents[j];
-                const float* pm = parent < 0 ? s_identity : s_mod + (size_t)parent * kMS;
-                const float* lc = s_loc + (size_t)j * kMS + col * 3;
-                const float l0 = lc[0], l1 = lc[1], l2 = lc[2], l3 = col == 3 ? 1.f : 0.f;
-                float* o = s_mod + (size_t)j * kMS + col * 3;
-#pragma unroll
-                for (int r = 0; r < 3; ++r)  // ozz Float4x4 product: (a0*x + a1*y) + (a2*z + a3*w)
-                    o[r] = (pm[r] * l0 + pm[3 + r] * l1) + (pm[6 + r] * l2 + pm[9 + r] * l3);
-            }
-            __syncwarp();
-        }
+        local_to_model_rounds(p.skel.rounds, s_sched, s_parents, s_identity, s_loc, s_mod, lane);
 
         // ---- K3: flip handedness + palette = model * inverse bind ----
         if (p.models) {
@@ -490,46 +541,119 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) model_kernel(const PosePa
                 if (pal) { st_v8(pal, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(pal + 8, 0, 0, 1, 0, 0, 0, 0, 1); }
                 if (p34) { st_v8(p34, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(p34 + 8, 0, 0, 1, 0, 0, 0, 0, 0); }
             }
-            for (int k = lane; k < K; k += 32) {
-                const int jm = s_remap[k];
-                float m[12];
-                if (jm >= 0) {
-                    const float* src = s_mod + (size_t)jm * kMS;  // Math::flipHandedness: Z * M * Z
-                    m[0] = src[0]; m[1] = src[1]; m[2] = -src[2];
-                    m[3] = src[3]; m[4] = src[4]; m[5] = -src[5];
-                    m[6] = -src[6]; m[7] = -src[7]; m[8] = src[8];
-                    m[9] = src[9]; m[10] = src[10]; m[11] = -src[11];
-                } else {  // unknown joint name: getJointModelMatrix returns mat4(1)
-#pragma unroll
-                    for (int e = 0; e < 12; ++e) m[e] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
-                }
-                const float* b = s_inv_bind + (size_t)k * kMS;
-                float v[4][3];  // [column][row]
-#pragma unroll
-                for (int col = 0; col < 4; ++col) {
-                    const float b0 = b[col * 3 + 0], b1 = b[col * 3 + 1], b2 = b[col * 3 + 2];
-                    const float b3 = col == 3 ? 1.f : 0.f;
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)  // glm mat4 * mat4: ((A0*b0 + A1*b1) + A2*b2) + A3*b3
-                        v[col][r] = ((m[r] * b0 + m[3 + r] * b1) + m[6 + r] * b2) + m[9 + r] * b3;
-                }
-                if (pal) {
-                    float* o = pal + (size_t)(k + 1) * 16;
-                    st_v8(o, v[0][0], v[0][1], v[0][2], 0.f, v[1][0], v[1][1], v[1][2], 0.f);
-                    st_v8(o + 8, v[2][0], v[2][1], v[2][2], 0.f, v[3][0], v[3][1], v[3][2], 1.f);
-                }
-                if (p34) {
-                    float* o = p34 + (size_t)(k + 1) * 16;
-                    st_v8(o, v[0][0], v[1][0], v[2][0], v[3][0], v[0][1], v[1][1], v[2][1], v[3][1]);
-                    st_v8(o + 8, v[0][2], v[1][2], v[2][2], v[3][2], 0.f, 0.f, 0.f, 0.f);
-                }
-            }
+            for (int k = lane; k < K; k += 32) palette_slot(s_remap[k], s_mod, s_inv_bind + (size_t)k * kMS, pal, p34, k);
         }
         __syncwarp();  // the matrix arrays are reused by the next character
     }
 }
 
+// ---- K1 + K2 + K3 in one kernel (round 2): no round trip of the local matrices through HBM ---------------------------------
+// The two-kernel path above writes 64 B of local matrix per joint and reads them back (profiles/r01_sample_kernel.txt,
+// r01_model_kernel.txt: 1.65 GB of DRAM traffic per 100k characters against 0.44 GB of algorithmic bytes).  Here a block owns
+// `cpb` characters at a time:
+//   phase 1  one thread per (character, joint): sampling + blend + FromAffine, as sample_kernel, into shared memory;
+//   phase 2  one warp per character: LocalToModelJob, level order (local_to_model_rounds);
+//   phase 3  one thread per (character, palette slot): flip + inverse bind, 256-bit stores of the palette(s).
+// Same device functions, same operation order: results are bit-identical to the two-kernel path.  MEASURED (B200, 100k characters,
+// profiles/r02_pose_fused_kernel.txt): DRAM traffic 0.40 GB instead of 1.65 GB, but 742 us instead of 613 us -- the path is
+// latency bound (barrier 2.8 and long-scoreboard 3.6 stalled warps per issued instruction at 27 resident warps), not bandwidth
+// bound, so the two kernels stay the default and this one is opt-in (DMK_OPT_POSE_FUSED).
+constexpr int kFusedMaxThreads = 288;   // 4 characters x 68 padded joints = 272 threads: 9 warps, 16 idle lanes
+#ifndef DMK_FUSED_MIN_BLOCKS
+#define DMK_FUSED_MIN_BLOCKS 3
+#endif
+template <int F>
+__global__ void __launch_bounds__(kFusedMaxThreads, DMK_FUSED_MIN_BLOCKS) pose_fused_kernel(const PoseParams p, int cpb) {
+    DMK_DYNAMIC_SMEM(smem_raw, 16);
+    const int J = p.skel.num_joints, P = p.skel.padded_joints, K = p.arm.num_joints, PS = K + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    float* s_inv_bind = reinterpret_cast<float*>(smem_raw);                   // [K][kMS]
+    float* s_identity = s_inv_bind + (size_t)K * kMS;                         // [12] (+4 pad)
+    int32_t* s_remap = reinterpret_cast<int32_t*>(s_identity + 16);           // [K]
+    int16_t* s_parents = reinterpret_cast<int16_t*>(s_remap + ((K + 3) & ~3)); // [P]
+    uint16_t* s_sched = reinterpret_cast<uint16_t*>(s_parents + ((P + 7) & ~7)); // [rounds][32]
+    const int per_char = (2 * P * kMS + 3) & ~3;                              // local + model matrices of one character
+    float* s_char0 = reinterpret_cast<float*>(
+        (reinterpret_cast<uintptr_t>(s_sched + (size_t)p.skel.rounds * 32) + 15) & ~uintptr_t(15));
+    uint8_t* s_live = reinterpret_cast<uint8_t*>(s_char0 + (size_t)cpb * per_char);   // [cpb] character has a state this frame
+
+    for (int i = threadIdx.x; i < K * 12; i += blockDim.x) s_inv_bind[(i / 12) * kMS + i % 12] = p.arm.inv_bind[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_remap[i] = p.arm.remap[i];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_parents[i] = i < J ? p.skel.parents[i] : (int16_t)-1;
+    for (int i = threadIdx.x; i < p.skel.rounds * 32; i += blockDim.x) s_sched[i] = p.skel.schedule[i];
+    if (threadIdx.x < 12) s_identity[threadIdx.x] = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.f : 0.f;
+    __syncthreads();
+
+    const int64_t n = p.n;
+    const int slot = threadIdx.x / P, j = threadIdx.x - slot * P;   // phase 1: this thread's (character of the group, joint)
+    const int64_t groups = (n + cpb - 1) / cpb;
+    for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const int64_t c0 = g * cpb;
+        // ---- phase 1: sample + blend + FromAffine -> shared memory ----
+        if (slot < cpb && c0 + slot < n) {
+            float m[12];
+            const bool live = sample_local_matrix<F>(p, c0 + slot, j, m);
+            if (j == 0) s_live[slot] = live ? 1 : 0;
+            if (live) {
+                float* d = s_char0 + (size_t)slot * per_char + (size_t)j * kMS;
+#pragma unroll
+                for (int e = 0; e < 12; ++e) d[e] = m[e];
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: local-to-model, one warp per character ----
+        for (int s2 = warp; s2 < cpb; s2 += (blockDim.x >> 5)) {
+            if (c0 + s2 >= n || !s_live[s2]) continue;
+            float* s_loc = s_char0 + (size_t)s2 * per_char;
+            local_to_model_rounds(p.skel.rounds, s_sched, s_parents, s_identity, s_loc, s_loc + (size_t)P * kMS, lane);
+        }
+        __syncthreads();
+        // ---- phase 3: models (optional) and palette slots, one thread per (character, joint / slot) ----
+        if (p.models) {
+            for (int idx = threadIdx.x; idx < cpb * J; idx += blockDim.x) {
+                const int s3 = idx / J, jj = idx - s3 * J;
+                if (c0 + s3 >= n || !s_live[s3]) continue;
+                const float* m = s_char0 + (size_t)s3 * per_char + (size_t)P * kMS + (size_t)jj * kMS;
+                float* o = p.models + ((size_t)(c0 + s3) * J + jj) * 16;
+                o[0] = m[0]; o[1] = m[1]; o[2] = -m[2]; o[3] = 0.f;
+                o[4] = m[3]; o[5] = m[4]; o[6] = -m[5]; o[7] = 0.f;
+                o[8] = -m[6]; o[9] = -m[7]; o[10] = m[8]; o[11] = 0.f;
+                o[12] = m[9]; o[13] = m[10]; o[14] = -m[11]; o[15] = 1.f;
+            }
+        }
+        if (p.palette || p.palette34) {
+            for (int idx = threadIdx.x; idx < cpb * PS; idx += blockDim.x) {
+                const int s3 = idx / PS, k = idx - s3 * PS - 1;   // k = -1: slot 0 = mat4(1) (src/skeleton.cpp:238)
+                if (c0 + s3 >= n || !s_live[s3]) continue;
+                float* pal = p.palette ? p.palette + (size_t)(c0 + s3) * PS * 16 : nullptr;
+                float* p34 = p.palette34 ? p.palette34 + (size_t)(c0 + s3) * PS * 16 : nullptr;
+                if (k < 0) {
+                    if (pal) { st_v8(pal, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(pal + 8, 0, 0, 1, 0, 0, 0, 0, 1); }
+                    if (p34) { st_v8(p34, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(p34 + 8, 0, 0, 1, 0, 0, 0, 0, 0); }
+                } else {
+                    palette_slot(s_remap[k], s_char0 + (size_t)s3 * per_char + (size_t)P * kMS, s_inv_bind + (size_t)k * kMS, pal, p34, k);
+                }
+            }
+        }
+        __syncthreads();  // the matrix arrays are reused by the next group
+    }
+}
+
 }  // namespace
+
+static size_t fused_smem_bytes_for(const PoseParams& p, int cpb) {
+    const int P = p.skel.padded_joints, K = p.arm.num_joints;
+    size_t b = 0;
+    b += (size_t)K * kMS * 4 + 16 * 4;
+    b += (size_t)((K + 3) & ~3) * 4;
+    b += (size_t)((P + 7) & ~7) * 2;
+    b += (size_t)p.skel.rounds * 32 * 2;
+    b += 16;
+    b += (size_t)((2 * P * kMS + 3) & ~3) * 4 * cpb;
+    b += (size_t)((cpb + 15) & ~15);
+    return b;
+}
 
 static size_t pose_smem_bytes_for(const PoseParams& p, int warps) {
     const int P = p.skel.padded_joints, K = p.arm.num_joints;
@@ -551,6 +675,35 @@ cudaError_t launch_pose(const PoseParams& p, int num_sms, cudaStream_t stream, i
         const int64_t total = p.n * p.num_layers;
         DMK_LAUNCH(advance_kernel, (unsigned)((total + 255) / 256), 256, 0, stream)(p);
         if (launches) ++*launches;
+    }
+    // fused sampling + local-to-model + palette where a group of characters fits a block (skeletons up to 288 padded joints)
+    if (p.fused && p.skel.padded_joints <= kFusedMaxThreads) {
+        const int P = p.skel.padded_joints;
+        int cpb = kFusedMaxThreads / P;
+        if (cpb > 8) cpb = 8;
+        const int threads = (cpb * P + 31) / 32 * 32;
+        const size_t smem = fused_smem_bytes_for(p, cpb);
+        const int shape = (p.clips.bucket_dir ? kBuckets : 0) | (p.key_indices ? kKeys : 0);
+        auto go = [&](auto kernel) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+            if (e != cudaSuccess) return e;
+            if (per_sm < 1) return cudaErrorInvalidConfiguration;
+            int64_t blocks = (p.n + cpb - 1) / cpb;
+            const int64_t cap = (int64_t)num_sms * per_sm;
+            if (blocks > cap) blocks = cap;
+            DMK_LAUNCH(kernel, (unsigned)blocks, threads, smem, stream)(p, cpb);
+            if (launches) ++*launches;
+            return cudaGetLastError();
+        };
+        switch (shape) {
+        case 0: return go(pose_fused_kernel<0>);
+        case kBuckets: return go(pose_fused_kernel<kBuckets>);
+        case kKeys: return go(pose_fused_kernel<kKeys>);
+        default: return go(pose_fused_kernel<kBuckets | kKeys>);
+        }
     }
     {
         const int64_t total = p.n * p.skel.padded_joints;

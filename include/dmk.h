@@ -172,7 +172,18 @@ enum {
     /* Diagnostic: 1 = skin with the round-1 kernel shape (every warp replicates the palette and skins) instead of the
      * producer-warp / compute-warps shape, for A/B timing of the two on the same crowd.  Layouts 1 and 2 only exist in the
      * round-1 shape.  Results are identical either way. */
-    DMK_OPT_SKIN_ROUND1_KERNEL = 5
+    DMK_OPT_SKIN_ROUND1_KERNEL = 5,
+    /* 1 = sampling, local-to-model and palette in ONE kernel (a block owns 4 characters; the local matrices stay in shared
+     * memory).  Measured on B200 (profiles/r02_pose_fused_kernel.txt, r02_pose_path_ab.txt): DRAM traffic of the pose path
+     * drops from 3.8x to 0.92x its algorithmic bytes, but the path is latency bound, not bandwidth bound, and the block-wide
+     * barriers between the phases cost more than the round trip saved: 742 us against 613 us per 100k characters.  Hence
+     * opt-in; the default is two kernels.  Crowds with several armatures (dmk_crowd_add_skin) always take the two-kernel
+     * path.  Results are bit-identical. */
+    DMK_OPT_POSE_FUSED = 6,
+    /* 1 = do not write the [N][K+1][16] column-major mat4 palette every step: only the 3x4 row-major palette the skinning
+     * kernel reads is kept (half of the pose path's writes).  dmk_crowd_palette_dev then returns NULL; dmk_crowd_get_palette,
+     * dmk_crowd_pack_visible_palettes and the exchange still deliver mat4 palettes (expanded from the 3x4 one on the way). */
+    DMK_OPT_PALETTE_3X4_ONLY = 7
 };
 DMK_API dmk_status dmk_crowd_set_option(dmk_crowd_t crowd, int option, int value);
 /* Launch shape the skinning kernel would use for a mesh of `vertex_pitch` vertices (multiple of 8), a palette of

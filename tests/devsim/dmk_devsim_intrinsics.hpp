@@ -235,6 +235,12 @@ inline void lds128_keep(float4& v, uint32_t addr, uint32_t take) {
 inline void warp_copy_palette(const float4* src, float4* dst, int palette_vec4, int lane) {
     for (int k = lane; k < palette_vec4; k += 32) dst[k] = src[k];
 }
+inline void warp_copy_palette34_as_mat4(const float* src34, float4* dst, int palette_vec4, int lane) {
+    for (int k = lane; k < palette_vec4; k += 32) {
+        const float* s = src34 + (size_t)(k >> 2) * 16 + (k & 3);
+        dst[k] = make_float4(s[0], s[4], s[8], (k & 3) == 3 ? 1.f : 0.f);
+    }
+}
 inline float4 lds128_or(uint32_t addr, uint32_t take, const float4& fallback) { return take ? lds128(addr) : fallback; }
 
 inline uint32_t ld_acquire_sys(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }

@@ -416,3 +416,37 @@ def test_third_outstanding_readback_is_refused_before_anything_is_enqueued(rigs)
     crowd.step(0.0, flags)          # a slot is free again
     crowd.collect_visibility(bits)
     crowd.collect_visibility(bits)
+
+
+def test_fused_and_two_kernel_pose_paths_are_bit_identical(rigs):
+    # DMK_OPT_POSE_FUSED: one kernel, the local matrices stay in shared memory; DMK_OPT_PALETTE_3X4_ONLY: only the 3x4
+    # palette is written, the mat4 consumers (getter, pack) expand it.  All of them must give the same bits.
+    g, o, a = rigs
+    n = 333
+    cr = synth.make_crowd(n, 2, len(a.clips), seed=41)
+    inst = synth.make_instances(n, seed=4, extent=60.0)
+    results = {}
+    for name, fused, only34 in (("fused", 1, 0), ("two kernels", 0, 0), ("fused, 3x4 only", 1, 1), ("two kernels, 3x4 only", 0, 1)):
+        crowd = g.crowd(n, 2, mesh=True)
+        crowd.enable_outputs(g.capi.OUT_MODELS | g.capi.OUT_LOCALS | g.capi.OUT_KEY_INDICES)
+        crowd.set_option(g.capi.OPT_POSE_FUSED, fused)
+        crowd.set_option(g.capi.OPT_PALETTE_3X4_ONLY, only34)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
+        crowd.set_instances(inst.world_inverse, inst.bbox)
+        crowd.set_camera(synth.sample_camera_view_proj(), 0.0)
+        for _ in range(3):
+            crowd.step(1.0 / 60.0, g.capi.STEP_ADVANCE | g.capi.STEP_POSE | g.capi.STEP_CULL | g.capi.STEP_SKIN)
+        assert (crowd.palette_dev() is None or crowd.palette_dev() == 0) == bool(only34)
+        bits, count = crowd.get_visibility()
+        from tests import devmem
+        buf = devmem.DeviceArray.zeros((count, g.arm.palette_size, 16))
+        crowd.pack_visible_palettes(buf.ptr, count)
+        g.ctx.sync()
+        packed = buf.numpy()
+        results[name] = (crowd.get_palette(), crowd.get_models(), crowd.get_locals(), crowd.get_key_indices(), crowd.get_skinned(), packed)
+        visible = np.flatnonzero(np.unpackbits(bits.view(np.uint8), bitorder="little")[:n])
+        assert np.array_equal(packed, results[name][0][visible]), name + ": packed visible palettes"
+    ref = results["fused"]
+    for name, got in results.items():
+        for what, x, y in zip(("palette", "models", "locals", "key indices", "skinned", "packed"), got, ref):
+            assert np.array_equal(x, y), f"{name}: {what} differs from the fused path"

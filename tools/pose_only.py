@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 from darmok_b200 import capi, synth
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 50   # [fused] one-kernel path, [pal44] also write the mat4 palette
 n = 100_000
 skel_s = synth.make_skeleton(67)
 clips_s = [synth.make_clip(skel_s, f"clip{i}", seed=i, duration=1.5) for i in range(8)]
@@ -20,6 +20,8 @@ with torch.cuda.stream(stream):
     clips = capi.ClipSet(ctx, skel, clip_objs)
     arm = capi.Armature(ctx, skel, arm_s.names, arm_s.inv_bind)
     crowd = capi.Crowd(ctx, skel, clips, arm, None, n, 2)
+    crowd.set_option(capi.OPT_POSE_FUSED, int("fused" in sys.argv))
+    crowd.set_option(capi.OPT_PALETTE_3X4_ONLY, int("pal44" not in sys.argv))
     cr = synth.make_crowd(n, 2, 8, seed=42)
     crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=float(np.finfo(np.float32).tiny))
     flags = capi.STEP_ADVANCE | capi.STEP_POSE
