@@ -26,6 +26,7 @@ OPT_SKIN_PLANAR_OUTPUT = 4
 OPT_SKIN_ROUND1_KERNEL = 5
 OPT_POSE_FUSED = 6
 OPT_PALETTE_3X4_ONLY = 7
+OPT_SKIN_REPLICATE_IN_SMEM = 8
 GROUP_BLEND, GROUP_PASSTHROUGH, GROUP_ZERO = 0, 1, 2
 TOP_GROUP0, TOP_TRANSITION, TOP_REST_POSE, TOP_SKIP = 0, 1, 2, 3
 PROGRAM_DTYPE = np.dtype([("n0", "u1"), ("n1", "u1"), ("rest0", "u1"), ("rest1", "u1"), ("mode0", "u1"), ("mode1", "u1"),

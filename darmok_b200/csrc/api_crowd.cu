@@ -120,6 +120,10 @@ dmk_status dmk_crowd_set_option(dmk_crowd_t c, int option, int value) {
             if (x.mesh) x.plan = plan_skin(x.mesh->vpad, x.mesh->palette_size, c->ctx->num_sms - c->reserved_sms, c->skin_variant, c->skin_legacy);
         return DMK_OK;
     }
+    if (option == DMK_OPT_SKIN_REPLICATE_IN_SMEM) {
+        c->skin_s2s = value != 0;
+        return DMK_OK;
+    }
     if (option == DMK_OPT_POSE_FUSED) {
         c->pose_fused = value != 0;
         return DMK_OK;
@@ -755,7 +759,9 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
             p.vertex_order_mode = c->mesh->clustered ? 2 : c->mesh->sorted ? 1 : 0;
             {
                 KernelTimer timer(ctx, DMK_KERNEL_SKIN);
-                DMK_CUDA(ctx, launch_skin(p, c->plan, s));
+                SkinPlan plan = c->plan;
+                plan.replicate_in_smem = c->skin_s2s;
+                DMK_CUDA(ctx, launch_skin(p, plan, s));
             }
             ++ctx->launches;
         }
@@ -776,7 +782,9 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
             q.vertex_order_mode = x.mesh->clustered ? 2 : x.mesh->sorted ? 1 : 0;
             {
                 KernelTimer timer(ctx, DMK_KERNEL_SKIN);
-                DMK_CUDA(ctx, launch_skin(q, x.plan, s));
+                SkinPlan plan = x.plan;
+                plan.replicate_in_smem = c->skin_s2s;
+                DMK_CUDA(ctx, launch_skin(q, plan, s));
             }
             ++ctx->launches;
         }

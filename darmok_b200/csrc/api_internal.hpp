@@ -165,6 +165,7 @@ struct dmk_crowd_s {
     int skin_variant = 0;   // DMK_OPT_SKIN_PLANAR_OUTPUT
     bool skin_legacy = false;   // DMK_OPT_SKIN_ROUND1_KERNEL
     bool pose_fused = false;   // DMK_OPT_POSE_FUSED
+    bool skin_s2s = false;     // DMK_OPT_SKIN_REPLICATE_IN_SMEM
     bool palette_3x4_only = false;   // DMK_OPT_PALETTE_3X4_ONLY: d_palette is not written; consumers expand d_palette34
     // device-side animators (dmk_crowd_set_animator)
     AnimStateDef* d_anim_states = nullptr;

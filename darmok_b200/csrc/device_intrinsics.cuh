@@ -16,6 +16,38 @@
 
 // kernel<<<grid, block, dynamic shared bytes, stream>>>(arguments...)  ==  DMK_LAUNCH(kernel, grid, block, bytes, stream)(arguments...)
 #define DMK_LAUNCH(kernel, grid, block, smem_bytes, stream) kernel<<<(grid), (block), (smem_bytes), (stream)>>>
+// the same as a thread-block cluster of ONE block: what cp.async.bulk shared::cta -> shared::cluster needs even when source and
+// destination are the same block's shared memory (a plain launch traps with "illegal instruction": tools/ubench_s2s.cu)
+namespace dmk {
+template <class... P>
+struct ClusterOfOneLaunch {
+    void (*kernel)(P...);
+    unsigned grid, block;
+    size_t smem;
+    cudaStream_t stream;
+    template <class... A>
+    void operator()(A&&... args) const {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(block);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kernel, P(args)...);
+    }
+};
+template <class... P>
+ClusterOfOneLaunch<P...> cluster_of_one(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream) {
+    return {kernel, grid, block, smem, stream};
+}
+}  // namespace dmk
+#define DMK_LAUNCH_CLUSTER_OF_ONE(kernel, grid, block, smem_bytes, stream) ::dmk::cluster_of_one(kernel, (grid), (block), (smem_bytes), (stream))
 // the block's dynamic shared memory as `unsigned char name[]`
 #define DMK_DYNAMIC_SMEM(name, alignment) extern __shared__ __align__(alignment) unsigned char name[]
 
@@ -67,6 +99,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// bulk copy shared -> shared inside the CTA (a CTA is a cluster of one: its shared::cta addresses are valid shared::cluster ones)
+__device__ __forceinline__ void bulk_s2s(void* dst_smem, const void* src_smem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "r"(smem_u32(src_smem)), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
 

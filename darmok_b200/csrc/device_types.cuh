@@ -106,6 +106,7 @@ struct SkinParams {
     int palette_size;         // PS
     int num_tiles;            // vertex tiles per character
     int tile_vertices;        // multiple of 8
+    int replicate_in_smem;    // replicas 1.. are copied from replica 0 inside shared memory instead of from global memory (set from the plan)
     int num_stages;           // staging depth of the producer warp's bulk copies (set by launch_skin from the plan)
     int vertex_order_mode;    // 0 caller's order; 1 grouped by influence count: the gathers of absent influences are predicated off;
                               // 2 clustered by bone (DMK_MESH_CLUSTER_BONES): also the block's bone once per thread and character

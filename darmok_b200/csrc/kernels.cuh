@@ -32,6 +32,7 @@ struct SkinPlan {
     int grid;           // persistent blocks
     int replicas;       // palette replicas in shared memory (bank-conflict-free gathers)
     size_t smem;
+    bool replicate_in_smem;   // one copy from global memory per character + REPL - 1 shared-memory copies (else REPL copies from global memory)
     int stages;         // bulk-copy staging depth
     bool legacy;        // the round-1 kernel shape (every warp replicates and skins) instead of producer warp + compute warps
     int variant;        // 0: interleaved [V][9] output, 8 vertices per thread; 1 / 2: planar [9][V] output, 4 per thread, <= 320 / 448 threads;

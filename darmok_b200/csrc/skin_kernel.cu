@@ -24,6 +24,8 @@
 #include "device_types.cuh"
 #include "kernels.cuh"
 
+#include <type_traits>
+
 namespace dmk {
 
 namespace {
@@ -300,6 +302,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
     unsigned char* s_repl = smem;                                        // [ring][REPL] palettes, RS apart
     uint64_t* s_full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)ring * buf_bytes);   // [kMaxRing] bulk copies -> compute warps
     uint64_t* s_empty_bar = s_full_bar + kMaxRing;                       // [kMaxRing] compute warps -> producer
+    uint64_t* s_stage_bar = s_empty_bar + kMaxRing;                      // [kMaxRing] shared-memory replication: replica 0 has arrived
+    const bool s2s = p.replicate_in_smem != 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncompute = (blockDim.x >> 5) - 1;                          // the last warp is the producer
@@ -317,6 +321,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
         for (int k = 0; k < ring; ++k) {
             mbar_init(&s_full_bar[k], 1);
             mbar_init(&s_empty_bar[k], ncompute);
+            mbar_init(&s_stage_bar[k], 1);
         }
         mbar_init_fence();
     }
@@ -329,21 +334,44 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
     const int passes = (p.num_tiles - tslot + tiles_per_pass - 1) / tiles_per_pass;   // tiles this block walks (1 unless the mesh has more tiles than the grid)
 
     if (warp == ncompute) {
-        // ---------------- producer: one thread.  Per (tile pass, character): wait until the ring buffer is free, then REPL bulk
-        // copies of the palette into it; their bytes complete the buffer's "full" barrier, nothing else is needed ----------------
+        // ---------------- producer: one thread.  Per (tile pass, character): wait until the ring buffer is free, then fill its REPL
+        // replicas with bulk copies; their bytes complete the buffer's "full" barrier, nothing else is needed.  Two ways:
+        //   * REPL copies from global memory (L2): simplest, but 8 x 4352 B per character and block is 10 GB of L2 reads per
+        //     100k x 5k launch next to 18 GB of writes (profiles/r02_skin_ws_clustered_v4.txt: lts throughput 74 %);
+        //   * (replicate_in_smem) ONE copy from global memory into replica 0, then REPL - 1 shared-memory -> shared-memory bulk
+        //     copies (cp.async.bulk.shared::cluster.shared::cta) one item behind, so the wait for replica 0 is never exposed.
+        //     MEASURED: slower (4.16 ms against 3.52 ms; the copies run at 15 B/cycle/SM, tools/ubench_s2s.cu, and take
+        //     shared-memory bandwidth from the gathers), so the first way is the default and this one a diagnostic option.
         if (lane != 0) return;
-        uint32_t rb = 0, rphase = 0;
+        const int64_t total = (int64_t)passes * my_count;
+        uint32_t rb = 0, rphase = 0, sb = 0, sphase = 0;
         bool wrapped = false;
-        for (int pass = 0; pass < passes; ++pass)
-            for (int64_t i = 0; i < my_count; ++i) {
+        int64_t i = 0;   // character of item q within this block's share
+        for (int64_t q = 0; q <= total; ++q) {
+            if (q < total) {
                 if (wrapped) mbar_wait(&s_empty_bar[rb], rphase ^ 1u);   // every compute warp is done with the item `ring` items back
                 const float* src = p.palette34 + (size_t)char_of(i) * PS * 16;
                 unsigned char* dst = s_repl + (size_t)rb * buf_bytes;
-                mbar_expect_tx(&s_full_bar[rb], pal_bytes * REPL);
+                if (s2s) {
+                    mbar_expect_tx(&s_stage_bar[rb], pal_bytes);
+                    bulk_g2s(dst, src, pal_bytes, &s_stage_bar[rb]);
+                } else {
+                    mbar_expect_tx(&s_full_bar[rb], pal_bytes * REPL);
 #pragma unroll
-                for (int r = 0; r < REPL; ++r) bulk_g2s(dst + (size_t)r * RS, src, pal_bytes, &s_full_bar[rb]);
+                    for (int r = 0; r < REPL; ++r) bulk_g2s(dst + (size_t)r * RS, src, pal_bytes, &s_full_bar[rb]);
+                }
+                if (++i == my_count) i = 0;
                 if (++rb == (uint32_t)ring) { rb = 0; rphase ^= 1u; wrapped = true; }
             }
+            if (s2s && q >= 1) {   // the item issued one iteration ago: its replica 0 has had a whole item's time to arrive
+                mbar_wait(&s_stage_bar[sb], sphase);
+                unsigned char* buf = s_repl + (size_t)sb * buf_bytes;
+                mbar_expect_tx(&s_full_bar[sb], pal_bytes * (REPL - 1));
+#pragma unroll
+                for (int r = 1; r < REPL; ++r) bulk_s2s(buf + (size_t)r * RS, buf, pal_bytes, &s_full_bar[sb]);
+                if (++sb == (uint32_t)ring) { sb = 0; sphase ^= 1u; }
+            }
+        }
         return;
     }
 
@@ -390,8 +418,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
 
         for (int64_t i = 0; i < my_count; ++i) {
             const int64_t cid = char_of(i);
+            if (s2s) mbar_wait(&s_stage_bar[rb], rphase);   // replica 0 (the async copy that the other replicas were made from)
             mbar_wait(&s_full_bar[rb], rphase);
-            if (active) {
+            // One character for this thread's 8 vertices.  RARE: some lane of the warp still gathers entry 0 of some vertex (a mixed
+            // block of a clustered mesh).  The common instantiation has no branch in it: one basic block of ~1000 instructions, so the
+            // scheduler can put the gathers of vertex v + 1 under the arithmetic of vertex v.
+            auto item = [&](auto rare_tag) {
+                constexpr bool RARE = decltype(rare_tag)::value;
                 const uint32_t base = repl_base + rb * buf_bytes;
                 float4 b0, b1, b2;   // the block's bone, once per character
                 if (SHARE) {
@@ -446,7 +479,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
                         // mixed blocks: a warp-uniform branch, so the common path carries neither the gather nor a select
                         addr(slots[v]);
                         float4 e0 = b0, e1 = b1, e2 = b2;
-                        if (rare >> v & 1u) {
+                        if (RARE && (rare >> v & 1u)) {
                             const uint32_t take = used >> (4 * v) & 1u;
                             e0 = lds128_or(a0, take, b0);
                             e1 = lds128_or(a0 + 16u, take, b1);
@@ -513,6 +546,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
                         st_v8(plane + (size_t)c * p.vpad, v8);
                     }
                 }
+                        };
+            if (active) {
+                if (SHARE && rare != 0u) item(std::true_type{});
+                else item(std::false_type{});
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty_bar[rb]);
@@ -530,7 +567,7 @@ constexpr int kComputeThreads = kMaxThreads - 32;   // warp-specialised shape: t
 bool is_legacy(int variant, bool legacy) { return legacy || variant == 1 || variant == 2; }
 size_t skin_smem_bytes(int palette_size, int repl, bool legacy, int ring = kMaxRing) {
     if (legacy) return (size_t)palette_size * (48 * kNumRepl * repl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
-    return (size_t)replica_stride(palette_size) * repl * ring + 8 * 2 * kMaxRing + 16;
+    return (size_t)replica_stride(palette_size) * repl * ring + 8 * 3 * kMaxRing + 16;
 }
 template <typename F>
 auto with_legacy_kernel(int repl, bool skip, int variant, F&& f) {
@@ -609,10 +646,12 @@ cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t 
     if (p.n <= 0 || p.vpad <= 0) return cudaSuccess;
     SkinParams q = p;
     q.num_stages = plan.stages;
+    q.replicate_in_smem = plan.replicate_in_smem ? 1 : 0;
     return with_kernel(plan.replicas, p.vertex_order_mode, plan.variant, plan.legacy, [&, p = q](auto kernel) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (e != cudaSuccess) return e;
-        DMK_LAUNCH(kernel, plan.grid, plan.threads, plan.smem, stream)(p);
+        if (p.replicate_in_smem) DMK_LAUNCH_CLUSTER_OF_ONE(kernel, plan.grid, plan.threads, plan.smem, stream)(p);
+        else DMK_LAUNCH(kernel, plan.grid, plan.threads, plan.smem, stream)(p);
         return cudaGetLastError();
     });
 }

@@ -183,7 +183,13 @@ enum {
     /* 1 = do not write the [N][K+1][16] column-major mat4 palette every step: only the 3x4 row-major palette the skinning
      * kernel reads is kept (half of the pose path's writes).  dmk_crowd_palette_dev then returns NULL; dmk_crowd_get_palette,
      * dmk_crowd_pack_visible_palettes and the exchange still deliver mat4 palettes (expanded from the 3x4 one on the way). */
-    DMK_OPT_PALETTE_3X4_ONLY = 7
+    DMK_OPT_PALETTE_3X4_ONLY = 7,
+    /* Skinning kernel, how the 8 palette replicas of a character reach shared memory: 0 (default) = eight bulk copies from
+     * global memory (L2); 1 = one bulk copy from global memory + seven shared-memory -> shared-memory bulk copies (an eighth
+     * of the L2 reads; the kernel is then launched as a thread-block cluster of one, which that copy needs).  Measured on
+     * B200 (profiles/r02_skin_variants_call8.jsonl): the shared-memory copies move 15 B/cycle/SM and compete with the
+     * gathers -- 4.16 ms against 3.52 ms -- so this stays a diagnostic.  Results are identical. */
+    DMK_OPT_SKIN_REPLICATE_IN_SMEM = 8
 };
 DMK_API dmk_status dmk_crowd_set_option(dmk_crowd_t crowd, int option, int value);
 /* Launch shape the skinning kernel would use for a mesh of `vertex_pitch` vertices (multiple of 8), a palette of

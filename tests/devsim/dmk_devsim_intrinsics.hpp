@@ -101,6 +101,7 @@ inline void mbar_check_complete(MBar* b) {
 #define gridDim (::devsim::g_grid_dim)
 
 #define DMK_LAUNCH(kernel, grid, block, smem_bytes, stream) ::devsim::launcher(kernel, (grid), (block), (smem_bytes))
+#define DMK_LAUNCH_CLUSTER_OF_ONE(kernel, grid, block, smem_bytes, stream) ::devsim::launcher(kernel, (grid), (block), (smem_bytes))
 #define DMK_DYNAMIC_SMEM(name, alignment) unsigned char* const name = ::devsim::dynamic_smem()
 
 // cuda_runtime.h only has the kernel-pointer overload of this one under nvcc
@@ -200,6 +201,13 @@ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint6
     if (bytes % 16 || reinterpret_cast<uintptr_t>(src_gmem) % 16 || reinterpret_cast<uintptr_t>(dst_smem) % 16)
         ::devsim::trap("cp.async.bulk: size and both addresses must be multiples of 16");
     ::devsim::bulk_copy(::devsim::smem_pointer(::devsim::smem_offset(dst_smem), bytes), src_gmem, bytes, reinterpret_cast<::devsim::MBar*>(bar));
+}
+
+inline void bulk_s2s(void* dst_smem, const void* src_smem, uint32_t bytes, uint64_t* bar) {
+    if (bytes % 16 || reinterpret_cast<uintptr_t>(src_smem) % 16 || reinterpret_cast<uintptr_t>(dst_smem) % 16)
+        ::devsim::trap("cp.async.bulk (shared -> shared): size and both addresses must be multiples of 16");
+    ::devsim::bulk_copy(::devsim::smem_pointer(::devsim::smem_offset(dst_smem), bytes), ::devsim::smem_pointer(::devsim::smem_offset(src_smem), bytes),
+                        bytes, reinterpret_cast<::devsim::MBar*>(bar));
 }
 
 inline void check_aligned(const void* p, size_t a, const char* what) {

@@ -54,8 +54,10 @@ def main():
             visible = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
             assert 148 < count < n, "the visible set must keep every block busy for several characters"
             # (layout, round-1 kernel shape): layouts 0 / 3 / 4 exist as producer-warp + compute-warps kernel and in the round-1 shape
-            for variant, round1 in ((0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (0, 1), (3, 1), (4, 1)):
-                crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, round1)
+            # round1 = 2: the producer-warp kernel with its replicas copied inside shared memory (DMK_OPT_SKIN_REPLICATE_IN_SMEM)
+            for variant, round1 in ((0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (0, 1), (3, 1), (4, 1), (0, 2), (3, 2)):
+                crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, int(round1 == 1))
+                crowd.set_option(capi.OPT_SKIN_REPLICATE_IN_SMEM, int(round1 == 2))
                 crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
                 devmem.fill_f32(crowd.skinned_dev(), n * vpad * 9, float("nan"))
                 crowd.step(0.0, capi.STEP_SKIN)

@@ -150,6 +150,7 @@ def config3_sorted():
     cases = [("ws_caller_order", 0, 0, 0), ("ws_caller_order_streams", 0, 3, 0), ("ws_caller_order_planes", 0, 4, 0),
              ("ws_sorted_by_influences", S, 0, 0),
              ("ws_clustered", CL, 0, 0), ("ws_clustered_streams", CL, 3, 0), ("ws_clustered_planes", CL, 4, 0),
+             ("ws_clustered_s2s", CL, 0, 2), ("ws_caller_order_s2s", 0, 0, 2), ("ws_clustered_streams_s2s", CL, 3, 2),
              ("round1_caller_order", 0, 0, 1), ("round1_sorted_by_influences", S, 0, 1), ("round1_clustered", CL, 0, 1),
              ("round1_three_float3_streams", 0, 3, 1), ("round1_planes_8_per_thread", 0, 4, 1),
              ("round1_planes_10_warps", 0, 1, 1), ("round1_planes_14_warps", 0, 2, 1),
@@ -169,7 +170,8 @@ def config3_sorted():
             crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
             cr = synth.make_crowd(n, 2, 8, seed=42)
             crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
-            crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, round1)
+            crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, int(round1 == 1))
+            crowd.set_option(capi.OPT_SKIN_REPLICATE_IN_SMEM, int(round1 == 2))   # (third field: 1 round-1 kernel, 2 replication inside shared memory)
             if variant:
                 crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
             crowd.step(1 / 60, capi.STEP_POSE)

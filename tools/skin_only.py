@@ -20,6 +20,7 @@ crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
 cr = synth.make_crowd(n, 2, 8, seed=42)
 crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=float(np.finfo(np.float32).tiny))
 crowd.set_option(capi.OPT_SKIN_ROUND1_KERNEL, int("round1" in sys.argv))
+crowd.set_option(capi.OPT_SKIN_REPLICATE_IN_SMEM, int("s2s" in sys.argv))
 for variant in (1, 2, 3, 4):
     if f"planar{variant}" in sys.argv:
         crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
