@@ -13,7 +13,7 @@ uint2 pack_key(const Float3Key& k) {
 uint2 pack_key(const QuaternionKey& k) {
     return make_uint2(static_cast<uint32_t>(static_cast<uint16_t>(k.value[0])) | (static_cast<uint32_t>(static_cast<uint16_t>(k.value[1])) << 16),
                       static_cast<uint32_t>(static_cast<uint16_t>(k.value[2])) | (static_cast<uint32_t>(k.largest) << 16) |
-                          (static_cast<uint32_t>(k.sign) << 18));
+                          (static_cast<uint32_t>(k.sign) << 18) | (static_cast<uint32_t>(k.format) << 19));
 }
 // keys of the ozz stream regrouped per track (stream order within a track = time order)
 template <typename Key>

@@ -116,10 +116,18 @@ __device__ __forceinline__ void sample_f3(const ClipSetDev& cs, int comp, int cl
 
 // DecompressQuaternion (Appendix A.4) for one key
 __device__ __forceinline__ void decode_quat(uint2 v, float q[4]) {
-    const float kInt2Float = 1.f / (32767.f * 1.4142135623730950488016887242097f);
-    const float f0 = kInt2Float * (float)(short)(v.x & 0xffffu);
-    const float f1 = kInt2Float * (float)(short)(v.x >> 16);
-    const float f2 = kInt2Float * (float)(short)(v.y & 0xffffu);
+    float f0, f1, f2;
+    if ((v.y >> 19) & 1u) {   // archive v7 (ozz >= 0.15): 15-bit magnitudes mapped from [-1/sqrt 2, 1/sqrt 2] (clip-uniform branch)
+        const float kScale = 1.4142135623730950488016887242097f / 32767.f, kOffset = -0.70710678118654752440084436210485f;
+        f0 = (float)(v.x & 0xffffu) * kScale + kOffset;
+        f1 = (float)(v.x >> 16) * kScale + kOffset;
+        f2 = (float)(v.y & 0xffffu) * kScale + kOffset;
+    } else {                  // archive v6: signed 16 bit
+        const float kInt2Float = 1.f / (32767.f * 1.4142135623730950488016887242097f);
+        f0 = kInt2Float * (float)(short)(v.x & 0xffffu);
+        f1 = kInt2Float * (float)(short)(v.x >> 16);
+        f2 = kInt2Float * (float)(short)(v.y & 0xffffu);
+    }
     const unsigned largest = (v.y >> 16) & 3u;
     // the rebuilt lane is zero in ozz's dot product, so the sum is ((f0^2 + f1^2) + f2^2) for every mapping
     const float dot = (f0 * f0 + f1 * f1) + f2 * f2;

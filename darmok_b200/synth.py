@@ -149,9 +149,78 @@ def _sorted_stream(ratios_per_track):
     return tr[order], ki[order]
 
 
-def write_animation_archive(name, duration, num_tracks, t_tracks, r_tracks, s_tracks) -> bytes:
+def compress_quat_v7(q):
+    """ozz >= 0.15 QuaternionKey: largest component dropped, the others mapped from [-1/sqrt 2, 1/sqrt 2] to 15 bits."""
+    q = np.asarray(q, np.float64)
+    largest = np.argmax(np.abs(q), axis=-1)
+    sign = (np.take_along_axis(q, largest[..., None], -1)[..., 0] < 0).astype(np.uint8)
+    mapping = np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])
+    others = np.take_along_axis(q, mapping[largest], -1)
+    quant = np.floor((others + 1.0 / SQRT2) * (32767.0 / SQRT2) + 0.5)
+    quant = np.clip(quant, 0, 32767).astype(np.int64)
+    return largest.astype(np.uint8), sign, quant
+
+
+def write_animation_archive_v7(name, duration, num_tracks, t_tracks, r_tracks, s_tracks) -> bytes:
+    """The same clip as an ozz-animation >= 0.15 archive (Animation version 7): shared timepoints, per component ratio indices
+    (u8 / u16), previouses (distance back to the previous key of the same track), no iframes, 3 x u16 values per key.
+    Layout from memory of upstream (SURVEY.md Appendix A.3'; darmok_b200/csrc/ozz_io.hpp): unvalidated against ozz itself."""
+    timepoints = np.unique(np.concatenate([np.asarray(t[0], np.float32) for tracks in (t_tracks, r_tracks, s_tracks) for t in tracks]))
+    wide = len(timepoints) > 256
+
+    def ctrl(tracks, values_of):
+        tr, ki = _sorted_stream([t[0] for t in tracks])
+        ratios = bytearray()
+        previouses = bytearray()
+        values = bytearray()
+        last = {}
+        for i, (a, b) in enumerate(zip(tr, ki)):
+            index = int(np.searchsorted(timepoints, np.float32(tracks[a][0][b])))
+            assert timepoints[index] == np.float32(tracks[a][0][b])
+            ratios += struct.pack("<H" if wide else "<B", index)
+            back = i - last[a] if a in last else 0
+            assert 0 <= back <= 0xffff, "a track's keys are further apart in the stream than a u16 offset reaches"
+            previouses += struct.pack("<H", back)
+            last[a] = i
+            values += values_of(a, b)
+        return len(tr), bytes(ratios) + bytes(previouses) + struct.pack("<f", 0.0) + bytes(values)   # no iframes, interval 0
+
+    def f3_values(tracks):
+        halves = [np.asarray(t[1], np.float32).astype(np.float16).view(np.uint16) for t in tracks]
+        return lambda a, b: struct.pack("<3H", int(halves[a][b][0]), int(halves[a][b][1]), int(halves[a][b][2]))
+
+    def q_values(tracks):
+        comp = [compress_quat_v7(t[1]) for t in tracks]
+
+        def one(a, b):
+            lg, sg, v = comp[a]
+            packed = int(lg[b]) | (int(sg[b]) << 2) | (int(v[b][0]) << 3) | (int(v[b][1]) << 18) | (int(v[b][2]) << 33)
+            return struct.pack("<3H", packed & 0xffff, (packed >> 16) & 0xffff, (packed >> 32) & 0xffff)
+        return one
+
+    nt, bt = ctrl(t_tracks, f3_values(t_tracks))
+    nr, br = ctrl(r_tracks, q_values(r_tracks))
+    ns, bs = ctrl(s_tracks, f3_values(s_tracks))
+    nm = name.encode()
+    buf = bytearray()
+    buf += struct.pack("<B", 1)
+    buf += b"ozz-animation\0"
+    buf += struct.pack("<I", 7)
+    buf += struct.pack("<fIII", float(duration), int(num_tracks), len(nm), len(timepoints))
+    buf += struct.pack("<III", nt, nr, ns)
+    buf += struct.pack("<IIIIII", 0, 0, 0, 0, 0, 0)   # iframe entries / descriptors of the three components: none
+    buf += nm
+    buf += timepoints.astype("<f4").tobytes()
+    buf += bt + br + bs
+    return bytes(buf)
+
+
+def write_animation_archive(name, duration, num_tracks, t_tracks, r_tracks, s_tracks, version=6) -> bytes:
     """*_tracks: list (len = padded track count) of (ratios f32[n], values) with values f32[n,3] (T,S) or
-    f32[n,4] (R).  Values are quantised here (half / smallest-three 16 bit)."""
+    f32[n,4] (R).  Values are quantised here (half / smallest-three 16 bit).  version: ozz Animation archive version (6 or 7)."""
+    if version == 7:
+        return write_animation_archive_v7(name, duration, num_tracks, t_tracks, r_tracks, s_tracks)
+    assert version == 6
     def pack_f3(tracks):
         tr, ki = _sorted_stream([t[0] for t in tracks])
         out = bytearray()
@@ -192,8 +261,9 @@ class SynthClip:
     archive: bytes
 
 
-def make_clip(skel: SynthSkeleton, name="clip", seed=0, duration=1.5, hz=30.0, drop=0.25) -> SynthClip:
-    """Looping clip: uniform `hz` keys with `drop` of the interior keys removed per track and component."""
+def make_clip(skel: SynthSkeleton, name="clip", seed=0, duration=1.5, hz=30.0, drop=0.25, version=6) -> SynthClip:
+    """Looping clip: uniform `hz` keys with `drop` of the interior keys removed per track and component.
+    version: ozz Animation archive version the clip is written as (6 = ozz 0.14, 7 = ozz >= 0.15); same keys either way."""
     rng = np.random.default_rng(seed + 1000003)
     j = skel.num_joints
     padded = (j + 3) // 4 * 4
@@ -233,7 +303,7 @@ def make_clip(skel: SynthSkeleton, name="clip", seed=0, duration=1.5, hz=30.0, d
         r_tracks.append((base_f32[mr], rk))
         s_tracks.append((base_f32[ms], sv[ms]))
     return SynthClip(name, float(np.float32(duration)),
-                     write_animation_archive(name, duration, j, t_tracks, r_tracks, s_tracks))
+                     write_animation_archive(name, duration, j, t_tracks, r_tracks, s_tracks, version=version))
 
 
 # ----------------------------------------------------------------------------------------------

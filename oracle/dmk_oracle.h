@@ -58,7 +58,8 @@ typedef struct orc_qkey { /* ozz QuaternionKey (v6): 13/2/1 bit-field in memory,
     uint16_t track;
     uint8_t largest;
     uint8_t sign;
-    int16_t value[3];
+    int16_t value[3]; /* format 0 (archive v6): signed 16 bit; format 1 (archive v7): 15-bit magnitudes 0 .. 32767 */
+    uint8_t format;
 } orc_qkey;
 
 typedef struct orc_animation {

@@ -161,7 +161,13 @@ static void decompress_q(const orc_qkey* k[4], float out[4][4]) {
         for (int c = 0; c < 4; ++c) cmp[c] = k[l]->value[m[c]];
         cmp[k[l]->largest] = 0;
         float cpnt[4];
-        for (int c = 0; c < 4; ++c) cpnt[c] = kInt2Float * (float)cmp[c];
+        if (k[l]->format == 1) {
+            /* archive v7 (ozz >= 0.15, from memory -- see ozz_archive.c): magnitudes mapped from [-1/sqrt 2, 1/sqrt 2] */
+            const float kScale = 1.4142135623730950488016887242097f / 32767.f, kOffset = -0.70710678118654752440084436210485f;
+            for (int c = 0; c < 4; ++c) cpnt[c] = c == k[l]->largest ? 0.f : (float)cmp[c] * kScale + kOffset;
+        } else {
+            for (int c = 0; c < 4; ++c) cpnt[c] = kInt2Float * (float)cmp[c];
+        }
         const float dot = cpnt[0] * cpnt[0] + cpnt[1] * cpnt[1] + cpnt[2] * cpnt[2] + cpnt[3] * cpnt[3];
         float ww0 = 1.f - dot;
         if (!(ww0 > 1e-16f)) ww0 = 1e-16f;   /* math::Max(eps, one - dot) */

@@ -95,6 +95,13 @@ def test_archive_reader_survives_damaged_archives_under_asan(assets_dir):
     r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "ozz_io_fuzz"), os.path.join(assets_dir, "skeleton.ozz"),
                         os.path.join(assets_dir, "Idle01.ozz"), "20000", "3"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and " 0 failures" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    # the same for an Animation archive version 7 (ozz >= 0.15): index / back-offset tables instead of per-key ratio and track
+    v7 = os.path.join(assets_dir, "Idle01_v7.ozz")
+    with open(v7, "wb") as f:
+        f.write(synth.make_clip(synth.make_skeleton(67), "Idle01", seed=100, duration=1.0, version=7).archive)
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "ozz_io_fuzz"), os.path.join(assets_dir, "skeleton.ozz"), v7, "20000", "5"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and " 0 failures" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 def test_host_tick_benchmark_mode_runs(binary, assets_dir):
