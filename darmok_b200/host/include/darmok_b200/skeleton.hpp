@@ -20,10 +20,11 @@
 #pragma once
 
 #include "easing.hpp"
+#include "expected.hpp"
 #include "glm_lite.hpp"
+#include "optional_ref.hpp"
 
 #include <cstdint>
-#include <expected>
 #include <filesystem>
 #include <functional>
 #include <memory>
@@ -42,11 +43,6 @@ struct dmk_mesh_s;
 struct dmk_crowd_s;
 
 namespace darmok {
-
-template <typename T, typename E>
-using expected = std::expected<T, E>;
-template <typename E>
-using unexpected = std::unexpected<E>;
 
 // ---- definitions (assets/protobuf/skeleton.proto:8-64) -----------------------------------------------------------
 struct SkeletalAnimatorAnimationDefinition {
@@ -130,18 +126,42 @@ using SkeletalAnimationMap = std::unordered_map<std::string, std::shared_ptr<Ske
 using DataLoader = std::function<expected<std::vector<uint8_t>, std::string>(const std::filesystem::path&)>;
 expected<std::vector<uint8_t>, std::string> loadFileData(const std::filesystem::path& path) noexcept;
 
-class B200SkeletonLoader final {   // replaces OzzSkeletonLoader
+// the loader interfaces SkeletalAnimator::load reaches through its load context (include/darmok/skeleton.hpp:58, :352;
+// include/darmok/asset.hpp:47-48; include/darmok/scene_serialize.hpp:370-378)
+class ISkeletonLoader {
+public:
+    virtual ~ISkeletonLoader() = default;
+    virtual expected<std::shared_ptr<Skeleton>, std::string> operator()(const std::filesystem::path& path) noexcept = 0;
+};
+class ISkeletalAnimationLoader {
+public:
+    virtual ~ISkeletalAnimationLoader() = default;
+    virtual expected<std::shared_ptr<SkeletalAnimation>, std::string> operator()(const std::filesystem::path& path) noexcept = 0;
+};
+class IAssetContext {   // the two getters of darmok's IAssetContext that this path uses
+public:
+    virtual ~IAssetContext() = default;
+    virtual ISkeletonLoader& getSkeletonLoader() noexcept = 0;
+    virtual ISkeletalAnimationLoader& getSkeletalAnimationLoader() noexcept = 0;
+};
+class IComponentLoadContext {   // ... and the one getter of IComponentLoadContext
+public:
+    virtual ~IComponentLoadContext() = default;
+    virtual IAssetContext& getAssets() noexcept = 0;
+};
+
+class B200SkeletonLoader final : public ISkeletonLoader {   // replaces OzzSkeletonLoader
 public:
     B200SkeletonLoader(std::shared_ptr<DeviceContext> ctx, DataLoader dataLoader = loadFileData) noexcept;
-    expected<std::shared_ptr<Skeleton>, std::string> operator()(const std::filesystem::path& path) noexcept;
+    expected<std::shared_ptr<Skeleton>, std::string> operator()(const std::filesystem::path& path) noexcept override;
 private:
     std::shared_ptr<DeviceContext> _ctx;
     DataLoader _dataLoader;
 };
-class B200SkeletalAnimationLoader final {   // replaces OzzSkeletalAnimationLoader
+class B200SkeletalAnimationLoader final : public ISkeletalAnimationLoader {   // replaces OzzSkeletalAnimationLoader
 public:
     B200SkeletalAnimationLoader(std::shared_ptr<DeviceContext> ctx, DataLoader dataLoader = loadFileData) noexcept;
-    expected<std::shared_ptr<SkeletalAnimation>, std::string> operator()(const std::filesystem::path& path) noexcept;
+    expected<std::shared_ptr<SkeletalAnimation>, std::string> operator()(const std::filesystem::path& path) noexcept override;
 private:
     std::shared_ptr<DeviceContext> _ctx;
     DataLoader _dataLoader;
@@ -151,7 +171,7 @@ private:
 // definition's animation_pattern with every "*" replaced by the animation's name (the name itself without a pattern);
 // animations that fail to load are left out of the map (a state without any known animation cannot be created).
 std::filesystem::path animationPath(const SkeletalAnimatorDefinition& def, std::string_view name) noexcept;
-SkeletalAnimationMap loadAnimations(const SkeletalAnimatorDefinition& def, B200SkeletalAnimationLoader& loader) noexcept;
+SkeletalAnimationMap loadAnimations(const SkeletalAnimatorDefinition& def, ISkeletalAnimationLoader& loader) noexcept;
 
 struct ArmatureJoint final {
     std::string name;
@@ -296,8 +316,8 @@ public:
     SkeletalAnimator& setBlendPosition(const glm::vec2& value) noexcept;
     const glm::vec2& getBlendPosition() const noexcept;
     const Definition& getDefinition() const noexcept;
-    const ISkeletalAnimatorState* getCurrentState() const noexcept;            // OptionalRef in darmok
-    const ISkeletalAnimatorTransition* getCurrentTransition() const noexcept;
+    OptionalRef<const ISkeletalAnimatorState> getCurrentState() const noexcept;            // include/darmok/skeleton.hpp:283
+    OptionalRef<const ISkeletalAnimatorTransition> getCurrentTransition() const noexcept;   // :284
     float getStateDuration(const std::string& name) const noexcept;
 
     bool play(std::string_view name, float speedFactor = 1.F) noexcept;
@@ -324,7 +344,9 @@ public:
     // skeleton from def.skeleton_path (its error is returned), animations through loadAnimations, then the animator is reset
     // (no state, no transition, speed 1, not paused, blend position (0, 0)) and shows the new skeleton's rest pose.  The
     // skinning targets stay; not for animators owned by a SkeletalAnimationSceneComponent.
-    expected<void, std::string> load(const Definition& def, B200SkeletonLoader& skeletons, B200SkeletalAnimationLoader& animations) noexcept;
+    expected<void, std::string> load(const Definition& def, ISkeletonLoader& skeletons, ISkeletalAnimationLoader& animations) noexcept;
+    // the reference signature (include/darmok/skeleton.hpp:297): the two loaders come from ctxt.getAssets()
+    expected<void, std::string> load(const Definition& def, IComponentLoadContext& ctxt) noexcept;
     static Definition createDefinition() noexcept { return {}; }   // src/skeleton_ozz.cpp:956-959
 
 private:

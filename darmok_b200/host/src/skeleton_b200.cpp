@@ -367,7 +367,7 @@ std::filesystem::path animationPath(const SkeletalAnimatorDefinition& def, std::
     return v;
 }
 
-SkeletalAnimationMap loadAnimations(const SkeletalAnimatorDefinition& def, B200SkeletalAnimationLoader& loader) noexcept {
+SkeletalAnimationMap loadAnimations(const SkeletalAnimatorDefinition& def, ISkeletalAnimationLoader& loader) noexcept {
     SkeletalAnimationMap anims;
     for (const auto& state : def.states)
         for (const auto& anim : state.animations)
@@ -375,7 +375,11 @@ SkeletalAnimationMap loadAnimations(const SkeletalAnimatorDefinition& def, B200S
     return anims;
 }
 
-expected<void, std::string> SkeletalAnimator::load(const Definition& def, B200SkeletonLoader& skeletons, B200SkeletalAnimationLoader& animations) noexcept {
+expected<void, std::string> SkeletalAnimator::load(const Definition& def, IComponentLoadContext& ctxt) noexcept {
+    auto& assets = ctxt.getAssets();   // src/skeleton_ozz.cpp:917-919
+    return load(def, assets.getSkeletonLoader(), assets.getSkeletalAnimationLoader());
+}
+expected<void, std::string> SkeletalAnimator::load(const Definition& def, ISkeletonLoader& skeletons, ISkeletalAnimationLoader& animations) noexcept {
     if (_batch) return unexpected<std::string>{"this animator is owned by its SkeletalAnimationSceneComponent"};
     auto skel = skeletons(def.skeleton_path);
     if (!skel) return unexpected<std::string>{skel.error()};
@@ -460,7 +464,7 @@ SkeletalAnimator& SkeletalAnimator::setBlendPosition(const glm::vec2& value) noe
 }
 const glm::vec2& SkeletalAnimator::getBlendPosition() const noexcept { return _core->getBlendPosition(); }
 const SkeletalAnimator::Definition& SkeletalAnimator::getDefinition() const noexcept { return _core->getDefinition(); }
-const ISkeletalAnimatorState* SkeletalAnimator::getCurrentState() const noexcept {
+OptionalRef<const ISkeletalAnimatorState> SkeletalAnimator::getCurrentState() const noexcept {
     if (!onDevice()) return _core->getCurrentState();
     auto& im = *_batch->_impl;
     const dmk_anim_state* st = im.stateOf(_batchIndex);
@@ -472,7 +476,7 @@ const ISkeletalAnimatorState* SkeletalAnimator::getCurrentState() const noexcept
     v.duration = im.stateDuration[static_cast<size_t>(st->state)] * st->state_speed;   // multiplies (C2)
     return &v;
 }
-const ISkeletalAnimatorTransition* SkeletalAnimator::getCurrentTransition() const noexcept {
+OptionalRef<const ISkeletalAnimatorTransition> SkeletalAnimator::getCurrentTransition() const noexcept {
     if (!onDevice()) return _core->getCurrentTransition();
     auto& im = *_batch->_impl;
     const dmk_anim_state* st = im.stateOf(_batchIndex);

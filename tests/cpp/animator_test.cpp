@@ -267,7 +267,7 @@ static ScenarioStats runScenarioCpu(const OracleAssets& o, const SkeletalAnimato
         }
         CHECK(std::memcmp(models.data(), ref.models().data(), models.size() * 4) == 0, "%s step %d: model matrices differ from the reference animator", label, step);
         CHECK(events == ref.events, "%s step %d: listener events differ (%zu vs %zu)", label, step, events.size(), ref.events.size());
-        const auto* cs = core.getCurrentState();
+        const auto cs = core.getCurrentState();
         const auto* rs = ref.currentState();
         CHECK((cs != nullptr) == (rs != nullptr), "%s step %d: current state presence", label, step);
         if (cs && rs) {
@@ -1212,7 +1212,7 @@ static int runGpu(const std::string& dir) {
                 auto& a = scene.getAnimator(i);
                 if (i % 2 == 0) CHECK(logs[(size_t)i].events == refs[i]->events, "frame %d animator %ld: listener events differ (%zu vs %zu)", frame, (long)i, logs[(size_t)i].events.size(), refs[i]->events.size());
                 if ((i + frame) % 3) continue;
-                const auto* cs = a.getCurrentState();
+                const auto cs = a.getCurrentState();
                 const auto* rs = refs[i]->currentState();
                 CHECK((cs != nullptr) == (rs != nullptr), "frame %d animator %ld: current state presence", frame, (long)i);
                 if (cs && rs) {
@@ -1221,7 +1221,7 @@ static int runGpu(const std::string& dir) {
                           std::string(cs->getName()).c_str(), cs->getNormalizedTime(), rs->getName().c_str(), rs->getNormalizedTime());
                     CHECK(std::fabs(cs->getDuration() - rs->getDuration()) <= 1e-6f * rs->getDuration(), "frame %d animator %ld: duration %g vs %g", frame, (long)i, cs->getDuration(), rs->getDuration());
                 }
-                const auto* ct = a.getCurrentTransition();
+                const auto ct = a.getCurrentTransition();
                 auto* rt = const_cast<orc::RefTransition*>(refs[i]->currentTransition());
                 CHECK((ct != nullptr) == (rt != nullptr), "frame %d animator %ld: transition presence", frame, (long)i);
                 if (ct && rt) {
