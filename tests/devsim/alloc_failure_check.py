@@ -63,10 +63,10 @@ def sequence(assets, made):
     crowd.animator_commands(np.full(n, 1, np.int32))
     crowd.step(1.0 / 60.0, capi.STEP_ANIMATOR | capi.STEP_POSE)
     crowd.animator_events(); crowd.animator_state()
-    ex = capi.Exchange.create(ctx, 2, 0, 16, arm.palette_size); made.append(ex)
+    ex = capi.Exchange.create(ctx, 2, 0, n, arm.palette_size); made.append(ex)   # capacity = crowd size: no overflow to report
     ex2 = ex.attach(ctx, 1); made.append(ex2)
     crowd.push_visible_palettes(ex, 1, 2)
-    crowd.push_visible_palettes(ex2, 1, 2)
+    crowd.push_visible_palettes(ex2, 1, -1)     # copy-engine transport: its local staging buffer is allocated at first use
     ex.wait(1); ex.release(1); ex.status()
     ctx.cull_host(synth.sample_camera_view_proj(), 0.0, inst.world_inverse, inst.bbox)
 

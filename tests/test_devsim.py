@@ -95,11 +95,11 @@ def jobs(assets_dir):  # noqa: F811
         "bench_1": (sim(*small), plain),
         "bench_1_layout": (sim(*small, "--skin-layout", "2", "--no-cpu-baseline"), plain),
         "bench_2": ([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
-                     os.path.join(DEVSIM, "bench_on_simulator.py"), "--gpus", "2", *small], _env(LIB, DMK_DEVSIM_DEVICES="2", OMP_NUM_THREADS="2")),
+                     os.path.join(DEVSIM, "bench_on_simulator.py"), "--gpus", "2", *small, "--gather", "nccl"], _env(LIB, DMK_DEVSIM_DEVICES="2", OMP_NUM_THREADS="2")),
         # DMK_DEVSIM_SHARED: large "device" blocks are memfd mappings that another process can open through the IPC handle, so the
         # peer-memory exchange runs between two real processes (concurrently: the flow control works in real time)
         "bench_2_peer": ([PY, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(ports[1]),
-                          os.path.join(DEVSIM, "bench_on_simulator.py"), "--gpus", "2", *small, "--gather", "peer"],
+                          os.path.join(DEVSIM, "bench_on_simulator.py"), "--gpus", "2", *small, "--gather", "peer-ce"],
                          _env(LIB, DMK_DEVSIM_DEVICES="2", DMK_DEVSIM_SHARED="1", OMP_NUM_THREADS="2")),
         "ipc_check": (script("tests", "peer_exchange_ipc_check.py"), _env(LIB, DMK_DEVSIM_SHARED="1")),
         "tool_3s": (sim("--script", "tools/bench_configs.py", "3s"), tool_env),
@@ -220,7 +220,8 @@ def test_bench_two_rank_arm_runs_on_the_simulator(jobs):
 def test_peer_memory_exchange_between_two_processes_on_the_simulator(jobs):
     # tests/peer_exchange_ipc_check.py: two processes, the render rank is rank 1, darmok_b200.parallel.PeerPaletteExchange start-up (handle
     # over gloo, open, barrier) and six frames of push / wait / release with the slab in memory both processes map; and bench.py
-    # --gather peer with two ranks (pack+transfer kernel on the side "stream", double-buffered slab, status check at the end)
+    # --gather peer-ce with two ranks (stage in-stream, copy + publish on the side "stream", double-buffered slab, content check and
+    # status check at the end)
     j = jobs["ipc_check"]
     assert j.returncode == 0 and "identical to what the ranks sent" in j.stdout and j.clean, j.tail
     j = jobs["bench_2_peer"]
@@ -228,13 +229,13 @@ def test_peer_memory_exchange_between_two_processes_on_the_simulator(jobs):
     lines = [ln for ln in j.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1, j.tail
     line = json.loads(lines[0])
-    assert line["n_gpus"] == 2 and "pack+transfer kernel" in line["config"]["gather"]
+    assert line["n_gpus"] == 2 and "DMA-engine copy" in line["config"]["gather"] and line["gather_verified"] is True
 
 
 def test_round_two_measurement_scripts_dry_run_on_the_simulator(jobs):
     # the scripts the next GPU call runs (tools/round2_first_call.sh), with a crowd of 200 characters x 72 vertices: they must get to
     # their last line without a Python error, so that GPU minutes are not spent finding a typo
-    for name, expect in (("tool_3s", "three_float3_streams"), ("tool_pipelined", "4_crowds"), ("tool_skin_only", "done")):
+    for name, expect in (("tool_3s", "ws_clustered_streams"), ("tool_pipelined", "4_crowds"), ("tool_skin_only", "done")):
         j = jobs[name]
         assert j.returncode == 0 and expect in j.stdout and j.clean, name + "\n" + j.tail
 
