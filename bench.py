@@ -470,7 +470,7 @@ def run_gpu(args):
             ratio = cr.ratio.copy()
             vis_bits = np.zeros((n + 31) // 32, np.uint32)
             e2e_flags = capi.STEP_POSE | capi.STEP_CULL | capi.STEP_SKIN | capi.STEP_READBACK_VISIBILITY
-            e2e_steps = max(3, min(args.steps, 40))
+            e2e_steps = max(3, args.steps) if os.environ.get("DMK_DEVSIM") == "1" else max(60, args.steps)   # ~0.3 s: one slow frame must not carry the mean
 
             def host_tick(r):
                 # host state machine tick (clip clocks of looping clips) -> layer state of the next frame
@@ -532,6 +532,8 @@ def run_gpu(args):
                 e2e_s = float(t.item())
             e2e = {"value": n * world * e2e_steps_done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(3 * 2 * n * 4),
                    "d2h_bytes_per_step": int(vis_bits.nbytes + 4), "steps": e2e_steps_done,
+                   "frame_ms_rank0": (lambda per: {"median": statistics.median(per), "p90": per[int(round(0.9 * (len(per) - 1)))], "max": per[-1]})(
+                       sorted(sum(p) * 1e3 for p in phases)),
                    "note": "frame loop with two frames in flight; per step: host clip clocks (numpy) -> dmk_crowd_update_layers (pinned H2D of clip/ratio/weight) -> "
                            "dmk_crowd_step(POSE|CULL|SKIN|READBACK_VISIBILITY) -> pack visible palettes (N > 1: the visible-palette exchange to rank 0, as in the "
                            "device-timed loop) -> dmk_crowd_collect_visibility (pinned D2H of the bitmask + count, waited per frame); "
@@ -638,6 +640,156 @@ def run_gpu(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# --config 2 / 5: the other single-GPU configurations of BASELINE.json, same JSON schema (one line)
+# ----------------------------------------------------------------------------------------------------------------
+def _peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def _timed(stream, dev, sampler_factory, steps, warmup, fn):
+    """W warm-up calls, then K calls between two CUDA events on `stream`; returns (ms per call, clocks)"""
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    sampler = sampler_factory()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop(t0, time.perf_counter())
+    return e0.elapsed_time(e1) / steps, clocks
+
+
+def run_config2(args):
+    """BASELINE.json configs[1]: 10k characters, 67 joints, single looping clip, palette only (no vertex skinning), 1 B200."""
+    import torch
+    from darmok_b200 import capi, synth
+    from oracle import oracle_py as O
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.Stream(device=dev)
+    n = 10_000
+    skel_s = synth.make_skeleton(67)
+    clips_s = [synth.make_clip(skel_s, "loop", seed=0, duration=1.5)]
+    arm_s = synth.make_armature(skel_s)
+    with torch.cuda.stream(stream):
+        ctx = capi.Context(0, stream.cuda_stream)
+        skel = capi.Skeleton(ctx, skel_s.archive)
+        clip_objs = [capi.Clip(ctx, c.archive) for c in clips_s]
+        clips = capi.ClipSet(ctx, skel, clip_objs)
+        arm = capi.Armature(ctx, skel, arm_s.names, arm_s.inv_bind)
+        crowd = capi.Crowd(ctx, skel, clips, arm, None, n, 1)
+        cr = synth.make_crowd(n, 1, 1, seed=42)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed)
+        flags = capi.STEP_ADVANCE | capi.STEP_POSE
+        steps = max(args.steps, 200)
+        launches0 = ctx.launches
+        ms, clocks = _timed(stream, dev, lambda: make_clock_sampler(0), steps, max(args.warmup, 20), lambda: crowd.step(DT, flags))
+        launches = (ctx.launches - launches0) * steps // (steps + max(args.warmup, 20))
+        # e2e: host layer state in (pinned H2D), every palette back out (D2H), through the C ABI
+        durations = np.array([c.duration for c in clips_s], np.float32)
+        ratio = cr.ratio.copy()
+        e2e_steps = 20
+        crowd.update_layers(cr.clip, ratio, cr.weight); crowd.step(DT, capi.STEP_POSE); crowd.get_palette()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ratio = np.fmod(ratio + np.float32(DT) / (durations[cr.clip] / cr.speed), np.float32(1.0)).astype(np.float32)
+            crowd.update_layers(cr.clip, ratio, cr.weight)
+            crowd.step(DT, capi.STEP_POSE)
+            pal = crowd.get_palette()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # cpu baseline: the oracle's sample + local-to-model + palette for the same crowd
+    oskel = O.Skeleton(skel_s.archive)
+    oclips = [O.Animation(c.archive) for c in clips_s]
+    remap = np.array([oskel.find_joint(nm) for nm in arm_s.names], np.int32)
+    ocrowd = O.Crowd(oskel, oclips, remap, arm_s.inv_bind, n, 1)
+    threads = host_threads()
+    ocrowd.step(cr.clip, cr.ratio, cr.weight, FLT_MIN, want=("palette",), num_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ocrowd.step(cr.clip, cr.ratio, cr.weight, FLT_MIN, want=("palette",), num_threads=threads)
+    cpu_rate = n * 5 / (time.perf_counter() - t0)
+    peak, peak_src = _peak()
+    alg = n * (arm.palette_size * 64 + 32)
+    achieved = alg / (ms * 1e-3) / 1e9
+    emit({"metric": "posed_characters_per_sec", "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 20),
+          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "BASELINE.json configs[1]: 10k characters, 67-joint skeleton, single looping clip, palette only (clip clock + sample + "
+                                 "local-to-model + palette; no vertex skinning) on 1 B200", "characters": n, "joints": 67, "layers": 1,
+                     "l2": "the crowd's state (0.4 MB in, 43.5 MB of palettes out) fits L2: launch / latency bound, not HBM bound (HBM floor 6.7 us)"},
+          "clocks": clocks,
+          "e2e": {"value": n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(3 * n * 4), "d2h_bytes_per_step": int(pal.nbytes), "steps": e2e_steps,
+                  "note": "host clip clocks -> dmk_crowd_update_layers (pinned H2D) -> dmk_crowd_step(POSE) -> dmk_crowd_get_palette (D2H of every palette)"},
+          "gpu_launches": int(launches),
+          "roofline": {"bound": "hbm", "kernel": "pose path K0-K3 (advance + sample + model kernels of one step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                       "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms},
+          "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
+                           "sample": f"the whole crowd ({n} characters) x 5 steps: oracle sample + local-to-model + palette, OpenMP {threads} threads"}})
+    return 0
+
+
+def run_config5(args):
+    """BASELINE.json configs[4]: 10M-instance frustum AABB cull (culling.cpp semantics), visibility bit-exact vs CPU."""
+    import torch
+    from darmok_b200 import capi, synth
+    from oracle import oracle_py as O
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.Stream(device=dev)
+    n = 10_000_000
+    inst = synth.make_instances(n, seed=5, extent=500.0)
+    vp = synth.sample_camera_view_proj()
+    with torch.cuda.stream(stream):
+        ctx = capi.Context(0, stream.cuda_stream)
+        corners = ctx.frustum_corners(vp, 0.0)
+        wi = torch.from_numpy(inst.world_inverse).to(dev)
+        bb = torch.from_numpy(inst.bbox).to(dev)
+        bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev)
+        steps = max(args.steps, 50)
+        ms, clocks = _timed(stream, dev, lambda: make_clock_sampler(0), steps, max(args.warmup, 5),
+                            lambda: ctx.cull_dev(corners, wi.data_ptr(), bb.data_ptr(), n, bits.data_ptr()))
+        got = bits.cpu().numpy().view(np.uint32)
+        t0 = time.perf_counter()
+        host_bits = ctx.cull_host(vp, 0.0, inst.world_inverse, inst.bbox)
+        e2e_s = time.perf_counter() - t0
+    m = 2_000_000
+    threads = host_threads()
+    t0 = time.perf_counter()
+    ref = O.cull_batch(O.frustum_corners(vp, 0.0), inst.world_inverse[:m], inst.bbox[:m], num_threads=threads)
+    cpu_s = time.perf_counter() - t0
+    exact = bool(np.array_equal(got[: m // 32], ref[: m // 32])) and bool(np.array_equal(host_bits, got))
+    if not exact:
+        raise SystemExit("visibility differs from the oracle")
+    peak, peak_src = _peak()
+    alg = n * 88.125
+    achieved = alg / (ms * 1e-3) / 1e9
+    emit({"metric": "culled_instances_per_sec", "value": n / (ms * 1e-3), "unit": "instances/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 5),
+          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "BASELINE.json configs[4]: 10M-instance frustum vs local-AABB cull (FrustumCuller::updateCulled semantics), 1 B200",
+                     "instances": n, "visible": int(np.unpackbits(got.view(np.uint8)).sum()),
+                     "visibility_bit_exact_vs_oracle": exact, "oracle_checked_instances": m,
+                     "l2": "inputs larger than L2: 880 MB of matrices and boxes per launch (L2 = 126 MB)"},
+          "clocks": clocks,
+          "e2e": {"value": n / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": int(n * 88), "d2h_bytes_per_step": int(host_bits.nbytes), "steps": 1,
+                  "note": "dmk_cull_host: pageable host matrices and boxes in (H2D), the bitmask out (D2H), one call"},
+          "gpu_launches": 1,
+          "roofline": {"bound": "hbm", "kernel": "cull_kernel<false> (K4)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                       "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms},
+          "cpu_baseline": {"value": m / cpu_s, "unit": "instances/s", "cores": threads, "kind": "port",
+                           "sample": f"{m} of the {n} instances, oracle/cull.c (the reference arithmetic, pinned by its shape_test.cpp vectors), OpenMP {threads} threads"}})
+    return 0
+
+
 class _DevArray:
     """__cuda_array_interface__ view of device memory owned by the library (no copy)."""
 
@@ -675,6 +827,9 @@ def main():
     ap.add_argument("--verts", type=int, default=5000)
     ap.add_argument("--clips", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5],
+                    help="which BASELINE.json configuration to measure: 3 (default, the headline: configs[2], and configs[3] with --gpus 8 --chars 125000 "
+                         "--clips 32), 2 = configs[1] (10k characters, palette only), 5 = configs[4] (10M-instance cull)")
     ap.add_argument("--reserve-sms", type=int, default=-1, help="N > 1: SMs left to the gather so that it overlaps the skinning")
     ap.add_argument("--skin-layout", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="DMK_OPT_SKIN_PLANAR_OUTPUT: 0 interleaved [V][9] (default), 1 / 2 nine component planes (10 / 14 warps), 3 three float3 "
@@ -698,6 +853,10 @@ def main():
         sys.exit("--reserve-sms must be 0 or at least 8 (with fewer NCCL CTAs the visible-palette gather no longer overlaps)")
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 2:
+        return run_config2(args)
+    if args.config == 5:
+        return run_config5(args)
     return run_gpu(args)
 
 
