@@ -339,7 +339,7 @@ dmk_status dmk_mesh_cluster_stats(const float* indices, const float* weights, in
         plan = plan_skin(vpad, palette_size, 148, 0);
         cudaGetLastError();   // without a device the occupancy query fails; the tile shape does not depend on it
     }
-    const ClusterResult cl = cluster_mesh(infl, plan.num_tiles, plan.tile_vertices);
+    const ClusterResult cl = cluster_mesh(infl, plan.num_tiles, plan.tile_vertices, plan.ws_vpt == 4 ? 16 : 32);
     if (out_order) std::copy(cl.order.begin(), cl.order.begin() + num_vertices, out_order);
     out_stats4[0] = cl.gather_wavefronts;
     out_stats4[1] = cl.gather_wavefronts_unclustered;
@@ -402,7 +402,7 @@ dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const fl
     std::vector<ClusterInfluence> stored;
     if (flags & DMK_MESH_CLUSTER_BONES) {
         const SkinPlan plan = plan_skin(vpad, palette_size, ctx->num_sms, 0);
-        ClusterResult cl = cluster_mesh(infl, plan.num_tiles, plan.tile_vertices);
+        ClusterResult cl = cluster_mesh(infl, plan.num_tiles, plan.tile_vertices, plan.ws_vpt == 4 ? 16 : 32);
         mesh->order.assign(cl.order.begin(), cl.order.begin() + num_vertices);   // padding sits behind the last real vertex
         stored = std::move(cl.stored);
         mesh->clustered = true;

@@ -153,7 +153,7 @@ dmk_status dmk_skin_plan(int vertex_pitch, int palette_size, int num_sms, int la
     out7[3] = plan.grid;
     out7[4] = plan.replicas;
     out7[5] = static_cast<int64_t>(plan.smem);
-    out7[6] = (layout == 1 || layout == 2) ? 4 : 8;
+    out7[6] = (layout == 1 || layout == 2) ? 4 : plan.ws_vpt;
     return DMK_OK;
 }
 

@@ -119,6 +119,17 @@ __device__ __forceinline__ void st_v8(float* p, float a, float b, float c, float
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h)
                  : "memory");
 }
+// the same where `take` is non-zero (a warp whose lanes store different register sets: one predicated store per set)
+__device__ __forceinline__ void st_v8_if(float* p, const float* v, uint32_t take) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "setp.ne.u32 P1, %9, 0;\n"
+        "@P1 st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+        "}\n" ::"l"(p),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "r"(take)
+        : "memory");
+}
 __device__ __forceinline__ void ld_v8(const float* p, float* v) {
     asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])

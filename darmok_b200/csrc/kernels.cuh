@@ -37,8 +37,10 @@ struct SkinPlan {
     bool legacy;        // the round-1 kernel shape (every warp replicates and skins) instead of producer warp + compute warps
     int variant;        // 0: interleaved [V][9] output, 8 vertices per thread; 1 / 2: planar [9][V] output, 4 per thread, <= 320 / 448 threads;
                         // 3: three float3 streams [3][V][3], 8 per thread; 4: planar [9][V], 8 per thread
+    int ws_vpt;         // vertices per thread of the warp-specialised kernel: 8, or 4 (two lanes per 8-vertex block; variant 0 with 8 replicas only)
 };
-SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant = 0, bool legacy = false);
+// ws_vpt: 8 or 4, 0 = the default (8, or what the environment variable DMK_SKIN_VPT says)
+SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant = 0, bool legacy = false, int ws_vpt = 0);
 cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t stream);
 
 // K6 payload: gather palettes of the listed characters into a dense buffer

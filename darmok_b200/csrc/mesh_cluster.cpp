@@ -52,7 +52,7 @@ Vtx normalise(const ClusterInfluence& in, int32_t id) {
 
 }  // namespace
 
-ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tiles, int tile_vertices) {
+ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tiles, int tile_vertices, int blocks_per_warp) {
     ClusterResult out;
     const int V = static_cast<int>(in.size());
     const int vpad = (V + kBlock - 1) / kBlock * kBlock;
@@ -63,6 +63,8 @@ ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tile
     if (vpad == 0) return out;
     if (num_tiles < 1) num_tiles = 1;
     if (tile_vertices < kBlock) tile_vertices = kBlock;
+    if (blocks_per_warp != 16) blocks_per_warp = 32;
+    const int quarters = blocks_per_warp / kQuarter;   // quarter-warp groups of 8 blocks per warp
 
     std::vector<Vtx> vt(static_cast<size_t>(vpad));
     for (int v = 0; v < V; ++v) vt[static_cast<size_t>(v)] = normalise(in[static_cast<size_t>(v)], v);
@@ -183,10 +185,10 @@ ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tile
     for (int t = 0; t < num_tiles; ++t) {
         const int begin = t * tb, end = std::min(dealt_end, (t + 1) * tb);
         if (begin >= end) continue;
-        const int len = end - begin, warps = (len + 31) / 32;
-        for (int quarter = 0; quarter < 4; ++quarter)
+        const int len = end - begin, warps = (len + blocks_per_warp - 1) / blocks_per_warp;
+        for (int quarter = 0; quarter < quarters; ++quarter)
             for (int w = 0; w < warps; ++w) {
-                const int pos = (w * 4 + quarter) * kQuarter;
+                const int pos = (w * quarters + quarter) * kQuarter;
                 if (pos < len) tile_slots[static_cast<size_t>(t)].push_back({begin + pos, std::min(kQuarter, len - pos)});
             }
         max_slots = std::max(max_slots, tile_slots[static_cast<size_t>(t)].size());
@@ -217,7 +219,7 @@ ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tile
         const int begin = t * tb, end = std::min(nb, (t + 1) * tb);
         for (int q0 = begin; q0 < end; q0 += kQuarter) {
             const int q1 = std::min(end, q0 + kQuarter);
-            out.gather_wavefronts += 3;   // the block bones of the 8 lanes
+            out.gather_wavefronts += blocks_per_warp == 16 ? 6 : 3;   // the block bones of the 8 lanes (read by both lanes of a pair)
             for (int k = 0; k < kBlock; ++k) {
                 uint32_t any = 0;
                 for (int pos = q0; pos < q1; ++pos) {

@@ -35,7 +35,8 @@ struct ClusterResult {
 
 // `in[v]`: the 4 (slot, weight) pairs of caller vertex v.  `tile_vertices` (multiple of 8) and `num_tiles`: the tile shape
 // of the skinning plan the order is dealt for (every tile, warp and quarter-warp gets the same mix of heavy and light
-// blocks); any other plan stays correct, only less balanced.
-ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tiles, int tile_vertices);
+// blocks); any other plan stays correct, only less balanced.  `blocks_per_warp`: 32 (a thread owns a block) or 16 (two lanes
+// share a block: the 4-vertices-per-thread shape); the gather statistics count the extra block-bone reads of the latter.
+ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tiles, int tile_vertices, int blocks_per_warp = 32);
 
 }  // namespace dmk

@@ -24,6 +24,7 @@
 #include "device_types.cuh"
 #include "kernels.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace dmk {
@@ -278,7 +279,10 @@ __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
 //     SKIP (absent influences are predicated off, whole quarter-warps at a time) the gathers drop from 96 to ~51 LDS.128
 //     per thread and character (dmk_mesh_cluster_stats), which takes the kernel off the L1 data pipe.
 // LAYOUT: 0 interleaved [V][9], 3 three float3 streams [3][V][3], 4 nine planes [9][V]  (DMK_OPT_SKIN_PLANAR_OUTPUT values).
-constexpr int kMaxRing = 4;   // replica ring of the warp-specialised kernel (SkinParams::num_stages: 4, fewer where shared memory is short)
+constexpr int kMaxRing = 4;   // replica ring of the warp-specialised kernel (SkinParams::num_stages: 4, fewer where shared memory is short).
+// MEASURED (profiles/r02_skin_ring_sleep_experiment.jsonl): rings of 5 and 6 buffers, and a producer that sleeps between the polls of
+// the "empty" barrier (its spin is 13 % of the warp instructions the kernel executes, one lane each) change neither the burst
+// nor the power-capped time -- the palettes are not what the compute warps wait for.
 
 // Replica layout of the warp-specialised kernel: REPL plain copies of the character's palette34 ([PS][16] floats, rows 0..2 of
 // every slot used), each written by ONE bulk copy straight from global memory -- no thread ever touches the palette on its
@@ -288,10 +292,18 @@ constexpr int kMaxRing = 4;   // replica ring of the warp-specialised kernel (Sk
 // of the round-1 kernel, for 2 more integer instructions per gather.
 __host__ __device__ inline uint32_t replica_stride(int palette_size) { return (uint32_t)palette_size * 64u + ((palette_size & 1) ? 80u : 16u); }
 
-template <int REPL, bool SKIP, bool SHARE, int LAYOUT>
-__global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParams p) {
-    static_assert(LAYOUT == 0 || LAYOUT == 3 || LAYOUT == 4, "8 vertices per thread: interleaved, three streams or nine planes");
-    constexpr int kVPT = 8;
+//
+// VPT = 4 (round 2, DMK_OPT_SKIN_VERTICES_PER_THREAD): an 8-vertex block -- still the unit of the output's whole sectors and
+// of the clustered mesh order -- is shared by TWO lanes of a warp, lane L (first 4 vertices) and lane L ^ 8 (last 4), so the 8
+// lanes of a quarter-warp still hold the same position of 8 consecutive blocks (what the predicated gathers need to cost no
+// wavefront).  4 x 36 B = 144 B is 4.5 sectors: the second lane passes its first 16 bytes to the first one by 4 shuffles, which
+// then writes 5 whole sectors, the second lane 4.  Half the registers per thread (13 x 4 bind-pose values instead of 13 x 8),
+// so 10 compute warps per SM instead of 7 (MAXT = 352).  Measured slower than 8 vertices per thread (see kMaxThreads4).
+template <int REPL, bool SKIP, bool SHARE, int LAYOUT, int VPT = 8, int MAXT = kMaxThreads>
+__global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
+    static_assert(LAYOUT == 0 || LAYOUT == 3 || LAYOUT == 4, "interleaved, three streams or nine planes");
+    static_assert(VPT == 8 || (VPT == 4 && LAYOUT == 0), "4 vertices per thread: interleaved output only");
+    constexpr int kVPT = VPT;
     constexpr bool STREAMS = LAYOUT == 3, PLANAR = LAYOUT == 4;
     DMK_DYNAMIC_SMEM(smem, 128);
     const int PS = p.palette_size;
@@ -382,9 +394,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
     const uint32_t odd_delta = (((lane_repl ^ 4u) & (REPL - 1)) - lane_repl) * RS;   // (mod 2^32)
     uint32_t rb = 0, rphase = 0;
     for (int tile = tslot; tile < p.num_tiles; tile += tiles_per_pass) {
-        // ---- this thread's 8 vertices: loaded once, kept in registers for every character ----
-        const int v0 = tile * p.tile_vertices + tid * kVPT;
-        const bool active = tid * kVPT < p.tile_vertices && v0 < p.vpad;
+        // ---- this thread's 8 (4) vertices: loaded once, kept in registers for every character ----
+        // the 8-vertex block of the tile this lane works on, and which half of it (VPT = 4: lanes L and L ^ 8 share a block)
+        const int blk = VPT == 8 ? tid : warp * 16 + ((lane >> 4) << 3) + (lane & 7);
+        const int half = VPT == 8 ? 0 : (lane >> 3) & 1;
+        const int v0 = tile * p.tile_vertices + blk * 8 + half * 4;
+        const bool active = blk * 8 < p.tile_vertices && v0 < p.vpad;
         float px[kVPT], py[kVPT], pz[kVPT], nx[kVPT], ny[kVPT], nz[kVPT], tx[kVPT], ty[kVPT], tz[kVPT];
         float w0[kVPT], w1[kVPT], w2[kVPT], w3[kVPT];
         uint32_t slots[kVPT];
@@ -400,7 +415,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
         }
         // bit 4 v + k: influence k of vertex v is fetched from shared memory (k = 0: unless it is the block's bone)
         uint32_t used = 0;
-        const uint32_t block_slot = slots[0] & 0xffu;
+        // the block's bone: entry 0 of the block's FIRST vertex (the other half's vertex 0 for the second lane of a pair)
+        const uint32_t block_slot = (VPT == 4 && half && active ? __ldg(p.slots + v0 - 4) : slots[0]) & 0xffu;
+        // VPT = 4: the whole warp runs the item when any lane has vertices (the pair's shuffles need both lanes), stores are predicated
+        const bool warp_active = VPT == 8 ? active : __ballot_sync(0xffffffffu, active) != 0u;
+        const uint32_t st_first = active && half == 0, st_second = active && half == 1;
 #pragma unroll
         for (int v = 0; v < kVPT; ++v) {
             uint32_t u = (SHARE && (slots[v] & 0xffu) == block_slot) ? 0u : 1u;
@@ -433,6 +452,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
                     b2 = lds128(base + block_off + 32u);
                 }
                 float res[kVPT * 9];
+                float recv[4];   // (VPT = 4) the first 16 bytes of the block's second half
                 uint32_t a0, a1, a2, a3;
                 auto slot_addr = [&](uint32_t slot) { return base + slot * 64u + ((slot & 1u) ? odd_delta : 0u); };
                 auto addr = [&](uint32_t s) {
@@ -524,10 +544,29 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
                         res[STREAMS ? kVPT * 3 + v * 3 + r : v * 9 + 3 + r] = fmaf(m2[r], nz[v], fmaf(m1[r], ny[v], m0[r] * nx[v]));
                         res[STREAMS ? kVPT * 6 + v * 3 + r : v * 9 + 6 + r] = fmaf(m2[r], tz[v], fmaf(m1[r], ty[v], m0[r] * tx[v]));
                     }
-                    if (LAYOUT == 0) {   // flush every 32-byte sector that just became complete
+                    if (LAYOUT == 0 && VPT == 8) {   // flush every 32-byte sector that just became complete
                         float* out = p.out + ((size_t)cid * p.vpad + v0) * 9;
 #pragma unroll
                         for (int sct = (v * 9) / 8; sct < ((v + 1) * 9) / 8; ++sct) st_v8(out + sct * 8, res + sct * 8);
+                    }
+                    if (LAYOUT == 0 && VPT == 4) {
+                        // this lane's 36 floats start on a sector boundary (first half of the block) or 16 bytes behind one
+                        // (second half).  First half: sectors [8 s, 8 s + 8), s = 0..3, and a fifth made of its last 4 floats and
+                        // the second half's first 4 (shuffled over as soon as they exist); second half: sectors [4 + 8 s, 12 + 8 s).
+                        float* out = p.out + ((size_t)cid * p.vpad + v0) * 9;
+                        if (v == 0) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) recv[k] = __shfl_xor_sync(0xffffffffu, res[k], 8);
+                        }
+#pragma unroll
+                        for (int sct = 0; sct < 4; ++sct) {
+                            if (8 * (sct + 1) > 9 * v && 8 * (sct + 1) <= 9 * (v + 1)) st_v8_if(out + 8 * sct, res + 8 * sct, st_first);
+                            if (4 + 8 * (sct + 1) > 9 * v && 4 + 8 * (sct + 1) <= 9 * (v + 1)) st_v8_if(out + 4 + 8 * sct, res + 4 + 8 * sct, st_second);
+                        }
+                        if (v == 3) {
+                            const float last[8] = {res[32], res[33], res[34], res[35], recv[0], recv[1], recv[2], recv[3]};
+                            st_v8_if(out + 32, last, st_first);
+                        }
                     }
                     if (STREAMS) {
 #pragma unroll
@@ -547,7 +586,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
                     }
                 }
                         };
-            if (active) {
+            if (warp_active) {
                 if (SHARE && rare != 0u) item(std::true_type{});
                 else item(std::false_type{});
             }
@@ -563,6 +602,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) skin_ws_kernel(const SkinParam
 namespace {
 constexpr size_t kMaxSmem = 227 * 1024;   // per-CTA shared memory limit on sm_100
 constexpr int kComputeThreads = kMaxThreads - 32;   // warp-specialised shape: the 8th warp is the producer
+// 4 vertices per thread: 10 compute warps + the producer (up to 184 registers; ptxas takes 153-168).  MEASURED (r02 call 11,
+// profiles/r02_skin_vpt4_experiment.jsonl): 3.73-3.79 ms against 3.54-3.59 ms for 8 vertices per thread on the clustered mesh,
+// 4.04 against 3.89 on the caller's order; 14 + 1 warps at 128 registers (spills) 5.10 ms.  More resident warps do not help:
+// the kernel is not short of warps to issue from, it is short of shared-memory and store bandwidth per SM.  Kept selectable
+// (DMK_SKIN_VPT=4 in the environment) as a diagnostic.
+constexpr int kMaxThreads4 = 352;
 // legacy: the round-1 kernel (every warp replicates and skins); the VPT = 4 layouts (1, 2) only exist in that shape
 bool is_legacy(int variant, bool legacy) { return legacy || variant == 1 || variant == 2; }
 size_t skin_smem_bytes(int palette_size, int repl, bool legacy, int ring = kMaxRing) {
@@ -585,7 +630,14 @@ auto with_legacy_kernel(int repl, bool skip, int variant, F&& f) {
 }
 // mode: 0 caller's vertex order, 1 influence-sorted (predicated gathers), 2 clustered by bone (block bone in registers + predicated gathers)
 template <int LAYOUT, typename F>
-auto with_ws_layout(int repl, int mode, F&& f) {
+auto with_ws_layout(int repl, int mode, int vpt, F&& f) {
+    if constexpr (LAYOUT == 0) {
+        if (repl == 8 && vpt == 4) {
+            if (mode == 2) return f(skin_ws_kernel<8, true, true, 0, 4, kMaxThreads4>);
+            if (mode == 1) return f(skin_ws_kernel<8, true, false, 0, 4, kMaxThreads4>);
+            return f(skin_ws_kernel<8, false, false, 0, 4, kMaxThreads4>);
+        }
+    }
     if (repl == 8) {
         if (mode == 2) return f(skin_ws_kernel<8, true, true, LAYOUT>);
         if (mode == 1) return f(skin_ws_kernel<8, true, false, LAYOUT>);
@@ -601,26 +653,25 @@ auto with_ws_layout(int repl, int mode, F&& f) {
     }
 }
 template <typename F>
-auto with_kernel(int repl, int mode, int variant, bool legacy, F&& f) {
+auto with_kernel(int repl, int mode, int variant, bool legacy, int vpt, F&& f) {
     if (is_legacy(variant, legacy)) return with_legacy_kernel(repl, mode != 0, variant, f);
-    if (variant == 3) return with_ws_layout<3>(repl, mode, f);
-    if (variant == 4) return with_ws_layout<4>(repl, mode, f);
-    return with_ws_layout<0>(repl, mode, f);
+    if (variant == 3) return with_ws_layout<3>(repl, mode, vpt, f);
+    if (variant == 4) return with_ws_layout<4>(repl, mode, vpt, f);
+    return with_ws_layout<0>(repl, mode, vpt, f);
+}
+int default_vpt() {
+    static const int v = [] {
+        const char* e = std::getenv("DMK_SKIN_VPT");
+        return e && std::atoi(e) == 4 ? 4 : 8;
+    }();
+    return v;
 }
 }  // namespace
 
-SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant, bool legacy) {
+SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant, bool legacy, int ws_vpt) {
     SkinPlan plan{};
     plan.variant = variant;
     plan.legacy = is_legacy(variant, legacy);
-    const int vpt = (variant == 1 || variant == 2) ? 4 : kVPT;
-    const int max_threads = variant == 1 ? 320 : variant == 2 ? 448 : plan.legacy ? kMaxThreads : kComputeThreads;
-    const int max_tile = max_threads * vpt;
-    plan.num_tiles = (vpad + max_tile - 1) / max_tile;
-    int tv = (vpad + plan.num_tiles - 1) / plan.num_tiles;
-    tv = (tv + kVPT - 1) / kVPT * kVPT;      // multiple of 8 for either shape
-    plan.tile_vertices = tv;
-    plan.threads = ((tv / vpt) + 31) / 32 * 32 + (plan.legacy ? 0 : 32);   // + the producer warp
     // 8 replicas make the gathers conflict free; palettes too large for that (> 226 slots; > 181 in the round-1 shape) fall back to fewer replicas
     // (and give up ring depth, down to 2 buffers, before giving up replicas)
     plan.replicas = kRepl;
@@ -629,8 +680,19 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant, bool le
     while (!plan.legacy && plan.stages > 2 && !fits()) --plan.stages;
     while (plan.replicas > 1 && !fits()) plan.replicas /= 2;
     plan.smem = skin_smem_bytes(palette_size, plan.replicas, plan.legacy, plan.stages);
+    // warp-specialised kernel, interleaved output, 8 replicas: 4 vertices per thread (two lanes per 8-vertex block) on request
+    if (ws_vpt == 0) ws_vpt = default_vpt();
+    plan.ws_vpt = (!plan.legacy && variant == 0 && plan.replicas == 8 && ws_vpt == 4) ? 4 : 8;
+    const int vpt = (variant == 1 || variant == 2) ? 4 : plan.ws_vpt;
+    const int max_threads = variant == 1 ? 320 : variant == 2 ? 448 : plan.legacy ? kMaxThreads : plan.ws_vpt == 4 ? kMaxThreads4 - 32 : kComputeThreads;
+    const int max_tile = max_threads * vpt;
+    plan.num_tiles = (vpad + max_tile - 1) / max_tile;
+    int tv = (vpad + plan.num_tiles - 1) / plan.num_tiles;
+    tv = (tv + kVPT - 1) / kVPT * kVPT;      // multiple of 8 for either shape
+    plan.tile_vertices = tv;
+    plan.threads = ((tv / vpt) + 31) / 32 * 32 + (plan.legacy ? 0 : 32);   // + the producer warp
     int occ = 1;
-    with_kernel(plan.replicas, 0, variant, legacy, [&](auto kernel) {
+    with_kernel(plan.replicas, 0, variant, legacy, plan.ws_vpt, [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, plan.threads, plan.smem) != cudaSuccess || occ < 1) occ = 1;
         return 0;
@@ -647,7 +709,7 @@ cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t 
     SkinParams q = p;
     q.num_stages = plan.stages;
     q.replicate_in_smem = plan.replicate_in_smem ? 1 : 0;
-    return with_kernel(plan.replicas, p.vertex_order_mode, plan.variant, plan.legacy, [&, p = q](auto kernel) {
+    return with_kernel(plan.replicas, p.vertex_order_mode, plan.variant, plan.legacy, plan.ws_vpt, [&, p = q](auto kernel) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (e != cudaSuccess) return e;
         if (p.replicate_in_smem) DMK_LAUNCH_CLUSTER_OF_ONE(kernel, plan.grid, plan.threads, plan.smem, stream)(p);

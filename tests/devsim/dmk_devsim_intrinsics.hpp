@@ -150,6 +150,11 @@ inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
     const int lane = static_cast<int>(threadIdx.x & 31u);
     return __shfl_sync_impl(v, lane + static_cast<int>(delta) < 32 ? lane + static_cast<int>(delta) : lane);
 }
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    const int lane = static_cast<int>(threadIdx.x & 31u);
+    return __shfl_sync_impl(v, lane ^ lane_mask);
+}
 template <class T, class U>
 inline T atomicAdd(T* p, U v) { const T o = *p; *p = static_cast<T>(o + static_cast<T>(v)); ::devsim::note_progress(); return o; }
 template <class T, class U>
@@ -220,6 +225,9 @@ inline void st_v8(float* p, const float* v) {
 inline void st_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
     const float v[8] = {a, b, c, d, e, f, g, h};
     st_v8(p, v);
+}
+inline void st_v8_if(float* p, const float* v, uint32_t take) {
+    if (take) st_v8(p, v);
 }
 inline void ld_v8(const float* p, float* v) {
     check_aligned(p, 32, "ld.global.v8.f32: address not 32-byte aligned");

@@ -6,6 +6,8 @@
 //                                   4: st.v8 per lane, lanes 96 B apart (three attribute planes of float3, 8 vertices per thread)
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_store tools/ubench_store.cu
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ void st8(float* p, float v) {
@@ -44,13 +46,30 @@ __global__ void __launch_bounds__(256) k(float* out, size_t chunks_per_block, fl
     }
 }
 
-int main() {
+int main(int argc, char** argv) {
     const size_t chunks_per_block = 1600, blocks = 148;
     const size_t bytes = blocks * chunks_per_block * 256 * 288;
     float* d;
     cudaMalloc(&d, bytes);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (argc >= 3 && !strcmp(argv[1], "sustained")) {
+        // ubench_store sustained <pattern 0 | 1 | 4> [launches]: the same launch back to back (what does the power cap leave of it?)
+        const int pat = atoi(argv[2]), launches = argc >= 4 ? atoi(argv[3]) : 600;
+        for (int a = 0; a < launches; a += 50) {
+            cudaEventRecord(e0);
+            for (int it = 0; it < 50; ++it) {
+                if (pat == 0) k<0><<<blocks, 256>>>(d, chunks_per_block, 1.f);
+                else if (pat == 1) k<1><<<blocks, 256>>>(d, chunks_per_block, 1.f);
+                else k<4><<<blocks, 256>>>(d, chunks_per_block, 1.f);
+            }
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("pattern %d launches %d-%d: %.3f ms each  %.1f GB/s\n", pat, a, a + 50, ms / 50, bytes / (ms / 50) / 1e6);
+        }
+        return 0;
+    }
     for (int pat = 0; pat < 5; ++pat) {
         float best = 1e9;
         for (int it = 0; it < 4; ++it) {
