@@ -17,3 +17,13 @@ def test_character_loop_of_every_skinning_shape_matches_the_oracle():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "skin_ring_check.py")], capture_output=True, text=True, timeout=300)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "cases match the oracle" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_four_vertices_per_thread_shape_matches_the_oracle():
+    """DMK_SKIN_VPT=4: two lanes share an 8-vertex block (the second passes its first 16 bytes to the first by shuffles so that
+    every store is a whole sector).  A diagnostic shape (measured slower, profiles/r02_skin_vpt4_experiment.jsonl); same checks."""
+    env = dict(os.environ, DMK_SKIN_VPT="4")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "skin_ring_check.py"), "--quick"], capture_output=True, text=True, timeout=300, env=env)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "cases match the oracle" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
