@@ -205,6 +205,7 @@ def test_bench_single_gpu_arm_runs_on_the_simulator(jobs):
         assert line["gpu_launches"] > 0 and line["steps"] == 3 and line["n_gpus"] == 1 and line["e2e"]["h2d_bytes_per_step"] > 0
         assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["frame_ms_rank0"]["frames"] == 3
         assert (line["cpu_baseline"] is not None) == has_cpu_baseline
+        assert line["sustained"] and "error" not in line["sustained"] and line["sustained"]["frames"] == 3, line["sustained"]
 
 
 def test_bench_two_rank_arm_runs_on_the_simulator(jobs):
