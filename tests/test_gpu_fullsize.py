@@ -47,6 +47,55 @@ def test_config3_full_size_duplicates_and_sampled_oracle():
         g.close()
 
 
+def test_config3_full_size_every_character_against_the_oracle():
+    """The whole job, not a sample: the palettes of ALL 100k characters against the oracle's (the oracle poses 100k characters in a
+    fraction of a second), and a checksum of checksums over the 18 GB of skinned vertices -- per character the float64 sum and sum of
+    squares of its 45 000 output floats, reduced on the device, against the same two numbers from the oracle's vertices, computed in
+    chunks of 4000 characters (0.7 GB of host memory at a time).  A missed tile, a stale palette or a wrong character id anywhere in
+    the launch moves a character's sums by orders of magnitude more than the rounding differences the tolerance allows."""
+    import torch
+    from tests import devmem
+    n, verts = 100_000, 5000
+    skel = synth.make_skeleton(67)
+    clips = [synth.make_clip(skel, f"clip{i}", seed=i, duration=1.5) for i in range(8)]
+    a = common.Assets(skel, clips, synth.make_armature(skel), synth.make_mesh(verts, 67))
+    g, o = GpuRig(a), OracleRig(a)
+    try:
+        # the mesh order bench.py measures (clustered by bone; the sampled test above keeps the caller's): sums over a character's
+        # vertices do not depend on the order they are stored in
+        g.mesh.close()
+        g.mesh = capi.Mesh(g.ctx, a.mesh.pos, a.mesh.nrm, a.mesh.tan, a.mesh.indices, a.mesh.weights, g.arm.palette_size, flags=capi.MESH_CLUSTER_BONES)
+        cr = synth.make_crowd(n, 2, len(clips), seed=7)
+        crowd = g.crowd(n, 2)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, threshold=FLT_MIN)
+        crowd.step(0.0, capi.STEP_POSE | capi.STEP_SKIN)
+        g.ctx.sync()
+        vp = g.mesh.vertex_pitch
+        dev = torch.as_tensor(devmem._Dev(crowd.skinned_dev(), (n, vp, 9), "<f4"), device=torch.device("cuda", 0))
+        chunk = 4000
+        got_sum, got_sq = np.empty(n), np.empty(n)
+        for c0 in range(0, n, chunk):   # float64 on the device, one chunk at a time (a chunk is 1.4 GB as float64)
+            x = dev[c0:c0 + chunk, :verts].double()
+            got_sum[c0:c0 + chunk] = x.sum(dim=(1, 2)).cpu().numpy()
+            got_sq[c0:c0 + chunk] = (x * x).sum(dim=(1, 2)).cpu().numpy()
+            del x
+        worst_pal = 0.0
+        for c0 in range(0, n, chunk):
+            c1 = min(n, c0 + chunk)
+            ref = o.crowd(c1 - c0, 2).step(cr.clip[:, c0:c1], cr.ratio[:, c0:c1], cr.weight[:, c0:c1], FLT_MIN, mesh=a.mesh, want=("palette", "skinned"))
+            assert_close(crowd.get_palette(c0, c1 - c0), ref["palette"], f"palettes of characters {c0}..{c1}")
+            r = ref["skinned"].astype(np.float64)
+            ref_sum, ref_sq = r.sum(axis=(1, 2)), (r * r).sum(axis=(1, 2))
+            # every output float is within 1e-5 relative | 1e-6 absolute of the oracle's (tests/common.assert_close), so the sums are
+            # within that times the sum of magnitudes; the rounding differences are unbiased, so a tenth of that bound still has three
+            # orders of magnitude of slack (measured: 4e-4 of the full bound) while ONE misplaced 8-vertex block exceeds it 300 times
+            mag = np.abs(r).sum(axis=(1, 2))
+            assert np.all(np.abs(got_sum[c0:c1] - ref_sum) <= 1e-6 * mag + 1e-7 * r[0].size), f"vertex checksum of a character in {c0}..{c1}"
+            assert np.all(np.abs(got_sq[c0:c1] - ref_sq) <= 3e-6 * ref_sq + 1e-5), f"vertex energy of a character in {c0}..{c1}"
+    finally:
+        g.close()
+
+
 def test_config5_full_size_permutation_and_prefix_oracle():
     import torch
     n = 10_000_000
