@@ -74,6 +74,7 @@ SIGNATURES = [
     ("dmk_mesh_create_ex", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u32, C.POINTER(_vp)]),
     ("dmk_mesh_vertex_order", _i, [_vp, _vp]),
     ("dmk_mesh_cluster_stats", _i, [_vp, _vp, _i, _i, _vp, C.POINTER(_i64)]),
+    ("dmk_mesh_cluster_layout", _i, [_i, _i, C.POINTER(_i64)]),
     ("dmk_mesh_destroy", None, [_vp]),
     ("dmk_mesh_num_vertices", _i, [_vp]),
     ("dmk_mesh_vertex_pitch", _i, [_vp]),
@@ -620,6 +621,25 @@ def mesh_cluster_stats(indices, weights, palette_size):
         raise DmkError(st, lib().dmk_last_error(None).decode())
     keys = ("gather_wavefronts", "gather_wavefronts_caller_order", "shared_blocks", "total_blocks")
     return order, dict(zip(keys, [int(x) for x in out]))
+
+
+def mesh_cluster_blocks(num_vertices, palette_size):
+    """dmk_mesh_cluster_layout (works without a device): (vertex pitch, [blocks][8] stored positions each skinning thread owns)"""
+    out = (C.c_int64 * 3)()
+    st = lib().dmk_mesh_cluster_layout(num_vertices, palette_size, out)
+    if st:
+        raise DmkError(st, lib().dmk_last_error(None).decode())
+    pitch, strided, tile = int(out[0]), int(out[1]), int(out[2])
+    if not strided:
+        return pitch, np.arange(pitch, dtype=np.int64).reshape(-1, 8)
+    blocks = []
+    for begin in range(0, pitch, tile):
+        tile_blocks = min(tile, pitch - begin) // 8
+        for p in range(tile_blocks):
+            w, l = divmod(p, 32)
+            nl = min(32, tile_blocks - 32 * w)
+            blocks.append([begin + 256 * w + k * nl + l for k in range(8)])
+    return pitch, np.array(blocks, np.int64)
 
 
 def skin_plan(vertex_pitch, palette_size=68, num_sms=148, layout=0):

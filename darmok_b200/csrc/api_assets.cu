@@ -333,18 +333,40 @@ dmk_status dmk_mesh_cluster_stats(const float* indices, const float* weights, in
     std::vector<ClusterInfluence> infl;
     std::string err;
     if (!vertex_influences(indices, weights, num_vertices, palette_size, infl, err)) return fail(nullptr, DMK_ERR_INVALID, err);
-    const int vpad = (num_vertices + 7) / 8 * 8;
+    int vpad = (num_vertices + 7) / 8 * 8;
     SkinPlan plan{};
     if (vpad > 0) {
-        plan = plan_skin(vpad, palette_size, 148, 0);
+        const int vpad64 = (num_vertices + 63) / 64 * 64;
+        plan = plan_skin(vpad64, palette_size, 148, 0);   // the bulk-store output path wants a pitch that is a multiple of 64
+        if (plan.strided_store) vpad = vpad64;
+        else plan = plan_skin(vpad, palette_size, 148, 0);
         cudaGetLastError();   // without a device the occupancy query fails; the tile shape does not depend on it
     }
-    const ClusterResult cl = cluster_mesh(infl, plan.num_tiles, plan.tile_vertices, plan.ws_vpt == 4 ? 16 : 32);
+    const ClusterResult cl = plan.strided_store ? cluster_mesh_strided(infl, vpad, plan.num_tiles, plan.tile_vertices)
+                                                : cluster_mesh(infl, plan.num_tiles, plan.tile_vertices, plan.ws_vpt == 4 ? 16 : 32);
     if (out_order) std::copy(cl.order.begin(), cl.order.begin() + num_vertices, out_order);
     out_stats4[0] = cl.gather_wavefronts;
     out_stats4[1] = cl.gather_wavefronts_unclustered;
     out_stats4[2] = cl.shared_blocks;
     out_stats4[3] = cl.total_blocks;
+    return DMK_OK;
+}
+
+dmk_status dmk_mesh_cluster_layout(int num_vertices, int palette_size, int64_t* out_layout3) {
+    if (num_vertices < 0 || !out_layout3 || palette_size < 1 || palette_size > kMaxPalette)
+        return fail(nullptr, DMK_ERR_INVALID, "dmk_mesh_cluster_layout: argument out of range");
+    int vpad = (num_vertices + 7) / 8 * 8;
+    SkinPlan plan{};
+    if (vpad > 0) {
+        const int vpad64 = (num_vertices + 63) / 64 * 64;
+        plan = plan_skin(vpad64, palette_size, 148, 0);
+        if (plan.strided_store) vpad = vpad64;
+        else plan = plan_skin(vpad, palette_size, 148, 0);
+        cudaGetLastError();
+    }
+    out_layout3[0] = vpad;
+    out_layout3[1] = plan.strided_store ? 1 : 0;
+    out_layout3[2] = plan.tile_vertices;
     return DMK_OK;
 }
 
@@ -359,7 +381,15 @@ dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const fl
     mesh->ctx = ctx;
     mesh->num_vertices = num_vertices;
     mesh->palette_size = palette_size;
-    const int vpad = (num_vertices + 7) / 8 * 8;
+    int vpad = (num_vertices + 7) / 8 * 8;
+    // clustered by bone: the vertex pitch becomes a multiple of 64 when the skinning plan offers the bulk-store output path for it
+    SkinPlan cluster_plan{};
+    if ((flags & DMK_MESH_CLUSTER_BONES) && num_vertices > 0) {
+        const int vpad64 = (num_vertices + 63) / 64 * 64;
+        cluster_plan = plan_skin(vpad64, palette_size, ctx->num_sms, 0);
+        if (cluster_plan.strided_store) vpad = vpad64;
+        else cluster_plan = plan_skin(vpad, palette_size, ctx->num_sms, 0);
+    }
     mesh->vpad = vpad;
     std::vector<float> pos(static_cast<size_t>(vpad) * 3, 0.f), nrm(pos.size(), 0.f), tan(pos.size(), 0.f);
     std::vector<float> w(static_cast<size_t>(vpad) * 4, 0.f);
@@ -401,8 +431,10 @@ dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const fl
     }
     std::vector<ClusterInfluence> stored;
     if (flags & DMK_MESH_CLUSTER_BONES) {
-        const SkinPlan plan = plan_skin(vpad, palette_size, ctx->num_sms, 0);
-        ClusterResult cl = cluster_mesh(infl, plan.num_tiles, plan.tile_vertices, plan.ws_vpt == 4 ? 16 : 32);
+        const SkinPlan& plan = cluster_plan;
+        ClusterResult cl = plan.strided_store ? cluster_mesh_strided(infl, vpad, plan.num_tiles, plan.tile_vertices)
+                                              : cluster_mesh(infl, plan.num_tiles, plan.tile_vertices, plan.ws_vpt == 4 ? 16 : 32);
+        mesh->strided = plan.strided_store;
         mesh->order.assign(cl.order.begin(), cl.order.begin() + num_vertices);   // padding sits behind the last real vertex
         stored = std::move(cl.stored);
         mesh->clustered = true;
@@ -414,7 +446,13 @@ dmk_status dmk_mesh_create_ex(dmk_context_t ctx, const float* position, const fl
     for (int s = 0; s < vpad; ++s) {
         float* wv = &w[static_cast<size_t>(s) * 4];
         wv[0] = 1.f;  // padding: 1 * identity
-        if (s >= num_vertices) continue;
+        if (s >= num_vertices) {
+            if (mesh->strided) {   // padding inside a short block: 0 * the block's bone (no gather, no mixed-block path; output 0 either way)
+                wv[0] = 0.f;
+                slots[s] = stored[static_cast<size_t>(s)].slot[0];
+            }
+            continue;
+        }
         const int v = mesh->order[static_cast<size_t>(s)];
         for (int k = 0; k < 3; ++k) {
             pos[static_cast<size_t>(s) * 3 + k] = position[static_cast<size_t>(v) * 3 + k];

@@ -756,7 +756,7 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
             p.palette_size = c->mesh->palette_size;
             p.num_tiles = c->plan.num_tiles;
             p.tile_vertices = c->plan.tile_vertices;
-            p.vertex_order_mode = c->mesh->clustered ? 2 : c->mesh->sorted ? 1 : 0;
+            p.vertex_order_mode = c->mesh->strided ? 3 : c->mesh->clustered ? 2 : c->mesh->sorted ? 1 : 0;
             {
                 KernelTimer timer(ctx, DMK_KERNEL_SKIN);
                 SkinPlan plan = c->plan;
@@ -779,7 +779,7 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
             q.palette_size = x.mesh->palette_size;
             q.num_tiles = x.plan.num_tiles;
             q.tile_vertices = x.plan.tile_vertices;
-            q.vertex_order_mode = x.mesh->clustered ? 2 : x.mesh->sorted ? 1 : 0;
+            q.vertex_order_mode = x.mesh->strided ? 3 : x.mesh->clustered ? 2 : x.mesh->sorted ? 1 : 0;
             {
                 KernelTimer timer(ctx, DMK_KERNEL_SKIN);
                 SkinPlan plan = x.plan;

@@ -100,6 +100,7 @@ struct dmk_mesh_s {
     bool sorted = false;
     int sort_block = 0;          // vertices per thread the influence grouping was dealt for (8 or 4)
     bool clustered = false;      // DMK_MESH_CLUSTER_BONES: every 8-vertex block names its common bone in entry 0 of its first vertex
+    bool strided = false;        // ... stored in the strided layout of the bulk-store output path (cluster_mesh_strided; pitch a multiple of 64)
     int64_t cluster_gather_wavefronts = 0;
     int cluster_shared_blocks = 0;
 };

@@ -109,6 +109,19 @@ __device__ __forceinline__ void bulk_s2s(void* dst_smem, const void* src_smem, u
                  : "memory");
 }
 
+// bulk copy shared -> global (the skinning kernel's output path): issued by one thread, tracked in that thread's bulk groups
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem_addr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory (st.shared) made visible to the async proxy (bulk copies) of this CTA
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
 // ---- wide global / shared accesses --------------------------------------------------------------------------------
 __device__ __forceinline__ void st_v8(float* p, const float* v) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),

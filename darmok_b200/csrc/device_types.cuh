@@ -110,6 +110,7 @@ struct SkinParams {
     int num_stages;           // staging depth of the producer warp's bulk copies (set by launch_skin from the plan)
     int vertex_order_mode;    // 0 caller's order; 1 grouped by influence count: the gathers of absent influences are predicated off;
                               // 2 clustered by bone (DMK_MESH_CLUSTER_BONES): also the block's bone once per thread and character
+                              // 3 clustered by bone in the STRIDED layout (cluster_mesh_strided): also the bulk-store output path
 };
 
 struct CullParams {

@@ -37,6 +37,7 @@ struct SkinPlan {
     bool legacy;        // the round-1 kernel shape (every warp replicates and skins) instead of producer warp + compute warps
     int variant;        // 0: interleaved [V][9] output, 8 vertices per thread; 1 / 2: planar [9][V] output, 4 per thread, <= 320 / 448 threads;
                         // 3: three float3 streams [3][V][3], 8 per thread; 4: planar [9][V], 8 per thread
+    bool strided_store; // the bulk-store output path is available for this shape (used when the mesh is stored for it: vertex_order_mode 3)
     int ws_vpt;         // vertices per thread of the warp-specialised kernel: 8, or 4 (two lanes per 8-vertex block; variant 0 with 8 replicas only)
 };
 // ws_vpt: 8 or 4, 0 = the default (8, or what the environment variable DMK_SKIN_VPT says)

@@ -39,4 +39,10 @@ struct ClusterResult {
 // share a block: the 4-vertices-per-thread shape); the gather statistics count the extra block-bone reads of the latter.
 ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tiles, int tile_vertices, int blocks_per_warp = 32);
 
+// The same for the STRIDED ownership of the skinning kernel's bulk-store output path: thread (warp w, lane l) of a tile owns the stored
+// vertices tile_begin + 256 w + k nl + l (k = 0..7; nl = 32, or the lanes in use in the tile's last warp), so that round k of a warp
+// is nl consecutive vertices.  `vpad` (vertex pitch) and `tile_vertices` are multiples of 64; positions >= in.size() are padding
+// (order = -1; they name their block's bone with weight 0: no gather, output 0).
+ClusterResult cluster_mesh_strided(const std::vector<ClusterInfluence>& in, int vpad, int num_tiles, int tile_vertices);
+
 }  // namespace dmk

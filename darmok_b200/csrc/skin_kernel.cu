@@ -279,6 +279,11 @@ __global__ void __launch_bounds__(MAXT, 1) skin_kernel(const SkinParams p) {
 //     SKIP (absent influences are predicated off, whole quarter-warps at a time) the gathers drop from 96 to ~51 LDS.128
 //     per thread and character (dmk_mesh_cluster_stats), which takes the kernel off the L1 data pipe.
 // LAYOUT: 0 interleaved [V][9], 3 three float3 streams [3][V][3], 4 nine planes [9][V]  (DMK_OPT_SKIN_PLANAR_OUTPUT values).
+#ifndef DMK_SKIN_OUT_BUFS
+#define DMK_SKIN_OUT_BUFS 8
+#endif
+constexpr int kOutBufs = DMK_SKIN_OUT_BUFS;   // staging buffers per compute warp of the bulk-store output path (a divisor of 8).  With 2 the warp
+// waits for the copy of two rounds ago to have READ its buffer, which takes longer than two rounds (5.95 ms per launch, measured)
 constexpr int kMaxRing = 4;   // replica ring of the warp-specialised kernel (SkinParams::num_stages: 4, fewer where shared memory is short).
 // MEASURED (profiles/r02_skin_ring_sleep_experiment.jsonl): rings of 5 and 6 buffers, and a producer that sleeps between the polls of
 // the "empty" barrier (its spin is 13 % of the warp instructions the kernel executes, one lane each) change neither the burst
@@ -299,10 +304,21 @@ __host__ __device__ inline uint32_t replica_stride(int palette_size) { return (u
 // wavefront).  4 x 36 B = 144 B is 4.5 sectors: the second lane passes its first 16 bytes to the first one by 4 shuffles, which
 // then writes 5 whole sectors, the second lane 4.  Half the registers per thread (13 x 4 bind-pose values instead of 13 x 8),
 // so 10 compute warps per SM instead of 7 (MAXT = 352).  Measured slower than 8 vertices per thread (see kMaxThreads4).
-template <int REPL, bool SKIP, bool SHARE, int LAYOUT, int VPT = 8, int MAXT = kMaxThreads>
+//
+// STRIDED (round 2, the bulk-store output path; meshes stored by cluster_mesh_strided): thread (warp w, lane l) owns the stored vertices
+// tile_begin + 256 w + k nl + l, k = 0..7 (nl = lanes of the warp that have vertices), so round k of a warp is nl consecutive
+// vertices = nl x 36 contiguous bytes of the output.  The lanes write them to a per-warp staging buffer in shared memory (9 x STS.32,
+// stride 9 words: conflict free) and ONE cp.async.bulk shared -> global per round sends them (two buffers per warp: the copy of round
+// k - 2 must have finished READING its buffer before round k overwrites it).  No st.global, no register staging of whole sectors, and
+// the output leaves as full 128-byte lines instead of 32 scattered sectors per store instruction.  tools/ubench_out_path.cu: with the
+// clustered mesh's ~6 gathers per vertex the memory side alone runs 3.21 ms with st.global.v8 and 2.99 ms this way (with the 12
+// gathers of the caller's order it is the other way round: the bulk copies' reads compete with the gathers, 4.17 against 3.40 ms).
+// In the kernel it LOSES (5.95 against 3.55 ms): see strided_enabled() below.  Opt-in, DMK_SKIN_BULK_STORE=1.
+template <int REPL, bool SKIP, bool SHARE, int LAYOUT, int VPT = 8, int MAXT = kMaxThreads, bool STRIDED = false>
 __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
     static_assert(LAYOUT == 0 || LAYOUT == 3 || LAYOUT == 4, "interleaved, three streams or nine planes");
     static_assert(VPT == 8 || (VPT == 4 && LAYOUT == 0), "4 vertices per thread: interleaved output only");
+    static_assert(!STRIDED || (VPT == 8 && LAYOUT == 0), "bulk-store output path: interleaved output, 8 vertices per thread");
     constexpr int kVPT = VPT;
     constexpr bool STREAMS = LAYOUT == 3, PLANAR = LAYOUT == 4;
     DMK_DYNAMIC_SMEM(smem, 128);
@@ -315,6 +331,8 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
     uint64_t* s_full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)ring * buf_bytes);   // [kMaxRing] bulk copies -> compute warps
     uint64_t* s_empty_bar = s_full_bar + kMaxRing;                       // [kMaxRing] compute warps -> producer
     uint64_t* s_stage_bar = s_empty_bar + kMaxRing;                      // [kMaxRing] shared-memory replication: replica 0 has arrived
+    // (STRIDED) [compute warps][kOutBufs][32 x 36 B], on a 128-byte boundary of the block's shared memory
+    unsigned char* s_out = smem + (((size_t)ring * buf_bytes + 8 * 3 * kMaxRing + 127) & ~(size_t)127);
     const bool s2s = p.replicate_in_smem != 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -398,14 +416,18 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
         // the 8-vertex block of the tile this lane works on, and which half of it (VPT = 4: lanes L and L ^ 8 share a block)
         const int blk = VPT == 8 ? tid : warp * 16 + ((lane >> 4) << 3) + (lane & 7);
         const int half = VPT == 8 ? 0 : (lane >> 3) & 1;
-        const int v0 = tile * p.tile_vertices + blk * 8 + half * 4;
-        const bool active = blk * 8 < p.tile_vertices && v0 < p.vpad;
+        // STRIDED: nl = lanes of this warp that have vertices (a multiple of 8: tiles and the vertex pitch are multiples of 64)
+        const int tile_verts = min(p.tile_vertices, p.vpad - tile * p.tile_vertices);
+        const int nl = STRIDED ? max(0, min(32, tile_verts / 8 - 32 * warp)) : 0;
+        const int v0 = STRIDED ? tile * p.tile_vertices + warp * 256 + lane : tile * p.tile_vertices + blk * 8 + half * 4;
+        const int vstep = STRIDED ? nl : 1;
+        const bool active = STRIDED ? lane < nl : (blk * 8 < p.tile_vertices && v0 < p.vpad);
         float px[kVPT], py[kVPT], pz[kVPT], nx[kVPT], ny[kVPT], nz[kVPT], tx[kVPT], ty[kVPT], tz[kVPT];
         float w0[kVPT], w1[kVPT], w2[kVPT], w3[kVPT];
         uint32_t slots[kVPT];
 #pragma unroll
         for (int v = 0; v < kVPT; ++v) {
-            const int vi = active ? v0 + v : 0;
+            const int vi = active ? v0 + v * vstep : 0;
             px[v] = __ldg(p.pos + (size_t)vi * 3 + 0); py[v] = __ldg(p.pos + (size_t)vi * 3 + 1); pz[v] = __ldg(p.pos + (size_t)vi * 3 + 2);
             nx[v] = __ldg(p.nrm + (size_t)vi * 3 + 0); ny[v] = __ldg(p.nrm + (size_t)vi * 3 + 1); nz[v] = __ldg(p.nrm + (size_t)vi * 3 + 2);
             tx[v] = __ldg(p.tan + (size_t)vi * 3 + 0); ty[v] = __ldg(p.tan + (size_t)vi * 3 + 1); tz[v] = __ldg(p.tan + (size_t)vi * 3 + 2);
@@ -418,7 +440,8 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
         // the block's bone: entry 0 of the block's FIRST vertex (the other half's vertex 0 for the second lane of a pair)
         const uint32_t block_slot = (VPT == 4 && half && active ? __ldg(p.slots + v0 - 4) : slots[0]) & 0xffu;
         // VPT = 4: the whole warp runs the item when any lane has vertices (the pair's shuffles need both lanes), stores are predicated
-        const bool warp_active = VPT == 8 ? active : __ballot_sync(0xffffffffu, active) != 0u;
+        const bool warp_active = (VPT == 8 && !STRIDED) ? active : __ballot_sync(0xffffffffu, active) != 0u;
+        const uint32_t stage_base = STRIDED ? smem_u32(s_out) + (uint32_t)warp * (kOutBufs * 1152u) + (uint32_t)lane * 36u : 0u;
         const uint32_t st_first = active && half == 0, st_second = active && half == 1;
 #pragma unroll
         for (int v = 0; v < kVPT; ++v) {
@@ -544,7 +567,24 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
                         res[STREAMS ? kVPT * 3 + v * 3 + r : v * 9 + 3 + r] = fmaf(m2[r], nz[v], fmaf(m1[r], ny[v], m0[r] * nx[v]));
                         res[STREAMS ? kVPT * 6 + v * 3 + r : v * 9 + 6 + r] = fmaf(m2[r], tz[v], fmaf(m1[r], ty[v], m0[r] * tx[v]));
                     }
-                    if (LAYOUT == 0 && VPT == 8) {   // flush every 32-byte sector that just became complete
+                    if (STRIDED) {
+                        // round v of this warp: nl consecutive vertices.  Buffer v % kOutBufs was last read by the bulk copy issued kOutBufs
+                        // rounds ago (with a buffer per round: by the same round of the previous character)
+                        const uint32_t buf = stage_base + (uint32_t)(v % kOutBufs) * 1152u;
+                        if (lane == 0) bulk_wait_read<kOutBufs - 1>();
+                        __syncwarp();
+                        if (active) {
+#pragma unroll
+                            for (int c = 0; c < 9; ++c) sts32(buf + 4u * c, res[v * 9 + c]);
+                        }
+                        fence_proxy_async_smem();   // the lanes' writes, before the async proxy reads them
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_s2g(p.out + ((size_t)cid * p.vpad + (size_t)(tile * p.tile_vertices + warp * 256 + v * nl)) * 9, buf, (uint32_t)nl * 36u);
+                            bulk_commit();
+                        }
+                    }
+                    if (LAYOUT == 0 && VPT == 8 && !STRIDED) {   // flush every 32-byte sector that just became complete
                         float* out = p.out + ((size_t)cid * p.vpad + v0) * 9;
 #pragma unroll
                         for (int sct = (v * 9) / 8; sct < ((v + 1) * 9) / 8; ++sct) st_v8(out + sct * 8, res + sct * 8);
@@ -595,6 +635,7 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
             if (++rb == (uint32_t)ring) { rb = 0; rphase ^= 1u; }
         }
     }
+    if (STRIDED && lane == 0) bulk_wait_all();   // the staging buffers must outlive the copies that read them
 }
 
 }  // namespace
@@ -610,9 +651,10 @@ constexpr int kComputeThreads = kMaxThreads - 32;   // warp-specialised shape: t
 constexpr int kMaxThreads4 = 352;
 // legacy: the round-1 kernel (every warp replicates and skins); the VPT = 4 layouts (1, 2) only exist in that shape
 bool is_legacy(int variant, bool legacy) { return legacy || variant == 1 || variant == 2; }
-size_t skin_smem_bytes(int palette_size, int repl, bool legacy, int ring = kMaxRing) {
+constexpr size_t kOutStageBytes = (size_t)(kComputeThreads / 32) * kOutBufs * 1152;   // bulk-store output path: kOutBufs rounds of 32 vertices per compute warp
+size_t skin_smem_bytes(int palette_size, int repl, bool legacy, int ring = kMaxRing, bool strided = false) {
     if (legacy) return (size_t)palette_size * (48 * kNumRepl * repl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
-    return (size_t)replica_stride(palette_size) * repl * ring + 8 * 3 * kMaxRing + 16;
+    return (size_t)replica_stride(palette_size) * repl * ring + 8 * 3 * kMaxRing + 16 + (strided ? kOutStageBytes + 128 : 0);
 }
 template <typename F>
 auto with_legacy_kernel(int repl, bool skip, int variant, F&& f) {
@@ -630,14 +672,16 @@ auto with_legacy_kernel(int repl, bool skip, int variant, F&& f) {
 }
 // mode: 0 caller's vertex order, 1 influence-sorted (predicated gathers), 2 clustered by bone (block bone in registers + predicated gathers)
 template <int LAYOUT, typename F>
-auto with_ws_layout(int repl, int mode, int vpt, F&& f) {
+auto with_ws_layout(int repl, int mode, int vpt, bool strided, F&& f) {
     if constexpr (LAYOUT == 0) {
+        if (repl == 8 && vpt == 8 && strided && mode == 3) return f(skin_ws_kernel<8, true, true, 0, 8, kMaxThreads, true>);
         if (repl == 8 && vpt == 4) {
             if (mode == 2) return f(skin_ws_kernel<8, true, true, 0, 4, kMaxThreads4>);
             if (mode == 1) return f(skin_ws_kernel<8, true, false, 0, 4, kMaxThreads4>);
             return f(skin_ws_kernel<8, false, false, 0, 4, kMaxThreads4>);
         }
     }
+    if (mode == 3) mode = 2;   // a mesh stored for the bulk-store path under another kernel: clustered semantics hold on any order
     if (repl == 8) {
         if (mode == 2) return f(skin_ws_kernel<8, true, true, LAYOUT>);
         if (mode == 1) return f(skin_ws_kernel<8, true, false, LAYOUT>);
@@ -653,11 +697,24 @@ auto with_ws_layout(int repl, int mode, int vpt, F&& f) {
     }
 }
 template <typename F>
-auto with_kernel(int repl, int mode, int variant, bool legacy, int vpt, F&& f) {
+auto with_kernel(int repl, int mode, int variant, bool legacy, int vpt, bool strided, F&& f) {
     if (is_legacy(variant, legacy)) return with_legacy_kernel(repl, mode != 0, variant, f);
-    if (variant == 3) return with_ws_layout<3>(repl, mode, vpt, f);
-    if (variant == 4) return with_ws_layout<4>(repl, mode, vpt, f);
-    return with_ws_layout<0>(repl, mode, vpt, f);
+    if (variant == 3) return with_ws_layout<3>(repl, mode, vpt, strided, f);
+    if (variant == 4) return with_ws_layout<4>(repl, mode, vpt, strided, f);
+    return with_ws_layout<0>(repl, mode, vpt, strided, f);
+}
+// The bulk-store output path is OFF unless DMK_SKIN_BULK_STORE=1 is in the environment.  MEASURED (profiles/r02_skin_bulk_store_experiment.txt):
+// correct on hardware, but 5.95 ms per launch against 3.55 ms, whatever the staging depth (2, 4 or 8 buffers per warp).  The bulk-copy
+// engine of an SM moves about 23 bytes per clock in total (tools/ubench_out_path.cu mode 2: 64.5 KB of stores per 2770 clocks; the
+// shared->shared copies of tools/ubench_s2s.cu: 15 B/clock): the 8 palette replicas (35 KB per character and block) already take half
+// of that, and 60 KB of output on top need 4300 clocks per character where the whole item has 3400.  The microbenchmark that promised
+// 2.99 against 3.21 ms had no palette copies in it.  Kept as a diagnostic (and as the record of why the output leaves through st.global).
+bool strided_enabled() {
+    static const bool v = [] {
+        const char* e = std::getenv("DMK_SKIN_BULK_STORE");
+        return e && std::atoi(e) == 1;
+    }();
+    return v;
 }
 int default_vpt() {
     static const int v = [] {
@@ -683,16 +740,22 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant, bool le
     // warp-specialised kernel, interleaved output, 8 replicas: 4 vertices per thread (two lanes per 8-vertex block) on request
     if (ws_vpt == 0) ws_vpt = default_vpt();
     plan.ws_vpt = (!plan.legacy && variant == 0 && plan.replicas == 8 && ws_vpt == 4) ? 4 : 8;
+    // bulk-store output path (meshes stored by cluster_mesh_strided): interleaved output, 8 replicas, pitch a multiple of 64 (a warp's
+    // lanes in use are then a multiple of 8, so every round -- lanes x 36 bytes -- starts and ends on a 32-byte sector)
+    plan.strided_store = !plan.legacy && variant == 0 && plan.replicas == 8 && plan.ws_vpt == 8 && vpad % 64 == 0 && strided_enabled() &&
+                         skin_smem_bytes(palette_size, plan.replicas, false, plan.stages, true) <= kMaxSmem;
+    if (plan.strided_store) plan.smem = skin_smem_bytes(palette_size, plan.replicas, false, plan.stages, true);
     const int vpt = (variant == 1 || variant == 2) ? 4 : plan.ws_vpt;
     const int max_threads = variant == 1 ? 320 : variant == 2 ? 448 : plan.legacy ? kMaxThreads : plan.ws_vpt == 4 ? kMaxThreads4 - 32 : kComputeThreads;
     const int max_tile = max_threads * vpt;
     plan.num_tiles = (vpad + max_tile - 1) / max_tile;
     int tv = (vpad + plan.num_tiles - 1) / plan.num_tiles;
     tv = (tv + kVPT - 1) / kVPT * kVPT;      // multiple of 8 for either shape
+    if (plan.strided_store) tv = (tv + 63) / 64 * 64;   // every warp's lanes in use are a multiple of 8: rounds are whole sectors
     plan.tile_vertices = tv;
     plan.threads = ((tv / vpt) + 31) / 32 * 32 + (plan.legacy ? 0 : 32);   // + the producer warp
     int occ = 1;
-    with_kernel(plan.replicas, 0, variant, legacy, plan.ws_vpt, [&](auto kernel) {
+    with_kernel(plan.replicas, plan.strided_store ? 3 : 0, variant, legacy, plan.ws_vpt, plan.strided_store, [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, plan.threads, plan.smem) != cudaSuccess || occ < 1) occ = 1;
         return 0;
@@ -709,7 +772,7 @@ cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t 
     SkinParams q = p;
     q.num_stages = plan.stages;
     q.replicate_in_smem = plan.replicate_in_smem ? 1 : 0;
-    return with_kernel(plan.replicas, p.vertex_order_mode, plan.variant, plan.legacy, plan.ws_vpt, [&, p = q](auto kernel) {
+    return with_kernel(plan.replicas, p.vertex_order_mode, plan.variant, plan.legacy, plan.ws_vpt, plan.strided_store, [&, p = q](auto kernel) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         if (e != cudaSuccess) return e;
         if (p.replicate_in_smem) DMK_LAUNCH_CLUSTER_OF_ONE(kernel, plan.grid, plan.threads, plan.smem, stream)(p);

@@ -139,6 +139,13 @@ DMK_API dmk_status dmk_mesh_vertex_order(dmk_mesh_t mesh, int32_t* out_order);
  * `indices` / `weights` as for dmk_mesh_create. */
 DMK_API dmk_status dmk_mesh_cluster_stats(const float* indices, const float* weights, int num_vertices, int palette_size,
                                           int32_t* out_order, int64_t* out_stats4);
+/* How DMK_MESH_CLUSTER_BONES stores a mesh of num_vertices vertices (no device needed): out_layout[0] = vertex pitch (what
+ * dmk_mesh_vertex_pitch will report: num_vertices rounded up to 8, or to 64 for the layout below), [1] = 1 when the blocks are
+ * STRIDED, [2] = vertices per tile of the skinning plan.  A block is what one thread of the skinning kernel owns.  Plain layout:
+ * 8 consecutive stored vertices.  Strided layout (the kernel's bulk-store output path: a warp's round of vertices is one contiguous
+ * piece of the output): inside a tile, the thread (warp w, lane l) owns positions tile_begin + 256 w + k nl + l, k = 0..7, with
+ * nl = min(32, blocks of the tile - 32 w). */
+DMK_API dmk_status dmk_mesh_cluster_layout(int num_vertices, int palette_size, int64_t* out_layout3);
 DMK_API void dmk_mesh_destroy(dmk_mesh_t mesh);
 DMK_API int dmk_mesh_num_vertices(dmk_mesh_t mesh);
 DMK_API int dmk_mesh_vertex_pitch(dmk_mesh_t mesh); /* vertices per character in the skinned buffer (V rounded up to 8) */

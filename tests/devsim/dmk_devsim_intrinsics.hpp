@@ -16,6 +16,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <unordered_map>
+#include <vector>
 #include <functional>
 #include <tuple>
 #include <type_traits>
@@ -213,6 +216,39 @@ inline void bulk_s2s(void* dst_smem, const void* src_smem, uint32_t bytes, uint6
         ::devsim::trap("cp.async.bulk (shared -> shared): size and both addresses must be multiples of 16");
     ::devsim::bulk_copy(::devsim::smem_pointer(::devsim::smem_offset(dst_smem), bytes), ::devsim::smem_pointer(::devsim::smem_offset(src_smem), bytes),
                         bytes, reinterpret_cast<::devsim::MBar*>(bar));
+}
+
+// bulk copies shared -> global, per issuing thread: an open group, committed groups, and the copy itself performed LAZILY -- when a
+// wait says its source has been read -- so that a buffer overwritten before the matching wait shows as a wrong result
+struct PendingStore { void* dst; uint32_t src; uint32_t bytes; };
+struct StoreQueue { std::vector<PendingStore> open; std::deque<std::vector<PendingStore>> committed; };
+inline std::unordered_map<unsigned, StoreQueue>& store_queues() { static std::unordered_map<unsigned, StoreQueue> q; return q; }
+inline void bulk_s2g(void* dst_gmem, uint32_t src_smem_addr, uint32_t bytes) {
+    if (bytes % 16 || src_smem_addr % 16 || reinterpret_cast<uintptr_t>(dst_gmem) % 16)
+        ::devsim::trap("cp.async.bulk (shared -> global): size and both addresses must be multiples of 16");
+    ::devsim::smem_pointer(src_smem_addr, bytes);   // bounds
+    store_queues()[threadIdx.x].open.push_back({dst_gmem, src_smem_addr, bytes});
+}
+inline void bulk_commit() {
+    StoreQueue& q = store_queues()[threadIdx.x];
+    q.committed.push_back(std::move(q.open));
+    q.open.clear();
+}
+inline void bulk_drain(size_t keep) {
+    StoreQueue& q = store_queues()[threadIdx.x];
+    while (q.committed.size() > keep) {
+        for (const PendingStore& c : q.committed.front()) std::memcpy(c.dst, ::devsim::smem_pointer(c.src, c.bytes), c.bytes);
+        q.committed.pop_front();
+        ::devsim::note_progress();
+    }
+}
+template <int N>
+inline void bulk_wait_read() { bulk_drain(N); }
+inline void bulk_wait_all() { bulk_drain(0); }
+inline void fence_proxy_async_smem() {}
+inline void sts32(uint32_t addr, float v) {
+    if (addr % 4) ::devsim::trap("st.shared.f32: address not 4-byte aligned");
+    std::memcpy(::devsim::smem_pointer(addr, 4), &v, 4);
 }
 
 inline void check_aligned(const void* p, size_t a, const char* what) {

@@ -37,6 +37,7 @@ def main():
     for num_vertices in (1, 4, 7, 9, 1249, 1256, 1281, 1792, 1793, 5000, 6007):
         mesh_s = synth.make_mesh(num_vertices, 67, seed=num_vertices, unskinned_fraction=0.02)
         mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size)
+        vpad = mesh.vertex_pitch
         n = 7 if num_vertices > 3000 else 37
         cr = synth.make_crowd(n, 2, len(base.clips), seed=num_vertices)
         inst = synth.make_instances(n, seed=3, extent=30.0)
@@ -50,7 +51,6 @@ def main():
         assert_close(reference, ref["skinned"], f"default kernel V={num_vertices}")
         bits, count = crowd.get_visibility()
         visible = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
-        vpad = (num_vertices + 7) // 8 * 8
         for variant in (1, 2, 3, 4):
             crowd.set_option(capi.OPT_SKIN_PLANAR_OUTPUT, variant)
             devmem.fill_f32(crowd.skinned_dev(), n * vpad * 9, float("nan"))

@@ -41,10 +41,10 @@ def main():
         cr = synth.make_crowd(n, 2, len(base.clips), seed=num_vertices)
         inst = synth.make_instances(n, seed=3, extent=60.0)
         ref = O.Crowd(oskel, oclips, remap, base.arm.inv_bind, n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, mesh=mesh_s, want=("skinned",))["skinned"]
-        vpad = (num_vertices + 7) // 8 * 8
         for flags in (0, capi.MESH_SORT_BY_INFLUENCES, capi.MESH_SORT_BY_INFLUENCES | capi.MESH_SORT_BLOCKS_OF_4, capi.MESH_CLUSTER_BONES):
             mesh = capi.Mesh(ctx, mesh_s.pos, mesh_s.nrm, mesh_s.tan, mesh_s.indices, mesh_s.weights, arm.palette_size, flags=flags)
             want = ref[:, mesh.order] if flags else ref
+            vpad = mesh.vertex_pitch
             crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
             crowd.set_layers(cr.clip, cr.ratio, cr.weight, cr.speed, threshold=FLT_MIN)
             crowd.set_instances(inst.world_inverse, inst.bbox)

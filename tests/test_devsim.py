@@ -112,6 +112,9 @@ def jobs(assets_dir):  # noqa: F811
         "asan_peer": (script("tests", "peer_exchange_check.py"), _env(LIB_ASAN, asan=True, DMK_DEVSIM_SEED="3")),
         "asan_ring": (script("tests", "skin_ring_check.py") + ["--quick"], _env(LIB_ASAN, asan=True, DMK_DEVSIM_SEED="3")),
         # 4 vertices per thread (two lanes per 8-vertex block, the pair's shuffles, predicated sector stores): a diagnostic shape, same checks
+        # the bulk-store output path (strided clustered mesh, staging in shared memory, cp.async.bulk shared -> global performed lazily by
+        # the simulator: a buffer reused before its wait shows as a wrong vertex): a diagnostic shape too
+        "asan_ring_bulk_store": (script("tests", "skin_ring_check.py") + ["--quick"], _env(LIB_ASAN, asan=True, DMK_DEVSIM_SEED="5", DMK_SKIN_BULK_STORE="1")),
         "asan_ring_vpt4": (script("tests", "skin_ring_check.py") + ["--quick"], _env(LIB_ASAN, asan=True, DMK_DEVSIM_SEED="4", DMK_SKIN_VPT="4")),
         "asan_tests": (_pytest_cmd("tests/test_multi_skin_gpu.py", "tests/test_pose_zero_gpu.py", "tests/test_gpu_skin.py", "tests/test_gpu_pose.py"), asan),
     }
@@ -257,6 +260,7 @@ def test_kernels_are_clean_under_address_and_ub_sanitizers(jobs):
     # groups, the pose tests
     for name, expect in (("asan_smoke", "smoke ok"), ("asan_planar", "bit-identical to the default kernel"),
                          ("asan_peer", "gives up on a rank that never publishes"), ("asan_ring", "cases match the oracle"), ("asan_ring_vpt4", "cases match the oracle"),
+                         ("asan_ring_bulk_store", "cases match the oracle"),
                          ("asan_tests", " passed")):
         j = jobs[name]
         assert j.returncode == 0 and expect in j.stdout and j.clean, name + "\n" + j.tail

@@ -1,6 +1,7 @@
 """BASELINE.json's full sizes (config 3: 100k characters x 5k vertices; config 5: 10M instances) through properties that do
 not need the oracle on the whole job: duplicated characters give identical bytes, a random sample of characters equals
-the oracle, permuting the instances permutes the visibility; plus the empty crowd."""
+the oracle, permuting the instances permutes the visibility; plus the empty crowd -- and, where the oracle is fast enough, the whole
+job: every palette and a checksum of every character's vertices (config 3), every visibility bit (config 5)."""
 import numpy as np
 import pytest
 
@@ -96,7 +97,7 @@ def test_config3_full_size_every_character_against_the_oracle():
         g.close()
 
 
-def test_config5_full_size_permutation_and_prefix_oracle():
+def test_config5_full_size_permutation_and_whole_oracle():
     import torch
     n = 10_000_000
     inst = synth.make_instances(n, seed=11, extent=900.0)
@@ -114,10 +115,8 @@ def test_config5_full_size_permutation_and_prefix_oracle():
 
         vis = cull(inst.world_inverse, inst.bbox)
         assert 0 < vis.sum() < n
-        # a 1M-instance prefix and a 1M-instance suffix against the oracle, bit for bit
-        m = 1_000_000
-        assert np.array_equal(vis[:m], capi.bits_to_bool(O.cull_batch(corners, inst.world_inverse[:m], inst.bbox[:m]), m))
-        assert np.array_equal(vis[-m:], capi.bits_to_bool(O.cull_batch(corners, inst.world_inverse[-m:], inst.bbox[-m:]), m))
+        # all 10M instances against the oracle, bit for bit (the oracle's cull runs on every host thread: about a second)
+        assert np.array_equal(vis, capi.bits_to_bool(O.cull_batch(corners, inst.world_inverse, inst.bbox), n))
         # permuting the instances permutes the visibility (no dependence on position in the launch)
         perm = np.random.default_rng(0).permutation(n)
         vis_perm = cull(np.ascontiguousarray(inst.world_inverse[perm]), np.ascontiguousarray(inst.bbox[perm]))

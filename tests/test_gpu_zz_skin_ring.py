@@ -27,3 +27,14 @@ def test_four_vertices_per_thread_shape_matches_the_oracle():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "skin_ring_check.py"), "--quick"], capture_output=True, text=True, timeout=300, env=env)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "cases match the oracle" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_bulk_store_output_path_matches_the_oracle():
+    """DMK_SKIN_BULK_STORE=1: the clustered mesh stored in the strided layout (pitch a multiple of 64), results staged in shared memory
+    and sent by cp.async.bulk shared -> global per round of 32 vertices.  A diagnostic shape (measured slower: the SM's bulk-copy
+    engine is already half busy with the palette replicas, profiles/r02_skin_bulk_store_experiment.txt); same checks."""
+    env = dict(os.environ, DMK_SKIN_BULK_STORE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "skin_ring_check.py"), "--quick"], capture_output=True, text=True, timeout=300, env=env)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "cases match the oracle" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

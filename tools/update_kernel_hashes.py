@@ -12,8 +12,8 @@ sys.path.insert(0, ROOT)
 from tests.test_capi_symbols import _kernel_sass  # noqa: E402
 
 KERNELS = [
-    ("skin_kernel.o", "skin_ws_kernelILi8ELb1ELb1ELi0ELi8ELi256EE"),   # clustered mesh, interleaved output: bench.py's default (profiles/r02_skin_ws_clustered_*)
-    ("skin_kernel.o", "skin_ws_kernelILi8ELb0ELb0ELi0ELi8ELi256EE"),   # caller's vertex order
+    ("skin_kernel.o", "skin_ws_kernelILi8ELb1ELb1ELi0ELi8ELi256ELb0EE"),   # clustered mesh, interleaved output: bench.py's default (profiles/r02_skin_ws_clustered_*)   # clustered mesh, interleaved output: bench.py's default (profiles/r02_skin_ws_clustered_*)
+    ("skin_kernel.o", "skin_ws_kernelILi8ELb0ELb0ELi0ELi8ELi256ELb0EE"),   # caller's vertex order
     ("skin_kernel.o", "skin_kernelILi8ELb0ELi8ELb0ELi256ELb0EE"),   # the round-1 kernel (DMK_OPT_SKIN_ROUND1_KERNEL), kept for A/B
     ("pose_kernel.o", "sample_kernelILi1EE"),
     ("pose_kernel.o", "model_kernel"),
