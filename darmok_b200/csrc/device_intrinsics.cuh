@@ -123,8 +123,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 // ---- wide global / shared accesses --------------------------------------------------------------------------------
+#ifndef DMK_ST_V8_OP
+#define DMK_ST_V8_OP "st.global.v8.f32"   // (experiments: -DDMK_ST_V8_OP='"st.global.cs.v8.f32"')
+#endif
 __device__ __forceinline__ void st_v8(float* p, const float* v) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+    asm volatile(DMK_ST_V8_OP " [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                  "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                  : "memory");
 }
