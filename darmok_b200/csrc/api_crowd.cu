@@ -1,6 +1,8 @@
 // api_crowd.cu -- C ABI of include/dmk.h: crowd: creation, options, per-frame inputs, device animators, the frame step
 #include "api_internal.hpp"
 
+#include <cstdlib>
+
 extern "C" {
 
 // ------------------------------------------------------------------------------------------------------------
@@ -68,7 +70,7 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
                     (void*)c->d_anim_transitions, (void*)c->d_anim_tables, (void*)c->d_anim_slots, (void*)c->d_anim_transition,
                     (void*)c->d_anim_transition_time, (void*)c->d_anim_events, (void*)c->d_anim_info, (void*)c->d_node_position, (void*)c->d_node_rotation,
                     (void*)c->d_node_scale, (void*)c->d_node_world, (void*)c->d_node_world_inverse, (void*)c->d_node_parent, (void*)c->d_entity_parent, (void*)c->d_anim_cmd, (void*)c->d_anim_status,
-                    (void*)c->d_anim_cmd_speed, (void*)c->d_anim_blend, (void*)c->d_anim_speed})
+                    (void*)c->d_anim_cmd_speed, (void*)c->d_anim_blend, (void*)c->d_anim_speed, (void*)c->d_skin_next})
         dev_free(p);
     for (auto& x : c->extra_skins) {
         dev_free(x.d_palette);
@@ -741,6 +743,19 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
         const bool visible_only = (flags & DMK_STEP_SKIN_VISIBLE_ONLY) != 0;
         if (visible_only && !c->culled_once) return fail(ctx, DMK_ERR_INVALID, "DMK_STEP_SKIN_VISIBLE_ONLY needs a cull step");
         SkinParams p{};
+        {   // per-tile counters of the dynamic character assignment (DMK_SKIN_STATIC_SPLIT=1 in the environment: the static split, for A/B)
+            static const bool static_split = [] { const char* e = std::getenv("DMK_SKIN_STATIC_SPLIT"); return e && std::atoi(e) == 1; }();
+            int tiles = c->mesh ? c->plan.num_tiles : 0;
+            for (const auto& x : c->extra_skins) tiles = std::max(tiles, x.mesh ? x.plan.num_tiles : 0);
+            if (!static_split && tiles > c->skin_next_capacity) {
+                dev_free(c->d_skin_next);
+                c->d_skin_next = nullptr;
+                c->skin_next_capacity = 0;
+                DMK_CUDA(ctx, dev_alloc(&c->d_skin_next, static_cast<size_t>(tiles)));
+                c->skin_next_capacity = tiles;
+            }
+            p.next_item = static_split ? nullptr : c->d_skin_next;
+        }
         p.char_ids = visible_only ? c->d_visible_ids : nullptr;
         p.char_count = visible_only ? c->d_visible_count : nullptr;
         p.n = c->n;

@@ -163,6 +163,8 @@ struct dmk_crowd_s {
     };
     std::vector<ExtraSkin> extra_skins;
     int reserved_sms = 0;
+    int32_t* d_skin_next = nullptr;   // [skin_next_capacity] per-tile counters of the skinning kernel's dynamic character assignment
+    int skin_next_capacity = 0;
     int skin_variant = 0;   // DMK_OPT_SKIN_PLANAR_OUTPUT
     bool skin_legacy = false;   // DMK_OPT_SKIN_ROUND1_KERNEL
     bool pose_fused = false;   // DMK_OPT_POSE_FUSED

@@ -108,6 +108,7 @@ struct SkinParams {
     int tile_vertices;        // multiple of 8
     int replicate_in_smem;    // replicas 1.. are copied from replica 0 inside shared memory instead of from global memory (set from the plan)
     int num_stages;           // staging depth of the producer warp's bulk copies (set by launch_skin from the plan)
+    int32_t* next_item;       // [num_tiles] counters of the warp-specialised kernel's dynamic character assignment (zeroed by launch_skin); null = static split
     int vertex_order_mode;    // 0 caller's order; 1 grouped by influence count: the gathers of absent influences are predicated off;
                               // 2 clustered by bone (DMK_MESH_CLUSTER_BONES): also the block's bone once per thread and character
                               // 3 clustered by bone in the STRIDED layout (cluster_mesh_strided): also the bulk-store output path

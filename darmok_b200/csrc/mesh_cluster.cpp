@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <cstring>
 
 namespace dmk {
@@ -223,8 +224,11 @@ ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tile
         const int begin = t * tb, end = std::min(dealt_end, (t + 1) * tb);
         if (begin >= end) continue;
         const int len = end - begin, warps = (len + blocks_per_warp - 1) / blocks_per_warp;
+        // (serpentine: odd rounds run over the warps backwards, so that no warp always gets the heavier group of its round -- a block's
+        // characters advance at the pace of its slowest warp)
         for (int quarter = 0; quarter < quarters; ++quarter)
-            for (int w = 0; w < warps; ++w) {
+            for (int wi = 0; wi < warps; ++wi) {
+                const int w = (quarter & 1) ? warps - 1 - wi : wi;
                 const int pos = (w * quarters + quarter) * kQuarter;
                 if (pos < len) tile_slots[static_cast<size_t>(t)].push_back({begin + pos, std::min(kQuarter, len - pos)});
             }
@@ -232,7 +236,8 @@ ClusterResult cluster_mesh(const std::vector<ClusterInfluence>& in, int num_tile
     }
     size_t next = 0;
     for (size_t s = 0; s < max_slots; ++s)
-        for (int t = 0; t < num_tiles; ++t) {
+        for (int ti = 0; ti < num_tiles; ++ti) {   // (serpentine over the tiles as well: every tile gets the same share of heavy groups)
+            const int t = (s & 1) ? num_tiles - 1 - ti : ti;
             const auto& slots = tile_slots[static_cast<size_t>(t)];
             if (s >= slots.size()) continue;
             for (int k = 0; k < slots[s].capacity && next < seq.size(); ++k) place[static_cast<size_t>(slots[s].first + k)] = seq[next++];
@@ -412,7 +417,8 @@ ClusterResult cluster_mesh_strided(const std::vector<ClusterInfluence>& in, int 
     for (int t = 0; t < tiles; ++t) {
         const int begin = t * tb, len = geo.tile_blocks(t), warps = (len + 31) / 32;
         for (int quarter = 0; quarter < 4; ++quarter)
-            for (int w = 0; w < warps; ++w) {
+            for (int wi = 0; wi < warps; ++wi) {
+                const int w = (quarter & 1) ? warps - 1 - wi : wi;   // serpentine, as in cluster_mesh
                 const int pos = (w * 4 + quarter) * kQuarter;
                 if (pos < len) tile_slots[static_cast<size_t>(t)].push_back({begin + pos, std::min(kQuarter, len - pos)});
             }
@@ -420,7 +426,8 @@ ClusterResult cluster_mesh_strided(const std::vector<ClusterInfluence>& in, int 
     }
     size_t next = 0;
     for (size_t sl = 0; sl < max_slots; ++sl)
-        for (int t = 0; t < tiles; ++t) {
+        for (int ti = 0; ti < tiles; ++ti) {
+            const int t = (sl & 1) ? tiles - 1 - ti : ti;
             const auto& slots = tile_slots[static_cast<size_t>(t)];
             if (sl >= slots.size()) continue;
             for (int k = 0; k < slots[sl].capacity; ++k) {

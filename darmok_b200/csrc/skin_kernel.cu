@@ -331,8 +331,9 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
     uint64_t* s_full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)ring * buf_bytes);   // [kMaxRing] bulk copies -> compute warps
     uint64_t* s_empty_bar = s_full_bar + kMaxRing;                       // [kMaxRing] compute warps -> producer
     uint64_t* s_stage_bar = s_empty_bar + kMaxRing;                      // [kMaxRing] shared-memory replication: replica 0 has arrived
+    volatile int32_t* s_cid = reinterpret_cast<volatile int32_t*>(s_stage_bar + kMaxRing);   // [kMaxRing] character of the item in a ring buffer, -1 = end of the tile pass
     // (STRIDED) [compute warps][kOutBufs][32 x 36 B], on a 128-byte boundary of the block's shared memory
-    unsigned char* s_out = smem + (((size_t)ring * buf_bytes + 8 * 3 * kMaxRing + 127) & ~(size_t)127);
+    unsigned char* s_out = smem + (((size_t)ring * buf_bytes + 8 * 3 * kMaxRing + 4 * kMaxRing + 127) & ~(size_t)127);
     const bool s2s = p.replicate_in_smem != 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -344,8 +345,8 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
 
     int64_t nchars = p.n;
     if (p.char_ids) nchars = p.char_count[0];
+    // static schedule (p.next_item == nullptr): this block takes characters group, group + ngroups, ... of each of its tiles
     const int64_t my_count = nchars > group ? (nchars - group + ngroups - 1) / ngroups : 0;
-    if (my_count == 0) return;
 
     if (tid == 0) {
         for (int k = 0; k < ring; ++k) {
@@ -357,12 +358,6 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
     }
     __syncthreads();
 
-    auto char_of = [&](int64_t i) -> int64_t {
-        const int64_t k = group + i * ngroups;
-        return p.char_ids ? (int64_t)__ldg(p.char_ids + k) : k;
-    };
-    const int passes = (p.num_tiles - tslot + tiles_per_pass - 1) / tiles_per_pass;   // tiles this block walks (1 unless the mesh has more tiles than the grid)
-
     if (warp == ncompute) {
         // ---------------- producer: one thread.  Per (tile pass, character): wait until the ring buffer is free, then fill its REPL
         // replicas with bulk copies; their bytes complete the buffer's "full" barrier, nothing else is needed.  Two ways:
@@ -372,35 +367,66 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
         //     copies (cp.async.bulk.shared::cluster.shared::cta) one item behind, so the wait for replica 0 is never exposed.
         //     MEASURED: slower (4.16 ms against 3.52 ms; the copies run at 15 B/cycle/SM, tools/ubench_s2s.cu, and take
         //     shared-memory bandwidth from the gathers), so the first way is the default and this one a diagnostic option.
+        //
+        // WHICH character: by default the blocks of a tile take the next one nobody has taken from a counter in global memory
+        // (p.next_item[tile], zeroed by launch_skin).  MEASURED (profiles/r02_skin_cta_finish_times_*.txt): with the static
+        // split (every block the same number of characters) most blocks of the 100k x 5k launch are done after 3.17-3.25 ms but
+        // eight of them -- the same SMs in every launch -- need 3.6 ms, and the kernel lasts as long as they do.
+        // The character of a ring buffer travels in s_cid (written before the arrival on the buffer's barrier); -1 ends a tile pass.
         if (lane != 0) return;
-        const int64_t total = (int64_t)passes * my_count;
         uint32_t rb = 0, rphase = 0, sb = 0, sphase = 0;
         bool wrapped = false;
-        int64_t i = 0;   // character of item q within this block's share
-        for (int64_t q = 0; q <= total; ++q) {
-            if (q < total) {
-                if (wrapped) mbar_wait(&s_empty_bar[rb], rphase ^ 1u);   // every compute warp is done with the item `ring` items back
-                const float* src = p.palette34 + (size_t)char_of(i) * PS * 16;
-                unsigned char* dst = s_repl + (size_t)rb * buf_bytes;
-                if (s2s) {
-                    mbar_expect_tx(&s_stage_bar[rb], pal_bytes);
-                    bulk_g2s(dst, src, pal_bytes, &s_stage_bar[rb]);
-                } else {
-                    mbar_expect_tx(&s_full_bar[rb], pal_bytes * REPL);
+        auto advance_rb = [&] { if (++rb == (uint32_t)ring) { rb = 0; rphase ^= 1u; wrapped = true; } };
+        auto advance_sb = [&] { if (++sb == (uint32_t)ring) { sb = 0; sphase ^= 1u; } };
+        for (int tile = tslot; tile < p.num_tiles; tile += tiles_per_pass) {
+            int64_t issued = 0, staged = 0, i_static = 0;   // items of this tile pass: requested / (s2s) replicated inside shared memory
+            bool exhausted = false;
+            for (;;) {
+                if (!exhausted) {
+                    int64_t k;
+                    if (p.next_item) k = atomicAdd(p.next_item + tile, 1);
+                    else k = i_static < my_count ? group + (i_static++) * ngroups : nchars;
+                    if (k >= nchars) {
+                        exhausted = true;
+                    } else {
+                        if (wrapped) mbar_wait(&s_empty_bar[rb], rphase ^ 1u);   // every compute warp is done with the item `ring` items back
+                        const int32_t cid = p.char_ids ? __ldg(p.char_ids + k) : (int32_t)k;
+                        s_cid[rb] = cid;
+                        const float* src = p.palette34 + (size_t)cid * PS * 16;
+                        unsigned char* dst = s_repl + (size_t)rb * buf_bytes;
+                        if (s2s) {
+                            mbar_expect_tx(&s_stage_bar[rb], pal_bytes);
+                            bulk_g2s(dst, src, pal_bytes, &s_stage_bar[rb]);
+                        } else {
+                            mbar_expect_tx(&s_full_bar[rb], pal_bytes * REPL);
 #pragma unroll
-                    for (int r = 0; r < REPL; ++r) bulk_g2s(dst + (size_t)r * RS, src, pal_bytes, &s_full_bar[rb]);
+                            for (int r = 0; r < REPL; ++r) bulk_g2s(dst + (size_t)r * RS, src, pal_bytes, &s_full_bar[rb]);
+                        }
+                        ++issued;
+                        advance_rb();
+                    }
                 }
-                if (++i == my_count) i = 0;
-                if (++rb == (uint32_t)ring) { rb = 0; rphase ^= 1u; wrapped = true; }
-            }
-            if (s2s && q >= 1) {   // the item issued one iteration ago: its replica 0 has had a whole item's time to arrive
-                mbar_wait(&s_stage_bar[sb], sphase);
-                unsigned char* buf = s_repl + (size_t)sb * buf_bytes;
-                mbar_expect_tx(&s_full_bar[sb], pal_bytes * (REPL - 1));
+                // (s2s) the item issued one iteration ago -- its replica 0 has had a whole item's time to arrive -- or, at the end, the last one
+                if (s2s && staged < issued && (exhausted || staged + 1 < issued)) {
+                    mbar_wait(&s_stage_bar[sb], sphase);
+                    unsigned char* buf = s_repl + (size_t)sb * buf_bytes;
+                    mbar_expect_tx(&s_full_bar[sb], pal_bytes * (REPL - 1));
 #pragma unroll
-                for (int r = 1; r < REPL; ++r) bulk_s2s(buf + (size_t)r * RS, buf, pal_bytes, &s_full_bar[sb]);
-                if (++sb == (uint32_t)ring) { sb = 0; sphase ^= 1u; }
+                    for (int r = 1; r < REPL; ++r) bulk_s2s(buf + (size_t)r * RS, buf, pal_bytes, &s_full_bar[sb]);
+                    ++staged;
+                    advance_sb();
+                }
+                if (exhausted && (!s2s || staged == issued)) break;
             }
+            // the end of this tile pass takes a ring slot of its own
+            if (wrapped) mbar_wait(&s_empty_bar[rb], rphase ^ 1u);
+            s_cid[rb] = -1;
+            if (s2s) {
+                mbar_arrive(&s_stage_bar[rb]);
+                advance_sb();
+            }
+            mbar_arrive(&s_full_bar[rb]);
+            advance_rb();
         }
         return;
     }
@@ -458,10 +484,10 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
             for (int v = 0; v < kVPT; ++v) rare |= __ballot_sync(0xffffffffu, (used >> (4 * v) & 1u) != 0u) != 0u ? 1u << v : 0u;
         }
 
-        for (int64_t i = 0; i < my_count; ++i) {
-            const int64_t cid = char_of(i);
+        for (;;) {
             if (s2s) mbar_wait(&s_stage_bar[rb], rphase);   // replica 0 (the async copy that the other replicas were made from)
             mbar_wait(&s_full_bar[rb], rphase);
+            const int64_t cid = s_cid[rb];                  // written by the producer before its arrival on the barrier; -1: the pass is over
             // One character for this thread's 8 vertices.  RARE: some lane of the warp still gathers entry 0 of some vertex (a mixed
             // block of a clustered mesh).  The common instantiation has no branch in it: one basic block of ~1000 instructions, so the
             // scheduler can put the gathers of vertex v + 1 under the arithmetic of vertex v.
@@ -626,13 +652,14 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
                     }
                 }
                         };
-            if (warp_active) {
+            if (warp_active && cid >= 0) {
                 if (SHARE && rare != 0u) item(std::true_type{});
                 else item(std::false_type{});
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty_bar[rb]);
             if (++rb == (uint32_t)ring) { rb = 0; rphase ^= 1u; }
+            if (cid < 0) break;
         }
     }
     if (STRIDED && lane == 0) bulk_wait_all();   // the staging buffers must outlive the copies that read them
@@ -654,7 +681,7 @@ bool is_legacy(int variant, bool legacy) { return legacy || variant == 1 || vari
 constexpr size_t kOutStageBytes = (size_t)(kComputeThreads / 32) * kOutBufs * 1152;   // bulk-store output path: kOutBufs rounds of 32 vertices per compute warp
 size_t skin_smem_bytes(int palette_size, int repl, bool legacy, int ring = kMaxRing, bool strided = false) {
     if (legacy) return (size_t)palette_size * (48 * kNumRepl * repl + 64 * kNumStage) + 8 * (kNumStage + kNumRepl) + 16;
-    return (size_t)replica_stride(palette_size) * repl * ring + 8 * 3 * kMaxRing + 16 + (strided ? kOutStageBytes + 128 : 0);
+    return (size_t)replica_stride(palette_size) * repl * ring + 8 * 3 * kMaxRing + 4 * kMaxRing + 16 + (strided ? kOutStageBytes + 128 : 0);
 }
 template <typename F>
 auto with_legacy_kernel(int repl, bool skip, int variant, F&& f) {
@@ -771,6 +798,10 @@ cudaError_t launch_skin(const SkinParams& p, const SkinPlan& plan, cudaStream_t 
     if (p.n <= 0 || p.vpad <= 0) return cudaSuccess;
     SkinParams q = p;
     q.num_stages = plan.stages;
+    if (q.next_item && !plan.legacy) {   // dynamic character assignment: one counter per tile, zero at every launch
+        const cudaError_t e = cudaMemsetAsync(q.next_item, 0, sizeof(int32_t) * (size_t)plan.num_tiles, stream);
+        if (e != cudaSuccess) return e;
+    }
     q.replicate_in_smem = plan.replicate_in_smem ? 1 : 0;
     return with_kernel(plan.replicas, p.vertex_order_mode, plan.variant, plan.legacy, plan.ws_vpt, plan.strided_store, [&, p = q](auto kernel) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
