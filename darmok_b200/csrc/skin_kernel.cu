@@ -338,15 +338,22 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncompute = (blockDim.x >> 5) - 1;                          // the last warp is the producer
+    // Which tiles and characters a block works on.  Dynamic (default, p.next_item): every block walks ALL tiles, starting at its own
+    // (blockIdx.x mod num_tiles), and takes the next character of the tile from a counter until none is left -- so blocks that are
+    // done with their tile help with the others, no SM has to stay idle to make the grid a multiple of the tile count, and tiles of
+    // different weight even out.  Static (p.next_item == nullptr, A/B): block (tile slot, group) takes characters group, group +
+    // ngroups, ... of the tiles tslot, tslot + tiles_per_pass, ...
+    const bool dynamic = p.next_item != nullptr;
     const int tiles_per_pass = min(p.num_tiles, (int)gridDim.x);
     const int ngroups = gridDim.x / tiles_per_pass;
     const int tslot = blockIdx.x % tiles_per_pass, group = blockIdx.x / tiles_per_pass;
-    if (group >= ngroups) return;
+    if (!dynamic && group >= ngroups) return;
+    const int tile_iters = dynamic ? p.num_tiles : (p.num_tiles - tslot + tiles_per_pass - 1) / tiles_per_pass;
+    auto tile_at = [&](int j) { return dynamic ? (int)((blockIdx.x + (unsigned)j) % (unsigned)p.num_tiles) : tslot + j * tiles_per_pass; };
 
     int64_t nchars = p.n;
     if (p.char_ids) nchars = p.char_count[0];
-    // static schedule (p.next_item == nullptr): this block takes characters group, group + ngroups, ... of each of its tiles
-    const int64_t my_count = nchars > group ? (nchars - group + ngroups - 1) / ngroups : 0;
+    const int64_t my_count = nchars > group ? (nchars - group + ngroups - 1) / ngroups : 0;   // (static split)
 
     if (tid == 0) {
         for (int k = 0; k < ring; ++k) {
@@ -378,7 +385,8 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
         bool wrapped = false;
         auto advance_rb = [&] { if (++rb == (uint32_t)ring) { rb = 0; rphase ^= 1u; wrapped = true; } };
         auto advance_sb = [&] { if (++sb == (uint32_t)ring) { sb = 0; sphase ^= 1u; } };
-        for (int tile = tslot; tile < p.num_tiles; tile += tiles_per_pass) {
+        for (int j = 0; j < tile_iters; ++j) {
+            const int tile = tile_at(j);
             int64_t issued = 0, staged = 0, i_static = 0;   // items of this tile pass: requested / (s2s) replicated inside shared memory
             bool exhausted = false;
             for (;;) {
@@ -437,7 +445,18 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
     const uint32_t repl_base = smem_u32(s_repl) + lane_repl * RS;
     const uint32_t odd_delta = (((lane_repl ^ 4u) & (REPL - 1)) - lane_repl) * RS;   // (mod 2^32)
     uint32_t rb = 0, rphase = 0;
-    for (int tile = tslot; tile < p.num_tiles; tile += tiles_per_pass) {
+    for (int j = 0; j < tile_iters; ++j) {
+        const int tile = tile_at(j);
+        // the first item of this tile pass -- or already its end, when the tile's characters were all taken before this block got here:
+        // then there is nothing to load
+        if (s2s) mbar_wait(&s_stage_bar[rb], rphase);
+        mbar_wait(&s_full_bar[rb], rphase);
+        if (s_cid[rb] < 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty_bar[rb]);
+            if (++rb == (uint32_t)ring) { rb = 0; rphase ^= 1u; }
+            continue;
+        }
         // ---- this thread's 8 (4) vertices: loaded once, kept in registers for every character ----
         // the 8-vertex block of the tile this lane works on, and which half of it (VPT = 4: lanes L and L ^ 8 share a block)
         const int blk = VPT == 8 ? tid : warp * 16 + ((lane >> 4) << 3) + (lane & 7);
@@ -788,8 +807,10 @@ SkinPlan plan_skin(int vpad, int palette_size, int num_sms, int variant, bool le
         return 0;
     });
     int grid = num_sms * occ;
-    const int tpp = plan.num_tiles < grid ? plan.num_tiles : grid;
-    grid = grid / tpp * tpp;
+    if (plan.legacy) {   // the round-1 kernel's static split wants a multiple of the tile count; the dynamic assignment uses every SM
+        const int tpp = plan.num_tiles < grid ? plan.num_tiles : grid;
+        grid = grid / tpp * tpp;
+    }
     plan.grid = grid;
     return plan;
 }

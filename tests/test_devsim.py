@@ -115,6 +115,8 @@ def jobs(assets_dir):  # noqa: F811
         # the bulk-store output path (strided clustered mesh, staging in shared memory, cp.async.bulk shared -> global performed lazily by
         # the simulator: a buffer reused before its wait shows as a wrong vertex): a diagnostic shape too
         "asan_ring_bulk_store": (script("tests", "skin_ring_check.py") + ["--quick"], _env(LIB_ASAN, asan=True, DMK_DEVSIM_SEED="5", DMK_SKIN_BULK_STORE="1")),
+        # the static split of the characters over the blocks (the default takes them from per-tile counters): kept for A/B
+        "asan_ring_static_split": (script("tests", "skin_ring_check.py") + ["--quick"], _env(LIB_ASAN, asan=True, DMK_DEVSIM_SEED="6", DMK_SKIN_STATIC_SPLIT="1")),
         "asan_ring_vpt4": (script("tests", "skin_ring_check.py") + ["--quick"], _env(LIB_ASAN, asan=True, DMK_DEVSIM_SEED="4", DMK_SKIN_VPT="4")),
         "asan_tests": (_pytest_cmd("tests/test_multi_skin_gpu.py", "tests/test_pose_zero_gpu.py", "tests/test_gpu_skin.py", "tests/test_gpu_pose.py"), asan),
     }
@@ -260,6 +262,7 @@ def test_kernels_are_clean_under_address_and_ub_sanitizers(jobs):
     # groups, the pose tests
     for name, expect in (("asan_smoke", "smoke ok"), ("asan_planar", "bit-identical to the default kernel"),
                          ("asan_peer", "gives up on a rank that never publishes"), ("asan_ring", "cases match the oracle"), ("asan_ring_vpt4", "cases match the oracle"),
+                         ("asan_ring_static_split", "cases match the oracle"),
                          ("asan_ring_bulk_store", "cases match the oracle"),
                          ("asan_tests", " passed")):
         j = jobs[name]

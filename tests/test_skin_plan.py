@@ -25,9 +25,12 @@ def test_every_vertex_is_owned_by_exactly_one_thread(layout):
             assert p["threads"] % 32 == 0 and 32 <= p["threads"] <= MAX_THREADS[layout]
             assert p["tile_vertices"] % 8 == 0 and p["num_tiles"] * p["tile_vertices"] >= vpad
             assert p["threads"] * vpt >= p["tile_vertices"]
-            # the persistent grid: whole groups of tile slots, never more blocks than SMs (one block per SM without a device)
+            # the persistent grid: never more blocks than SMs (one block per SM without a device).  Layouts 1 and 2 only exist in the
+            # round-1 kernel shape, whose static split wants whole groups of tile slots; the producer-warp kernel takes characters from
+            # per-tile counters and uses every SM
             tiles_per_pass = min(p["num_tiles"], p["grid"])
-            assert 1 <= p["grid"] <= num_sms and p["grid"] % tiles_per_pass == 0
+            assert 1 <= p["grid"] <= num_sms
+            assert p["grid"] % tiles_per_pass == 0 if layout in (1, 2) else p["grid"] == num_sms
             owner = np.zeros(vpad, np.int32)
             for tile in range(p["num_tiles"]):
                 tid = np.arange(p["threads"])
