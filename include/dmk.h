@@ -161,7 +161,9 @@ DMK_API int64_t dmk_crowd_size(dmk_crowd_t crowd);
 enum {
     DMK_OPT_FORCE_KEY_SEARCH = 1,
     /* Leave `value` SMs out of the persistent skinning grid so that a collective enqueued on another stream (the
-     * visible-palette gather over NVLink) runs concurrently with the skinning kernel instead of after it. */
+     * visible-palette gather over NVLink) runs concurrently with the skinning kernel instead of after it.  The grid
+     * otherwise takes every SM (its blocks fill the register file: nothing else fits beside them); the copy-engine
+     * transport needs one SM for its one-thread flow-control kernels, NCCL eight. */
     DMK_OPT_SKIN_RESERVED_SMS = 2,
     /* With dmk_crowd_set_transforms: also store the world inverse the cull derives for each entity (64 B/entity more
      * written per CULL step) so that dmk_crowd_get_world_inverses / dmk_crowd_world_inverse_dev can hand it on, e.g. to
