@@ -347,9 +347,12 @@ __global__ void __launch_bounds__(MAXT, 1) skin_ws_kernel(const SkinParams p) {
     const int tiles_per_pass = min(p.num_tiles, (int)gridDim.x);
     const int ngroups = gridDim.x / tiles_per_pass;
     const int tslot = blockIdx.x % tiles_per_pass, group = blockIdx.x / tiles_per_pass;
-    if (!dynamic && group >= ngroups) return;
-    const int tile_iters = dynamic ? p.num_tiles : (p.num_tiles - tslot + tiles_per_pass - 1) / tiles_per_pass;
-    auto tile_at = [&](int j) { return dynamic ? (int)((blockIdx.x + (unsigned)j) % (unsigned)p.num_tiles) : tslot + j * tiles_per_pass; };
+    if (!(dynamic && p.num_tiles <= (int)gridDim.x) && group >= ngroups) return;
+    // (a mesh with more tiles than blocks -- or the static split -- : tiles tslot, tslot + tiles_per_pass, ...; helping is limited to the
+    // next 7 tiles so that a huge mesh with few characters does not pay one empty hand-shake per tile and block)
+    const bool walk = dynamic && p.num_tiles <= (int)gridDim.x;
+    const int tile_iters = walk ? min(p.num_tiles, 8) : (p.num_tiles - tslot + tiles_per_pass - 1) / tiles_per_pass;
+    auto tile_at = [&](int j) { return walk ? (int)((blockIdx.x + (unsigned)j) % (unsigned)p.num_tiles) : tslot + j * tiles_per_pass; };
 
     int64_t nchars = p.n;
     if (p.char_ids) nchars = p.char_count[0];

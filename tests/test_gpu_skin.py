@@ -168,3 +168,28 @@ def test_clustered_mesh_shares_a_bone_per_block_and_matches_the_oracle(assets):
                 assert_close(crowd.get_skinned(), ref[:, order], f"skinned (clustered order, layout {layout}, round-1 shape {round1})")
     finally:
         g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("clustered", [False, True])
+def test_mesh_with_more_tiles_than_a_block_walks(clustered):
+    """9 tiles: a block of the skinning kernel starts at its own tile and helps with at most the next 7, so no block visits every
+    tile -- every tile still gets its characters from its own blocks (dynamic character assignment, skin_kernel.cu)."""
+    from darmok_b200 import capi
+    n, verts = 170, 16001
+    skel = synth.make_skeleton(20)
+    clips = [synth.make_clip(skel, f"clip{i}", seed=i, duration=1.0) for i in range(2)]
+    a = common.Assets(skel, clips, synth.make_armature(skel), synth.make_mesh(verts, 20, seed=3))
+    g, o = GpuRig(a, with_mesh=False), OracleRig(a)
+    try:
+        m = a.mesh
+        g.mesh = capi.Mesh(g.ctx, m.pos, m.nrm, m.tan, m.indices, m.weights, g.arm.palette_size, flags=capi.MESH_CLUSTER_BONES if clustered else 0)
+        assert capi.skin_plan(g.mesh.vertex_pitch, g.arm.palette_size, 148, 0)["num_tiles"] == 9
+        cr = synth.make_crowd(n, 2, len(clips), seed=7)
+        crowd = g.crowd(n, 2)
+        crowd.set_layers(cr.clip, cr.ratio, cr.weight, threshold=FLT_MIN)
+        crowd.step(0.0, capi.STEP_POSE | capi.STEP_SKIN)
+        ref = o.crowd(n, 2).step(cr.clip, cr.ratio, cr.weight, FLT_MIN, mesh=m, want=("skinned",))["skinned"]
+        assert_close(crowd.get_skinned(), ref[:, g.mesh.order] if clustered else ref, "skinned vertices, 9 tiles")
+    finally:
+        g.close()
