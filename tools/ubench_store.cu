@@ -17,12 +17,28 @@ __device__ __forceinline__ void st4(float* p, float v) {
     asm volatile("st.global.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(p), "f"(v) : "memory");
 }
 
+// g_next != nullptr: the blocks take chunks from a counter (dynamic) instead of each writing its own chunks_per_block chunks -- the
+// static split lasts as long as the slowest SM (the skinning kernel's finding, profiles/r02_skin_cta_finish_times_static.txt)
+__device__ unsigned long long g_counter;
 template <int PATTERN>
-__global__ void __launch_bounds__(256) k(float* out, size_t chunks_per_block, float v) {
+__global__ void __launch_bounds__(256) k(float* out, size_t chunks_per_block, float v, int dynamic = 0) {
     // each block writes chunks of 256 threads * 288 B = 73728 B
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (size_t c = 0; c < chunks_per_block; ++c) {
-        float* base = out + ((size_t)blockIdx.x * chunks_per_block + c) * (256 * 72);
+    __shared__ unsigned long long s_chunk;
+    const size_t total = chunks_per_block * gridDim.x;
+    for (size_t c = 0;; ++c) {
+        size_t chunk;
+        if (dynamic) {
+            __syncthreads();
+            if (tid == 0) s_chunk = atomicAdd(&g_counter, 1ull);
+            __syncthreads();
+            chunk = s_chunk;
+            if (chunk >= total) break;
+        } else {
+            if (c >= chunks_per_block) break;
+            chunk = (size_t)blockIdx.x * chunks_per_block + c;
+        }
+        float* base = out + chunk * (256 * 72);
         float* wbase = base + warp * (32 * 72);
         if (PATTERN == 0) {
 #pragma unroll
@@ -53,6 +69,31 @@ int main(int argc, char** argv) {
     cudaMalloc(&d, bytes);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (argc >= 2 && !strcmp(argv[1], "dynamic")) {
+        // ubench_store dynamic: every pattern with the static split and with chunks taken from a counter
+        for (int pat = 0; pat < 5; ++pat) {
+            if (pat == 3) continue;
+            for (int dyn = 0; dyn < 2; ++dyn) {
+                float best = 1e9;
+                for (int it = 0; it < 4; ++it) {
+                    unsigned long long zero = 0;
+                    cudaMemcpyToSymbol(g_counter, &zero, sizeof(zero));
+                    cudaEventRecord(e0);
+                    if (pat == 0) k<0><<<blocks, 256>>>(d, chunks_per_block, 1.f, dyn);
+                    if (pat == 1) k<1><<<blocks, 256>>>(d, chunks_per_block, 1.f, dyn);
+                    if (pat == 2) k<2><<<blocks, 256>>>(d, chunks_per_block, 1.f, dyn);
+                    if (pat == 4) k<4><<<blocks, 256>>>(d, chunks_per_block, 1.f, dyn);
+                    cudaEventRecord(e1);
+                    cudaEventSynchronize(e1);
+                    float ms; cudaEventElapsedTime(&ms, e0, e1);
+                    if (ms < best) best = ms;
+                }
+                printf("pattern %d %s: %.3f ms  %.1f GB/s\n", pat, dyn ? "dynamic" : "static ", best, bytes / best / 1e6);
+            }
+        }
+        printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+        return 0;
+    }
     if (argc >= 3 && !strcmp(argv[1], "sustained")) {
         // ubench_store sustained <pattern 0 | 1 | 4> [launches]: the same launch back to back (what does the power cap leave of it?)
         const int pat = atoi(argv[2]), launches = argc >= 4 ? atoi(argv[3]) : 600;
