@@ -72,6 +72,12 @@ void dmk_crowd_destroy(dmk_crowd_t c) {
                     (void*)c->d_node_scale, (void*)c->d_node_world, (void*)c->d_node_world_inverse, (void*)c->d_node_parent, (void*)c->d_entity_parent, (void*)c->d_anim_cmd, (void*)c->d_anim_status,
                     (void*)c->d_anim_cmd_speed, (void*)c->d_anim_blend, (void*)c->d_anim_speed, (void*)c->d_skin_next})
         dev_free(p);
+    if (c->upload_stream) {
+        cudaStreamSynchronize(c->upload_stream);
+        cudaStreamDestroy(c->upload_stream);
+    }
+    if (c->layers_idle) cudaEventDestroy(c->layers_idle);
+    if (c->upload_done) cudaEventDestroy(c->upload_done);
     for (auto& x : c->extra_skins) {
         dev_free(x.d_palette);
         dev_free(x.d_palette34);
@@ -205,6 +211,8 @@ dmk_status dmk_crowd_set_layers(dmk_crowd_t c, int num_layers, const int32_t* cl
         if (clip[i] < 0 || clip[i] >= c->clips->num_clips)
             return fail(ctx, DMK_ERR_INVALID, "layer references clip " + std::to_string(clip[i]) + " outside the clip set");
     cudaStream_t s = ctx->stream;
+    if (dmk_status st = join_layer_upload(c)) return st;
+    c->layers_idle_recorded = false;   // an upload that follows orders itself behind these copies
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_clip, clip, ln * 4, cudaMemcpyHostToDevice, s));
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_ratio, ratio, ln * 4, cudaMemcpyHostToDevice, s));
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_weight, weight, ln * 4, cudaMemcpyHostToDevice, s));
@@ -261,6 +269,8 @@ dmk_status dmk_crowd_set_programs(dmk_crowd_t c, int num_layers, const int32_t* 
     std::memcpy(h + 2 * lbytes, weight, lbytes);
     std::memcpy(h + 3 * lbytes, programs, pbytes);
     cudaStream_t s = ctx->stream;
+    if (dmk_status st = join_layer_upload(c)) return st;
+    c->layers_idle_recorded = false;
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_clip, h, lbytes, cudaMemcpyHostToDevice, s));
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_ratio, h + lbytes, lbytes, cudaMemcpyHostToDevice, s));
     DMK_CUDA(ctx, cudaMemcpyAsync(c->d_weight, h + 2 * lbytes, lbytes, cudaMemcpyHostToDevice, s));
@@ -295,10 +305,25 @@ dmk_status dmk_crowd_update_layers(dmk_crowd_t c, int num_layers, const int32_t*
     std::memcpy(h, clip, bytes);
     std::memcpy(h + bytes, ratio, bytes);
     std::memcpy(h + 2 * bytes, weight, bytes);
-    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_clip, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_ratio, h + bytes, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_weight, h + 2 * bytes, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return stage_release(c);
+    // The copies go on the crowd's upload stream: behind the last step that used the layer arrays, not behind everything the context's
+    // stream already holds (the skinning kernel of the previous frame) -- the next step waits for them (join_layer_upload).
+    if (!c->upload_stream) {
+        DMK_CUDA(ctx, cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking));
+        DMK_CUDA(ctx, cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
+    }
+    if (!c->layers_idle_recorded) {   // nothing has stepped yet: order behind what the setters enqueued
+        if (dmk_status st = mark_layers_idle(c)) return st;
+    }
+    cudaStream_t up = c->upload_stream;
+    DMK_CUDA(ctx, cudaStreamWaitEvent(up, c->layers_idle, 0));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_clip, h, bytes, cudaMemcpyHostToDevice, up));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_ratio, h + bytes, bytes, cudaMemcpyHostToDevice, up));
+    DMK_CUDA(ctx, cudaMemcpyAsync(c->d_weight, h + 2 * bytes, bytes, cudaMemcpyHostToDevice, up));
+    DMK_CUDA(ctx, cudaEventRecord(c->upload_done, up));
+    c->upload_pending = true;
+    DMK_CUDA(ctx, cudaEventRecord(c->stage_done[c->stage_next], up));   // (stage_release on the upload stream)
+    c->stage_next ^= 1;
+    return DMK_OK;
 }
 
 // ---- device-side animators ------------------------------------------------------------
@@ -366,6 +391,7 @@ dmk_status dmk_crowd_set_animator(dmk_crowd_t c, const dmk_anim_state_def* state
         DMK_CUDA(ctx, dev_alloc(&c->d_anim_speed, n));
     }
     if (!c->d_program) DMK_CUDA(ctx, dev_alloc(&c->d_program, n));
+    if (dmk_status st = join_layer_upload(c)) return st;
     DMK_CUDA(ctx, launch_animator_init(animator_params(c, 0.f), c->d_anim_cmd_speed, c->d_anim_blend, c->d_anim_speed, ctx->stream));
     DMK_CUDA(ctx, cudaMemsetAsync(c->d_anim_status, 0, n * sizeof(int32_t), ctx->stream));
     DMK_CUDA(ctx, cudaMemsetAsync(c->d_anim_events, 0xff, n * sizeof(AnimEvents), ctx->stream));
@@ -440,6 +466,7 @@ dmk_status dmk_crowd_get_animator_state(dmk_crowd_t c, dmk_anim_state* out_state
     if (bind(ctx)) return DMK_ERR_CUDA;
     const size_t n = static_cast<size_t>(c->n);
     if (!c->d_anim_info) DMK_CUDA(ctx, dev_alloc(&c->d_anim_info, n));
+    if (dmk_status st = join_layer_upload(c)) return st;
     DMK_CUDA(ctx, launch_animator_query(animator_params(c, 0.f), c->d_anim_info, ctx->stream));
     ++ctx->launches;
     DMK_CUDA(ctx, cudaMemcpyAsync(out_states, c->d_anim_info, n * sizeof(AnimStateInfo), cudaMemcpyDeviceToHost, ctx->stream));
@@ -455,6 +482,7 @@ dmk_status dmk_crowd_get_programs(dmk_crowd_t c, int num_layers, int32_t* out_cl
     if (out_programs && !c->d_program) return fail(ctx, DMK_ERR_INVALID, "the crowd has no pose programs");
     if (bind(ctx)) return DMK_ERR_CUDA;
     const size_t n = static_cast<size_t>(c->n), ln = static_cast<size_t>(num_layers) * n;
+    if (dmk_status st = join_layer_upload(c)) return st;
     if (out_clip) DMK_CUDA(ctx, cudaMemcpyAsync(out_clip, c->d_clip, ln * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_ratio) DMK_CUDA(ctx, cudaMemcpyAsync(out_ratio, c->d_ratio, ln * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_weight) DMK_CUDA(ctx, cudaMemcpyAsync(out_weight, c->d_weight, ln * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -599,6 +627,9 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
     // refused before anything is enqueued: a third outstanding read-back has no slot to land in
     if ((flags & DMK_STEP_CULL) && (flags & DMK_STEP_READBACK_VISIBILITY) && c->vis_pending == 2)
         return fail(ctx, DMK_ERR_INVALID, "two visibility read-backs are already outstanding: collect one first");
+    if (flags & (DMK_STEP_ANIMATOR | DMK_STEP_POSE | DMK_STEP_ADVANCE)) {
+        if (dmk_status st = join_layer_upload(c)) return st;
+    }
     if (flags & DMK_STEP_ANIMATOR) {
         if (!c->animator_set) return fail(ctx, DMK_ERR_INVALID, "dmk_crowd_set_animator has not been called");
         if (flags & DMK_STEP_ADVANCE) return fail(ctx, DMK_ERR_UNSUPPORTED, "the device animators own the clip clocks: do not combine them with DMK_STEP_ADVANCE");
@@ -689,6 +720,9 @@ dmk_status dmk_crowd_step(dmk_crowd_t c, float dt, uint32_t flags) {
             }
         }
         ctx->launches += pose_launches;
+    }
+    if (flags & (DMK_STEP_ANIMATOR | DMK_STEP_POSE | DMK_STEP_ADVANCE)) {
+        if (dmk_status st = mark_layers_idle(c)) return st;   // the layer arrays may be overwritten by the next frame's upload from here on
     }
     if (flags & DMK_STEP_CULL) {
         if (!c->instances_set || !c->camera_set)

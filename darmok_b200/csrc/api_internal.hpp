@@ -163,6 +163,12 @@ struct dmk_crowd_s {
     };
     std::vector<ExtraSkin> extra_skins;
     int reserved_sms = 0;
+    // dmk_crowd_update_layers (the per-frame upload) copies on its own stream, behind the last step that read the layer arrays
+    // (layers_idle, recorded after the pose part of a step) and in front of the next one (upload_done): the copy runs under the
+    // skinning kernel of the frame before instead of in front of the pose kernels
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t layers_idle = nullptr, upload_done = nullptr;
+    bool layers_idle_recorded = false, upload_pending = false;
     int32_t* d_skin_next = nullptr;   // [skin_next_capacity] per-tile counters of the skinning kernel's dynamic character assignment
     int skin_next_capacity = 0;
     int skin_variant = 0;   // DMK_OPT_SKIN_PLANAR_OUTPUT
@@ -298,3 +304,19 @@ void drain_timers(dmk_context_t ctx) {
 }
 
 }  // namespace
+
+// The context's stream waits for a pending per-frame upload (dmk_crowd_update_layers) before anything touches the layer arrays.
+static inline dmk_status join_layer_upload(dmk_crowd_t c) {
+    if (c->upload_pending) {
+        DMK_CUDA(c->ctx, cudaStreamWaitEvent(c->ctx->stream, c->upload_done, 0));
+        c->upload_pending = false;
+    }
+    return DMK_OK;
+}
+// ... and tells the upload stream when the layer arrays are free again (after the kernels of a step that read or write them)
+static inline dmk_status mark_layers_idle(dmk_crowd_t c) {
+    if (!c->layers_idle) DMK_CUDA(c->ctx, cudaEventCreateWithFlags(&c->layers_idle, cudaEventDisableTiming));
+    DMK_CUDA(c->ctx, cudaEventRecord(c->layers_idle, c->ctx->stream));
+    c->layers_idle_recorded = true;
+    return DMK_OK;
+}

@@ -248,6 +248,7 @@ dmk_status dmk_crowd_get_ratios(dmk_crowd_t c, float* out_ratio, uint8_t* out_lo
     if (!c->layers_set) return fail(c->ctx, DMK_ERR_INVALID, "dmk_crowd_set_layers has not been called");
     if (bind(c->ctx)) return DMK_ERR_CUDA;
     const size_t ln = static_cast<size_t>(c->num_layers) * static_cast<size_t>(c->n);
+    if (dmk_status st = join_layer_upload(c)) return st;
     if (out_ratio) DMK_CUDA(c->ctx, cudaMemcpyAsync(out_ratio, c->d_ratio, ln * 4, cudaMemcpyDeviceToHost, c->ctx->stream));
     if (out_looped) DMK_CUDA(c->ctx, cudaMemcpyAsync(out_looped, c->d_looped, ln, cudaMemcpyDeviceToHost, c->ctx->stream));
     return finish_and_check(c);

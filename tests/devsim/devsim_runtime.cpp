@@ -533,6 +533,7 @@ cudaError_t cudaStreamCreate(cudaStream_t* s) {
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned int) { return cudaStreamCreate(s); }
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }   // (everything here completes at the call)
 
 cudaError_t cudaEventCreate(cudaEvent_t* e) {
     *e = reinterpret_cast<cudaEvent_t>(new EventImpl());

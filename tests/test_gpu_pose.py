@@ -450,3 +450,52 @@ def test_fused_and_two_kernel_pose_paths_are_bit_identical(rigs):
     for name, got in results.items():
         for what, x, y in zip(("palette", "models", "locals", "key indices", "skinned", "packed"), got, ref):
             assert np.array_equal(x, y), f"{name}: {what} differs from the fused path"
+
+
+@pytest.mark.gpu
+def test_per_frame_upload_overlaps_the_previous_frame_without_touching_it():
+    """dmk_crowd_update_layers copies on the crowd's own upload stream: behind the pose kernels of the frame before (which read the
+    layer arrays), under its skinning kernel, in front of the next pose step.  Eight frames with different layers are queued without
+    a single host synchronisation; the palette of every frame -- copied aside on the context's stream right behind its step -- must be
+    the one the same layers give with a synchronisation after every call."""
+    from tests import devmem
+    if devmem.DEVSIM:
+        pytest.skip("stream ordering: nothing to see on the simulator (every call completes at once)")
+    import torch
+    from darmok_b200 import capi
+    a = common.default_assets(num_vertices=3000)
+    n, frames = 30_000, 8
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx = capi.Context(0, stream.cuda_stream)
+        skel = capi.Skeleton(ctx, a.skel.archive)
+        clip_objs = [capi.Clip(ctx, c.archive) for c in a.clips]
+        clips = capi.ClipSet(ctx, skel, clip_objs)
+        arm = capi.Armature(ctx, skel, a.arm.names, a.arm.inv_bind)
+        mesh = capi.Mesh(ctx, a.mesh.pos, a.mesh.nrm, a.mesh.tan, a.mesh.indices, a.mesh.weights, arm.palette_size)
+        crowd = capi.Crowd(ctx, skel, clips, arm, mesh, n, 2)
+        try:
+            layers = [synth.make_crowd(n, 2, len(a.clips), seed=100 + k) for k in range(frames)]
+            crowd.set_layers(layers[0].clip, layers[0].ratio, layers[0].weight, layers[0].speed, threshold=FLT_MIN)
+            ps = arm.palette_size
+            view = torch.as_tensor(devmem._Dev(crowd.palette_dev(), (n, ps, 16), "<f4"), device=torch.device("cuda", 0))
+            flags = capi.STEP_POSE | capi.STEP_SKIN      # the skinning kernel is what the next frame's upload runs under
+            want = []
+            for k in range(frames):                      # reference: one frame at a time
+                crowd.update_layers(layers[k].clip, layers[k].ratio, layers[k].weight)
+                crowd.step(0.0, flags)
+                ctx.sync()
+                want.append(view.clone())
+            torch.cuda.synchronize()
+            got = [torch.empty_like(view) for _ in range(frames)]
+            for k in range(frames):                      # pipelined: nothing waits
+                crowd.update_layers(layers[k].clip, layers[k].ratio, layers[k].weight)
+                crowd.step(0.0, flags)
+                got[k].copy_(view, non_blocking=True)    # torch's current stream is the context's
+            torch.cuda.synchronize()
+            for k in range(frames):
+                assert torch.equal(got[k], want[k]), f"frame {k}: the palettes differ from the synchronous run"
+            assert not torch.equal(want[0], want[1])
+        finally:
+            for o in (crowd, mesh, arm, clips, *clip_objs, skel, ctx):
+                o.close()
