@@ -459,7 +459,14 @@ def run_gpu(args):
                         "min": per[0], "max": per[-1], "frames": len(per)}
         except Exception as exc:   # the distribution is an extra: it never costs the line
             frame_ms = {"error": str(exc)[:200]}
+        by_rank = None
         if world > 1:
+            # max over ranks for the value; every rank's own time and SM clock next to it (a board under another power limit shows here)
+            mine = torch.tensor([elapsed_ms / args.steps, float(clocks.get("sm_mhz") or 0.0), 1.0 if clocks.get("reasons") else 0.0], dtype=torch.float64, device=dev)
+            everyone = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(everyone, mine)
+            by_rank = {"ms_per_step": [round(float(x[0]), 4) for x in everyone], "sm_mhz": [float(x[1]) for x in everyone],
+                       "throttle_reasons_seen": [bool(x[2] > 0) for x in everyone]}
             t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             elapsed_ms = float(t.item())
@@ -683,6 +690,7 @@ def run_gpu(args):
         "sustained": sustained,
     }
     if world > 1:
+        line["by_rank"] = by_rank
         line["gather_verified"] = gather_verified
         line["gather_capacity_characters"] = int(cap)
     emit(line)
