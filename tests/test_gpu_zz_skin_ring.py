@@ -38,3 +38,13 @@ def test_bulk_store_output_path_matches_the_oracle():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "skin_ring_check.py"), "--quick"], capture_output=True, text=True, timeout=300, env=env)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "cases match the oracle" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_static_split_of_the_characters_matches_the_oracle():
+    """DMK_SKIN_STATIC_SPLIT=1: every block takes a fixed share of the characters (the schedule before the per-tile counters; kept as
+    the A/B side of profiles/r02_skin_dynamic_assignment.txt); same checks."""
+    env = dict(os.environ, DMK_SKIN_STATIC_SPLIT="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "skin_ring_check.py"), "--quick"], capture_output=True, text=True, timeout=300, env=env)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "cases match the oracle" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
