@@ -248,7 +248,10 @@ enum { DMK_GROUP_BLEND = 0, DMK_GROUP_PASSTHROUGH = 1, DMK_GROUP_ZERO = 2 };
 enum { DMK_TOP_GROUP0 = 0, DMK_TOP_TRANSITION = 1, DMK_TOP_REST_POSE = 2, DMK_TOP_SKIP = 3 };
 DMK_API dmk_status dmk_crowd_set_programs(dmk_crowd_t crowd, int num_layers, const int32_t* clip, const float* ratio,
                                           const float* weight, const dmk_pose_program* programs);
-/* per-frame variant for a host-side state machine: pinned staging + async copy of clip/ratio/weight only */
+/* per-frame variant for a host-side state machine: pinned staging + async copy of clip/ratio/weight only.  The caller's arrays may
+ * be reused as soon as the call returns.  The copy runs on a stream of the crowd's own: behind the last step that read the layer
+ * arrays (i.e. under the skinning kernel of the frame before, not behind it) and in front of the next dmk_crowd_step, which waits for
+ * it -- the order of results is the order of the calls, as if everything were on the context's stream. */
 DMK_API dmk_status dmk_crowd_update_layers(dmk_crowd_t crowd, int num_layers, const int32_t* clip, const float* ratio,
                                            const float* weight);
 
