@@ -118,19 +118,47 @@ dmk_status dmk_skeleton_load_ozz(dmk_context_t ctx, const void* bytes, size_t si
         depth[j] = skel->data.parents[j] < 0 ? 0 : depth[skel->data.parents[j]] + 1;
         max_depth = std::max(max_depth, depth[j]);
     }
+    // Which 8 joints of a depth share a round is free: lane (joint j, column c) reads and writes shared memory at 13 j + 3 c + r, so two
+    // joints of a round collide in a bank iff 13 (j - j') = 3 (c' - c) (mod 32), i.e. j - j' in {0, 2, 13, 15, 17, 19, 30} (mod 32);
+    // their parents' matrices (13 p + e) collide iff p = p' (mod 32) for different parents.  Greedy: rounds without such pairs first.
+    auto clash = [&](int a, int b) {
+        const int d = ((a - b) % 32 + 32) % 32;
+        if (d == 0 || d == 2 || d == 13 || d == 15 || d == 17 || d == 19 || d == 30) return true;
+        const int pa = skel->data.parents[a], pb = skel->data.parents[b];
+        return pa >= 0 && pb >= 0 && pa != pb && pa % 32 == pb % 32;
+    };
     std::vector<uint16_t> sched;
     for (int d = 0; d <= max_depth && J > 0; ++d) {
-        size_t in_round = 0;
-        for (int j = 0; j < J; ++j) {
-            if (depth[j] != d) continue;
-            for (int c = 0; c < 4; ++c) {
-                sched.push_back(static_cast<uint16_t>(j | (c << 12)));
+        std::vector<int> todo;
+        for (int j = 0; j < J; ++j)
+            if (depth[j] == d) todo.push_back(j);
+        while (!todo.empty()) {
+            std::vector<int> round, rest;
+            for (int j : todo) {
+                bool ok = round.size() < 8;
+                for (size_t i = 0; ok && i < round.size(); ++i) ok = !clash(j, round[i]);
+                (ok ? round : rest).push_back(j);
+            }
+            // joints that clash with everything chosen so far still have to run: when a whole round's worth is left over, or at the
+            // end of the depth, they fill the round up (as many rounds as before: ceil(joints of the depth / 8))
+            const size_t rounds_left = (rest.size() + round.size() + 7) / 8;
+            if (round.size() < 8 && rounds_left * 8 - 8 < rest.size()) {
+                while (round.size() < 8 && !rest.empty()) {
+                    round.push_back(rest.front());
+                    rest.erase(rest.begin());
+                }
+            }
+            size_t in_round = 0;
+            for (int j : round)
+                for (int c = 0; c < 4; ++c) {
+                    sched.push_back(static_cast<uint16_t>(j | (c << 12)));
+                    ++in_round;
+                }
+            while (in_round % 32) {
+                sched.push_back(kIdleTask);
                 ++in_round;
             }
-        }
-        while (in_round % 32) {
-            sched.push_back(kIdleTask);
-            ++in_round;
+            todo.swap(rest);
         }
     }
     skel->rounds = static_cast<int>(sched.size() / 32);
@@ -276,8 +304,38 @@ dmk_status dmk_armature_create(dmk_context_t ctx, dmk_skeleton_t skel, const cha
             for (int r = 0; r < 3; ++r) ib[static_cast<size_t>(k) * 12 + c * 3 + r] = m[c * 4 + r];
         arm->remap.push_back(joint_names[k] ? dmk_skeleton_find_joint(skel, joint_names[k]) : -1);
     }
-    DMK_CUDA(ctx, upload(ctx, &arm->d_remap, arm->remap));
-    DMK_CUDA(ctx, upload(ctx, &arm->d_inv_bind, ib));
+    // Processing order of the palette pass (ArmatureDev): groups of 32 armature joints whose skeleton joints differ mod 32, as far as the
+    // armature allows -- a warp reads 32 model matrices at once, 13 floats apart per joint, and equal residues share a bank.
+    std::vector<int> order;
+    {
+        std::vector<char> taken(static_cast<size_t>(num_joints), 0);
+        int left = num_joints;
+        while (left > 0) {
+            bool used[32] = {};
+            int in_group = 0;
+            for (int pass = 0; pass < 2 && in_group < 32; ++pass)            // pass 0: distinct residues only; pass 1: fill up
+                for (int k = 0; k < num_joints && in_group < 32; ++k) {
+                    if (taken[static_cast<size_t>(k)]) continue;
+                    const int jm = arm->remap[static_cast<size_t>(k)];
+                    const int res = jm < 0 ? -1 : jm % 32;                   // unknown names read the identity: no bank of the model array
+                    if (pass == 0 && res >= 0 && used[res]) continue;
+                    if (res >= 0) used[res] = true;
+                    taken[static_cast<size_t>(k)] = 1;
+                    order.push_back(k);
+                    ++in_group;
+                    --left;
+                }
+        }
+    }
+    std::vector<int32_t> remap_ordered(static_cast<size_t>(num_joints));
+    std::vector<float> ib_ordered(ib.size());
+    for (int i = 0; i < num_joints; ++i) {
+        const int k = order[static_cast<size_t>(i)];
+        remap_ordered[static_cast<size_t>(i)] = (arm->remap[static_cast<size_t>(k)] & 0xffff) | (k << 16);
+        std::copy(ib.begin() + static_cast<long>(k) * 12, ib.begin() + static_cast<long>(k) * 12 + 12, ib_ordered.begin() + static_cast<long>(i) * 12);
+    }
+    DMK_CUDA(ctx, upload(ctx, &arm->d_remap, remap_ordered));
+    DMK_CUDA(ctx, upload(ctx, &arm->d_inv_bind, ib_ordered));
     *out = arm.release();
     return DMK_OK;
 }

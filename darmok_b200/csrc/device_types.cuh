@@ -58,8 +58,10 @@ struct SkeletonDev {
 };
 
 struct ArmatureDev {
-    const int32_t* remap;     // [K] skeleton joint of armature joint k, -1 = unknown name
-    const float* inv_bind;    // [K][12] affine 3x4, column-major columns of 3 (c0 c1 c2 c3)
+    // The armature joints in the PROCESSING ORDER the host chose (dmk_armature_create): entry i is armature joint order[i], and the 32
+    // entries a warp handles together name skeleton joints that differ mod 32 (their model matrices sit in different shared-memory banks)
+    const int32_t* remap;     // [K] (skeleton joint & 0xffff, 0xffff = unknown name) | (armature joint order[i] << 16)
+    const float* inv_bind;    // [K][12] affine 3x4 of armature joint order[i], column-major columns of 3 (c0 c1 c2 c3)
     int num_joints;           // K
 };
 

@@ -549,7 +549,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) model_kernel(const PosePa
                 if (pal) { st_v8(pal, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(pal + 8, 0, 0, 1, 0, 0, 0, 0, 1); }
                 if (p34) { st_v8(p34, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(p34 + 8, 0, 0, 1, 0, 0, 0, 0, 0); }
             }
-            for (int k = lane; k < K; k += 32) palette_slot(s_remap[k], s_mod, s_inv_bind + (size_t)k * kMS, pal, p34, k);
+            // armature joints in the ORDER the host chose (ArmatureDev): the 32 lanes of a pass read model matrices of joints that differ
+            // mod 32, i.e. from 32 different banks (stride kMS is odd); the entry carries the joint and the palette slot it fills
+            for (int i = lane; i < K; i += 32) {
+                const int32_t e = s_remap[i];
+                palette_slot((int)(int16_t)(e & 0xffff), s_mod, s_inv_bind + (size_t)i * kMS, pal, p34, e >> 16);
+            }
         }
         __syncwarp();  // the matrix arrays are reused by the next character
     }
@@ -640,7 +645,8 @@ __global__ void __launch_bounds__(kFusedMaxThreads, DMK_FUSED_MIN_BLOCKS) pose_f
                     if (pal) { st_v8(pal, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(pal + 8, 0, 0, 1, 0, 0, 0, 0, 1); }
                     if (p34) { st_v8(p34, 1, 0, 0, 0, 0, 1, 0, 0); st_v8(p34 + 8, 0, 0, 1, 0, 0, 0, 0, 0); }
                 } else {
-                    palette_slot(s_remap[k], s_char0 + (size_t)s3 * per_char + (size_t)P * kMS, s_inv_bind + (size_t)k * kMS, pal, p34, k);
+                    const int32_t e = s_remap[k];   // (entry k of the host's processing order: joint | palette slot << 16)
+                    palette_slot((int)(int16_t)(e & 0xffff), s_char0 + (size_t)s3 * per_char + (size_t)P * kMS, s_inv_bind + (size_t)k * kMS, pal, p34, e >> 16);
                 }
             }
         }
